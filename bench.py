@@ -1,0 +1,421 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the LJ / CuH2 hot path in atom-force evaluations per second.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--workload cuh2_batch|lj_fluid_1m|cuh2_slab_256k] [--configs C]
+
+Headline workload (BASELINE.json configs[4]): a batch of C = 65 536 perturbed copies of the
+218-atom Cu slab + H2 (NEB / dimer images) PER GPU, evaluated by the CuH2 EAM in one engine call.
+A "step" is one pass of the hot path over the batch.  Ranks are independent (no collective on the
+data path): weak scaling, value = total atoms evaluated by all ranks / max-over-ranks time.
+
+  value     device-resident: inputs already in HBM, CUDA events on the launching stream
+  e2e       the same metric through the public host-buffer call (pinned host arrays in, host
+            arrays out), H2D / D2H copies inside the timed region
+  roofline  algorithmic FP64 work of the dominant kernel / measured DFMA peak (measured live
+            here: MEASURED_PEAKS.json carries no FP64 figure), plus the HBM fraction
+  cpu_baseline / --impl reference: the reference CPU path (its own vesin neighbor search from
+            oracle/_ref feeding the restated Fortran passes; one process per host core because
+            the reference potential is ProcessSerial) on a bounded sample of the same workload
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "atom-force evals/sec (atoms x configs / s)"
+UNIT = "atom-evals/s"
+
+# algorithmic work per atom-eval (exp counted as 30 flops, FMA as 2)
+FLOPS_PER_ATOM = {"cuh2_batch": 23000.0, "lj_fluid_1m": 8503.0, "cuh2_slab_256k": 41200.0}
+BYTES_PER_ATOM = {"cuh2_batch": 76.0, "lj_fluid_1m": 52.0, "cuh2_slab_256k": 76.0}
+
+
+# ------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """nvidia-smi sampling during the timed region (B200_PROFILING.md clocks line)."""
+
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                 "-i", str(self.gpu), "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                smax.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": float(max(smax)) if smax else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# --------------------------------------------------------------------------- distributed glue
+def dist_setup(n_gpus):
+    import torch
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local))
+    else:
+        torch.cuda.set_device(0)
+    return world, rank, local
+
+
+def barrier(world):
+    import torch
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+    torch.cuda.synchronize()
+
+
+def max_over_ranks(x, world):
+    if world == 1:
+        return x
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([x], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def sum_over_ranks(x, world):
+    if world == 1:
+        return x
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([x], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return float(t.item())
+
+
+# ------------------------------------------------------------------------------ CPU reference
+def _cpu_worker(args):
+    """One process = one ProcessSerial reference potential looping over its slice."""
+    seed, n_configs, budget_s = args
+    from oracle import pyoracle as po
+    from rgpot_b200 import workloads
+    offsets, pos, Z, boxes = workloads.cuh2_batch(n_configs, seed=seed)
+    use_ref = po.ref_available()
+    done = 0
+    t0 = time.perf_counter()
+    for s in range(n_configs):
+        a, b = int(offsets[s]), int(offsets[s + 1])
+        po.cuh2_force(pos[a:b], Z[a:b], boxes[s].reshape(3, 3), use_ref=use_ref)
+        done += b - a
+        if time.perf_counter() - t0 > budget_s:
+            break
+    return done, time.perf_counter() - t0
+
+
+def cpu_reference_rate(budget_s=12.0, procs=None, configs_per_proc=4000):
+    """atom-evals/s of the reference CPU path on this host: P processes, bounded sample."""
+    import multiprocessing as mp
+    from oracle import pyoracle as po
+    procs = procs or os.cpu_count() or 1
+    ctx = mp.get_context("fork")
+    t0 = time.perf_counter()
+    with ctx.Pool(procs) as pool:
+        res = pool.map(_cpu_worker, [(9000 + p, configs_per_proc, budget_s) for p in range(procs)])
+    wall = time.perf_counter() - t0
+    atoms = sum(r[0] for r in res)
+    busy = max(r[1] for r in res)
+    kind = "reference" if po.ref_available() else "port"
+    sample = (f"{atoms // 218} perturbed 218-atom CuH2 configs over {procs} processes, {busy:.1f} s each "
+              f"({'vendored vesin from oracle/_ref + ' if kind == 'reference' else ''}"
+              f"C restatement of rgpot_cuh2.f90; the Fortran kernel cannot be built here)")
+    return {"value": atoms / busy, "unit": UNIT, "cores": procs, "kind": kind, "sample": sample,
+            "wall_s": wall}
+
+
+# ------------------------------------------------------------------------------- our workloads
+def run_cuh2_batch(args, world, rank, local):
+    import torch
+
+    import rgpot_b200
+    from rgpot_b200 import workloads
+
+    n_cfg = args.configs
+    offsets, pos, Z, boxes = workloads.cuh2_batch(n_cfg, seed=1000 + rank)
+    n_atoms = int(offsets[-1])
+    pot = rgpot_b200.CuH2Pot(device=local)
+
+    dev = torch.device("cuda", local)
+    d_pos = torch.from_numpy(pos).to(dev)
+    d_Z = torch.from_numpy(Z).to(dev)
+    d_boxes = torch.from_numpy(np.ascontiguousarray(boxes)).to(dev)
+    d_F = torch.empty((n_atoms, 3), dtype=torch.float64, device=dev)
+    d_E = torch.empty(n_cfg, dtype=torch.float64, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def step():
+        pot.force_batch_device(offsets, d_pos, d_Z, d_boxes, d_F, d_E, stream)
+
+    for _ in range(args.warmup):
+        step()
+    st = pot.sync_status()
+    assert st == 0, f"engine status {st}"
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = pot.launch_count()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier(world)
+    t0.record()
+    for _ in range(args.steps):
+        step()
+    t1.record()
+    torch.cuda.synchronize()
+    barrier(world)
+    dev_ms = t0.elapsed_time(t1)
+    launches = pot.launch_count() - launches0
+    assert pot.sync_status() == 0
+    checksum = float(d_E.sum().item())
+
+    # ---- end to end through the public host-buffer call, pinned host memory
+    h_pos = rgpot_b200.pinned_empty((n_atoms, 3))
+    h_Z = rgpot_b200.pinned_empty((n_atoms,), np.int32)
+    h_boxes = rgpot_b200.pinned_empty((n_cfg, 9))
+    h_F = rgpot_b200.pinned_empty((n_atoms, 3))
+    h_E = rgpot_b200.pinned_empty((n_cfg,))
+    h_pos[:] = pos
+    h_Z[:] = Z
+    h_boxes[:] = boxes
+    e2e_steps = max(1, min(args.steps, 5))
+    pot.forceBatchPacked(offsets, h_pos, h_Z, h_boxes, h_F, h_E)  # warm-up (allocations)
+    barrier(world)
+    w0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        pot.forceBatchPacked(offsets, h_pos, h_Z, h_boxes, h_F, h_E)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - w0
+    barrier(world)
+    assert abs(float(h_E.sum()) - checksum) <= 1e-9 * abs(checksum)
+    clocks = sampler.stop() if rank == 0 else None
+
+    dev_ms = max_over_ranks(dev_ms, world)
+    e2e_s = max_over_ranks(e2e_s, world)
+    total_atoms = sum_over_ranks(float(n_atoms), world)
+    value = total_atoms * args.steps / (dev_ms * 1e-3)
+    e2e_value = total_atoms * e2e_steps / e2e_s
+    h2d = pos.nbytes + Z.nbytes + boxes.nbytes + offsets.nbytes
+    d2h = h_F.nbytes + h_E.nbytes
+
+    # roofline of the dominant kernel (k_eam_small: the whole step is one launch of it)
+    kernel_s = dev_ms * 1e-3 / args.steps
+    fp64_peak = rgpot_b200.measure_fp64_tflops(local) if rank == 0 else 0.0
+    achieved_tf = FLOPS_PER_ATOM["cuh2_batch"] * n_atoms / kernel_s / 1e12
+    peaks = load_peaks()
+    hbm_gbs = BYTES_PER_ATOM["cuh2_batch"] * n_atoms / kernel_s / 1e9
+    roofline = {"bound": "fp64", "kernel": "k_eam_small", "achieved": achieved_tf, "peak": fp64_peak,
+                "unit": "TFLOP/s", "frac": achieved_tf / fp64_peak if fp64_peak else None,
+                "peak_source": "DFMA microbenchmark measured in this run (MEASURED_PEAKS.json has no FP64 entry)",
+                "flops_per_atom_eval": FLOPS_PER_ATOM["cuh2_batch"],
+                "traffic": None,
+                "hbm": {"achieved": hbm_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                        "frac": hbm_gbs / peaks["hbm_gbs"], "peak_source": peaks["source"]}}
+    return {
+        "value": value, "ms_per_step": dev_ms / args.steps, "gpu_launches": launches,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+                "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
+                "api": "CuH2Pot.forceBatchPacked -> rgpot_b200_force_batch_packed (pinned host buffers)"},
+        "roofline": roofline, "clocks": clocks,
+        "config": {"workload": f"cuh2_batch: {n_cfg} perturbed 218-atom Cu slab + H2 configs per GPU "
+                               f"(BASELINE configs[4])",
+                   "configs_per_gpu": n_cfg, "atoms_per_config": 218, "global_configs": n_cfg * world,
+                   "parallelism": f"{world} independent rank(s), batch sharded, no collective",
+                   "l2": "inputs + outputs (0.7 GB per step) exceed the 126 MB L2"},
+    }
+
+
+def run_single_system(args, name, local):
+    """LJ 1M fluid / Cu slab 256k on one GPU: device-resident value + e2e."""
+    import torch
+
+    import rgpot_b200
+    from rgpot_b200 import workloads
+
+    if name == "lj_fluid_1m":
+        pos, Z, box = workloads.lj_fluid(args.lj_atoms)
+        pot = rgpot_b200.LJPot(rgpot_b200.LJConfig(1.0, 2.5, 1.0), device=local)
+        kernel = "k_lj_gather"
+    else:
+        pos, Z, box = workloads.cu_slab_triclinic(cells=args.slab_cells)
+        pot = rgpot_b200.CuH2Pot(device=local)
+        kernel = "k_eam_force"
+    n = len(pos)
+    dev = torch.device("cuda", local)
+    d_pos = torch.from_numpy(pos).to(dev)
+    d_Z = torch.from_numpy(Z).to(dev)
+    d_F = torch.empty((n, 3), dtype=torch.float64, device=dev)
+    d_E = torch.empty(1, dtype=torch.float64, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    steps = max(3, min(args.steps, 10))
+    for _ in range(3):
+        pot.force_device(d_pos, d_Z, box, d_F, d_E, stream)
+    l0 = pot.launch_count()
+    total_ms = 0.0
+    for _ in range(steps):
+        flush.zero_()  # 256 MB write: evicts the 126 MB L2 between timed iterations
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        pot.force_device(d_pos, d_Z, box, d_F, d_E, stream, sync=False)
+        t1.record()
+        torch.cuda.synchronize()
+        total_ms += t0.elapsed_time(t1)
+    assert pot.sync_status() == 0
+    launches = pot.launch_count() - l0
+    value = n * steps / (total_ms * 1e-3)
+    w0 = time.perf_counter()
+    for _ in range(3):
+        e, f, _ = pot(pos, Z, box)
+    e2e = n * 3 / (time.perf_counter() - w0)
+    assert abs(e - float(d_E.item())) <= 1e-12 * abs(e)
+    fp64_peak = rgpot_b200.measure_fp64_tflops(local)
+    tf = FLOPS_PER_ATOM[name] * value / 1e12
+    return {"workload": name, "n_atoms": n, "value": value, "unit": UNIT, "ms_per_step": total_ms / steps,
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(pos.nbytes + Z.nbytes),
+                    "d2h_bytes_per_step": int(pos.nbytes + 8)},
+            "gpu_launches": launches, "energy": e,
+            "roofline": {"bound": "fp64", "kernel": kernel, "achieved": tf, "peak": fp64_peak,
+                         "unit": "TFLOP/s", "frac": tf / fp64_peak if fp64_peak else None,
+                         "note": "whole step (cell build + force kernels) timed, flops of the path"},
+            "l2": "256 MB flush write between timed iterations"}
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            p = json.load(fh)
+        return {"hbm_gbs": p["hbm_gbs"], "source": "MEASURED_PEAKS.json (measured)"}
+    return {"hbm_gbs": 6650.0, "source": "B200_PROFILING.md fallback"}
+
+
+# ------------------------------------------------------------------------------------- main
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cuh2_batch",
+                    choices=["cuh2_batch", "lj_fluid_1m", "cuh2_slab_256k"])
+    ap.add_argument("--configs", type=int, default=65536, help="configurations per GPU")
+    ap.add_argument("--lj-atoms", type=int, default=1_000_000)
+    ap.add_argument("--slab-cells", type=int, default=40)
+    ap.add_argument("--no-extras", action="store_true", help="skip the LJ 1M / Cu 256k side lines")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    if args.impl == "reference":
+        rank = int(os.environ.get("RANK", "0"))
+        if rank != 0:
+            return
+        per_step = max(2.0, min(20.0, 120.0 / max(1, args.steps + min(args.warmup, 1))))
+        cpu_reference_rate(budget_s=1.0, configs_per_proc=50)  # warm-up
+        rates, walls = [], []
+        for _ in range(args.steps):
+            r = cpu_reference_rate(budget_s=per_step)
+            rates.append(r["value"])
+            walls.append(r["wall_s"])
+        value = float(np.mean(rates))
+        line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(np.mean(walls)) * 1e3,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic",
+                "config": {"workload": "cuh2_batch: perturbed 218-atom Cu slab + H2 configs (BASELINE configs[4]); "
+                                       "each step a bounded sample on all host cores"},
+                "cpu_baseline": {"value": value, "unit": UNIT, "cores": r["cores"], "kind": r["kind"],
+                                 "sample": r["sample"]},
+                "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return
+
+    # the CPU baseline runs first, in forked processes, before this process touches CUDA
+    cpu_base = None
+    if int(os.environ.get("WORLD_SIZE", "1")) == 1:
+        cpu_base = {k: v for k, v in cpu_reference_rate(args.cpu_seconds).items() if k != "wall_s"}
+    world, rank, local = dist_setup(args.gpus)
+    if args.workload == "cuh2_batch":
+        res = run_cuh2_batch(args, world, rank, local)
+    else:
+        r = run_single_system(args, args.workload, local)
+        res = {"value": r["value"], "ms_per_step": r["ms_per_step"], "gpu_launches": r["gpu_launches"],
+               "e2e": r["e2e"], "roofline": r["roofline"], "clocks": None,
+               "config": {"workload": args.workload, "n_atoms": r["n_atoms"], "l2": r["l2"]}}
+    if rank == 0:
+        line = {"metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": res["config"], "e2e": res["e2e"], "gpu_launches": res["gpu_launches"],
+                "roofline": res["roofline"], "clocks": res["clocks"]}
+        if world == 1:
+            line["cpu_baseline"] = cpu_base
+            if args.workload == "cuh2_batch" and not args.no_extras:
+                line["also"] = [run_single_system(args, "lj_fluid_1m", local),
+                                run_single_system(args, "cuh2_slab_256k", local)]
+        print(json.dumps(line))
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,156 @@
+/**
+ * @file rgpot_b200.h
+ * @brief C ABI of the B200 (sm_100a) CUDA engine for rgpot's LJ / LJCluster / CuH2 hot path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++ / torch types.  Host units are
+ * those of rgpot: positions and box in Angstrom, energies in eV, forces in eV/Angstrom;
+ * positions and forces are x/y/z interleaved, the box is nine doubles, row-major, one cell
+ * vector per row (reference: CppCore/rgpot/ForceStructs.hpp:20-36).
+ *
+ * Which reference interface each entry point replaces:
+ *
+ *  - rgpot_b200_abi_version / _create / _destroy / _force / _available follow the reference's
+ *    dlopen-engine ABI (CppCore/rgpot/XTBPot/xtb_c_abi.h:49-65,
+ *    CppCore/rgpot/MetatomicPot/metatomic_c_abi.h:45-61): opaque handle, 0 = success,
+ *    errbuf at create, `variance` may be NULL.  _force is what
+ *    `LJPot::forceImpl` (CppCore/rgpot/LennardJones/LJPot.cc:38-84),
+ *    `LJClusterPot::forceImpl` (LJClusterPot.cc:33-83) and `CuH2Pot::forceImpl`
+ *    (CppCore/rgpot/fortran/FortranPots.cc:78-90) compute.
+ *  - rgpot_b200_force_batch is the native implementation of
+ *    `Potential<D>::forceBatchImpl(const ForceBatch&)` (CppCore/rgpot/Potential.hpp:235-240,
+ *    ForceStructs.hpp:50-54); the reference only has the per-system default loop.
+ *  - rgpot_cuh2_force / rgpot_fortran_last_error are the exact symbols the reference's C++ face
+ *    binds for the Fortran kernel (FortranPots.cc:33-40, rgpot_cuh2_capi.f90:31-58,
+ *    rgpot_ferror.f90:41-56): link librgpot_b200.so instead of the Fortran objects and
+ *    `fortranpots::CuH2Pot` runs on the GPU unmodified.
+ *  - the *_device entry points take device pointers ("any device" in
+ *    rgpot-core/include/rgpot.h:78-88) and never touch host memory on the data path.
+ *
+ * Status codes (rgpot_cuh2.f90:404-429, rgpot_neighbors.f90:111-115):
+ *   0 success; 1 neighbor-search failure (singular box, non-finite coordinate) or size error;
+ *   2 an atomic number outside {29, 1} (CuH2 only); 3 two atoms occupy the same position
+ *   (CuH2 only); >= 100 CUDA / engine failure.  On any non-zero status the outputs are zeroed,
+ *   like the reference, and the message is available from rgpot_b200_last_error.
+ *
+ * There is no CPU fallback: every entry point fails with a CUDA status if no B200-class
+ * device is usable.
+ */
+#ifndef RGPOT_B200_H
+#define RGPOT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RGPOT_B200_API __attribute__((visibility("default")))
+#define RGPOT_B200_ABI_VERSION 1
+
+typedef struct RgpotB200Pot RgpotB200Pot;
+
+/** Potential selector; the names follow rgpot's PotType (CppCore/rgpot/pot_types.hpp:26-45). */
+enum {
+  RGPOT_B200_LJ = 0,         /**< PotType::LJ        -- periodic, orthorhombic nearest image */
+  RGPOT_B200_LJ_CLUSTER = 1, /**< PotType::LJCluster -- free boundaries                       */
+  RGPOT_B200_CUH2 = 2        /**< PotType::CuH2      -- Cu/H EAM, all images inside 6.1 A     */
+};
+
+typedef struct RgpotB200Config {
+  int kind;      /**< RGPOT_B200_LJ / _LJ_CLUSTER / _CUH2 */
+  int device;    /**< CUDA device ordinal; -1 keeps the calling thread's current device */
+  double u0;     /**< LJConfig::u0     (LJPot.hpp:30-34), default 1.0  */
+  double cutoff; /**< LJConfig::cutoff, default 15.0; ignored for CuH2 (fixed 6.1) */
+  double psi;    /**< LJConfig::psi,    default 1.0  */
+  /** 0: reference semantics (box diagonal only, one nearest image per pair, LJPot.cc:35).
+   *  1: opt-in general triclinic LJ: every periodic image with d2 < rc2 (vesin semantics);
+   *     no reference counterpart exists for this mode.                                      */
+  int lj_all_images;
+  int reserved[7];
+} RgpotB200Config;
+
+RGPOT_B200_API int rgpot_b200_abi_version(void);
+/** Number of usable CUDA devices of compute capability >= 10.0 (0 if none). */
+RGPOT_B200_API int rgpot_b200_available(void);
+/** Fill `cfg` with the reference defaults for `kind`. */
+RGPOT_B200_API void rgpot_b200_default_config(int kind, RgpotB200Config *cfg);
+
+RGPOT_B200_API RgpotB200Pot *rgpot_b200_create(const RgpotB200Config *cfg, char *errbuf,
+                                               size_t errlen);
+RGPOT_B200_API void rgpot_b200_destroy(RgpotB200Pot *pot);
+
+/** Energy + forces of one system from HOST buffers.  `forces` (3 * nAtoms) is overwritten. */
+RGPOT_B200_API int rgpot_b200_force(RgpotB200Pot *pot, long nAtoms, const double *positions,
+                                    const int *atomicNrs, double *forces, double *energy,
+                                    double *variance, const double *box);
+
+/** Many independent systems in one call, HOST buffers, parallel arrays like ForceBatch.
+ *  forces[i] must hold 3 * nAtoms[i] doubles; energies holds nSystems doubles.
+ *  `statuses` (may be NULL) receives one status per system; the return value is the first
+ *  non-zero status (0 if all succeeded).                                                    */
+RGPOT_B200_API int rgpot_b200_force_batch(RgpotB200Pot *pot, size_t nSystems,
+                                          const size_t *nAtoms, const double *const *positions,
+                                          const int *const *atomicNrs, const double *const *boxes,
+                                          double *const *forces, double *energies, int *statuses);
+
+/** Same batch with the systems stored back to back: system s owns atoms
+ *  [offsets[s], offsets[s+1]) of `positions` / `atomicNrs` / `forces` and boxes[9*s .. 9*s+8].
+ *  Buffers allocated with rgpot_b200_host_alloc are copied asynchronously.                  */
+RGPOT_B200_API int rgpot_b200_force_batch_packed(RgpotB200Pot *pot, size_t nSystems,
+                                                 const size_t *offsets, const double *positions,
+                                                 const int *atomicNrs, const double *boxes,
+                                                 double *forces, double *energies, int *statuses);
+
+/** Device-resident variants: every pointer except `box` (9 host doubles) and `offsets` (host
+ *  array of nSystems + 1 atom offsets) is a device pointer on the handle's device; work is
+ *  enqueued on `cuda_stream` (a cudaStream_t, NULL = the handle's own stream) and the call
+ *  returns without synchronising.  Status flags are checked by rgpot_b200_sync_status.      */
+RGPOT_B200_API int rgpot_b200_force_device(RgpotB200Pot *pot, long nAtoms, const double *d_positions,
+                                           const int *d_atomicNrs, double *d_forces,
+                                           double *d_energy, const double *box, void *cuda_stream);
+RGPOT_B200_API int rgpot_b200_force_batch_device(RgpotB200Pot *pot, size_t nSystems,
+                                                 const size_t *offsets, const double *d_positions,
+                                                 const int *d_atomicNrs, const double *d_boxes,
+                                                 double *d_forces, double *d_energies,
+                                                 void *cuda_stream);
+/** Wait for the last *_device call and return its status (0 / 1 / 2 / 3 / >= 100). */
+RGPOT_B200_API int rgpot_b200_sync_status(RgpotB200Pot *pot);
+
+/** Neighbor table the engine acts on, for pair-set parity checks and list consumers:
+ *  writes up to `cap` entries (i, j) into pairs[2k], pairs[2k+1] and the periodic shift S into
+ *  shifts[3k..3k+2] (vec = r_j - r_i + S.H), in unspecified order; *n_out receives the total
+ *  count.  CuH2 / all-image mode: directed entries, self images dropped
+ *  (rgpot_neighbors.f90:126-134).  LJ reference mode: unordered pairs i < j, shifts zero.
+ *  `path`: 0 = automatic, 1 = force the cell-list kernels, 2 = force the all-pairs kernels.  */
+RGPOT_B200_API int rgpot_b200_neighbors(RgpotB200Pot *pot, long nAtoms, const double *positions,
+                                        const int *atomicNrs, const double *box, int path,
+                                        long cap, int32_t *pairs, int32_t *shifts, long *n_out);
+
+/** Message of the last failure on this handle (rgpot_ferror.f90:41-56 semantics, but per
+ *  handle): copies at most buffer_len - 1 bytes, NUL-terminates, returns the length. */
+RGPOT_B200_API int rgpot_b200_last_error(RgpotB200Pot *pot, char *buffer, int buffer_len);
+
+/** Kernels this handle has launched since creation (evidence for bench.py's gpu_launches). */
+RGPOT_B200_API long rgpot_b200_launch_count(RgpotB200Pot *pot);
+/** Tuning / test hooks: force a code path for subsequent calls.
+ *  key "path": 0 auto, 1 cell-list, 2 all-pairs.                                            */
+RGPOT_B200_API int rgpot_b200_set_option(RgpotB200Pot *pot, const char *key, long value);
+
+/** Page-locked host memory for the batch entry points. */
+RGPOT_B200_API void *rgpot_b200_host_alloc(size_t bytes);
+RGPOT_B200_API void rgpot_b200_host_free(void *ptr);
+
+/** Sustained FP64 FMA rate of the device (TFLOP/s): the measured roofline denominator. */
+RGPOT_B200_API double rgpot_b200_measure_fp64_tflops(int device, int iters);
+
+/* ---- exact drop-in for the reference's Fortran entry (FortranPots.cc:33-40) ------------ */
+RGPOT_B200_API int rgpot_cuh2_force(int32_t natoms, const double *positions,
+                                    const int32_t *atomic_numbers, const double *cell,
+                                    double *forces, double *energy);
+RGPOT_B200_API int rgpot_fortran_last_error(char *buffer, int buffer_len);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RGPOT_B200_H */

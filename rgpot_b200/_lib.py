@@ -1,0 +1,84 @@
+"""ctypes binding of include/rgpot_b200.h (the engine's C ABI).
+
+Loading never falls back to anything: if librgpot_b200.so is missing the import of the
+binding raises, and if no B200 is usable every call returns a CUDA status which the host
+layer turns into an exception.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "librgpot_b200.so")
+CSRC = os.path.join(HERE, "csrc")
+
+KIND_LJ, KIND_LJ_CLUSTER, KIND_CUH2 = 0, 1, 2
+
+
+class Config(C.Structure):
+    """RgpotB200Config"""
+
+    _fields_ = [
+        ("kind", C.c_int),
+        ("device", C.c_int),
+        ("u0", C.c_double),
+        ("cutoff", C.c_double),
+        ("psi", C.c_double),
+        ("lj_all_images", C.c_int),
+        ("reserved", C.c_int * 7),
+    ]
+
+
+# every symbol include/rgpot_b200.h declares: (name, restype, argtypes)
+_vp, _sz, _i, _l, _d = C.c_void_p, C.c_size_t, C.c_int, C.c_long, C.c_double
+SYMBOLS = [
+    ("rgpot_b200_abi_version", _i, []),
+    ("rgpot_b200_available", _i, []),
+    ("rgpot_b200_default_config", None, [_i, C.POINTER(Config)]),
+    ("rgpot_b200_create", _vp, [C.POINTER(Config), C.c_char_p, _sz]),
+    ("rgpot_b200_destroy", None, [_vp]),
+    ("rgpot_b200_force", _i, [_vp, _l, _vp, _vp, _vp, C.POINTER(_d), C.POINTER(_d), _vp]),
+    ("rgpot_b200_force_batch", _i, [_vp, _sz, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    ("rgpot_b200_force_batch_packed", _i, [_vp, _sz, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    ("rgpot_b200_force_device", _i, [_vp, _l, _vp, _vp, _vp, _vp, _vp, _vp]),
+    ("rgpot_b200_force_batch_device", _i, [_vp, _sz, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    ("rgpot_b200_sync_status", _i, [_vp]),
+    ("rgpot_b200_neighbors", _i, [_vp, _l, _vp, _vp, _vp, _i, _l, _vp, _vp, C.POINTER(_l)]),
+    ("rgpot_b200_last_error", _i, [_vp, C.c_char_p, _i]),
+    ("rgpot_b200_launch_count", _l, [_vp]),
+    ("rgpot_b200_set_option", _i, [_vp, C.c_char_p, _l]),
+    ("rgpot_b200_host_alloc", _vp, [_sz]),
+    ("rgpot_b200_host_free", None, [_vp]),
+    ("rgpot_b200_measure_fp64_tflops", _d, [_i, _i]),
+    ("rgpot_cuh2_force", _i, [C.c_int32, _vp, _vp, _vp, _vp, C.POINTER(_d)]),
+    ("rgpot_fortran_last_error", _i, [C.c_char_p, _i]),
+]
+
+
+def build(verbose: bool = False) -> str:
+    """Compile the CUDA engine for sm_100a (nvcc cross-compiles without a GPU)."""
+    subprocess.run(["make", "-s", "-C", CSRC], check=True,
+                   stdout=None if verbose else subprocess.DEVNULL)
+    return LIB_PATH
+
+
+_LIB = None
+
+
+def lib():
+    """The loaded engine.  Raises if the shared library is absent -- there is no other path."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} is missing: build it with `make -C rgpot_b200/csrc` "
+                "(or __graft_entry__.build()); rgpot_b200 has no CPU fallback")
+        handle = C.CDLL(LIB_PATH)
+        for name, restype, argtypes in SYMBOLS:
+            fn = getattr(handle, name)  # AttributeError if the ABI lost a symbol
+            fn.restype = restype
+            fn.argtypes = argtypes
+        _LIB = handle
+    return _LIB

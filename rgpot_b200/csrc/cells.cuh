@@ -1,0 +1,271 @@
+// cells.cuh -- GPU cell-list build: bin -> count -> scan -> scatter -> per-cell order.
+//
+// Replaces the neighbor search under the reference path:
+//   * vesin CellList::add_point / cells_ buckets  (third_party/vesin/vesin-single-build.cpp:1421-1442)
+//   * the O(N^2) scan of CppCore/rgpot/nlist/vesin_visit.hpp:82-110 (LJ)
+// The result is a cell-sorted copy of the atoms (double4: x, y, z, packed meta) plus the CSR
+// cell starts.  Atoms inside a cell are ordered by original index, so every later summation
+// has a fixed order and results are bit-reproducible run to run (no floating-point atomics).
+#pragma once
+
+#include <limits.h>
+
+#include "common.cuh"
+
+namespace rb {
+
+// ---- bounding box of free (non-periodic) directions ---------------------------------------
+// order-preserving map double -> unsigned 64 so min/max can use integer atomics
+RB_D unsigned long long dkey(double v) {
+  unsigned long long u = (unsigned long long)__double_as_longlong(v);
+  return (u & 0x8000000000000000ull) ? ~u : (u | 0x8000000000000000ull);
+}
+RB_HD double dkey_inv(unsigned long long k) {
+  unsigned long long u = (k & 0x8000000000000000ull) ? (k & 0x7fffffffffffffffull) : ~k;
+#ifdef __CUDA_ARCH__
+  return __longlong_as_double((long long)u);
+#else
+  double d;
+  memcpy(&d, &u, sizeof d);
+  return d;
+#endif
+}
+
+// mm[0..2] = min keys, mm[3..5] = max keys (pre-initialised to ~0 / 0)
+__global__ void k_bbox(const double* __restrict__ pos, int n, unsigned long long* __restrict__ mm) {
+  unsigned long long lo[3] = {~0ull, ~0ull, ~0ull}, hi[3] = {0ull, 0ull, 0ull};
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const unsigned long long key = dkey(pos[3 * (size_t)i + k]);
+      lo[k] = key < lo[k] ? key : lo[k];
+      hi[k] = key > hi[k] ? key : hi[k];
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    for (int off = 16; off > 0; off >>= 1) {
+      const unsigned long long a = __shfl_xor_sync(0xffffffffu, lo[k], off);
+      const unsigned long long b = __shfl_xor_sync(0xffffffffu, hi[k], off);
+      lo[k] = a < lo[k] ? a : lo[k];
+      hi[k] = b > hi[k] ? b : hi[k];
+    }
+    if ((threadIdx.x & 31) == 0) {
+      atomicMin(&mm[k], lo[k]);
+      atomicMax(&mm[3 + k], hi[k]);
+    }
+  }
+}
+
+// ---- binning ----------------------------------------------------------------------------
+// cell coordinate + periodic wrap count of one position (vesin add_point :1421-1442; the
+// bounding-box form of BoundingBox::cartesian_to_fractional :244-260 for free directions).
+RB_D void locate(const Box& box, const Grid& g, double x, double y, double z, int c[3], int s[3]) {
+  const double p[3] = {x, y, z};
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    double f;
+    if (box.periodic[k]) {
+      f = p[0] * box.Hinv[k] + p[1] * box.Hinv[3 + k] + p[2] * box.Hinv[6 + k];
+    } else {
+      f = (p[k] - box.lo[k]) / box.ext[k];
+    }
+    // clamp before the int conversion so absurd coordinates cannot overflow
+    double cf = floor(f * (double)g.nc[k]);
+    cf = fmin(fmax(cf, -2.0e9), 2.0e9);
+    int ci = (int)cf;
+    if (box.periodic[k]) {
+      divmod_i(ci, g.nc[k], s[k], c[k]);
+    } else {
+      c[k] = min(max(ci, 0), g.nc[k] - 1);
+      s[k] = 0;
+    }
+  }
+}
+
+__global__ void k_bin(const double* __restrict__ pos, int n, Box box, Grid g,
+                      int* __restrict__ cell_of, int* __restrict__ rank, int* __restrict__ ashift,
+                      int* __restrict__ counts, Status* __restrict__ st) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double x = pos[3 * (size_t)i], y = pos[3 * (size_t)i + 1], z = pos[3 * (size_t)i + 2];
+  if (!(isfinite(x) && isfinite(y) && isfinite(z))) {
+    atomicOr(&st->flags, kFlagNonFinite);
+    atomicMin(&st->first_bad_atom, i);
+    cell_of[i] = 0;
+    ashift[i] = 0;
+    rank[i] = atomicAdd(&counts[0], 1);
+    return;
+  }
+  int c[3], s[3];
+  locate(box, g, x, y, z, c, s);
+  unsigned fl = 0;
+  if ((s[0] | s[1] | s[2]) != 0) fl |= kFlagAtomShift;
+  if (abs(s[0]) > 511 || abs(s[1]) > 511 || abs(s[2]) > 511) fl |= kFlagShiftRange;
+  if (fl) atomicOr(&st->flags, fl);
+  const int cell = (c[2] * g.nc[1] + c[1]) * g.nc[0] + c[0];
+  cell_of[i] = cell;
+  ashift[i] = ((s[0] + 512) & 1023) | (((s[1] + 512) & 1023) << 10) | (((s[2] + 512) & 1023) << 20);
+  rank[i] = atomicAdd(&counts[cell], 1);  // integer atomic: the COUNT is order-independent
+}
+
+// ---- exclusive scan over the cell counts (three small kernels) ------------------------------
+constexpr int kScanBlock = 1024;
+constexpr int kScanItems = 4;  // per thread -> 4096 cells per block
+
+__global__ void k_scan_partial(const int* __restrict__ counts, int n, int* __restrict__ block_sums) {
+  __shared__ int warp_sums[32];
+  const int base = blockIdx.x * kScanBlock * kScanItems;
+  int v = 0;
+  for (int t = 0; t < kScanItems; ++t) {
+    const int idx = base + threadIdx.x * kScanItems + t;
+    if (idx < n) v += counts[idx];
+  }
+  for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+  if ((threadIdx.x & 31) == 0) warp_sums[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    int w = warp_sums[threadIdx.x];
+    for (int off = 16; off > 0; off >>= 1) w += __shfl_down_sync(0xffffffffu, w, off);
+    if (threadIdx.x == 0) block_sums[blockIdx.x] = w;
+  }
+}
+
+// single block: exclusive scan of the block sums in place (serial over chunks of 1024)
+__global__ void k_scan_blocks(int* __restrict__ block_sums, int nblocks) {
+  __shared__ int sh[kScanBlock];
+  __shared__ int carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int base = 0; base < nblocks; base += kScanBlock) {
+    const int idx = base + threadIdx.x;
+    const int v = idx < nblocks ? block_sums[idx] : 0;
+    sh[threadIdx.x] = v;
+    __syncthreads();
+    for (int off = 1; off < kScanBlock; off <<= 1) {
+      const int add = threadIdx.x >= off ? sh[threadIdx.x - off] : 0;
+      __syncthreads();
+      sh[threadIdx.x] += add;
+      __syncthreads();
+    }
+    const int incl = sh[threadIdx.x];
+    if (idx < nblocks) block_sums[idx] = carry + incl - v;
+    __syncthreads();
+    if (threadIdx.x == kScanBlock - 1) carry += incl;
+    __syncthreads();
+  }
+}
+
+// starts[c] = exclusive prefix of counts; starts[n] = total
+__global__ void k_scan_final(const int* __restrict__ counts, int n, const int* __restrict__ block_offs,
+                             int* __restrict__ starts) {
+  __shared__ int sh[kScanBlock];
+  const int base = blockIdx.x * kScanBlock * kScanItems;
+  int v[kScanItems];
+  int sum = 0;
+  for (int t = 0; t < kScanItems; ++t) {
+    const int idx = base + threadIdx.x * kScanItems + t;
+    v[t] = idx < n ? counts[idx] : 0;
+    sum += v[t];
+  }
+  sh[threadIdx.x] = sum;
+  __syncthreads();
+  for (int off = 1; off < kScanBlock; off <<= 1) {
+    const int add = threadIdx.x >= off ? sh[threadIdx.x - off] : 0;
+    __syncthreads();
+    sh[threadIdx.x] += add;
+    __syncthreads();
+  }
+  int run = block_offs[blockIdx.x] + sh[threadIdx.x] - sum;
+  for (int t = 0; t < kScanItems; ++t) {
+    const int idx = base + threadIdx.x * kScanItems + t;
+    if (idx < n) starts[idx] = run;
+    run += v[t];
+    if (idx == n - 1) starts[n] = run;
+  }
+}
+
+// ---- scatter + deterministic per-cell order --------------------------------------------------
+__global__ void k_scatter(const int* __restrict__ cell_of, const int* __restrict__ rank,
+                          const int* __restrict__ starts, int n, int* __restrict__ order) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) order[starts[cell_of[i]] + rank[i]] = i;
+}
+
+// one thread per cell: insertion sort of the cell's (short) segment by original index
+__global__ void k_cell_order(const int* __restrict__ starts, int ncells, int* __restrict__ order) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= ncells) return;
+  const int b = starts[c], e = starts[c + 1];
+  for (int a = b + 1; a < e; ++a) {
+    const int v = order[a];
+    int p = a - 1;
+    while (p >= b && order[p] > v) {
+      order[p + 1] = order[p];
+      --p;
+    }
+    order[p + 1] = v;
+  }
+}
+
+// sorted records; species from atomic numbers (rgpot_cuh2.f90:463-489 classify) when check_z
+__global__ void k_gather_sorted(const double* __restrict__ pos, const int* __restrict__ Z,
+                                const int* __restrict__ order, const int* __restrict__ cell_of,
+                                const int* __restrict__ ashift, int n, int check_z,
+                                double4* __restrict__ spos, int* __restrict__ scell,
+                                Status* __restrict__ st) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n) return;
+  const int i = order[s];
+  int species = 0;
+  if (check_z) {
+    const int z = Z[i];
+    if (z == 29) {
+      species = 0;
+    } else if (z == 1) {
+      species = 1;
+    } else {
+      atomicOr(&st->flags, kFlagForeignZ);
+      atomicMin(&st->first_bad_atom, i);
+    }
+  }
+  const int sh = ashift[i];
+  const unsigned long long meta =
+      pack_meta(i, species, (sh & 1023) - 512, ((sh >> 10) & 1023) - 512, ((sh >> 20) & 1023) - 512);
+  spos[s] = make_double4(pos[3 * (size_t)i], pos[3 * (size_t)i + 1], pos[3 * (size_t)i + 2],
+                         __longlong_as_double((long long)meta));
+  scell[s] = cell_of[i];
+}
+
+// ---- deterministic energy reduction --------------------------------------------------------
+// per-block partial sums were written by the force kernels in block order; one block folds them
+// in a fixed tree.  out[0] = sum
+__global__ void k_reduce_partials(const double* __restrict__ partials, int n, double* __restrict__ out) {
+  __shared__ double sh[1024];
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) acc += partials[i];
+  sh[threadIdx.x] = acc;
+  __syncthreads();
+  for (int off = blockDim.x / 2; off > 0; off >>= 1) {
+    if (threadIdx.x < off) sh[threadIdx.x] += sh[threadIdx.x + off];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[0] = sh[0];
+}
+
+// fixed-order block sum helper used by the force kernels (blockDim multiple of 32, <= 1024)
+RB_D double block_sum(double v, double* sh32) {
+  for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (lane == 0) sh32[w] = v;
+  __syncthreads();
+  double r = 0.0;
+  if (w == 0) {
+    r = lane < (int)((blockDim.x + 31) >> 5) ? sh32[lane] : 0.0;
+    for (int off = 16; off > 0; off >>= 1) r += __shfl_down_sync(0xffffffffu, r, off);
+  }
+  __syncthreads();
+  return r;  // valid in thread 0
+}
+
+}  // namespace rb

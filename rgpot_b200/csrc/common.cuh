@@ -1,0 +1,106 @@
+// common.cuh -- shared types and exact-arithmetic helpers of the B200 engine.
+//
+// Bit-exact neighbor decisions: the reference is compiled for baseline x86-64 (no FMA), so
+// every operation that feeds an accept/reject test is written with __dadd_rn / __dmul_rn,
+// which nvcc never contracts.  Everything after the decision (the physics) may use FMA.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace rb {
+
+#define RB_HD __host__ __device__ __forceinline__
+#define RB_D __device__ __forceinline__
+
+constexpr int kKindLJ = 0;
+constexpr int kKindLJCluster = 1;
+constexpr int kKindCuH2 = 2;
+
+// Status flag bits raised by kernels (device word), mapped to ABI statuses on the host.
+constexpr unsigned kFlagNonFinite = 1u;    // -> status 1 (vesin: non-finite coordinate)
+constexpr unsigned kFlagForeignZ = 2u;     // -> status 2
+constexpr unsigned kFlagCoincident = 4u;   // -> status 3
+constexpr unsigned kFlagShiftRange = 8u;   // atom further than +-511 cells outside the box
+constexpr unsigned kFlagListOverflow = 16u;  // per-system, internal: retry on the slow path
+constexpr unsigned kFlagAtomShift = 32u;   // informational: some atom sits outside the cell
+
+struct Status {
+  unsigned flags;
+  int first_bad_atom;  // smallest original index that raised NonFinite / ForeignZ (else INT_MAX)
+  int bad_value;       // its atomic number (ForeignZ)
+  int pad;
+};
+
+// Geometry of one periodic (or free) cell, prepared on the host with the reference's own
+// operation order (vesin-single-build.cpp:100-143, 158-276).
+struct Box {
+  double H[9];     // rows = cell vectors (LJ reference mode: diag(box[0], box[4], box[8]))
+  double Hinv[9];  // inverse, vesin's cofactor formula
+  double face[3];  // distances between faces
+  double lo[3];    // bounding-box origin of non-periodic directions
+  double ext[3];   // bounding-box extent of non-periodic directions
+  int periodic[3];
+  int pad;
+};
+
+// Cell grid: nc cells per direction, stencil half-widths ns, nearest-image dedupe ranges.
+struct Grid {
+  int nc[3];
+  int ns_lo[3];  // stencil runs over delta in [-ns_lo, +ns_hi]
+  int ns_hi[3];
+  int ncells;
+};
+
+// sorted-atom record: position + packed metadata (original index, species, wrap shift).
+// meta: bits 0..31 original index | 32..33 species | 34..43, 44..53, 54..63 shift + 512.
+RB_HD unsigned long long pack_meta(int orig, int species, int s0, int s1, int s2) {
+  return (unsigned long long)(unsigned)orig | ((unsigned long long)(species & 3) << 32) |
+         ((unsigned long long)((s0 + 512) & 1023) << 34) |
+         ((unsigned long long)((s1 + 512) & 1023) << 44) |
+         ((unsigned long long)((s2 + 512) & 1023) << 54);
+}
+RB_HD int meta_orig(unsigned long long m) { return (int)(unsigned)(m & 0xffffffffull); }
+RB_HD int meta_species(unsigned long long m) { return (int)((m >> 32) & 3); }
+RB_HD int meta_shift(unsigned long long m, int k) { return (int)((m >> (34 + 10 * k)) & 1023) - 512; }
+
+// ---- exact (never-contracted) arithmetic -------------------------------------------------
+RB_D double xadd(double a, double b) { return __dadd_rn(a, b); }
+RB_D double xsub(double a, double b) { return __dadd_rn(a, -b); }
+RB_D double xmul(double a, double b) { return __dmul_rn(a, b); }
+
+// dx*dx + dy*dy + dz*dz, left to right, separately rounded (vesin Vector::dot :40-42,
+// vesin_visit.hpp:103).
+RB_D double xnorm2(double dx, double dy, double dz) {
+  return xadd(xadd(xmul(dx, dx), xmul(dy, dy)), xmul(dz, dz));
+}
+
+// CellShift::cartesian component k: s0*H[0][k] + s1*H[1][k] + s2*H[2][k]
+// (vesin-single-build.cpp:372-383 via operator*(Vector, Matrix) :138-143).
+RB_D double shift_component(const double* __restrict__ H, int k, double s0, double s1, double s2) {
+  return xadd(xadd(xmul(s0, H[k]), xmul(s1, H[3 + k])), xmul(s2, H[6 + k]));
+}
+
+// vesin_visit.hpp:23-25 fold: d - w * (double)(long long)(d*inv + copysign(0.5, d*inv)).
+RB_D double fold_component(double d, double w, double inv) {
+  const double t = xmul(d, inv);
+  const double n = (double)(long long)xadd(t, copysign(0.5, t));
+  return xsub(d, xmul(w, n));
+}
+
+// python-convention divmod (vesin-single-build.cpp:1322-1332)
+RB_HD void divmod_i(int a, int b, int& q, int& r) {
+  q = a / b;
+  r = a % b;
+  if (r < 0) {
+    r += b;
+    q -= 1;
+  }
+}
+
+struct LJParams {
+  double u0, psi2, shiftU, rc2;
+  double w[3], inv[3];  // fold widths / inverse widths (inv = 0 disables the fold)
+};
+
+}  // namespace rb

@@ -1,0 +1,1332 @@
+// engine.cu -- host side of the B200 engine: handle state, path selection, launches, C ABI.
+//
+// One handle = one CUDA device + one stream + its own scratch buffers (no process-global state:
+// the reference's Fortran entry keeps a module-saved table and is ProcessSerial,
+// CppCore/rgpot/fortran/FortranPots.hpp:14-18; this engine is PerInstance).
+//
+// There is deliberately no CPU path in this file: if CUDA is unusable every entry point fails.
+#include <cuda_runtime.h>
+#include <limits.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/rgpot_b200.h"
+#include "cells.cuh"
+#include "common.cuh"
+#include "gather.cuh"
+#include "physics.cuh"
+#include "small.cuh"
+
+using namespace rb;
+
+namespace {
+
+constexpr int kStatusCuda = 100;
+constexpr int kStatusArgs = 101;
+constexpr int kStatusRange = 102;
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <class T>
+  T* as() const {
+    return static_cast<T*>(p);
+  }
+};
+
+struct HostBuf {  // pinned
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMallocHost(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() {
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <class T>
+  T* as() const {
+    return static_cast<T*>(p);
+  }
+};
+
+// CuH2 defaults (rgpot_cuh2.f90:58-105) with the five cutoff shifts of cut_shifted (:118-135)
+// evaluated on the host with libm, exactly like the reference does on every call.
+EamParams make_eam_params() {
+  EamParams p{};
+  const double da[3] = {2862.3, 86.1495, 79.5013};
+  const double aa[3] = {3.51236, 4.21154, 2.47961};
+  const double db[3] = {-109.107, 15355.5, -107.555};
+  const double ab[3] = {1.75618, 6.07604, 2.99918};
+  for (int k = 0; k < 3; ++k) {
+    p.da[k] = da[k];
+    p.aa[k] = aa[k];
+    p.db[k] = db[k];
+    p.ab[k] = ab[k];
+  }
+  p.scale[0] = 0.273072;
+  p.ba[0] = 3.69051;
+  p.bb[0] = 7.38101;
+  p.gamma[0] = 512.0;
+  p.scale[1] = 2.14389;
+  p.ba[1] = 3.77701;
+  p.bb[1] = 0.0;
+  p.gamma[1] = 0.0;
+  const double fcu[8] = {-112.945,    8510.04,     -261734.0,     4780090.0,
+                         -52341900.0, 339124000.0, -1201500000.0, 1796190000.0};
+  const double fh[5] = {-81.7537, 838.668, -3952.35, 8767.87, -6599.37};
+  memcpy(p.f_cu, fcu, sizeof fcu);
+  memcpy(p.f_h, fh, sizeof fh);
+  p.rcut = 6.1;
+  p.rc2 = p.rcut * p.rcut;
+  const double r = p.rcut;
+  for (int k = 0; k < 3; ++k) {
+    volatile double t1 = p.da[k] * exp(-p.aa[k] * r);
+    volatile double t2 = p.db[k] * exp(-p.ab[k] * r);
+    volatile double s = t1 + t2;
+    p.phicut[k] = s - 0.0;
+  }
+  {
+    // Cu: r**6 by square-and-multiply (libgfortran pow_r8_i4): r^2 * r^4
+    volatile double t1 = exp(-p.ba[0] * r);
+    volatile double t2 = p.gamma[0] * exp(-p.bb[0] * r);
+    volatile double r2 = r * r;
+    volatile double r4 = r2 * r2;
+    volatile double r6 = r2 * r4;
+    volatile double t3 = p.scale[0] * r6;
+    volatile double s = t1 + t2;
+    p.rhocut[0] = t3 * s - 0.0;
+  }
+  {
+    volatile double t1 = exp(-p.ba[1] * r);
+    volatile double t2 = p.gamma[1] * exp(-p.bb[1] * r);
+    volatile double t3 = p.scale[1] * 1.0;
+    volatile double s = t1 + t2;
+    p.rhocut[1] = t3 * s - 0.0;
+  }
+  return p;
+}
+
+}  // namespace
+
+struct RgpotB200Pot {
+  RgpotB200Config cfg{};
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  int sm_count = 0;
+  size_t smem_optin = 0;
+  double lj_shiftU = 0.0;
+  double lj_rc = 0.0;  // effective cutoff (cluster: <= 0 -> 1e6)
+  int forced_path = 0;
+  long launches = 0;
+  std::string last_error;
+
+  // single-system scratch
+  DevBuf pos, Z, F, cell_of, rank, ashift, counts, starts, blocksums, order, spos, scell, dfd, eemb,
+      partials, energy, status, mm, emit_pairs, emit_shifts, emit_count;
+  // batch scratch
+  DevBuf b_pos, b_Z, b_F, b_off, b_boxes, b_E, b_flags, b_bad, b_map;
+  HostBuf h_pos, h_Z, h_F, h_off, h_boxes, h_E, h_flags, h_bad, h_small;
+  // outstanding async (device API) call, resolved by rgpot_b200_sync_status
+  struct Pending {
+    bool active = false;
+    bool batch = false;        // a packed batch (else one system)
+    bool small_single = false; // single system that ran as a batch of one
+    long n = 0;
+    size_t nsys = 0;
+    const double* pos = nullptr;
+    const int* Z = nullptr;
+    double* F = nullptr;
+    double* E = nullptr;
+    const double* d_boxes = nullptr;
+    double box[9] = {0};
+    bool has_box = false;
+    cudaStream_t st = nullptr;
+    std::vector<size_t> offsets;
+  } pend;
+
+  ~RgpotB200Pot() {
+    cudaSetDevice(device);
+    DevBuf* d[] = {&pos, &Z, &F, &cell_of, &rank, &ashift, &counts, &starts, &blocksums, &order,
+                   &spos, &scell, &dfd, &eemb, &partials, &energy, &status, &mm, &emit_pairs,
+                   &emit_shifts, &emit_count, &b_pos, &b_Z, &b_F, &b_off, &b_boxes, &b_E, &b_flags,
+                   &b_bad, &b_map};
+    for (auto* b : d) b->release();
+    HostBuf* h[] = {&h_pos, &h_Z, &h_F, &h_off, &h_boxes, &h_E, &h_flags, &h_bad, &h_small};
+    for (auto* b : h) b->release();
+    if (stream) cudaStreamDestroy(stream);
+  }
+};
+
+namespace {
+
+#define CU_TRY(pot, expr)                                                                   \
+  do {                                                                                      \
+    cudaError_t _e = (expr);                                                                \
+    if (_e != cudaSuccess) {                                                                \
+      (pot)->last_error = std::string("CUDA failure: ") + cudaGetErrorString(_e) + " at " + \
+                          #expr;                                                            \
+      return kStatusCuda;                                                                   \
+    }                                                                                       \
+  } while (0)
+
+int fail(RgpotB200Pot* pot, int status, const std::string& msg) {
+  pot->last_error = msg;
+  return status;
+}
+
+// ---- box / grid preparation (host, reference operation order) ---------------------------------
+bool invert_box(const double* m, double* v) {
+  // vesin Matrix::determinant / inverse, vesin-single-build.cpp:100-128
+  const double det = m[0] * (m[4] * m[8] - m[7] * m[5]) - m[1] * (m[3] * m[8] - m[5] * m[6]) +
+                     m[2] * (m[3] * m[7] - m[4] * m[6]);
+  if (!(fabs(det) >= 1e-30)) return false;
+  v[0] = (m[4] * m[8] - m[7] * m[5]) / det;
+  v[1] = (m[2] * m[7] - m[1] * m[8]) / det;
+  v[2] = (m[1] * m[5] - m[2] * m[4]) / det;
+  v[3] = (m[5] * m[6] - m[3] * m[8]) / det;
+  v[4] = (m[0] * m[8] - m[2] * m[6]) / det;
+  v[5] = (m[3] * m[2] - m[0] * m[5]) / det;
+  v[6] = (m[3] * m[7] - m[6] * m[4]) / det;
+  v[7] = (m[6] * m[1] - m[0] * m[7]) / det;
+  v[8] = (m[0] * m[4] - m[3] * m[1]) / det;
+  return true;
+}
+
+void face_distances(const double* H, double* face) {
+  // vesin-single-build.cpp:258-275
+  auto cross = [](const double* a, const double* b, double* c) {
+    c[0] = a[1] * b[2] - a[2] * b[1];
+    c[1] = a[2] * b[0] - a[0] * b[2];
+    c[2] = a[0] * b[1] - a[1] * b[0];
+  };
+  auto dot = [](const double* a, const double* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; };
+  const double *a = H, *b = H + 3, *c = H + 6;
+  double n[3];
+  const double* vec[3] = {a, b, c};
+  const double* o1[3] = {b, c, a};
+  const double* o2[3] = {c, a, b};
+  for (int k = 0; k < 3; ++k) {
+    cross(o1[k], o2[k], n);
+    const double nn = sqrt(dot(n, n));
+    face[k] = fabs(dot(n, vec[k])) / nn;
+  }
+}
+
+struct Plan {
+  Box box;
+  Grid grid;
+  int geo;
+  LJParams lj;
+  double rc2;
+};
+
+// margin that keeps cell adjacency strictly conservative against rounding in the binning
+constexpr double kCellMargin = 1.0 + 1.0e-6;
+
+void finish_grid(Plan& pl, double rc, long n, bool images) {
+  const double rcm = rc * kCellMargin;
+  double ncd[3];
+  for (int k = 0; k < 3; ++k) {
+    const double width = pl.box.periodic[k] ? pl.box.face[k] : pl.box.ext[k];
+    double c = floor(width / rcm);
+    if (!(c >= 1.0)) c = 1.0;
+    if (c > 1024.0) c = 1024.0;
+    ncd[k] = c;
+  }
+  // bound the cell count (memory and empty-cell overhead): about one cell per atom at most
+  const double cap = std::max(64.0, 2.0 * (double)n);
+  double total = ncd[0] * ncd[1] * ncd[2];
+  while (total > cap) {
+    int kmax = 0;
+    for (int k = 1; k < 3; ++k)
+      if (ncd[k] > ncd[kmax]) kmax = k;
+    if (ncd[kmax] <= 1.0) break;
+    ncd[kmax] = floor(ncd[kmax] * 0.9);
+    if (ncd[kmax] < 1.0) ncd[kmax] = 1.0;
+    total = ncd[0] * ncd[1] * ncd[2];
+  }
+  for (int k = 0; k < 3; ++k) {
+    const int nc = (int)ncd[k];
+    pl.grid.nc[k] = nc;
+    if (images) {
+      // vesin CellList n_search (:1380-1392): cells to look through so no image is missed
+      const double width = pl.box.face[k];
+      int ns = (int)ceil(rcm * (double)nc / width);
+      if (ns < 1) ns = 1;
+      pl.grid.ns_lo[k] = pl.grid.ns_hi[k] = ns;
+    } else if (pl.box.periodic[k]) {
+      // nearest-image LJ: every DISTINCT neighbouring cell once
+      pl.grid.ns_lo[k] = nc >= 3 ? 1 : 0;
+      pl.grid.ns_hi[k] = nc >= 2 ? 1 : 0;
+    } else {
+      pl.grid.ns_lo[k] = pl.grid.ns_hi[k] = 1;
+    }
+  }
+  pl.grid.ncells = pl.grid.nc[0] * pl.grid.nc[1] * pl.grid.nc[2];
+}
+
+}  // namespace
+
+// ================================================================================================
+//  launches
+// ================================================================================================
+namespace {
+
+inline int div_up(long a, int b) { return (int)((a + b - 1) / b); }
+
+int check_launch(RgpotB200Pot* pot, const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    pot->last_error = std::string("CUDA launch failure (") + what + "): " + cudaGetErrorString(e);
+    return kStatusCuda;
+  }
+  pot->launches++;
+  return 0;
+}
+
+#define LAUNCH_CHECK(pot, what)                 \
+  do {                                          \
+    int _s = check_launch(pot, what);           \
+    if (_s) return _s;                          \
+  } while (0)
+
+// Cell-list path for ONE system whose positions / Z already sit on the device.
+// Leaves forces in d_F (original order), energy in d_E[0], flags in pot->status.
+int run_cell_path(RgpotB200Pot* pot, long n, const double* d_pos, const int* d_Z, double* d_F,
+                  double* d_E, const double* box, cudaStream_t st, const EmitArgs* emit) {
+  const int kind = pot->cfg.kind;
+  const bool eam = kind == RGPOT_B200_CUH2;
+  const bool images = eam || pot->cfg.lj_all_images;
+  Plan pl{};
+  const double rc = eam ? 6.1 : pot->lj_rc;
+
+  CU_TRY(pot, pot->status.reserve(sizeof(Status)));
+  Status init{0u, INT_MAX, 0, 0};
+  CU_TRY(pot, cudaMemcpyAsync(pot->status.p, &init, sizeof init, cudaMemcpyHostToDevice, st));
+
+  if (images) {
+    memcpy(pl.box.H, box, 9 * sizeof(double));
+    if (!invert_box(pl.box.H, pl.box.Hinv))
+      return fail(pot, 1, "rgpot_neighbors: vesin build failed: the box matrix is not invertible");
+    face_distances(pl.box.H, pl.box.face);
+    for (int k = 0; k < 3; ++k) {
+      pl.box.periodic[k] = 1;
+      pl.box.lo[k] = 0.0;
+      pl.box.ext[k] = 1.0;
+    }
+  } else {
+    // LJ reference semantics: only the box diagonal is read (LJPot.cc:35, PairListCache.hpp:176-184)
+    const bool cluster = kind == RGPOT_B200_LJ_CLUSTER;
+    memset(pl.box.H, 0, sizeof pl.box.H);
+    memset(pl.box.Hinv, 0, sizeof pl.box.Hinv);
+    bool need_bbox = false;
+    for (int k = 0; k < 3; ++k) {
+      const double w = box ? box[4 * k] : 0.0;
+      const bool per = !cluster && w != 0.0 && std::isfinite(w);
+      pl.box.periodic[k] = per ? 1 : 0;
+      pl.box.H[4 * k] = per ? w : 1.0;
+      pl.box.Hinv[4 * k] = per ? 1.0 / w : 1.0;
+      pl.box.face[k] = per ? fabs(w) : 1.0;
+      pl.lj.w[k] = cluster ? 0.0 : w;
+      pl.lj.inv[k] = per ? 1.0 / w : 0.0;
+      if (!per) need_bbox = true;
+    }
+    for (int k = 0; k < 3; ++k) {
+      pl.box.lo[k] = 0.0;
+      pl.box.ext[k] = 1.0;
+    }
+    if (need_bbox) {
+      CU_TRY(pot, pot->mm.reserve(6 * sizeof(unsigned long long)));
+      unsigned long long initmm[6] = {~0ull, ~0ull, ~0ull, 0ull, 0ull, 0ull};
+      CU_TRY(pot, cudaMemcpyAsync(pot->mm.p, initmm, sizeof initmm, cudaMemcpyHostToDevice, st));
+      k_bbox<<<std::min(div_up(n, 256), 4 * pot->sm_count), 256, 0, st>>>(
+          d_pos, (int)n, pot->mm.as<unsigned long long>());
+      LAUNCH_CHECK(pot, "k_bbox");
+      unsigned long long got[6];
+      CU_TRY(pot, cudaMemcpyAsync(got, pot->mm.p, sizeof got, cudaMemcpyDeviceToHost, st));
+      CU_TRY(pot, cudaStreamSynchronize(st));
+      for (int k = 0; k < 3; ++k) {
+        if (pl.box.periodic[k]) continue;
+        double lo = dkey_inv(got[k]), hi = dkey_inv(got[3 + k]);
+        if (!std::isfinite(lo) || !std::isfinite(hi)) {
+          lo = 0.0;
+          hi = 1.0;
+        }
+        double ext = (hi - lo) * (1.0 + 1e-9);
+        if (!(ext > 1e-6)) ext = 1.0;
+        pl.box.lo[k] = lo;
+        pl.box.ext[k] = ext;
+      }
+    }
+  }
+  pl.lj.u0 = pot->cfg.u0;
+  pl.lj.psi2 = pot->cfg.psi * pot->cfg.psi;
+  pl.lj.shiftU = pot->lj_shiftU;
+  pl.lj.rc2 = rc * rc;
+  pl.rc2 = rc * rc;
+  finish_grid(pl, rc, n, images);
+  if (images) {
+    pl.geo = GEO_IMAGES;
+  } else {
+    bool shift_ok = true;
+    for (int k = 0; k < 3; ++k)
+      if (pl.box.periodic[k] && pl.grid.nc[k] < 3) shift_ok = false;
+    pl.geo = shift_ok ? GEO_LJ_SHIFT : GEO_LJ_FOLD;
+  }
+
+  const int ncells = pl.grid.ncells;
+  const int nscan = div_up(ncells, kScanBlock * kScanItems);
+  CU_TRY(pot, pot->cell_of.reserve(sizeof(int) * n));
+  CU_TRY(pot, pot->rank.reserve(sizeof(int) * n));
+  CU_TRY(pot, pot->ashift.reserve(sizeof(int) * n));
+  CU_TRY(pot, pot->counts.reserve(sizeof(int) * ((size_t)ncells + 1)));
+  CU_TRY(pot, pot->starts.reserve(sizeof(int) * ((size_t)ncells + 1)));
+  CU_TRY(pot, pot->blocksums.reserve(sizeof(int) * ((size_t)nscan + 1)));
+  CU_TRY(pot, pot->order.reserve(sizeof(int) * n));
+  CU_TRY(pot, pot->spos.reserve(sizeof(double4) * n));
+  CU_TRY(pot, pot->scell.reserve(sizeof(int) * n));
+  const int nblk = div_up(n, 128);
+  CU_TRY(pot, pot->partials.reserve(sizeof(double) * nblk));
+  if (eam) {
+    CU_TRY(pot, pot->dfd.reserve(sizeof(double) * n));
+    CU_TRY(pot, pot->eemb.reserve(sizeof(double) * n));
+  }
+
+  Status* d_st = pot->status.as<Status>();
+  CU_TRY(pot, cudaMemsetAsync(pot->counts.p, 0, sizeof(int) * ((size_t)ncells + 1), st));
+  k_bin<<<div_up(n, 256), 256, 0, st>>>(d_pos, (int)n, pl.box, pl.grid, pot->cell_of.as<int>(),
+                                        pot->rank.as<int>(), pot->ashift.as<int>(),
+                                        pot->counts.as<int>(), d_st);
+  LAUNCH_CHECK(pot, "k_bin");
+  k_scan_partial<<<nscan, kScanBlock, 0, st>>>(pot->counts.as<int>(), ncells, pot->blocksums.as<int>());
+  LAUNCH_CHECK(pot, "k_scan_partial");
+  k_scan_blocks<<<1, kScanBlock, 0, st>>>(pot->blocksums.as<int>(), nscan);
+  LAUNCH_CHECK(pot, "k_scan_blocks");
+  k_scan_final<<<nscan, kScanBlock, 0, st>>>(pot->counts.as<int>(), ncells, pot->blocksums.as<int>(),
+                                             pot->starts.as<int>());
+  LAUNCH_CHECK(pot, "k_scan_final");
+  k_scatter<<<div_up(n, 256), 256, 0, st>>>(pot->cell_of.as<int>(), pot->rank.as<int>(),
+                                            pot->starts.as<int>(), (int)n, pot->order.as<int>());
+  LAUNCH_CHECK(pot, "k_scatter");
+  k_cell_order<<<div_up(ncells, 128), 128, 0, st>>>(pot->starts.as<int>(), ncells, pot->order.as<int>());
+  LAUNCH_CHECK(pot, "k_cell_order");
+  k_gather_sorted<<<div_up(n, 256), 256, 0, st>>>(d_pos, d_Z, pot->order.as<int>(),
+                                                  pot->cell_of.as<int>(), pot->ashift.as<int>(), (int)n,
+                                                  eam ? 1 : 0, pot->spos.as<double4>(),
+                                                  pot->scell.as<int>(), d_st);
+  LAUNCH_CHECK(pot, "k_gather_sorted");
+
+  GatherArgs ga{};
+  ga.spos = pot->spos.as<double4>();
+  ga.scell = pot->scell.as<int>();
+  ga.starts = pot->starts.as<int>();
+  ga.n = (int)n;
+  ga.box = pl.box;
+  ga.grid = pl.grid;
+  ga.lj = pl.lj;
+  ga.rc2 = pl.rc2;
+  ga.st_in = d_st;
+
+  if (emit) {
+    if (pl.geo == GEO_IMAGES)
+      k_emit_pairs<GEO_IMAGES><<<nblk, 128, 0, st>>>(ga, *emit);
+    else if (pl.geo == GEO_LJ_SHIFT)
+      k_emit_pairs<GEO_LJ_SHIFT><<<nblk, 128, 0, st>>>(ga, *emit);
+    else
+      k_emit_pairs<GEO_LJ_FOLD><<<nblk, 128, 0, st>>>(ga, *emit);
+    LAUNCH_CHECK(pot, "k_emit_pairs");
+    return 0;
+  }
+
+  double* d_part = pot->partials.as<double>();
+  if (eam) {
+    k_eam_density<<<nblk, 128, 0, st>>>(ga, pot->dfd.as<double>(), pot->eemb.as<double>(), d_st);
+    LAUNCH_CHECK(pot, "k_eam_density");
+    k_eam_force<<<nblk, 128, 0, st>>>(ga, pot->dfd.as<double>(), pot->eemb.as<double>(), d_F, d_part);
+    LAUNCH_CHECK(pot, "k_eam_force");
+  } else if (pl.geo == GEO_IMAGES) {
+    k_lj_gather<GEO_IMAGES><<<nblk, 128, 0, st>>>(ga, d_F, d_part);
+    LAUNCH_CHECK(pot, "k_lj_gather<images>");
+  } else if (pl.geo == GEO_LJ_SHIFT) {
+    k_lj_gather<GEO_LJ_SHIFT><<<nblk, 128, 0, st>>>(ga, d_F, d_part);
+    LAUNCH_CHECK(pot, "k_lj_gather<shift>");
+  } else {
+    k_lj_gather<GEO_LJ_FOLD><<<nblk, 128, 0, st>>>(ga, d_F, d_part);
+    LAUNCH_CHECK(pot, "k_lj_gather<fold>");
+  }
+  k_reduce_partials<<<1, 1024, 0, st>>>(d_part, nblk, d_E);
+  LAUNCH_CHECK(pot, "k_reduce_partials");
+  return 0;
+}
+
+// shared memory a k_eam_small block needs
+size_t eam_small_smem(long n, int maxnb) { return (size_t)n * (68 + 4 * (size_t)maxnb) + 16; }
+
+// pick the list capacity for a batch whose largest system has nmax atoms (0 = does not fit)
+int eam_small_maxnb(const RgpotB200Pot* pot, long nmax) {
+  if (nmax < 1) return 96;
+  if (nmax > 65535) return 0;
+  // two resident blocks per SM when possible, else the roomiest list that still fits one block
+  const size_t per_sm = 227 * 1024;
+  if (eam_small_smem(nmax, 96) <= per_sm / 2 - 2048) return 96;
+  for (int maxnb : {160, 128, 96}) {
+    if (eam_small_smem(nmax, maxnb) <= pot->smem_optin - 1024) return maxnb;
+  }
+  return 0;
+}
+
+// Launch the batched all-pairs kernel over nsys systems (device-resident, packed).
+int launch_small(RgpotB200Pot* pot, size_t nsys, long nmax, const long long* d_off,
+                 const double* d_boxes, const double* d_pos, const int* d_Z, double* d_F,
+                 double* d_E, unsigned* d_flags, int* d_bad, int maxnb, cudaStream_t st,
+                 const EmitArgs* emit) {
+  SmallArgs a{};
+  a.pos = d_pos;
+  a.Z = d_Z;
+  a.off = d_off;
+  a.boxes = d_boxes;
+  a.F = d_F;
+  a.E = d_E;
+  a.sys_flags = d_flags;
+  a.sys_bad = d_bad;
+  a.nsys = (int)nsys;
+  a.maxnb = maxnb;
+  a.cluster = pot->cfg.kind == RGPOT_B200_LJ_CLUSTER;
+  a.u0 = pot->cfg.u0;
+  a.psi2 = pot->cfg.psi * pot->cfg.psi;
+  a.shiftU = pot->lj_shiftU;
+  a.cutoff = pot->lj_rc;
+  if (emit) a.emit = *emit;
+  if (pot->cfg.kind == RGPOT_B200_CUH2) {
+    const size_t smem = eam_small_smem(nmax, maxnb);
+    // lanes per atom: fill about 448 threads
+    int tpa = 1;
+    while (tpa < 8 && nmax * (tpa * 2) <= 512) tpa *= 2;
+    int threads = (int)std::min<long>(512, ((nmax * tpa + 31) / 32) * 32);
+    if (threads < 32) threads = 32;
+    auto launch = [&](auto kern) -> int {
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)pot->smem_optin);
+      if (e != cudaSuccess) {
+        pot->last_error = std::string("CUDA failure: ") + cudaGetErrorString(e);
+        return kStatusCuda;
+      }
+      kern<<<(unsigned)nsys, threads, smem, st>>>(a);
+      return check_launch(pot, "k_eam_small");
+    };
+    switch (tpa) {
+      case 1: return launch(k_eam_small<1>);
+      case 2: return launch(k_eam_small<2>);
+      case 4: return launch(k_eam_small<4>);
+      default: return launch(k_eam_small<8>);
+    }
+  }
+  const size_t smem = sizeof(double) * 3 * (size_t)nmax + 16;
+  cudaError_t e = cudaFuncSetAttribute(k_lj_small, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)pot->smem_optin);
+  if (e != cudaSuccess) return fail(pot, kStatusCuda, std::string("CUDA failure: ") + cudaGetErrorString(e));
+  int threads = (int)std::min<long>(256, ((nmax + 31) / 32) * 32);
+  if (threads < 32) threads = 32;
+  k_lj_small<<<(unsigned)nsys, threads, smem, st>>>(a);
+  return check_launch(pot, "k_lj_small");
+}
+
+// can a system of n atoms run on the all-pairs kernels?
+bool small_eligible(const RgpotB200Pot* pot, long n) {
+  if (pot->cfg.kind == RGPOT_B200_CUH2) return n <= 512 && eam_small_maxnb(pot, n) > 0;
+  if (pot->cfg.lj_all_images) return false;  // opt-in mode lives on the cell path only
+  return n <= 2048;
+}
+
+// status word -> ABI status + message.  Precedence follows rgpot_cuh2.f90:412-429:
+// classify (2) before the table build (1) before the coincidence guard (3).
+int map_flags(RgpotB200Pot* pot, unsigned flags, int bad_atom, int bad_z, const double* host_pos) {
+  const bool eam = pot->cfg.kind == RGPOT_B200_CUH2;
+  if (eam && (flags & kFlagForeignZ)) {
+    char buf[256];
+    snprintf(buf, sizeof buf,
+             "rgpot_cuh2: atom %d has atomic number %d; this potential covers Cu (29) and H (1) only",
+             bad_atom + 1, bad_z);
+    return fail(pot, 2, buf);
+  }
+  const bool images = eam || pot->cfg.lj_all_images;
+  if (images && (flags & kFlagNonFinite)) {
+    char buf[256];
+    if (host_pos && bad_atom != INT_MAX && bad_atom >= 0) {
+      int axis = 0;
+      for (int k = 0; k < 3; ++k)
+        if (!std::isfinite(host_pos[3 * (size_t)bad_atom + k])) {
+          axis = k;
+          break;
+        }
+      snprintf(buf, sizeof buf,
+               "rgpot_neighbors: vesin build failed: point %d has non-finite coordinate along axis %d: %f",
+               bad_atom, axis, host_pos[3 * (size_t)bad_atom + axis]);
+    } else {
+      snprintf(buf, sizeof buf,
+               "rgpot_neighbors: vesin build failed: non-finite coordinate or singular box");
+    }
+    return fail(pot, 1, buf);
+  }
+  if (flags & kFlagShiftRange)
+    return fail(pot, kStatusRange, "rgpot_b200: an atom lies more than 500 cell widths outside the box");
+  if (eam && (flags & kFlagCoincident))
+    return fail(pot, 3, "rgpot_cuh2: two atoms occupy the same position");
+  return 0;
+}
+
+void lj_setup(RgpotB200Pot* pot) {
+  // LJPot.hpp:52-53 ; LJClusterPot.cc:46 (cutoff <= 0 means "no cutoff" for clusters)
+  const RgpotB200Config& c = pot->cfg;
+  const double a = pow(c.psi / c.cutoff, 6.0);
+  pot->lj_shiftU = 4.0 * c.u0 * a * (a - 1.0);
+  pot->lj_rc = c.cutoff;
+  if (c.kind == RGPOT_B200_LJ_CLUSTER && !(c.cutoff > 0.0)) pot->lj_rc = 1.0e6;
+}
+
+// ---- FP64 peak microbenchmark ------------------------------------------------------------------
+__global__ void k_dfma_peak(double* out, int iters, double a, double b) {
+  double x0 = threadIdx.x * 1e-9, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5,
+         x6 = x0 + 6, x7 = x0 + 7;
+  for (int i = 0; i < iters; ++i) {
+    x0 = fma(x0, a, b);
+    x1 = fma(x1, a, b);
+    x2 = fma(x2, a, b);
+    x3 = fma(x3, a, b);
+    x4 = fma(x4, a, b);
+    x5 = fma(x5, a, b);
+    x6 = fma(x6, a, b);
+    x7 = fma(x7, a, b);
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+}
+
+}  // namespace
+
+// ================================================================================================
+//  C ABI
+// ================================================================================================
+extern "C" {
+
+int rgpot_b200_abi_version(void) { return RGPOT_B200_ABI_VERSION; }
+
+int rgpot_b200_available(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  int ok = 0;
+  for (int d = 0; d < n; ++d) {
+    cudaDeviceProp p;
+    if (cudaGetDeviceProperties(&p, d) == cudaSuccess && p.major >= 10) ++ok;
+  }
+  return ok;
+}
+
+void rgpot_b200_default_config(int kind, RgpotB200Config* cfg) {
+  if (!cfg) return;
+  memset(cfg, 0, sizeof *cfg);
+  cfg->kind = kind;
+  cfg->device = -1;
+  cfg->u0 = 1.0;
+  cfg->cutoff = kind == RGPOT_B200_CUH2 ? 6.1 : 15.0;
+  cfg->psi = 1.0;
+}
+
+RgpotB200Pot* rgpot_b200_create(const RgpotB200Config* cfg, char* errbuf, size_t errlen) {
+  auto err = [&](const std::string& m) -> RgpotB200Pot* {
+    if (errbuf && errlen) snprintf(errbuf, errlen, "%s", m.c_str());
+    return nullptr;
+  };
+  if (!cfg) return err("rgpot_b200_create: null config");
+  if (cfg->kind < RGPOT_B200_LJ || cfg->kind > RGPOT_B200_CUH2)
+    return err("rgpot_b200_create: unknown potential kind");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return err(std::string("rgpot_b200_create: no CUDA device (") +
+               (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0") +
+               "); this engine has no CPU fallback");
+  }
+  int dev = cfg->device;
+  if (dev < 0) {
+    if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
+  }
+  if (dev >= ndev) return err("rgpot_b200_create: device ordinal out of range");
+  cudaDeviceProp prop;
+  if (cudaSetDevice(dev) != cudaSuccess || cudaGetDeviceProperties(&prop, dev) != cudaSuccess)
+    return err("rgpot_b200_create: cannot select the device");
+  if (prop.major < 10)
+    return err("rgpot_b200_create: the engine is built for sm_100a (B200) only");
+  auto* pot = new RgpotB200Pot();
+  pot->cfg = *cfg;
+  pot->device = dev;
+  pot->sm_count = prop.multiProcessorCount;
+  pot->smem_optin = prop.sharedMemPerBlockOptin;
+  if (cudaStreamCreateWithFlags(&pot->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    delete pot;
+    return err("rgpot_b200_create: cannot create a stream");
+  }
+  if (cfg->kind == RGPOT_B200_CUH2) {
+    const EamParams p = make_eam_params();
+    if (cudaMemcpyToSymbol(c_eam, &p, sizeof p) != cudaSuccess) {
+      delete pot;
+      return err("rgpot_b200_create: cannot upload the EAM coefficients");
+    }
+  } else {
+    lj_setup(pot);
+  }
+  return pot;
+}
+
+void rgpot_b200_destroy(RgpotB200Pot* pot) { delete pot; }
+
+int rgpot_b200_last_error(RgpotB200Pot* pot, char* buffer, int buffer_len) {
+  if (!pot || !buffer || buffer_len <= 0) return 0;
+  const int n = (int)std::min<size_t>(pot->last_error.size(), (size_t)buffer_len - 1);
+  memcpy(buffer, pot->last_error.data(), n);
+  buffer[n] = 0;
+  return n;
+}
+
+long rgpot_b200_launch_count(RgpotB200Pot* pot) { return pot ? pot->launches : 0; }
+
+int rgpot_b200_set_option(RgpotB200Pot* pot, const char* key, long value) {
+  if (!pot || !key) return kStatusArgs;
+  if (strcmp(key, "path") == 0) {
+    pot->forced_path = (int)value;
+    return 0;
+  }
+  return kStatusArgs;
+}
+
+void* rgpot_b200_host_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  return p;
+}
+void rgpot_b200_host_free(void* ptr) {
+  if (ptr) cudaFreeHost(ptr);
+}
+
+double rgpot_b200_measure_fp64_tflops(int device, int iters) {
+  if (device >= 0 && cudaSetDevice(device) != cudaSuccess) return 0.0;
+  cudaDeviceProp prop;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return 0.0;
+  const int blocks = prop.multiProcessorCount * 8, threads = 256;
+  double* out = nullptr;
+  if (cudaMalloc(&out, sizeof(double) * blocks * threads) != cudaSuccess) return 0.0;
+  cudaEvent_t t0, t1;
+  cudaEventCreate(&t0);
+  cudaEventCreate(&t1);
+  if (iters < 1000) iters = 1000;
+  double best = 0.0;
+  for (int rep = 0; rep < 5; ++rep) {
+    cudaEventRecord(t0);
+    k_dfma_peak<<<blocks, threads>>>(out, iters, 1.0000001, 1e-9);
+    cudaEventRecord(t1);
+    cudaEventSynchronize(t1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, t0, t1);
+    const double flops = 2.0 * 8.0 * (double)iters * blocks * threads;
+    if (rep > 0 && ms > 0) best = std::max(best, flops / (ms * 1e-3) / 1e12);
+  }
+  cudaEventDestroy(t0);
+  cudaEventDestroy(t1);
+  cudaFree(out);
+  return best;
+}
+
+// ------------------------------------------------------------------------------------------------
+// device-resident entry points
+// ------------------------------------------------------------------------------------------------
+static int force_device_impl(RgpotB200Pot* pot, long n, const double* d_pos, const int* d_Z,
+                             double* d_F, double* d_E, const double* box, cudaStream_t st,
+                             const EmitArgs* emit, int path) {
+  const int kind = pot->cfg.kind;
+  if (path == 0) path = pot->forced_path;
+  bool small = small_eligible(pot, n);
+  if (path == 1) small = false;
+  if (path == 2 && !small_eligible(pot, n))
+    return fail(pot, kStatusArgs, "rgpot_b200: system too large for the all-pairs kernels");
+  if (small) {
+    // a batch of one
+    CU_TRY(pot, pot->b_off.reserve(2 * sizeof(long long)));
+    CU_TRY(pot, pot->b_boxes.reserve(9 * sizeof(double)));
+    CU_TRY(pot, pot->b_flags.reserve(sizeof(unsigned)));
+    CU_TRY(pot, pot->b_bad.reserve(2 * sizeof(int)));
+    const long long off[2] = {0, n};
+    double hb[9] = {0};
+    if (box) memcpy(hb, box, sizeof hb);
+    CU_TRY(pot, cudaMemcpyAsync(pot->b_off.p, off, sizeof off, cudaMemcpyHostToDevice, st));
+    CU_TRY(pot, cudaMemcpyAsync(pot->b_boxes.p, hb, sizeof hb, cudaMemcpyHostToDevice, st));
+    CU_TRY(pot, cudaMemsetAsync(pot->b_flags.p, 0, sizeof(unsigned), st));
+    const int maxnb = kind == RGPOT_B200_CUH2 ? eam_small_maxnb(pot, n) : 0;
+    int s = launch_small(pot, 1, n, pot->b_off.as<long long>(), pot->b_boxes.as<double>(), d_pos, d_Z,
+                         d_F, d_E, pot->b_flags.as<unsigned>(), pot->b_bad.as<int>(), maxnb, st, emit);
+    if (s) return s;
+    pot->pend.small_single = true;
+    return 0;
+  }
+  pot->pend.small_single = false;
+  return run_cell_path(pot, n, d_pos, d_Z, d_F, d_E, box, st, emit);
+}
+
+// Read back the flags of the last single-system call and turn them into a status.
+// May rerun a list-overflow system on the cell path (needs the device inputs again).
+static int finish_single(RgpotB200Pot* pot, long n, const double* d_pos, const int* d_Z, double* d_F,
+                         double* d_E, const double* box, cudaStream_t st, const double* host_pos,
+                         const int* host_Z) {
+  unsigned flags = 0;
+  int bad = INT_MAX, badz = 0;
+  if (pot->pend.small_single) {
+    int hb[2] = {INT_MAX, 0};
+    CU_TRY(pot, cudaMemcpyAsync(&flags, pot->b_flags.p, sizeof flags, cudaMemcpyDeviceToHost, st));
+    CU_TRY(pot, cudaMemcpyAsync(hb, pot->b_bad.p, sizeof hb, cudaMemcpyDeviceToHost, st));
+    CU_TRY(pot, cudaStreamSynchronize(st));
+    if (flags & kFlagListOverflow) {
+      pot->pend.small_single = false;
+      int s = run_cell_path(pot, n, d_pos, d_Z, d_F, d_E, box, st, nullptr);
+      if (s) return s;
+      return finish_single(pot, n, d_pos, d_Z, d_F, d_E, box, st, host_pos, host_Z);
+    }
+    bad = hb[0];
+    badz = hb[1];
+  } else {
+    Status stt{};
+    CU_TRY(pot, cudaMemcpyAsync(&stt, pot->status.p, sizeof stt, cudaMemcpyDeviceToHost, st));
+    CU_TRY(pot, cudaStreamSynchronize(st));
+    flags = stt.flags;
+    bad = stt.first_bad_atom;
+    if ((flags & kFlagForeignZ) && bad != INT_MAX) {
+      if (host_Z) {
+        badz = host_Z[bad];
+      } else {
+        CU_TRY(pot, cudaMemcpy(&badz, d_Z + bad, sizeof(int), cudaMemcpyDeviceToHost));
+      }
+    }
+  }
+  return map_flags(pot, flags, bad, badz, host_pos);
+}
+
+int rgpot_b200_force_device(RgpotB200Pot* pot, long nAtoms, const double* d_positions,
+                            const int* d_atomicNrs, double* d_forces, double* d_energy,
+                            const double* box, void* cuda_stream) {
+  if (!pot) return kStatusArgs;
+  pot->last_error.clear();
+  CU_TRY(pot, cudaSetDevice(pot->device));
+  cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : pot->stream;
+  pot->pend.active = false;
+  if (nAtoms < 0 || nAtoms > INT_MAX / 4) return fail(pot, kStatusArgs, "rgpot_b200: bad atom count");
+  const bool eam = pot->cfg.kind == RGPOT_B200_CUH2;
+  // reference early-outs: rgpot_cuh2_capi.f90:50 (natoms < 1), LJPot.cc:50-52, LJClusterPot.cc:43-45
+  const bool trivial = eam ? nAtoms < 1
+                           : (nAtoms < 2 || (pot->cfg.kind == RGPOT_B200_LJ && !(pot->cfg.cutoff > 0.0)));
+  if (trivial) {
+    if (nAtoms > 0) CU_TRY(pot, cudaMemsetAsync(d_forces, 0, sizeof(double) * 3 * nAtoms, st));
+    CU_TRY(pot, cudaMemsetAsync(d_energy, 0, sizeof(double), st));
+    return 0;
+  }
+  if (eam && !d_atomicNrs) return fail(pot, kStatusArgs, "rgpot_b200: CuH2 needs atomic numbers");
+  int s = force_device_impl(pot, nAtoms, d_positions, d_atomicNrs, d_forces, d_energy, box, st,
+                            nullptr, 0);
+  if (s) {
+    cudaMemsetAsync(d_forces, 0, sizeof(double) * 3 * nAtoms, st);
+    cudaMemsetAsync(d_energy, 0, sizeof(double), st);
+    return s;
+  }
+  RgpotB200Pot::Pending& pd = pot->pend;
+  pd.active = true;
+  pd.batch = false;
+  pd.n = nAtoms;
+  pd.pos = d_positions;
+  pd.Z = d_atomicNrs;
+  pd.F = d_forces;
+  pd.E = d_energy;
+  pd.st = st;
+  pd.has_box = box != nullptr;
+  if (box) memcpy(pd.box, box, sizeof pd.box);
+  return 0;
+}
+
+// forward declaration (batch device)
+static int batch_sync_status(RgpotB200Pot* pot);
+
+int rgpot_b200_sync_status(RgpotB200Pot* pot) {
+  if (!pot) return kStatusArgs;
+  CU_TRY(pot, cudaSetDevice(pot->device));
+  RgpotB200Pot::Pending& pd = pot->pend;
+  if (!pd.active) {
+    CU_TRY(pot, cudaStreamSynchronize(pot->stream));
+    return 0;
+  }
+  pd.active = false;
+  if (pd.batch) return batch_sync_status(pot);
+  int s = finish_single(pot, pd.n, pd.pos, pd.Z, pd.F, pd.E, pd.has_box ? pd.box : nullptr, pd.st,
+                        nullptr, nullptr);
+  if (s) {
+    cudaMemsetAsync(pd.F, 0, sizeof(double) * 3 * pd.n, pd.st);
+    cudaMemsetAsync(pd.E, 0, sizeof(double), pd.st);
+    cudaStreamSynchronize(pd.st);
+  }
+  return s;
+}
+
+// ------------------------------------------------------------------------------------------------
+// host-buffer single system
+// ------------------------------------------------------------------------------------------------
+int rgpot_b200_force(RgpotB200Pot* pot, long nAtoms, const double* positions, const int* atomicNrs,
+                     double* forces, double* energy, double* variance, const double* box) {
+  if (!pot) return kStatusArgs;
+  pot->last_error.clear();
+  if (variance) *variance = 0.0;
+  if (energy) *energy = 0.0;
+  if (nAtoms > 0 && forces) memset(forces, 0, sizeof(double) * 3 * (size_t)nAtoms);
+  if (!energy || (nAtoms > 0 && (!positions || !forces)))
+    return fail(pot, kStatusArgs, "rgpot_b200_force: null buffer");
+  CU_TRY(pot, cudaSetDevice(pot->device));
+  if (nAtoms < 0 || nAtoms > INT_MAX / 4) return fail(pot, kStatusArgs, "rgpot_b200: bad atom count");
+  const bool eam = pot->cfg.kind == RGPOT_B200_CUH2;
+  const bool trivial = eam ? nAtoms < 1
+                           : (nAtoms < 2 || (pot->cfg.kind == RGPOT_B200_LJ && !(pot->cfg.cutoff > 0.0)));
+  if (trivial) return 0;
+  if (eam && !atomicNrs) return fail(pot, kStatusArgs, "rgpot_b200: CuH2 needs atomic numbers");
+  if ((eam || pot->cfg.kind == RGPOT_B200_LJ) && !box)
+    return fail(pot, kStatusArgs, "rgpot_b200_force: null box");
+  cudaStream_t st = pot->stream;
+  const size_t n = (size_t)nAtoms;
+  CU_TRY(pot, pot->pos.reserve(sizeof(double) * 3 * n));
+  CU_TRY(pot, pot->F.reserve(sizeof(double) * 3 * n));
+  CU_TRY(pot, pot->energy.reserve(sizeof(double)));
+  CU_TRY(pot, cudaMemcpyAsync(pot->pos.p, positions, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, st));
+  const int* d_Z = nullptr;
+  if (eam) {
+    CU_TRY(pot, pot->Z.reserve(sizeof(int) * n));
+    CU_TRY(pot, cudaMemcpyAsync(pot->Z.p, atomicNrs, sizeof(int) * n, cudaMemcpyHostToDevice, st));
+    d_Z = pot->Z.as<int>();
+  }
+  int s = force_device_impl(pot, nAtoms, pot->pos.as<double>(), d_Z, pot->F.as<double>(),
+                            pot->energy.as<double>(), box, st, nullptr, 0);
+  if (s) return s;
+  s = finish_single(pot, nAtoms, pot->pos.as<double>(), d_Z, pot->F.as<double>(),
+                    pot->energy.as<double>(), box, st, positions, atomicNrs);
+  if (s) return s;  // outputs stay zeroed, like the reference
+  CU_TRY(pot, cudaMemcpyAsync(forces, pot->F.p, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost, st));
+  CU_TRY(pot, cudaMemcpyAsync(energy, pot->energy.p, sizeof(double), cudaMemcpyDeviceToHost, st));
+  CU_TRY(pot, cudaStreamSynchronize(st));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// neighbor table inspection
+// ------------------------------------------------------------------------------------------------
+int rgpot_b200_neighbors(RgpotB200Pot* pot, long nAtoms, const double* positions, const int* atomicNrs,
+                         const double* box, int path, long cap, int32_t* pairs, int32_t* shifts,
+                         long* n_out) {
+  if (!pot || !n_out) return kStatusArgs;
+  pot->last_error.clear();
+  *n_out = 0;
+  CU_TRY(pot, cudaSetDevice(pot->device));
+  if (nAtoms < 1) return 0;
+  cudaStream_t st = pot->stream;
+  const size_t n = (size_t)nAtoms;
+  const bool eam = pot->cfg.kind == RGPOT_B200_CUH2;
+  CU_TRY(pot, pot->pos.reserve(sizeof(double) * 3 * n));
+  CU_TRY(pot, pot->F.reserve(sizeof(double) * 3 * n));
+  CU_TRY(pot, pot->energy.reserve(sizeof(double)));
+  CU_TRY(pot, cudaMemcpyAsync(pot->pos.p, positions, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, st));
+  const int* d_Z = nullptr;
+  std::vector<int> fakeZ;
+  if (eam) {
+    CU_TRY(pot, pot->Z.reserve(sizeof(int) * n));
+    if (!atomicNrs) {
+      fakeZ.assign(n, 29);
+      atomicNrs = fakeZ.data();
+    }
+    CU_TRY(pot, cudaMemcpyAsync(pot->Z.p, atomicNrs, sizeof(int) * n, cudaMemcpyHostToDevice, st));
+    d_Z = pot->Z.as<int>();
+  }
+  const size_t capz = (size_t)std::max<long>(cap, 1);
+  CU_TRY(pot, pot->emit_pairs.reserve(sizeof(int32_t) * 2 * capz));
+  CU_TRY(pot, pot->emit_shifts.reserve(sizeof(int32_t) * 3 * capz));
+  CU_TRY(pot, pot->emit_count.reserve(sizeof(unsigned long long)));
+  CU_TRY(pot, cudaMemsetAsync(pot->emit_count.p, 0, sizeof(unsigned long long), st));
+  EmitArgs em{pot->emit_pairs.as<int32_t>(), pot->emit_shifts.as<int32_t>(),
+              pot->emit_count.as<unsigned long long>(), cap};
+  int s = force_device_impl(pot, nAtoms, pot->pos.as<double>(), d_Z, pot->F.as<double>(),
+                            pot->energy.as<double>(), box, st, &em, path);
+  if (s) return s;
+  unsigned long long cnt = 0;
+  CU_TRY(pot, cudaMemcpyAsync(&cnt, pot->emit_count.p, sizeof cnt, cudaMemcpyDeviceToHost, st));
+  CU_TRY(pot, cudaStreamSynchronize(st));
+  *n_out = (long)cnt;
+  const size_t m = (size_t)std::min<unsigned long long>(cnt, (unsigned long long)std::max<long>(cap, 0));
+  if (m > 0 && pairs && shifts) {
+    CU_TRY(pot, cudaMemcpy(pairs, pot->emit_pairs.p, sizeof(int32_t) * 2 * m, cudaMemcpyDeviceToHost));
+    CU_TRY(pot, cudaMemcpy(shifts, pot->emit_shifts.p, sizeof(int32_t) * 3 * m, cudaMemcpyDeviceToHost));
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// batches
+// ------------------------------------------------------------------------------------------------
+// Device-resident packed batch.  offsets: host array (nSystems + 1); d_boxes: device, 9 per system.
+// host copy of one system's box: from the caller's host array when there is one, else from the device
+static int fetch_box(RgpotB200Pot* pot, const double* h_boxes, const double* d_boxes, size_t id,
+                     double* out) {
+  if (h_boxes) {
+    memcpy(out, h_boxes + 9 * id, 9 * sizeof(double));
+    return 0;
+  }
+  CU_TRY(pot, cudaMemcpy(out, d_boxes + 9 * id, 9 * sizeof(double), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+static int batch_device_impl(RgpotB200Pot* pot, size_t nsys, const size_t* offsets, const double* d_pos,
+                             const int* d_Z, const double* d_boxes, const double* h_boxes,
+                             double* d_F, double* d_E, cudaStream_t st) {
+  const int kind = pot->cfg.kind;
+  const bool eam = kind == RGPOT_B200_CUH2;
+  // plan: which systems fit the all-pairs kernel
+  long nmax_small = 0;
+  std::vector<int> small_ids, big_ids;
+  small_ids.reserve(nsys);
+  for (size_t s = 0; s < nsys; ++s) {
+    const long n = (long)(offsets[s + 1] - offsets[s]);
+    if (pot->forced_path != 1 && small_eligible(pot, n)) {
+      small_ids.push_back((int)s);
+      nmax_small = std::max(nmax_small, n);
+    } else {
+      big_ids.push_back((int)s);
+    }
+  }
+  CU_TRY(pot, pot->b_off.reserve(sizeof(long long) * (nsys + 1)));
+  CU_TRY(pot, pot->h_off.reserve(sizeof(long long) * (nsys + 1)));
+  CU_TRY(pot, pot->b_flags.reserve(sizeof(unsigned) * nsys));
+  CU_TRY(pot, pot->b_bad.reserve(sizeof(int) * 2 * nsys));
+  long long* ho = pot->h_off.as<long long>();
+  for (size_t s = 0; s <= nsys; ++s) ho[s] = (long long)offsets[s];
+  CU_TRY(pot, cudaMemcpyAsync(pot->b_off.p, ho, sizeof(long long) * (nsys + 1), cudaMemcpyHostToDevice, st));
+  CU_TRY(pot, cudaMemsetAsync(pot->b_flags.p, 0, sizeof(unsigned) * nsys, st));
+
+  if (!small_ids.empty()) {
+    const int maxnb = eam ? eam_small_maxnb(pot, nmax_small) : 0;
+    if (small_ids.size() == nsys) {
+      int s = launch_small(pot, nsys, nmax_small, pot->b_off.as<long long>(), d_boxes, d_pos, d_Z, d_F,
+                           d_E, pot->b_flags.as<unsigned>(), pot->b_bad.as<int>(), maxnb, st, nullptr);
+      if (s) return s;
+    } else {
+      // per-system launches for the small members of a mixed batch (rare)
+      for (int id : small_ids) {
+        const long n = (long)(offsets[id + 1] - offsets[id]);
+        int s = launch_small(pot, 1, n, pot->b_off.as<long long>() + id, d_boxes + 9 * (size_t)id, d_pos,
+                             d_Z, d_F, d_E + id, pot->b_flags.as<unsigned>() + id,
+                             pot->b_bad.as<int>() + 2 * (size_t)id, maxnb, st, nullptr);
+        if (s) return s;
+      }
+    }
+  }
+  // big systems: one cell-list pass each (status folded into the per-system flag array)
+  for (int id : big_ids) {
+    const long n = (long)(offsets[id + 1] - offsets[id]);
+    const size_t o = offsets[id];
+    const bool trivial = eam ? n < 1 : (n < 2 || (kind == RGPOT_B200_LJ && !(pot->cfg.cutoff > 0.0)));
+    if (trivial) {
+      if (n > 0) CU_TRY(pot, cudaMemsetAsync(d_F + 3 * o, 0, sizeof(double) * 3 * n, st));
+      CU_TRY(pot, cudaMemsetAsync(d_E + id, 0, sizeof(double), st));
+      continue;
+    }
+    double hbox[9];
+    int s = fetch_box(pot, h_boxes, d_boxes, (size_t)id, hbox);
+    if (s) return s;
+    s = run_cell_path(pot, n, d_pos + 3 * o, d_Z ? d_Z + o : nullptr, d_F + 3 * o, d_E + id, hbox, st,
+                      nullptr);
+    if (s == 1) {
+      // singular box of one member: record, keep going
+      unsigned f = kFlagNonFinite;
+      CU_TRY(pot, cudaMemcpyAsync(pot->b_flags.as<unsigned>() + id, &f, sizeof f, cudaMemcpyHostToDevice, st));
+      continue;
+    }
+    if (s) return s;
+    // fold the single-system Status into the per-system arrays
+    CU_TRY(pot, cudaMemcpyAsync(pot->b_flags.as<unsigned>() + id, pot->status.p, sizeof(unsigned),
+                                cudaMemcpyDeviceToDevice, st));
+    CU_TRY(pot, cudaMemcpyAsync(pot->b_bad.as<int>() + 2 * (size_t)id,
+                                (char*)pot->status.p + offsetof(Status, first_bad_atom), sizeof(int),
+                                cudaMemcpyDeviceToDevice, st));
+    // the status buffer is reused by the next system: order is kept by the stream
+  }
+  return 0;
+}
+
+// After a batch ran: read flags, rerun list-overflow systems on the cell path, produce statuses.
+// Returns the first non-zero status.  h_* describe where the data of the batch lives.
+static int batch_finish(RgpotB200Pot* pot, size_t nsys, const size_t* offsets, const double* d_pos,
+                        const int* d_Z, const double* h_boxes, const double* d_boxes, double* d_F,
+                        double* d_E,
+                        cudaStream_t st, const double* host_pos, const int* host_Z, int* statuses) {
+  CU_TRY(pot, pot->h_flags.reserve(sizeof(unsigned) * nsys));
+  CU_TRY(pot, pot->h_bad.reserve(sizeof(int) * 2 * nsys));
+  unsigned* hf = pot->h_flags.as<unsigned>();
+  int* hb = pot->h_bad.as<int>();
+  CU_TRY(pot, cudaMemcpyAsync(hf, pot->b_flags.p, sizeof(unsigned) * nsys, cudaMemcpyDeviceToHost, st));
+  CU_TRY(pot, cudaMemcpyAsync(hb, pot->b_bad.p, sizeof(int) * 2 * nsys, cudaMemcpyDeviceToHost, st));
+  CU_TRY(pot, cudaStreamSynchronize(st));
+  int first = 0;
+  std::string first_msg;
+  for (size_t s = 0; s < nsys; ++s) {
+    unsigned f = hf[s];
+    const long n = (long)(offsets[s + 1] - offsets[s]);
+    const size_t o = offsets[s];
+    int bad = hb[2 * s], badz = hb[2 * s + 1];
+    if (f & kFlagListOverflow) {
+      double hbox[9];
+      int rs = fetch_box(pot, h_boxes, d_boxes, s, hbox);
+      if (rs) return rs;
+      rs = run_cell_path(pot, n, d_pos + 3 * o, d_Z ? d_Z + o : nullptr, d_F + 3 * o, d_E + s, hbox, st,
+                         nullptr);
+      if (rs >= kStatusCuda) return rs;
+      Status stt{};
+      if (rs == 0) {
+        CU_TRY(pot, cudaMemcpyAsync(&stt, pot->status.p, sizeof stt, cudaMemcpyDeviceToHost, st));
+        CU_TRY(pot, cudaStreamSynchronize(st));
+        f = stt.flags;
+        bad = stt.first_bad_atom;
+      } else {
+        f = kFlagNonFinite;
+      }
+    }
+    int status = 0;
+    if (f & ~(kFlagAtomShift)) {
+      if ((f & kFlagForeignZ) && bad != INT_MAX && bad >= 0) {
+        if (host_Z) {
+          badz = host_Z[o + bad];
+        } else if (d_Z) {
+          CU_TRY(pot, cudaMemcpy(&badz, d_Z + o + bad, sizeof(int), cudaMemcpyDeviceToHost));
+        }
+      }
+      status = map_flags(pot, f, bad, badz, host_pos ? host_pos + 3 * o : nullptr);
+      if (status) {
+        if (n > 0) CU_TRY(pot, cudaMemsetAsync(d_F + 3 * o, 0, sizeof(double) * 3 * n, st));
+        CU_TRY(pot, cudaMemsetAsync(d_E + s, 0, sizeof(double), st));
+        if (!first) {
+          first = status;
+          char pre[64];
+          snprintf(pre, sizeof pre, "system %zu: ", s);
+          first_msg = pre + pot->last_error;
+        }
+      }
+    }
+    if (statuses) statuses[s] = status;
+  }
+  if (first) pot->last_error = first_msg;
+  return first;
+}
+
+int rgpot_b200_force_batch_device(RgpotB200Pot* pot, size_t nSystems, const size_t* offsets,
+                                  const double* d_positions, const int* d_atomicNrs,
+                                  const double* d_boxes, double* d_forces, double* d_energies,
+                                  void* cuda_stream) {
+  if (!pot) return kStatusArgs;
+  pot->last_error.clear();
+  pot->pend.active = false;
+  if (nSystems == 0) return 0;
+  if (!offsets || !d_boxes || !d_positions || !d_forces || !d_energies)
+    return fail(pot, kStatusArgs, "rgpot_b200_force_batch_device: null buffer");
+  if (pot->cfg.kind == RGPOT_B200_CUH2 && !d_atomicNrs)
+    return fail(pot, kStatusArgs, "rgpot_b200: CuH2 needs atomic numbers");
+  CU_TRY(pot, cudaSetDevice(pot->device));
+  cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : pot->stream;
+  int s = batch_device_impl(pot, nSystems, offsets, d_positions, d_atomicNrs, d_boxes, nullptr, d_forces,
+                            d_energies, st);
+  if (s) return s;
+  RgpotB200Pot::Pending& pd = pot->pend;
+  pd.active = true;
+  pd.batch = true;
+  pd.nsys = nSystems;
+  pd.offsets.assign(offsets, offsets + nSystems + 1);
+  pd.pos = d_positions;
+  pd.Z = d_atomicNrs;
+  pd.F = d_forces;
+  pd.E = d_energies;
+  pd.d_boxes = d_boxes;
+  pd.st = st;
+  return 0;
+}
+
+static int batch_sync_status(RgpotB200Pot* pot) {
+  RgpotB200Pot::Pending& pd = pot->pend;
+  int s = batch_finish(pot, pd.nsys, pd.offsets.data(), pd.pos, pd.Z, nullptr, pd.d_boxes, pd.F, pd.E,
+                       pd.st, nullptr, nullptr, nullptr);
+  cudaStreamSynchronize(pd.st);
+  return s;
+}
+
+int rgpot_b200_force_batch_packed(RgpotB200Pot* pot, size_t nSystems, const size_t* offsets,
+                                  const double* positions, const int* atomicNrs, const double* boxes,
+                                  double* forces, double* energies, int* statuses) {
+  if (!pot) return kStatusArgs;
+  pot->last_error.clear();
+  if (nSystems == 0) return 0;
+  if (!offsets || !positions || !boxes || !forces || !energies)
+    return fail(pot, kStatusArgs, "rgpot_b200_force_batch_packed: null buffer");
+  const bool eam = pot->cfg.kind == RGPOT_B200_CUH2;
+  if (eam && !atomicNrs) return fail(pot, kStatusArgs, "rgpot_b200: CuH2 needs atomic numbers");
+  CU_TRY(pot, cudaSetDevice(pot->device));
+  cudaStream_t st = pot->stream;
+  const size_t base = offsets[0];
+  const size_t total = offsets[nSystems] - base;
+  std::vector<size_t> rel(nSystems + 1);
+  for (size_t s = 0; s <= nSystems; ++s) rel[s] = offsets[s] - base;
+  CU_TRY(pot, pot->b_pos.reserve(sizeof(double) * 3 * std::max<size_t>(total, 1)));
+  CU_TRY(pot, pot->b_F.reserve(sizeof(double) * 3 * std::max<size_t>(total, 1)));
+  CU_TRY(pot, pot->b_E.reserve(sizeof(double) * nSystems));
+  CU_TRY(pot, pot->b_boxes.reserve(sizeof(double) * 9 * nSystems));
+  CU_TRY(pot, cudaMemcpyAsync(pot->b_pos.p, positions + 3 * base, sizeof(double) * 3 * total,
+                              cudaMemcpyHostToDevice, st));
+  const int* d_Z = nullptr;
+  if (eam) {
+    CU_TRY(pot, pot->b_Z.reserve(sizeof(int) * std::max<size_t>(total, 1)));
+    CU_TRY(pot, cudaMemcpyAsync(pot->b_Z.p, atomicNrs + base, sizeof(int) * total, cudaMemcpyHostToDevice, st));
+    d_Z = pot->b_Z.as<int>();
+  }
+  CU_TRY(pot, cudaMemcpyAsync(pot->b_boxes.p, boxes, sizeof(double) * 9 * nSystems, cudaMemcpyHostToDevice, st));
+  int s = batch_device_impl(pot, nSystems, rel.data(), pot->b_pos.as<double>(), d_Z,
+                            pot->b_boxes.as<double>(), boxes, pot->b_F.as<double>(), pot->b_E.as<double>(), st);
+  if (s) return s;
+  s = batch_finish(pot, nSystems, rel.data(), pot->b_pos.as<double>(), d_Z, boxes,
+                   pot->b_boxes.as<double>(), pot->b_F.as<double>(), pot->b_E.as<double>(), st, positions + 3 * base, atomicNrs ? atomicNrs + base : nullptr,
+                   statuses);
+  if (s >= kStatusCuda) return s;
+  CU_TRY(pot, cudaMemcpyAsync(forces + 3 * base, pot->b_F.p, sizeof(double) * 3 * total,
+                              cudaMemcpyDeviceToHost, st));
+  CU_TRY(pot, cudaMemcpyAsync(energies, pot->b_E.p, sizeof(double) * nSystems, cudaMemcpyDeviceToHost, st));
+  CU_TRY(pot, cudaStreamSynchronize(st));
+  return s;
+}
+
+int rgpot_b200_force_batch(RgpotB200Pot* pot, size_t nSystems, const size_t* nAtoms,
+                           const double* const* positions, const int* const* atomicNrs,
+                           const double* const* boxes, double* const* forces, double* energies,
+                           int* statuses) {
+  if (!pot) return kStatusArgs;
+  pot->last_error.clear();
+  if (nSystems == 0) return 0;
+  if (!nAtoms || !positions || !forces || !energies)
+    return fail(pot, kStatusArgs, "rgpot_b200_force_batch: null buffer");
+  const bool eam = pot->cfg.kind == RGPOT_B200_CUH2;
+  if (eam && !atomicNrs) return fail(pot, kStatusArgs, "rgpot_b200: CuH2 needs atomic numbers");
+  CU_TRY(pot, cudaSetDevice(pot->device));
+  std::vector<size_t> off(nSystems + 1, 0);
+  for (size_t s = 0; s < nSystems; ++s) off[s + 1] = off[s] + nAtoms[s];
+  const size_t total = off[nSystems];
+  // gather into pinned staging (ForceBatch buffers are independent allocations in general)
+  CU_TRY(pot, pot->h_pos.reserve(sizeof(double) * 3 * std::max<size_t>(total, 1)));
+  CU_TRY(pot, pot->h_F.reserve(sizeof(double) * 3 * std::max<size_t>(total, 1)));
+  CU_TRY(pot, pot->h_boxes.reserve(sizeof(double) * 9 * nSystems));
+  CU_TRY(pot, pot->h_E.reserve(sizeof(double) * nSystems));
+  if (eam) CU_TRY(pot, pot->h_Z.reserve(sizeof(int) * std::max<size_t>(total, 1)));
+  double* hp = pot->h_pos.as<double>();
+  double* hbx = pot->h_boxes.as<double>();
+  int* hz = pot->h_Z.as<int>();
+  static const double free_box[9] = {1e6, 0, 0, 0, 1e6, 0, 0, 0, 1e6};
+  for (size_t s = 0; s < nSystems; ++s) {
+    if (nAtoms[s] > 0) {
+      if (!positions[s] || !forces[s]) return fail(pot, kStatusArgs, "rgpot_b200_force_batch: null system buffer");
+      memcpy(hp + 3 * off[s], positions[s], sizeof(double) * 3 * nAtoms[s]);
+      if (eam) {
+        if (!atomicNrs[s]) return fail(pot, kStatusArgs, "rgpot_b200: CuH2 needs atomic numbers");
+        memcpy(hz + off[s], atomicNrs[s], sizeof(int) * nAtoms[s]);
+      }
+    }
+    const double* b = (boxes && boxes[s]) ? boxes[s] : free_box;
+    memcpy(hbx + 9 * s, b, sizeof(double) * 9);
+  }
+  int st = rgpot_b200_force_batch_packed(pot, nSystems, off.data(), hp, eam ? hz : nullptr, hbx,
+                                         pot->h_F.as<double>(), pot->h_E.as<double>(), statuses);
+  if (st >= kStatusCuda) return st;
+  const double* hF = pot->h_F.as<double>();
+  const double* hE = pot->h_E.as<double>();
+  for (size_t s = 0; s < nSystems; ++s) {
+    if (nAtoms[s] > 0) memcpy(forces[s], hF + 3 * off[s], sizeof(double) * 3 * nAtoms[s]);
+    energies[s] = hE[s];
+  }
+  return st;
+}
+
+// ------------------------------------------------------------------------------------------------
+// exact drop-in for the Fortran entry (FortranPots.cc:33-40): process-wide default handle,
+// thread-local error text (rgpot_ferror.f90 keeps one process-global buffer).
+// ------------------------------------------------------------------------------------------------
+static std::mutex g_cuh2_mu;
+static RgpotB200Pot* g_cuh2 = nullptr;
+static thread_local std::string g_last_fortran_error;
+
+int rgpot_cuh2_force(int32_t natoms, const double* positions, const int32_t* atomic_numbers,
+                     const double* cell, double* forces, double* energy) {
+  std::lock_guard<std::mutex> lk(g_cuh2_mu);
+  g_last_fortran_error.clear();
+  if (!g_cuh2) {
+    RgpotB200Config cfg;
+    rgpot_b200_default_config(RGPOT_B200_CUH2, &cfg);
+    char err[256] = {0};
+    g_cuh2 = rgpot_b200_create(&cfg, err, sizeof err);
+    if (!g_cuh2) {
+      g_last_fortran_error = err;
+      if (energy) *energy = 0.0;
+      if (forces && natoms > 0) memset(forces, 0, sizeof(double) * 3 * (size_t)natoms);
+      return kStatusCuda;
+    }
+  }
+  int s = rgpot_b200_force(g_cuh2, natoms, positions, atomic_numbers, forces, energy, nullptr, cell);
+  if (s) g_last_fortran_error = g_cuh2->last_error;
+  return s;
+}
+
+int rgpot_fortran_last_error(char* buffer, int buffer_len) {
+  if (!buffer || buffer_len <= 0) return 0;
+  const int n = (int)std::min<size_t>(g_last_fortran_error.size(), (size_t)buffer_len - 1);
+  memcpy(buffer, g_last_fortran_error.data(), n);
+  buffer[n] = 0;
+  return n;
+}
+
+}  // extern "C"

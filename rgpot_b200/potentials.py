@@ -1,0 +1,380 @@
+"""Host-side mirror of the reference's potential interface, on top of the engine's C ABI.
+
+Names, argument meaning and error behaviour follow the reference:
+
+* ``LJPot`` / ``LJClusterPot`` / ``CuH2Pot`` -- ``Potential<D>::operator()(positions, atmtypes,
+  box) -> (energy, forces, variance)`` (CppCore/rgpot/Potential.hpp:165-211), constructed from
+  the same plain config aggregates (LJPot.hpp:30-34, LJClusterPot.hpp:34-38).
+* ``forceBatch`` -- ``PotentialBase::forceBatch(const ForceBatch&)`` (Potential.hpp:89-91,
+  251-312); here it is native (``caps().batched`` is True).
+* ``evaluate_lj`` / ``LJPot.__call__`` -- the nanobind module surface
+  (python/bind/bind_module.cpp:84-96, 160-173): shape errors raise ``ValueError``, outputs are
+  fresh numpy arrays.
+* failures of the CuH2 kernel raise ``RuntimeError("CuH2 potential failed (status k): msg")``
+  like CppCore/rgpot/fortran/FortranPots.cc:44-56.
+
+The compute is entirely in the CUDA engine; this module only marshals numpy / torch buffers.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import struct
+from dataclasses import dataclass
+from enum import Enum
+
+import numpy as np
+
+from . import _lib
+
+
+# ----------------------------------------------------------------------------- capabilities
+class Reentrancy(Enum):
+    """CppCore/rgpot/pot_caps.hpp:20-29"""
+
+    SharedInstance = 0
+    PerInstance = 1
+    ProcessSerial = 2
+
+
+@dataclass(frozen=True)
+class PotCaps:
+    """CppCore/rgpot/pot_caps.hpp:34-45"""
+
+    reentrancy: Reentrancy = Reentrancy.SharedInstance
+    perImageInstances: bool = False
+    batched: bool = False
+    periodic: bool = True
+
+
+class PotType(Enum):
+    """The three members of CppCore/rgpot/pot_types.hpp:26-45 this engine serves."""
+
+    CuH2 = 1
+    LJ = 2
+    LJCluster = 9
+
+
+@dataclass
+class LJConfig:
+    """LJPot.hpp:30-34"""
+
+    u0: float = 1.0
+    cutoff: float = 15.0
+    psi: float = 1.0
+
+
+@dataclass
+class LJClusterConfig:
+    """LJClusterPot.hpp:34-38"""
+
+    u0: float = 1.0
+    cutoff: float = 15.0
+    psi: float = 1.0
+
+
+class PotentialError(RuntimeError):
+    def __init__(self, label: str, status: int, message: str):
+        text = f"{label} potential failed (status {status})"
+        if message:
+            text += ": " + message
+        super().__init__(text)
+        self.status = status
+        self.message = message
+
+
+# kernel-version salt mixed into paramsKey (ParamHash.hpp:19-51, LJPot.hpp:54-59): a different
+# value from the reference's CPU kernels (1) so a shared result cache never mixes the two.
+_KERNEL_VERSION = 0xB2000001
+
+
+def _fnv1a(chunks) -> int:
+    h = 0xCBF29CE484222325
+    for chunk in chunks:
+        for b in chunk:
+            h ^= b
+            h = (h * 0x100000001B3) & 0xFFFFFFFFFFFFFFFF
+    return h
+
+
+def _as_positions(positions) -> np.ndarray:
+    arr = np.asarray(positions)
+    if arr.ndim != 2 or arr.shape[1] != 3:
+        raise ValueError("positions must have shape (n_atoms, 3)")
+    return np.ascontiguousarray(arr, dtype=np.float64)
+
+
+def _as_types(atom_types, n: int) -> np.ndarray:
+    arr = np.asarray(atom_types)
+    if arr.ndim != 1 or arr.shape[0] != n:
+        raise ValueError("atom_types length must match n_atoms")
+    return np.ascontiguousarray(arr, dtype=np.int32)
+
+
+def _as_box(box) -> np.ndarray:
+    arr = np.asarray(box)
+    if arr.ndim != 2 or arr.shape != (3, 3):
+        raise ValueError("box must have shape (3, 3)")
+    return np.ascontiguousarray(arr, dtype=np.float64)
+
+
+class _EnginePot:
+    """One engine handle (one CUDA device, one stream, private scratch)."""
+
+    _kind = _lib.KIND_LJ
+    _label = "LJ"
+    _type = PotType.LJ
+
+    def __init__(self, u0=1.0, cutoff=15.0, psi=1.0, device: int = -1, lj_all_images: bool = False):
+        self._lib = _lib.lib()
+        cfg = _lib.Config()
+        self._lib.rgpot_b200_default_config(self._kind, C.byref(cfg))
+        cfg.device = int(device)
+        if self._kind != _lib.KIND_CUH2:
+            cfg.u0, cfg.cutoff, cfg.psi = float(u0), float(cutoff), float(psi)
+            cfg.lj_all_images = int(bool(lj_all_images))
+        self._cfg = cfg
+        err = C.create_string_buffer(512)
+        self._h = self._lib.rgpot_b200_create(C.byref(cfg), err, 512)
+        if not self._h:
+            raise RuntimeError(err.value.decode() or "rgpot_b200_create failed")
+        self.force_calls = 0  # registry<T>::forceCalls (PotHelpers.hpp:31-34)
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            self._lib.rgpot_b200_destroy(h)
+            self._h = None
+
+    # -- interface mirror ---------------------------------------------------------------------
+    def get_type(self) -> PotType:
+        return self._type
+
+    def caps(self) -> PotCaps:
+        return PotCaps(reentrancy=Reentrancy.PerInstance, batched=True,
+                       periodic=self._kind != _lib.KIND_LJ_CLUSTER)
+
+    def paramsKey(self) -> int:
+        if self._kind == _lib.KIND_CUH2:
+            return _fnv1a([struct.pack("<Q", _KERNEL_VERSION)])
+        c = self._cfg
+        return _fnv1a([struct.pack("<Q", _KERNEL_VERSION), struct.pack("<d", c.u0),
+                       struct.pack("<d", c.cutoff), struct.pack("<d", c.psi)])
+
+    def _last_error(self) -> str:
+        buf = C.create_string_buffer(512)
+        self._lib.rgpot_b200_last_error(self._h, buf, 512)
+        return buf.value.decode()
+
+    def _raise(self, status: int):
+        raise PotentialError(self._label, status, self._last_error())
+
+    def set_path(self, path: int) -> None:
+        """0 automatic, 1 cell-list kernels, 2 all-pairs kernels (test hook)."""
+        self._lib.rgpot_b200_set_option(self._h, b"path", int(path))
+
+    def launch_count(self) -> int:
+        return int(self._lib.rgpot_b200_launch_count(self._h))
+
+    def __call__(self, positions, atom_types, box):
+        pos = _as_positions(positions)
+        types = _as_types(atom_types, pos.shape[0])
+        cell = _as_box(box)
+        forces = np.zeros_like(pos)
+        e, v = C.c_double(0.0), C.c_double(0.0)
+        st = self._lib.rgpot_b200_force(self._h, pos.shape[0], pos.ctypes.data, types.ctypes.data,
+                                        forces.ctypes.data, C.byref(e), C.byref(v), cell.ctypes.data)
+        if st != 0:
+            self._raise(st)
+        self.force_calls += 1
+        return e.value, forces, v.value
+
+    def forceImpl(self, positions, atom_types, box):
+        e, f, _ = self(positions, atom_types, box)
+        return e, f
+
+    def forceBatch(self, systems, return_statuses: bool = False):
+        """systems: sequence of (positions, atom_types, box).  Returns [(energy, forces, variance)].
+
+        Native batch: one engine call, independent systems of any sizes (ForceStructs.hpp:39-54).
+        """
+        n = len(systems)
+        if n == 0:
+            return []
+        pos = [_as_positions(s[0]) for s in systems]
+        typ = [_as_types(s[1], p.shape[0]) for s, p in zip(systems, pos)]
+        box = [_as_box(s[2]) for s in systems]
+        frc = [np.zeros_like(p) for p in pos]
+        natoms = (C.c_size_t * n)(*[p.shape[0] for p in pos])
+        pp = (C.c_void_p * n)(*[p.ctypes.data for p in pos])
+        zz = (C.c_void_p * n)(*[t.ctypes.data for t in typ])
+        bb = (C.c_void_p * n)(*[b.ctypes.data for b in box])
+        ff = (C.c_void_p * n)(*[f.ctypes.data for f in frc])
+        energies = np.zeros(n)
+        statuses = np.zeros(n, dtype=np.int32)
+        st = self._lib.rgpot_b200_force_batch(self._h, n, natoms, pp, zz, bb, ff, energies.ctypes.data,
+                                              statuses.ctypes.data)
+        if st != 0 and not return_statuses:
+            self._raise(st)
+        self.force_calls += n
+        out = [(float(energies[i]), frc[i], 0.0) for i in range(n)]
+        return (out, statuses) if return_statuses else out
+
+    def forceBatchPacked(self, offsets, positions, atom_types, boxes, forces=None, energies=None,
+                         statuses=None):
+        """Back-to-back layout (rgpot_b200_force_batch_packed); buffers may be pinned arrays from
+        ``pinned_empty``.  Returns (energies, forces)."""
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        nsys = len(offsets) - 1
+        total = int(offsets[-1])
+        positions = np.ascontiguousarray(positions, dtype=np.float64)
+        boxes = np.ascontiguousarray(boxes, dtype=np.float64)
+        if atom_types is not None:
+            atom_types = np.ascontiguousarray(atom_types, dtype=np.int32)
+        if forces is None:
+            forces = np.zeros((total, 3))
+        if energies is None:
+            energies = np.zeros(nsys)
+        st = self._lib.rgpot_b200_force_batch_packed(
+            self._h, nsys, offsets.ctypes.data, positions.ctypes.data,
+            atom_types.ctypes.data if atom_types is not None else None, boxes.ctypes.data,
+            forces.ctypes.data, energies.ctypes.data,
+            statuses.ctypes.data if statuses is not None else None)
+        if st != 0 and statuses is None:
+            self._raise(st)
+        self.force_calls += nsys
+        return energies, forces
+
+    # -- device-resident entry points (torch CUDA tensors carry the memory) ---------------------
+    def force_device(self, d_pos, d_Z, box, d_F, d_E, stream=None, sync: bool = True):
+        cell = _as_box(box)
+        s = self._lib.rgpot_b200_force_device(
+            self._h, int(d_pos.shape[0]), d_pos.data_ptr(), d_Z.data_ptr() if d_Z is not None else None,
+            d_F.data_ptr(), d_E.data_ptr(), cell.ctypes.data, stream)
+        if s != 0:
+            self._raise(s)
+        if sync:
+            s = self._lib.rgpot_b200_sync_status(self._h)
+            if s != 0:
+                self._raise(s)
+
+    def force_batch_device(self, offsets, d_pos, d_Z, d_boxes, d_F, d_E, stream=None):
+        """Enqueue only; call ``sync_status`` to collect the status."""
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        s = self._lib.rgpot_b200_force_batch_device(
+            self._h, len(offsets) - 1, offsets.ctypes.data, d_pos.data_ptr(),
+            d_Z.data_ptr() if d_Z is not None else None, d_boxes.data_ptr(), d_F.data_ptr(),
+            d_E.data_ptr(), stream)
+        if s != 0:
+            self._raise(s)
+
+    def sync_status(self) -> int:
+        return int(self._lib.rgpot_b200_sync_status(self._h))
+
+    # -- neighbor table --------------------------------------------------------------------------
+    def neighbors(self, positions, atom_types, box, path: int = 0):
+        """(pairs (m, 2), shifts (m, 3)) of the table the kernels act on, unspecified order."""
+        pos = _as_positions(positions)
+        cell = _as_box(box)
+        types = None if atom_types is None else _as_types(atom_types, pos.shape[0])
+        n_out = C.c_long(0)
+        cap = max(1024, 160 * pos.shape[0])
+        while True:
+            pairs = np.zeros((cap, 2), dtype=np.int32)
+            shifts = np.zeros((cap, 3), dtype=np.int32)
+            st = self._lib.rgpot_b200_neighbors(
+                self._h, pos.shape[0], pos.ctypes.data, types.ctypes.data if types is not None else None,
+                cell.ctypes.data, int(path), cap, pairs.ctypes.data, shifts.ctypes.data, C.byref(n_out))
+            if st != 0:
+                self._raise(st)
+            if n_out.value <= cap:
+                return pairs[: n_out.value], shifts[: n_out.value]
+            cap = int(n_out.value)
+
+
+class LJPot(_EnginePot):
+    """Shifted 12-6 Lennard-Jones, periodic, orthorhombic nearest image (LJPot.hpp:40-86)."""
+
+    _kind, _label, _type = _lib.KIND_LJ, "LJ", PotType.LJ
+
+    def __init__(self, config: LJConfig | None = None, device: int = -1, all_images: bool = False):
+        c = config or LJConfig()
+        self._config = c
+        super().__init__(c.u0, c.cutoff, c.psi, device, all_images)
+
+    def config(self) -> LJConfig:
+        return self._config
+
+
+class LJClusterPot(_EnginePot):
+    """Free-boundary shifted 12-6 Lennard-Jones (LJClusterPot.hpp:47-100)."""
+
+    _kind, _label, _type = _lib.KIND_LJ_CLUSTER, "LJCluster", PotType.LJCluster
+
+    def __init__(self, config: LJClusterConfig | None = None, device: int = -1):
+        c = config or LJClusterConfig()
+        self._config = c
+        super().__init__(c.u0, c.cutoff, c.psi, device)
+
+    def config(self) -> LJClusterConfig:
+        return self._config
+
+
+class CuH2Pot(_EnginePot):
+    """Cu-H embedded-atom potential (fortranpots::CuH2Pot, FortranPots.hpp:29-45)."""
+
+    _kind, _label, _type = _lib.KIND_CUH2, "CuH2", PotType.CuH2
+
+    def __init__(self, device: int = -1):
+        super().__init__(device=device)
+
+
+# -------------------------------------------------------------------- module-level functions
+_DEFAULT = {}
+
+
+def _default(cls):
+    if cls not in _DEFAULT:
+        _DEFAULT[cls] = cls()
+    return _DEFAULT[cls]
+
+
+def evaluate_lj(positions, atom_types, box):
+    """python/bind/bind_module.cpp:84-96 -- (energy, forces (n, 3), variance), default LJConfig."""
+    pos = np.asarray(positions)
+    typ = np.asarray(atom_types)
+    cell = np.asarray(box)
+    if pos.ndim != 2 or typ.ndim != 1 or cell.ndim != 2:
+        raise ValueError("evaluate_lj expects positions (n,3), atom_types (n,), box (3,3)")
+    return _default(LJPot)(pos, typ, cell)
+
+
+def evaluate_cuh2(positions, atom_types, box):
+    """Same call shape for the CuH2 EAM (the reference module exposes LJ only)."""
+    return _default(CuH2Pot)(positions, atom_types, box)
+
+
+def pinned_empty(shape, dtype=np.float64) -> np.ndarray:
+    """numpy array on page-locked memory from rgpot_b200_host_alloc (kept alive by the array)."""
+    lib = _lib.lib()
+    dtype = np.dtype(dtype)
+    count = int(np.prod(shape))
+    nbytes = max(count * dtype.itemsize, 1)
+    ptr = lib.rgpot_b200_host_alloc(nbytes)
+    if not ptr:
+        raise MemoryError("rgpot_b200_host_alloc failed")
+
+    class _Owner:
+        def __init__(self, p):
+            self.p = p
+
+        def __del__(self):
+            lib.rgpot_b200_host_free(self.p)
+
+    buf = (C.c_char * nbytes).from_address(ptr)
+    buf._owner = _Owner(ptr)
+    arr = np.frombuffer(buf, dtype=dtype, count=count).reshape(shape)
+    return arr
+
+
+def measure_fp64_tflops(device: int = -1, iters: int = 20000) -> float:
+    return float(_lib.lib().rgpot_b200_measure_fp64_tflops(device, iters))

@@ -1,0 +1,69 @@
+"""The C-ABI library loads and exports every symbol include/rgpot_b200.h declares (no compute)."""
+import os
+import re
+
+import pytest
+
+from rgpot_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def engine():
+    if not os.path.exists(_lib.LIB_PATH):
+        _lib.build()
+    return _lib.lib()
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "rgpot_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"RGPOT_B200_API\s+[^;(]*?\b(rgpot_\w+)\s*\(", text)))
+
+
+def test_header_symbols_are_exported(engine):
+    names = declared_symbols()
+    assert len(names) >= 20
+    for name in names:
+        assert hasattr(engine, name), f"{name} declared in rgpot_b200.h but not exported"
+    assert set(names) == {s[0] for s in _lib.SYMBOLS}, "python binding table out of sync with the header"
+
+
+def test_abi_version_and_defaults(engine):
+    assert engine.rgpot_b200_abi_version() == 1
+    cfg = _lib.Config()
+    engine.rgpot_b200_default_config(_lib.KIND_LJ, cfg)
+    assert (cfg.u0, cfg.cutoff, cfg.psi, cfg.device) == (1.0, 15.0, 1.0, -1)  # LJPot.hpp:30-34
+    engine.rgpot_b200_default_config(_lib.KIND_CUH2, cfg)
+    assert cfg.cutoff == 6.1  # rgpot_cuh2.f90:100
+
+
+def test_fortran_dropin_symbols_present(engine):
+    # the exact names FortranPots.cc:33-40 binds
+    assert hasattr(engine, "rgpot_cuh2_force") and hasattr(engine, "rgpot_fortran_last_error")
+
+
+def test_no_cpu_fallback_without_gpu(engine):
+    """Without a usable device the engine refuses to create a handle (it must not compute)."""
+    if engine.rgpot_b200_available() > 0:
+        pytest.skip("a GPU is present")
+    import ctypes as C
+    cfg = _lib.Config()
+    engine.rgpot_b200_default_config(_lib.KIND_LJ, cfg)
+    err = C.create_string_buffer(256)
+    assert not engine.rgpot_b200_create(cfg, err, 256)
+    assert b"no CPU fallback" in err.value
+    import rgpot_b200
+    with pytest.raises(RuntimeError):
+        rgpot_b200.LJPot()
+
+
+def test_engine_sources_do_not_touch_the_oracle():
+    """Product code must never import, link or call anything under oracle/."""
+    pkg = os.path.join(ROOT, "rgpot_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cc", "Makefile")):
+                text = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert "pyoracle" not in text and "liboracle" not in text and "oracle/" not in text, f

@@ -1,0 +1,380 @@
+"""Parity of the CUDA path against the CPU oracle and the committed golden fixtures.
+
+Everything here calls the product through its C ABI (rgpot_b200 -> librgpot_b200.so) on a B200.
+Tolerances (BASELINE.json north_star): neighbor pair sets bit-exact; FP64 energies within 1e-10
+relative; forces within 1e-10 relative / 1e-9 eV/A absolute.
+"""
+import numpy as np
+import pytest
+
+import rgpot_b200
+from rgpot_b200 import workloads
+
+pytestmark = pytest.mark.gpu
+
+E_RTOL = 1e-10
+F_RTOL, F_ATOL = 1e-10, 1e-9
+
+
+def assert_energy(e, ref):
+    assert abs(e - ref) <= E_RTOL * abs(ref) + 1e-12, (e, ref)
+
+
+def assert_forces(f, ref):
+    assert f.shape == ref.shape
+    err = np.abs(f - ref)
+    assert (err <= F_ATOL + F_RTOL * np.abs(ref)).all(), float(err.max())
+
+
+def canon(pairs, shifts):
+    rec = np.column_stack([pairs.astype(np.int64), shifts.astype(np.int64)])
+    if len(rec) == 0:
+        return rec.reshape(0, 5)
+    order = np.lexsort((rec[:, 4], rec[:, 3], rec[:, 2], rec[:, 1], rec[:, 0]))
+    return rec[order]
+
+
+@pytest.fixture(scope="module")
+def lj():
+    return rgpot_b200.LJPot()
+
+
+@pytest.fixture(scope="module")
+def ljc():
+    return rgpot_b200.LJClusterPot()
+
+
+@pytest.fixture(scope="module")
+def cuh2():
+    return rgpot_b200.CuH2Pot()
+
+
+# ------------------------------------------------------------------------------------------- LJ
+def test_lj_cluster_pins(ljc, golden):
+    g = golden("lj13_cluster.json")
+    pos, box = np.array(g["positions"]), np.array(g["box"]).reshape(3, 3)
+    e, f, v = ljc(pos, np.ones(13, np.int32), box)
+    assert e == pytest.approx(g["pin_energy"], rel=1e-9)  # LJClusterPotTest.cc:68
+    assert np.sqrt((f ** 2).sum(1)).max() == pytest.approx(g["pin_max_force"], rel=1e-9)
+    assert v == 0.0
+    assert_energy(e, g["ref_cluster_energy"])
+    assert_forces(f, np.array(g["ref_cluster_forces"]))
+    assert not ljc.caps().periodic and ljc.caps().batched
+
+
+def test_lj_periodic_equals_cluster_and_ignores_cell(lj, ljc, golden):
+    g = golden("lj13_cluster.json")
+    pos, box = np.array(g["positions"]), np.array(g["box"]).reshape(3, 3)
+    z = np.ones(13, np.int32)
+    e_c, f_c, _ = ljc(pos, z, box)
+    e_p, f_p, _ = lj(pos, z, box)
+    assert e_c == pytest.approx(e_p, rel=1e-12)  # LJClusterPotTest.cc:72-94
+    assert np.abs(f_c - f_p).max() < 1e-12
+    e_t, _, _ = ljc(pos, z, np.eye(3) * 5.0)  # :96-112
+    assert e_t == pytest.approx(e_c, rel=1e-12)
+
+
+@pytest.mark.parametrize("path", [1, 2])
+def test_lj_reference_cases(golden, path):
+    for name, c in golden("lj_reference_cases.json")["cases"].items():
+        pot = rgpot_b200.LJPot(rgpot_b200.LJConfig(c["u0"], c["cutoff"], c["psi"]))
+        pot.set_path(path)
+        pos, box = np.array(c["positions"]), np.array(c["box"]).reshape(3, 3)
+        z = np.ones(len(pos), np.int32)
+        e, f, _ = pot(pos, z, box)
+        assert_energy(e, c["energy"])
+        assert_forces(f, np.array(c["forces"]))
+        pairs, shifts = pot.neighbors(pos, z, box, path=path)
+        want = np.array(c["pairs"], dtype=np.int64).reshape(-1, 2)
+        got = canon(pairs, shifts)[:, :2]
+        assert np.array_equal(got, want[np.lexsort((want[:, 1], want[:, 0]))]), name
+
+
+def test_lj_invariance_dimer(lj):
+    # InvarianceTest.cc:25-89 (rc = 15 > L/2: nearest image only) and test_rgpot_pip_core.py:27-56
+    box = np.eye(3) * 10.0
+    pos = np.array([[1.0, 1.0, 1.0], [2.5, 1.0, 1.0]])
+    z = np.ones(2, np.int32)
+    e0, f0, _ = lj(pos, z, box)
+    e1, _, _ = lj(pos + np.array([3.3, -2.1, 0.7]), z, box)
+    assert e1 == pytest.approx(e0, abs=1e-12)
+    rot = np.array([[0.0, -1.0, 0.0], [1.0, 0.0, 0.0], [0.0, 0.0, 1.0]])
+    e2, _, _ = lj((pos - pos[0]) @ rot.T + pos[0], z, box)
+    assert e2 == pytest.approx(e0, abs=1e-12)
+    assert np.isfinite(e0) and np.abs(f0[0] + f0[1]).max() < 1e-9
+    ef, ff, _ = rgpot_b200.evaluate_lj(pos, z, box)
+    assert ef == pytest.approx(e0, abs=1e-12) and np.abs(ff - f0).max() < 1e-12
+    n0 = lj.force_calls
+    lj(pos, z, box)
+    assert lj.force_calls == n0 + 1
+
+
+def _random_fluid(n, rho, seed, wrapped):
+    rng = np.random.default_rng(seed)
+    m = int(np.ceil(n ** (1 / 3)))
+    L = (n / rho) ** (1 / 3)
+    g = (np.stack(np.meshgrid(*[np.arange(m)] * 3, indexing="ij"), -1).reshape(-1, 3)[:n] + 0.5) * (L / m)
+    pos = g + rng.normal(0, 0.08, g.shape)
+    if wrapped:
+        pos = np.mod(pos, L)
+    else:
+        pos += rng.integers(-2, 3, size=g.shape) * L  # whole-box displacements: unwrapped input
+    return pos, np.diag([L, L, L])
+
+
+@pytest.mark.parametrize("n,wrapped,path", [(700, True, 1), (700, False, 1), (700, False, 2),
+                                            (4000, True, 1), (4000, False, 1)])
+def test_lj_fluid_vs_oracle(oracle, n, wrapped, path):
+    pos, box = _random_fluid(n, 0.8442, n + int(wrapped), wrapped)
+    pot = rgpot_b200.LJPot(rgpot_b200.LJConfig(1.0, 2.5, 1.0))
+    pot.set_path(path)
+    z = np.ones(n, np.int32)
+    e, f, _ = pot(pos, z, box)
+    e_o, f_o, _ = oracle.lj_force(pos, box, 1.0, 2.5, 1.0)
+    assert_energy(e, e_o)
+    assert_forces(f, f_o)
+    pairs, shifts = pot.neighbors(pos, z, box, path=path)
+    want = oracle.lj_pairs(pos, box, 2.5).astype(np.int64)
+    assert np.array_equal(canon(pairs, shifts)[:, :2], want[np.lexsort((want[:, 1], want[:, 0]))])
+
+
+def test_lj_cluster_large_cell_path(oracle):
+    rng = np.random.default_rng(3)
+    n = 3000
+    pos = rng.random((n, 3)) * 22.0
+    # relax overlaps a little so forces stay moderate
+    pot = rgpot_b200.LJClusterPot(rgpot_b200.LJClusterConfig(1.0, 3.0, 1.0))
+    pot.set_path(1)
+    e, f, _ = pot(pos, np.ones(n, np.int32), np.eye(3) * 5.0)
+    e_o, f_o, _ = oracle.lj_force(pos, np.eye(3) * 5.0, 1.0, 3.0, 1.0, cluster=True)
+    assert abs(e - e_o) <= 1e-10 * abs(e_o)
+    assert (np.abs(f - f_o) <= 1e-9 + 1e-10 * np.abs(f_o)).all()
+
+
+def test_lj_trivial_inputs(lj, ljc):
+    box = np.eye(3) * 10
+    e, f, _ = lj(np.zeros((1, 3)), np.ones(1, np.int32), box)  # LJPot.cc:50-52
+    assert e == 0.0 and np.array_equal(f, np.zeros((1, 3)))
+    e, f, _ = lj(np.zeros((0, 3)), np.zeros(0, np.int32), box)
+    assert e == 0.0 and f.shape == (0, 3)
+    z = rgpot_b200.LJPot(rgpot_b200.LJConfig(cutoff=0.0))
+    e, f, _ = z(np.array([[0, 0, 0], [1.0, 0, 0]]), np.ones(2, np.int32), box)
+    assert e == 0.0 and not f.any()
+    with pytest.raises(ValueError):
+        lj(np.zeros((3, 2)), np.ones(3, np.int32), box)
+    with pytest.raises(ValueError):
+        lj(np.zeros((3, 3)), np.ones(2, np.int32), box)
+    with pytest.raises(ValueError):
+        lj(np.zeros((3, 3)), np.ones(3, np.int32), np.zeros(9))
+
+
+# ----------------------------------------------------------------------------------------- CuH2
+@pytest.mark.parametrize("path", [1, 2])
+def test_cuh2_pin4(cuh2, golden, path):
+    g = golden("cuh2_pin4.json")
+    cuh2.set_path(path)
+    e, f, v = cuh2(g["positions"], g["Z"], np.array(g["box"]).reshape(3, 3))
+    cuh2.set_path(0)
+    assert_energy(e, g["pin_energy"])  # CuH2PotTest.cc:24 (upstream tolerance 1e-6)
+    assert_forces(f, np.array(g["pin_forces"]))
+    assert v == 0.0
+
+
+def test_cuh2_dimer(cuh2, golden):
+    g = golden("cuh2_dimer.json")
+    e, f, _ = cuh2(g["positions"], g["Z"], np.array(g["box"]).reshape(3, 3))
+    assert e == pytest.approx(g["pin_energy"], rel=1e-6)  # tests/rpc_integ.py:76-78
+    assert f[0, 0] == pytest.approx(g["pin_f0x"], rel=1e-6)
+    assert f[1, 0] == pytest.approx(g["pin_f1x"], rel=1e-6)
+
+
+@pytest.mark.parametrize("path", [1, 2])
+def test_cuh2_slab218(cuh2, golden, path):
+    g = golden("cuh2_slab218.json")
+    pos, Z, box = np.array(g["positions"]), np.array(g["Z"], np.int32), np.array(g["box"]).reshape(3, 3)
+    cuh2.set_path(path)
+    e, f, _ = cuh2(pos, Z, box)
+    pairs, shifts = cuh2.neighbors(pos, Z, box, path=path)
+    cuh2.set_path(0)
+    assert_energy(e, g["energy"])
+    assert_forces(f, np.array(g["forces"]))
+    assert len(pairs) == g["n_directed_pairs"]
+
+
+@pytest.mark.parametrize("path", [1, 2])
+def test_cuh2_pair_sets_match_vesin(cuh2, golden, path):
+    for name, c in golden("vesin_pairsets.json")["cases"].items():
+        pos, box = np.array(c["positions"]), np.array(c["box"]).reshape(3, 3)
+        pairs, shifts = cuh2.neighbors(pos, np.full(len(pos), 29, np.int32), box, path=path)
+        assert np.array_equal(canon(pairs, shifts), np.array(c["pairs"]).reshape(-1, 5)), name
+
+
+@pytest.mark.parametrize("path", [1, 2])
+def test_cuh2_physics_suite(cuh2, oracle, path):
+    # test_cuh2.f90:71-137, multi-image box
+    pos, Z, box = workloads.cu_slab_with_h2()
+    cuh2.set_path(path)
+    try:
+        e, f0, _ = cuh2(pos, Z, box)
+        e_o, f_o = oracle.cuh2_force(pos, Z, box)
+        assert_energy(e, e_o)
+        assert_forces(f0, f_o)
+        assert np.abs(f0.sum(0)).max() < 1e-9
+        e_t, _, _ = cuh2(pos + 0.37, Z, box)
+        assert abs(e_t - e) < 1e-8
+        e_r, f_r, _ = cuh2(pos[::-1], Z[::-1], box)
+        assert abs(e_r - e) < 1e-8 and np.abs(f_r[::-1] - f0).max() < 1e-5
+        delta = 1e-5
+        for atom in [0, 4, 8, 13, 19, 26, 31, 32, 33]:
+            for c in range(3):
+                p = pos.copy()
+                p[atom, c] += delta
+                ep, _, _ = cuh2(p, Z, box)
+                p[atom, c] -= 2 * delta
+                em, _, _ = cuh2(p, Z, box)
+                assert abs(-(ep - em) / (2 * delta) - f0[atom, c]) < 1e-5
+    finally:
+        cuh2.set_path(0)
+
+
+def test_cuh2_errors(cuh2):
+    pos, Z, box = workloads.cu_slab_with_h2()
+    bad = Z.copy()
+    bad[2] = 26
+    with pytest.raises(rgpot_b200.PotentialError) as ei:
+        cuh2(pos, bad, box)
+    assert ei.value.status == 2
+    assert str(ei.value) == ("CuH2 potential failed (status 2): rgpot_cuh2: atom 3 has atomic number 26; "
+                             "this potential covers Cu (29) and H (1) only")
+    p2 = pos.copy()
+    p2[1] = p2[0]
+    with pytest.raises(rgpot_b200.PotentialError) as ei:
+        cuh2(p2, Z, box)
+    assert ei.value.status == 3 and "two atoms occupy the same position" in str(ei.value)
+    with pytest.raises(rgpot_b200.PotentialError) as ei:
+        cuh2(pos, Z, np.zeros((3, 3)))
+    assert ei.value.status == 1 and "not invertible" in str(ei.value)
+    p3 = pos.copy()
+    p3[5, 1] = np.nan
+    with pytest.raises(rgpot_b200.PotentialError) as ei:
+        cuh2(p3, Z, box)
+    assert ei.value.status == 1 and "non-finite" in str(ei.value)
+    e, f, _ = cuh2(np.zeros((0, 3)), np.zeros(0, np.int32), box)
+    assert e == 0.0 and f.shape == (0, 3)
+    # errors on the cell path too
+    cuh2.set_path(1)
+    try:
+        with pytest.raises(rgpot_b200.PotentialError) as ei:
+            cuh2(pos, bad, box)
+        assert ei.value.status == 2 and "atom 3 has atomic number 26" in str(ei.value)
+        with pytest.raises(rgpot_b200.PotentialError) as ei:
+            cuh2(p2, Z, box)
+        assert ei.value.status == 3
+    finally:
+        cuh2.set_path(0)
+
+
+def test_cuh2_triclinic_slab_vs_oracle(cuh2, oracle):
+    pos, Z, box = workloads.cu_slab_triclinic(cells=8, n_h2_side=3)  # 2066 atoms, sheared cell
+    e, f, _ = cuh2(pos, Z, box)
+    e_o, f_o, t = oracle.cuh2_force(pos, Z, box, return_table=True)
+    assert_energy(e, e_o)
+    assert_forces(f, f_o)
+    pairs, shifts = cuh2.neighbors(pos, Z, box)
+    assert np.array_equal(canon(pairs, shifts), oracle.canonical_pairs(t))
+    # unwrapped input (atoms far outside the cell): same physics, per-pair shifts
+    rng = np.random.default_rng(1)
+    moved = pos + (rng.integers(-3, 4, size=pos.shape) @ box)
+    e2, f2, _ = cuh2(moved, Z, box)
+    e2_o, f2_o, t2 = oracle.cuh2_force(moved, Z, box, return_table=True)
+    assert_energy(e2, e2_o)
+    assert_forces(f2, f2_o)
+    pairs, shifts = cuh2.neighbors(moved, Z, box)
+    assert np.array_equal(canon(pairs, shifts), oracle.canonical_pairs(t2))
+
+
+def test_cuh2_commensurate_shear(cuh2):
+    a = 3.615
+    cu = workloads._fcc(4, a)
+    Z = np.full(len(cu), 29, np.int32)
+    e0, _, _ = cuh2(cu, Z, np.diag([4 * a] * 3))
+    e1, _, _ = cuh2(cu, Z, np.array([[4 * a, 0, 0], [a, 4 * a, 0], [a / 2, a / 2, 4 * a]]))
+    assert e0 == pytest.approx(-906.183991113513, rel=1e-10)
+    assert e1 == pytest.approx(e0, rel=1e-10)
+
+
+# ---------------------------------------------------------------------------------------- batches
+def test_force_batch_heterogeneous(cuh2, oracle):
+    slab, Zs, bs = workloads.cuh2_slab218()
+    small, Z2, b2 = workloads.cu_slab_with_h2()
+    pin, Zp, bp = workloads.cuh2_pin4()
+    big, Zb, bb = workloads.cu_slab_triclinic(cells=6, n_h2_side=2)  # 872 atoms -> cell path
+    rng = np.random.default_rng(0)
+    systems = [(slab + rng.normal(0, 0.05, slab.shape), Zs, bs) for _ in range(5)]
+    systems += [(small, Z2, b2), (pin, Zp, bp), (big, Zb, bb), (np.zeros((0, 3)), np.zeros(0, np.int32), bs)]
+    out = cuh2.forceBatch(systems)
+    assert len(out) == len(systems)
+    for (e, f, v), (p, z, b) in zip(out, systems):
+        e_o, f_o = oracle.cuh2_force(p, z, b)
+        assert_energy(e, e_o)
+        assert_forces(f, f_o)
+        assert v == 0.0
+
+
+def test_force_batch_reports_per_system_status(cuh2):
+    slab, Zs, bs = workloads.cuh2_slab218()
+    bad = Zs.copy()
+    bad[7] = 8
+    systems = [(slab, Zs, bs), (slab, bad, bs), (slab, Zs, bs)]
+    out, statuses = cuh2.forceBatch(systems, return_statuses=True)
+    assert list(statuses) == [0, 2, 0]
+    assert out[1][0] == 0.0 and not out[1][1].any()  # failed member is zeroed like the reference
+    assert out[0][0] == pytest.approx(out[2][0], rel=1e-15)
+    with pytest.raises(rgpot_b200.PotentialError) as ei:
+        cuh2.forceBatch(systems)
+    assert ei.value.status == 2 and "atom 8 has atomic number 8" in str(ei.value)
+
+
+def test_force_batch_lj(oracle):
+    pot = rgpot_b200.LJPot(rgpot_b200.LJConfig(1.0, 2.5, 1.0))
+    systems = []
+    for k, n in enumerate([13, 64, 200, 2500]):
+        p, b = _random_fluid(n, 0.8, 50 + k, wrapped=False)
+        systems.append((p, np.ones(n, np.int32), b))
+    for (e, f, _), (p, z, b) in zip(pot.forceBatch(systems), systems):
+        e_o, f_o, _ = oracle.lj_force(p, b, 1.0, 2.5, 1.0)
+        assert_energy(e, e_o)
+        assert_forces(f, f_o)
+
+
+def test_results_are_bit_reproducible(cuh2):
+    offsets, pos, Z, boxes = workloads.cuh2_batch(64)
+    e1, f1 = cuh2.forceBatchPacked(offsets, pos, Z, boxes)
+    e2, f2 = cuh2.forceBatchPacked(offsets, pos, Z, boxes)
+    assert np.array_equal(e1, e2) and np.array_equal(f1, f2)
+    big, Zb, bb = workloads.cu_slab_triclinic(cells=7, n_h2_side=2)
+    a = cuh2(big, Zb, bb)
+    b = cuh2(big, Zb, bb)
+    assert a[0] == b[0] and np.array_equal(a[1], b[1])
+
+
+def test_fortran_dropin_symbol(golden):
+    """rgpot_cuh2_force / rgpot_fortran_last_error with the reference's exact signature."""
+    import ctypes as C
+    from rgpot_b200 import _lib
+    lib = _lib.lib()
+    g = golden("cuh2_pin4.json")
+    pos = np.array(g["positions"])
+    Z = np.array(g["Z"], np.int32)
+    box = np.array(g["box"])
+    F = np.zeros_like(pos)
+    e = C.c_double()
+    st = lib.rgpot_cuh2_force(4, pos.ctypes.data, Z.ctypes.data, box.ctypes.data, F.ctypes.data, C.byref(e))
+    assert st == 0
+    assert_energy(e.value, g["pin_energy"])
+    Z[0] = 3
+    st = lib.rgpot_cuh2_force(4, pos.ctypes.data, Z.ctypes.data, box.ctypes.data, F.ctypes.data, C.byref(e))
+    buf = C.create_string_buffer(512)
+    n = lib.rgpot_fortran_last_error(buf, 512)
+    assert st == 2 and n > 0 and b"atom 1 has atomic number 3" in buf.value
+    assert e.value == 0.0 and not F.any()

@@ -1,0 +1,154 @@
+"""The oracle against every golden vector the reference's own tests hold for this path.
+
+Not a GPU test: this pins the CHECKER (oracle/), so that parity of the CUDA path against the
+oracle means parity against the reference.
+"""
+import numpy as np
+import pytest
+
+from rgpot_b200 import workloads
+
+
+def test_lj_cluster_pins(oracle, golden):
+    # CppCore/tests/LJClusterPotTest.cc:55-69
+    g = golden("lj13_cluster.json")
+    pos, box = np.array(g["positions"]), np.array(g["box"]).reshape(3, 3)
+    e, f, npairs = oracle.lj_force(pos, box, cluster=True)
+    assert npairs == 78
+    assert e == pytest.approx(g["pin_energy"], rel=1e-9)
+    assert e == pytest.approx(g["pin_eon_energy"], rel=1e-4)
+    assert np.sqrt((f ** 2).sum(1)).max() == pytest.approx(g["pin_max_force"], rel=1e-9)
+    # against the reference object itself: identical scan order, so bit-exact
+    assert e == g["ref_cluster_energy"]
+    assert np.array_equal(f, np.array(g["ref_cluster_forces"]))
+
+
+def test_lj_periodic_equals_cluster(oracle, golden):
+    # LJClusterPotTest.cc:72-94
+    g = golden("lj13_cluster.json")
+    pos, box = np.array(g["positions"]), np.array(g["box"]).reshape(3, 3)
+    e_c, f_c, _ = oracle.lj_force(pos, box, cluster=True)
+    e_p, f_p, _ = oracle.lj_force(pos, box, cluster=False)
+    assert e_c == pytest.approx(e_p, rel=1e-12)
+    assert np.abs(f_c - f_p).max() < 1e-12
+    assert e_p == g["ref_periodic_energy"]
+
+
+def test_lj_cluster_ignores_cell(oracle, golden):
+    # LJClusterPotTest.cc:96-112
+    g = golden("lj13_cluster.json")
+    pos, box = np.array(g["positions"]), np.array(g["box"]).reshape(3, 3)
+    e_wide, _, _ = oracle.lj_force(pos, box, cluster=True)
+    e_tight, _, _ = oracle.lj_force(pos, np.eye(3) * 5.0, cluster=True)
+    assert e_tight == pytest.approx(e_wide, rel=1e-12)
+
+
+def test_lj_reference_cases(oracle, golden):
+    # outputs of the unmodified LJPot.cc (oracle/_ref) on periodic boxes incl. rc > L/2
+    for name, c in golden("lj_reference_cases.json")["cases"].items():
+        pos, box = np.array(c["positions"]), np.array(c["box"]).reshape(3, 3)
+        e, f, npairs = oracle.lj_force(pos, box, c["u0"], c["cutoff"], c["psi"])
+        assert e == c["energy"], name
+        assert np.array_equal(f, np.array(c["forces"])), name
+        assert npairs == len(c["pairs"])
+
+
+def test_lj_invariance_dimer(oracle):
+    # CppCore/tests/InvarianceTest.cc:25-89: dimer r = 1.5, 10 A box, rc = 15 > L/2
+    box = np.eye(3) * 10.0
+    pos = np.array([[1.0, 1.0, 1.0], [2.5, 1.0, 1.0]])
+    e0, f0, _ = oracle.lj_force(pos, box)
+    e1, _, _ = oracle.lj_force(pos + np.array([3.3, -2.1, 0.7]), box)
+    assert e1 == pytest.approx(e0, abs=1e-12)
+    rot = np.array([[0.0, -1.0, 0.0], [1.0, 0.0, 0.0], [0.0, 0.0, 1.0]])
+    e2, _, _ = oracle.lj_force((pos - pos[0]) @ rot.T + pos[0], box)
+    assert e2 == pytest.approx(e0, abs=1e-12)
+    assert np.abs(f0[0] + f0[1]).max() < 1e-9  # tests/test_rgpot_pip_core.py:27-56
+
+
+def test_cuh2_pin4(oracle, golden):
+    # CppCore/tests/CuH2PotTest.cc:11-42 -- 17-digit energy and 12 force components
+    g = golden("cuh2_pin4.json")
+    e, f = oracle.cuh2_force(g["positions"], g["Z"], np.array(g["box"]).reshape(3, 3))
+    assert abs(e - g["pin_energy"]) <= 2e-15 * abs(g["pin_energy"])
+    assert np.abs(f - np.array(g["pin_forces"])).max() < 1e-13
+
+
+def test_cuh2_dimer(oracle, golden):
+    # tests/rpc_integ.py:52-78
+    g = golden("cuh2_dimer.json")
+    e, f = oracle.cuh2_force(g["positions"], g["Z"], np.array(g["box"]).reshape(3, 3))
+    assert e == pytest.approx(g["pin_energy"], rel=g["pin_rel_tol"])
+    assert f[0, 0] == pytest.approx(g["pin_f0x"], rel=g["pin_rel_tol"])
+    assert f[1, 0] == pytest.approx(g["pin_f1x"], rel=g["pin_rel_tol"])
+
+
+def test_cuh2_slab218_fixture(oracle, golden):
+    g = golden("cuh2_slab218.json")
+    e, f, t = oracle.cuh2_force(g["positions"], g["Z"], np.array(g["box"]).reshape(3, 3), return_table=True)
+    assert e == pytest.approx(g["energy"], rel=1e-13)
+    assert np.abs(f - np.array(g["forces"])).max() < 1e-11
+    assert int(t["row"][-1]) == g["n_directed_pairs"] == 11954
+
+
+def test_cuh2_physics_suite(oracle):
+    # CppCore/rgpot/fortran/test_cuh2.f90:71-137 in the multi-image box (7.23 A < 2 * 6.1 A)
+    pos, Z, box = workloads.cu_slab_with_h2()
+    e, f0, t = oracle.cuh2_force(pos, Z, box, return_table=True)
+    assert int(t["row"][-1]) == 1874  # multi-image pairs present
+    assert e == pytest.approx(-107.3299063315978, rel=1e-12)
+    assert np.abs(f0.sum(0)).max() < 1e-9
+    e_t, _ = oracle.cuh2_force(pos + 0.37, Z, box)
+    assert abs(e_t - e) < 1e-8
+    e_r, f_r = oracle.cuh2_force(pos[::-1], Z[::-1], box)
+    assert abs(e_r - e) < 1e-8
+    assert np.abs(f_r[::-1] - f0).max() < 1e-5
+    delta = 1e-5
+    for atom in [0, 4, 8, 13, 19, 26, 31, 32, 33]:
+        for c in range(3):
+            p = pos.copy()
+            p[atom, c] += delta
+            ep, _ = oracle.cuh2_force(p, Z, box)
+            p[atom, c] -= 2 * delta
+            em, _ = oracle.cuh2_force(p, Z, box)
+            assert abs(-(ep - em) / (2 * delta) - f0[atom, c]) < 1e-5
+
+
+def test_cuh2_errors(oracle):
+    pos, Z, box = workloads.cu_slab_with_h2()
+    bad = Z.copy()
+    bad[2] = 26
+    with pytest.raises(oracle.CuH2Error) as ei:
+        oracle.cuh2_force(pos, bad, box)
+    assert ei.value.status == 2
+    assert "atom 3 has atomic number 26; this potential covers Cu (29) and H (1) only" in ei.value.message
+    p2 = pos.copy()
+    p2[1] = p2[0]
+    with pytest.raises(oracle.CuH2Error) as ei:
+        oracle.cuh2_force(p2, Z, box)
+    assert ei.value.status == 3 and "two atoms occupy the same position" in ei.value.message
+    with pytest.raises(oracle.CuH2Error) as ei:
+        oracle.cuh2_force(pos, Z, np.zeros((3, 3)))
+    assert ei.value.status == 1 and "not invertible" in ei.value.message
+    e, f = oracle.cuh2_force(np.zeros((0, 3)), np.zeros(0, np.int32), box)
+    assert e == 0.0 and f.shape == (0, 3)
+
+
+def test_vesin_pairset_fixtures(oracle, golden):
+    # pair sets produced by the vendored vesin itself (triclinic, atoms outside the cell, images)
+    for name, c in golden("vesin_pairsets.json")["cases"].items():
+        t = oracle.nlist(c["positions"], np.array(c["box"]).reshape(3, 3), c["cutoff"])
+        assert np.array_equal(oracle.canonical_pairs(t), np.array(c["pairs"]).reshape(-1, 5)), name
+        assert t["n_self_images"] == c["n_self_images"]
+
+
+def test_triclinic_commensurate_shear(oracle):
+    # a lattice-commensurate shear leaves a perfect crystal's energy unchanged
+    a = 3.615
+    cu = workloads._fcc(4, a)
+    Z = np.full(len(cu), 29, dtype=np.int32)
+    e0, _ = oracle.cuh2_force(cu, Z, np.diag([4 * a] * 3))
+    e1, _ = oracle.cuh2_force(cu, Z, np.array([[4 * a, 0, 0], [a, 4 * a, 0], [0, 0, 4 * a]]))
+    e2, _ = oracle.cuh2_force(cu, Z, np.array([[4 * a, 0, 0], [a, 4 * a, 0], [a / 2, a / 2, 4 * a]]))
+    assert e0 == pytest.approx(-906.183991113513, rel=1e-12)
+    assert e1 == pytest.approx(e0, rel=1e-11) and e2 == pytest.approx(e0, rel=1e-11)
