@@ -197,7 +197,11 @@ def run_cuh2_batch(args, world, rank, local):
     d_boxes = torch.from_numpy(np.ascontiguousarray(boxes)).to(dev)
     d_F = torch.empty((n_atoms, 3), dtype=torch.float64, device=dev)
     d_E = torch.empty(n_cfg, dtype=torch.float64, device=dev)
-    stream = torch.cuda.current_stream().cuda_stream
+    # a dedicated (non-default) stream: the engine launches on it and the CUDA events below are
+    # recorded on it, so they bracket exactly the engine's kernels
+    tstream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(tstream)
+    stream = tstream.cuda_stream
 
     def step():
         pot.force_batch_device(offsets, d_pos, d_Z, d_boxes, d_F, d_E, stream)
@@ -301,7 +305,9 @@ def run_single_system(args, name, local):
     d_Z = torch.from_numpy(Z).to(dev)
     d_F = torch.empty((n, 3), dtype=torch.float64, device=dev)
     d_E = torch.empty(1, dtype=torch.float64, device=dev)
-    stream = torch.cuda.current_stream().cuda_stream
+    tstream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(tstream)
+    stream = tstream.cuda_stream
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
     steps = max(3, min(args.steps, 10))
     for _ in range(3):

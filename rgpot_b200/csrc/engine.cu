@@ -500,7 +500,7 @@ int eam_small_maxnb(const RgpotB200Pot* pot, long nmax) {
   const size_t per_sm = 227 * 1024;
   if (eam_small_smem(nmax, 96) <= per_sm / 2 - 2048) return 96;
   for (int maxnb : {160, 128, 96}) {
-    if (eam_small_smem(nmax, maxnb) <= pot->smem_optin - 1024) return maxnb;
+    if (eam_small_smem(nmax, maxnb) <= pot->smem_optin - 2048) return maxnb;
   }
   return 0;
 }
@@ -535,8 +535,11 @@ int launch_small(RgpotB200Pot* pot, size_t nsys, long nmax, const long long* d_o
     int threads = (int)std::min<long>(512, ((nmax * tpa + 31) / 32) * 32);
     if (threads < 32) threads = 32;
     auto launch = [&](auto kern) -> int {
-      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (int)pot->smem_optin);
+      cudaFuncAttributes fa;
+      cudaError_t e = cudaFuncGetAttributes(&fa, kern);
+      if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)(pot->smem_optin - fa.sharedSizeBytes));
       if (e != cudaSuccess) {
         pot->last_error = std::string("CUDA failure: ") + cudaGetErrorString(e);
         return kStatusCuda;
@@ -552,8 +555,11 @@ int launch_small(RgpotB200Pot* pot, size_t nsys, long nmax, const long long* d_o
     }
   }
   const size_t smem = sizeof(double) * 3 * (size_t)nmax + 16;
-  cudaError_t e = cudaFuncSetAttribute(k_lj_small, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)pot->smem_optin);
+  cudaFuncAttributes fa;
+  cudaError_t e = cudaFuncGetAttributes(&fa, k_lj_small);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(k_lj_small, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)(pot->smem_optin - fa.sharedSizeBytes));
   if (e != cudaSuccess) return fail(pot, kStatusCuda, std::string("CUDA failure: ") + cudaGetErrorString(e));
   int threads = (int)std::min<long>(256, ((nmax + 31) / 32) * 32);
   if (threads < 32) threads = 32;
@@ -580,6 +586,8 @@ int map_flags(RgpotB200Pot* pot, unsigned flags, int bad_atom, int bad_z, const 
     return fail(pot, 2, buf);
   }
   const bool images = eam || pot->cfg.lj_all_images;
+  if (images && (flags & kFlagSingularBox))
+    return fail(pot, 1, "rgpot_neighbors: vesin build failed: the box matrix is not invertible");
   if (images && (flags & kFlagNonFinite)) {
     char buf[256];
     if (host_pos && bad_atom != INT_MAX && bad_atom >= 0) {
@@ -1081,7 +1089,7 @@ static int batch_device_impl(RgpotB200Pot* pot, size_t nsys, const size_t* offse
                       nullptr);
     if (s == 1) {
       // singular box of one member: record, keep going
-      unsigned f = kFlagNonFinite;
+      unsigned f = kFlagSingularBox;
       CU_TRY(pot, cudaMemcpyAsync(pot->b_flags.as<unsigned>() + id, &f, sizeof f, cudaMemcpyHostToDevice, st));
       continue;
     }
@@ -1131,7 +1139,7 @@ static int batch_finish(RgpotB200Pot* pot, size_t nsys, const size_t* offsets, c
         f = stt.flags;
         bad = stt.first_bad_atom;
       } else {
-        f = kFlagNonFinite;
+        f = kFlagSingularBox;
       }
     }
     int status = 0;

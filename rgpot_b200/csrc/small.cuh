@@ -175,15 +175,14 @@ k_eam_small(SmallArgs a) {
 
   if (threadIdx.x == 0) {
     small_box_init(a.boxes + 9 * (size_t)sys, c_eam.rcut, sb);
-    blk_flags = sb.bad ? kFlagNonFinite : 0u;  // vesin: "the box matrix is not invertible" -> status 1
+    blk_flags = sb.bad ? kFlagSingularBox : 0u;  // vesin: "the box matrix is not invertible"
     blk_bad[0] = INT_MAX;
     blk_bad[1] = 0;
   }
   __syncthreads();
-  const bool box_bad = sb.bad != 0;
 
   // ---- load, classify (rgpot_cuh2.f90:463-489), wrap into the cell
-  for (int i = threadIdx.x; i < n && !box_bad; i += blockDim.x) {
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
     const double x = a.pos[3 * (base + i)], y = a.pos[3 * (base + i) + 1], z = a.pos[3 * (base + i) + 2];
     px[i] = x;
     py[i] = y;
@@ -222,7 +221,7 @@ k_eam_small(SmallArgs a) {
     ash[i] = ((w[0] + 512) & 1023) | (((w[1] + 512) & 1023) << 10) | (((w[2] + 512) & 1023) << 20);
   }
   __syncthreads();
-  if (blk_flags & (kFlagForeignZ | kFlagNonFinite | kFlagShiftRange)) {
+  if (blk_flags & (kFlagForeignZ | kFlagNonFinite | kFlagShiftRange | kFlagSingularBox)) {
     // the reference leaves energy and forces zeroed on failure
     for (int t = threadIdx.x; t < 3 * n; t += blockDim.x) a.F[3 * base + t] = 0.0;
     if (threadIdx.x == 0) {
