@@ -133,6 +133,15 @@ EamParams make_eam_params() {
     volatile double s = t1 + t2;
     p.rhocut[1] = t3 * s - 0.0;
   }
+  // physics threshold: d2 < rc2 (vesin) and sqrt(d2) < rcut (rgpot_cuh2.f90:522) in one compare
+  double T = p.rc2;
+  while (sqrt(T) >= p.rcut) T = nextafter(T, 0.0);
+  while (sqrt(nextafter(T, INFINITY)) < p.rcut) T = nextafter(T, INFINITY);
+  T = nextafter(T, INFINITY);  // smallest d2 whose rounded sqrt reaches rcut
+  p.rc2_phys = T < p.rc2 ? T : p.rc2;
+  p.cu_delta = 2.0 * p.ba[0] - p.bb[0];
+  p.cucu_square = (p.aa[0] == 2.0 * p.ab[0]) ? 1 : 0;
+  p.cu_taylor = (fabs(p.cu_delta) * p.rcut < 1.0e-3) ? 1 : 0;
   return p;
 }
 
@@ -490,7 +499,12 @@ int run_cell_path(RgpotB200Pot* pot, long n, const double* d_pos, const int* d_Z
 }
 
 // shared memory a k_eam_small block needs
-size_t eam_small_smem(long n, int maxnb) { return (size_t)n * (68 + 4 * (size_t)maxnb) + 16; }
+size_t eam_small_smem(long n, int maxnb) {  // must match the layout in k_eam_small
+  const size_t npad = ((size_t)n + 127) & ~(size_t)127;
+  size_t bytes = sizeof(double) * (7 * (size_t)n + 81);
+  bytes = (bytes + 15) & ~(size_t)15;
+  return bytes + sizeof(float) * 3 * npad + sizeof(int) * 4 * (size_t)n + sizeof(unsigned) * (size_t)n * maxnb;
+}
 
 // pick the list capacity for a batch whose largest system has nmax atoms (0 = does not fit)
 int eam_small_maxnb(const RgpotB200Pot* pot, long nmax) {
@@ -498,9 +512,9 @@ int eam_small_maxnb(const RgpotB200Pot* pot, long nmax) {
   if (nmax > 65535) return 0;
   // two resident blocks per SM when possible, else the roomiest list that still fits one block
   const size_t per_sm = 227 * 1024;
-  if (eam_small_smem(nmax, 96) <= per_sm / 2 - 2048) return 96;
+  if (eam_small_smem(nmax, 96) + 6 * 1024 <= per_sm / 2 - 1024) return 96;
   for (int maxnb : {160, 128, 96}) {
-    if (eam_small_smem(nmax, maxnb) <= pot->smem_optin - 2048) return maxnb;
+    if (eam_small_smem(nmax, maxnb) + 6 * 1024 <= pot->smem_optin) return maxnb;
   }
   return 0;
 }
@@ -531,8 +545,8 @@ int launch_small(RgpotB200Pot* pot, size_t nsys, long nmax, const long long* d_o
     const size_t smem = eam_small_smem(nmax, maxnb);
     // lanes per atom: fill about 448 threads
     int tpa = 1;
-    while (tpa < 8 && nmax * (tpa * 2) <= 512) tpa *= 2;
-    int threads = (int)std::min<long>(512, ((nmax * tpa + 31) / 32) * 32);
+    while (tpa < 8 && nmax * (tpa * 2) <= 448) tpa *= 2;
+    int threads = (int)std::min<long>(448, ((nmax * tpa + 31) / 32) * 32);
     if (threads < 32) threads = 32;
     auto launch = [&](auto kern) -> int {
       cudaFuncAttributes fa;
@@ -1001,6 +1015,19 @@ int rgpot_b200_neighbors(RgpotB200Pot* pot, long nAtoms, const double* positions
   int s = force_device_impl(pot, nAtoms, pot->pos.as<double>(), d_Z, pot->F.as<double>(),
                             pot->energy.as<double>(), box, st, &em, path);
   if (s) return s;
+  if (pot->pend.small_single) {
+    // the all-pairs kernel bows out of systems whose lists it cannot hold (far images, crowded
+    // atoms): the table then comes from the cell-list kernels, like the forces would
+    unsigned flags = 0;
+    CU_TRY(pot, cudaMemcpyAsync(&flags, pot->b_flags.p, sizeof flags, cudaMemcpyDeviceToHost, st));
+    CU_TRY(pot, cudaStreamSynchronize(st));
+    if (flags & kFlagListOverflow) {
+      CU_TRY(pot, cudaMemsetAsync(pot->emit_count.p, 0, sizeof(unsigned long long), st));
+      s = run_cell_path(pot, nAtoms, pot->pos.as<double>(), d_Z, pot->F.as<double>(),
+                        pot->energy.as<double>(), box, st, &em);
+      if (s) return s;
+    }
+  }
   unsigned long long cnt = 0;
   CU_TRY(pot, cudaMemcpyAsync(&cnt, pot->emit_count.p, sizeof cnt, cudaMemcpyDeviceToHost, st));
   CU_TRY(pot, cudaStreamSynchronize(st));

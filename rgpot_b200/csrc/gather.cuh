@@ -189,14 +189,13 @@ k_eam_density(GatherArgs a, double* __restrict__ dfd_sorted, double* __restrict_
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= a.n) return;
   const double4 pi = a.spos[i];
-  const double rcut = c_eam.rcut;
+  const double rc2_phys = c_eam.rc2_phys;
   double rho = 0.0;
   bool coincident = false;
   auto body = [&](int, unsigned long long mj, double, double, double, double d2, int, int, int) {
-    const double r = sqrt(d2);
-    if (r <= 0.0) coincident = true;
-    if (r >= rcut) return;  // :522 -- sqrt can round up onto the cutoff
-    rho += eam_rho(meta_species(mj), r);
+    if (d2 == 0.0) coincident = true;  // dist <= 0 guard, rgpot_cuh2.f90:422-428
+    if (!(d2 < rc2_phys)) return;      // :522 -- sqrt(d2) can round up onto the cutoff
+    rho += eam_density_entry(meta_species(mj), d2);
   };
   walk_dispatch<GEO_IMAGES>(a, i, pi, body);
   if (coincident) atomicOr(&st->flags, kFlagCoincident);
@@ -219,12 +218,11 @@ k_eam_force(GatherArgs a, const double* __restrict__ dfd_sorted,
     const unsigned long long mi = (unsigned long long)__double_as_longlong(pi.w);
     const int zi = meta_species(mi);
     const double dfd_i = dfd_sorted[i];
-    const double rcut = c_eam.rcut;
+    const double rc2_phys = c_eam.rc2_phys;
     auto body = [&](int j, unsigned long long mj, double dx, double dy, double dz, double d2, int,
                     int, int) {
-      const double r = sqrt(d2);
-      if (r >= rcut) return;
-      eam_force_entry(zi, meta_species(mj), dfd_i, dfd_sorted[j], dx, dy, dz, r, e, fx, fy, fz);
+      if (!(d2 < rc2_phys)) return;
+      eam_force_entry(zi, meta_species(mj), dfd_i, dfd_sorted[j], dx, dy, dz, d2, e, fx, fy, fz);
     };
     walk_dispatch<GEO_IMAGES>(a, i, pi, body);
     e += eemb_sorted[i];

@@ -6,6 +6,17 @@
 //          are the same doubles the reference subtracts)
 // The CuH2 EAM is fully analytic (no spline tables exist upstream), so the coefficients live in
 // __constant__ memory and the kernels evaluate the same closed forms.
+//
+// The radial terms are exp-bound (the reference evaluates 10 exponentials per directed pair).
+// Here a directed Cu-Cu pair costs 3:
+//   * alpha_A(CuCu) == 2 alpha_B(CuCu) exactly, so exp(-alpha_A r) = exp(-alpha_B r)^2;
+//   * beta_b(Cu) = 2 beta_a(Cu) - 1e-5, so exp(-beta_b r) = exp(-beta_a r)^2 * exp(1e-5 r) with
+//     the last factor a 3-term Taylor series (|1e-5 r| < 6.1e-5, truncation < 6e-19);
+//   * exp itself is a branch-free range-limited kernel (arguments lie in [-38, 0]).
+// Each identity is checked on the host against the coefficient values before it is enabled
+// (EamParams::cucu_square / cu_taylor); otherwise the generic two-exponential form runs.
+// All of this changes results by a few ulp, far inside the 1e-10 parity budget; accept/reject
+// decisions never depend on it.
 #pragma once
 
 #include "common.cuh"
@@ -19,6 +30,13 @@ struct EamParams {
   double scale[2], ba[2], bb[2], gamma[2], rhocut[2];
   double f_cu[8], f_h[5];
   double rcut, rc2;
+  // physics threshold on d2: pairs with d2 >= rc2_phys are skipped.  It equals
+  // min(rc2, smallest d2 whose correctly rounded sqrt reaches rcut), i.e. exactly the
+  // reference's `d2 < rc2` (vesin filter) AND `sqrt(d2) < rcut` (rgpot_cuh2.f90:522,554).
+  double rc2_phys;
+  double cu_delta;  // 2 beta_a(Cu) - beta_b(Cu)
+  int cucu_square;  // alpha_A(CuCu) == 2 alpha_B(CuCu)
+  int cu_taylor;    // |cu_delta| * rcut small enough for the 3-term series
 };
 
 __constant__ EamParams c_eam;
@@ -39,41 +57,102 @@ RB_D void lj_pair(const LJParams& p, double dx, double dy, double dz, double r2,
   fz -= fs * dz;
 }
 
+// ---- FP64 building blocks --------------------------------------------------------------------
+// exp(x) for x in about [-700, 700] with no special cases: k = rint(x log2 e) by the magic-number
+// add, two-term Cody-Waite reduction, degree-11 near-minimax polynomial (Chebyshev-node
+// interpolant on |r| <= ln2/2, max relative error 1.6e-17 before rounding), exponent patched in
+// with integer arithmetic.  About 1 ulp; 16 FP64 instructions, no branch.
+RB_D double exp_fast(double x) {
+  const double kMagic = 6755399441055744.0;  // 1.5 * 2^52
+  const double t = fma(x, 1.4426950408889634074, kMagic);
+  const int k = __double2loint(t);
+  const double kf = t - kMagic;
+  double r = fma(kf, -6.93147180369123816490e-01, x);
+  r = fma(kf, -1.90821492927058770002e-10, r);
+  double p = 2.5110095611886237e-08;
+  p = fma(p, r, 2.7632715071632255e-07);
+  p = fma(p, r, 2.7557240761739257e-06);
+  p = fma(p, r, 2.4801485278370062e-05);
+  p = fma(p, r, 1.9841269890193705e-04);
+  p = fma(p, r, 1.3888888952505406e-03);
+  p = fma(p, r, 8.333333333319546e-03);
+  p = fma(p, r, 4.166666666648738e-02);
+  p = fma(p, r, 1.666666666666668e-01);
+  p = fma(p, r, 5.000000000000019e-01);
+  p = fma(p, r, 1.0);
+  p = fma(p, r, 1.0);
+  return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
+}
+
+// 1/sqrt(a) for normal positive a: hardware seed (rsqrt.approx, ~2^-22) + one cubic Newton
+// step (error ~ e^3), ~1 ulp, 5 FP64 instructions.
+RB_D double rsqrt_fast(double a) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+  const double h = a * y;
+  const double e = fma(-h, y, 1.0);
+  const double c = fma(e, 0.375, 0.5);
+  return fma(y, e * c, y);
+}
+
 // ---- CuH2 EAM ------------------------------------------------------------------------------
 RB_D int pair_kind(int zi, int zj) { return zi + zj; }  // Cu=0, H=1: 0 CuCu, 1 HCu, 2 HH
 
-// r ** neta with neta_cu = 6 (square-and-multiply like libgfortran: r^2 * r^4), neta_h = 0
-RB_D double rpow(int species, double r) {
-  if (species == 1) return 1.0;
+// the two exponentials of the Cu density and r^6 (square-and-multiply like libgfortran: r^2*r^4)
+struct CuDensityTerms {
+  double ea, eb, r6;
+};
+RB_D CuDensityTerms cu_density_terms(double r) {
+  CuDensityTerms t;
+  t.ea = exp_fast(-c_eam.ba[0] * r);
+  if (c_eam.cu_taylor) {
+    const double z = c_eam.cu_delta * r;
+    const double corr = fma(z, fma(z, fma(z, 1.0 / 6.0, 0.5), 1.0), 1.0);
+    t.eb = t.ea * t.ea * corr;
+  } else {
+    t.eb = exp_fast(-c_eam.bb[0] * r);
+  }
   const double r2 = r * r;
-  return r2 * (r2 * r2);
+  t.r6 = r2 * (r2 * r2);
+  return t;
 }
 
 // density a neighbour of `species` deposits at distance r (shifted)   :228-262
 RB_D double eam_rho(int species, double r) {
-  const double t1 = exp(-c_eam.ba[species] * r);
-  // gamma_h = 0: the reference multiplies exp(0) by zero, which is exactly 0
-  const double t2 = species == 0 ? c_eam.gamma[0] * exp(-c_eam.bb[0] * r) : 0.0;
-  const double t3 = c_eam.scale[species] * rpow(species, r);
-  return t3 * (t1 + t2) - c_eam.rhocut[species];
+  if (species == 0) {
+    const CuDensityTerms t = cu_density_terms(r);
+    return c_eam.scale[0] * t.r6 * fma(c_eam.gamma[0], t.eb, t.ea) - c_eam.rhocut[0];
+  }
+  // gamma_h = 0 and neta_h = 0: a single exponential (the reference multiplies exp(0) by zero)
+  return c_eam.scale[1] * exp_fast(-c_eam.ba[1] * r) - c_eam.rhocut[1];
 }
 
 // (drho/dr) / r   :241-291
 RB_D double eam_drho(int species, double r, double rinv) {
-  const double t1 = exp(-c_eam.ba[species] * r);
-  const double t2 = species == 0 ? c_eam.gamma[0] * exp(-c_eam.bb[0] * r) : 0.0;
-  const double t3 = c_eam.scale[species] * rpow(species, r);
-  const double raw = t3 * (t1 + t2);
-  const double neta = species == 0 ? 6.0 : 0.0;
-  return (neta * raw * rinv - t3 * (c_eam.ba[species] * t1 + c_eam.bb[species] * t2)) * rinv;
+  if (species == 0) {
+    const CuDensityTerms t = cu_density_terms(r);
+    const double t2 = c_eam.gamma[0] * t.eb;
+    const double t3 = c_eam.scale[0] * t.r6;
+    const double raw = t3 * (t.ea + t2);
+    return (6.0 * raw * rinv - t3 * fma(c_eam.bb[0], t2, c_eam.ba[0] * t.ea)) * rinv;
+  }
+  const double t1 = exp_fast(-c_eam.ba[1] * r);
+  return -(c_eam.scale[1] * c_eam.ba[1] * t1) * rinv;
 }
 
 // pair energy and (dphi/dr)/r   :143-218
 RB_D void eam_phi(int kind, double r, double rinv, double& phi, double& dphi_r) {
-  const double t1 = c_eam.da[kind] * exp(-c_eam.aa[kind] * r);
-  const double t2 = c_eam.db[kind] * exp(-c_eam.ab[kind] * r);
+  double ea, eb;
+  eb = exp_fast(-c_eam.ab[kind] * r);
+  if (kind == 0 && c_eam.cucu_square) {
+    ea = eb * eb;
+  } else {
+    ea = exp_fast(-c_eam.aa[kind] * r);
+  }
+  const double t1 = c_eam.da[kind] * ea;
+  const double t2 = c_eam.db[kind] * eb;
   phi = t1 + t2 - c_eam.phicut[kind];
-  dphi_r = -(c_eam.aa[kind] * t1 + c_eam.ab[kind] * t2) * rinv;
+  dphi_r = -fma(c_eam.aa[kind], t1, c_eam.ab[kind] * t2) * rinv;
 }
 
 // embedding energy and derivative, explicit powers and left-to-right sums like :298-370
@@ -102,20 +181,35 @@ RB_D void eam_embed(int species, double x, double& emb, double& demb) {
   }
 }
 
+// r and 1/r of an accepted entry.  d2 < rc2_phys has been checked by the caller, so neither the
+// correctly rounded sqrt nor a division is needed any more.
+RB_D void radial(double d2, double& r, double& rinv) {
+  rinv = rsqrt_fast(d2);
+  r = d2 * rinv;
+}
+
+// one accepted directed entry of the density pass (atom_density :518-529)
+RB_D double eam_density_entry(int zj, double d2) {
+  double r, rinv;
+  radial(d2, r, rinv);
+  return eam_rho(zj, r);
+}
+
 // one accepted directed entry of the force pass (atom_force :552-586).
 // vec = r_j - r_i + S.H ; returns half pair energy and accumulates f_i += w * vec.
 RB_D void eam_force_entry(int zi, int zj, double dfd_i, double dfd_j, double vx, double vy,
-                          double vz, double r, double& e, double& fx, double& fy, double& fz) {
-  const double rinv = 1.0 / r;
+                          double vz, double d2, double& e, double& fx, double& fy, double& fz) {
+  double r, rinv;
+  radial(d2, r, rinv);
   double phi, w;
   eam_phi(pair_kind(zi, zj), r, rinv, phi, w);
   e += 0.5 * phi;
-  const double drho_ij = eam_drho(zj, r, rinv);                    // what j deposits on i
+  const double drho_ij = eam_drho(zj, r, rinv);                         // what j deposits on i
   const double drho_ji = (zi == zj) ? drho_ij : eam_drho(zi, r, rinv);  // what i deposits on j
   w = w + drho_ij * dfd_i + drho_ji * dfd_j;
-  fx += w * vx;
-  fy += w * vy;
-  fz += w * vz;
+  fx = fma(w, vx, fx);
+  fy = fma(w, vy, fy);
+  fz = fma(w, vz, fz);
 }
 
 }  // namespace rb

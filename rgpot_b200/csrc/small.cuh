@@ -145,48 +145,112 @@ RB_D double entry_vec(const SmallBox& sb, const double* px, const double* py, co
   return xnorm2(vx, vy, vz);
 }
 
-// TPA = lanes cooperating on one atom (power of two, <= 32)
+// --------------------------------------------------------------------------------------------
+// k_eam_small: one block = one system.
+//
+//  phase A  load, classify (rgpot_cuh2.f90:463-489), wrap into the cell (fractional coordinates,
+//           FP64 + an FP32 copy for the prefilter); table of the 27 nearest image vectors S.H
+//  phase B  neighbor search, one WARP per atom, four candidates per lane and round:
+//             FP32 prefilter (nearest image in fractional space, Cartesian distance with a
+//             conservative margin; runs on the FP32 pipe, the FP64 pipe stays free),
+//             survivors are compacted through a per-warp shared-memory queue and take the EXACT
+//             FP64 test of vesin ((p_j - p_i) + S.H, d2 < rc2) 32 at a time, full lanes;
+//             accepted entries are appended to the atom's list in a fixed order.
+//           Boxes narrower than two cutoffs (several images per pair) take a serial enumeration
+//           by lane 0 instead.
+//  phase C  atoms ordered by neighbor count so the lanes of a warp run equally long loops
+//  phase D  density + embedding (rgpot_cuh2.f90:436-451), TPA lanes per atom over its list
+//  phase E  pair energy + forces (rgpot_cuh2.f90:454-457), same mapping
+// Every sum has a fixed order: results are bit-reproducible.
+//
+// list entry: j (16 bits) | image index (5 bits, 0..26 = (S0+1) + 3 (S1+1) + 9 (S2+1)) << 16
+//             | species of j << 21.  Images further than one cell away (atoms far outside the
+//             box) raise kFlagListOverflow and the system reruns on the cell-list kernels.
+// --------------------------------------------------------------------------------------------
+struct SmallBoxF {  // FP32 mirror for the prefilter
+  float h[9];
+  float thr2;  // (rc + margin)^2
+  int ortho;   // diagonal cell: three multiplies instead of a 3x3 product
+};
+
+
 template <int TPA>
-__global__ void __launch_bounds__(512, 2)
+__global__ void __launch_bounds__(448, 2)
 k_eam_small(SmallArgs a) {
-  extern __shared__ double smem[];
+  extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ double sh32[32];
   __shared__ SmallBox sb;
+  __shared__ SmallBoxF sbf;
   __shared__ unsigned blk_flags;
   __shared__ int blk_bad[2];
+  __shared__ unsigned short q_i[14][64];  // per-warp survivor queues (<= 14 warps per block)
+  __shared__ unsigned short q_j[14][64];
 
   const int sys = blockIdx.x;
   const long long base = a.off[sys];
   const int n = (int)(a.off[sys + 1] - base);
   const int maxnb = a.maxnb;
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int nwarp = blockDim.x >> 5;
+  const int npad = (n + 127) & ~127;
 
   // shared layout
-  double* px = smem;
-  double* py = px + n;
-  double* pz = py + n;
-  double* gx = pz + n;  // wrapped fractional coordinates
-  double* gy = gx + n;
-  double* gz = gy + n;
-  double* dfd = gz + n;
-  int* ash = (int*)(dfd + n);        // packed wrap counts (10 bits each, biased 512)
-  int* cnt = ash + n;                // neighbors per atom
-  int* spc = cnt + n;                // species
-  unsigned* list = (unsigned*)(spc + n);  // n * maxnb entries
+  double* pos3 = reinterpret_cast<double*>(smem_raw);  // x, y, z interleaved
+  double* g3 = pos3 + 3 * n;                            // wrapped fractional coordinates
+  double* dfd = g3 + 3 * n;
+  double* svt = dfd + n;                                // 27 image vectors, 3 doubles each
+  size_t off_bytes = sizeof(double) * (7 * (size_t)n + 81);
+  off_bytes = (off_bytes + 15) & ~(size_t)15;
+  float* fx32 = reinterpret_cast<float*>(smem_raw + off_bytes);
+  float* fy32 = fx32 + npad;
+  float* fz32 = fy32 + npad;
+  int* ash = reinterpret_cast<int*>(fz32 + npad);  // packed wrap counts (10 bits each, biased 512)
+  int* cnt = ash + n;                              // neighbors per atom
+  int* spc = cnt + n;                              // species
+  int* perm = spc + n;                             // atoms by decreasing neighbor count
+  unsigned* list = reinterpret_cast<unsigned*>(perm + n);  // n * maxnb entries
 
   if (threadIdx.x == 0) {
     small_box_init(a.boxes + 9 * (size_t)sys, c_eam.rcut, sb);
     blk_flags = sb.bad ? kFlagSingularBox : 0u;  // vesin: "the box matrix is not invertible"
     blk_bad[0] = INT_MAX;
     blk_bad[1] = 0;
+    if (!sb.bad) {
+      double hmax = 0.0;
+      for (int k = 0; k < 9; ++k) {
+        sbf.h[k] = (float)sb.H[k];
+        hmax += fabs(sb.H[k]);
+      }
+      sbf.ortho = sb.H[1] == 0.0 && sb.H[2] == 0.0 && sb.H[3] == 0.0 && sb.H[5] == 0.0 &&
+                  sb.H[6] == 0.0 && sb.H[7] == 0.0;
+      // FP32 error of the wrapped fractional separation (~3 ulp of 1) times the cell size,
+      // plus the rounding of the Cartesian norm: generous, the exact test follows anyway
+      const double margin = 1.0e-6 * hmax + 1.0e-5 * c_eam.rcut;
+      const double thr = c_eam.rcut + margin;
+      sbf.thr2 = (float)(thr * thr * (1.0 + 1.0e-6));
+    }
   }
   __syncthreads();
+  if (threadIdx.x < 27 && !sb.bad) {
+    const int t = (int)threadIdx.x;
+    const double s0 = (double)(t % 3 - 1), s1 = (double)((t / 3) % 3 - 1), s2 = (double)(t / 9 - 1);
+    svt[3 * threadIdx.x] = shift_component(sb.H, 0, s0, s1, s2);
+    svt[3 * threadIdx.x + 1] = shift_component(sb.H, 1, s0, s1, s2);
+    svt[3 * threadIdx.x + 2] = shift_component(sb.H, 2, s0, s1, s2);
+  }
 
-  // ---- load, classify (rgpot_cuh2.f90:463-489), wrap into the cell
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+  // ---- phase A
+  for (int i = threadIdx.x; i < npad; i += blockDim.x) {
+    if (i >= n) {  // padding: NaN never passes the prefilter
+      fx32[i] = fy32[i] = fz32[i] = __int_as_float(0x7fc00000);
+      continue;
+    }
     const double x = a.pos[3 * (base + i)], y = a.pos[3 * (base + i) + 1], z = a.pos[3 * (base + i) + 2];
-    px[i] = x;
-    py[i] = y;
-    pz[i] = z;
+    pos3[3 * i] = x;
+    pos3[3 * i + 1] = y;
+    pos3[3 * i + 2] = z;
+    cnt[i] = 0;
     const int zn = a.Z[base + i];
     int sp = 0;
     if (zn == 29) {
@@ -200,7 +264,9 @@ k_eam_small(SmallArgs a) {
     spc[i] = sp;
     if (!(isfinite(x) && isfinite(y) && isfinite(z))) {
       atomicOr(&blk_flags, kFlagNonFinite);
-      gx[i] = gy[i] = gz[i] = 0.0;
+      atomicMin(&blk_bad[0], i);
+      g3[3 * i] = g3[3 * i + 1] = g3[3 * i + 2] = 0.0;
+      fx32[i] = fy32[i] = fz32[i] = 0.f;
       ash[i] = 512 | (512 << 10) | (512 << 20);
       continue;
     }
@@ -214,10 +280,14 @@ k_eam_small(SmallArgs a) {
       w[k] = (int)fl;
       f[k] -= fl;
     }
-    gx[i] = f[0];
-    gy[i] = f[1];
-    gz[i] = f[2];
+    g3[3 * i] = f[0];
+    g3[3 * i + 1] = f[1];
+    g3[3 * i + 2] = f[2];
+    fx32[i] = (float)f[0];
+    fy32[i] = (float)f[1];
+    fz32[i] = (float)f[2];
     if (abs(w[0]) > 500 || abs(w[1]) > 500 || abs(w[2]) > 500) atomicOr(&blk_flags, kFlagShiftRange);
+    if ((w[0] | w[1] | w[2]) != 0) atomicOr(&blk_flags, kFlagAtomShift);
     ash[i] = ((w[0] + 512) & 1023) | (((w[1] + 512) & 1023) << 10) | (((w[2] + 512) & 1023) << 20);
   }
   __syncthreads();
@@ -228,63 +298,139 @@ k_eam_small(SmallArgs a) {
       a.E[sys] = 0.0;
       a.sys_flags[sys] = blk_flags;
       a.sys_bad[2 * sys] = blk_bad[0];
-      a.sys_bad[2 * sys + 1] = (blk_bad[0] != INT_MAX) ? a.Z[base + blk_bad[0]] : 0;
+      a.sys_bad[2 * sys + 1] =
+          ((blk_flags & kFlagForeignZ) && blk_bad[0] != INT_MAX) ? a.Z[base + blk_bad[0]] : 0;
     }
     return;
   }
 
-  const int sub = threadIdx.x % TPA;
-  const int grp = threadIdx.x / TPA;
-  const int ngrp = blockDim.x / TPA;
-  const unsigned grp_shift = (threadIdx.x & 31) - sub;  // first lane of this group in the warp
-  const unsigned grp_mask = (TPA == 32) ? 0xffffffffu : (((1u << TPA) - 1u) << grp_shift);
   const double rc2 = c_eam.rc2;
-  const double rcut = c_eam.rcut;
+  const bool wrapped_atoms = (blk_flags & kFlagAtomShift) != 0;
 
-  // ---- neighbor search: all pairs, candidate image from the wrapped fractional separation
-  for (int ib = 0; ib < n; ib += ngrp) {
-    const int i = ib + grp;
-    const bool vi = i < n;
-    int count = 0;
-    if (sb.fast) {
-      const double gxi = vi ? gx[i] : 0.0, gyi = vi ? gy[i] : 0.0, gzi = vi ? gz[i] : 0.0;
-      const int ai = vi ? ash[i] : 0;
-      for (int jb = 0; jb < n; jb += TPA) {
-        const int j = jb + sub;
-        bool acc = false;
-        int S0 = 0, S1 = 0, S2 = 0;
-        if (vi && j < n && j != i) {
-          double t0 = gx[j] - gxi, t1 = gy[j] - gyi, t2 = gz[j] - gzi;
-          if (t0 > 0.5) { t0 -= 1.0; S0 = -1; } else if (t0 < -0.5) { t0 += 1.0; S0 = 1; }
-          if (t1 > 0.5) { t1 -= 1.0; S1 = -1; } else if (t1 < -0.5) { t1 += 1.0; S1 = 1; }
-          if (t2 > 0.5) { t2 -= 1.0; S2 = -1; } else if (t2 < -0.5) { t2 += 1.0; S2 = 1; }
-          if (fabs(t0) <= sb.q[0] && fabs(t1) <= sb.q[1] && fabs(t2) <= sb.q[2]) {
-            const int aj = ash[j];
-            S0 += (ai & 1023) - (aj & 1023);
-            S1 += ((ai >> 10) & 1023) - ((aj >> 10) & 1023);
-            S2 += ((ai >> 20) & 1023) - ((aj >> 20) & 1023);
-            double vx, vy, vz;
-            acc = entry_vec(sb, px, py, pz, i, j, S0, S1, S2, vx, vy, vz) < rc2;
-          }
+  // ---- phase B
+  if (sb.fast) {
+    unsigned short* qi = q_i[warp];
+    unsigned short* qj = q_j[warp];
+    int qn = 0;  // warp-uniform queue length
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const float h0 = sbf.h[0], h1 = sbf.h[1], h2 = sbf.h[2], h3 = sbf.h[3], h4 = sbf.h[4],
+                h5 = sbf.h[5], h6 = sbf.h[6], h7 = sbf.h[7], h8 = sbf.h[8];
+    const float thr2 = sbf.thr2;
+    const bool ortho = sbf.ortho != 0;
+
+    // exact test + ordered append of the first m queue entries (m <= 32)
+    auto drain = [&](int m) {
+      int i = 0xffff, j = 0, tidx = 13;
+      bool acc = false, far_image = false;
+      if (lane < m) {
+        i = (int)qi[lane];
+        j = (int)qj[lane];
+        // the prefilter's image choice, recomputed the same way: S' = -rint(g_j - g_i)
+        int S0 = -(int)rintf(fx32[j] - fx32[i]);
+        int S1 = -(int)rintf(fy32[j] - fy32[i]);
+        int S2 = -(int)rintf(fz32[j] - fz32[i]);
+        if (wrapped_atoms) {
+          const int ai = ash[i], aj = ash[j];
+          S0 += (ai & 1023) - (aj & 1023);
+          S1 += ((ai >> 10) & 1023) - ((aj >> 10) & 1023);
+          S2 += ((ai >> 20) & 1023) - ((aj >> 20) & 1023);
+          far_image = abs(S0) > 1 || abs(S1) > 1 || abs(S2) > 1;
         }
-        const unsigned bal = __ballot_sync(0xffffffffu, acc);
-        const unsigned gb = (bal & grp_mask) >> grp_shift;
-        if (acc) {
-          const int slot = count + __popc(gb & ((1u << sub) - 1u));
-          if (slot < maxnb && abs(S0) < 16 && abs(S1) < 16 && abs(S2) < 16) {
-            list[(size_t)i * maxnb + slot] = pack_entry(j, S0, S1, S2);
-          } else {
-            atomicOr(&blk_flags, kFlagListOverflow);
-          }
+        if (!far_image) {
+          tidx = (S0 + 1) + 3 * (S1 + 1) + 9 * (S2 + 1);
+          const double* pi = pos3 + 3 * i;
+          const double* pj = pos3 + 3 * j;
+          const double* sv = svt + 3 * tidx;
+          const double vx = xadd(xsub(pj[0], pi[0]), sv[0]);
+          const double vy = xadd(xsub(pj[1], pi[1]), sv[1]);
+          const double vz = xadd(xsub(pj[2], pi[2]), sv[2]);
+          acc = xnorm2(vx, vy, vz) < rc2;
         }
-        count += __popc(gb);
       }
-    } else if (vi && sub == 0) {
-      // small boxes: several images per pair; the group leader enumerates them in order
+      if (far_image) atomicOr(&blk_flags, kFlagListOverflow);
+      // queue entries are ordered by atom: lanes of one atom are contiguous
+      const int iprev = __shfl_up_sync(0xffffffffu, i, 1);
+      const unsigned heads = __ballot_sync(0xffffffffu, lane == 0 || i != iprev);
+      const unsigned bal = __ballot_sync(0xffffffffu, acc);
+      const int start = 31 - __clz((int)(heads & (lt_mask | (1u << lane))));
+      const unsigned after = heads & ~((2u << lane) - 1u);   // heads above my lane
+      const int end = after ? (__ffs((int)after) - 1) : 32;  // one past my group's last lane
+      const unsigned grp = (end == 32 ? 0xffffffffu : ((1u << end) - 1u)) & ~((1u << start) - 1u);
+      const int basecnt = lane < m ? cnt[i] : 0;
+      __syncwarp();  // every lane has read its atom's count before any group closes it
+      if (lane < m && acc) {
+        const int slot = basecnt + __popc(bal & grp & lt_mask);
+        if (slot < maxnb) {
+          list[i * maxnb + slot] = (unsigned)j | ((unsigned)tidx << 16) | ((unsigned)spc[j] << 21);
+        } else {
+          atomicOr(&blk_flags, kFlagListOverflow);
+        }
+      }
+      if (lane < m && lane == end - 1) cnt[i] = basecnt + __popc(bal & grp);
+      __syncwarp();
+    };
+
+    for (int i = warp; i < n; i += nwarp) {
+      const float gxi = fx32[i], gyi = fy32[i], gzi = fz32[i];
+      for (int jb = 0; jb < npad; jb += 128) {
+        const int j0 = jb + 4 * lane;
+        const float4 X = *reinterpret_cast<const float4*>(fx32 + j0);
+        const float4 Y = *reinterpret_cast<const float4*>(fy32 + j0);
+        const float4 Z = *reinterpret_cast<const float4*>(fz32 + j0);
+        const float xs[4] = {X.x, X.y, X.z, X.w}, ys[4] = {Y.x, Y.y, Y.z, Y.w}, zs[4] = {Z.x, Z.y, Z.z, Z.w};
+        bool pass[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          float t0 = xs[c] - gxi, t1 = ys[c] - gyi, t2 = zs[c] - gzi;
+          t0 -= rintf(t0);
+          t1 -= rintf(t1);
+          t2 -= rintf(t2);
+          float dx, dy, dz;
+          if (ortho) {
+            dx = t0 * h0;
+            dy = t1 * h4;
+            dz = t2 * h8;
+          } else {
+            dx = fmaf(t0, h0, fmaf(t1, h3, t2 * h6));
+            dy = fmaf(t0, h1, fmaf(t1, h4, t2 * h7));
+            dz = fmaf(t0, h2, fmaf(t1, h5, t2 * h8));
+          }
+          pass[c] = (fmaf(dx, dx, fmaf(dy, dy, dz * dz)) <= thr2) && (j0 + c != i);
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const unsigned bal = __ballot_sync(0xffffffffu, pass[c]);
+          if (bal == 0u) continue;
+          if (pass[c]) {
+            const int p = qn + __popc(bal & lt_mask);
+            qi[p] = (unsigned short)i;
+            qj[p] = (unsigned short)(j0 + c);
+          }
+          qn += __popc(bal);
+          __syncwarp();
+          if (qn >= 32) {
+            drain(32);
+            if (lane < qn - 32) {  // move the tail to the front (disjoint ranges)
+              const unsigned short ti = qi[32 + lane], tj = qj[32 + lane];
+              qi[lane] = ti;
+              qj[lane] = tj;
+            }
+            qn -= 32;
+            __syncwarp();
+          }
+        }
+      }
+    }
+    if (qn > 0) drain(qn);
+  } else if (lane == 0) {
+    // small boxes: several images per pair; one lane enumerates them in (j, image) order
+    for (int i = warp; i < n; i += nwarp) {
       const int ai = ash[i];
+      int count = 0;
       for (int j = 0; j < n; ++j) {
         if (j == i) continue;  // self images are dropped (rgpot_neighbors.f90:132)
-        const double t0 = gx[j] - gx[i], t1 = gy[j] - gy[i], t2 = gz[j] - gz[i];
+        const double t0 = g3[3 * j] - g3[3 * i], t1 = g3[3 * j + 1] - g3[3 * i + 1],
+                     t2 = g3[3 * j + 2] - g3[3 * i + 2];
         const int aj = ash[j];
         const int w0 = (ai & 1023) - (aj & 1023), w1 = ((ai >> 10) & 1023) - ((aj >> 10) & 1023),
                   w2 = ((ai >> 20) & 1023) - ((aj >> 20) & 1023);
@@ -296,9 +442,13 @@ k_eam_small(SmallArgs a) {
             for (int s2 = lo2; s2 <= hi2; ++s2) {
               const int S0 = s0 + w0, S1 = s1 + w1, S2 = s2 + w2;
               double vx, vy, vz;
-              if (entry_vec(sb, px, py, pz, i, j, S0, S1, S2, vx, vy, vz) < rc2) {
-                if (count < maxnb && abs(S0) < 16 && abs(S1) < 16 && abs(S2) < 16) {
-                  list[(size_t)i * maxnb + count] = pack_entry(j, S0, S1, S2);
+              vx = xadd(xsub(pos3[3 * j], pos3[3 * i]), shift_component(sb.H, 0, (double)S0, (double)S1, (double)S2));
+              vy = xadd(xsub(pos3[3 * j + 1], pos3[3 * i + 1]), shift_component(sb.H, 1, (double)S0, (double)S1, (double)S2));
+              vz = xadd(xsub(pos3[3 * j + 2], pos3[3 * i + 2]), shift_component(sb.H, 2, (double)S0, (double)S1, (double)S2));
+              if (xnorm2(vx, vy, vz) < rc2) {
+                if (count < maxnb && abs(S0) <= 1 && abs(S1) <= 1 && abs(S2) <= 1) {
+                  const int tidx = (S0 + 1) + 3 * (S1 + 1) + 9 * (S2 + 1);
+                  list[i * maxnb + count] = (unsigned)j | ((unsigned)tidx << 16) | ((unsigned)spc[j] << 21);
                 } else {
                   atomicOr(&blk_flags, kFlagListOverflow);
                 }
@@ -306,9 +456,8 @@ k_eam_small(SmallArgs a) {
               }
             }
       }
+      cnt[i] = count;
     }
-    if (!sb.fast) count = __shfl_sync(0xffffffffu, count, grp_shift);  // leader's count
-    if (vi && sub == 0) cnt[i] = count;
   }
   __syncthreads();
   if (blk_flags & kFlagListOverflow) {
@@ -320,39 +469,61 @@ k_eam_small(SmallArgs a) {
   if (a.emit.pairs != nullptr) {
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
       for (int s = 0; s < cnt[i]; ++s) {
-        const unsigned en = list[(size_t)i * maxnb + s];
+        const unsigned en = list[i * maxnb + s];
         const unsigned long long k = atomicAdd(a.emit.count, 1ull);
         if ((long)k < a.emit.cap) {
+          const int tidx = (int)((en >> 16) & 31u);
           a.emit.pairs[2 * k] = i;
           a.emit.pairs[2 * k + 1] = (int)(en & 0xffffu);
-          a.emit.shifts[3 * k] = (int)((en >> 16) & 31u) - 16;
-          a.emit.shifts[3 * k + 1] = (int)((en >> 21) & 31u) - 16;
-          a.emit.shifts[3 * k + 2] = (int)((en >> 26) & 31u) - 16;
+          a.emit.shifts[3 * k] = tidx % 3 - 1;
+          a.emit.shifts[3 * k + 1] = (tidx / 3) % 3 - 1;
+          a.emit.shifts[3 * k + 2] = tidx / 9 - 1;
         }
       }
     }
   }
 
+  // ---- phase C: rank atoms by decreasing neighbor count (ties by index: deterministic)
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int ci = cnt[i];
+    int rank = 0;
+    for (int j = 0; j < n; ++j) {
+      const int cj = cnt[j];
+      rank += (cj > ci) || (cj == ci && j < i);
+    }
+    perm[rank] = i;
+  }
+  __syncthreads();
+
+  const int sub = threadIdx.x % TPA;
+  const int grp = threadIdx.x / TPA;
+  const int ngrp = blockDim.x / TPA;
+  const double rc2_phys = c_eam.rc2_phys;
+
   double e = 0.0;
-  // ---- pass 1 + 2: density, embedding (rgpot_cuh2.f90:436-451)
+  // ---- phase D: density, embedding
   for (int ib = 0; ib < n; ib += ngrp) {
-    const int i = ib + grp;
-    const bool vi = i < n;
+    const int slot = ib + grp;
+    const bool vi = slot < n;
     double rho = 0.0;
     bool coincident = false;
+    int i = 0;
     if (vi) {
+      i = perm[slot];
       const int c = cnt[i];
+      const double xi = pos3[3 * i], yi = pos3[3 * i + 1], zi = pos3[3 * i + 2];
+      const unsigned* row = list + i * maxnb;
       for (int s = sub; s < c; s += TPA) {
-        const unsigned en = list[(size_t)i * maxnb + s];
-        const int j = (int)(en & 0xffffu);
-        double vx, vy, vz;
-        const double d2 = entry_vec(sb, px, py, pz, i, j, (int)((en >> 16) & 31u) - 16,
-                                    (int)((en >> 21) & 31u) - 16, (int)((en >> 26) & 31u) - 16, vx,
-                                    vy, vz);
-        const double r = sqrt(d2);
-        if (r <= 0.0) coincident = true;
-        if (r >= rcut) continue;
-        rho += eam_rho(spc[j], r);
+        const unsigned en = row[s];
+        const double* pj = pos3 + 3 * (en & 0xffffu);
+        const double* sv = svt + 3 * ((en >> 16) & 31u);
+        const double vx = xadd(xsub(pj[0], xi), sv[0]);
+        const double vy = xadd(xsub(pj[1], yi), sv[1]);
+        const double vz = xadd(xsub(pj[2], zi), sv[2]);
+        const double d2 = xnorm2(vx, vy, vz);
+        if (d2 == 0.0) coincident = true;  // dist <= 0 guard, rgpot_cuh2.f90:422-428
+        if (!(d2 < rc2_phys)) continue;    // :522
+        rho += eam_density_entry((int)(en >> 21), d2);
       }
     }
 #pragma unroll
@@ -375,25 +546,30 @@ k_eam_small(SmallArgs a) {
     return;
   }
 
-  // ---- pass 3: pair energy and forces (rgpot_cuh2.f90:454-457)
+  // ---- phase E: pair energy and forces
   for (int ib = 0; ib < n; ib += ngrp) {
-    const int i = ib + grp;
-    const bool vi = i < n;
+    const int slot = ib + grp;
+    const bool vi = slot < n;
     double fx = 0.0, fy = 0.0, fz = 0.0, ep = 0.0;
+    int i = 0;
     if (vi) {
+      i = perm[slot];
       const int c = cnt[i];
       const int zi = spc[i];
       const double dfd_i = dfd[i];
+      const double xi = pos3[3 * i], yi = pos3[3 * i + 1], zi_ = pos3[3 * i + 2];
+      const unsigned* row = list + i * maxnb;
       for (int s = sub; s < c; s += TPA) {
-        const unsigned en = list[(size_t)i * maxnb + s];
+        const unsigned en = row[s];
         const int j = (int)(en & 0xffffu);
-        double vx, vy, vz;
-        const double d2 = entry_vec(sb, px, py, pz, i, j, (int)((en >> 16) & 31u) - 16,
-                                    (int)((en >> 21) & 31u) - 16, (int)((en >> 26) & 31u) - 16, vx,
-                                    vy, vz);
-        const double r = sqrt(d2);
-        if (r >= rcut) continue;
-        eam_force_entry(zi, spc[j], dfd_i, dfd[j], vx, vy, vz, r, ep, fx, fy, fz);
+        const double* pj = pos3 + 3 * j;
+        const double* sv = svt + 3 * ((en >> 16) & 31u);
+        const double vx = xadd(xsub(pj[0], xi), sv[0]);
+        const double vy = xadd(xsub(pj[1], yi), sv[1]);
+        const double vz = xadd(xsub(pj[2], zi_), sv[2]);
+        const double d2 = xnorm2(vx, vy, vz);
+        if (!(d2 < rc2_phys)) continue;
+        eam_force_entry(zi, (int)(en >> 21), dfd_i, dfd[j], vx, vy, vz, d2, ep, fx, fy, fz);
       }
     }
 #pragma unroll
