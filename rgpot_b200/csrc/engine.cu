@@ -151,6 +151,8 @@ struct RgpotB200Pot {
   RgpotB200Config cfg{};
   int device = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t pipe[3] = {nullptr, nullptr, nullptr};  // copy/compute pipeline of the batch path
+  cudaEvent_t ev_ready = nullptr;
   int sm_count = 0;
   size_t smem_optin = 0;
   double lj_shiftU = 0.0;
@@ -192,6 +194,9 @@ struct RgpotB200Pot {
     for (auto* b : d) b->release();
     HostBuf* h[] = {&h_pos, &h_Z, &h_F, &h_off, &h_boxes, &h_E, &h_flags, &h_bad, &h_small};
     for (auto* b : h) b->release();
+    for (auto& s : pipe)
+      if (s) cudaStreamDestroy(s);
+    if (ev_ready) cudaEventDestroy(ev_ready);
     if (stream) cudaStreamDestroy(stream);
   }
 };
@@ -717,9 +722,12 @@ RgpotB200Pot* rgpot_b200_create(const RgpotB200Config* cfg, char* errbuf, size_t
   pot->device = dev;
   pot->sm_count = prop.multiProcessorCount;
   pot->smem_optin = prop.sharedMemPerBlockOptin;
-  if (cudaStreamCreateWithFlags(&pot->stream, cudaStreamNonBlocking) != cudaSuccess) {
+  bool ok = cudaStreamCreateWithFlags(&pot->stream, cudaStreamNonBlocking) == cudaSuccess;
+  for (auto& s : pot->pipe) ok = ok && cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) == cudaSuccess;
+  ok = ok && cudaEventCreateWithFlags(&pot->ev_ready, cudaEventDisableTiming) == cudaSuccess;
+  if (!ok) {
     delete pot;
-    return err("rgpot_b200_create: cannot create a stream");
+    return err("rgpot_b200_create: cannot create streams");
   }
   if (cfg->kind == RGPOT_B200_CUH2) {
     const EamParams p = make_eam_params();
@@ -1136,8 +1144,8 @@ static int batch_device_impl(RgpotB200Pot* pot, size_t nsys, const size_t* offse
 // Returns the first non-zero status.  h_* describe where the data of the batch lives.
 static int batch_finish(RgpotB200Pot* pot, size_t nsys, const size_t* offsets, const double* d_pos,
                         const int* d_Z, const double* h_boxes, const double* d_boxes, double* d_F,
-                        double* d_E,
-                        cudaStream_t st, const double* host_pos, const int* host_Z, int* statuses) {
+                        double* d_E, cudaStream_t st, const double* host_pos, const int* host_Z,
+                        int* statuses, std::vector<size_t>* touched = nullptr) {
   CU_TRY(pot, pot->h_flags.reserve(sizeof(unsigned) * nsys));
   CU_TRY(pot, pot->h_bad.reserve(sizeof(int) * 2 * nsys));
   unsigned* hf = pot->h_flags.as<unsigned>();
@@ -1153,6 +1161,7 @@ static int batch_finish(RgpotB200Pot* pot, size_t nsys, const size_t* offsets, c
     const size_t o = offsets[s];
     int bad = hb[2 * s], badz = hb[2 * s + 1];
     if (f & kFlagListOverflow) {
+      if (touched) touched->push_back(s);
       double hbox[9];
       int rs = fetch_box(pot, h_boxes, d_boxes, s, hbox);
       if (rs) return rs;
@@ -1180,6 +1189,7 @@ static int batch_finish(RgpotB200Pot* pot, size_t nsys, const size_t* offsets, c
       }
       status = map_flags(pot, f, bad, badz, host_pos ? host_pos + 3 * o : nullptr);
       if (status) {
+        if (touched) touched->push_back(s);
         if (n > 0) CU_TRY(pot, cudaMemsetAsync(d_F + 3 * o, 0, sizeof(double) * 3 * n, st));
         CU_TRY(pot, cudaMemsetAsync(d_E + s, 0, sizeof(double), st));
         if (!first) {
@@ -1235,6 +1245,118 @@ static int batch_sync_status(RgpotB200Pot* pot) {
   return s;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Copy/compute pipeline of a homogeneous (all-pairs-eligible) host batch: the batch is cut into
+// chunks that flow through three streams, so the H2D copy of chunk k+1, the kernel of chunk k and
+// the D2H copy of chunk k-1 overlap.  `stage_in(c0, c1)` is called right before chunk [c0, c1) is
+// copied (the pointer-array entry packs the chunk into pinned staging there); `stage_out(c0, c1)`
+// is called once the chunk's results are on the host.
+// ------------------------------------------------------------------------------------------------
+}  // extern "C" (templates need C++ linkage)
+
+template <class StageIn, class StageOut>
+static int batch_pipeline(RgpotB200Pot* pot, size_t nsys, const size_t* rel, long nmax, const double* h_pos,
+                          const int* h_Z, const double* h_boxes, double* h_F, double* h_E, int* statuses,
+                          StageIn&& stage_in, StageOut&& stage_out) {
+  const bool eam = pot->cfg.kind == RGPOT_B200_CUH2;
+  const size_t total = rel[nsys];
+  CU_TRY(pot, pot->b_pos.reserve(sizeof(double) * 3 * std::max<size_t>(total, 1)));
+  CU_TRY(pot, pot->b_F.reserve(sizeof(double) * 3 * std::max<size_t>(total, 1)));
+  CU_TRY(pot, pot->b_E.reserve(sizeof(double) * nsys));
+  CU_TRY(pot, pot->b_boxes.reserve(sizeof(double) * 9 * nsys));
+  if (eam) CU_TRY(pot, pot->b_Z.reserve(sizeof(int) * std::max<size_t>(total, 1)));
+  CU_TRY(pot, pot->b_off.reserve(sizeof(long long) * (nsys + 1)));
+  CU_TRY(pot, pot->h_off.reserve(sizeof(long long) * (nsys + 1)));
+  CU_TRY(pot, pot->b_flags.reserve(sizeof(unsigned) * nsys));
+  CU_TRY(pot, pot->b_bad.reserve(sizeof(int) * 2 * nsys));
+  long long* ho = pot->h_off.as<long long>();
+  for (size_t s = 0; s <= nsys; ++s) ho[s] = (long long)rel[s];
+  cudaStream_t st0 = pot->stream;
+  CU_TRY(pot, cudaMemcpyAsync(pot->b_off.p, ho, sizeof(long long) * (nsys + 1), cudaMemcpyHostToDevice, st0));
+  CU_TRY(pot, cudaMemsetAsync(pot->b_flags.p, 0, sizeof(unsigned) * nsys, st0));
+  CU_TRY(pot, cudaEventRecord(pot->ev_ready, st0));
+  for (auto& s : pot->pipe) CU_TRY(pot, cudaStreamWaitEvent(s, pot->ev_ready, 0));
+
+  const int maxnb = eam ? eam_small_maxnb(pot, nmax) : 0;
+  size_t chunk = (nsys + 15) / 16;
+  chunk = std::min<size_t>(std::max<size_t>(chunk, 256), 8192);
+  const size_t nchunks = (nsys + chunk - 1) / chunk;
+  std::vector<cudaEvent_t> done(nchunks, nullptr);
+  int rc = 0;
+  double* d_pos = pot->b_pos.as<double>();
+  int* d_Z = eam ? pot->b_Z.as<int>() : nullptr;
+  double* d_boxes = pot->b_boxes.as<double>();
+  double* d_F = pot->b_F.as<double>();
+  double* d_E = pot->b_E.as<double>();
+  for (size_t k = 0; k < nchunks && rc == 0; ++k) {
+    const size_t c0 = k * chunk, c1 = std::min(nsys, c0 + chunk);
+    const size_t a0 = rel[c0], a1 = rel[c1];
+    cudaStream_t st = pot->pipe[k % 3];
+    stage_in(c0, c1);
+    auto cu = [&](cudaError_t err, const char* what) {
+      if (err != cudaSuccess && rc == 0) {
+        pot->last_error = std::string("CUDA failure: ") + cudaGetErrorString(err) + " at " + what;
+        rc = kStatusCuda;
+      }
+    };
+    if (a1 > a0) {
+      cu(cudaMemcpyAsync(d_pos + 3 * a0, h_pos + 3 * a0, sizeof(double) * 3 * (a1 - a0), cudaMemcpyHostToDevice, st), "H2D positions");
+      if (eam) cu(cudaMemcpyAsync(d_Z + a0, h_Z + a0, sizeof(int) * (a1 - a0), cudaMemcpyHostToDevice, st), "H2D atomic numbers");
+    }
+    cu(cudaMemcpyAsync(d_boxes + 9 * c0, h_boxes + 9 * c0, sizeof(double) * 9 * (c1 - c0), cudaMemcpyHostToDevice, st), "H2D boxes");
+    if (rc) break;
+    rc = launch_small(pot, c1 - c0, nmax, pot->b_off.as<long long>() + c0, d_boxes + 9 * c0, d_pos, d_Z, d_F,
+                      d_E + c0, pot->b_flags.as<unsigned>() + c0, pot->b_bad.as<int>() + 2 * c0, maxnb, st, nullptr);
+    if (rc) break;
+    if (a1 > a0)
+      cu(cudaMemcpyAsync(h_F + 3 * a0, d_F + 3 * a0, sizeof(double) * 3 * (a1 - a0), cudaMemcpyDeviceToHost, st), "D2H forces");
+    cu(cudaMemcpyAsync(h_E + c0, d_E + c0, sizeof(double) * (c1 - c0), cudaMemcpyDeviceToHost, st), "D2H energies");
+    cu(cudaEventCreateWithFlags(&done[k], cudaEventDisableTiming), "event");
+    if (done[k]) cu(cudaEventRecord(done[k], st), "event record");
+  }
+  for (size_t k = 0; k < nchunks; ++k) {
+    if (!done[k]) continue;
+    if (rc == 0 && cudaEventSynchronize(done[k]) == cudaSuccess) {
+      const size_t c0 = k * chunk, c1 = std::min(nsys, c0 + chunk);
+      stage_out(c0, c1);
+    }
+    cudaEventDestroy(done[k]);
+  }
+  for (auto& s : pot->pipe) cudaStreamSynchronize(s);
+  if (rc) return rc;
+
+  // statuses; list-overflow members rerun on the cell path; failed members are zeroed
+  std::vector<size_t> touched;
+  int s = batch_finish(pot, nsys, rel, d_pos, d_Z, h_boxes, d_boxes, d_F, d_E, st0, h_pos, h_Z, statuses, &touched);
+  if (s >= kStatusCuda) return s;
+  for (size_t id : touched) {
+    const size_t a0 = rel[id], a1 = rel[id + 1];
+    if (a1 > a0)
+      CU_TRY(pot, cudaMemcpyAsync(h_F + 3 * a0, d_F + 3 * a0, sizeof(double) * 3 * (a1 - a0), cudaMemcpyDeviceToHost, st0));
+    CU_TRY(pot, cudaMemcpyAsync(h_E + id, d_E + id, sizeof(double), cudaMemcpyDeviceToHost, st0));
+  }
+  CU_TRY(pot, cudaStreamSynchronize(st0));
+  if (!touched.empty()) {
+    std::sort(touched.begin(), touched.end());
+    for (size_t id : touched) stage_out(id, id + 1);
+  }
+  return s;
+}
+
+extern "C" {
+
+// largest system of the batch if EVERY member can run on the all-pairs kernels, else -1
+static long batch_all_small(const RgpotB200Pot* pot, size_t nsys, const size_t* rel) {
+  if (pot->forced_path == 1) return -1;
+  long nmax = 0;
+  for (size_t s = 0; s < nsys; ++s) {
+    const long n = (long)(rel[s + 1] - rel[s]);
+    if (!small_eligible(pot, n)) return -1;
+    nmax = std::max(nmax, n);
+  }
+  return nmax;
+}
+
 int rgpot_b200_force_batch_packed(RgpotB200Pot* pot, size_t nSystems, const size_t* offsets,
                                   const double* positions, const int* atomicNrs, const double* boxes,
                                   double* forces, double* energies, int* statuses) {
@@ -1251,6 +1373,15 @@ int rgpot_b200_force_batch_packed(RgpotB200Pot* pot, size_t nSystems, const size
   const size_t total = offsets[nSystems] - base;
   std::vector<size_t> rel(nSystems + 1);
   for (size_t s = 0; s <= nSystems; ++s) rel[s] = offsets[s] - base;
+
+  const long nmax = batch_all_small(pot, nSystems, rel.data());
+  if (nmax >= 0) {
+    auto nop = [](size_t, size_t) {};
+    return batch_pipeline(pot, nSystems, rel.data(), nmax, positions + 3 * base,
+                          atomicNrs ? atomicNrs + base : nullptr, boxes, forces + 3 * base, energies,
+                          statuses, nop, nop);
+  }
+
   CU_TRY(pot, pot->b_pos.reserve(sizeof(double) * 3 * std::max<size_t>(total, 1)));
   CU_TRY(pot, pot->b_F.reserve(sizeof(double) * 3 * std::max<size_t>(total, 1)));
   CU_TRY(pot, pot->b_E.reserve(sizeof(double) * nSystems));
@@ -1268,7 +1399,8 @@ int rgpot_b200_force_batch_packed(RgpotB200Pot* pot, size_t nSystems, const size
                             pot->b_boxes.as<double>(), boxes, pot->b_F.as<double>(), pot->b_E.as<double>(), st);
   if (s) return s;
   s = batch_finish(pot, nSystems, rel.data(), pot->b_pos.as<double>(), d_Z, boxes,
-                   pot->b_boxes.as<double>(), pot->b_F.as<double>(), pot->b_E.as<double>(), st, positions + 3 * base, atomicNrs ? atomicNrs + base : nullptr,
+                   pot->b_boxes.as<double>(), pot->b_F.as<double>(), pot->b_E.as<double>(), st,
+                   positions + 3 * base, atomicNrs ? atomicNrs + base : nullptr,
                    statuses);
   if (s >= kStatusCuda) return s;
   CU_TRY(pot, cudaMemcpyAsync(forces + 3 * base, pot->b_F.p, sizeof(double) * 3 * total,
@@ -1291,9 +1423,13 @@ int rgpot_b200_force_batch(RgpotB200Pot* pot, size_t nSystems, const size_t* nAt
   if (eam && !atomicNrs) return fail(pot, kStatusArgs, "rgpot_b200: CuH2 needs atomic numbers");
   CU_TRY(pot, cudaSetDevice(pot->device));
   std::vector<size_t> off(nSystems + 1, 0);
-  for (size_t s = 0; s < nSystems; ++s) off[s + 1] = off[s] + nAtoms[s];
+  for (size_t s = 0; s < nSystems; ++s) {
+    off[s + 1] = off[s] + nAtoms[s];
+    if (nAtoms[s] > 0 && (!positions[s] || !forces[s] || (eam && !atomicNrs[s])))
+      return fail(pot, kStatusArgs, "rgpot_b200_force_batch: null system buffer");
+  }
   const size_t total = off[nSystems];
-  // gather into pinned staging (ForceBatch buffers are independent allocations in general)
+  // ForceBatch buffers are independent allocations in general: gather through pinned staging
   CU_TRY(pot, pot->h_pos.reserve(sizeof(double) * 3 * std::max<size_t>(total, 1)));
   CU_TRY(pot, pot->h_F.reserve(sizeof(double) * 3 * std::max<size_t>(total, 1)));
   CU_TRY(pot, pot->h_boxes.reserve(sizeof(double) * 9 * nSystems));
@@ -1302,28 +1438,33 @@ int rgpot_b200_force_batch(RgpotB200Pot* pot, size_t nSystems, const size_t* nAt
   double* hp = pot->h_pos.as<double>();
   double* hbx = pot->h_boxes.as<double>();
   int* hz = pot->h_Z.as<int>();
+  double* hF = pot->h_F.as<double>();
+  double* hE = pot->h_E.as<double>();
   static const double free_box[9] = {1e6, 0, 0, 0, 1e6, 0, 0, 0, 1e6};
-  for (size_t s = 0; s < nSystems; ++s) {
-    if (nAtoms[s] > 0) {
-      if (!positions[s] || !forces[s]) return fail(pot, kStatusArgs, "rgpot_b200_force_batch: null system buffer");
-      memcpy(hp + 3 * off[s], positions[s], sizeof(double) * 3 * nAtoms[s]);
-      if (eam) {
-        if (!atomicNrs[s]) return fail(pot, kStatusArgs, "rgpot_b200: CuH2 needs atomic numbers");
-        memcpy(hz + off[s], atomicNrs[s], sizeof(int) * nAtoms[s]);
+  auto pack = [&](size_t c0, size_t c1) {
+    for (size_t s = c0; s < c1; ++s) {
+      if (nAtoms[s] > 0) {
+        memcpy(hp + 3 * off[s], positions[s], sizeof(double) * 3 * nAtoms[s]);
+        if (eam) memcpy(hz + off[s], atomicNrs[s], sizeof(int) * nAtoms[s]);
       }
+      const double* b = (boxes && boxes[s]) ? boxes[s] : free_box;
+      memcpy(hbx + 9 * s, b, sizeof(double) * 9);
     }
-    const double* b = (boxes && boxes[s]) ? boxes[s] : free_box;
-    memcpy(hbx + 9 * s, b, sizeof(double) * 9);
-  }
-  int st = rgpot_b200_force_batch_packed(pot, nSystems, off.data(), hp, eam ? hz : nullptr, hbx,
-                                         pot->h_F.as<double>(), pot->h_E.as<double>(), statuses);
+  };
+  auto unpack = [&](size_t c0, size_t c1) {
+    for (size_t s = c0; s < c1; ++s) {
+      if (nAtoms[s] > 0) memcpy(forces[s], hF + 3 * off[s], sizeof(double) * 3 * nAtoms[s]);
+      energies[s] = hE[s];
+    }
+  };
+  const long nmax = batch_all_small(pot, nSystems, off.data());
+  if (nmax >= 0)  // packing of chunk k+1 overlaps the copies and kernels of chunk k
+    return batch_pipeline(pot, nSystems, off.data(), nmax, hp, eam ? hz : nullptr, hbx, hF, hE, statuses, pack,
+                          unpack);
+  pack(0, nSystems);
+  int st = rgpot_b200_force_batch_packed(pot, nSystems, off.data(), hp, eam ? hz : nullptr, hbx, hF, hE, statuses);
   if (st >= kStatusCuda) return st;
-  const double* hF = pot->h_F.as<double>();
-  const double* hE = pot->h_E.as<double>();
-  for (size_t s = 0; s < nSystems; ++s) {
-    if (nAtoms[s] > 0) memcpy(forces[s], hF + 3 * off[s], sizeof(double) * 3 * nAtoms[s]);
-    energies[s] = hE[s];
-  }
+  unpack(0, nSystems);
   return st;
 }
 
