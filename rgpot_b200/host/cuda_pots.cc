@@ -1,0 +1,102 @@
+// cuda_pots.cc -- host glue between rgpot's plugin interface and the engine's C ABI.
+#include "cuda_pots.hpp"
+
+#include <array>
+#include <cstring>
+#include <stdexcept>
+#include <vector>
+
+namespace rgpot {
+namespace b200detail {
+
+namespace {
+// FNV-1a over the config fields plus a kernel-version salt, the scheme of
+// CppCore/rgpot/ParamHash.hpp:19-51 / LJPot.hpp:54-59.  The salt differs from the CPU kernels'
+// (1) so a shared result cache never mixes CPU and GPU results.
+constexpr uint64_t kKernelVersion = 0xB2000001ull;
+struct Fnv {
+  uint64_t h = 0xcbf29ce484222325ull;
+  void bytes(const void *p, size_t n) {
+    const auto *b = static_cast<const unsigned char *>(p);
+    for (size_t i = 0; i < n; ++i) {
+      h ^= b[i];
+      h *= 0x100000001b3ull;
+    }
+  }
+  void u64(uint64_t v) { bytes(&v, sizeof v); }
+  void f64(double v) {
+    uint64_t b;
+    std::memcpy(&b, &v, sizeof b);
+    bytes(&b, sizeof b);
+  }
+};
+} // namespace
+
+Engine::Engine(int kind, const LJCudaConfig &c) {
+  RgpotB200Config cfg;
+  rgpot_b200_default_config(kind, &cfg);
+  cfg.device = c.device;
+  Fnv fp;
+  fp.u64(kKernelVersion);
+  if (kind != RGPOT_B200_CUH2) {
+    cfg.u0 = c.u0;
+    cfg.cutoff = c.cutoff;
+    cfg.psi = c.psi;
+    cfg.lj_all_images = c.all_images ? 1 : 0;
+    fp.f64(c.u0);
+    fp.f64(c.cutoff);
+    fp.f64(c.psi);
+  }
+  key_ = fp.h;
+  char err[512] = {0};
+  h_ = rgpot_b200_create(&cfg, err, sizeof err);
+  if (!h_) throw std::runtime_error(std::string("rgpot_b200 engine: ") + err);
+}
+
+Engine::~Engine() { rgpot_b200_destroy(h_); }
+
+// FortranPots.cc:44-56: "<pot> potential failed (status k): <message>"
+void Engine::raise(const char *label, int status) const {
+  std::array<char, 512> buffer{};
+  const int written = rgpot_b200_last_error(h_, buffer.data(), static_cast<int>(buffer.size()));
+  std::string message = std::string(label) + " potential failed (status " + std::to_string(status) + ")";
+  if (written > 0) {
+    message += ": ";
+    message.append(buffer.data(), static_cast<size_t>(written));
+  }
+  throw std::runtime_error(message);
+}
+
+void Engine::force(const char *label, const ForceInput &in, ForceOut *out) const {
+  const int status = rgpot_b200_force(h_, static_cast<long>(in.nAtoms), in.pos, in.atmnrs, out->F,
+                                      &out->energy, &out->variance, in.box);
+  if (status != 0) raise(label, status);
+  out->variance = 0.0;
+}
+
+void Engine::forceBatch(const char *label, const ForceBatch &batch) const {
+  const size_t n = batch.nSystems;
+  if (n == 0) return;
+  std::vector<size_t> natoms(n);
+  std::vector<const double *> pos(n), box(n);
+  std::vector<const int *> z(n);
+  std::vector<double *> frc(n);
+  std::vector<double> energy(n);
+  for (size_t i = 0; i < n; ++i) {
+    natoms[i] = batch.in[i].nAtoms;
+    pos[i] = batch.in[i].pos;
+    z[i] = batch.in[i].atmnrs;
+    box[i] = batch.in[i].box;
+    frc[i] = batch.out[i].F;
+  }
+  const int status = rgpot_b200_force_batch(h_, n, natoms.data(), pos.data(), z.data(), box.data(),
+                                            frc.data(), energy.data(), nullptr);
+  for (size_t i = 0; i < n; ++i) {
+    batch.out[i].energy = energy[i];
+    batch.out[i].variance = 0.0;
+  }
+  if (status != 0) raise(label, status);
+}
+
+} // namespace b200detail
+} // namespace rgpot

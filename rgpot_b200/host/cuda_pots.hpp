@@ -1,0 +1,94 @@
+// cuda_pots.hpp -- rgpot plugin classes backed by the B200 engine (include/rgpot_b200.h).
+//
+// Drop-in `Potential<Derived>` subclasses (CppCore/rgpot/Potential.hpp:138-343):
+//   rgpot::LJCudaPot         <->  rgpot::LJPot          (LennardJones/LJPot.hpp:40-86)
+//   rgpot::LJClusterCudaPot  <->  rgpot::LJClusterPot   (LennardJones/LJClusterPot.hpp:47-100)
+//   rgpot::CuH2CudaPot       <->  fortranpots::CuH2Pot  (fortran/FortranPots.hpp:29-45)
+// Same PotType (so cache keys and potserv's selector strings stay valid), same config aggregates,
+// same exception text on failure (FortranPots.cc:44-56); forceBatchImpl is native and
+// caps().batched is true.  Build against the real rgpot headers with
+// -DRGPOT_B200_USE_REFERENCE_HEADERS -I<rgpot>/CppCore, or standalone against rgpot_iface.hpp.
+#pragma once
+
+#ifdef RGPOT_B200_USE_REFERENCE_HEADERS
+#include "rgpot/ForceStructs.hpp"
+#include "rgpot/Potential.hpp"
+#include "rgpot/pot_caps.hpp"
+#include "rgpot/pot_types.hpp"
+#else
+#include "rgpot_iface.hpp"
+#endif
+
+#include <cstdint>
+#include <memory>
+#include <string>
+
+#include "../../include/rgpot_b200.h"
+
+namespace rgpot {
+
+/// LJConfig-compatible aggregate (LJPot.hpp:30-34) plus the device ordinal.
+struct LJCudaConfig {
+  double u0 = 1.0;
+  double cutoff = 15.0;
+  double psi = 1.0;
+  int device = -1;
+  bool all_images = false; ///< opt-in triclinic LJ (no reference counterpart)
+};
+
+namespace b200detail {
+
+/// Owns one engine handle; shared by the three classes below.
+class Engine {
+public:
+  Engine(int kind, const LJCudaConfig &c);
+  ~Engine();
+  Engine(const Engine &) = delete;
+  Engine &operator=(const Engine &) = delete;
+  void force(const char *label, const ForceInput &in, ForceOut *out) const;
+  void forceBatch(const char *label, const ForceBatch &batch) const;
+  [[nodiscard]] uint64_t paramsKey() const noexcept { return key_; }
+
+private:
+  [[noreturn]] void raise(const char *label, int status) const;
+  RgpotB200Pot *h_ = nullptr;
+  uint64_t key_ = 0;
+};
+
+} // namespace b200detail
+
+#define RGPOT_B200_POT_CLASS(ClassName, PotTypeValue, Kind, Label, Periodic)                       \
+  class ClassName : public Potential<ClassName> {                                                 \
+  public:                                                                                          \
+    ClassName() : ClassName(LJCudaConfig{}) {}                                                     \
+    explicit ClassName(const LJCudaConfig &c)                                                      \
+        : Potential(PotType::PotTypeValue), m_config(c),                                           \
+          m_engine(std::make_shared<b200detail::Engine>(Kind, c)) {}                               \
+    void forceImpl(const ForceInput &in, ForceOut *out) const override {                           \
+      m_engine->force(Label, in, out);                                                             \
+    }                                                                                              \
+    void forceBatchImpl(const ForceBatch &batch) const override {                                  \
+      m_engine->forceBatch(Label, batch);                                                          \
+    }                                                                                              \
+    [[nodiscard]] PotCaps caps() const noexcept override {                                         \
+      PotCaps c;                                                                                   \
+      c.reentrancy = Reentrancy::PerInstance; /* one stream + scratch per handle */                \
+      c.batched = true;                                                                            \
+      c.periodic = Periodic;                                                                       \
+      return c;                                                                                    \
+    }                                                                                              \
+    [[nodiscard]] uint64_t paramsKey() const noexcept override { return m_engine->paramsKey(); }   \
+    [[nodiscard]] const LJCudaConfig &config() const noexcept { return m_config; }                 \
+                                                                                                   \
+  private:                                                                                         \
+    LJCudaConfig m_config;                                                                         \
+    std::shared_ptr<b200detail::Engine> m_engine;                                                  \
+  }
+
+RGPOT_B200_POT_CLASS(LJCudaPot, LJ, RGPOT_B200_LJ, "LJ", true);
+RGPOT_B200_POT_CLASS(LJClusterCudaPot, LJCluster, RGPOT_B200_LJ_CLUSTER, "LJCluster", false);
+RGPOT_B200_POT_CLASS(CuH2CudaPot, CuH2, RGPOT_B200_CUH2, "CuH2", true);
+
+#undef RGPOT_B200_POT_CLASS
+
+} // namespace rgpot
