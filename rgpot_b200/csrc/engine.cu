@@ -22,6 +22,7 @@
 #include "gather.cuh"
 #include "physics.cuh"
 #include "small.cuh"
+#include "tile.cuh"
 
 using namespace rb;
 
@@ -430,7 +431,8 @@ int run_cell_path(RgpotB200Pot* pot, long n, const double* d_pos, const int* d_Z
   CU_TRY(pot, pot->spos.reserve(sizeof(double4) * n));
   CU_TRY(pot, pot->scell.reserve(sizeof(int) * n));
   const int nblk = div_up(n, 128);
-  CU_TRY(pot, pot->partials.reserve(sizeof(double) * nblk));
+  const int npart = std::max(nblk, ncells);
+  CU_TRY(pot, pot->partials.reserve(sizeof(double) * npart));
   if (eam) {
     CU_TRY(pot, pot->dfd.reserve(sizeof(double) * n));
     CU_TRY(pot, pot->eemb.reserve(sizeof(double) * n));
@@ -484,16 +486,59 @@ int run_cell_path(RgpotB200Pot* pot, long n, const double* d_pos, const int* d_Z
 
   double* d_part = pot->partials.as<double>();
   if (eam) {
+    const bool tile_ok = pl.grid.ns_lo[0] == 1 && pl.grid.ns_lo[1] == 1 && pl.grid.ns_lo[2] == 1 &&
+                         pl.grid.ns_hi[0] == 1 && pl.grid.ns_hi[1] == 1 && pl.grid.ns_hi[2] == 1;
+    if (tile_ok) {
+      // warp-per-cell tile kernels; the gather kernels cover atoms outside the cell (per-pair
+      // image shifts) -- each side returns at once when the binning flag is not its own
+      CU_TRY(pot, cudaMemsetAsync(d_part, 0, sizeof(double) * npart, st));
+      double edge = 0.0;
+      for (int k = 0; k < 3; ++k) {
+        // longest cell edge vector bounds the FP32 offsets
+        const double len = sqrt(pl.box.H[3 * k] * pl.box.H[3 * k] + pl.box.H[3 * k + 1] * pl.box.H[3 * k + 1] +
+                                pl.box.H[3 * k + 2] * pl.box.H[3 * k + 2]);
+        edge = std::max(edge, len / pl.grid.nc[k]);
+      }
+      const double margin = 1.0e-6 * 6.0 * edge + 1.0e-5 * rc;
+      const float thr2f = (float)((rc + margin) * (rc + margin) * (1.0 + 1.0e-6));
+      const int tb = div_up(ncells, kTileWarps);
+      k_eam_tile<0><<<tb, kTileWarps * 32, 0, st>>>(ga, thr2f, pot->dfd.as<double>(), pot->eemb.as<double>(),
+                                                   d_F, d_part, d_st);
+      LAUNCH_CHECK(pot, "k_eam_tile<density>");
+      k_eam_tile<1><<<tb, kTileWarps * 32, 0, st>>>(ga, thr2f, pot->dfd.as<double>(), pot->eemb.as<double>(),
+                                                   d_F, d_part, d_st);
+      LAUNCH_CHECK(pot, "k_eam_tile<force>");
+      ga.only_if_atom_shift = 1;
+    }
     k_eam_density<<<nblk, 128, 0, st>>>(ga, pot->dfd.as<double>(), pot->eemb.as<double>(), d_st);
     LAUNCH_CHECK(pot, "k_eam_density");
     k_eam_force<<<nblk, 128, 0, st>>>(ga, pot->dfd.as<double>(), pot->eemb.as<double>(), d_F, d_part);
     LAUNCH_CHECK(pot, "k_eam_force");
+    k_reduce_partials<<<1, 1024, 0, st>>>(d_part, tile_ok ? npart : nblk, d_E);
+    LAUNCH_CHECK(pot, "k_reduce_partials");
+    return 0;
   } else if (pl.geo == GEO_IMAGES) {
     k_lj_gather<GEO_IMAGES><<<nblk, 128, 0, st>>>(ga, d_F, d_part);
     LAUNCH_CHECK(pot, "k_lj_gather<images>");
   } else if (pl.geo == GEO_LJ_SHIFT) {
+    // warp-per-cell tile kernel; the literal-fold gather kernel covers the (rare) case of atoms
+    // outside the cell -- each of the two returns at once when the binning flag is not its own
+    CU_TRY(pot, cudaMemsetAsync(d_part, 0, sizeof(double) * npart, st));
+    double edge = 0.0;
+    for (int k = 0; k < 3; ++k) {
+      const double width = pl.box.periodic[k] ? pl.box.face[k] : pl.box.ext[k];
+      edge = std::max(edge, width / pl.grid.nc[k]);
+    }
+    const double margin = 1.0e-6 * 4.0 * edge + 1.0e-5 * rc;
+    const float thr2f = (float)((rc + margin) * (rc + margin) * (1.0 + 1.0e-6));
+    k_lj_tile<<<div_up(ncells, kTileWarps), kTileWarps * 32, 0, st>>>(ga, thr2f, d_F, d_part);
+    LAUNCH_CHECK(pot, "k_lj_tile");
+    ga.only_if_atom_shift = 1;
     k_lj_gather<GEO_LJ_SHIFT><<<nblk, 128, 0, st>>>(ga, d_F, d_part);
     LAUNCH_CHECK(pot, "k_lj_gather<shift>");
+    k_reduce_partials<<<1, 1024, 0, st>>>(d_part, npart, d_E);
+    LAUNCH_CHECK(pot, "k_reduce_partials");
+    return 0;
   } else {
     k_lj_gather<GEO_LJ_FOLD><<<nblk, 128, 0, st>>>(ga, d_F, d_part);
     LAUNCH_CHECK(pot, "k_lj_gather<fold>");

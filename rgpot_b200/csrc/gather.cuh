@@ -34,6 +34,8 @@ struct GatherArgs {
   LJParams lj;
   double rc2;           // GEO_IMAGES accept threshold (strict <)
   const Status* st_in;  // flags from binning (kFlagAtomShift selects the per-pair shift form)
+  int only_if_atom_shift;  // 1: run only when some atom sits outside the cell (the tile kernels
+                           //    of tile.cuh cover the other case)
 };
 
 // optional pair emission for rgpot_b200_neighbors
@@ -164,6 +166,7 @@ template <int GEO>
 __global__ void __launch_bounds__(128)
 k_lj_gather(GatherArgs a, double* __restrict__ F, double* __restrict__ partials) {
   __shared__ double sh32[32];
+  if (a.only_if_atom_shift && !(a.st_in->flags & kFlagAtomShift)) return;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   double e = 0.0, fx = 0.0, fy = 0.0, fz = 0.0;
   if (i < a.n) {
@@ -186,6 +189,7 @@ k_lj_gather(GatherArgs a, double* __restrict__ F, double* __restrict__ partials)
 __global__ void __launch_bounds__(128)
 k_eam_density(GatherArgs a, double* __restrict__ dfd_sorted, double* __restrict__ eemb_sorted,
               Status* __restrict__ st) {
+  if (a.only_if_atom_shift && !(a.st_in->flags & kFlagAtomShift)) return;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= a.n) return;
   const double4 pi = a.spos[i];
@@ -211,6 +215,7 @@ k_eam_force(GatherArgs a, const double* __restrict__ dfd_sorted,
             const double* __restrict__ eemb_sorted, double* __restrict__ F,
             double* __restrict__ partials) {
   __shared__ double sh32[32];
+  if (a.only_if_atom_shift && !(a.st_in->flags & kFlagAtomShift)) return;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   double e = 0.0, fx = 0.0, fy = 0.0, fz = 0.0;
   if (i < a.n) {
