@@ -267,7 +267,11 @@ def run_cuh2_batch(args, world, rank, local):
                 "unit": "TFLOP/s", "frac": achieved_tf / fp64_peak if fp64_peak else None,
                 "peak_source": "DFMA microbenchmark measured in this run (MEASURED_PEAKS.json has no FP64 entry)",
                 "flops_per_atom_eval": FLOPS_PER_ATOM["cuh2_batch"],
-                "traffic": None,
+                "traffic": (lambda t: None if t is None else t * n_atoms)(
+                    measured_traffic_per_atom("k_eam_small", 16384 * 218)),
+                "traffic_note": "DRAM read+write bytes of one k_eam_small launch, scaled per atom from the "
+                                "committed ncu capture (profiles/, 16384 configs); algorithmic bytes are "
+                                "76 B/atom-eval",
                 "hbm": {"achieved": hbm_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                         "frac": hbm_gbs / peaks["hbm_gbs"], "peak_source": peaks["source"]}}
     return {
@@ -340,6 +344,24 @@ def run_single_system(args, name, local):
                          "unit": "TFLOP/s", "frac": tf / fp64_peak if fp64_peak else None,
                          "note": "whole step (cell build + force kernels) timed, flops of the path"},
             "l2": "256 MB flush write between timed iterations"}
+
+
+def measured_traffic_per_atom(kernel_substr, atoms_in_capture):
+    """DRAM bytes per atom-eval of the dominant kernel from the committed `ncu --set full` capture
+    (profiles/r01_*_summary.json, dram__bytes_read.sum + dram__bytes_write.sum), or None."""
+    import glob
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_summary.json")), reverse=True):
+        try:
+            recs = json.load(open(path))
+        except (OSError, ValueError):
+            continue
+        for r in recs:
+            if kernel_substr in r.get("kernel", "") and "dram_read" in r:
+                scale = {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}
+                tot = r["dram_read"] * scale.get(r.get("dram_read_unit", "byte"), 1.0) + \
+                    r["dram_write"] * scale.get(r.get("dram_write_unit", "byte"), 1.0)
+                return tot / atoms_in_capture
+    return None
 
 
 def load_peaks():
