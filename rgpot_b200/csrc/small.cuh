@@ -185,6 +185,7 @@ k_eam_small(SmallArgs a) {
   __shared__ int blk_bad[2];
   __shared__ unsigned short q_i[14][64];  // per-warp survivor queues (<= 14 warps per block)
   __shared__ unsigned short q_j[14][64];
+  __shared__ int hist[256];
 
   const int sys = blockIdx.x;
   const long long base = a.off[sys];
@@ -483,17 +484,39 @@ k_eam_small(SmallArgs a) {
     }
   }
 
-  // ---- phase C: rank atoms by decreasing neighbor count (ties by index: deterministic)
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    const int ci = cnt[i];
-    int rank = 0;
-    for (int j = 0; j < n; ++j) {
-      const int cj = cnt[j];
-      rank += (cj > ci) || (cj == ci && j < i);
-    }
-    perm[rank] = i;
+  // ---- phase C: order atoms by decreasing neighbor count (counting sort).  The order only decides
+  // which lanes work on which atom; every per-atom result, and the energy sum below (taken in atom
+  // order), is independent of it, so the integer atomics do not disturb reproducibility.
+  for (int b = threadIdx.x; b < 256; b += blockDim.x) hist[b] = 0;
+  __syncthreads();
+  int my_rank[2] = {0, 0};  // blockDim >= n / 2 for every launch configuration (n <= 511, >= 256 threads)
+  {
+    int k = 0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x, ++k) my_rank[k & 1] = atomicAdd(&hist[min(cnt[i], 255)], 1);
   }
   __syncthreads();
+  if (warp == 0) {  // exclusive scan over the bins, largest count first
+    int carry = 0;
+    for (int base = 255; base >= 0; base -= 32) {
+      const int b = base - lane;
+      const int v = hist[b];
+      int incl = v;
+#pragma unroll
+      for (int off = 1; off < 32; off <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, off);
+        if (lane >= off) incl += t;
+      }
+      hist[b] = carry + incl - v;
+      carry += __shfl_sync(0xffffffffu, incl, 31);
+    }
+  }
+  __syncthreads();
+  {
+    int k = 0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x, ++k) perm[hist[min(cnt[i], 255)] + my_rank[k & 1]] = i;
+  }
+  __syncthreads();
+  double* eatom = g3;  // per-atom energies (the fractional coordinates are no longer needed)
 
   const int sub = threadIdx.x % TPA;
   const int grp = threadIdx.x / TPA;
@@ -533,7 +556,7 @@ k_eam_small(SmallArgs a) {
       double emb, demb;
       eam_embed(spc[i], rho, emb, demb);
       dfd[i] = demb;
-      e += emb;
+      eatom[i] = emb;
     }
   }
   __syncthreads();
@@ -583,9 +606,11 @@ k_eam_small(SmallArgs a) {
       a.F[3 * (base + i)] = fx;
       a.F[3 * (base + i) + 1] = fy;
       a.F[3 * (base + i) + 2] = fz;
-      e += ep;
+      eatom[i] += ep;
     }
   }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += blockDim.x) e += eatom[i];  // atom order: reproducible
   const double bs = block_sum(e, sh32);
   if (threadIdx.x == 0) {
     a.E[sys] = bs;
