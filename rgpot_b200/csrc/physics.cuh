@@ -202,11 +202,28 @@ RB_D void eam_force_entry(int zi, int zj, double dfd_i, double dfd_j, double vx,
   double r, rinv;
   radial(d2, r, rinv);
   double phi, w;
-  eam_phi(pair_kind(zi, zj), r, rinv, phi, w);
+  if ((zi | zj) == 0) {
+    // Cu-Cu (the bulk of every slab): every coefficient index is static, so the constants are
+    // operands of the FP64 instructions instead of separately loaded registers
+    const double eb = exp_fast(-c_eam.ab[0] * r);
+    const double ea = c_eam.cucu_square ? eb * eb : exp_fast(-c_eam.aa[0] * r);
+    const double t1 = c_eam.da[0] * ea;
+    const double t2 = c_eam.db[0] * eb;
+    phi = t1 + t2 - c_eam.phicut[0];
+    w = -fma(c_eam.aa[0], t1, c_eam.ab[0] * t2) * rinv;
+    const CuDensityTerms t = cu_density_terms(r);
+    const double g2 = c_eam.gamma[0] * t.eb;
+    const double t3 = c_eam.scale[0] * t.r6;
+    const double raw = t3 * (t.ea + g2);
+    const double drho = (6.0 * raw * rinv - t3 * fma(c_eam.bb[0], g2, c_eam.ba[0] * t.ea)) * rinv;
+    w = fma(drho, dfd_i + dfd_j, w);  // the same density derivative acts at both ends
+  } else {
+    eam_phi(pair_kind(zi, zj), r, rinv, phi, w);
+    const double drho_ij = eam_drho(zj, r, rinv);                         // what j deposits on i
+    const double drho_ji = (zi == zj) ? drho_ij : eam_drho(zi, r, rinv);  // what i deposits on j
+    w = w + drho_ij * dfd_i + drho_ji * dfd_j;
+  }
   e += 0.5 * phi;
-  const double drho_ij = eam_drho(zj, r, rinv);                         // what j deposits on i
-  const double drho_ji = (zi == zj) ? drho_ij : eam_drho(zi, r, rinv);  // what i deposits on j
-  w = w + drho_ij * dfd_i + drho_ji * dfd_j;
   fx = fma(w, vx, fx);
   fy = fma(w, vy, fy);
   fz = fma(w, vz, fz);
