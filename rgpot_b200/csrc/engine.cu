@@ -338,7 +338,8 @@ int check_launch(RgpotB200Pot* pot, const char* what) {
 // Cell-list path for ONE system whose positions / Z already sit on the device.
 // Leaves forces in d_F (original order), energy in d_E[0], flags in pot->status.
 int run_cell_path(RgpotB200Pot* pot, long n, const double* d_pos, const int* d_Z, double* d_F,
-                  double* d_E, const double* box, cudaStream_t st, const EmitArgs* emit) {
+                  double* d_E, const double* box, cudaStream_t st, const EmitArgs* emit,
+                  bool allow_tile = true) {
   const int kind = pot->cfg.kind;
   const bool eam = kind == RGPOT_B200_CUH2;
   const bool images = eam || pot->cfg.lj_all_images;
@@ -486,8 +487,9 @@ int run_cell_path(RgpotB200Pot* pot, long n, const double* d_pos, const int* d_Z
 
   double* d_part = pot->partials.as<double>();
   if (eam) {
-    const bool tile_ok = pl.grid.ns_lo[0] == 1 && pl.grid.ns_lo[1] == 1 && pl.grid.ns_lo[2] == 1 &&
-                         pl.grid.ns_hi[0] == 1 && pl.grid.ns_hi[1] == 1 && pl.grid.ns_hi[2] == 1;
+    const bool tile_ok = allow_tile && pl.grid.ns_lo[0] == 1 && pl.grid.ns_lo[1] == 1 &&
+                         pl.grid.ns_lo[2] == 1 && pl.grid.ns_hi[0] == 1 && pl.grid.ns_hi[1] == 1 &&
+                         pl.grid.ns_hi[2] == 1;
     if (tile_ok) {
       // warp-per-cell tile kernels; the gather kernels cover atoms outside the cell (per-pair
       // image shifts) -- each side returns at once when the binning flag is not its own
@@ -502,12 +504,11 @@ int run_cell_path(RgpotB200Pot* pot, long n, const double* d_pos, const int* d_Z
       const double margin = 1.0e-6 * 6.0 * edge + 1.0e-5 * rc;
       const float thr2f = (float)((rc + margin) * (rc + margin) * (1.0 + 1.0e-6));
       const int tb = div_up(ncells, kTileWarps);
-      k_eam_tile<0><<<tb, kTileWarps * 32, 0, st>>>(ga, thr2f, pot->dfd.as<double>(), pot->eemb.as<double>(),
-                                                   d_F, d_part, d_st);
-      LAUNCH_CHECK(pot, "k_eam_tile<density>");
-      k_eam_tile<1><<<tb, kTileWarps * 32, 0, st>>>(ga, thr2f, pot->dfd.as<double>(), pot->eemb.as<double>(),
-                                                   d_F, d_part, d_st);
-      LAUNCH_CHECK(pot, "k_eam_tile<force>");
+      TileOut to{d_F, d_part, pot->dfd.as<double>(), pot->eemb.as<double>(), d_st};
+      k_tile<TILE_EAM_DENSITY><<<tb, kTileWarps * 32, 0, st>>>(ga, thr2f, to);
+      LAUNCH_CHECK(pot, "k_tile<eam density>");
+      k_tile<TILE_EAM_FORCE><<<tb, kTileWarps * 32, 0, st>>>(ga, thr2f, to);
+      LAUNCH_CHECK(pot, "k_tile<eam force>");
       ga.only_if_atom_shift = 1;
     }
     k_eam_density<<<nblk, 128, 0, st>>>(ga, pot->dfd.as<double>(), pot->eemb.as<double>(), d_st);
@@ -520,7 +521,7 @@ int run_cell_path(RgpotB200Pot* pot, long n, const double* d_pos, const int* d_Z
   } else if (pl.geo == GEO_IMAGES) {
     k_lj_gather<GEO_IMAGES><<<nblk, 128, 0, st>>>(ga, d_F, d_part);
     LAUNCH_CHECK(pot, "k_lj_gather<images>");
-  } else if (pl.geo == GEO_LJ_SHIFT) {
+  } else if (pl.geo == GEO_LJ_SHIFT && allow_tile) {
     // warp-per-cell tile kernel; the literal-fold gather kernel covers the (rare) case of atoms
     // outside the cell -- each of the two returns at once when the binning flag is not its own
     CU_TRY(pot, cudaMemsetAsync(d_part, 0, sizeof(double) * npart, st));
@@ -531,14 +532,18 @@ int run_cell_path(RgpotB200Pot* pot, long n, const double* d_pos, const int* d_Z
     }
     const double margin = 1.0e-6 * 4.0 * edge + 1.0e-5 * rc;
     const float thr2f = (float)((rc + margin) * (rc + margin) * (1.0 + 1.0e-6));
-    k_lj_tile<<<div_up(ncells, kTileWarps), kTileWarps * 32, 0, st>>>(ga, thr2f, d_F, d_part);
-    LAUNCH_CHECK(pot, "k_lj_tile");
+    TileOut to{d_F, d_part, nullptr, nullptr, d_st};
+    k_tile<TILE_LJ><<<div_up(ncells, kTileWarps), kTileWarps * 32, 0, st>>>(ga, thr2f, to);
+    LAUNCH_CHECK(pot, "k_tile<lj>");
     ga.only_if_atom_shift = 1;
     k_lj_gather<GEO_LJ_SHIFT><<<nblk, 128, 0, st>>>(ga, d_F, d_part);
     LAUNCH_CHECK(pot, "k_lj_gather<shift>");
     k_reduce_partials<<<1, 1024, 0, st>>>(d_part, npart, d_E);
     LAUNCH_CHECK(pot, "k_reduce_partials");
     return 0;
+  } else if (pl.geo == GEO_LJ_SHIFT) {
+    k_lj_gather<GEO_LJ_SHIFT><<<nblk, 128, 0, st>>>(ga, d_F, d_part);
+    LAUNCH_CHECK(pot, "k_lj_gather<shift>");
   } else {
     k_lj_gather<GEO_LJ_FOLD><<<nblk, 128, 0, st>>>(ga, d_F, d_part);
     LAUNCH_CHECK(pot, "k_lj_gather<fold>");
@@ -898,7 +903,7 @@ static int finish_single(RgpotB200Pot* pot, long n, const double* d_pos, const i
     CU_TRY(pot, cudaStreamSynchronize(st));
     if (flags & kFlagListOverflow) {
       pot->pend.small_single = false;
-      int s = run_cell_path(pot, n, d_pos, d_Z, d_F, d_E, box, st, nullptr);
+      int s = run_cell_path(pot, n, d_pos, d_Z, d_F, d_E, box, st, nullptr, false);
       if (s) return s;
       return finish_single(pot, n, d_pos, d_Z, d_F, d_E, box, st, host_pos, host_Z);
     }
@@ -908,6 +913,13 @@ static int finish_single(RgpotB200Pot* pot, long n, const double* d_pos, const i
     Status stt{};
     CU_TRY(pot, cudaMemcpyAsync(&stt, pot->status.p, sizeof stt, cudaMemcpyDeviceToHost, st));
     CU_TRY(pot, cudaStreamSynchronize(st));
+    if (stt.flags & kFlagListOverflow) {
+      // a tile kernel ran out of piece slots (very sparse survivors): redo on the gather kernels
+      int s = run_cell_path(pot, n, d_pos, d_Z, d_F, d_E, box, st, nullptr, false);
+      if (s) return s;
+      CU_TRY(pot, cudaMemcpyAsync(&stt, pot->status.p, sizeof stt, cudaMemcpyDeviceToHost, st));
+      CU_TRY(pot, cudaStreamSynchronize(st));
+    }
     flags = stt.flags;
     bad = stt.first_bad_atom;
     if ((flags & kFlagForeignZ) && bad != INT_MAX) {
@@ -1211,7 +1223,7 @@ static int batch_finish(RgpotB200Pot* pot, size_t nsys, const size_t* offsets, c
       int rs = fetch_box(pot, h_boxes, d_boxes, s, hbox);
       if (rs) return rs;
       rs = run_cell_path(pot, n, d_pos + 3 * o, d_Z ? d_Z + o : nullptr, d_F + 3 * o, d_E + s, hbox, st,
-                         nullptr);
+                         nullptr, false);
       if (rs >= kStatusCuda) return rs;
       Status stt{};
       if (rs == 0) {
