@@ -192,20 +192,19 @@ __global__ void k_scatter(const int* __restrict__ cell_of, const int* __restrict
   if (i < n) order[starts[cell_of[i]] + rank[i]] = i;
 }
 
-// one thread per cell: insertion sort of the cell's (short) segment by original index
-__global__ void k_cell_order(const int* __restrict__ starts, int ncells, int* __restrict__ order) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= ncells) return;
+// deterministic order inside a cell: every atom finds its rank among the atoms of its cell (the
+// number of cell mates with a smaller original index) and moves there.  One thread per atom, so
+// the cost does not depend on how few cells there are.
+__global__ void k_cell_order(const int* __restrict__ starts, const int* __restrict__ cell_of,
+                             const int* __restrict__ order_in, int n, int* __restrict__ order_out) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n) return;
+  const int i = order_in[s];
+  const int c = cell_of[i];
   const int b = starts[c], e = starts[c + 1];
-  for (int a = b + 1; a < e; ++a) {
-    const int v = order[a];
-    int p = a - 1;
-    while (p >= b && order[p] > v) {
-      order[p + 1] = order[p];
-      --p;
-    }
-    order[p + 1] = v;
-  }
+  int rank = 0;
+  for (int t = b; t < e; ++t) rank += order_in[t] < i;
+  order_out[b + rank] = i;
 }
 
 // sorted records; species from atomic numbers (rgpot_cuh2.f90:463-489 classify) when check_z

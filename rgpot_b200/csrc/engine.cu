@@ -163,7 +163,7 @@ struct RgpotB200Pot {
   std::string last_error;
 
   // single-system scratch
-  DevBuf pos, Z, F, cell_of, rank, ashift, counts, starts, blocksums, order, spos, scell, dfd, eemb,
+  DevBuf pos, Z, F, cell_of, rank, ashift, counts, starts, blocksums, order, order2, spos, scell, dfd, eemb,
       partials, energy, status, mm, emit_pairs, emit_shifts, emit_count;
   // batch scratch
   DevBuf b_pos, b_Z, b_F, b_off, b_boxes, b_E, b_flags, b_bad, b_map;
@@ -188,7 +188,7 @@ struct RgpotB200Pot {
 
   ~RgpotB200Pot() {
     cudaSetDevice(device);
-    DevBuf* d[] = {&pos, &Z, &F, &cell_of, &rank, &ashift, &counts, &starts, &blocksums, &order,
+    DevBuf* d[] = {&pos, &Z, &F, &cell_of, &rank, &ashift, &counts, &starts, &blocksums, &order, &order2,
                    &spos, &scell, &dfd, &eemb, &partials, &energy, &status, &mm, &emit_pairs,
                    &emit_shifts, &emit_count, &b_pos, &b_Z, &b_F, &b_off, &b_boxes, &b_E, &b_flags,
                    &b_bad, &b_map};
@@ -455,9 +455,11 @@ int run_cell_path(RgpotB200Pot* pot, long n, const double* d_pos, const int* d_Z
   k_scatter<<<div_up(n, 256), 256, 0, st>>>(pot->cell_of.as<int>(), pot->rank.as<int>(),
                                             pot->starts.as<int>(), (int)n, pot->order.as<int>());
   LAUNCH_CHECK(pot, "k_scatter");
-  k_cell_order<<<div_up(ncells, 128), 128, 0, st>>>(pot->starts.as<int>(), ncells, pot->order.as<int>());
+  CU_TRY(pot, pot->order2.reserve(sizeof(int) * n));
+  k_cell_order<<<div_up(n, 256), 256, 0, st>>>(pot->starts.as<int>(), pot->cell_of.as<int>(),
+                                               pot->order.as<int>(), (int)n, pot->order2.as<int>());
   LAUNCH_CHECK(pot, "k_cell_order");
-  k_gather_sorted<<<div_up(n, 256), 256, 0, st>>>(d_pos, d_Z, pot->order.as<int>(),
+  k_gather_sorted<<<div_up(n, 256), 256, 0, st>>>(d_pos, d_Z, pot->order2.as<int>(),
                                                   pot->cell_of.as<int>(), pot->ashift.as<int>(), (int)n,
                                                   eam ? 1 : 0, pot->spos.as<double4>(),
                                                   pot->scell.as<int>(), d_st);
