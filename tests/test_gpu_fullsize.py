@@ -1,0 +1,103 @@
+"""BASELINE.json's full sizes, checked through size-independent properties (the CPU oracle is
+O(N^2) for LJ and minutes for 14M atom-evals, so it only samples here)."""
+import numpy as np
+import pytest
+
+import rgpot_b200
+from rgpot_b200 import workloads
+
+pytestmark = pytest.mark.gpu
+
+
+def _close(a, b, rtol=1e-10, atol=1e-9):
+    return np.abs(a - b) <= atol + rtol * np.abs(b)
+
+
+def test_lj_fluid_1m_properties(oracle):
+    """configs[2]: 1 000 000 atoms, rc = 2.5 sigma, cubic periodic box."""
+    pos, Z, box = workloads.lj_fluid()
+    n = len(pos)
+    assert n == 1_000_000
+    pot = rgpot_b200.LJPot(rgpot_b200.LJConfig(1.0, 2.5, 1.0))
+    e, f, _ = pot(pos, Z, box)  # tile kernels (every atom inside the cell)
+    assert np.isfinite(e) and np.isfinite(f).all()
+    # Newton's third law holds pair by pair in the reference's scatter form: zero net force
+    assert np.abs(f.sum(0)).max() < 1e-6
+    # same physics with half the atoms moved by whole box vectors: the literal-fold gather kernel
+    # runs instead of the tile kernel and must agree
+    L = box[0, 0]
+    moved = pos.copy()
+    moved[::2] += np.array([L, -2 * L, 3 * L])
+    e2, f2, _ = pot(moved, Z, box)
+    assert abs(e2 - e) <= 1e-10 * abs(e)
+    assert _close(f2, f, rtol=1e-9, atol=1e-8).all()  # the fold loses a few ulp at |x| ~ 3 L
+    # relabelling the atoms permutes the forces and leaves the energy alone
+    perm = np.random.default_rng(5).permutation(n)
+    e3, f3, _ = pot(pos[perm], Z, box)
+    assert abs(e3 - e) <= 1e-10 * abs(e)
+    assert _close(f3, f[perm]).all()
+    # spot check against the reference algorithm on a sub-box the O(N^2) oracle can afford:
+    # forces on atoms deep inside a slab only depend on neighbours within rc
+    sel = np.where((pos[:, 0] < 14.0) & (pos[:, 1] < 14.0) & (pos[:, 2] < 14.0))[0]
+    core = np.where((pos[:, 0] > 2.6) & (pos[:, 0] < 11.4) & (pos[:, 1] > 2.6) & (pos[:, 1] < 11.4) &
+                    (pos[:, 2] > 2.6) & (pos[:, 2] < 11.4))[0]
+    sub = pos[sel]
+    _, f_o, _ = oracle.lj_force(sub, np.eye(3) * 1000.0, 1.0, 2.5, 1.0, cluster=True)
+    lookup = {g: k for k, g in enumerate(sel)}
+    idx = np.array([lookup[g] for g in core])
+    assert len(idx) > 500
+    assert _close(f[core], f_o[idx]).all()
+
+
+def test_cuh2_slab_256k_properties(oracle):
+    """configs[3]: 256 000 Cu + 512 H, triclinic (sheared) periodic cell."""
+    pos, Z, box = workloads.cu_slab_triclinic()
+    assert len(pos) == 256_512
+    pot = rgpot_b200.CuH2Pot()
+    e, f, _ = pot(pos, Z, box)  # tile kernels
+    assert np.isfinite(e) and np.abs(f.sum(0)).max() < 1e-6
+    # atoms pushed out of the cell by whole cell vectors: per-pair image shifts, gather kernels
+    rng = np.random.default_rng(2)
+    moved = pos + rng.integers(-2, 3, size=pos.shape) @ box
+    e2, f2, _ = pot(moved, Z, box)
+    assert abs(e2 - e) <= 1e-10 * abs(e)
+    assert _close(f2, f, rtol=1e-9, atol=1e-8).all()
+    # pin the absolute physics at this size through the commensurate-shear identity:
+    # a perfect 40^3 fcc crystal has the bulk energy per atom the oracle gives for 4^3 cells
+    # (-906.183991113513 eV / 256 atoms), in the cubic cell and in any lattice-commensurate shear
+    a = 3.615
+    crystal = workloads._fcc(40, a) + 0.1
+    Zc = np.full(len(crystal), 29, dtype=np.int32)
+    cubic = np.diag([40 * a] * 3)
+    sheared = np.array([[40 * a, 0, 0], [10 * a, 40 * a, 0], [5 * a, 5 * a, 40 * a]])
+    e_bulk = -906.183991113513 / 256 * len(crystal)
+    e_c, f_c, _ = pot(workloads.wrap_into_cell(crystal, cubic), Zc, cubic)
+    e_s, f_s, _ = pot(workloads.wrap_into_cell(crystal, sheared), Zc, sheared)
+    assert abs(e_c - e_bulk) <= 1e-10 * abs(e_bulk)
+    assert abs(e_s - e_bulk) <= 1e-10 * abs(e_bulk)
+    assert np.abs(f_c).max() < 1e-8 and np.abs(f_s).max() < 1e-8
+
+
+def test_cuh2_batch_65536_properties(oracle):
+    """configs[4]: 65 536 perturbed 218-atom configurations in one call."""
+    n_cfg = 65536
+    offsets, pos, Z, boxes = workloads.cuh2_batch(n_cfg)
+    pot = rgpot_b200.CuH2Pot()
+    E, F = pot.forceBatchPacked(offsets, pos, Z, boxes)
+    assert np.isfinite(E).all() and np.isfinite(F).all()
+    # independence: evaluating two halves separately gives bit-identical results
+    half = n_cfg // 2
+    a0 = int(offsets[half])
+    E1, F1 = pot.forceBatchPacked(offsets[: half + 1], pos[:a0], Z[:a0], boxes[:half])
+    E2, F2 = pot.forceBatchPacked(offsets[half:] - offsets[half], pos[a0:], Z[a0:], boxes[half:])
+    assert np.array_equal(E, np.concatenate([E1, E2]))
+    assert np.array_equal(F, np.concatenate([F1, F2]))
+    # zero net force per configuration
+    net = np.abs(F.reshape(n_cfg, 218, 3).sum(1)).max()
+    assert net < 1e-9
+    # a random sample against the oracle
+    for s in np.random.default_rng(0).choice(n_cfg, 24, replace=False):
+        b, e_ = int(offsets[s]), int(offsets[s + 1])
+        e_o, f_o = oracle.cuh2_force(pos[b:e_], Z[b:e_], boxes[s].reshape(3, 3))
+        assert abs(E[s] - e_o) <= 1e-10 * abs(e_o)
+        assert _close(F[b:e_], f_o).all()
