@@ -11,7 +11,8 @@ import os
 import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "librgpot_b200.so")
+# RGPOT_B200_ENGINE selects another build of the same ABI (A/B timing of kernel variants)
+LIB_PATH = os.environ.get("RGPOT_B200_ENGINE") or os.path.join(HERE, "librgpot_b200.so")
 CSRC = os.path.join(HERE, "csrc")
 
 KIND_LJ, KIND_LJ_CLUSTER, KIND_CUH2 = 0, 1, 2
