@@ -1007,7 +1007,16 @@ int rgpot_b200_force(RgpotB200Pot* pot, long nAtoms, const double* positions, co
   pot->last_error.clear();
   if (variance) *variance = 0.0;
   if (energy) *energy = 0.0;
-  if (nAtoms > 0 && forces) memset(forces, 0, sizeof(double) * 3 * (size_t)nAtoms);
+  // outputs are zeroed on every early return and on failure (the reference zeroes first,
+  // LJPot.cc:44-49 / rgpot_cuh2_capi.f90:47-48); on success they are overwritten wholesale
+  struct ZeroOnExit {
+    double* f;
+    size_t n;
+    bool armed = true;
+    ~ZeroOnExit() {
+      if (armed && f && n) memset(f, 0, sizeof(double) * 3 * n);
+    }
+  } zero{forces, nAtoms > 0 ? (size_t)nAtoms : 0};
   if (!energy || (nAtoms > 0 && (!positions || !forces)))
     return fail(pot, kStatusArgs, "rgpot_b200_force: null buffer");
   CU_TRY(pot, cudaSetDevice(pot->device));
@@ -1040,6 +1049,7 @@ int rgpot_b200_force(RgpotB200Pot* pot, long nAtoms, const double* positions, co
   CU_TRY(pot, cudaMemcpyAsync(forces, pot->F.p, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost, st));
   CU_TRY(pot, cudaMemcpyAsync(energy, pot->energy.p, sizeof(double), cudaMemcpyDeviceToHost, st));
   CU_TRY(pot, cudaStreamSynchronize(st));
+  zero.armed = false;
   return 0;
 }
 

@@ -175,11 +175,18 @@ class _EnginePot:
     def launch_count(self) -> int:
         return int(self._lib.rgpot_b200_launch_count(self._h))
 
-    def __call__(self, positions, atom_types, box):
+    def __call__(self, positions, atom_types, box, out=None):
+        """(energy, forces, variance).  `out`, if given, is a C-contiguous float64 (n, 3) array that
+        receives the forces (e.g. a `pinned_empty` buffer reused across calls)."""
         pos = _as_positions(positions)
         types = _as_types(atom_types, pos.shape[0])
         cell = _as_box(box)
-        forces = np.zeros_like(pos)
+        if out is None:
+            forces = np.empty_like(pos)  # the engine overwrites (or zeroes) every element
+        else:
+            forces = out
+            if forces.shape != pos.shape or forces.dtype != np.float64 or not forces.flags.c_contiguous:
+                raise ValueError("out must be a C-contiguous float64 array of shape (n_atoms, 3)")
         e, v = C.c_double(0.0), C.c_double(0.0)
         st = self._lib.rgpot_b200_force(self._h, pos.shape[0], pos.ctypes.data, types.ctypes.data,
                                         forces.ctypes.data, C.byref(e), C.byref(v), cell.ctypes.data)
