@@ -46,7 +46,7 @@ extern "C" {
 #endif
 
 #define RGPOT_B200_API __attribute__((visibility("default")))
-#define RGPOT_B200_ABI_VERSION 1
+#define RGPOT_B200_ABI_VERSION 2
 
 typedef struct RgpotB200Pot RgpotB200Pot;
 
@@ -54,7 +54,9 @@ typedef struct RgpotB200Pot RgpotB200Pot;
 enum {
   RGPOT_B200_LJ = 0,         /**< PotType::LJ        -- periodic, orthorhombic nearest image */
   RGPOT_B200_LJ_CLUSTER = 1, /**< PotType::LJCluster -- free boundaries                       */
-  RGPOT_B200_CUH2 = 2        /**< PotType::CuH2      -- Cu/H EAM, all images inside 6.1 A     */
+  RGPOT_B200_CUH2 = 2,       /**< PotType::CuH2      -- Cu/H EAM, all images inside 6.1 A     */
+  RGPOT_B200_MORSE = 3       /**< PotType::Morse     -- shifted Morse pair potential, same pair search as
+                                  LJ (CppCore/rgpot/Morse/MorsePot.{hpp,cc}); SURVEY 8(f) rank 1 */
 };
 
 typedef struct RgpotB200Config {
@@ -68,6 +70,10 @@ typedef struct RgpotB200Config {
    *     no reference counterpart exists for this mode.                                      */
   int lj_all_images;
   int reserved[7];
+  /** MorseConfig (Morse/MorsePot.hpp:31-36): De, a, re; the cutoff goes in `cutoff` (default 9.5).
+   *  Defaults 0.7102 eV, 1.6047 1/A, 2.8970 A (platinum).  Unused by the other kinds.        */
+  double morse_De, morse_a, morse_re;
+  double reserved_f;
 } RgpotB200Config;
 
 RGPOT_B200_API int rgpot_b200_abi_version(void);

@@ -87,6 +87,42 @@ long oracle_lj_force(long n, const double *pos, const double *box, double u0, do
   return visited;
 }
 
+/* MorsePot::forceImpl, CppCore/rgpot/Morse/MorsePot.cc:33-78 (same scan and fold as LJPot),
+ * shift CppCore/rgpot/Morse/MorsePot.hpp:56-61. */
+long oracle_morse_force(long n, const double *pos, const double *box, double De, double a,
+                        double re, double cutoff, double *F, double *energy) {
+  *energy = 0.0;
+  for (long i = 0; i < 3 * n; ++i) F[i] = 0.0;
+  if (n < 2 || cutoff <= 0.0) return 0; /* MorsePot.cc:43-45 */
+  const double dc = 1.0 - exp(-a * (cutoff - re));
+  const double ecut = De * dc * dc - De;
+  const double twoDeA = 2.0 * De * a;
+  scan_t s;
+  scan_setup(&s, box, cutoff, 0);
+  double acc = 0.0;
+  long visited = 0;
+  for (long i = 0; i < n; ++i) {
+    for (long j = i + 1; j < n; ++j) {
+      double dv[3];
+      const double r2 = folded(&s, pos, i, j, dv);
+      if (r2 <= s.rc2) {
+        const double r = sqrt(r2);
+        const double d = 1.0 - exp(-a * (r - re));
+        acc += De * d * d - De - ecut;
+        const double fs = twoDeA * d * (d - 1.0) / r;
+        for (int k = 0; k < 3; ++k) {
+          const double f = fs * (-dv[k]);
+          F[3 * i + k] += f;
+          F[3 * j + k] -= f;
+        }
+        ++visited;
+      }
+    }
+  }
+  *energy = acc;
+  return visited;
+}
+
 long oracle_lj_pairs(long n, const double *pos, const double *box, double cutoff, int cluster,
                      int32_t *pairs, long cap) {
   if (n < 2 || (!cluster && cutoff <= 0.0)) return 0;

@@ -32,6 +32,10 @@ extern "C" {
 long oracle_lj_force(long n, const double *pos, const double *box, double u0, double cutoff,
                      double psi, int cluster, double *F, double *energy);
 
+/* MorsePot::forceImpl: CppCore/rgpot/Morse/MorsePot.cc:33-78.            */
+long oracle_morse_force(long n, const double *pos, const double *box, double De, double a,
+                        double re, double cutoff, double *F, double *energy);
+
 /* Same scan, pair set only: writes up to cap (i, j) pairs (i < j) into pairs[2*k..]
  * and returns the total count.  vesin_visit.hpp:82-110.                            */
 long oracle_lj_pairs(long n, const double *pos, const double *box, double cutoff, int cluster,

@@ -45,6 +45,9 @@ def _declare_common(lib):
     lib.oracle_lj_force.restype = C.c_long
     lib.oracle_lj_force.argtypes = [C.c_long, _f64p, _f64p, C.c_double, C.c_double, C.c_double,
                                     C.c_int, _f64p, C.POINTER(C.c_double)]
+    lib.oracle_morse_force.restype = C.c_long
+    lib.oracle_morse_force.argtypes = [C.c_long, _f64p, _f64p, C.c_double, C.c_double, C.c_double,
+                                       C.c_double, _f64p, C.POINTER(C.c_double)]
     lib.oracle_lj_pairs.restype = C.c_long
     lib.oracle_lj_pairs.argtypes = [C.c_long, _f64p, _f64p, C.c_double, C.c_int, _i32p, C.c_long]
     lib.oracle_nlist_build.restype = C.c_int
@@ -95,6 +98,9 @@ def ref_lib():
         _REF.ref_lj_force.restype = C.c_int
         _REF.ref_lj_force.argtypes = [C.c_long, _f64p, _i32p, _f64p, C.c_double, C.c_double,
                                       C.c_double, C.c_int, _f64p, C.POINTER(C.c_double)]
+        _REF.ref_morse_force.restype = C.c_int
+        _REF.ref_morse_force.argtypes = [C.c_long, _f64p, _i32p, _f64p, C.c_double, C.c_double,
+                                         C.c_double, C.c_double, _f64p, C.POINTER(C.c_double)]
         _REF.ref_lj_params_key.restype = C.c_uint64
         _REF.ref_lj_params_key.argtypes = [C.c_double, C.c_double, C.c_double, C.c_int]
         _REF.ref_table_new.restype = C.c_void_p
@@ -122,6 +128,24 @@ def lj_force(pos, box, u0=1.0, cutoff=15.0, psi=1.0, cluster=False):
     npairs = oracle_lib().oracle_lj_force(len(pos), pos, box, u0, cutoff, psi, int(cluster), F,
                                           C.byref(e))
     return e.value, F, npairs
+
+
+def morse_force(pos, box, De=0.7102, a=1.6047, re=2.8970, cutoff=9.5):
+    pos, box = _prep(pos, box)
+    F = np.zeros_like(pos)
+    e = C.c_double(0.0)
+    n = oracle_lib().oracle_morse_force(len(pos), pos, box, De, a, re, cutoff, F, C.byref(e))
+    return e.value, F, n
+
+
+def ref_morse_force(pos, box, De=0.7102, a=1.6047, re=2.8970, cutoff=9.5):
+    pos, box = _prep(pos, box)
+    Z = np.full(len(pos), 78, dtype=np.int32)
+    F = np.zeros_like(pos)
+    e = C.c_double(0.0)
+    if ref_lib().ref_morse_force(len(pos), pos, Z, box, De, a, re, cutoff, F, C.byref(e)) != 0:
+        raise RuntimeError("reference Morse threw")
+    return e.value, F
 
 
 def lj_pairs(pos, box, cutoff, cluster=False):

@@ -11,6 +11,7 @@
 
 #include "rgpot/LennardJones/LJClusterPot.hpp"
 #include "rgpot/LennardJones/LJPot.hpp"
+#include "rgpot/Morse/MorsePot.hpp"
 #include "vesin.h"
 
 #include "oracle.h"
@@ -30,6 +31,21 @@ int ref_lj_force(long n, const double *pos, const int *Z, const double *box, dou
       rgpot::LJPot pot{rgpot::LJConfig{u0, cutoff, psi}};
       pot.forceImpl(in, &out);
     }
+  } catch (...) {
+    return 1;
+  }
+  *energy = out.energy;
+  return 0;
+}
+
+// rgpot::MorsePot::forceImpl through the reference class itself.
+int ref_morse_force(long n, const double *pos, const int *Z, const double *box, double De, double a,
+                    double re, double cutoff, double *F, double *energy) {
+  rgpot::ForceInput in{static_cast<size_t>(n), pos, Z, box};
+  rgpot::ForceOut out{F, 0.0, 0.0};
+  try {
+    rgpot::MorsePot pot{rgpot::MorseConfig{De, a, re, cutoff}};
+    pot.forceImpl(in, &out);
   } catch (...) {
     return 1;
   }

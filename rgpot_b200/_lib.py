@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("RGPOT_B200_ENGINE") or os.path.join(HERE, "librgpot_b200.so")
 CSRC = os.path.join(HERE, "csrc")
 
-KIND_LJ, KIND_LJ_CLUSTER, KIND_CUH2 = 0, 1, 2
+KIND_LJ, KIND_LJ_CLUSTER, KIND_CUH2, KIND_MORSE = 0, 1, 2, 3
 
 
 class Config(C.Structure):
@@ -29,6 +29,10 @@ class Config(C.Structure):
         ("psi", C.c_double),
         ("lj_all_images", C.c_int),
         ("reserved", C.c_int * 7),
+        ("morse_De", C.c_double),
+        ("morse_a", C.c_double),
+        ("morse_re", C.c_double),
+        ("reserved_f", C.c_double),
     ]
 
 

@@ -99,9 +99,13 @@ RB_HD void divmod_i(int a, int b, int& q, int& r) {
   }
 }
 
+// parameters of the pair potentials that share the LJ pair search (LJ, LJCluster, Morse)
 struct LJParams {
   double u0, psi2, shiftU, rc2;
   double w[3], inv[3];  // fold widths / inverse widths (inv = 0 disables the fold)
+  int morse;            // 0: shifted 12-6 LJ, 1: shifted Morse
+  int pad;
+  double m_de, m_a, m_re, m_ecut, m_two_de_a;  // MorsePot.hpp:56-61, MorsePot.cc:51
 };
 
 }  // namespace rb

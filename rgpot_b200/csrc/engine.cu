@@ -157,6 +157,7 @@ struct RgpotB200Pot {
   int sm_count = 0;
   size_t smem_optin = 0;
   double lj_shiftU = 0.0;
+  double morse_ecut = 0.0;  // MorsePot.hpp:56-61
   double lj_rc = 0.0;  // effective cutoff (cluster: <= 0 -> 1e6)
   int forced_path = 0;
   long launches = 0;
@@ -409,6 +410,12 @@ int run_cell_path(RgpotB200Pot* pot, long n, const double* d_pos, const int* d_Z
   pl.lj.psi2 = pot->cfg.psi * pot->cfg.psi;
   pl.lj.shiftU = pot->lj_shiftU;
   pl.lj.rc2 = rc * rc;
+  pl.lj.morse = pot->cfg.kind == RGPOT_B200_MORSE ? 1 : 0;
+  pl.lj.m_de = pot->cfg.morse_De;
+  pl.lj.m_a = pot->cfg.morse_a;
+  pl.lj.m_re = pot->cfg.morse_re;
+  pl.lj.m_ecut = pot->morse_ecut;
+  pl.lj.m_two_de_a = 2.0 * pot->cfg.morse_De * pot->cfg.morse_a;
   pl.rc2 = rc * rc;
   finish_grid(pl, rc, n, images);
   if (images) {
@@ -597,6 +604,11 @@ int launch_small(RgpotB200Pot* pot, size_t nsys, long nmax, const long long* d_o
   a.psi2 = pot->cfg.psi * pot->cfg.psi;
   a.shiftU = pot->lj_shiftU;
   a.cutoff = pot->lj_rc;
+  a.morse = pot->cfg.kind == RGPOT_B200_MORSE ? 1 : 0;
+  a.m_de = pot->cfg.morse_De;
+  a.m_a = pot->cfg.morse_a;
+  a.m_re = pot->cfg.morse_re;
+  a.m_ecut = pot->morse_ecut;
   if (emit) a.emit = *emit;
   if (pot->cfg.kind == RGPOT_B200_CUH2) {
     const size_t smem = eam_small_smem(nmax, maxnb);
@@ -691,6 +703,9 @@ void lj_setup(RgpotB200Pot* pot) {
   pot->lj_shiftU = 4.0 * c.u0 * a * (a - 1.0);
   pot->lj_rc = c.cutoff;
   if (c.kind == RGPOT_B200_LJ_CLUSTER && !(c.cutoff > 0.0)) pot->lj_rc = 1.0e6;
+  // MorsePot.hpp:56-61: shift so that U(cutoff) = 0, the same closed form as the pair kernel
+  const double d = 1.0 - exp(-c.morse_a * (c.cutoff - c.morse_re));
+  pot->morse_ecut = c.morse_De * d * d - c.morse_De;
 }
 
 // ---- FP64 peak microbenchmark ------------------------------------------------------------------
@@ -739,8 +754,11 @@ void rgpot_b200_default_config(int kind, RgpotB200Config* cfg) {
   cfg->kind = kind;
   cfg->device = -1;
   cfg->u0 = 1.0;
-  cfg->cutoff = kind == RGPOT_B200_CUH2 ? 6.1 : 15.0;
+  cfg->cutoff = kind == RGPOT_B200_CUH2 ? 6.1 : (kind == RGPOT_B200_MORSE ? 9.5 : 15.0);
   cfg->psi = 1.0;
+  cfg->morse_De = 0.7102;  // MorsePot.hpp:31-36 (platinum)
+  cfg->morse_a = 1.6047;
+  cfg->morse_re = 2.8970;
 }
 
 RgpotB200Pot* rgpot_b200_create(const RgpotB200Config* cfg, char* errbuf, size_t errlen) {
@@ -749,7 +767,7 @@ RgpotB200Pot* rgpot_b200_create(const RgpotB200Config* cfg, char* errbuf, size_t
     return nullptr;
   };
   if (!cfg) return err("rgpot_b200_create: null config");
-  if (cfg->kind < RGPOT_B200_LJ || cfg->kind > RGPOT_B200_CUH2)
+  if (cfg->kind < RGPOT_B200_LJ || cfg->kind > RGPOT_B200_MORSE)
     return err("rgpot_b200_create: unknown potential kind");
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -947,7 +965,7 @@ int rgpot_b200_force_device(RgpotB200Pot* pot, long nAtoms, const double* d_posi
   const bool eam = pot->cfg.kind == RGPOT_B200_CUH2;
   // reference early-outs: rgpot_cuh2_capi.f90:50 (natoms < 1), LJPot.cc:50-52, LJClusterPot.cc:43-45
   const bool trivial = eam ? nAtoms < 1
-                           : (nAtoms < 2 || (pot->cfg.kind == RGPOT_B200_LJ && !(pot->cfg.cutoff > 0.0)));
+                           : (nAtoms < 2 || (pot->cfg.kind != RGPOT_B200_LJ_CLUSTER && !(pot->cfg.cutoff > 0.0)));
   if (trivial) {
     if (nAtoms > 0) CU_TRY(pot, cudaMemsetAsync(d_forces, 0, sizeof(double) * 3 * nAtoms, st));
     CU_TRY(pot, cudaMemsetAsync(d_energy, 0, sizeof(double), st));
@@ -1023,10 +1041,10 @@ int rgpot_b200_force(RgpotB200Pot* pot, long nAtoms, const double* positions, co
   if (nAtoms < 0 || nAtoms > INT_MAX / 4) return fail(pot, kStatusArgs, "rgpot_b200: bad atom count");
   const bool eam = pot->cfg.kind == RGPOT_B200_CUH2;
   const bool trivial = eam ? nAtoms < 1
-                           : (nAtoms < 2 || (pot->cfg.kind == RGPOT_B200_LJ && !(pot->cfg.cutoff > 0.0)));
+                           : (nAtoms < 2 || (pot->cfg.kind != RGPOT_B200_LJ_CLUSTER && !(pot->cfg.cutoff > 0.0)));
   if (trivial) return 0;
   if (eam && !atomicNrs) return fail(pot, kStatusArgs, "rgpot_b200: CuH2 needs atomic numbers");
-  if ((eam || pot->cfg.kind == RGPOT_B200_LJ) && !box)
+  if (pot->cfg.kind != RGPOT_B200_LJ_CLUSTER && !box)
     return fail(pot, kStatusArgs, "rgpot_b200_force: null box");
   cudaStream_t st = pot->stream;
   const size_t n = (size_t)nAtoms;
@@ -1180,7 +1198,7 @@ static int batch_device_impl(RgpotB200Pot* pot, size_t nsys, const size_t* offse
   for (int id : big_ids) {
     const long n = (long)(offsets[id + 1] - offsets[id]);
     const size_t o = offsets[id];
-    const bool trivial = eam ? n < 1 : (n < 2 || (kind == RGPOT_B200_LJ && !(pot->cfg.cutoff > 0.0)));
+    const bool trivial = eam ? n < 1 : (n < 2 || (kind != RGPOT_B200_LJ_CLUSTER && !(pot->cfg.cutoff > 0.0)));
     if (trivial) {
       if (n > 0) CU_TRY(pot, cudaMemsetAsync(d_F + 3 * o, 0, sizeof(double) * 3 * n, st));
       CU_TRY(pot, cudaMemsetAsync(d_E + id, 0, sizeof(double), st));

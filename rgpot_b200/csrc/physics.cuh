@@ -41,17 +41,33 @@ struct EamParams {
 
 __constant__ EamParams c_eam;
 
-// ---- Lennard-Jones -----------------------------------------------------------------------
+// ---- pair potentials on the LJ pair search ------------------------------------------------------
+// Pair energy U and fs with F_i += fs * (r_i - r_j) for one accepted pair at squared distance r2.
+//   LJ    : CppCore/rgpot/LennardJones/LJPot.cc:61-81
+//   Morse : CppCore/rgpot/Morse/MorsePot.cc:53-62  (sqrt and exp as the reference calls them)
+RB_D void pair_eval(const LJParams& p, double r2, double& u, double& fs) {
+  if (p.morse) {
+    const double r = sqrt(r2);
+    const double d = 1.0 - exp(-p.m_a * (r - p.m_re));
+    u = p.m_de * d * d - p.m_de - p.m_ecut;
+    fs = p.m_two_de_a * d * (d - 1.0) / r;
+  } else {
+    const double invR2 = 1.0 / r2;
+    const double sr2 = p.psi2 * invR2;
+    const double a = sr2 * sr2 * sr2;
+    const double b = 4.0 * p.u0 * a;
+    u = b * (a - 1.0) - p.shiftU;
+    fs = 6.0 * b * invR2 * (2.0 * a - 1.0);
+  }
+}
+
 // one directed entry of the gather form: half the pair energy, the whole force on i.
 // d = r_j - r_i (folded / shifted), so F_i -= fs * d   (LJPot.cc:70-77 with d = r_i - r_j).
 RB_D void lj_pair(const LJParams& p, double dx, double dy, double dz, double r2, double& e,
                   double& fx, double& fy, double& fz) {
-  const double invR2 = 1.0 / r2;
-  const double sr2 = p.psi2 * invR2;
-  const double a = sr2 * sr2 * sr2;
-  const double b = 4.0 * p.u0 * a;
-  e += 0.5 * (b * (a - 1.0) - p.shiftU);
-  const double fs = 6.0 * b * invR2 * (2.0 * a - 1.0);
+  double u, fs;
+  pair_eval(p, r2, u, fs);
+  e += 0.5 * u;
   fx -= fs * dx;
   fy -= fs * dy;
   fz -= fs * dz;

@@ -30,6 +30,8 @@ struct SmallArgs {
   int maxnb;               // neighbor-list capacity per atom (EAM)
   int cluster;             // LJ: free boundaries
   double u0, psi2, shiftU, cutoff;  // LJ
+  int morse;                        // Morse instead of LJ
+  double m_de, m_a, m_re, m_ecut;
   EmitArgs emit;           // optional (single system only)
 };
 
@@ -50,6 +52,12 @@ k_lj_small(SmallArgs a) {
   p.psi2 = a.psi2;
   p.shiftU = a.shiftU;
   p.rc2 = xmul(a.cutoff, a.cutoff);
+  p.morse = a.morse;
+  p.m_de = a.m_de;
+  p.m_a = a.m_a;
+  p.m_re = a.m_re;
+  p.m_ecut = a.m_ecut;
+  p.m_two_de_a = 2.0 * a.m_de * a.m_a;
   const double* box = a.boxes + 9 * (size_t)sys;
 #pragma unroll
   for (int k = 0; k < 3; ++k) {

@@ -306,12 +306,18 @@ k_tile(GatherArgs a, float thr2f, TileOut o) {
         const double d2 = xnorm2(dx, dy, dz);
         if (POT == TILE_LJ) {
           if (d2 <= rc2 && j != self) {  // vesin_visit.hpp:104, and i != j
-            const double invR2 = rcp_fast(d2);
-            const double sr2 = a.lj.psi2 * invR2;
-            const double a6 = sr2 * sr2 * sr2;
-            const double b = 4.0 * a.lj.u0 * a6;
-            e_lane += 0.5 * (b * (a6 - 1.0) - a.lj.shiftU);
-            const double fs = 6.0 * b * invR2 * (2.0 * a6 - 1.0);
+            double u, fs;
+            if (a.lj.morse) {
+              pair_eval(a.lj, d2, u, fs);
+            } else {
+              const double invR2 = rcp_fast(d2);
+              const double sr2 = a.lj.psi2 * invR2;
+              const double a6 = sr2 * sr2 * sr2;
+              const double b = 4.0 * a.lj.u0 * a6;
+              u = b * (a6 - 1.0) - a.lj.shiftU;
+              fs = 6.0 * b * invR2 * (2.0 * a6 - 1.0);
+            }
+            e_lane += 0.5 * u;
             acc[0] = fma(-fs, dx, acc[0]);
             acc[1] = fma(-fs, dy, acc[1]);
             acc[2] = fma(-fs, dz, acc[2]);

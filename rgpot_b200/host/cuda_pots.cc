@@ -2,6 +2,7 @@
 #include "cuda_pots.hpp"
 
 #include <array>
+#include <cmath>
 #include <cstring>
 #include <stdexcept>
 #include <vector>
@@ -47,6 +48,26 @@ Engine::Engine(int kind, const LJCudaConfig &c) {
     fp.f64(c.cutoff);
     fp.f64(c.psi);
   }
+  key_ = fp.h;
+  char err[512] = {0};
+  h_ = rgpot_b200_create(&cfg, err, sizeof err);
+  if (!h_) throw std::runtime_error(std::string("rgpot_b200 engine: ") + err);
+}
+
+Engine::Engine(const MorseCudaConfig &c) {
+  RgpotB200Config cfg;
+  rgpot_b200_default_config(RGPOT_B200_MORSE, &cfg);
+  cfg.device = c.device;
+  cfg.morse_De = c.De;
+  cfg.morse_a = c.a;
+  cfg.morse_re = c.re;
+  cfg.cutoff = c.cutoff;
+  Fnv fp;  // MorsePot.hpp:62-68
+  fp.u64(kKernelVersion);
+  fp.f64(c.De);
+  fp.f64(c.a);
+  fp.f64(c.re);
+  fp.f64(c.cutoff);
   key_ = fp.h;
   char err[512] = {0};
   h_ = rgpot_b200_create(&cfg, err, sizeof err);
@@ -99,4 +120,10 @@ void Engine::forceBatch(const char *label, const ForceBatch &batch) const {
 }
 
 } // namespace b200detail
+
+double MorseCudaPot::energyShift() const noexcept {
+  const double d = 1.0 - std::exp(-m_config.a * (m_config.cutoff - m_config.re));
+  return m_config.De * d * d - m_config.De;
+}
+
 } // namespace rgpot

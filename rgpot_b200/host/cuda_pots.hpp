@@ -36,12 +36,22 @@ struct LJCudaConfig {
   bool all_images = false; ///< opt-in triclinic LJ (no reference counterpart)
 };
 
+/// MorseConfig-compatible aggregate (Morse/MorsePot.hpp:31-36) plus the device ordinal.
+struct MorseCudaConfig {
+  double De = 0.7102;
+  double a = 1.6047;
+  double re = 2.8970;
+  double cutoff = 9.5;
+  int device = -1;
+};
+
 namespace b200detail {
 
 /// Owns one engine handle; shared by the three classes below.
 class Engine {
 public:
   Engine(int kind, const LJCudaConfig &c);
+  explicit Engine(const MorseCudaConfig &c);
   ~Engine();
   Engine(const Engine &) = delete;
   Engine &operator=(const Engine &) = delete;
@@ -90,5 +100,28 @@ RGPOT_B200_POT_CLASS(LJClusterCudaPot, LJCluster, RGPOT_B200_LJ_CLUSTER, "LJClus
 RGPOT_B200_POT_CLASS(CuH2CudaPot, CuH2, RGPOT_B200_CUH2, "CuH2", true);
 
 #undef RGPOT_B200_POT_CLASS
+
+/// rgpot::MorsePot on the engine (Morse/MorsePot.hpp:44-101): same PotType, same energyShift().
+class MorseCudaPot : public Potential<MorseCudaPot> {
+public:
+  MorseCudaPot() : MorseCudaPot(MorseCudaConfig{}) {}
+  explicit MorseCudaPot(const MorseCudaConfig &c)
+      : Potential(PotType::Morse), m_config(c), m_engine(std::make_shared<b200detail::Engine>(c)) {}
+  void forceImpl(const ForceInput &in, ForceOut *out) const override { m_engine->force("Morse", in, out); }
+  void forceBatchImpl(const ForceBatch &batch) const override { m_engine->forceBatch("Morse", batch); }
+  [[nodiscard]] PotCaps caps() const noexcept override {
+    PotCaps c;
+    c.reentrancy = Reentrancy::PerInstance;
+    c.batched = true;
+    return c;
+  }
+  [[nodiscard]] uint64_t paramsKey() const noexcept override { return m_engine->paramsKey(); }
+  [[nodiscard]] const MorseCudaConfig &config() const noexcept { return m_config; }
+  [[nodiscard]] double energyShift() const noexcept;
+
+private:
+  MorseCudaConfig m_config;
+  std::shared_ptr<b200detail::Engine> m_engine;
+};
 
 } // namespace rgpot

@@ -104,6 +104,37 @@ int main() {
   CHECK(ljc.paramsKey() == lj.paramsKey());
   (void)v_c; (void)v_p; (void)v_t; (void)f_t;
 
+  // ---- MorsePotTest.cc:62-117
+  {
+    rgpot::MorseCudaPot morse;
+    CHECK(std::fabs(morse.energyShift() - (-3.5537997279178057e-05)) < 1e-14);
+    AtomMatrix two{{10.0, 10.0, 10.0}, {10.0 + 2.8970, 10.0, 10.0}};
+    std::vector<int> pt{78, 78};
+    std::array<std::array<double, 3>, 3> b40{{{40, 0, 0}, {0, 40, 0}, {0, 0, 40}}};
+    auto [e2, f2, v2] = morse(two, pt, b40);
+    (void)v2;
+    CHECK(std::fabs(e2 - (-0.71016446200272088)) < 1e-12);
+    for (size_t i = 0; i < 2; ++i)
+      for (size_t j = 0; j < 3; ++j) CHECK(std::fabs(f2(i, j)) < 1e-12);
+    auto [em, fm, vm] = morse(cluster, ones, cell);
+    (void)vm;
+    CHECK(within_rel(em, 7483.1166203812, 1e-9));
+    const double row0[3] = {-2056.95286055812, 333.678513150438, 1022.83140169994};
+    for (size_t j = 0; j < 3; ++j) CHECK(within_rel(fm(0, j), row0[j], 1e-9));
+    double wm = 0, net[3] = {0, 0, 0};
+    for (size_t i = 0; i < 13; ++i) {
+      wm = std::fmax(wm, std::sqrt(fm(i, 0) * fm(i, 0) + fm(i, 1) * fm(i, 1) + fm(i, 2) * fm(i, 2)));
+      for (size_t j = 0; j < 3; ++j) net[j] += fm(i, j);
+    }
+    CHECK(within_rel(wm, 2480.28362300107, 1e-9));
+    for (double s : net) CHECK(std::fabs(s) < 1e-9);
+    rgpot::MorseCudaConfig deeper;
+    deeper.De = 0.8;
+    CHECK(rgpot::MorseCudaPot{}.paramsKey() == morse.paramsKey());
+    CHECK(rgpot::MorseCudaPot{deeper}.paramsKey() != morse.paramsKey());
+    CHECK(morse.get_type() == rgpot::PotType::Morse);
+  }
+
   std::printf(failures ? "test_host: %d FAILURES\n" : "test_host: ok\n", failures);
   return failures ? 1 : 0;
 }

@@ -51,6 +51,7 @@ class PotType(Enum):
 
     CuH2 = 1
     LJ = 2
+    Morse = 8
     LJCluster = 9
 
 
@@ -70,6 +71,16 @@ class LJClusterConfig:
     u0: float = 1.0
     cutoff: float = 15.0
     psi: float = 1.0
+
+
+@dataclass
+class MorseConfig:
+    """Morse/MorsePot.hpp:31-36 (platinum defaults)"""
+
+    De: float = 0.7102
+    a: float = 1.6047
+    re: float = 2.8970
+    cutoff: float = 9.5
 
 
 class PotentialError(RuntimeError):
@@ -124,12 +135,16 @@ class _EnginePot:
     _label = "LJ"
     _type = PotType.LJ
 
-    def __init__(self, u0=1.0, cutoff=15.0, psi=1.0, device: int = -1, lj_all_images: bool = False):
+    def __init__(self, u0=1.0, cutoff=15.0, psi=1.0, device: int = -1, lj_all_images: bool = False,
+                 morse=None):
         self._lib = _lib.lib()
         cfg = _lib.Config()
         self._lib.rgpot_b200_default_config(self._kind, C.byref(cfg))
         cfg.device = int(device)
-        if self._kind != _lib.KIND_CUH2:
+        if self._kind == _lib.KIND_MORSE:
+            cfg.morse_De, cfg.morse_a, cfg.morse_re = float(morse.De), float(morse.a), float(morse.re)
+            cfg.cutoff = float(morse.cutoff)
+        elif self._kind != _lib.KIND_CUH2:
             cfg.u0, cfg.cutoff, cfg.psi = float(u0), float(cutoff), float(psi)
             cfg.lj_all_images = int(bool(lj_all_images))
         self._cfg = cfg
@@ -157,6 +172,10 @@ class _EnginePot:
         if self._kind == _lib.KIND_CUH2:
             return _fnv1a([struct.pack("<Q", _KERNEL_VERSION)])
         c = self._cfg
+        if self._kind == _lib.KIND_MORSE:  # MorsePot.hpp:62-68
+            return _fnv1a([struct.pack("<Q", _KERNEL_VERSION), struct.pack("<d", c.morse_De),
+                           struct.pack("<d", c.morse_a), struct.pack("<d", c.morse_re),
+                           struct.pack("<d", c.cutoff)])
         return _fnv1a([struct.pack("<Q", _KERNEL_VERSION), struct.pack("<d", c.u0),
                        struct.pack("<d", c.cutoff), struct.pack("<d", c.psi)])
 
@@ -324,6 +343,27 @@ class LJClusterPot(_EnginePot):
 
     def config(self) -> LJClusterConfig:
         return self._config
+
+
+class MorsePot(_EnginePot):
+    """Shifted Morse pair potential, periodic orthorhombic nearest image (Morse/MorsePot.hpp:44-101)."""
+
+    _kind, _label, _type = _lib.KIND_MORSE, "Morse", PotType.Morse
+
+    def __init__(self, config: MorseConfig | None = None, device: int = -1):
+        c = config or MorseConfig()
+        self._config = c
+        super().__init__(device=device, morse=c)
+
+    def config(self) -> MorseConfig:
+        return self._config
+
+    def energyShift(self) -> float:
+        """MorsePot.hpp:72-74: the unshifted pair energy at the cutoff."""
+        import math
+        c = self._config
+        d = 1.0 - math.exp(-c.a * (c.cutoff - c.re))
+        return c.De * d * d - c.De
 
 
 class CuH2Pot(_EnginePot):

@@ -31,12 +31,14 @@ def test_header_symbols_are_exported(engine):
 
 
 def test_abi_version_and_defaults(engine):
-    assert engine.rgpot_b200_abi_version() == 1
+    assert engine.rgpot_b200_abi_version() == 2
     cfg = _lib.Config()
     engine.rgpot_b200_default_config(_lib.KIND_LJ, cfg)
     assert (cfg.u0, cfg.cutoff, cfg.psi, cfg.device) == (1.0, 15.0, 1.0, -1)  # LJPot.hpp:30-34
     engine.rgpot_b200_default_config(_lib.KIND_CUH2, cfg)
     assert cfg.cutoff == 6.1  # rgpot_cuh2.f90:100
+    engine.rgpot_b200_default_config(_lib.KIND_MORSE, cfg)
+    assert (cfg.morse_De, cfg.morse_a, cfg.morse_re, cfg.cutoff) == (0.7102, 1.6047, 2.8970, 9.5)  # MorsePot.hpp:31-36
 
 
 def test_fortran_dropin_symbols_present(engine):

@@ -378,3 +378,42 @@ def test_fortran_dropin_symbol(golden):
     n = lib.rgpot_fortran_last_error(buf, 512)
     assert st == 2 and n > 0 and b"atom 1 has atomic number 3" in buf.value
     assert e.value == 0.0 and not F.any()
+
+
+# ---------------------------------------------------------------------------------------- Morse
+def test_morse_pins(golden):
+    """CppCore/tests/MorsePotTest.cc:62-126 (same pair search as LJ)."""
+    pot = rgpot_b200.MorsePot()
+    assert pot.energyShift() == pytest.approx(-3.5537997279178057e-05, abs=1e-14)
+    two = np.array([[10.0, 10.0, 10.0], [10.0 + 2.8970, 10.0, 10.0]])
+    e2, f2, _ = pot(two, np.full(2, 78, np.int32), np.eye(3) * 40.0)
+    assert e2 == pytest.approx(-0.71016446200272088, abs=1e-12)
+    assert np.abs(f2).max() < 1e-12
+    g = golden("lj13_cluster.json")
+    pos, box = np.array(g["positions"]), np.array(g["box"]).reshape(3, 3)
+    e, f, _ = pot(pos, np.ones(13, np.int32), box)
+    assert e == pytest.approx(7483.1166203812, rel=1e-9)
+    assert f[0] == pytest.approx([-2056.95286055812, 333.678513150438, 1022.83140169994], rel=1e-9)
+    assert np.sqrt((f ** 2).sum(1)).max() == pytest.approx(2480.28362300107, rel=1e-9)
+    assert np.abs(f.sum(0)).max() < 1e-9
+    deeper = rgpot_b200.MorsePot(rgpot_b200.MorseConfig(De=0.8))
+    assert rgpot_b200.MorsePot().paramsKey() == pot.paramsKey() != deeper.paramsKey()
+    assert pot.get_type() == rgpot_b200.PotType.Morse
+
+
+@pytest.mark.parametrize("n,wrapped,path", [(300, False, 2), (3000, True, 1), (3000, False, 1)])
+def test_morse_vs_oracle(oracle, n, wrapped, path):
+    # a loose Pt-like lattice so the 9.5 A cutoff reaches several shells
+    rng = np.random.default_rng(n + path)
+    m = int(np.ceil(n ** (1 / 3)))
+    L = 2.9 * m
+    g = (np.stack(np.meshgrid(*[np.arange(m)] * 3, indexing="ij"), -1).reshape(-1, 3)[:n] + 0.5) * 2.9
+    pos = g + rng.normal(0, 0.1, g.shape)
+    pos = np.mod(pos, L) if wrapped else pos + rng.integers(-1, 2, size=g.shape) * L
+    box = np.diag([L, L, L])
+    pot = rgpot_b200.MorsePot()
+    pot.set_path(path)
+    e, f, _ = pot(pos, np.full(n, 78, np.int32), box)
+    e_o, f_o, _ = oracle.morse_force(pos, box)
+    assert_energy(e, e_o)
+    assert_forces(f, f_o)

@@ -152,3 +152,18 @@ def test_triclinic_commensurate_shear(oracle):
     e2, _ = oracle.cuh2_force(cu, Z, np.array([[4 * a, 0, 0], [a, 4 * a, 0], [a / 2, a / 2, 4 * a]]))
     assert e0 == pytest.approx(-906.183991113513, rel=1e-12)
     assert e1 == pytest.approx(e0, rel=1e-11) and e2 == pytest.approx(e0, rel=1e-11)
+
+
+def test_morse_pins(oracle, golden):
+    # CppCore/tests/MorsePotTest.cc:62-117
+    e2, f2, _ = oracle.morse_force([[10.0, 10.0, 10.0], [10.0 + 2.8970, 10.0, 10.0]], np.eye(3) * 40.0)
+    assert e2 == pytest.approx(-0.71016446200272088, abs=1e-12)
+    assert np.abs(f2).max() < 1e-12
+    g = golden("lj13_cluster.json")
+    pos, box = np.array(g["positions"]), np.array(g["box"]).reshape(3, 3)
+    e, f, n = oracle.morse_force(pos, box)
+    assert n == 78
+    assert e == pytest.approx(7483.1166203812, rel=1e-9)
+    assert f[0] == pytest.approx([-2056.95286055812, 333.678513150438, 1022.83140169994], rel=1e-9)
+    assert np.sqrt((f ** 2).sum(1)).max() == pytest.approx(2480.28362300107, rel=1e-9)
+    assert np.abs(f.sum(0)).max() < 1e-9

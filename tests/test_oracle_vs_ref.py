@@ -76,3 +76,13 @@ def test_params_key_matches_reference_scheme(ref):
     k0 = lib.ref_lj_params_key(1.0, 15.0, 1.0, 0)
     assert k0 == lib.ref_lj_params_key(1.0, 15.0, 1.0, 1)
     assert k0 != lib.ref_lj_params_key(1.0, 20.0, 1.0, 0)
+
+
+def test_morse_restatement_is_bit_exact(ref):
+    rng = np.random.default_rng(9)
+    for n, L, rc in [(80, 14.0, 5.0), (40, 8.0, 9.5), (150, 25.0, 9.5)]:
+        pos = rng.random((n, 3)) * L * 1.2 - 0.1 * L
+        box = np.diag([L, 1.1 * L, 0.9 * L])
+        e_r, f_r = ref.ref_morse_force(pos, box, 0.7102, 1.6047, 2.8970, rc)
+        e_o, f_o, _ = ref.morse_force(pos, box, 0.7102, 1.6047, 2.8970, rc)
+        assert e_o == e_r and np.array_equal(f_o, f_r)
