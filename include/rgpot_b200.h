@@ -55,8 +55,10 @@ enum {
   RGPOT_B200_LJ = 0,         /**< PotType::LJ        -- periodic, orthorhombic nearest image */
   RGPOT_B200_LJ_CLUSTER = 1, /**< PotType::LJCluster -- free boundaries                       */
   RGPOT_B200_CUH2 = 2,       /**< PotType::CuH2      -- Cu/H EAM, all images inside 6.1 A     */
-  RGPOT_B200_MORSE = 3       /**< PotType::Morse     -- shifted Morse pair potential, same pair search as
+  RGPOT_B200_MORSE = 3,      /**< PotType::Morse     -- shifted Morse pair potential, same pair search as
                                   LJ (CppCore/rgpot/Morse/MorsePot.{hpp,cc}); SURVEY 8(f) rank 1 */
+  RGPOT_B200_ZBL = 4         /**< PotType::ZBL       -- screened nuclear repulsion with switching, free
+                                  boundaries, species-pair tables (CppCore/rgpot/ZBL/ZBLPot.{hpp,cc}) */
 };
 
 typedef struct RgpotB200Config {
@@ -73,7 +75,10 @@ typedef struct RgpotB200Config {
   /** MorseConfig (Morse/MorsePot.hpp:31-36): De, a, re; the cutoff goes in `cutoff` (default 9.5).
    *  Defaults 0.7102 eV, 1.6047 1/A, 2.8970 A (platinum).  Unused by the other kinds.        */
   double morse_De, morse_a, morse_re;
-  double reserved_f;
+  /** ZBLConfig (ZBL/ZBLPot.hpp:29-32): cut_inner here, cut_global in `cutoff` (defaults 2.0 / 2.5);
+   *  create fails unless 0 < cut_inner < cut_global (ZBLPot.cc:76-79).  At most 16 distinct
+   *  atomic numbers per call.                                                                */
+  double zbl_cut_inner;
 } RgpotB200Config;
 
 RGPOT_B200_API int rgpot_b200_abi_version(void);

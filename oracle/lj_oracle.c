@@ -123,6 +123,94 @@ long oracle_morse_force(long n, const double *pos, const double *box, double De,
   return visited;
 }
 
+/* ---- ZBL: CppCore/rgpot/ZBL/ZBLPot.cc:20-72 (constants, e_zbl, dzbldr, d2zbldr2),
+ * :88-129 (buildTables), :172-248 (forceImpl; free boundaries, r2 <= cut_global^2). */
+typedef struct {
+  double d1, d2, d3, d4, zze, sw1, sw2, sw3, sw4, sw5;
+} zbl_t;
+static double zbl_e(const zbl_t *p, double r) {
+  const double r_inv = 1.0 / r;
+  const double sum = 0.18175 * exp(-p->d1 * r) + 0.50986 * exp(-p->d2 * r) +
+                     0.28022 * exp(-p->d3 * r) + 0.02817 * exp(-p->d4 * r);
+  return p->zze * sum * r_inv;
+}
+static double zbl_de(const zbl_t *p, double r) {
+  const double r_inv = 1.0 / r;
+  const double e1 = exp(-p->d1 * r), e2 = exp(-p->d2 * r), e3 = exp(-p->d3 * r), e4 = exp(-p->d4 * r);
+  const double sum = 0.18175 * e1 + 0.50986 * e2 + 0.28022 * e3 + 0.02817 * e4;
+  const double sum_p = -0.18175 * p->d1 * e1 - 0.50986 * p->d2 * e2 - 0.28022 * p->d3 * e3 - 0.02817 * p->d4 * e4;
+  return p->zze * (sum_p - sum * r_inv) * r_inv;
+}
+static double zbl_d2e(const zbl_t *p, double r) {
+  const double r_inv = 1.0 / r;
+  const double e1 = exp(-p->d1 * r), e2 = exp(-p->d2 * r), e3 = exp(-p->d3 * r), e4 = exp(-p->d4 * r);
+  const double sum = 0.18175 * e1 + 0.50986 * e2 + 0.28022 * e3 + 0.02817 * e4;
+  const double sum_p = 0.18175 * e1 * p->d1 + 0.50986 * e2 * p->d2 + 0.28022 * e3 * p->d3 + 0.02817 * e4 * p->d4;
+  const double sum_pp = 0.18175 * e1 * p->d1 * p->d1 + 0.50986 * e2 * p->d2 * p->d2 +
+                        0.28022 * e3 * p->d3 * p->d3 + 0.02817 * e4 * p->d4 * p->d4;
+  return p->zze * (sum_pp + 2.0 * sum_p * r_inv + 2.0 * sum * r_inv * r_inv) * r_inv;
+}
+static zbl_t zbl_pair(int zi_, int zj_, double cut_inner, double cut_global) {
+  const double zi = (double)zi_, zj = (double)zj_, tc = cut_global - cut_inner;
+  const double a_inv = (pow(zi, 0.23) + pow(zj, 0.23)) / 0.46850;
+  zbl_t p;
+  p.d1 = 3.19980 * a_inv;
+  p.d2 = 0.94229 * a_inv;
+  p.d3 = 0.40290 * a_inv;
+  p.d4 = 0.20162 * a_inv;
+  p.zze = zi * zj * 14.399645;
+  const double fc = zbl_e(&p, cut_global), fcp = zbl_de(&p, cut_global), fcpp = zbl_d2e(&p, cut_global);
+  const double swa = (-3.0 * fcp + tc * fcpp) / (tc * tc);
+  const double swb = (2.0 * fcp - tc * fcpp) / (tc * tc * tc);
+  p.sw1 = swa;
+  p.sw2 = swb;
+  p.sw3 = swa / 3.0;
+  p.sw4 = swb / 4.0;
+  p.sw5 = -fc + (tc / 2.0) * fcp - (tc * tc / 12.0) * fcpp;
+  return p;
+}
+
+long oracle_zbl_force(long n, const double *pos, const int *Z, double cut_inner, double cut_global,
+                      double *F, double *energy) {
+  *energy = 0.0;
+  for (long i = 0; i < 3 * n; ++i) F[i] = 0.0;
+  if (n < 2) return 0; /* ZBLPot.cc:180-182 */
+  const double rc2 = cut_global * cut_global, rin2 = cut_inner * cut_inner;
+  double acc = 0.0;
+  long visited = 0;
+  for (long i = 0; i < n; ++i) {
+    for (long j = i + 1; j < n; ++j) {
+      double d[3];
+      for (int k = 0; k < 3; ++k) d[k] = pos[3 * j + k] - pos[3 * i + k]; /* no fold: free boundaries */
+      const double r2 = d[0] * d[0] + d[1] * d[1] + d[2] * d[2];
+      if (r2 <= rc2) {
+        /* the table entry is symmetric in (i, j): build it for the ordered pair like buildTables
+         * does (i <= j in species order) so the same pow() arguments are used */
+        const int za = Z[i] < Z[j] ? Z[i] : Z[j], zb = Z[i] < Z[j] ? Z[j] : Z[i];
+        const zbl_t p = zbl_pair(za, zb, cut_inner, cut_global);
+        const double r = sqrt(r2);
+        double e_pair = zbl_e(&p, r) + p.sw5;
+        double dEdr = zbl_de(&p, r);
+        if (r2 > rin2) {
+          const double t = r - cut_inner;
+          e_pair += t * t * t * (p.sw3 + p.sw4 * t);
+          dEdr += t * t * (p.sw1 + p.sw2 * t);
+        }
+        acc += e_pair;
+        const double fs = -dEdr / r;
+        for (int k = 0; k < 3; ++k) {
+          const double f = fs * (-d[k]);
+          F[3 * i + k] += f;
+          F[3 * j + k] -= f;
+        }
+        ++visited;
+      }
+    }
+  }
+  *energy = acc;
+  return visited;
+}
+
 long oracle_lj_pairs(long n, const double *pos, const double *box, double cutoff, int cluster,
                      int32_t *pairs, long cap) {
   if (n < 2 || (!cluster && cutoff <= 0.0)) return 0;

@@ -36,6 +36,10 @@ long oracle_lj_force(long n, const double *pos, const double *box, double u0, do
 long oracle_morse_force(long n, const double *pos, const double *box, double De, double a,
                         double re, double cutoff, double *F, double *energy);
 
+/* ZBLPot::forceImpl: CppCore/rgpot/ZBL/ZBLPot.cc:172-248.                  */
+long oracle_zbl_force(long n, const double *pos, const int *Z, double cut_inner, double cut_global,
+                      double *F, double *energy);
+
 /* Same scan, pair set only: writes up to cap (i, j) pairs (i < j) into pairs[2*k..]
  * and returns the total count.  vesin_visit.hpp:82-110.                            */
 long oracle_lj_pairs(long n, const double *pos, const double *box, double cutoff, int cluster,

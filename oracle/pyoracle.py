@@ -48,6 +48,9 @@ def _declare_common(lib):
     lib.oracle_morse_force.restype = C.c_long
     lib.oracle_morse_force.argtypes = [C.c_long, _f64p, _f64p, C.c_double, C.c_double, C.c_double,
                                        C.c_double, _f64p, C.POINTER(C.c_double)]
+    lib.oracle_zbl_force.restype = C.c_long
+    lib.oracle_zbl_force.argtypes = [C.c_long, _f64p, _i32p, C.c_double, C.c_double, _f64p,
+                                     C.POINTER(C.c_double)]
     lib.oracle_lj_pairs.restype = C.c_long
     lib.oracle_lj_pairs.argtypes = [C.c_long, _f64p, _f64p, C.c_double, C.c_int, _i32p, C.c_long]
     lib.oracle_nlist_build.restype = C.c_int
@@ -101,6 +104,9 @@ def ref_lib():
         _REF.ref_morse_force.restype = C.c_int
         _REF.ref_morse_force.argtypes = [C.c_long, _f64p, _i32p, _f64p, C.c_double, C.c_double,
                                          C.c_double, C.c_double, _f64p, C.POINTER(C.c_double)]
+        _REF.ref_zbl_force.restype = C.c_int
+        _REF.ref_zbl_force.argtypes = [C.c_long, _f64p, _i32p, _f64p, C.c_double, C.c_double, _f64p,
+                                       C.POINTER(C.c_double)]
         _REF.ref_lj_params_key.restype = C.c_uint64
         _REF.ref_lj_params_key.argtypes = [C.c_double, C.c_double, C.c_double, C.c_int]
         _REF.ref_table_new.restype = C.c_void_p
@@ -145,6 +151,25 @@ def ref_morse_force(pos, box, De=0.7102, a=1.6047, re=2.8970, cutoff=9.5):
     e = C.c_double(0.0)
     if ref_lib().ref_morse_force(len(pos), pos, Z, box, De, a, re, cutoff, F, C.byref(e)) != 0:
         raise RuntimeError("reference Morse threw")
+    return e.value, F
+
+
+def zbl_force(pos, Z, cut_inner=2.0, cut_global=2.5):
+    pos = np.ascontiguousarray(pos, dtype=np.float64).reshape(-1, 3)
+    Z = np.ascontiguousarray(Z, dtype=np.int32)
+    F = np.zeros_like(pos)
+    e = C.c_double(0.0)
+    n = oracle_lib().oracle_zbl_force(len(pos), pos, Z, cut_inner, cut_global, F, C.byref(e))
+    return e.value, F, n
+
+
+def ref_zbl_force(pos, Z, box, cut_inner=2.0, cut_global=2.5):
+    pos, box = _prep(pos, box)
+    Z = np.ascontiguousarray(Z, dtype=np.int32)
+    F = np.zeros_like(pos)
+    e = C.c_double(0.0)
+    if ref_lib().ref_zbl_force(len(pos), pos, Z, box, cut_inner, cut_global, F, C.byref(e)) != 0:
+        raise RuntimeError("reference ZBL threw")
     return e.value, F
 
 

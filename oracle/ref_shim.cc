@@ -12,6 +12,7 @@
 #include "rgpot/LennardJones/LJClusterPot.hpp"
 #include "rgpot/LennardJones/LJPot.hpp"
 #include "rgpot/Morse/MorsePot.hpp"
+#include "rgpot/ZBL/ZBLPot.hpp"
 #include "vesin.h"
 
 #include "oracle.h"
@@ -45,6 +46,21 @@ int ref_morse_force(long n, const double *pos, const int *Z, const double *box, 
   rgpot::ForceOut out{F, 0.0, 0.0};
   try {
     rgpot::MorsePot pot{rgpot::MorseConfig{De, a, re, cutoff}};
+    pot.forceImpl(in, &out);
+  } catch (...) {
+    return 1;
+  }
+  *energy = out.energy;
+  return 0;
+}
+
+// rgpot::ZBLPot::forceImpl through the reference class itself.
+int ref_zbl_force(long n, const double *pos, const int *Z, const double *box, double cut_inner,
+                  double cut_global, double *F, double *energy) {
+  rgpot::ForceInput in{static_cast<size_t>(n), pos, Z, box};
+  rgpot::ForceOut out{F, 0.0, 0.0};
+  try {
+    rgpot::ZBLPot pot{rgpot::ZBLConfig{cut_inner, cut_global}};
     pot.forceImpl(in, &out);
   } catch (...) {
     return 1;

@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("RGPOT_B200_ENGINE") or os.path.join(HERE, "librgpot_b200.so")
 CSRC = os.path.join(HERE, "csrc")
 
-KIND_LJ, KIND_LJ_CLUSTER, KIND_CUH2, KIND_MORSE = 0, 1, 2, 3
+KIND_LJ, KIND_LJ_CLUSTER, KIND_CUH2, KIND_MORSE, KIND_ZBL = 0, 1, 2, 3, 4
 
 
 class Config(C.Structure):
@@ -32,7 +32,7 @@ class Config(C.Structure):
         ("morse_De", C.c_double),
         ("morse_a", C.c_double),
         ("morse_re", C.c_double),
-        ("reserved_f", C.c_double),
+        ("zbl_cut_inner", C.c_double),
     ]
 
 

@@ -217,7 +217,9 @@ __global__ void k_gather_sorted(const double* __restrict__ pos, const int* __res
   if (s >= n) return;
   const int i = order[s];
   int species = 0;
-  if (check_z) {
+  if (check_z == 2) {
+    species = Z[i] & 15;  // ZBL: the host already mapped atomic numbers to type indices
+  } else if (check_z) {
     const int z = Z[i];
     if (z == 29) {
       species = 0;

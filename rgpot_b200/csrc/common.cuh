@@ -54,16 +54,18 @@ struct Grid {
 };
 
 // sorted-atom record: position + packed metadata (original index, species, wrap shift).
-// meta: bits 0..31 original index | 32..33 species | 34..43, 44..53, 54..63 shift + 512.
+// meta: bits 0..27 original index (< 2^28 atoms) | 28..31 species / type index (16) |
+//       32..41, 42..51, 52..61 shift + 512.
+constexpr int kMaxAtoms = (1 << 28) - 1;
 RB_HD unsigned long long pack_meta(int orig, int species, int s0, int s1, int s2) {
-  return (unsigned long long)(unsigned)orig | ((unsigned long long)(species & 3) << 32) |
-         ((unsigned long long)((s0 + 512) & 1023) << 34) |
-         ((unsigned long long)((s1 + 512) & 1023) << 44) |
-         ((unsigned long long)((s2 + 512) & 1023) << 54);
+  return (unsigned long long)((unsigned)orig & 0x0fffffffu) | ((unsigned long long)(species & 15) << 28) |
+         ((unsigned long long)((s0 + 512) & 1023) << 32) |
+         ((unsigned long long)((s1 + 512) & 1023) << 42) |
+         ((unsigned long long)((s2 + 512) & 1023) << 52);
 }
-RB_HD int meta_orig(unsigned long long m) { return (int)(unsigned)(m & 0xffffffffull); }
-RB_HD int meta_species(unsigned long long m) { return (int)((m >> 32) & 3); }
-RB_HD int meta_shift(unsigned long long m, int k) { return (int)((m >> (34 + 10 * k)) & 1023) - 512; }
+RB_HD int meta_orig(unsigned long long m) { return (int)(m & 0x0fffffffull); }
+RB_HD int meta_species(unsigned long long m) { return (int)((m >> 28) & 15); }
+RB_HD int meta_shift(unsigned long long m, int k) { return (int)((m >> (32 + 10 * k)) & 1023) - 512; }
 
 // ---- exact (never-contracted) arithmetic -------------------------------------------------
 RB_D double xadd(double a, double b) { return __dadd_rn(a, b); }
@@ -103,9 +105,11 @@ RB_HD void divmod_i(int a, int b, int& q, int& r) {
 struct LJParams {
   double u0, psi2, shiftU, rc2;
   double w[3], inv[3];  // fold widths / inverse widths (inv = 0 disables the fold)
-  int morse;            // 0: shifted 12-6 LJ, 1: shifted Morse
-  int pad;
+  int morse;            // 0: shifted 12-6 LJ, 1: shifted Morse, 2: ZBL
+  int zbl_nt;           // ZBL: number of species types
   double m_de, m_a, m_re, m_ecut, m_two_de_a;  // MorsePot.hpp:56-61, MorsePot.cc:51
+  const double* zbl_table;  // ZBL: nt x nt x 10 coefficients (d1..d4, zze, sw1..sw5), ZBLPot.hpp:35-46
+  double zbl_rin, zbl_rin2;  // ZBL: switching starts above this (squared) distance
 };
 
 }  // namespace rb

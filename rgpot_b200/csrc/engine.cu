@@ -158,6 +158,8 @@ struct RgpotB200Pot {
   size_t smem_optin = 0;
   double lj_shiftU = 0.0;
   double morse_ecut = 0.0;  // MorsePot.hpp:56-61
+  std::vector<int> zbl_species;  // sorted unique atomic numbers of the cached table (ZBLPot.cc:150-166)
+  DevBuf zbl_table;
   double lj_rc = 0.0;  // effective cutoff (cluster: <= 0 -> 1e6)
   int forced_path = 0;
   long launches = 0;
@@ -192,7 +194,7 @@ struct RgpotB200Pot {
     DevBuf* d[] = {&pos, &Z, &F, &cell_of, &rank, &ashift, &counts, &starts, &blocksums, &order, &order2,
                    &spos, &scell, &dfd, &eemb, &partials, &energy, &status, &mm, &emit_pairs,
                    &emit_shifts, &emit_count, &b_pos, &b_Z, &b_F, &b_off, &b_boxes, &b_E, &b_flags,
-                   &b_bad, &b_map};
+                   &b_bad, &b_map, &zbl_table};
     for (auto* b : d) b->release();
     HostBuf* h[] = {&h_pos, &h_Z, &h_F, &h_off, &h_boxes, &h_E, &h_flags, &h_bad, &h_small};
     for (auto* b : h) b->release();
@@ -363,7 +365,7 @@ int run_cell_path(RgpotB200Pot* pot, long n, const double* d_pos, const int* d_Z
     }
   } else {
     // LJ reference semantics: only the box diagonal is read (LJPot.cc:35, PairListCache.hpp:176-184)
-    const bool cluster = kind == RGPOT_B200_LJ_CLUSTER;
+    const bool cluster = kind == RGPOT_B200_LJ_CLUSTER || kind == RGPOT_B200_ZBL;
     memset(pl.box.H, 0, sizeof pl.box.H);
     memset(pl.box.Hinv, 0, sizeof pl.box.Hinv);
     bool need_bbox = false;
@@ -410,7 +412,11 @@ int run_cell_path(RgpotB200Pot* pot, long n, const double* d_pos, const int* d_Z
   pl.lj.psi2 = pot->cfg.psi * pot->cfg.psi;
   pl.lj.shiftU = pot->lj_shiftU;
   pl.lj.rc2 = rc * rc;
-  pl.lj.morse = pot->cfg.kind == RGPOT_B200_MORSE ? 1 : 0;
+  pl.lj.morse = pot->cfg.kind == RGPOT_B200_MORSE ? 1 : (pot->cfg.kind == RGPOT_B200_ZBL ? 2 : 0);
+  pl.lj.zbl_table = pot->zbl_table.as<double>();
+  pl.lj.zbl_nt = (int)pot->zbl_species.size();
+  pl.lj.zbl_rin = pot->cfg.zbl_cut_inner;
+  pl.lj.zbl_rin2 = pot->cfg.zbl_cut_inner * pot->cfg.zbl_cut_inner;
   pl.lj.m_de = pot->cfg.morse_De;
   pl.lj.m_a = pot->cfg.morse_a;
   pl.lj.m_re = pot->cfg.morse_re;
@@ -468,7 +474,7 @@ int run_cell_path(RgpotB200Pot* pot, long n, const double* d_pos, const int* d_Z
   LAUNCH_CHECK(pot, "k_cell_order");
   k_gather_sorted<<<div_up(n, 256), 256, 0, st>>>(d_pos, d_Z, pot->order2.as<int>(),
                                                   pot->cell_of.as<int>(), pot->ashift.as<int>(), (int)n,
-                                                  eam ? 1 : 0, pot->spos.as<double4>(),
+                                                  eam ? 1 : (kind == RGPOT_B200_ZBL ? 2 : 0), pot->spos.as<double4>(),
                                                   pot->scell.as<int>(), d_st);
   LAUNCH_CHECK(pot, "k_gather_sorted");
 
@@ -599,12 +605,15 @@ int launch_small(RgpotB200Pot* pot, size_t nsys, long nmax, const long long* d_o
   a.sys_bad = d_bad;
   a.nsys = (int)nsys;
   a.maxnb = maxnb;
-  a.cluster = pot->cfg.kind == RGPOT_B200_LJ_CLUSTER;
+  a.cluster = pot->cfg.kind == RGPOT_B200_LJ_CLUSTER || pot->cfg.kind == RGPOT_B200_ZBL;
   a.u0 = pot->cfg.u0;
   a.psi2 = pot->cfg.psi * pot->cfg.psi;
   a.shiftU = pot->lj_shiftU;
   a.cutoff = pot->lj_rc;
-  a.morse = pot->cfg.kind == RGPOT_B200_MORSE ? 1 : 0;
+  a.morse = pot->cfg.kind == RGPOT_B200_MORSE ? 1 : (pot->cfg.kind == RGPOT_B200_ZBL ? 2 : 0);
+  a.zbl_table = pot->zbl_table.as<double>();
+  a.zbl_nt = (int)pot->zbl_species.size();
+  a.zbl_rin = pot->cfg.zbl_cut_inner;
   a.m_de = pot->cfg.morse_De;
   a.m_a = pot->cfg.morse_a;
   a.m_re = pot->cfg.morse_re;
@@ -637,7 +646,7 @@ int launch_small(RgpotB200Pot* pot, size_t nsys, long nmax, const long long* d_o
       default: return launch(k_eam_small<8>);
     }
   }
-  const size_t smem = sizeof(double) * 3 * (size_t)nmax + 16;
+  const size_t smem = sizeof(double) * 3 * (size_t)nmax + sizeof(int) * (size_t)nmax + 16;
   cudaFuncAttributes fa;
   cudaError_t e = cudaFuncGetAttributes(&fa, k_lj_small);
   if (e == cudaSuccess)
@@ -693,6 +702,78 @@ int map_flags(RgpotB200Pot* pot, unsigned flags, int bad_atom, int bad_z, const 
     return fail(pot, kStatusRange, "rgpot_b200: an atom lies more than 500 cell widths outside the box");
   if (eam && (flags & kFlagCoincident))
     return fail(pot, 3, "rgpot_cuh2: two atoms occupy the same position");
+  return 0;
+}
+
+// ---- ZBL species tables (ZBLPot.cc:38-72 radial functions, :88-129 buildTables) ------------------
+constexpr int kStatusSpecies = 103;
+struct ZblCoeffs {
+  double d1, d2, d3, d4, zze, sw1, sw2, sw3, sw4, sw5;
+};
+double zbl_e(const ZblCoeffs& p, double r) {
+  const double r_inv = 1.0 / r;
+  const double sum = 0.18175 * exp(-p.d1 * r) + 0.50986 * exp(-p.d2 * r) + 0.28022 * exp(-p.d3 * r) +
+                     0.02817 * exp(-p.d4 * r);
+  return p.zze * sum * r_inv;
+}
+double zbl_de(const ZblCoeffs& p, double r) {
+  const double r_inv = 1.0 / r;
+  const double e1 = exp(-p.d1 * r), e2 = exp(-p.d2 * r), e3 = exp(-p.d3 * r), e4 = exp(-p.d4 * r);
+  const double sum = 0.18175 * e1 + 0.50986 * e2 + 0.28022 * e3 + 0.02817 * e4;
+  const double sum_p = -0.18175 * p.d1 * e1 - 0.50986 * p.d2 * e2 - 0.28022 * p.d3 * e3 - 0.02817 * p.d4 * e4;
+  return p.zze * (sum_p - sum * r_inv) * r_inv;
+}
+double zbl_d2e(const ZblCoeffs& p, double r) {
+  const double r_inv = 1.0 / r;
+  const double e1 = exp(-p.d1 * r), e2 = exp(-p.d2 * r), e3 = exp(-p.d3 * r), e4 = exp(-p.d4 * r);
+  const double sum = 0.18175 * e1 + 0.50986 * e2 + 0.28022 * e3 + 0.02817 * e4;
+  const double sum_p = 0.18175 * e1 * p.d1 + 0.50986 * e2 * p.d2 + 0.28022 * e3 * p.d3 + 0.02817 * e4 * p.d4;
+  const double sum_pp = 0.18175 * e1 * p.d1 * p.d1 + 0.50986 * e2 * p.d2 * p.d2 + 0.28022 * e3 * p.d3 * p.d3 +
+                        0.02817 * e4 * p.d4 * p.d4;
+  return p.zze * (sum_pp + 2.0 * sum_p * r_inv + 2.0 * sum * r_inv * r_inv) * r_inv;
+}
+
+// Map atomic numbers to type indices (sorted unique, ZBLPot.cc:186-196) and make sure the device
+// table matches the species set.  `types` receives one index per atom.
+int zbl_prepare(RgpotB200Pot* pot, size_t n, const int* Z, int* types, cudaStream_t st) {
+  std::vector<int> uniq(Z, Z + n);
+  std::sort(uniq.begin(), uniq.end());
+  uniq.erase(std::unique(uniq.begin(), uniq.end()), uniq.end());
+  if (uniq.size() > 16)
+    return fail(pot, kStatusSpecies, "rgpot_b200: ZBL handles at most 16 distinct atomic numbers per call");
+  for (size_t k = 0; k < n; ++k)
+    types[k] = (int)(std::lower_bound(uniq.begin(), uniq.end(), Z[k]) - uniq.begin());
+  if (uniq == pot->zbl_species && pot->zbl_table.p) return 0;
+  const size_t nt = uniq.size();
+  const double cut_inner = pot->cfg.zbl_cut_inner, cut_global = pot->cfg.cutoff;
+  const double tc = cut_global - cut_inner;
+  std::vector<double> table(10 * nt * nt);
+  for (size_t i = 0; i < nt; ++i)
+    for (size_t j = i; j < nt; ++j) {
+      const double zi = (double)uniq[i], zj = (double)uniq[j];
+      const double a_inv = (pow(zi, 0.23) + pow(zj, 0.23)) / 0.46850;
+      ZblCoeffs p{};
+      p.d1 = 3.19980 * a_inv;
+      p.d2 = 0.94229 * a_inv;
+      p.d3 = 0.40290 * a_inv;
+      p.d4 = 0.20162 * a_inv;
+      p.zze = zi * zj * 14.399645;
+      const double fc = zbl_e(p, cut_global), fcp = zbl_de(p, cut_global), fcpp = zbl_d2e(p, cut_global);
+      const double swa = (-3.0 * fcp + tc * fcpp) / (tc * tc);
+      const double swb = (2.0 * fcp - tc * fcpp) / (tc * tc * tc);
+      const double swc = -fc + (tc / 2.0) * fcp - (tc * tc / 12.0) * fcpp;
+      p.sw1 = swa;
+      p.sw2 = swb;
+      p.sw3 = swa / 3.0;
+      p.sw4 = swb / 4.0;
+      p.sw5 = swc;
+      memcpy(&table[10 * (i * nt + j)], &p, sizeof p);
+      memcpy(&table[10 * (j * nt + i)], &p, sizeof p);
+    }
+  CU_TRY(pot, cudaStreamSynchronize(st));  // the previous table may still be in use
+  CU_TRY(pot, pot->zbl_table.reserve(sizeof(double) * table.size()));
+  CU_TRY(pot, cudaMemcpy(pot->zbl_table.p, table.data(), sizeof(double) * table.size(), cudaMemcpyHostToDevice));
+  pot->zbl_species = uniq;
   return 0;
 }
 
@@ -754,7 +835,8 @@ void rgpot_b200_default_config(int kind, RgpotB200Config* cfg) {
   cfg->kind = kind;
   cfg->device = -1;
   cfg->u0 = 1.0;
-  cfg->cutoff = kind == RGPOT_B200_CUH2 ? 6.1 : (kind == RGPOT_B200_MORSE ? 9.5 : 15.0);
+  cfg->cutoff = kind == RGPOT_B200_CUH2 ? 6.1 : (kind == RGPOT_B200_MORSE ? 9.5 : (kind == RGPOT_B200_ZBL ? 2.5 : 15.0));
+  cfg->zbl_cut_inner = 2.0;  // ZBLPot.hpp:29-32
   cfg->psi = 1.0;
   cfg->morse_De = 0.7102;  // MorsePot.hpp:31-36 (platinum)
   cfg->morse_a = 1.6047;
@@ -767,8 +849,10 @@ RgpotB200Pot* rgpot_b200_create(const RgpotB200Config* cfg, char* errbuf, size_t
     return nullptr;
   };
   if (!cfg) return err("rgpot_b200_create: null config");
-  if (cfg->kind < RGPOT_B200_LJ || cfg->kind > RGPOT_B200_MORSE)
+  if (cfg->kind < RGPOT_B200_LJ || cfg->kind > RGPOT_B200_ZBL)
     return err("rgpot_b200_create: unknown potential kind");
+  if (cfg->kind == RGPOT_B200_ZBL && (!(cfg->zbl_cut_inner > 0.0) || !(cfg->zbl_cut_inner < cfg->cutoff)))
+    return err("ZBLPot: invalid cutoffs, require 0.0 < cut_inner < cut_global.");  // ZBLPot.cc:76-79
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
   if (e != cudaSuccess || ndev == 0) {
@@ -961,17 +1045,30 @@ int rgpot_b200_force_device(RgpotB200Pot* pot, long nAtoms, const double* d_posi
   CU_TRY(pot, cudaSetDevice(pot->device));
   cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : pot->stream;
   pot->pend.active = false;
-  if (nAtoms < 0 || nAtoms > INT_MAX / 4) return fail(pot, kStatusArgs, "rgpot_b200: bad atom count");
+  if (nAtoms < 0 || nAtoms > kMaxAtoms) return fail(pot, kStatusArgs, "rgpot_b200: bad atom count");
   const bool eam = pot->cfg.kind == RGPOT_B200_CUH2;
   // reference early-outs: rgpot_cuh2_capi.f90:50 (natoms < 1), LJPot.cc:50-52, LJClusterPot.cc:43-45
   const bool trivial = eam ? nAtoms < 1
-                           : (nAtoms < 2 || (pot->cfg.kind != RGPOT_B200_LJ_CLUSTER && !(pot->cfg.cutoff > 0.0)));
+                           : (nAtoms < 2 || (pot->cfg.kind != RGPOT_B200_LJ_CLUSTER && pot->cfg.kind != RGPOT_B200_ZBL && !(pot->cfg.cutoff > 0.0)));
   if (trivial) {
     if (nAtoms > 0) CU_TRY(pot, cudaMemsetAsync(d_forces, 0, sizeof(double) * 3 * nAtoms, st));
     CU_TRY(pot, cudaMemsetAsync(d_energy, 0, sizeof(double), st));
     return 0;
   }
-  if (eam && !d_atomicNrs) return fail(pot, kStatusArgs, "rgpot_b200: CuH2 needs atomic numbers");
+  const bool zbl = pot->cfg.kind == RGPOT_B200_ZBL;
+  if ((eam || zbl) && !d_atomicNrs)
+    return fail(pot, kStatusArgs, "rgpot_b200: this potential needs atomic numbers");
+  if (zbl) {
+    // the species set decides the coefficient table: one round trip of the atomic numbers
+    std::vector<int> hz((size_t)nAtoms), types((size_t)nAtoms);
+    CU_TRY(pot, cudaMemcpyAsync(hz.data(), d_atomicNrs, sizeof(int) * nAtoms, cudaMemcpyDeviceToHost, st));
+    CU_TRY(pot, cudaStreamSynchronize(st));
+    int zs = zbl_prepare(pot, (size_t)nAtoms, hz.data(), types.data(), st);
+    if (zs) return zs;
+    CU_TRY(pot, pot->Z.reserve(sizeof(int) * nAtoms));
+    CU_TRY(pot, cudaMemcpy(pot->Z.p, types.data(), sizeof(int) * nAtoms, cudaMemcpyHostToDevice));
+    d_atomicNrs = pot->Z.as<int>();
+  }
   int s = force_device_impl(pot, nAtoms, d_positions, d_atomicNrs, d_forces, d_energy, box, st,
                             nullptr, 0);
   if (s) {
@@ -1038,13 +1135,14 @@ int rgpot_b200_force(RgpotB200Pot* pot, long nAtoms, const double* positions, co
   if (!energy || (nAtoms > 0 && (!positions || !forces)))
     return fail(pot, kStatusArgs, "rgpot_b200_force: null buffer");
   CU_TRY(pot, cudaSetDevice(pot->device));
-  if (nAtoms < 0 || nAtoms > INT_MAX / 4) return fail(pot, kStatusArgs, "rgpot_b200: bad atom count");
+  if (nAtoms < 0 || nAtoms > kMaxAtoms) return fail(pot, kStatusArgs, "rgpot_b200: bad atom count");
   const bool eam = pot->cfg.kind == RGPOT_B200_CUH2;
   const bool trivial = eam ? nAtoms < 1
-                           : (nAtoms < 2 || (pot->cfg.kind != RGPOT_B200_LJ_CLUSTER && !(pot->cfg.cutoff > 0.0)));
+                           : (nAtoms < 2 || (pot->cfg.kind != RGPOT_B200_LJ_CLUSTER && pot->cfg.kind != RGPOT_B200_ZBL && !(pot->cfg.cutoff > 0.0)));
   if (trivial) return 0;
-  if (eam && !atomicNrs) return fail(pot, kStatusArgs, "rgpot_b200: CuH2 needs atomic numbers");
-  if (pot->cfg.kind != RGPOT_B200_LJ_CLUSTER && !box)
+  const bool zbl = pot->cfg.kind == RGPOT_B200_ZBL;
+  if ((eam || zbl) && !atomicNrs) return fail(pot, kStatusArgs, "rgpot_b200: this potential needs atomic numbers");
+  if (pot->cfg.kind != RGPOT_B200_LJ_CLUSTER && pot->cfg.kind != RGPOT_B200_ZBL && !box)
     return fail(pot, kStatusArgs, "rgpot_b200_force: null box");
   cudaStream_t st = pot->stream;
   const size_t n = (size_t)nAtoms;
@@ -1056,6 +1154,14 @@ int rgpot_b200_force(RgpotB200Pot* pot, long nAtoms, const double* positions, co
   if (eam) {
     CU_TRY(pot, pot->Z.reserve(sizeof(int) * n));
     CU_TRY(pot, cudaMemcpyAsync(pot->Z.p, atomicNrs, sizeof(int) * n, cudaMemcpyHostToDevice, st));
+    d_Z = pot->Z.as<int>();
+  } else if (zbl) {
+    // species-pair tables are keyed on the set of atomic numbers (ZBLPot.cc:150-196)
+    std::vector<int> types(n);
+    int zs = zbl_prepare(pot, n, atomicNrs, types.data(), st);
+    if (zs) return zs;
+    CU_TRY(pot, pot->Z.reserve(sizeof(int) * n));
+    CU_TRY(pot, cudaMemcpy(pot->Z.p, types.data(), sizeof(int) * n, cudaMemcpyHostToDevice));
     d_Z = pot->Z.as<int>();
   }
   int s = force_device_impl(pot, nAtoms, pot->pos.as<double>(), d_Z, pot->F.as<double>(),
@@ -1098,6 +1204,13 @@ int rgpot_b200_neighbors(RgpotB200Pot* pot, long nAtoms, const double* positions
       atomicNrs = fakeZ.data();
     }
     CU_TRY(pot, cudaMemcpyAsync(pot->Z.p, atomicNrs, sizeof(int) * n, cudaMemcpyHostToDevice, st));
+    d_Z = pot->Z.as<int>();
+  } else if (pot->cfg.kind == RGPOT_B200_ZBL) {
+    std::vector<int> z(n, 1), types(n);
+    int zs = zbl_prepare(pot, n, atomicNrs ? atomicNrs : z.data(), types.data(), st);
+    if (zs) return zs;
+    CU_TRY(pot, pot->Z.reserve(sizeof(int) * n));
+    CU_TRY(pot, cudaMemcpy(pot->Z.p, types.data(), sizeof(int) * n, cudaMemcpyHostToDevice));
     d_Z = pot->Z.as<int>();
   }
   const size_t capz = (size_t)std::max<long>(cap, 1);
@@ -1198,7 +1311,7 @@ static int batch_device_impl(RgpotB200Pot* pot, size_t nsys, const size_t* offse
   for (int id : big_ids) {
     const long n = (long)(offsets[id + 1] - offsets[id]);
     const size_t o = offsets[id];
-    const bool trivial = eam ? n < 1 : (n < 2 || (kind != RGPOT_B200_LJ_CLUSTER && !(pot->cfg.cutoff > 0.0)));
+    const bool trivial = eam ? n < 1 : (n < 2 || (kind != RGPOT_B200_LJ_CLUSTER && kind != RGPOT_B200_ZBL && !(pot->cfg.cutoff > 0.0)));
     if (trivial) {
       if (n > 0) CU_TRY(pot, cudaMemsetAsync(d_F + 3 * o, 0, sizeof(double) * 3 * n, st));
       CU_TRY(pot, cudaMemsetAsync(d_E + id, 0, sizeof(double), st));
@@ -1305,6 +1418,9 @@ int rgpot_b200_force_batch_device(RgpotB200Pot* pot, size_t nSystems, const size
     return fail(pot, kStatusArgs, "rgpot_b200_force_batch_device: null buffer");
   if (pot->cfg.kind == RGPOT_B200_CUH2 && !d_atomicNrs)
     return fail(pot, kStatusArgs, "rgpot_b200: CuH2 needs atomic numbers");
+  if (pot->cfg.kind == RGPOT_B200_ZBL)
+    return fail(pot, kStatusArgs, "rgpot_b200: ZBL batches go through the host entry points "
+                                  "(the species table is built from the atomic numbers on the host)");
   CU_TRY(pot, cudaSetDevice(pot->device));
   cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : pot->stream;
   int s = batch_device_impl(pot, nSystems, offsets, d_positions, d_atomicNrs, d_boxes, nullptr, d_forces,
@@ -1345,7 +1461,7 @@ template <class StageIn, class StageOut>
 static int batch_pipeline(RgpotB200Pot* pot, size_t nsys, const size_t* rel, long nmax, const double* h_pos,
                           const int* h_Z, const double* h_boxes, double* h_F, double* h_E, int* statuses,
                           StageIn&& stage_in, StageOut&& stage_out) {
-  const bool eam = pot->cfg.kind == RGPOT_B200_CUH2;
+  const bool eam = pot->cfg.kind == RGPOT_B200_CUH2 || pot->cfg.kind == RGPOT_B200_ZBL;  // has a Z array
   const size_t total = rel[nsys];
   CU_TRY(pot, pot->b_pos.reserve(sizeof(double) * 3 * std::max<size_t>(total, 1)));
   CU_TRY(pot, pot->b_F.reserve(sizeof(double) * 3 * std::max<size_t>(total, 1)));
@@ -1364,7 +1480,7 @@ static int batch_pipeline(RgpotB200Pot* pot, size_t nsys, const size_t* rel, lon
   CU_TRY(pot, cudaEventRecord(pot->ev_ready, st0));
   for (auto& s : pot->pipe) CU_TRY(pot, cudaStreamWaitEvent(s, pot->ev_ready, 0));
 
-  const int maxnb = eam ? eam_small_maxnb(pot, nmax) : 0;
+  const int maxnb = pot->cfg.kind == RGPOT_B200_CUH2 ? eam_small_maxnb(pot, nmax) : 0;
   size_t chunk = (nsys + 15) / 16;
   chunk = std::min<size_t>(std::max<size_t>(chunk, 256), 8192);
   const size_t nchunks = (nsys + chunk - 1) / chunk;
@@ -1452,14 +1568,23 @@ int rgpot_b200_force_batch_packed(RgpotB200Pot* pot, size_t nSystems, const size
   if (nSystems == 0) return 0;
   if (!offsets || !positions || !boxes || !forces || !energies)
     return fail(pot, kStatusArgs, "rgpot_b200_force_batch_packed: null buffer");
-  const bool eam = pot->cfg.kind == RGPOT_B200_CUH2;
-  if (eam && !atomicNrs) return fail(pot, kStatusArgs, "rgpot_b200: CuH2 needs atomic numbers");
+  const bool zbl = pot->cfg.kind == RGPOT_B200_ZBL;
+  const bool eam = pot->cfg.kind == RGPOT_B200_CUH2 || zbl;  // "carries a per-atom integer array"
+  if (eam && !atomicNrs) return fail(pot, kStatusArgs, "rgpot_b200: this potential needs atomic numbers");
   CU_TRY(pot, cudaSetDevice(pot->device));
   cudaStream_t st = pot->stream;
   const size_t base = offsets[0];
   const size_t total = offsets[nSystems] - base;
   std::vector<size_t> rel(nSystems + 1);
   for (size_t s = 0; s <= nSystems; ++s) rel[s] = offsets[s] - base;
+  std::vector<int> zbl_types;
+  if (zbl) {
+    // one table over the union of the batch's species: coefficients only depend on the pair
+    zbl_types.resize(std::max<size_t>(total, 1));
+    int zs = zbl_prepare(pot, total, atomicNrs + base, zbl_types.data(), st);
+    if (zs) return zs;
+    atomicNrs = zbl_types.data() - base;
+  }
 
   const long nmax = batch_all_small(pot, nSystems, rel.data());
   if (nmax >= 0) {
@@ -1506,8 +1631,9 @@ int rgpot_b200_force_batch(RgpotB200Pot* pot, size_t nSystems, const size_t* nAt
   if (nSystems == 0) return 0;
   if (!nAtoms || !positions || !forces || !energies)
     return fail(pot, kStatusArgs, "rgpot_b200_force_batch: null buffer");
-  const bool eam = pot->cfg.kind == RGPOT_B200_CUH2;
-  if (eam && !atomicNrs) return fail(pot, kStatusArgs, "rgpot_b200: CuH2 needs atomic numbers");
+  const bool zbl = pot->cfg.kind == RGPOT_B200_ZBL;
+  const bool eam = pot->cfg.kind == RGPOT_B200_CUH2 || zbl;  // carries a per-atom integer array
+  if (eam && !atomicNrs) return fail(pot, kStatusArgs, "rgpot_b200: this potential needs atomic numbers");
   CU_TRY(pot, cudaSetDevice(pot->device));
   std::vector<size_t> off(nSystems + 1, 0);
   for (size_t s = 0; s < nSystems; ++s) {
@@ -1545,7 +1671,7 @@ int rgpot_b200_force_batch(RgpotB200Pot* pot, size_t nSystems, const size_t* nAt
     }
   };
   const long nmax = batch_all_small(pot, nSystems, off.data());
-  if (nmax >= 0)  // packing of chunk k+1 overlaps the copies and kernels of chunk k
+  if (nmax >= 0 && !zbl)  // packing of chunk k+1 overlaps the copies and kernels of chunk k
     return batch_pipeline(pot, nSystems, off.data(), nmax, hp, eam ? hz : nullptr, hbx, hF, hE, statuses, pack,
                           unpack);
   pack(0, nSystems);

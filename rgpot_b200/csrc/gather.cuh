@@ -171,8 +171,9 @@ k_lj_gather(GatherArgs a, double* __restrict__ F, double* __restrict__ partials)
   double e = 0.0, fx = 0.0, fy = 0.0, fz = 0.0;
   if (i < a.n) {
     const double4 pi = a.spos[i];
-    auto body = [&](int, unsigned long long, double dx, double dy, double dz, double d2, int, int,
-                    int) { lj_pair(a.lj, dx, dy, dz, d2, e, fx, fy, fz); };
+    const int ti = meta_species((unsigned long long)__double_as_longlong(pi.w));
+    auto body = [&](int, unsigned long long mj, double dx, double dy, double dz, double d2, int, int,
+                    int) { lj_pair(a.lj, ti, meta_species(mj), dx, dy, dz, d2, e, fx, fy, fz); };
     walk_dispatch<GEO>(a, i, pi, body);
     const int o = meta_orig((unsigned long long)__double_as_longlong(pi.w));
     F[3 * (size_t)o] = fx;

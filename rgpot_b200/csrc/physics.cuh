@@ -45,8 +45,24 @@ __constant__ EamParams c_eam;
 // Pair energy U and fs with F_i += fs * (r_i - r_j) for one accepted pair at squared distance r2.
 //   LJ    : CppCore/rgpot/LennardJones/LJPot.cc:61-81
 //   Morse : CppCore/rgpot/Morse/MorsePot.cc:53-62  (sqrt and exp as the reference calls them)
-RB_D void pair_eval(const LJParams& p, double r2, double& u, double& fs) {
-  if (p.morse) {
+//   ZBL   : CppCore/rgpot/ZBL/ZBLPot.cc:38-60 (e_zbl, dzbldr), :233-240 (switching)
+RB_D void pair_eval(const LJParams& p, double r2, int ti, int tj, double& u, double& fs) {
+  if (p.morse == 2) {
+    const double* c = p.zbl_table + 10 * (ti * p.zbl_nt + tj);
+    const double r = sqrt(r2);
+    const double r_inv = 1.0 / r;
+    const double e1 = exp(-c[0] * r), e2 = exp(-c[1] * r), e3 = exp(-c[2] * r), e4 = exp(-c[3] * r);
+    const double sum = 0.18175 * e1 + 0.50986 * e2 + 0.28022 * e3 + 0.02817 * e4;
+    const double sum_p = -0.18175 * c[0] * e1 - 0.50986 * c[1] * e2 - 0.28022 * c[2] * e3 - 0.02817 * c[3] * e4;
+    u = c[4] * sum * r_inv + c[9];
+    double dEdr = c[4] * (sum_p - sum * r_inv) * r_inv;
+    if (r2 > p.zbl_rin2) {
+      const double t = r - p.zbl_rin;
+      u += t * t * t * (c[7] + c[8] * t);
+      dEdr += t * t * (c[5] + c[6] * t);
+    }
+    fs = -dEdr / r;
+  } else if (p.morse == 1) {
     const double r = sqrt(r2);
     const double d = 1.0 - exp(-p.m_a * (r - p.m_re));
     u = p.m_de * d * d - p.m_de - p.m_ecut;
@@ -63,10 +79,10 @@ RB_D void pair_eval(const LJParams& p, double r2, double& u, double& fs) {
 
 // one directed entry of the gather form: half the pair energy, the whole force on i.
 // d = r_j - r_i (folded / shifted), so F_i -= fs * d   (LJPot.cc:70-77 with d = r_i - r_j).
-RB_D void lj_pair(const LJParams& p, double dx, double dy, double dz, double r2, double& e,
-                  double& fx, double& fy, double& fz) {
+RB_D void lj_pair(const LJParams& p, int ti, int tj, double dx, double dy, double dz, double r2,
+                  double& e, double& fx, double& fy, double& fz) {
   double u, fs;
-  pair_eval(p, r2, u, fs);
+  pair_eval(p, r2, ti, tj, u, fs);
   e += 0.5 * u;
   fx -= fs * dx;
   fy -= fs * dy;

@@ -30,8 +30,11 @@ struct SmallArgs {
   int maxnb;               // neighbor-list capacity per atom (EAM)
   int cluster;             // LJ: free boundaries
   double u0, psi2, shiftU, cutoff;  // LJ
-  int morse;                        // Morse instead of LJ
+  int morse;                        // 1 Morse, 2 ZBL instead of LJ
   double m_de, m_a, m_re, m_ecut;
+  const double* zbl_table;          // ZBL coefficient table (device)
+  int zbl_nt;
+  double zbl_rin;
   EmitArgs emit;           // optional (single system only)
 };
 
@@ -44,7 +47,10 @@ k_lj_small(SmallArgs a) {
   const long long base = a.off[sys];
   const int n = (int)(a.off[sys + 1] - base);
   double* px = smem;  // 3n interleaved
+  int* tp = reinterpret_cast<int*>(smem + 3 * n);  // ZBL: type index per atom
   for (int t = threadIdx.x; t < 3 * n; t += blockDim.x) px[t] = a.pos[3 * base + t];
+  if (a.morse == 2)
+    for (int t = threadIdx.x; t < n; t += blockDim.x) tp[t] = a.Z[base + t];
 
   // fold parameters: PairListCache.hpp:176-184 ; LJClusterPot.cc:46-55 (no fold at all)
   LJParams p;
@@ -58,6 +64,10 @@ k_lj_small(SmallArgs a) {
   p.m_re = a.m_re;
   p.m_ecut = a.m_ecut;
   p.m_two_de_a = 2.0 * a.m_de * a.m_a;
+  p.zbl_table = a.zbl_table;
+  p.zbl_nt = a.zbl_nt;
+  p.zbl_rin = a.zbl_rin;
+  p.zbl_rin2 = a.zbl_rin * a.zbl_rin;
   const double* box = a.boxes + 9 * (size_t)sys;
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
@@ -69,6 +79,7 @@ k_lj_small(SmallArgs a) {
   double e = 0.0;
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     const double xi = px[3 * i], yi = px[3 * i + 1], zi = px[3 * i + 2];
+    const int ti = a.morse == 2 ? tp[i] : 0;
     double fx = 0.0, fy = 0.0, fz = 0.0;
     for (int j = 0; j < n; ++j) {
       if (j == i) continue;
@@ -77,7 +88,7 @@ k_lj_small(SmallArgs a) {
       const double dz = fold_component(xsub(px[3 * j + 2], zi), p.w[2], p.inv[2]);
       const double r2 = xnorm2(dx, dy, dz);
       if (!(r2 <= p.rc2)) continue;
-      lj_pair(p, dx, dy, dz, r2, e, fx, fy, fz);
+      lj_pair(p, ti, a.morse == 2 ? tp[j] : 0, dx, dy, dz, r2, e, fx, fy, fz);
       if (a.emit.pairs != nullptr && i < j) {
         const unsigned long long k = atomicAdd(a.emit.count, 1ull);
         if ((long)k < a.emit.cap) {

@@ -267,6 +267,8 @@ k_tile(GatherArgs a, float thr2f, TileOut o) {
         if (POT == TILE_EAM_FORCE) {
           zi = meta_species((unsigned long long)__double_as_longlong(a.spos[self].w));
           dfd_i = o.dfd_sorted[self];
+        } else if (POT == TILE_LJ && a.lj.morse == 2) {
+          zi = meta_species((unsigned long long)__double_as_longlong(a.spos[self].w));
         }
       };
       bool used = false;  // the current atom received at least one survivor from this lane
@@ -308,7 +310,7 @@ k_tile(GatherArgs a, float thr2f, TileOut o) {
           if (d2 <= rc2 && j != self) {  // vesin_visit.hpp:104, and i != j
             double u, fs;
             if (a.lj.morse) {
-              pair_eval(a.lj, d2, u, fs);
+              pair_eval(a.lj, d2, zi, meta_species((unsigned long long)__double_as_longlong(pj.w)), u, fs);
             } else {
               const double invR2 = rcp_fast(d2);
               const double sr2 = a.lj.psi2 * invR2;

@@ -74,6 +74,24 @@ Engine::Engine(const MorseCudaConfig &c) {
   if (!h_) throw std::runtime_error(std::string("rgpot_b200 engine: ") + err);
 }
 
+Engine::Engine(const ZBLCudaConfig &c) {
+  if (!(c.cut_inner > 0.0) || !(c.cut_inner < c.cut_global))
+    throw std::invalid_argument("ZBLPot: invalid cutoffs, require 0.0 < cut_inner < cut_global.");
+  RgpotB200Config cfg;
+  rgpot_b200_default_config(RGPOT_B200_ZBL, &cfg);
+  cfg.device = c.device;
+  cfg.zbl_cut_inner = c.cut_inner;
+  cfg.cutoff = c.cut_global;
+  Fnv fp;  // ZBLPot.cc:80-84
+  fp.u64(kKernelVersion);
+  fp.f64(c.cut_inner);
+  fp.f64(c.cut_global);
+  key_ = fp.h;
+  char err[512] = {0};
+  h_ = rgpot_b200_create(&cfg, err, sizeof err);
+  if (!h_) throw std::runtime_error(std::string("rgpot_b200 engine: ") + err);
+}
+
 Engine::~Engine() { rgpot_b200_destroy(h_); }
 
 // FortranPots.cc:44-56: "<pot> potential failed (status k): <message>"

@@ -45,6 +45,13 @@ struct MorseCudaConfig {
   int device = -1;
 };
 
+/// ZBLConfig-compatible aggregate (ZBL/ZBLPot.hpp:29-32) plus the device ordinal.
+struct ZBLCudaConfig {
+  double cut_inner = 2.0;
+  double cut_global = 2.5;
+  int device = -1;
+};
+
 namespace b200detail {
 
 /// Owns one engine handle; shared by the three classes below.
@@ -52,6 +59,7 @@ class Engine {
 public:
   Engine(int kind, const LJCudaConfig &c);
   explicit Engine(const MorseCudaConfig &c);
+  explicit Engine(const ZBLCudaConfig &c);
   ~Engine();
   Engine(const Engine &) = delete;
   Engine &operator=(const Engine &) = delete;
@@ -121,6 +129,30 @@ public:
 
 private:
   MorseCudaConfig m_config;
+  std::shared_ptr<b200detail::Engine> m_engine;
+};
+
+/// rgpot::ZBLPot on the engine (ZBL/ZBLPot.hpp:60-130): free boundaries, species-pair tables.
+class ZBLCudaPot : public Potential<ZBLCudaPot> {
+public:
+  ZBLCudaPot() : ZBLCudaPot(ZBLCudaConfig{}) {}
+  /// @throws std::invalid_argument unless 0 < cut_inner < cut_global (ZBLPot.cc:76-79)
+  explicit ZBLCudaPot(const ZBLCudaConfig &c)
+      : Potential(PotType::ZBL), m_config(c), m_engine(std::make_shared<b200detail::Engine>(c)) {}
+  void forceImpl(const ForceInput &in, ForceOut *out) const override { m_engine->force("ZBL", in, out); }
+  void forceBatchImpl(const ForceBatch &batch) const override { m_engine->forceBatch("ZBL", batch); }
+  [[nodiscard]] PotCaps caps() const noexcept override {
+    PotCaps c;
+    c.reentrancy = Reentrancy::PerInstance;
+    c.batched = true;
+    c.periodic = false;
+    return c;
+  }
+  [[nodiscard]] uint64_t paramsKey() const noexcept override { return m_engine->paramsKey(); }
+  [[nodiscard]] const ZBLCudaConfig &config() const noexcept { return m_config; }
+
+private:
+  ZBLCudaConfig m_config;
   std::shared_ptr<b200detail::Engine> m_engine;
 };
 

@@ -135,6 +135,52 @@ int main() {
     CHECK(morse.get_type() == rgpot::PotType::Morse);
   }
 
+  // ---- ZBLPotTest.cc:36-142
+  {
+    rgpot::ZBLCudaPot zbl;
+    AtomMatrix dimer2{{9.40, 9.35, 9.30}, {10.60, 10.65, 10.70}};  // siAuDimer(), ZBLPotTest.cc:26-28
+    std::array<std::array<double, 3>, 3> c20{{{20, 0, 0}, {0, 20, 0}, {0, 0, 20}}};
+    std::array<std::array<double, 3>, 3> c3{{{3, 0, 0}, {0, 3, 0}, {0, 0, 3}}};
+    auto [e, f, v] = zbl(dimer2, std::vector<int>{14, 79}, c20);
+    (void)v;
+    CHECK(std::fabs(e - 0.38537731) < 1e-8);
+    const double ef[2][3] = {{-2.37926, -2.57753, -2.7758}, {2.37926, 2.57753, 2.7758}};
+    for (size_t i = 0; i < 2; ++i)
+      for (size_t j = 0; j < 3; ++j) CHECK(std::fabs(f(i, j) - ef[i][j]) < 1e-5);
+    auto [e_au, f_au, v_au] = zbl(dimer2, std::vector<int>{79, 79}, c20);
+    auto [e_si, f_si, v_si] = zbl(dimer2, std::vector<int>{14, 14}, c20);
+    auto [e_again, f_again, v_again] = zbl(dimer2, std::vector<int>{14, 79}, c20);
+    (void)f_au; (void)v_au; (void)f_si; (void)v_si; (void)f_again; (void)v_again;
+    CHECK(within_rel(e, 0.38537730883, 1e-9));
+    CHECK(within_rel(e_au, 0.961609764914, 1e-9));
+    CHECK(within_rel(e_si, 0.167604056792, 1e-9));
+    CHECK(e_again == e);
+    auto [e_tight, f_tight, v_tight] = zbl(dimer2, std::vector<int>{14, 79}, c3);
+    (void)f_tight; (void)v_tight;
+    CHECK(e_tight == e);
+    CHECK(!zbl.caps().periodic);
+    AtomMatrix at_cut{{5.0, 5.0, 5.0}, {7.5, 5.0, 5.0}};
+    auto [e_cut, f_cut, v_cut] = zbl(at_cut, std::vector<int>{14, 79}, c20);
+    (void)v_cut;
+    CHECK(std::fabs(e_cut) < 1e-12);
+    for (size_t i = 0; i < 2; ++i)
+      for (size_t j = 0; j < 3; ++j) CHECK(std::fabs(f_cut(i, j)) < 1e-12);
+    bool threw = false;
+    try {
+      rgpot::ZBLCudaConfig bad;
+      bad.cut_inner = 2.5;
+      bad.cut_global = 2.0;
+      rgpot::ZBLCudaPot p{bad};
+    } catch (const std::invalid_argument &) {
+      threw = true;
+    }
+    CHECK(threw);
+    rgpot::ZBLCudaConfig wide;
+    wide.cut_global = 4.5;
+    CHECK(rgpot::ZBLCudaPot{}.paramsKey() == zbl.paramsKey());
+    CHECK(rgpot::ZBLCudaPot{wide}.paramsKey() != zbl.paramsKey());
+  }
+
   std::printf(failures ? "test_host: %d FAILURES\n" : "test_host: ok\n", failures);
   return failures ? 1 : 0;
 }

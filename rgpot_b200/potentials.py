@@ -53,6 +53,7 @@ class PotType(Enum):
     LJ = 2
     Morse = 8
     LJCluster = 9
+    ZBL = 10
 
 
 @dataclass
@@ -81,6 +82,14 @@ class MorseConfig:
     a: float = 1.6047
     re: float = 2.8970
     cutoff: float = 9.5
+
+
+@dataclass
+class ZBLConfig:
+    """ZBL/ZBLPot.hpp:29-32"""
+
+    cut_inner: float = 2.0
+    cut_global: float = 2.5
 
 
 class PotentialError(RuntimeError):
@@ -136,7 +145,7 @@ class _EnginePot:
     _type = PotType.LJ
 
     def __init__(self, u0=1.0, cutoff=15.0, psi=1.0, device: int = -1, lj_all_images: bool = False,
-                 morse=None):
+                 morse=None, zbl=None):
         self._lib = _lib.lib()
         cfg = _lib.Config()
         self._lib.rgpot_b200_default_config(self._kind, C.byref(cfg))
@@ -144,6 +153,8 @@ class _EnginePot:
         if self._kind == _lib.KIND_MORSE:
             cfg.morse_De, cfg.morse_a, cfg.morse_re = float(morse.De), float(morse.a), float(morse.re)
             cfg.cutoff = float(morse.cutoff)
+        elif self._kind == _lib.KIND_ZBL:
+            cfg.zbl_cut_inner, cfg.cutoff = float(zbl.cut_inner), float(zbl.cut_global)
         elif self._kind != _lib.KIND_CUH2:
             cfg.u0, cfg.cutoff, cfg.psi = float(u0), float(cutoff), float(psi)
             cfg.lj_all_images = int(bool(lj_all_images))
@@ -151,7 +162,10 @@ class _EnginePot:
         err = C.create_string_buffer(512)
         self._h = self._lib.rgpot_b200_create(C.byref(cfg), err, 512)
         if not self._h:
-            raise RuntimeError(err.value.decode() or "rgpot_b200_create failed")
+            msg = err.value.decode() or "rgpot_b200_create failed"
+            if "invalid cutoffs" in msg:
+                raise ValueError(msg)  # std::invalid_argument upstream (ZBLPot.cc:76-79)
+            raise RuntimeError(msg)
         self.force_calls = 0  # registry<T>::forceCalls (PotHelpers.hpp:31-34)
 
     def __del__(self):
@@ -166,12 +180,15 @@ class _EnginePot:
 
     def caps(self) -> PotCaps:
         return PotCaps(reentrancy=Reentrancy.PerInstance, batched=True,
-                       periodic=self._kind != _lib.KIND_LJ_CLUSTER)
+                       periodic=self._kind not in (_lib.KIND_LJ_CLUSTER, _lib.KIND_ZBL))
 
     def paramsKey(self) -> int:
         if self._kind == _lib.KIND_CUH2:
             return _fnv1a([struct.pack("<Q", _KERNEL_VERSION)])
         c = self._cfg
+        if self._kind == _lib.KIND_ZBL:  # ZBLPot.cc:80-84
+            return _fnv1a([struct.pack("<Q", _KERNEL_VERSION), struct.pack("<d", c.zbl_cut_inner),
+                           struct.pack("<d", c.cutoff)])
         if self._kind == _lib.KIND_MORSE:  # MorsePot.hpp:62-68
             return _fnv1a([struct.pack("<Q", _KERNEL_VERSION), struct.pack("<d", c.morse_De),
                            struct.pack("<d", c.morse_a), struct.pack("<d", c.morse_re),
@@ -364,6 +381,21 @@ class MorsePot(_EnginePot):
         c = self._config
         d = 1.0 - math.exp(-c.a * (c.cutoff - c.re))
         return c.De * d * d - c.De
+
+
+class ZBLPot(_EnginePot):
+    """Ziegler-Biersack-Littmark screened nuclear repulsion with switching, free boundaries
+    (ZBL/ZBLPot.hpp:60-130)."""
+
+    _kind, _label, _type = _lib.KIND_ZBL, "ZBL", PotType.ZBL
+
+    def __init__(self, config: ZBLConfig | None = None, device: int = -1):
+        c = config or ZBLConfig()
+        self._config = c
+        super().__init__(device=device, zbl=c)
+
+    def config(self) -> ZBLConfig:
+        return self._config
 
 
 class CuH2Pot(_EnginePot):

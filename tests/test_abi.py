@@ -39,6 +39,8 @@ def test_abi_version_and_defaults(engine):
     assert cfg.cutoff == 6.1  # rgpot_cuh2.f90:100
     engine.rgpot_b200_default_config(_lib.KIND_MORSE, cfg)
     assert (cfg.morse_De, cfg.morse_a, cfg.morse_re, cfg.cutoff) == (0.7102, 1.6047, 2.8970, 9.5)  # MorsePot.hpp:31-36
+    engine.rgpot_b200_default_config(_lib.KIND_ZBL, cfg)
+    assert (cfg.zbl_cut_inner, cfg.cutoff) == (2.0, 2.5)  # ZBLPot.hpp:29-32
 
 
 def test_fortran_dropin_symbols_present(engine):

@@ -417,3 +417,62 @@ def test_morse_vs_oracle(oracle, n, wrapped, path):
     e_o, f_o, _ = oracle.morse_force(pos, box)
     assert_energy(e, e_o)
     assert_forces(f, f_o)
+
+
+# ------------------------------------------------------------------------------------------ ZBL
+def test_zbl_pins():
+    """CppCore/tests/ZBLPotTest.cc:36-160 (free boundaries, species tables)."""
+    pot = rgpot_b200.ZBLPot()
+    dimer = np.array([[9.40, 9.35, 9.30], [10.60, 10.65, 10.70]])
+    cell = np.eye(3) * 20.0
+    e, f, _ = pot(dimer, [14, 79], cell)
+    assert e == pytest.approx(0.38537731, abs=1e-8)  # LAMMPS pair_style zbl 2.0 2.5
+    assert np.abs(f - np.array([[-2.37926, -2.57753, -2.7758], [2.37926, 2.57753, 2.7758]])).max() < 1e-5
+    assert e == pytest.approx(0.38537730883, rel=1e-9)
+    # tables follow the species set of each call (ZBLPotTest.cc:91-115)
+    assert pot(dimer, [79, 79], cell)[0] == pytest.approx(0.961609764914, rel=1e-9)
+    assert pot(dimer, [14, 14], cell)[0] == pytest.approx(0.167604056792, rel=1e-9)
+    assert pot(dimer, [14, 79], cell)[0] == e
+    # the cell is ignored (:117-131)
+    assert pot(dimer, [14, 79], np.eye(3) * 3.0)[0] == e
+    assert not pot.caps().periodic
+    # switching zeroes energy and force at the cutoff (:57-89)
+    e_cut, f_cut, _ = pot(np.array([[5.0, 5.0, 5.0], [7.5, 5.0, 5.0]]), [14, 79], cell)
+    assert abs(e_cut) < 1e-12 and np.abs(f_cut).max() < 1e-12
+    e_far, f_far, _ = pot(np.array([[5.0, 5.0, 5.0], [8.0, 5.0, 5.0]]), [14, 79], cell)
+    assert e_far == 0.0 and not f_far.any()
+    # invalid cutoff pairs (:133-146), fingerprint (:148-157)
+    for bad in [(2.5, 2.0), (2.0, 2.0), (0.0, 2.5)]:
+        with pytest.raises(ValueError):
+            rgpot_b200.ZBLPot(rgpot_b200.ZBLConfig(*bad))
+    wide = rgpot_b200.ZBLPot(rgpot_b200.ZBLConfig(2.0, 4.5))
+    assert rgpot_b200.ZBLPot().paramsKey() == pot.paramsKey() != wide.paramsKey()
+
+
+@pytest.mark.parametrize("n,path", [(200, 2), (2500, 1), (2500, 0)])
+def test_zbl_vs_oracle(oracle, n, path):
+    rng = np.random.default_rng(n + path)
+    L = (n / 0.09) ** (1 / 3)  # a few neighbours inside 2.5 A
+    pos = rng.random((n, 3)) * L
+    Z = rng.choice([1, 8, 14, 29, 79], n).astype(np.int32)
+    pot = rgpot_b200.ZBLPot()
+    pot.set_path(path)
+    e, f, _ = pot(pos, Z, np.eye(3) * 5.0)
+    e_o, f_o, _ = oracle.zbl_force(pos, Z)
+    assert_energy(e, e_o)
+    assert (np.abs(f - f_o) <= 1e-9 + 1e-10 * np.abs(f_o)).all()
+    # batches share one table over the union of the species
+    half = n // 2
+    out = pot.forceBatch([(pos[:half], Z[:half], np.eye(3)), (pos[half:], Z[half:], np.eye(3))])
+    for (eb, fb, _), sl in zip(out, (slice(0, half), slice(half, n))):
+        eo, fo, _ = oracle.zbl_force(pos[sl], Z[sl])
+        assert_energy(eb, eo)
+        assert (np.abs(fb - fo) <= 1e-9 + 1e-10 * np.abs(fo)).all()
+
+
+def test_zbl_too_many_species():
+    pot = rgpot_b200.ZBLPot()
+    pos = np.random.default_rng(0).random((20, 3)) * 6
+    with pytest.raises(rgpot_b200.PotentialError) as ei:
+        pot(pos, np.arange(1, 21, dtype=np.int32), np.eye(3) * 6)
+    assert ei.value.status == 103

@@ -167,3 +167,19 @@ def test_morse_pins(oracle, golden):
     assert f[0] == pytest.approx([-2056.95286055812, 333.678513150438, 1022.83140169994], rel=1e-9)
     assert np.sqrt((f ** 2).sum(1)).max() == pytest.approx(2480.28362300107, rel=1e-9)
     assert np.abs(f.sum(0)).max() < 1e-9
+
+
+def test_zbl_pins(oracle):
+    # CppCore/tests/ZBLPotTest.cc:36-142: LAMMPS pair_style zbl 2.0 2.5 values
+    dimer = np.array([[9.40, 9.35, 9.30], [10.60, 10.65, 10.70]])
+    e, f, n = oracle.zbl_force(dimer, [14, 79])
+    assert n == 1
+    assert e == pytest.approx(0.38537731, abs=1e-8)
+    assert np.abs(f - np.array([[-2.37926, -2.57753, -2.7758], [2.37926, 2.57753, 2.7758]])).max() < 1e-5
+    assert e == pytest.approx(0.38537730883, rel=1e-9)
+    assert oracle.zbl_force(dimer, [79, 79])[0] == pytest.approx(0.961609764914, rel=1e-9)
+    assert oracle.zbl_force(dimer, [14, 14])[0] == pytest.approx(0.167604056792, rel=1e-9)
+    e_cut, f_cut, _ = oracle.zbl_force([[5.0, 5.0, 5.0], [7.5, 5.0, 5.0]], [14, 79])
+    assert abs(e_cut) < 1e-12 and np.abs(f_cut).max() < 1e-12
+    e_far, f_far, n_far = oracle.zbl_force([[5.0, 5.0, 5.0], [8.0, 5.0, 5.0]], [14, 79])
+    assert n_far == 0 and e_far == 0.0 and not f_far.any()

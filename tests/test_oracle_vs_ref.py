@@ -86,3 +86,13 @@ def test_morse_restatement_is_bit_exact(ref):
         e_r, f_r = ref.ref_morse_force(pos, box, 0.7102, 1.6047, 2.8970, rc)
         e_o, f_o, _ = ref.morse_force(pos, box, 0.7102, 1.6047, 2.8970, rc)
         assert e_o == e_r and np.array_equal(f_o, f_r)
+
+
+def test_zbl_restatement_is_bit_exact(ref):
+    rng = np.random.default_rng(13)
+    for n, L, species in [(60, 7.0, [14, 79]), (120, 9.0, [1, 8, 14, 29, 79]), (30, 4.0, [6])]:
+        pos = rng.random((n, 3)) * L
+        Z = rng.choice(species, n).astype(np.int32)
+        e_r, f_r = ref.ref_zbl_force(pos, Z, np.eye(3) * 3.0)  # the cell is ignored
+        e_o, f_o, _ = ref.zbl_force(pos, Z)
+        assert e_o == e_r and np.array_equal(f_o, f_r)
