@@ -548,7 +548,10 @@ int run_cell_path(RgpotB200Pot* pot, long n, const double* d_pos, const int* d_Z
     const double margin = 1.0e-6 * 4.0 * edge + 1.0e-5 * rc;
     const float thr2f = (float)((rc + margin) * (rc + margin) * (1.0 + 1.0e-6));
     TileOut to{d_F, d_part, nullptr, nullptr, d_st};
-    k_tile<TILE_LJ><<<div_up(ncells, kTileWarps), kTileWarps * 32, 0, st>>>(ga, thr2f, to);
+    if (pl.lj.morse)
+      k_tile<TILE_PAIR><<<div_up(ncells, kTileWarps), kTileWarps * 32, 0, st>>>(ga, thr2f, to);
+    else
+      k_tile<TILE_LJ><<<div_up(ncells, kTileWarps), kTileWarps * 32, 0, st>>>(ga, thr2f, to);
     LAUNCH_CHECK(pot, "k_tile<lj>");
     ga.only_if_atom_shift = 1;
     k_lj_gather<GEO_LJ_SHIFT><<<nblk, 128, 0, st>>>(ga, d_F, d_part);

@@ -128,7 +128,7 @@ RB_D double seg_scan(double v, int key, int lane) {
 // registers; the partial sum of every (lane, atom) piece is parked in a shared slot and each
 // atom's owner lane adds the pieces that belong to it in lane order.  No queue, no atomics, a
 // fixed summation order.
-enum { TILE_LJ = 0, TILE_EAM_DENSITY = 1, TILE_EAM_FORCE = 2 };
+enum { TILE_LJ = 0, TILE_EAM_DENSITY = 1, TILE_EAM_FORCE = 2, TILE_PAIR = 3 };  // TILE_PAIR: Morse / ZBL on the LJ geometry
 constexpr int kTilePieces = 4;  // (lane, atom) pieces a lane may produce per chunk
 
 struct TileOut {
@@ -168,10 +168,11 @@ k_tile(GatherArgs a, float thr2f, TileOut o) {
   }
   const Grid& g = a.grid;
   const int cx = cell % g.nc[0], cy = (cell / g.nc[0]) % g.nc[1], cz = cell / (g.nc[0] * g.nc[1]);
-  const int ncand = tile_build_segments<POT == TILE_LJ>(a, w, cx, cy, cz, lane);
+  constexpr bool kPairGeo = POT == TILE_LJ || POT == TILE_PAIR;  // LJ pair search (one image per stencil cell)
+  const int ncand = tile_build_segments<kPairGeo>(a, w, cx, cy, cz, lane);
   const double4 o4 = a.spos[ib];  // local origin of the FP32 offsets
-  const double rc2 = POT == TILE_LJ ? a.lj.rc2 : a.rc2;
-  const double rc2_phys = POT == TILE_LJ ? 0.0 : c_eam.rc2_phys;
+  const double rc2 = kPairGeo ? a.lj.rc2 : a.rc2;
+  const double rc2_phys = kPairGeo ? 0.0 : c_eam.rc2_phys;
   constexpr int NV = POT == TILE_EAM_DENSITY ? 1 : 3;
   double e_lane = 0.0;
   bool coincident = false;
@@ -267,7 +268,7 @@ k_tile(GatherArgs a, float thr2f, TileOut o) {
         if (POT == TILE_EAM_FORCE) {
           zi = meta_species((unsigned long long)__double_as_longlong(a.spos[self].w));
           dfd_i = o.dfd_sorted[self];
-        } else if (POT == TILE_LJ && a.lj.morse == 2) {
+        } else if (POT == TILE_PAIR) {
           zi = meta_species((unsigned long long)__double_as_longlong(a.spos[self].w));
         }
       };
@@ -308,17 +309,20 @@ k_tile(GatherArgs a, float thr2f, TileOut o) {
         const double d2 = xnorm2(dx, dy, dz);
         if (POT == TILE_LJ) {
           if (d2 <= rc2 && j != self) {  // vesin_visit.hpp:104, and i != j
+            const double invR2 = rcp_fast(d2);
+            const double sr2 = a.lj.psi2 * invR2;
+            const double a6 = sr2 * sr2 * sr2;
+            const double b = 4.0 * a.lj.u0 * a6;
+            e_lane += 0.5 * (b * (a6 - 1.0) - a.lj.shiftU);
+            const double fs = 6.0 * b * invR2 * (2.0 * a6 - 1.0);
+            acc[0] = fma(-fs, dx, acc[0]);
+            acc[1] = fma(-fs, dy, acc[1]);
+            acc[2] = fma(-fs, dz, acc[2]);
+          }
+        } else if (POT == TILE_PAIR) {
+          if (d2 <= rc2 && j != self) {
             double u, fs;
-            if (a.lj.morse) {
-              pair_eval(a.lj, d2, zi, meta_species((unsigned long long)__double_as_longlong(pj.w)), u, fs);
-            } else {
-              const double invR2 = rcp_fast(d2);
-              const double sr2 = a.lj.psi2 * invR2;
-              const double a6 = sr2 * sr2 * sr2;
-              const double b = 4.0 * a.lj.u0 * a6;
-              u = b * (a6 - 1.0) - a.lj.shiftU;
-              fs = 6.0 * b * invR2 * (2.0 * a6 - 1.0);
-            }
+            pair_eval(a.lj, d2, zi, meta_species((unsigned long long)__double_as_longlong(pj.w)), u, fs);
             e_lane += 0.5 * u;
             acc[0] = fma(-fs, dx, acc[0]);
             acc[1] = fma(-fs, dy, acc[1]);
