@@ -53,6 +53,7 @@ SYMBOLS = [
     ("rgpot_b200_neighbors", _i, [_vp, _l, _vp, _vp, _vp, _i, _l, _vp, _vp, C.POINTER(_l)]),
     ("rgpot_b200_last_error", _i, [_vp, C.c_char_p, _i]),
     ("rgpot_b200_launch_count", _l, [_vp]),
+    ("rgpot_b200_stat", _l, [_vp, C.c_char_p]),
     ("rgpot_b200_set_option", _i, [_vp, C.c_char_p, _l]),
     ("rgpot_b200_host_alloc", _vp, [_sz]),
     ("rgpot_b200_host_free", None, [_vp]),

@@ -1,0 +1,513 @@
+// brick.cuh -- brick kernels for one large system (the >= 100k-atom configurations).
+//
+// One thread block owns a BRICK of cells of the cell list (cell edge >= rc / ns, ns = 1 or 2, so
+// the stencil of a cell is (2 ns + 1)^3 cells; with ns = 2 an atom tests 211 candidates in an LJ
+// fluid where 27 cutoff-sized cells offer 364).  Three stages, all in shared memory:
+//
+//   stage   the atoms of the brick's halo (brick + ns cells on every side, periodic images
+//           included) are copied once: FP64 positions as x / y / z arrays, and an FP32 copy of the
+//           image-shifted position relative to the brick origin (with image code and species).
+//           A brick of 108 atoms stages 864 candidates (8 per atom); a per-cell walk reads 27+.
+//   search  every thread owns an atom (kTPA threads share one and split the stencil rows): FP32
+//           prefilter over the atom's own stencil -- the (2 ns + 1)^2 rows of 2 ns + 1 cells that
+//           are contiguous in the staged order -- 6 FP32 operations, a compare and a predicated
+//           16-bit store into the thread's private survivor list.  FP32 pipe only; no ballots,
+//           no queues, no compaction, no block barrier before the next stage.
+//   physics the thread walks its list: the separation is redone in FP64 with the REFERENCE's
+//           expression ((p_j - p_i) + shift, unfused norm: accept / reject is bit-exact), the pair
+//           terms are evaluated and accumulated in registers.  Every lane works on a survivor;
+//           the sums have a fixed order (stencil order, then a fixed shuffle tree over the kTPA
+//           threads): bit-reproducible, no atomics.
+//
+// The kernels are valid for the fast geometry only (no atom outside the cell; LJ: every periodic
+// direction >= 2 ns + 1 cells); they return immediately when the binning flags say otherwise and
+// the gather kernels of gather.cuh take over.  A brick whose halo does not fit the staged capacity,
+// or an atom whose survivors overflow its list, is evaluated by the same block with the per-atom
+// gather walk -- slower, same results, no host round trip.
+#pragma once
+
+#include "gather.cuh"
+
+namespace rb {
+
+enum { TILE_LJ = 0, TILE_EAM_DENSITY = 1, TILE_EAM_FORCE = 2, TILE_PAIR = 3 };  // TILE_PAIR: Morse / ZBL on the LJ geometry
+
+constexpr int kBrickMaxThreads = 256;
+constexpr int kBrickMaxHalo = 512;  // (4 + 2*2)^3
+constexpr int kBrickMaxCells = 64;
+constexpr int kShiftCodes = 125;    // image counts q in [-2, 2]^3
+
+template <bool B>
+struct BoolTag {
+  static constexpr bool value = B;
+};
+
+struct TileOut {
+  double* F;            // forces, original order (LJ, EAM force)
+  double* partials;     // per-brick energy partials (LJ, EAM force)
+  double* dfd_sorted;   // EAM: F'(rho), sorted order (written by density, read by force)
+  double* eemb_sorted;  // EAM: F(rho)
+  Status* st;
+};
+
+struct BrickPlan {
+  int bd[3];      // cells per brick and direction
+  int nb[3];      // bricks per direction
+  int ns[3];      // stencil half width per direction (cells)
+  int nbricks;
+  int cap_cand;   // staged halo atoms a block can hold (multiple of 32)
+  int cap_list;   // survivor-list entries per thread
+  int tpa;        // threads per atom (1, 2, 4)
+  int threads;    // block size
+  float thr2f;    // FP32 prefilter threshold (conservative superset of d2 <= rc2)
+  unsigned smem;  // dynamic shared memory per block
+};
+
+RB_HD unsigned brick_smem_bytes(int cap_cand, int cap_list, int threads, bool force_pass) {
+  return (unsigned)(cap_cand * ((force_pass ? 4 : 3) * sizeof(double) + sizeof(float4) + sizeof(unsigned short)) +
+                    (size_t)cap_list * threads * sizeof(unsigned short) + 16);
+}
+
+// 1/a for normal positive a: hardware seed + one cubic Newton step (~1 ulp), no slow path
+RB_D double rcp_fast(double a) {
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+  const double e = fma(-a, y, 1.0);  // |e| <= 2^-22 (seed accuracy); y (1 + e + e^2) leaves e^3
+  return fma(y, fma(e, e, e), y);
+}
+
+// ---- per-atom gather walk (the in-kernel slow path of an oversized brick) -----------------------
+template <int POT>
+__device__ __noinline__ void brick_slow_atom(const GatherArgs& a, const TileOut& o, int i, double& e, bool& coincident) {
+  const double4 pi = a.spos[i];
+  const unsigned long long mi = (unsigned long long)__double_as_longlong(pi.w);
+  const int zi = meta_species(mi);
+  double fx = 0.0, fy = 0.0, fz = 0.0;
+  if (POT == TILE_LJ || POT == TILE_PAIR) {
+    auto body = [&](int, unsigned long long mj, double dx, double dy, double dz, double d2, int, int, int) {
+      lj_pair(a.lj, zi, meta_species(mj), dx, dy, dz, d2, e, fx, fy, fz);
+    };
+    walk_neighbors<GEO_LJ_SHIFT, false>(a, i, pi, body);
+  } else if (POT == TILE_EAM_DENSITY) {
+    const double rc2_phys = c_eam.rc2_phys;
+    double rho = 0.0;
+    auto body = [&](int, unsigned long long mj, double, double, double, double d2, int, int, int) {
+      if (d2 == 0.0) coincident = true;
+      if (!(d2 < rc2_phys)) return;
+      rho += eam_density_entry(meta_species(mj), d2);
+    };
+    walk_neighbors<GEO_IMAGES, false>(a, i, pi, body);
+    double emb, demb;
+    eam_embed(zi, rho, emb, demb);
+    o.dfd_sorted[i] = demb;
+    o.eemb_sorted[i] = emb;
+    return;
+  } else {
+    const double rc2_phys = c_eam.rc2_phys;
+    const double dfd_i = o.dfd_sorted[i];
+    auto body = [&](int j, unsigned long long mj, double dx, double dy, double dz, double d2, int, int, int) {
+      if (!(d2 < rc2_phys)) return;
+      eam_force_entry(zi, meta_species(mj), dfd_i, o.dfd_sorted[j], dx, dy, dz, d2, e, fx, fy, fz);
+    };
+    walk_neighbors<GEO_IMAGES, false>(a, i, pi, body);
+    e += o.eemb_sorted[i];
+  }
+  const int orig = meta_orig(mi);
+  o.F[3 * (size_t)orig] = fx;
+  o.F[3 * (size_t)orig + 1] = fy;
+  o.F[3 * (size_t)orig + 2] = fz;
+}
+
+// ---- the brick kernel ------------------------------------------------------------------------
+template <int POT, int TPA>
+__global__ void __launch_bounds__(kBrickMaxThreads, 3)
+k_brick(const __grid_constant__ GatherArgs a, const __grid_constant__ BrickPlan bp,
+        const __grid_constant__ TileOut o) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ unsigned short hstart[kBrickMaxHalo + 2];  // staged start of every halo cell
+  __shared__ int hgstart[kBrickMaxHalo];                // start of the halo cell in the sorted atom array
+  __shared__ unsigned char hcode[kBrickMaxHalo];        // image code of the halo cell
+  __shared__ double svtab[kShiftCodes][3];              // image vector per code (reference arithmetic)
+  __shared__ unsigned short bc_astart[kBrickMaxCells + 2];  // brick-local atom prefix
+  __shared__ int s_shifted, s_ntot;
+  __shared__ int box_stack[8][6];  // boxes of cells still to do: first cell, extent
+  __shared__ int box_sp;
+
+  if (a.st_in->flags & kFlagAtomShift) return;  // the gather kernels of gather.cuh take over
+  constexpr bool kPairGeo = POT == TILE_LJ || POT == TILE_PAIR;  // LJ pair search (w * q image vectors)
+  constexpr bool kForce = POT == TILE_EAM_FORCE;
+  constexpr int NV = POT == TILE_EAM_DENSITY ? 1 : 3;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int nthreads = blockDim.x;
+  const Grid& g = a.grid;
+
+  double* c64 = reinterpret_cast<double*>(smem_raw);  // x, y, z of staged atom s at c64[3 s ..]
+  double* c64w = c64 + 3 * bp.cap_cand;               // EAM force pass: F'(rho_j)
+  float4* c32 = reinterpret_cast<float4*>(c64 + (kForce ? 4 : 3) * bp.cap_cand);  // offset x, y, z, |offset|^2
+  unsigned short* cinfo = reinterpret_cast<unsigned short*>(c32 + bp.cap_cand);   // image code | species << 8
+  unsigned short* lists = cinfo + bp.cap_cand;
+
+  // image vectors; the brick of this block as the first box
+  if (tid < kShiftCodes) {
+    const double q0 = (double)(tid % 5 - 2), q1 = (double)((tid / 5) % 5 - 2), q2 = (double)(tid / 25 - 2);
+    if (kPairGeo) {
+      svtab[tid][0] = xmul(a.lj.w[0], q0);
+      svtab[tid][1] = xmul(a.lj.w[1], q1);
+      svtab[tid][2] = xmul(a.lj.w[2], q2);
+    } else {
+      svtab[tid][0] = shift_component(a.box.H, 0, q0, q1, q2);
+      svtab[tid][1] = shift_component(a.box.H, 1, q0, q1, q2);
+      svtab[tid][2] = shift_component(a.box.H, 2, q0, q1, q2);
+    }
+  }
+  if (tid == 0) {
+    const int b[3] = {(int)blockIdx.x % bp.nb[0], ((int)blockIdx.x / bp.nb[0]) % bp.nb[1],
+                      (int)blockIdx.x / (bp.nb[0] * bp.nb[1])};
+    for (int k = 0; k < 3; ++k) {
+      box_stack[0][k] = b[k] * bp.bd[k];
+      box_stack[0][3 + k] = min(bp.bd[k], g.nc[k] - b[k] * bp.bd[k]);
+    }
+    box_sp = 1;
+  }
+  double e_thr = 0.0;
+  bool coincident = false;
+
+  // A brick whose halo exceeds the staged capacity (a locally dense region) is cut in two and the
+  // halves are done one after the other; every atom sees the same candidates in the same order
+  // either way, so the results do not depend on the capacities.
+  for (;;) {
+    __syncthreads();
+    const int sp = box_sp;
+    if (sp == 0) break;
+    int c0[3], bw[3], hd[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      c0[k] = box_stack[sp - 1][k];
+      bw[k] = box_stack[sp - 1][3 + k];
+      hd[k] = bw[k] + 2 * bp.ns[k];
+    }
+    const int nh = hd[0] * hd[1] * hd[2];
+    const int nbc = bw[0] * bw[1] * bw[2];
+    __syncthreads();
+    if (tid == 0) {
+      box_sp = sp - 1;
+      s_shifted = 0;
+    }
+    __syncthreads();
+
+    // ---- halo cells ---------------------------------------------------------------------------------
+    const float inv_hd0 = 1.0f / (float)hd[0], inv_hd1 = 1.0f / (float)hd[1];
+    for (int h = tid; h < nh; h += nthreads) {
+      // h = (hz * hd1 + hy) * hd0 + hx; small numbers: exact float division
+      const int hyz = (int)(((float)h + 0.5f) * inv_hd0);
+      const int hz = (int)(((float)hyz + 0.5f) * inv_hd1);
+      const int hc[3] = {h - hyz * hd[0], hyz - hz * hd[1], hz};
+      int q[3], r[3];
+      bool valid = true;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        q[k] = 0;
+        r[k] = c0[k] - bp.ns[k] + hc[k];
+        if (a.box.periodic[k]) {
+          while (r[k] < 0) {
+            r[k] += g.nc[k];
+            --q[k];
+          }
+          while (r[k] >= g.nc[k]) {
+            r[k] -= g.nc[k];
+            ++q[k];
+          }
+        } else if (r[k] < 0 || r[k] >= g.nc[k]) {
+          valid = false;
+        }
+      }
+      int hcount = 0, jb = 0;
+      if (valid) {
+        const int cell = (r[2] * g.nc[1] + r[1]) * g.nc[0] + r[0];
+        jb = a.starts[cell];
+        hcount = min(a.starts[cell + 1] - jb, 65535);
+        if (hcount > 0 && (q[0] | q[1] | q[2]) != 0) s_shifted = 1;
+      }
+      hgstart[h] = jb;
+      hcode[h] = (unsigned char)((q[2] + 2) * 25 + (q[1] + 2) * 5 + (q[0] + 2));
+      hstart[h + 1] = (unsigned short)hcount;  // counts first, prefix below
+    }
+    __syncthreads();
+    if (wid == 0) {  // exclusive prefix over <= 512 counts: sixteen per lane
+      int sum = 0;
+      for (int t = 0; t < 16; ++t) {
+        const int h = lane * 16 + t;
+        if (h < nh) sum += hstart[h + 1];
+      }
+      int incl = sum;
+#pragma unroll
+      for (int off = 1; off < 32; off <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, off);
+        if (lane >= off) incl += t;
+      }
+      int run = incl - sum;
+      if (lane == 0) hstart[0] = 0;
+      for (int t = 0; t < 16; ++t) {
+        const int h = lane * 16 + t;
+        if (h < nh) {
+          run += hstart[h + 1];
+          hstart[h + 1] = (unsigned short)min(run, 65535);
+        }
+      }
+      if (lane == 31) s_ntot = incl;
+    }
+    __syncthreads();
+    const int ntot = s_ntot;
+    if (ntot > bp.cap_cand) {
+      int kmax = 2;
+      for (int k = 1; k >= 0; --k)
+        if (bw[k] > bw[kmax]) kmax = k;
+      if (bw[kmax] > 1) {  // cut the box in two along its longest direction
+        if (tid == 0) {
+          const int half = bw[kmax] / 2;
+          for (int part = 0; part < 2; ++part) {
+            for (int k = 0; k < 3; ++k) {
+              box_stack[sp - 1 + part][k] = c0[k] + (k == kmax && part == 0 ? half : 0);
+              box_stack[sp - 1 + part][3 + k] = k == kmax ? (part == 0 ? bw[k] - half : half) : bw[k];
+            }
+          }
+          box_sp = sp + 1;
+        }
+        continue;
+      }
+      // a single cell whose stencil does not fit: per-atom gather walk straight from global memory
+      int r[3] = {c0[0], c0[1], c0[2]};
+      const int cell = (r[2] * g.nc[1] + r[1]) * g.nc[0] + r[0];
+      const int jb = a.starts[cell], je = a.starts[cell + 1];
+      if (tid == 0 && je > jb) atomicAdd(&o.st->slow_atoms, je - jb);
+      for (int j = jb + tid; j < je; j += nthreads) brick_slow_atom<POT>(a, o, j, e_thr, coincident);
+      continue;
+    }
+    // brick-local atom prefix over the box's own cells (x fastest)
+    const float inv_bw0 = 1.0f / (float)bw[0], inv_bw1 = 1.0f / (float)bw[1];
+    auto center_of = [&](int c) {
+      const int cyz = (int)(((float)c + 0.5f) * inv_bw0);
+      const int lz = (int)(((float)cyz + 0.5f) * inv_bw1);
+      const int lx = c - cyz * bw[0], ly = cyz - lz * bw[1];
+      return ((lz + bp.ns[2]) * hd[1] + (ly + bp.ns[1])) * hd[0] + lx + bp.ns[0];
+    };
+    if (wid == 0) {
+      int cnt[2], sum = 0;
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        const int c = lane * 2 + t;
+        cnt[t] = 0;
+        if (c < nbc) {
+          const int hc = center_of(c);
+          cnt[t] = (int)hstart[hc + 1] - (int)hstart[hc];
+        }
+        sum += cnt[t];
+      }
+      int incl = sum;
+#pragma unroll
+      for (int off = 1; off < 32; off <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, off);
+        if (lane >= off) incl += t;
+      }
+      int run = incl - sum;
+      if (lane == 0) bc_astart[0] = 0;
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        const int c = lane * 2 + t;
+        run += cnt[t];
+        if (c < nbc) bc_astart[c + 1] = (unsigned short)run;
+      }
+    }
+    // brick origin for the FP32 offsets (any nearby point serves; it only has to be common)
+    double org[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      const double fr = ((double)c0[d] + 0.5 * (double)bw[d]) / (double)g.nc[d];  // box centre
+      if (a.box.periodic[d]) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) org[k] += fr * a.box.H[3 * d + k];
+      } else {
+        org[d] += a.box.lo[d] + a.box.ext[d] * fr;
+      }
+    }
+    // ---- stage the halo: a thread copies whole halo cells ----------------------------------------------
+    for (int h = tid; h < nh; h += nthreads) {
+      const int sb = hstart[h], se = hstart[h + 1], jb = hgstart[h] - sb;
+      const int code = hcode[h];
+      const double svx = svtab[code][0] - org[0], svy = svtab[code][1] - org[1], svz = svtab[code][2] - org[2];
+      for (int s = sb; s < se; ++s) {
+        const double4 p = a.spos[jb + s];
+        c64[3 * s] = p.x;
+        c64[3 * s + 1] = p.y;
+        c64[3 * s + 2] = p.z;
+        if (kForce) c64w[s] = o.dfd_sorted[jb + s];
+        const float fx = (float)(p.x + svx), fy = (float)(p.y + svy), fz = (float)(p.z + svz);
+        c32[s] = make_float4(fx, fy, fz, fmaf(fx, fx, fmaf(fy, fy, fz * fz)));
+        cinfo[s] = (unsigned short)(code | (meta_species((unsigned long long)__double_as_longlong(p.w)) << 8));
+      }
+    }
+    __syncthreads();
+    const int natoms = bc_astart[nbc];
+    if (natoms == 0) continue;
+
+    const double rc2 = kPairGeo ? a.lj.rc2 : a.rc2;
+    const double rc2_phys = kPairGeo ? 0.0 : c_eam.rc2_phys;
+    const int apb = nthreads / TPA;  // atoms per pass
+    const int nrx = 2 * bp.ns[0] + 1, nry = 2 * bp.ns[1] + 1, nrows = nry * (2 * bp.ns[2] + 1);
+    // private survivor list of this thread: entry k at shared byte address lsa0 + k * lstride
+    const unsigned lsa0 = (unsigned)__cvta_generic_to_shared(lists + tid), lstride = 2u * (unsigned)nthreads;
+    const unsigned lsa_end = lsa0 + (unsigned)bp.cap_list * lstride;
+    const float inv_lstride = 1.0f / (float)lstride;
+    // SHIFTED: some halo cell of this box is a periodic image (only bricks at the box faces);
+    // elsewhere (p_j - p_i) + 0 is p_j - p_i and the image-vector lookup is skipped
+    auto evaluate = [&](auto shifted_tag) {
+      constexpr bool SHIFTED = decltype(shifted_tag)::value;
+      constexpr bool kNeedInfo = SHIFTED || POT != TILE_LJ;
+      for (int a0 = 0; a0 < natoms; a0 += apb) {
+        const int ai = a0 + tid / TPA;
+        const int sub = tid % TPA;
+        double acc[3] = {0.0, 0.0, 0.0};
+        int si = 0, gi = 0;
+        const bool active = ai < natoms;
+        if (active) {
+          int c = 0;
+#pragma unroll
+          for (int step = 32; step > 0; step >>= 1)
+            if (c + step < nbc && bc_astart[c + step] <= ai) c += step;
+          const int hc = center_of(c), il = ai - bc_astart[c];
+          si = hstart[hc] + il;
+          gi = hgstart[hc] + il;
+          // |c - f|^2 = |c|^2 + (|f|^2 - 2 c.f): three FFMA and one add per candidate
+          const float4 fi = c32[si];
+          const float m2x = -2.0f * fi.x, m2y = -2.0f * fi.y, m2z = -2.0f * fi.z;
+          const float thr = bp.thr2f - fi.w;
+          const double pix = c64[3 * si], piy = c64[3 * si + 1], piz = c64[3 * si + 2];
+          const int zi = cinfo[si] >> 8;
+          double dfd_i = 0.0;
+          if (kForce) dfd_i = c64w[si];
+          const int hlow = hc - (bp.ns[2] * hd[1] + bp.ns[1]) * hd[0] - bp.ns[0];  // stencil corner
+          int ry = sub % nry, rz = sub / nry, row = sub;
+          int s = 0, s1 = 0;  // cursor in the current stencil row
+          bool more = true;
+          // rounds of search-then-physics: one round unless the private list fills up first
+          do {
+            // ---- search: this thread's rows of the atom's stencil, FP32 ----------------------------------
+            unsigned lsa = lsa0;
+            for (;;) {
+              if (s == s1) {  // next row: 2 ns + 1 cells that are contiguous in the staged order
+                if (row >= nrows) {
+                  more = false;
+                  break;
+                }
+                const int h0 = hlow + (rz * hd[1] + ry) * hd[0];
+                s = hstart[h0];
+                s1 = hstart[h0 + nrx];
+                row += TPA;
+                ry += TPA;
+                while (ry >= nry) {
+                  ry -= nry;
+                  ++rz;
+                }
+                if (s == s1) continue;
+              }
+              const int room = bp.cap_list - (int)(((float)(lsa - lsa0) + 0.5f) * inv_lstride);
+              const int se = min(s1, s + room);
+              if (se == s) break;  // list full: evaluate it, then come back
+#pragma unroll 4
+              for (; s < se; ++s) {
+                const float4 f = c32[s];
+                const float t = fmaf(f.x, m2x, fmaf(f.y, m2y, fmaf(f.z, m2z, f.w)));
+                asm volatile("st.shared.u16 [%0], %1;" ::"r"(lsa), "h"((unsigned short)s));  // kept only if it passes
+                lsa += t <= thr ? lstride : 0u;
+              }
+              if (s < s1) break;  // the row continues after the list has been evaluated
+            }
+            // ---- physics: exact FP64 test and pair terms for the listed candidates ------------------------
+            for (unsigned la = lsa0; la < lsa; la += lstride) {
+              unsigned short s16;
+              asm volatile("ld.shared.u16 %0, [%1];" : "=h"(s16) : "r"(la));
+              const int sj = s16;
+              int info = 0;
+              if (kNeedInfo) info = cinfo[sj];
+              const double* pj = c64 + 3 * sj;
+              double dx = xsub(pj[0], pix), dy = xsub(pj[1], piy), dz = xsub(pj[2], piz);
+              if (SHIFTED) {
+                const int code = info & 127;
+                dx = xadd(dx, svtab[code][0]);
+                dy = xadd(dy, svtab[code][1]);
+                dz = xadd(dz, svtab[code][2]);
+              }
+              const double d2 = xnorm2(dx, dy, dz);
+              if (POT == TILE_LJ) {
+                if (d2 <= rc2 && sj != si) {  // vesin_visit.hpp:104
+                  const double invR2 = rcp_fast(d2);
+                  const double sr2 = a.lj.psi2 * invR2;
+                  const double a6 = sr2 * sr2 * sr2;
+                  const double bb = 4.0 * a.lj.u0 * a6;
+                  e_thr += 0.5 * (bb * (a6 - 1.0) - a.lj.shiftU);
+                  const double fs = 6.0 * bb * invR2 * (2.0 * a6 - 1.0);
+                  acc[0] = fma(-fs, dx, acc[0]);
+                  acc[1] = fma(-fs, dy, acc[1]);
+                  acc[2] = fma(-fs, dz, acc[2]);
+                }
+              } else if (POT == TILE_PAIR) {
+                if (d2 <= rc2 && sj != si) {
+                  double u, fs;
+                  pair_eval(a.lj, d2, zi, info >> 8, u, fs);
+                  e_thr += 0.5 * u;
+                  acc[0] = fma(-fs, dx, acc[0]);
+                  acc[1] = fma(-fs, dy, acc[1]);
+                  acc[2] = fma(-fs, dz, acc[2]);
+                }
+              } else if (d2 < rc2 && sj != si) {  // vesin :1202; the atom itself is no neighbour
+                const int zj = info >> 8;
+                if (POT == TILE_EAM_DENSITY) {
+                  if (d2 == 0.0) coincident = true;
+                  if (d2 < rc2_phys) acc[0] += eam_density_entry(zj, d2);
+                } else if (d2 < rc2_phys) {
+                  eam_force_entry(zi, zj, dfd_i, c64w[sj], dx, dy, dz, d2, e_thr, acc[0], acc[1], acc[2]);
+                }
+              }
+            }
+          } while (more);
+        }
+        __syncwarp();
+        // the TPA threads of an atom fold their partial sums in a fixed tree
+#pragma unroll
+        for (int off = 1; off < TPA; off <<= 1) {
+#pragma unroll
+          for (int k = 0; k < NV; ++k) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], off);
+        }
+        if (active && sub == 0) {
+          if (POT == TILE_EAM_DENSITY) {
+            double emb, demb;
+            eam_embed(cinfo[si] >> 8, acc[0], emb, demb);
+            o.dfd_sorted[gi] = demb;
+            o.eemb_sorted[gi] = emb;
+          } else {
+            const int orig = meta_orig((unsigned long long)__double_as_longlong(a.spos[gi].w));
+            o.F[3 * (size_t)orig] = acc[0];
+            o.F[3 * (size_t)orig + 1] = acc[1];
+            o.F[3 * (size_t)orig + 2] = acc[2];
+            if (POT == TILE_EAM_FORCE) e_thr += o.eemb_sorted[gi];
+          }
+        }
+      }
+    };
+    if (s_shifted)
+      evaluate(BoolTag<true>{});
+    else
+      evaluate(BoolTag<false>{});
+  }
+
+  if (POT == TILE_EAM_DENSITY) {
+    if (coincident) atomicOr(&o.st->flags, kFlagCoincident);
+  } else {
+    // one energy partial per warp (fixed shuffle tree); the warps retire independently
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) e_thr += __shfl_down_sync(0xffffffffu, e_thr, off);
+    if (lane == 0) o.partials[blockIdx.x * (kBrickMaxThreads / 32) + wid] = e_thr;
+  }
+}
+
+}  // namespace rb

@@ -30,7 +30,7 @@ struct Status {
   unsigned flags;
   int first_bad_atom;  // smallest original index that raised NonFinite / ForeignZ (else INT_MAX)
   int bad_value;       // its atomic number (ForeignZ)
-  int pad;
+  int slow_atoms;      // diagnostics: atoms a brick kernel evaluated on its slow path
 };
 
 // Geometry of one periodic (or free) cell, prepared on the host with the reference's own

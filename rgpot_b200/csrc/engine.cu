@@ -22,7 +22,7 @@
 #include "gather.cuh"
 #include "physics.cuh"
 #include "small.cuh"
-#include "tile.cuh"
+#include "brick.cuh"
 
 using namespace rb;
 
@@ -156,13 +156,23 @@ struct RgpotB200Pot {
   cudaEvent_t ev_ready = nullptr;
   int sm_count = 0;
   size_t smem_optin = 0;
+  size_t smem_per_sm = 0;
   double lj_shiftU = 0.0;
   double morse_ecut = 0.0;  // MorsePot.hpp:56-61
   std::vector<int> zbl_species;  // sorted unique atomic numbers of the cached table (ZBLPot.cc:150-166)
   DevBuf zbl_table;
   double lj_rc = 0.0;  // effective cutoff (cluster: <= 0 -> 1e6)
   int forced_path = 0;
+  // tuning overrides of the brick kernels (0 = automatic), rgpot_b200_set_option
+  int opt_brick[3] = {0, 0, 0};
+  int opt_tpa = 0;
+  int opt_threads = 0;
+  int opt_list = 0;
+  int opt_slack = 0;  // percent of extra staged capacity over the mean halo population (0 = automatic)
+  int opt_fine = 0;          // 1: never use half-cutoff cells
+  long opt_fine_min = 20000;  // atoms from which half-cutoff cells are used
   long launches = 0;
+  long slow_atoms = 0;  // diagnostics of the last single-system call (brick slow path)
   std::string last_error;
 
   // single-system scratch
@@ -271,12 +281,14 @@ struct Plan {
 // margin that keeps cell adjacency strictly conservative against rounding in the binning
 constexpr double kCellMargin = 1.0 + 1.0e-6;
 
-void finish_grid(Plan& pl, double rc, long n, bool images) {
+// fine = 1: cells of at least the cutoff (27-cell stencil); fine = 2: half-cutoff cells (125-cell
+// stencil, 42 % fewer candidates per atom) for the brick kernels of large systems
+void finish_grid(Plan& pl, double rc, long n, bool images, int fine) {
   const double rcm = rc * kCellMargin;
   double ncd[3];
   for (int k = 0; k < 3; ++k) {
     const double width = pl.box.periodic[k] ? pl.box.face[k] : pl.box.ext[k];
-    double c = floor(width / rcm);
+    double c = floor((double)fine * width / rcm);
     if (!(c >= 1.0)) c = 1.0;
     if (c > 1024.0) c = 1024.0;
     ncd[k] = c;
@@ -302,12 +314,13 @@ void finish_grid(Plan& pl, double rc, long n, bool images) {
       int ns = (int)ceil(rcm * (double)nc / width);
       if (ns < 1) ns = 1;
       pl.grid.ns_lo[k] = pl.grid.ns_hi[k] = ns;
-    } else if (pl.box.periodic[k]) {
+    } else if (pl.box.periodic[k] && fine == 1) {
       // nearest-image LJ: every DISTINCT neighbouring cell once
       pl.grid.ns_lo[k] = nc >= 3 ? 1 : 0;
       pl.grid.ns_hi[k] = nc >= 2 ? 1 : 0;
     } else {
-      pl.grid.ns_lo[k] = pl.grid.ns_hi[k] = 1;
+      // fine periodic grids are only kept by the caller when nc >= 2 * fine + 1 (distinct cells)
+      pl.grid.ns_lo[k] = pl.grid.ns_hi[k] = fine;
     }
   }
   pl.grid.ncells = pl.grid.nc[0] * pl.grid.nc[1] * pl.grid.nc[2];
@@ -337,6 +350,133 @@ int check_launch(RgpotB200Pot* pot, const char* what) {
     int _s = check_launch(pot, what);           \
     if (_s) return _s;                          \
   } while (0)
+
+// ---- brick kernels (brick.cuh): plan and launch ------------------------------------------------
+inline int round_up(int v, int m) { return ((v + m - 1) / m) * m; }
+
+// FP32 prefilter threshold: a superset of the exact accept test.  A = bound on the staged FP32
+// offsets (brick halo relative to the brick origin), so rounding the two positions and their
+// difference moves a component by at most delta, and d2 by at most the last factor.
+float brick_threshold(const Plan& pl, const int bd[3], const int ns[3], double rc) {
+  // staged FP32 offsets are relative to the brick centre: |component| <= A
+  double A = 0.0;
+  for (int k = 0; k < 3; ++k) {
+    double ext = 0.0;
+    for (int d = 0; d < 3; ++d) {
+      const double comp = pl.box.periodic[d] ? fabs(pl.box.H[3 * d + k]) : (d == k ? pl.box.ext[d] : 0.0);
+      ext += (0.5 * bd[d] + ns[d] + 0.01) * comp / pl.grid.nc[d];
+    }
+    A = std::max(A, ext);
+  }
+  // The search evaluates |c|^2 + (|f|^2 - 2 c.f) in FP32.  With u = 2^-24: rounding the two offsets
+  // moves a component by <= 2 A u (delta), and every one of the ~10 FP32 operations rounds a partial
+  // result of magnitude <= 4 * 3 A^2, so the computed value exceeds the exact d2 of an accepted
+  // pair by at most the bound below (doubled for safety).
+  const double u = ldexp(1.0, -24);
+  const double delta = 2.0 * A * u * 1.001;
+  const double err = 2.0 * sqrt(3.0) * rc * delta + 3.0 * delta * delta + 10.0 * u * 12.0 * A * A;
+  const double t = (rc * rc + 2.0 * err) * (1.0 + 1.0e-6);
+  float f = (float)t;
+  if ((double)f < t) f = nextafterf(f, INFINITY);
+  return nextafterf(f, INFINITY);
+}
+
+bool plan_bricks(const RgpotB200Pot* pot, const Plan& pl, long n, double rc, bool eam, BrickPlan& bp) {
+  const Grid& g = pl.grid;
+  int ns[3];
+  for (int k = 0; k < 3; ++k) {
+    if (g.ns_lo[k] != g.ns_hi[k] || g.ns_lo[k] < 1 || g.ns_lo[k] > 2) return false;
+    ns[k] = g.ns_lo[k];
+  }
+  const double mean = (double)n / (double)g.ncells;
+  // expected neighbours per atom from the mean number density (cells tile the occupied volume)
+  double cellvol = 1.0;
+  {
+    double cv[3][3];
+    for (int d = 0; d < 3; ++d)
+      for (int k = 0; k < 3; ++k)
+        cv[d][k] = (pl.box.periodic[d] ? pl.box.H[3 * d + k] : (d == k ? pl.box.ext[d] : 0.0)) / g.nc[d];
+    cellvol = fabs(cv[0][0] * (cv[1][1] * cv[2][2] - cv[1][2] * cv[2][1]) -
+                   cv[0][1] * (cv[1][0] * cv[2][2] - cv[1][2] * cv[2][0]) +
+                   cv[0][2] * (cv[1][0] * cv[2][1] - cv[1][1] * cv[2][0]));
+  }
+  const double nnb = mean / cellvol * (4.0 / 3.0) * M_PI * rc * rc * rc + 1.0;
+  int tpa = pot->opt_tpa ? pot->opt_tpa : 2;
+  if (tpa != 1 && tpa != 2 && tpa != 4) tpa = 2;
+  const double slots = (double)kBrickMaxThreads / tpa;
+  int bd[3] = {1, 1, 1};
+  if (pot->opt_brick[0] > 0) {
+    for (int k = 0; k < 3; ++k) bd[k] = std::max(1, std::min({pot->opt_brick[k], g.nc[k], 4}));
+  } else {
+    // grow the brick (x, y, z in turn, up to 4 cells) while its mean population fills < 90 % of
+    // the atom slots of a block
+    double pop = mean;
+    for (int round = 0; round < 3; ++round) {
+      for (int k = 0; k < 3; ++k) {
+        const int next = bd[k] == 1 ? 2 : (bd[k] == 2 ? 4 : 0);
+        if (next && g.nc[k] >= next && pop * next / bd[k] <= 0.9 * slots) {
+          pop *= (double)next / bd[k];
+          bd[k] = next;
+        }
+      }
+    }
+  }
+  for (;;) {
+    const int ncell = bd[0] * bd[1] * bd[2];
+    const int nhalo = (bd[0] + 2 * ns[0]) * (bd[1] + 2 * ns[1]) * (bd[2] + 2 * ns[2]);
+    if (ncell <= kBrickMaxCells && nhalo <= kBrickMaxHalo) {
+      const double pop = mean * ncell;
+      int threads = pot->opt_threads ? pot->opt_threads : round_up((int)ceil(pop * 1.15 * tpa), 32);
+      threads = std::max(64, std::min(kBrickMaxThreads, round_up(threads, 32)));
+      // capacities: generous first; tightened when that buys a third resident block per SM (an
+      // oversized brick or list is still evaluated correctly, on the block's slow path)
+      const unsigned per_block3 = (unsigned)(pot->smem_per_sm / 3) - 1024u - 8192u;
+      for (int tight = 0; tight < 2; ++tight) {
+        const double fc = tight ? 1.15 : 1.3, fl = tight ? 1.0 : 1.4;
+        const double fcc = pot->opt_slack ? 1.0 + 0.01 * pot->opt_slack : fc;
+        bp.cap_cand = std::min(65504, round_up((int)(nhalo * mean * fcc) + 32, 32));
+        bp.cap_list = pot->opt_list ? pot->opt_list : std::max(24, (int)(nnb / tpa * fl) + 14);
+        bp.smem = brick_smem_bytes(bp.cap_cand, bp.cap_list, threads, eam);
+        if (bp.smem <= per_block3) break;
+      }
+      if ((size_t)bp.smem + 10240 <= pot->smem_optin) {
+        for (int k = 0; k < 3; ++k) {
+          bp.bd[k] = bd[k];
+          bp.ns[k] = ns[k];
+          bp.nb[k] = (g.nc[k] + bd[k] - 1) / bd[k];
+        }
+        bp.nbricks = bp.nb[0] * bp.nb[1] * bp.nb[2];
+        bp.tpa = tpa;
+        bp.threads = threads;
+        bp.thr2f = brick_threshold(pl, bd, ns, rc);
+        return true;
+      }
+    }
+    // too large for shared memory: shrink the brick, largest direction first
+    int kmax = 2;
+    for (int k = 1; k >= 0; --k)
+      if (bd[k] > bd[kmax]) kmax = k;
+    if (bd[kmax] == 1) return false;
+    bd[kmax] = bd[kmax] == 4 ? 2 : 1;
+  }
+}
+
+template <int POT>
+int launch_brick(RgpotB200Pot* pot, const GatherArgs& ga, const BrickPlan& bp, const TileOut& to,
+                 cudaStream_t st, const char* what) {
+  const unsigned smem = brick_smem_bytes(bp.cap_cand, bp.cap_list, bp.threads, POT == TILE_EAM_FORCE);
+  auto go = [&](auto kern) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    kern<<<bp.nbricks, bp.threads, smem, st>>>(ga, bp, to);
+  };
+  if (bp.tpa == 1)
+    go(k_brick<POT, 1>);
+  else if (bp.tpa == 4)
+    go(k_brick<POT, 4>);
+  else
+    go(k_brick<POT, 2>);
+  return check_launch(pot, what);
+}
 
 // Cell-list path for ONE system whose positions / Z already sit on the device.
 // Leaves forces in d_F (original order), energy in d_E[0], flags in pot->status.
@@ -423,13 +563,26 @@ int run_cell_path(RgpotB200Pot* pot, long n, const double* d_pos, const int* d_Z
   pl.lj.m_ecut = pot->morse_ecut;
   pl.lj.m_two_de_a = 2.0 * pot->cfg.morse_De * pot->cfg.morse_a;
   pl.rc2 = rc * rc;
-  finish_grid(pl, rc, n, images);
+  // half-cutoff cells for systems large enough to fill the machine with bricks
+  int fine = (allow_tile && !emit && n >= pot->opt_fine_min && pot->opt_fine != 1) ? 2 : 1;
+  for (;;) {
+    finish_grid(pl, rc, n, images, fine);
+    bool ok = true;
+    if (fine == 2) {
+      for (int k = 0; k < 3; ++k) {
+        if (!images && pl.box.periodic[k] && pl.grid.nc[k] < 5) ok = false;
+        if (pl.grid.ns_lo[k] > 2 || pl.grid.ns_hi[k] > 2) ok = false;
+      }
+    }
+    if (ok) break;
+    fine = 1;
+  }
   if (images) {
     pl.geo = GEO_IMAGES;
   } else {
     bool shift_ok = true;
     for (int k = 0; k < 3; ++k)
-      if (pl.box.periodic[k] && pl.grid.nc[k] < 3) shift_ok = false;
+      if (pl.box.periodic[k] && pl.grid.nc[k] < 2 * fine + 1) shift_ok = false;
     pl.geo = shift_ok ? GEO_LJ_SHIFT : GEO_LJ_FOLD;
   }
 
@@ -501,62 +654,49 @@ int run_cell_path(RgpotB200Pot* pot, long n, const double* d_pos, const int* d_Z
   }
 
   double* d_part = pot->partials.as<double>();
+  int npart_used = nblk;
   if (eam) {
-    const bool tile_ok = allow_tile && pl.grid.ns_lo[0] == 1 && pl.grid.ns_lo[1] == 1 &&
-                         pl.grid.ns_lo[2] == 1 && pl.grid.ns_hi[0] == 1 && pl.grid.ns_hi[1] == 1 &&
-                         pl.grid.ns_hi[2] == 1;
+    BrickPlan bp{};
+    const bool tile_ok = allow_tile && plan_bricks(pot, pl, n, rc, true, bp);
     if (tile_ok) {
-      // warp-per-cell tile kernels; the gather kernels cover atoms outside the cell (per-pair
-      // image shifts) -- each side returns at once when the binning flag is not its own
-      CU_TRY(pot, cudaMemsetAsync(d_part, 0, sizeof(double) * npart, st));
-      double edge = 0.0;
-      for (int k = 0; k < 3; ++k) {
-        // longest cell edge vector bounds the FP32 offsets
-        const double len = sqrt(pl.box.H[3 * k] * pl.box.H[3 * k] + pl.box.H[3 * k + 1] * pl.box.H[3 * k + 1] +
-                                pl.box.H[3 * k + 2] * pl.box.H[3 * k + 2]);
-        edge = std::max(edge, len / pl.grid.nc[k]);
-      }
-      const double margin = 1.0e-6 * 6.0 * edge + 1.0e-5 * rc;
-      const float thr2f = (float)((rc + margin) * (rc + margin) * (1.0 + 1.0e-6));
-      const int tb = div_up(ncells, kTileWarps);
+      // brick kernels; the gather kernels cover atoms outside the cell (per-pair image shifts) --
+      // each side returns at once when the binning flag is not its own
+      npart_used = std::max(nblk, bp.nbricks * (kBrickMaxThreads / 32));
+      CU_TRY(pot, pot->partials.reserve(sizeof(double) * npart_used));
+      d_part = pot->partials.as<double>();
+      CU_TRY(pot, cudaMemsetAsync(d_part, 0, sizeof(double) * npart_used, st));
       TileOut to{d_F, d_part, pot->dfd.as<double>(), pot->eemb.as<double>(), d_st};
-      k_tile<TILE_EAM_DENSITY><<<tb, kTileWarps * 32, 0, st>>>(ga, thr2f, to);
-      LAUNCH_CHECK(pot, "k_tile<eam density>");
-      k_tile<TILE_EAM_FORCE><<<tb, kTileWarps * 32, 0, st>>>(ga, thr2f, to);
-      LAUNCH_CHECK(pot, "k_tile<eam force>");
+      int ls = launch_brick<TILE_EAM_DENSITY>(pot, ga, bp, to, st, "k_brick<eam density>");
+      if (ls) return ls;
+      ls = launch_brick<TILE_EAM_FORCE>(pot, ga, bp, to, st, "k_brick<eam force>");
+      if (ls) return ls;
       ga.only_if_atom_shift = 1;
     }
     k_eam_density<<<nblk, 128, 0, st>>>(ga, pot->dfd.as<double>(), pot->eemb.as<double>(), d_st);
     LAUNCH_CHECK(pot, "k_eam_density");
     k_eam_force<<<nblk, 128, 0, st>>>(ga, pot->dfd.as<double>(), pot->eemb.as<double>(), d_F, d_part);
     LAUNCH_CHECK(pot, "k_eam_force");
-    k_reduce_partials<<<1, 1024, 0, st>>>(d_part, tile_ok ? npart : nblk, d_E);
+    k_reduce_partials<<<1, 1024, 0, st>>>(d_part, tile_ok ? npart_used : nblk, d_E);
     LAUNCH_CHECK(pot, "k_reduce_partials");
     return 0;
   } else if (pl.geo == GEO_IMAGES) {
     k_lj_gather<GEO_IMAGES><<<nblk, 128, 0, st>>>(ga, d_F, d_part);
     LAUNCH_CHECK(pot, "k_lj_gather<images>");
-  } else if (pl.geo == GEO_LJ_SHIFT && allow_tile) {
-    // warp-per-cell tile kernel; the literal-fold gather kernel covers the (rare) case of atoms
-    // outside the cell -- each of the two returns at once when the binning flag is not its own
-    CU_TRY(pot, cudaMemsetAsync(d_part, 0, sizeof(double) * npart, st));
-    double edge = 0.0;
-    for (int k = 0; k < 3; ++k) {
-      const double width = pl.box.periodic[k] ? pl.box.face[k] : pl.box.ext[k];
-      edge = std::max(edge, width / pl.grid.nc[k]);
-    }
-    const double margin = 1.0e-6 * 4.0 * edge + 1.0e-5 * rc;
-    const float thr2f = (float)((rc + margin) * (rc + margin) * (1.0 + 1.0e-6));
+  } else if (BrickPlan bp{}; pl.geo == GEO_LJ_SHIFT && allow_tile && plan_bricks(pot, pl, n, rc, false, bp)) {
+    // brick kernel; the literal-fold gather kernel covers the (rare) case of atoms outside the
+    // cell -- each of the two returns at once when the binning flag is not its own
+    npart_used = std::max(nblk, bp.nbricks * (kBrickMaxThreads / 32));
+    CU_TRY(pot, pot->partials.reserve(sizeof(double) * npart_used));
+    d_part = pot->partials.as<double>();
+    CU_TRY(pot, cudaMemsetAsync(d_part, 0, sizeof(double) * npart_used, st));
     TileOut to{d_F, d_part, nullptr, nullptr, d_st};
-    if (pl.lj.morse)
-      k_tile<TILE_PAIR><<<div_up(ncells, kTileWarps), kTileWarps * 32, 0, st>>>(ga, thr2f, to);
-    else
-      k_tile<TILE_LJ><<<div_up(ncells, kTileWarps), kTileWarps * 32, 0, st>>>(ga, thr2f, to);
-    LAUNCH_CHECK(pot, "k_tile<lj>");
+    int ls = pl.lj.morse ? launch_brick<TILE_PAIR>(pot, ga, bp, to, st, "k_brick<pair>")
+                         : launch_brick<TILE_LJ>(pot, ga, bp, to, st, "k_brick<lj>");
+    if (ls) return ls;
     ga.only_if_atom_shift = 1;
     k_lj_gather<GEO_LJ_SHIFT><<<nblk, 128, 0, st>>>(ga, d_F, d_part);
     LAUNCH_CHECK(pot, "k_lj_gather<shift>");
-    k_reduce_partials<<<1, 1024, 0, st>>>(d_part, npart, d_E);
+    k_reduce_partials<<<1, 1024, 0, st>>>(d_part, npart_used, d_E);
     LAUNCH_CHECK(pot, "k_reduce_partials");
     return 0;
   } else if (pl.geo == GEO_LJ_SHIFT) {
@@ -879,6 +1019,7 @@ RgpotB200Pot* rgpot_b200_create(const RgpotB200Config* cfg, char* errbuf, size_t
   pot->device = dev;
   pot->sm_count = prop.multiProcessorCount;
   pot->smem_optin = prop.sharedMemPerBlockOptin;
+  pot->smem_per_sm = prop.sharedMemPerMultiprocessor;
   bool ok = cudaStreamCreateWithFlags(&pot->stream, cudaStreamNonBlocking) == cudaSuccess;
   for (auto& s : pot->pipe) ok = ok && cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) == cudaSuccess;
   ok = ok && cudaEventCreateWithFlags(&pot->ev_ready, cudaEventDisableTiming) == cudaSuccess;
@@ -910,10 +1051,47 @@ int rgpot_b200_last_error(RgpotB200Pot* pot, char* buffer, int buffer_len) {
 
 long rgpot_b200_launch_count(RgpotB200Pot* pot) { return pot ? pot->launches : 0; }
 
+long rgpot_b200_stat(RgpotB200Pot* pot, const char* key) {
+  if (!pot || !key) return -1;
+  if (strcmp(key, "launches") == 0) return pot->launches;
+  if (strcmp(key, "slow_atoms") == 0) return pot->slow_atoms;
+  return -1;
+}
+
 int rgpot_b200_set_option(RgpotB200Pot* pot, const char* key, long value) {
   if (!pot || !key) return kStatusArgs;
   if (strcmp(key, "path") == 0) {
     pot->forced_path = (int)value;
+    return 0;
+  }
+  if (strcmp(key, "brick") == 0) {  // decimal xyz, e.g. 221; 0 = automatic
+    pot->opt_brick[0] = (int)(value / 100) % 10;
+    pot->opt_brick[1] = (int)(value / 10) % 10;
+    pot->opt_brick[2] = (int)value % 10;
+    return 0;
+  }
+  if (strcmp(key, "brick_tpa") == 0) {
+    pot->opt_tpa = (int)value;
+    return 0;
+  }
+  if (strcmp(key, "brick_list") == 0) {
+    pot->opt_list = (int)value;
+    return 0;
+  }
+  if (strcmp(key, "brick_slack") == 0) {
+    pot->opt_slack = (int)value;
+    return 0;
+  }
+  if (strcmp(key, "fine") == 0) {
+    pot->opt_fine = (int)value;
+    return 0;
+  }
+  if (strcmp(key, "fine_min") == 0) {
+    pot->opt_fine_min = value;
+    return 0;
+  }
+  if (strcmp(key, "brick_threads") == 0) {
+    pot->opt_threads = (int)value;
     return 0;
   }
   return kStatusArgs;
@@ -1028,6 +1206,7 @@ static int finish_single(RgpotB200Pot* pot, long n, const double* d_pos, const i
       CU_TRY(pot, cudaStreamSynchronize(st));
     }
     flags = stt.flags;
+    pot->slow_atoms = stt.slow_atoms;
     bad = stt.first_bad_atom;
     if ((flags & kFlagForeignZ) && bad != INT_MAX) {
       if (host_Z) {

@@ -208,8 +208,18 @@ class _EnginePot:
         """0 automatic, 1 cell-list kernels, 2 all-pairs kernels (test hook)."""
         self._lib.rgpot_b200_set_option(self._h, b"path", int(path))
 
+    def set_option(self, key: str, value: int) -> None:
+        """Tuning / test hooks of the engine (rgpot_b200_set_option): "path", "brick" (cells per
+        brick as decimal xyz, 0 = automatic), "brick_tpa", "brick_threads"."""
+        if self._lib.rgpot_b200_set_option(self._h, key.encode(), int(value)) != 0:
+            raise ValueError(f"unknown engine option {key!r}")
+
     def launch_count(self) -> int:
         return int(self._lib.rgpot_b200_launch_count(self._h))
+
+    def stat(self, key: str) -> int:
+        """Engine diagnostics (rgpot_b200_stat): "launches", "slow_atoms"."""
+        return int(self._lib.rgpot_b200_stat(self._h, key.encode()))
 
     def __call__(self, positions, atom_types, box, out=None):
         """(energy, forces, variance).  `out`, if given, is a C-contiguous float64 (n, 3) array that

@@ -16,6 +16,9 @@ import sys
 import tempfile
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BYSTALL = "--by-stall" in sys.argv  # sort by stall samples instead of instructions
+if BYSTALL:
+    sys.argv.remove("--by-stall")
 OUTER = "--outer" in sys.argv  # attribute inlined code to the kernel-level line that called it
 if OUTER:
     sys.argv.remove("--outer")
@@ -78,7 +81,7 @@ def main():
             tot[k] += v
     print(f"total warp-instr {tot[0]:.3e}  thread-instr {tot[1]:.3e}  samples {tot[2]}")
     src_cache = {}
-    for loc, (n, t, s) in sorted(per.items(), key=lambda kv: -kv[1][0])[:top]:
+    for loc, (n, t, s) in sorted(per.items(), key=lambda kv: -kv[1][2 if BYSTALL else 0])[:top]:
         fname, ln = loc
         text = ""
         path = os.path.join(ROOT, "rgpot_b200", "csrc", fname)
