@@ -298,11 +298,11 @@ def run_single_system(args, name, local):
     if name == "lj_fluid_1m":
         pos, Z, box = workloads.lj_fluid(args.lj_atoms)
         pot = rgpot_b200.LJPot(rgpot_b200.LJConfig(1.0, 2.5, 1.0), device=local)
-        kernel = "k_lj_gather"
+        kernel = "k_brick<LJ>"
     else:
         pos, Z, box = workloads.cu_slab_triclinic(cells=args.slab_cells)
         pot = rgpot_b200.CuH2Pot(device=local)
-        kernel = "k_eam_force"
+        kernel = "k_brick<EAM_DENSITY> + k_brick<EAM_FORCE>"
     n = len(pos)
     dev = torch.device("cuda", local)
     d_pos = torch.from_numpy(pos).to(dev)

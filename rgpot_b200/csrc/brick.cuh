@@ -131,7 +131,6 @@ k_brick(const __grid_constant__ GatherArgs a, const __grid_constant__ BrickPlan 
   __shared__ unsigned short bc_astart[kBrickMaxCells + 2];  // brick-local atom prefix
   __shared__ int s_shifted, s_ntot;
   __shared__ int box_stack[8][6];  // boxes of cells still to do: first cell, extent
-  __shared__ int box_sp;
 
   if (a.st_in->flags & kFlagAtomShift) return;  // the gather kernels of gather.cuh take over
   constexpr bool kPairGeo = POT == TILE_LJ || POT == TILE_PAIR;  // LJ pair search (w * q image vectors)
@@ -148,16 +147,16 @@ k_brick(const __grid_constant__ GatherArgs a, const __grid_constant__ BrickPlan 
   unsigned short* lists = cinfo + bp.cap_cand;
 
   // image vectors; the brick of this block as the first box
-  if (tid < kShiftCodes) {
-    const double q0 = (double)(tid % 5 - 2), q1 = (double)((tid / 5) % 5 - 2), q2 = (double)(tid / 25 - 2);
+  for (int t = tid; t < kShiftCodes; t += nthreads) {
+    const double q0 = (double)(t % 5 - 2), q1 = (double)((t / 5) % 5 - 2), q2 = (double)(t / 25 - 2);
     if (kPairGeo) {
-      svtab[tid][0] = xmul(a.lj.w[0], q0);
-      svtab[tid][1] = xmul(a.lj.w[1], q1);
-      svtab[tid][2] = xmul(a.lj.w[2], q2);
+      svtab[t][0] = xmul(a.lj.w[0], q0);
+      svtab[t][1] = xmul(a.lj.w[1], q1);
+      svtab[t][2] = xmul(a.lj.w[2], q2);
     } else {
-      svtab[tid][0] = shift_component(a.box.H, 0, q0, q1, q2);
-      svtab[tid][1] = shift_component(a.box.H, 1, q0, q1, q2);
-      svtab[tid][2] = shift_component(a.box.H, 2, q0, q1, q2);
+      svtab[t][0] = shift_component(a.box.H, 0, q0, q1, q2);
+      svtab[t][1] = shift_component(a.box.H, 1, q0, q1, q2);
+      svtab[t][2] = shift_component(a.box.H, 2, q0, q1, q2);
     }
   }
   if (tid == 0) {
@@ -167,7 +166,6 @@ k_brick(const __grid_constant__ GatherArgs a, const __grid_constant__ BrickPlan 
       box_stack[0][k] = b[k] * bp.bd[k];
       box_stack[0][3 + k] = min(bp.bd[k], g.nc[k] - b[k] * bp.bd[k]);
     }
-    box_sp = 1;
   }
   double e_thr = 0.0;
   bool coincident = false;
@@ -175,10 +173,9 @@ k_brick(const __grid_constant__ GatherArgs a, const __grid_constant__ BrickPlan 
   // A brick whose halo exceeds the staged capacity (a locally dense region) is cut in two and the
   // halves are done one after the other; every atom sees the same candidates in the same order
   // either way, so the results do not depend on the capacities.
+  int sp = 1;
+  __syncthreads();
   for (;;) {
-    __syncthreads();
-    const int sp = box_sp;
-    if (sp == 0) break;
     int c0[3], bw[3], hd[3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
@@ -188,11 +185,7 @@ k_brick(const __grid_constant__ GatherArgs a, const __grid_constant__ BrickPlan 
     }
     const int nh = hd[0] * hd[1] * hd[2];
     const int nbc = bw[0] * bw[1] * bw[2];
-    __syncthreads();
-    if (tid == 0) {
-      box_sp = sp - 1;
-      s_shifted = 0;
-    }
+    if (tid == 0) s_shifted = 0;
     __syncthreads();
 
     // ---- halo cells ---------------------------------------------------------------------------------
@@ -254,7 +247,10 @@ k_brick(const __grid_constant__ GatherArgs a, const __grid_constant__ BrickPlan 
           hstart[h + 1] = (unsigned short)min(run, 65535);
         }
       }
-      if (lane == 31) s_ntot = incl;
+      if (lane == 31) {
+        s_ntot = incl;
+        if (sp == 1) atomicMax(&o.st->max_halo, incl);  // whole bricks only: sizes the next call
+      }
     }
     __syncthreads();
     const int ntot = s_ntot;
@@ -271,8 +267,9 @@ k_brick(const __grid_constant__ GatherArgs a, const __grid_constant__ BrickPlan 
               box_stack[sp - 1 + part][3 + k] = k == kmax ? (part == 0 ? bw[k] - half : half) : bw[k];
             }
           }
-          box_sp = sp + 1;
         }
+        sp += 1;
+        __syncthreads();
         continue;
       }
       // a single cell whose stencil does not fit: per-atom gather walk straight from global memory
@@ -281,6 +278,8 @@ k_brick(const __grid_constant__ GatherArgs a, const __grid_constant__ BrickPlan 
       const int jb = a.starts[cell], je = a.starts[cell + 1];
       if (tid == 0 && je > jb) atomicAdd(&o.st->slow_atoms, je - jb);
       for (int j = jb + tid; j < je; j += nthreads) brick_slow_atom<POT>(a, o, j, e_thr, coincident);
+      if (--sp == 0) break;
+      __syncthreads();
       continue;
     }
     // brick-local atom prefix over the box's own cells (x fastest)
@@ -348,7 +347,6 @@ k_brick(const __grid_constant__ GatherArgs a, const __grid_constant__ BrickPlan 
     }
     __syncthreads();
     const int natoms = bc_astart[nbc];
-    if (natoms == 0) continue;
 
     const double rc2 = kPairGeo ? a.lj.rc2 : a.rc2;
     const double rc2_phys = kPairGeo ? 0.0 : c_eam.rc2_phys;
@@ -494,10 +492,16 @@ k_brick(const __grid_constant__ GatherArgs a, const __grid_constant__ BrickPlan 
         }
       }
     };
-    if (s_shifted)
-      evaluate(BoolTag<true>{});
-    else
-      evaluate(BoolTag<false>{});
+    if (natoms > 0) {
+      if (s_shifted)
+        evaluate(BoolTag<true>{});
+      else
+        evaluate(BoolTag<false>{});
+    }
+    // the stack only changes when a box is cut (all threads, before any evaluation), so every
+    // thread knows whether boxes remain: the last box needs no barrier and the warps retire alone
+    if (--sp == 0) break;
+    __syncthreads();
   }
 
   if (POT == TILE_EAM_DENSITY) {

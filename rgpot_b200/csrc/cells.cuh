@@ -207,6 +207,42 @@ __global__ void k_cell_order(const int* __restrict__ starts, const int* __restri
   order_out[b + rank] = i;
 }
 
+// k_cell_order and k_gather_sorted in one pass: the atom finds its rank inside its cell and writes
+// its sorted record there directly
+__global__ void k_order_gather(const double* __restrict__ pos, const int* __restrict__ Z,
+                               const int* __restrict__ starts, const int* __restrict__ cell_of,
+                               const int* __restrict__ order_in, const int* __restrict__ ashift, int n,
+                               int check_z, double4* __restrict__ spos, int* __restrict__ scell,
+                               Status* __restrict__ st) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n) return;
+  const int i = order_in[s];
+  const int c = cell_of[i];
+  const int b = starts[c], e = starts[c + 1];
+  int rank = 0;
+  for (int t = b; t < e; ++t) rank += order_in[t] < i;
+  int species = 0;
+  if (check_z == 2) {
+    species = Z[i] & 15;  // ZBL: the host already mapped atomic numbers to type indices
+  } else if (check_z) {
+    const int z = Z[i];
+    if (z == 29) {
+      species = 0;
+    } else if (z == 1) {
+      species = 1;
+    } else {
+      atomicOr(&st->flags, kFlagForeignZ);
+      atomicMin(&st->first_bad_atom, i);
+    }
+  }
+  const int sh = ashift[i];
+  const unsigned long long meta =
+      pack_meta(i, species, (sh & 1023) - 512, ((sh >> 10) & 1023) - 512, ((sh >> 20) & 1023) - 512);
+  spos[b + rank] = make_double4(pos[3 * (size_t)i], pos[3 * (size_t)i + 1], pos[3 * (size_t)i + 2],
+                                __longlong_as_double((long long)meta));
+  scell[b + rank] = c;
+}
+
 // sorted records; species from atomic numbers (rgpot_cuh2.f90:463-489 classify) when check_z
 __global__ void k_gather_sorted(const double* __restrict__ pos, const int* __restrict__ Z,
                                 const int* __restrict__ order, const int* __restrict__ cell_of,
@@ -252,6 +288,21 @@ __global__ void k_reduce_partials(const double* __restrict__ partials, int n, do
     __syncthreads();
   }
   if (threadIdx.x == 0) out[0] = sh[0];
+}
+
+// first stage for long partial arrays: block b folds the fixed slice [b * per, (b + 1) * per)
+__global__ void k_reduce_slices(const double* __restrict__ partials, int n, int per, double* __restrict__ out) {
+  __shared__ double sh[256];
+  const int lo = blockIdx.x * per, hi = min(n, lo + per);
+  double acc = 0.0;
+  for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) acc += partials[i];
+  sh[threadIdx.x] = acc;
+  __syncthreads();
+  for (int off = blockDim.x / 2; off > 0; off >>= 1) {
+    if (threadIdx.x < off) sh[threadIdx.x] += sh[threadIdx.x + off];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[blockIdx.x] = sh[0];
 }
 
 // fixed-order block sum helper used by the force kernels (blockDim multiple of 32, <= 1024)

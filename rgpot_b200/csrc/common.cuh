@@ -31,6 +31,8 @@ struct Status {
   int first_bad_atom;  // smallest original index that raised NonFinite / ForeignZ (else INT_MAX)
   int bad_value;       // its atomic number (ForeignZ)
   int slow_atoms;      // diagnostics: atoms a brick kernel evaluated on its slow path
+  int max_halo;        // feedback: largest halo population a brick kernel met (sizes the next call)
+  int pad[3];
 };
 
 // Geometry of one periodic (or free) cell, prepared on the host with the reference's own

@@ -173,11 +173,19 @@ struct RgpotB200Pot {
   long opt_fine_min = 20000;  // atoms from which half-cutoff cells are used
   long launches = 0;
   long slow_atoms = 0;  // diagnostics of the last single-system call (brick slow path)
+  // feedback from the brick kernels: the largest halo population seen for a given (atoms, grid,
+  // brick) signature sizes the staged capacity of the next call with that signature
+  struct BrickMemo {
+    long n = -1;
+    int nc[3] = {0, 0, 0};
+    int bd[3] = {0, 0, 0};
+    int max_halo = 0;
+  } memo, memo_pending;
   std::string last_error;
 
   // single-system scratch
   DevBuf pos, Z, F, cell_of, rank, ashift, counts, starts, blocksums, order, order2, spos, scell, dfd, eemb,
-      partials, energy, status, mm, emit_pairs, emit_shifts, emit_count;
+      partials, partials2, energy, status, mm, emit_pairs, emit_shifts, emit_count;
   // batch scratch
   DevBuf b_pos, b_Z, b_F, b_off, b_boxes, b_E, b_flags, b_bad, b_map;
   HostBuf h_pos, h_Z, h_F, h_off, h_boxes, h_E, h_flags, h_bad, h_small;
@@ -202,7 +210,7 @@ struct RgpotB200Pot {
   ~RgpotB200Pot() {
     cudaSetDevice(device);
     DevBuf* d[] = {&pos, &Z, &F, &cell_of, &rank, &ashift, &counts, &starts, &blocksums, &order, &order2,
-                   &spos, &scell, &dfd, &eemb, &partials, &energy, &status, &mm, &emit_pairs,
+                   &spos, &scell, &dfd, &eemb, &partials, &partials2, &energy, &status, &mm, &emit_pairs,
                    &emit_shifts, &emit_count, &b_pos, &b_Z, &b_F, &b_off, &b_boxes, &b_E, &b_flags,
                    &b_bad, &b_map, &zbl_table};
     for (auto* b : d) b->release();
@@ -401,25 +409,16 @@ bool plan_bricks(const RgpotB200Pot* pot, const Plan& pl, long n, double rc, boo
                    cv[0][2] * (cv[1][0] * cv[2][1] - cv[1][1] * cv[2][0]));
   }
   const double nnb = mean / cellvol * (4.0 / 3.0) * M_PI * rc * rc * rc + 1.0;
-  int tpa = pot->opt_tpa ? pot->opt_tpa : 2;
+  int tpa = pot->opt_tpa ? pot->opt_tpa : (nnb > 64.0 ? 4 : 2);  // long lists: more threads per atom
   if (tpa != 1 && tpa != 2 && tpa != 4) tpa = 2;
   const double slots = (double)kBrickMaxThreads / tpa;
   int bd[3] = {1, 1, 1};
   if (pot->opt_brick[0] > 0) {
     for (int k = 0; k < 3; ++k) bd[k] = std::max(1, std::min({pot->opt_brick[k], g.nc[k], 4}));
   } else {
-    // grow the brick (x, y, z in turn, up to 4 cells) while its mean population fills < 90 % of
-    // the atom slots of a block
-    double pop = mean;
-    for (int round = 0; round < 3; ++round) {
-      for (int k = 0; k < 3; ++k) {
-        const int next = bd[k] == 1 ? 2 : (bd[k] == 2 ? 4 : 0);
-        if (next && g.nc[k] >= next && pop * next / bd[k] <= 0.9 * slots) {
-          pop *= (double)next / bd[k];
-          bd[k] = next;
-        }
-      }
-    }
+    // the largest brick (up to 4 cells a side) shared memory allows: staging and table work per
+    // atom shrink with the brick; a brick with more atoms than slots takes several passes
+    for (int k = 0; k < 3; ++k) bd[k] = g.nc[k] >= 4 ? 4 : (g.nc[k] >= 2 ? 2 : 1);
   }
   for (;;) {
     const int ncell = bd[0] * bd[1] * bd[2];
@@ -428,6 +427,7 @@ bool plan_bricks(const RgpotB200Pot* pot, const Plan& pl, long n, double rc, boo
       const double pop = mean * ncell;
       int threads = pot->opt_threads ? pot->opt_threads : round_up((int)ceil(pop * 1.15 * tpa), 32);
       threads = std::max(64, std::min(kBrickMaxThreads, round_up(threads, 32)));
+      (void)slots;
       // capacities: generous first; tightened when that buys a third resident block per SM (an
       // oversized brick or list is still evaluated correctly, on the block's slow path)
       const unsigned per_block3 = (unsigned)(pot->smem_per_sm / 3) - 1024u - 8192u;
@@ -435,6 +435,10 @@ bool plan_bricks(const RgpotB200Pot* pot, const Plan& pl, long n, double rc, boo
         const double fc = tight ? 1.15 : 1.3, fl = tight ? 1.0 : 1.4;
         const double fcc = pot->opt_slack ? 1.0 + 0.01 * pot->opt_slack : fc;
         bp.cap_cand = std::min(65504, round_up((int)(nhalo * mean * fcc) + 32, 32));
+        const auto& m = pot->memo;
+        const bool known = !pot->opt_slack && m.n == n && m.max_halo > 0 && m.nc[0] == g.nc[0] && m.nc[1] == g.nc[1] &&
+                           m.nc[2] == g.nc[2] && m.bd[0] == bd[0] && m.bd[1] == bd[1] && m.bd[2] == bd[2];
+        if (known) bp.cap_cand = std::min(65504, round_up((int)(m.max_halo * 1.04) + 24, 32));
         bp.cap_list = pot->opt_list ? pot->opt_list : std::max(24, (int)(nnb / tpa * fl) + 14);
         bp.smem = brick_smem_bytes(bp.cap_cand, bp.cap_list, threads, eam);
         if (bp.smem <= per_block3) break;
@@ -446,6 +450,15 @@ bool plan_bricks(const RgpotB200Pot* pot, const Plan& pl, long n, double rc, boo
           bp.nb[k] = (g.nc[k] + bd[k] - 1) / bd[k];
         }
         bp.nbricks = bp.nb[0] * bp.nb[1] * bp.nb[2];
+        {
+          auto& mp = const_cast<RgpotB200Pot*>(pot)->memo_pending;
+          mp.n = n;
+          for (int k = 0; k < 3; ++k) {
+            mp.nc[k] = g.nc[k];
+            mp.bd[k] = bd[k];
+          }
+          mp.max_halo = 0;
+        }
         bp.tpa = tpa;
         bp.threads = threads;
         bp.thr2f = brick_threshold(pl, bd, ns, rc);
@@ -478,6 +491,21 @@ int launch_brick(RgpotB200Pot* pot, const GatherArgs& ga, const BrickPlan& bp, c
   return check_launch(pot, what);
 }
 
+// fixed-order fold of the energy partials: long arrays in two stages
+int reduce_energy(RgpotB200Pot* pot, double* d_part, int n, double* d_E, cudaStream_t st) {
+  if (n > 4096) {
+    const int nb = 128, per = (n + nb - 1) / nb;
+    CU_TRY(pot, pot->partials2.reserve(sizeof(double) * nb));
+    k_reduce_slices<<<nb, 256, 0, st>>>(d_part, n, per, pot->partials2.as<double>());
+    LAUNCH_CHECK(pot, "k_reduce_slices");
+    k_reduce_partials<<<1, 128, 0, st>>>(pot->partials2.as<double>(), nb, d_E);
+  } else {
+    k_reduce_partials<<<1, 1024, 0, st>>>(d_part, n, d_E);
+  }
+  LAUNCH_CHECK(pot, "k_reduce_partials");
+  return 0;
+}
+
 // Cell-list path for ONE system whose positions / Z already sit on the device.
 // Leaves forces in d_F (original order), energy in d_E[0], flags in pot->status.
 int run_cell_path(RgpotB200Pot* pot, long n, const double* d_pos, const int* d_Z, double* d_F,
@@ -490,7 +518,8 @@ int run_cell_path(RgpotB200Pot* pot, long n, const double* d_pos, const int* d_Z
   const double rc = eam ? 6.1 : pot->lj_rc;
 
   CU_TRY(pot, pot->status.reserve(sizeof(Status)));
-  Status init{0u, INT_MAX, 0, 0};
+  Status init{};
+  init.first_bad_atom = INT_MAX;
   CU_TRY(pot, cudaMemcpyAsync(pot->status.p, &init, sizeof init, cudaMemcpyHostToDevice, st));
 
   if (images) {
@@ -621,15 +650,11 @@ int run_cell_path(RgpotB200Pot* pot, long n, const double* d_pos, const int* d_Z
   k_scatter<<<div_up(n, 256), 256, 0, st>>>(pot->cell_of.as<int>(), pot->rank.as<int>(),
                                             pot->starts.as<int>(), (int)n, pot->order.as<int>());
   LAUNCH_CHECK(pot, "k_scatter");
-  CU_TRY(pot, pot->order2.reserve(sizeof(int) * n));
-  k_cell_order<<<div_up(n, 256), 256, 0, st>>>(pot->starts.as<int>(), pot->cell_of.as<int>(),
-                                               pot->order.as<int>(), (int)n, pot->order2.as<int>());
-  LAUNCH_CHECK(pot, "k_cell_order");
-  k_gather_sorted<<<div_up(n, 256), 256, 0, st>>>(d_pos, d_Z, pot->order2.as<int>(),
-                                                  pot->cell_of.as<int>(), pot->ashift.as<int>(), (int)n,
-                                                  eam ? 1 : (kind == RGPOT_B200_ZBL ? 2 : 0), pot->spos.as<double4>(),
-                                                  pot->scell.as<int>(), d_st);
-  LAUNCH_CHECK(pot, "k_gather_sorted");
+  k_order_gather<<<div_up(n, 256), 256, 0, st>>>(d_pos, d_Z, pot->starts.as<int>(), pot->cell_of.as<int>(),
+                                                 pot->order.as<int>(), pot->ashift.as<int>(), (int)n,
+                                                 eam ? 1 : (kind == RGPOT_B200_ZBL ? 2 : 0),
+                                                 pot->spos.as<double4>(), pot->scell.as<int>(), d_st);
+  LAUNCH_CHECK(pot, "k_order_gather");
 
   GatherArgs ga{};
   ga.spos = pot->spos.as<double4>();
@@ -676,9 +701,7 @@ int run_cell_path(RgpotB200Pot* pot, long n, const double* d_pos, const int* d_Z
     LAUNCH_CHECK(pot, "k_eam_density");
     k_eam_force<<<nblk, 128, 0, st>>>(ga, pot->dfd.as<double>(), pot->eemb.as<double>(), d_F, d_part);
     LAUNCH_CHECK(pot, "k_eam_force");
-    k_reduce_partials<<<1, 1024, 0, st>>>(d_part, tile_ok ? npart_used : nblk, d_E);
-    LAUNCH_CHECK(pot, "k_reduce_partials");
-    return 0;
+    return reduce_energy(pot, d_part, tile_ok ? npart_used : nblk, d_E, st);
   } else if (pl.geo == GEO_IMAGES) {
     k_lj_gather<GEO_IMAGES><<<nblk, 128, 0, st>>>(ga, d_F, d_part);
     LAUNCH_CHECK(pot, "k_lj_gather<images>");
@@ -696,9 +719,7 @@ int run_cell_path(RgpotB200Pot* pot, long n, const double* d_pos, const int* d_Z
     ga.only_if_atom_shift = 1;
     k_lj_gather<GEO_LJ_SHIFT><<<nblk, 128, 0, st>>>(ga, d_F, d_part);
     LAUNCH_CHECK(pot, "k_lj_gather<shift>");
-    k_reduce_partials<<<1, 1024, 0, st>>>(d_part, npart_used, d_E);
-    LAUNCH_CHECK(pot, "k_reduce_partials");
-    return 0;
+    return reduce_energy(pot, d_part, npart_used, d_E, st);
   } else if (pl.geo == GEO_LJ_SHIFT) {
     k_lj_gather<GEO_LJ_SHIFT><<<nblk, 128, 0, st>>>(ga, d_F, d_part);
     LAUNCH_CHECK(pot, "k_lj_gather<shift>");
@@ -706,9 +727,7 @@ int run_cell_path(RgpotB200Pot* pot, long n, const double* d_pos, const int* d_Z
     k_lj_gather<GEO_LJ_FOLD><<<nblk, 128, 0, st>>>(ga, d_F, d_part);
     LAUNCH_CHECK(pot, "k_lj_gather<fold>");
   }
-  k_reduce_partials<<<1, 1024, 0, st>>>(d_part, nblk, d_E);
-  LAUNCH_CHECK(pot, "k_reduce_partials");
-  return 0;
+  return reduce_energy(pot, d_part, nblk, d_E, st);
 }
 
 // shared memory a k_eam_small block needs
@@ -1207,6 +1226,13 @@ static int finish_single(RgpotB200Pot* pot, long n, const double* d_pos, const i
     }
     flags = stt.flags;
     pot->slow_atoms = stt.slow_atoms;
+    if (stt.max_halo > 0 && pot->memo_pending.n >= 0) {  // brick kernels ran: remember what they met
+      const bool same = pot->memo.n == pot->memo_pending.n && !memcmp(pot->memo.nc, pot->memo_pending.nc, sizeof pot->memo.nc) &&
+                        !memcmp(pot->memo.bd, pot->memo_pending.bd, sizeof pot->memo.bd);
+      const int prev = same ? pot->memo.max_halo : 0;
+      pot->memo = pot->memo_pending;
+      pot->memo.max_halo = std::max(prev, stt.max_halo);
+    }
     bad = stt.first_bad_atom;
     if ((flags & kFlagForeignZ) && bad != INT_MAX) {
       if (host_Z) {

@@ -16,14 +16,14 @@ E_RTOL = 1e-10
 F_RTOL, F_ATOL = 1e-10, 1e-9
 
 
-def assert_energy(e, ref):
-    assert abs(e - ref) <= E_RTOL * abs(ref) + 1e-12, (e, ref)
+def assert_energy(e, ref, what=None):
+    assert abs(e - ref) <= E_RTOL * abs(ref) + 1e-12, (e, ref, what)
 
 
-def assert_forces(f, ref):
+def assert_forces(f, ref, what=None):
     assert f.shape == ref.shape
     err = np.abs(f - ref)
-    assert (err <= F_ATOL + F_RTOL * np.abs(ref)).all(), float(err.max())
+    assert (err <= F_ATOL + F_RTOL * np.abs(ref)).all(), (float(err.max()), what)
 
 
 def canon(pairs, shifts):
@@ -476,3 +476,117 @@ def test_zbl_too_many_species():
     with pytest.raises(rgpot_b200.PotentialError) as ei:
         pot(pos, np.arange(1, 21, dtype=np.int32), np.eye(3) * 6)
     assert ei.value.status == 103
+
+
+# ------------------------------------------------------------------------- brick kernels (brick.cuh)
+# The large-system path: half-cutoff cells (fine = 2), private survivor lists evaluated in rounds,
+# oversized bricks cut in two.  The engine options shrink the capacities so that small systems walk
+# every one of those branches; all variants must agree with the oracle AND bit for bit with each
+# other (the summation order of an atom does not depend on the capacities).
+BRICK_VARIANTS = [
+    {},                                                   # automatic
+    {"fine": 1},                                          # cutoff-sized cells, 27-cell stencil
+    {"brick_list": 3},                                    # many search / physics rounds per atom
+    {"brick_slack": -70},                                 # staged capacity far too small: bricks are cut
+    {"brick": 111, "brick_threads": 64},                  # one cell per brick
+    {"brick": 421, "brick_threads": 96, "brick_list": 7},
+]
+
+
+def _with_options(pot, opts):
+    pot.set_option("fine_min", 0)
+    for key in ("fine", "brick_list", "brick_slack", "brick", "brick_threads", "brick_tpa"):
+        pot.set_option(key, opts.get(key, 0))
+
+
+@pytest.mark.parametrize("wrapped", [True, False])
+def test_brick_lj_variants_vs_oracle(oracle, wrapped):
+    n = 4000
+    pos, box = _random_fluid(n, 0.8442, 77, wrapped)
+    z = np.ones(n, np.int32)
+    e_o, f_o, _ = oracle.lj_force(pos, box, 1.0, 2.5, 1.0)
+    pot = rgpot_b200.LJPot(rgpot_b200.LJConfig(1.0, 2.5, 1.0))
+    pot.set_path(1)
+    first = {}
+    for opts in BRICK_VARIANTS:
+        for tpa in (1, 2, 4):
+            _with_options(pot, dict(opts, brick_tpa=tpa))
+            e, f, _ = pot(pos, z, box)
+            assert_energy(e, e_o, (opts, tpa))
+            assert_forces(f, f_o, (opts, tpa))
+            assert pot.stat("slow_atoms") == 0
+            key = (tpa, opts.get("fine", 0))  # same threads per atom + same cell grid => same order
+            if key in first:
+                assert np.array_equal(f, first[key]), (opts, tpa)
+            else:
+                first[key] = f
+
+
+def test_brick_cuh2_variants_vs_oracle(cuh2, oracle):
+    pos, Z, box = workloads.cu_slab_triclinic(cells=8, n_h2_side=3)  # 2066 atoms, sheared cell
+    e_o, f_o = oracle.cuh2_force(pos, Z, box)
+    pot = rgpot_b200.CuH2Pot()
+    pot.set_path(1)
+    first = {}
+    for opts in BRICK_VARIANTS:
+        for tpa in (2, 4):
+            _with_options(pot, dict(opts, brick_tpa=tpa))
+            e, f, _ = pot(pos, Z, box)
+            assert_energy(e, e_o, (opts, tpa))
+            assert_forces(f, f_o, (opts, tpa))
+            if "brick_slack" not in opts:
+                # the slab's bulk is denser than its mean, so a first call may cut bricks or walk a
+                # cell on the slow path; the engine remembers the halo populations it met and the
+                # next call with the same signature is sized for them
+                e, f, _ = pot(pos, Z, box)
+                assert_energy(e, e_o, (opts, tpa))
+                assert_forces(f, f_o, (opts, tpa))
+                assert pot.stat("slow_atoms") == 0
+                key = (tpa, opts.get("fine", 0))
+                if key in first:
+                    assert np.array_equal(f, first[key]), (opts, tpa)
+                else:
+                    first[key] = f
+
+
+def test_brick_morse_zbl_fine_cells(oracle):
+    n = 3000
+    pos, box = _random_fluid(n, 0.041, 5, True)  # 2.9 A lattice: the 9.5 A cutoff reaches several shells
+    z = np.ones(n, np.int32)
+    pot = rgpot_b200.MorsePot()
+    pot.set_path(1)
+    _with_options(pot, {"brick_list": 5})
+    e, f, _ = pot(pos, z, box)
+    e_o, f_o, _ = oracle.morse_force(pos, box)
+    assert_energy(e, e_o)
+    assert_forces(f, f_o)
+    rng = np.random.default_rng(11)
+    zz = rng.choice([1, 6, 14, 29], size=n).astype(np.int32)
+    cl = rng.random((n, 3)) * (n / 0.09) ** (1 / 3)
+    zb = rgpot_b200.ZBLPot()
+    zb.set_path(1)
+    _with_options(zb, {})
+    e, f, _ = zb(cl, zz, np.eye(3))
+    e_o, f_o, _ = oracle.zbl_force(cl, zz)
+    assert_energy(e, e_o)
+    assert (np.abs(f - f_o) <= 1e-9 + 1e-10 * np.abs(f_o)).all()
+
+
+def test_brick_dense_cell_falls_back_in_kernel(oracle):
+    """A cell whose own stencil exceeds the staged capacity takes the per-atom gather walk inside
+    the kernel (reported by the slow_atoms diagnostic); results still match the oracle."""
+    rng = np.random.default_rng(4)
+    n = 6000
+    pos, box = _random_fluid(n, 0.8442, 9, True)
+    # a dense blob: 600 atoms inside one small region (LJ with a tiny well so forces stay finite)
+    blob = rng.random((600, 3)) * 1.2 + 4.0
+    pos = np.vstack([pos, blob])
+    z = np.ones(len(pos), np.int32)
+    pot = rgpot_b200.LJPot(rgpot_b200.LJConfig(1.0e-6, 2.5, 0.3))
+    pot.set_path(1)
+    _with_options(pot, {"brick_slack": -60})
+    e, f, _ = pot(pos, z, box)
+    e_o, f_o, _ = oracle.lj_force(pos, box, 1.0e-6, 2.5, 0.3)
+    assert_energy(e, e_o)
+    assert_forces(f, f_o)
+    assert pot.stat("slow_atoms") > 0
