@@ -37,10 +37,6 @@ constexpr int kBrickMaxHalo = 512;  // (4 + 2*2)^3
 constexpr int kBrickMaxCells = 64;
 constexpr int kShiftCodes = 125;    // image counts q in [-2, 2]^3
 
-template <bool B>
-struct BoolTag {
-  static constexpr bool value = B;
-};
 
 struct TileOut {
   double* F;            // forces, original order (LJ, EAM force)

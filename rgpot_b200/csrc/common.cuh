@@ -69,6 +69,12 @@ RB_HD int meta_orig(unsigned long long m) { return (int)(m & 0x0fffffffull); }
 RB_HD int meta_species(unsigned long long m) { return (int)((m >> 28) & 15); }
 RB_HD int meta_shift(unsigned long long m, int k) { return (int)((m >> (32 + 10 * k)) & 1023) - 512; }
 
+// compile-time flag passed to generic lambdas (two specialisations of one loop body)
+template <bool B>
+struct BoolTag {
+  static constexpr bool value = B;
+};
+
 // ---- exact (never-contracted) arithmetic -------------------------------------------------
 RB_D double xadd(double a, double b) { return __dadd_rn(a, b); }
 RB_D double xsub(double a, double b) { return __dadd_rn(a, -b); }

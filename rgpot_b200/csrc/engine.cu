@@ -731,11 +731,19 @@ int run_cell_path(RgpotB200Pot* pot, long n, const double* d_pos, const int* d_Z
 }
 
 // shared memory a k_eam_small block needs
+int eam_small_tpa(long nmax) {  // lanes per atom: fill about 448 threads
+  int tpa = 1;
+  while (tpa < 8 && nmax * (tpa * 2) <= 448) tpa *= 2;
+  return tpa;
+}
+
 size_t eam_small_smem(long n, int maxnb) {  // must match the layout in k_eam_small
-  const size_t npad = ((size_t)n + 127) & ~(size_t)127;
+  const int tpa = eam_small_tpa(n);
+  const size_t ntl = (size_t)n * tpa, lcap = (size_t)(maxnb + tpa - 1) / tpa + 4;
   size_t bytes = sizeof(double) * (7 * (size_t)n + 81);
   bytes = (bytes + 15) & ~(size_t)15;
-  return bytes + sizeof(float) * 3 * npad + sizeof(int) * 4 * (size_t)n + sizeof(unsigned) * (size_t)n * maxnb;
+  return bytes + sizeof(float) * 4 * (size_t)n + sizeof(int) * 4 * (size_t)n +
+         sizeof(unsigned short) * (((ntl + 1) & ~(size_t)1) + lcap * ntl) + 16;
 }
 
 // pick the list capacity for a batch whose largest system has nmax atoms (0 = does not fit)
@@ -744,7 +752,9 @@ int eam_small_maxnb(const RgpotB200Pot* pot, long nmax) {
   if (nmax > 65535) return 0;
   // two resident blocks per SM when possible, else the roomiest list that still fits one block
   const size_t per_sm = 227 * 1024;
-  if (eam_small_smem(nmax, 96) + 6 * 1024 <= per_sm / 2 - 1024) return 96;
+  for (int maxnb : {160, 128, 96}) {
+    if (eam_small_smem(nmax, maxnb) + 6 * 1024 <= per_sm / 2 - 1024) return maxnb;
+  }
   for (int maxnb : {160, 128, 96}) {
     if (eam_small_smem(nmax, maxnb) + 6 * 1024 <= pot->smem_optin) return maxnb;
   }
@@ -783,9 +793,7 @@ int launch_small(RgpotB200Pot* pot, size_t nsys, long nmax, const long long* d_o
   if (emit) a.emit = *emit;
   if (pot->cfg.kind == RGPOT_B200_CUH2) {
     const size_t smem = eam_small_smem(nmax, maxnb);
-    // lanes per atom: fill about 448 threads
-    int tpa = 1;
-    while (tpa < 8 && nmax * (tpa * 2) <= 448) tpa *= 2;
+    const int tpa = eam_small_tpa(nmax);
     int threads = (int)std::min<long>(448, ((nmax * tpa + 31) / 32) * 32);
     if (threads < 32) threads = 32;
     auto launch = [&](auto kern) -> int {

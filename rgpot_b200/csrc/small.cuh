@@ -169,12 +169,14 @@ RB_D double entry_vec(const SmallBox& sb, const double* px, const double* py, co
 //
 //  phase A  load, classify (rgpot_cuh2.f90:463-489), wrap into the cell (fractional coordinates,
 //           FP64 + an FP32 copy for the prefilter); table of the 27 nearest image vectors S.H
-//  phase B  neighbor search, one WARP per atom, four candidates per lane and round:
-//             FP32 prefilter (nearest image in fractional space, Cartesian distance with a
-//             conservative margin; runs on the FP32 pipe, the FP64 pipe stays free),
-//             survivors are compacted through a per-warp shared-memory queue and take the EXACT
-//             FP64 test of vesin ((p_j - p_i) + S.H, d2 < rc2) 32 at a time, full lanes;
-//             accepted entries are appended to the atom's list in a fixed order.
+//  phase B  neighbor search, TPA threads per atom (the mapping of the physics phases): a thread
+//           tests its share of the other atoms -- FP32, nearest image in fractional space,
+//           Cartesian distance with a conservative margin; every lane of a warp reads the same
+//           candidate (a shared-memory broadcast) and runs the same trip count -- and appends the
+//           survivors to its PRIVATE 16-bit list with a predicated store: no ballots, no queues.
+//           A second sweep over the (short) list adds the image index and the species.  The
+//           exact FP64 test of vesin ((p_j - p_i) + S.H, d2 < rc2) is the one the physics phases
+//           evaluate anyway, so accept / reject stays bit-exact without a separate pass.
 //           Boxes narrower than two cutoffs (several images per pair) take a serial enumeration
 //           by lane 0 instead.
 //  phase C  atoms ordered by neighbor count so the lanes of a warp run equally long loops
@@ -182,9 +184,11 @@ RB_D double entry_vec(const SmallBox& sb, const double* px, const double* py, co
 //  phase E  pair energy + forces (rgpot_cuh2.f90:454-457), same mapping
 // Every sum has a fixed order: results are bit-reproducible.
 //
-// list entry: j (16 bits) | image index (5 bits, 0..26 = (S0+1) + 3 (S1+1) + 9 (S2+1)) << 16
-//             | species of j << 21.  Images further than one cell away (atoms far outside the
-//             box) raise kFlagListOverflow and the system reruns on the cell-list kernels.
+// list entry (16 bits): j (9 bits, n <= 512) | image index (5 bits, 0..26 = (S0+1) + 3 (S1+1)
+//             + 9 (S2+1)) << 9 | species of j << 14.  Entry k of thread t = i * TPA + sub sits at
+//             list[k * n * TPA + t].  Images further than one cell away (atoms far outside the
+//             box) or a full list raise kFlagListOverflow and the system reruns on the cell-list
+//             kernels.
 // --------------------------------------------------------------------------------------------
 struct SmallBoxF {  // FP32 mirror for the prefilter
   float h[9];
@@ -202,8 +206,6 @@ k_eam_small(SmallArgs a) {
   __shared__ SmallBoxF sbf;
   __shared__ unsigned blk_flags;
   __shared__ int blk_bad[2];
-  __shared__ unsigned short q_i[14][64];  // per-warp survivor queues (<= 14 warps per block)
-  __shared__ unsigned short q_j[14][64];
   __shared__ int hist[256];
 
   const int sys = blockIdx.x;
@@ -213,7 +215,8 @@ k_eam_small(SmallArgs a) {
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int nwarp = blockDim.x >> 5;
-  const int npad = (n + 127) & ~127;
+  const int NTL = n * TPA;                       // search / physics threads of this system
+  const int lcap = (maxnb + TPA - 1) / TPA + 4;  // list entries per thread
 
   // shared layout
   double* pos3 = reinterpret_cast<double*>(smem_raw);  // x, y, z interleaved
@@ -222,14 +225,13 @@ k_eam_small(SmallArgs a) {
   double* svt = dfd + n;                                // 27 image vectors, 3 doubles each
   size_t off_bytes = sizeof(double) * (7 * (size_t)n + 81);
   off_bytes = (off_bytes + 15) & ~(size_t)15;
-  float* fx32 = reinterpret_cast<float*>(smem_raw + off_bytes);
-  float* fy32 = fx32 + npad;
-  float* fz32 = fy32 + npad;
-  int* ash = reinterpret_cast<int*>(fz32 + npad);  // packed wrap counts (10 bits each, biased 512)
-  int* cnt = ash + n;                              // neighbors per atom
+  float4* g32 = reinterpret_cast<float4*>(smem_raw + off_bytes);  // FP32 copy of the wrapped fractional coordinates
+  int* ash = reinterpret_cast<int*>(g32 + n);      // packed wrap counts (10 bits each, biased 512)
+  int* cnt = ash + n;                              // listed candidates per atom
   int* spc = cnt + n;                              // species
   int* perm = spc + n;                             // atoms by decreasing neighbor count
-  unsigned* list = reinterpret_cast<unsigned*>(perm + n);  // n * maxnb entries
+  unsigned short* cnt16 = reinterpret_cast<unsigned short*>(perm + n);  // listed candidates per thread
+  unsigned short* list = cnt16 + ((NTL + 1) & ~1);                      // lcap * NTL entries
 
   if (threadIdx.x == 0) {
     small_box_init(a.boxes + 9 * (size_t)sys, c_eam.rcut, sb);
@@ -261,11 +263,7 @@ k_eam_small(SmallArgs a) {
   }
 
   // ---- phase A
-  for (int i = threadIdx.x; i < npad; i += blockDim.x) {
-    if (i >= n) {  // padding: NaN never passes the prefilter
-      fx32[i] = fy32[i] = fz32[i] = __int_as_float(0x7fc00000);
-      continue;
-    }
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
     const double x = a.pos[3 * (base + i)], y = a.pos[3 * (base + i) + 1], z = a.pos[3 * (base + i) + 2];
     pos3[3 * i] = x;
     pos3[3 * i + 1] = y;
@@ -286,7 +284,7 @@ k_eam_small(SmallArgs a) {
       atomicOr(&blk_flags, kFlagNonFinite);
       atomicMin(&blk_bad[0], i);
       g3[3 * i] = g3[3 * i + 1] = g3[3 * i + 2] = 0.0;
-      fx32[i] = fy32[i] = fz32[i] = 0.f;
+      g32[i] = make_float4(0.f, 0.f, 0.f, 0.f);
       ash[i] = 512 | (512 << 10) | (512 << 20);
       continue;
     }
@@ -303,9 +301,7 @@ k_eam_small(SmallArgs a) {
     g3[3 * i] = f[0];
     g3[3 * i + 1] = f[1];
     g3[3 * i + 2] = f[2];
-    fx32[i] = (float)f[0];
-    fy32[i] = (float)f[1];
-    fz32[i] = (float)f[2];
+    g32[i] = make_float4((float)f[0], (float)f[1], (float)f[2], 0.f);
     if (abs(w[0]) > 500 || abs(w[1]) > 500 || abs(w[2]) > 500) atomicOr(&blk_flags, kFlagShiftRange);
     if ((w[0] | w[1] | w[2]) != 0) atomicOr(&blk_flags, kFlagAtomShift);
     ash[i] = ((w[0] + 512) & 1023) | (((w[1] + 512) & 1023) << 10) | (((w[2] + 512) & 1023) << 20);
@@ -329,84 +325,27 @@ k_eam_small(SmallArgs a) {
 
   // ---- phase B
   if (sb.fast) {
-    unsigned short* qi = q_i[warp];
-    unsigned short* qj = q_j[warp];
-    int qn = 0;  // warp-uniform queue length
-    const unsigned lt_mask = (1u << lane) - 1u;
     const float h0 = sbf.h[0], h1 = sbf.h[1], h2 = sbf.h[2], h3 = sbf.h[3], h4 = sbf.h[4],
                 h5 = sbf.h[5], h6 = sbf.h[6], h7 = sbf.h[7], h8 = sbf.h[8];
     const float thr2 = sbf.thr2;
     const bool ortho = sbf.ortho != 0;
-
-    // exact test + ordered append of the first m queue entries (m <= 32)
-    auto drain = [&](int m) {
-      int i = 0xffff, j = 0, tidx = 13;
-      bool acc = false, far_image = false;
-      if (lane < m) {
-        i = (int)qi[lane];
-        j = (int)qj[lane];
-        // the prefilter's image choice, recomputed the same way: S' = -rint(g_j - g_i)
-        int S0 = -(int)rintf(fx32[j] - fx32[i]);
-        int S1 = -(int)rintf(fy32[j] - fy32[i]);
-        int S2 = -(int)rintf(fz32[j] - fz32[i]);
-        if (wrapped_atoms) {
-          const int ai = ash[i], aj = ash[j];
-          S0 += (ai & 1023) - (aj & 1023);
-          S1 += ((ai >> 10) & 1023) - ((aj >> 10) & 1023);
-          S2 += ((ai >> 20) & 1023) - ((aj >> 20) & 1023);
-          far_image = abs(S0) > 1 || abs(S1) > 1 || abs(S2) > 1;
-        }
-        if (!far_image) {
-          tidx = (S0 + 1) + 3 * (S1 + 1) + 9 * (S2 + 1);
-          const double* pi = pos3 + 3 * i;
-          const double* pj = pos3 + 3 * j;
-          const double* sv = svt + 3 * tidx;
-          const double vx = xadd(xsub(pj[0], pi[0]), sv[0]);
-          const double vy = xadd(xsub(pj[1], pi[1]), sv[1]);
-          const double vz = xadd(xsub(pj[2], pi[2]), sv[2]);
-          acc = xnorm2(vx, vy, vz) < rc2;
-        }
-      }
-      if (far_image) atomicOr(&blk_flags, kFlagListOverflow);
-      // queue entries are ordered by atom: lanes of one atom are contiguous
-      const int iprev = __shfl_up_sync(0xffffffffu, i, 1);
-      const unsigned heads = __ballot_sync(0xffffffffu, lane == 0 || i != iprev);
-      const unsigned bal = __ballot_sync(0xffffffffu, acc);
-      const int start = 31 - __clz((int)(heads & (lt_mask | (1u << lane))));
-      const unsigned after = heads & ~((2u << lane) - 1u);   // heads above my lane
-      const int end = after ? (__ffs((int)after) - 1) : 32;  // one past my group's last lane
-      const unsigned grp = (end == 32 ? 0xffffffffu : ((1u << end) - 1u)) & ~((1u << start) - 1u);
-      const int basecnt = lane < m ? cnt[i] : 0;
-      __syncwarp();  // every lane has read its atom's count before any group closes it
-      if (lane < m && acc) {
-        const int slot = basecnt + __popc(bal & grp & lt_mask);
-        if (slot < maxnb) {
-          list[i * maxnb + slot] = (unsigned)j | ((unsigned)tidx << 16) | ((unsigned)spc[j] << 21);
-        } else {
-          atomicOr(&blk_flags, kFlagListOverflow);
-        }
-      }
-      if (lane < m && lane == end - 1) cnt[i] = basecnt + __popc(bal & grp);
-      __syncwarp();
-    };
-
-    for (int i = warp; i < n; i += nwarp) {
-      const float gxi = fx32[i], gyi = fy32[i], gzi = fz32[i];
-      for (int jb = 0; jb < npad; jb += 128) {
-        const int j0 = jb + 4 * lane;
-        const float4 X = *reinterpret_cast<const float4*>(fx32 + j0);
-        const float4 Y = *reinterpret_cast<const float4*>(fy32 + j0);
-        const float4 Z = *reinterpret_cast<const float4*>(fz32 + j0);
-        const float xs[4] = {X.x, X.y, X.z, X.w}, ys[4] = {Y.x, Y.y, Y.z, Y.w}, zs[4] = {Z.x, Z.y, Z.z, Z.w};
-        bool pass[4];
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          float t0 = xs[c] - gxi, t1 = ys[c] - gyi, t2 = zs[c] - gzi;
+    const unsigned lbase = (unsigned)__cvta_generic_to_shared(list), lstride = 2u * (unsigned)NTL;
+    for (int t = threadIdx.x; t < NTL; t += blockDim.x) {
+      const int i = t / TPA, sub = t - i * TPA;
+      const float4 gi = g32[i];
+      const unsigned la0 = lbase + 2u * (unsigned)t, la_last = la0 + (unsigned)(lcap - 1) * lstride;
+      unsigned la = la0;  // list cursor (shared byte address); the last slot doubles as the overflow sink
+      auto search = [&](auto ortho_tag) {
+        constexpr bool ORTHO = decltype(ortho_tag)::value;
+#pragma unroll 4
+        for (int j = sub; j < n; j += TPA) {
+          const float4 c = g32[j];  // the same address in every lane of an atom group: a broadcast
+          float t0 = c.x - gi.x, t1 = c.y - gi.y, t2 = c.z - gi.z;
           t0 -= rintf(t0);
           t1 -= rintf(t1);
           t2 -= rintf(t2);
           float dx, dy, dz;
-          if (ortho) {
+          if (ORTHO) {
             dx = t0 * h0;
             dy = t1 * h4;
             dz = t2 * h8;
@@ -415,33 +354,39 @@ k_eam_small(SmallArgs a) {
             dy = fmaf(t0, h1, fmaf(t1, h4, t2 * h7));
             dz = fmaf(t0, h2, fmaf(t1, h5, t2 * h8));
           }
-          pass[c] = (fmaf(dx, dx, fmaf(dy, dy, dz * dz)) <= thr2) && (j0 + c != i);
+          const bool pass = (fmaf(dx, dx, fmaf(dy, dy, dz * dz)) <= thr2) && (j != i);
+          asm volatile("st.shared.u16 [%0], %1;" ::"r"(la), "h"((unsigned short)j));  // kept only if it passes
+          la = min(la + (pass ? lstride : 0u), la_last);
         }
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const unsigned bal = __ballot_sync(0xffffffffu, pass[c]);
-          if (bal == 0u) continue;
-          if (pass[c]) {
-            const int p = qn + __popc(bal & lt_mask);
-            qi[p] = (unsigned short)i;
-            qj[p] = (unsigned short)(j0 + c);
-          }
-          qn += __popc(bal);
-          __syncwarp();
-          if (qn >= 32) {
-            drain(32);
-            if (lane < qn - 32) {  // move the tail to the front (disjoint ranges)
-              const unsigned short ti = qi[32 + lane], tj = qj[32 + lane];
-              qi[lane] = ti;
-              qj[lane] = tj;
-            }
-            qn -= 32;
-            __syncwarp();
-          }
+      };
+      if (ortho)
+        search(BoolTag<true>{});
+      else
+        search(BoolTag<false>{});
+      if (la == la_last) atomicOr(&blk_flags, kFlagListOverflow);
+      const int c = (int)(((float)(la - la0) + 0.5f) / (float)lstride);
+      // second sweep: image index S' = -rint(g_j - g_i) (the search's choice, recomputed the same
+      // way) plus the atoms' own wrap counts, and the species of j
+      const int ai = ash[i];
+      bool far_image = false;
+      unsigned short* row = list + t;
+      for (int k = 0; k < c; ++k) {
+        const int j = row[k * NTL];
+        const float4 gj = g32[j];
+        int S0 = -(int)rintf(gj.x - gi.x), S1 = -(int)rintf(gj.y - gi.y), S2 = -(int)rintf(gj.z - gi.z);
+        if (wrapped_atoms) {
+          const int aj = ash[j];
+          S0 += (ai & 1023) - (aj & 1023);
+          S1 += ((ai >> 10) & 1023) - ((aj >> 10) & 1023);
+          S2 += ((ai >> 20) & 1023) - ((aj >> 20) & 1023);
+          far_image |= abs(S0) > 1 || abs(S1) > 1 || abs(S2) > 1;
         }
+        const int tidx = (S0 + 1) + 3 * (S1 + 1) + 9 * (S2 + 1);
+        row[k * NTL] = (unsigned short)(j | ((tidx & 31) << 9) | (spc[j] << 14));
       }
+      if (far_image) atomicOr(&blk_flags, kFlagListOverflow);
+      cnt16[t] = (unsigned short)c;
     }
-    if (qn > 0) drain(qn);
   } else if (lane == 0) {
     // small boxes: several images per pair; one lane enumerates them in (j, image) order
     for (int i = warp; i < n; i += nwarp) {
@@ -466,9 +411,10 @@ k_eam_small(SmallArgs a) {
               vy = xadd(xsub(pos3[3 * j + 1], pos3[3 * i + 1]), shift_component(sb.H, 1, (double)S0, (double)S1, (double)S2));
               vz = xadd(xsub(pos3[3 * j + 2], pos3[3 * i + 2]), shift_component(sb.H, 2, (double)S0, (double)S1, (double)S2));
               if (xnorm2(vx, vy, vz) < rc2) {
-                if (count < maxnb && abs(S0) <= 1 && abs(S1) <= 1 && abs(S2) <= 1) {
+                if (count / TPA < lcap && abs(S0) <= 1 && abs(S1) <= 1 && abs(S2) <= 1) {
                   const int tidx = (S0 + 1) + 3 * (S1 + 1) + 9 * (S2 + 1);
-                  list[i * maxnb + count] = (unsigned)j | ((unsigned)tidx << 16) | ((unsigned)spc[j] << 21);
+                  list[(count / TPA) * NTL + i * TPA + count % TPA] =
+                      (unsigned short)(j | (tidx << 9) | (spc[j] << 14));
                 } else {
                   atomicOr(&blk_flags, kFlagListOverflow);
                 }
@@ -476,8 +422,15 @@ k_eam_small(SmallArgs a) {
               }
             }
       }
-      cnt[i] = count;
+      for (int sub = 0; sub < TPA; ++sub) cnt16[i * TPA + sub] = (unsigned short)((count + TPA - 1 - sub) / TPA);
     }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {  // candidates per atom: balances the lanes below
+    int c = 0;
+#pragma unroll
+    for (int sub = 0; sub < TPA; ++sub) c += cnt16[i * TPA + sub];
+    cnt[i] = c;
   }
   __syncthreads();
   if (blk_flags & kFlagListOverflow) {
@@ -487,14 +440,22 @@ k_eam_small(SmallArgs a) {
 
   // optional emission of the table (rgpot_b200_neighbors)
   if (a.emit.pairs != nullptr) {
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-      for (int s = 0; s < cnt[i]; ++s) {
-        const unsigned en = list[i * maxnb + s];
+    for (int t = threadIdx.x; t < NTL; t += blockDim.x) {
+      const int i = t / TPA;
+      for (int s = 0; s < cnt16[t]; ++s) {
+        const unsigned en = list[s * NTL + t];
+        const int j = (int)(en & 511u), tidx = (int)((en >> 9) & 31u);
+        const double* pi = pos3 + 3 * i;
+        const double* pj = pos3 + 3 * j;
+        const double* sv = svt + 3 * tidx;
+        const double vx = xadd(xsub(pj[0], pi[0]), sv[0]);
+        const double vy = xadd(xsub(pj[1], pi[1]), sv[1]);
+        const double vz = xadd(xsub(pj[2], pi[2]), sv[2]);
+        if (!(xnorm2(vx, vy, vz) < rc2)) continue;  // the exact test of vesin
         const unsigned long long k = atomicAdd(a.emit.count, 1ull);
         if ((long)k < a.emit.cap) {
-          const int tidx = (int)((en >> 16) & 31u);
           a.emit.pairs[2 * k] = i;
-          a.emit.pairs[2 * k + 1] = (int)(en & 0xffffu);
+          a.emit.pairs[2 * k + 1] = j;
           a.emit.shifts[3 * k] = tidx % 3 - 1;
           a.emit.shifts[3 * k + 1] = (tidx / 3) % 3 - 1;
           a.emit.shifts[3 * k + 2] = tidx / 9 - 1;
@@ -552,20 +513,20 @@ k_eam_small(SmallArgs a) {
     int i = 0;
     if (vi) {
       i = perm[slot];
-      const int c = cnt[i];
+      const int c = cnt16[i * TPA + sub];
       const double xi = pos3[3 * i], yi = pos3[3 * i + 1], zi = pos3[3 * i + 2];
-      const unsigned* row = list + i * maxnb;
-      for (int s = sub; s < c; s += TPA) {
-        const unsigned en = row[s];
-        const double* pj = pos3 + 3 * (en & 0xffffu);
-        const double* sv = svt + 3 * ((en >> 16) & 31u);
+      const unsigned short* row = list + i * TPA + sub;
+      for (int s = 0; s < c; ++s) {
+        const unsigned en = row[s * NTL];
+        const double* pj = pos3 + 3 * (en & 511u);
+        const double* sv = svt + 3 * ((en >> 9) & 31u);
         const double vx = xadd(xsub(pj[0], xi), sv[0]);
         const double vy = xadd(xsub(pj[1], yi), sv[1]);
         const double vz = xadd(xsub(pj[2], zi), sv[2]);
         const double d2 = xnorm2(vx, vy, vz);
         if (d2 == 0.0) coincident = true;  // dist <= 0 guard, rgpot_cuh2.f90:422-428
         if (!(d2 < rc2_phys)) continue;    // :522
-        rho += eam_density_entry((int)(en >> 21), d2);
+        rho += eam_density_entry((int)(en >> 14), d2);
       }
     }
 #pragma unroll
@@ -596,22 +557,22 @@ k_eam_small(SmallArgs a) {
     int i = 0;
     if (vi) {
       i = perm[slot];
-      const int c = cnt[i];
+      const int c = cnt16[i * TPA + sub];
       const int zi = spc[i];
       const double dfd_i = dfd[i];
       const double xi = pos3[3 * i], yi = pos3[3 * i + 1], zi_ = pos3[3 * i + 2];
-      const unsigned* row = list + i * maxnb;
-      for (int s = sub; s < c; s += TPA) {
-        const unsigned en = row[s];
-        const int j = (int)(en & 0xffffu);
+      const unsigned short* row = list + i * TPA + sub;
+      for (int s = 0; s < c; ++s) {
+        const unsigned en = row[s * NTL];
+        const int j = (int)(en & 511u);
         const double* pj = pos3 + 3 * j;
-        const double* sv = svt + 3 * ((en >> 16) & 31u);
+        const double* sv = svt + 3 * ((en >> 9) & 31u);
         const double vx = xadd(xsub(pj[0], xi), sv[0]);
         const double vy = xadd(xsub(pj[1], yi), sv[1]);
         const double vz = xadd(xsub(pj[2], zi_), sv[2]);
         const double d2 = xnorm2(vx, vy, vz);
         if (!(d2 < rc2_phys)) continue;
-        eam_force_entry(zi, (int)(en >> 21), dfd_i, dfd[j], vx, vy, vz, d2, ep, fx, fy, fz);
+        eam_force_entry(zi, (int)(en >> 14), dfd_i, dfd[j], vx, vy, vz, d2, ep, fx, fy, fz);
       }
     }
 #pragma unroll

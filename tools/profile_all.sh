@@ -15,9 +15,9 @@ CMD="python bench.py --steps 2 --warmup 3 --workload cuh2_batch --configs 16384 
 $CMD > /dev/null 2>&1 && ncu --set full --clock-control none --import-source on -k regex:k_eam_small -s 3 -c 1 \
     -o gpurun_out/${TAG}_k_eam_small $CMD > /dev/null 2>&1
 CMD="python bench.py --steps 2 --warmup 3 --workload lj_fluid_1m"
-$CMD > /dev/null 2>&1 && ncu --set full --clock-control none --import-source on -k regex:k_lj_tile -s 3 -c 1 \
-    -o gpurun_out/${TAG}_k_lj_tile $CMD > /dev/null 2>&1
+$CMD > /dev/null 2>&1 && ncu --set full --clock-control none --import-source on -k regex:k_brick -s 3 -c 1 \
+    -o gpurun_out/${TAG}_k_brick_lj $CMD > /dev/null 2>&1
 CMD="python bench.py --steps 2 --warmup 3 --workload cuh2_slab_256k"
-$CMD > /dev/null 2>&1 && ncu --set full --clock-control none --import-source on -k regex:k_eam_tile -s 6 -c 2 \
-    -o gpurun_out/${TAG}_k_eam_tile $CMD > /dev/null 2>&1
+$CMD > /dev/null 2>&1 && ncu --set full --clock-control none --import-source on -k regex:k_brick -s 6 -c 2 \
+    -o gpurun_out/${TAG}_k_brick_eam $CMD > /dev/null 2>&1
 ls -la gpurun_out | tail -12
