@@ -129,6 +129,7 @@ k_brick(const __grid_constant__ GatherArgs a, const __grid_constant__ BrickPlan 
   __shared__ int box_stack[8][6];  // boxes of cells still to do: first cell, extent
 
   if (a.st_in->flags & kFlagAtomShift) return;  // the gather kernels of gather.cuh take over
+  if (POT == TILE_EAM_DENSITY || POT == TILE_EAM_FORCE) exp_table_init();
   constexpr bool kPairGeo = POT == TILE_LJ || POT == TILE_PAIR;  // LJ pair search (w * q image vectors)
   constexpr bool kForce = POT == TILE_EAM_FORCE;
   constexpr int NV = POT == TILE_EAM_DENSITY ? 1 : 3;

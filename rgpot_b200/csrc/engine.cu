@@ -1056,7 +1056,10 @@ RgpotB200Pot* rgpot_b200_create(const RgpotB200Config* cfg, char* errbuf, size_t
   }
   if (cfg->kind == RGPOT_B200_CUH2) {
     const EamParams p = make_eam_params();
-    if (cudaMemcpyToSymbol(c_eam, &p, sizeof p) != cudaSuccess) {
+    double tab[64];
+    for (int j = 0; j < 64; ++j) tab[j] = exp2((double)j / 64.0);
+    if (cudaMemcpyToSymbol(c_exp2tab, tab, sizeof tab) != cudaSuccess ||
+        cudaMemcpyToSymbol(c_eam, &p, sizeof p) != cudaSuccess) {
       delete pot;
       return err("rgpot_b200_create: cannot upload the EAM coefficients");
     }

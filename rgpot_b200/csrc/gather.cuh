@@ -191,6 +191,7 @@ __global__ void __launch_bounds__(128)
 k_eam_density(GatherArgs a, double* __restrict__ dfd_sorted, double* __restrict__ eemb_sorted,
               Status* __restrict__ st) {
   if (a.only_if_atom_shift && !(a.st_in->flags & kFlagAtomShift)) return;
+  exp_table_init();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= a.n) return;
   const double4 pi = a.spos[i];
@@ -217,6 +218,7 @@ k_eam_force(GatherArgs a, const double* __restrict__ dfd_sorted,
             double* __restrict__ partials) {
   __shared__ double sh32[32];
   if (a.only_if_atom_shift && !(a.st_in->flags & kFlagAtomShift)) return;
+  exp_table_init();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   double e = 0.0, fx = 0.0, fy = 0.0, fz = 0.0;
   if (i < a.n) {

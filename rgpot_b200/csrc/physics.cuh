@@ -90,30 +90,41 @@ RB_D void lj_pair(const LJParams& p, int ti, int tj, double dx, double dy, doubl
 }
 
 // ---- FP64 building blocks --------------------------------------------------------------------
-// exp(x) for x in about [-700, 700] with no special cases: k = rint(x log2 e) by the magic-number
-// add, two-term Cody-Waite reduction, degree-11 near-minimax polynomial (Chebyshev-node
-// interpolant on |r| <= ln2/2, max relative error 1.6e-17 before rounding), exponent patched in
-// with integer arithmetic.  About 1 ulp; 16 FP64 instructions, no branch.
+// exp(x) for x in about [-700, 700] with no special cases:  x = (64 k + j) ln2 / 64 + r,
+// |r| <= ln2 / 128, so exp(x) = 2^k * 2^(j/64) * e^r.  n = 64 k + j = rint(64 x log2 e) by the
+// magic-number add, a two-term Cody-Waite reduction, 2^(j/64) from a 64-entry table in shared
+// memory (correctly rounded doubles, uploaded by the host), e^r as a degree-5 Taylor polynomial
+// (truncation r^6 / 720 < 3.4e-17), 2^k patched into the exponent with integer arithmetic.
+// About 1 ulp; 10 FP64 instructions and one shared-memory load, no branch.  (The radial terms of
+// the EAM are exp-bound: this is 6 FP64 instructions fewer than a table-free degree-11 kernel.)
+__constant__ double c_exp2tab[64];
+
+RB_D double* exp_table() {
+  __shared__ double tab[64];
+  return tab;
+}
+// every thread of the block calls this once, before any thread returns; includes the barrier
+RB_D void exp_table_init() {
+  double* tab = exp_table();
+  for (int t = threadIdx.x; t < 64; t += blockDim.x) tab[t] = c_exp2tab[t];
+  __syncthreads();
+}
+
 RB_D double exp_fast(double x) {
   const double kMagic = 6755399441055744.0;  // 1.5 * 2^52
-  const double t = fma(x, 1.4426950408889634074, kMagic);
-  const int k = __double2loint(t);
+  const double t = fma(x, 92.332482616893656758, kMagic);  // 64 log2 e
+  const int n = __double2loint(t);
   const double kf = t - kMagic;
-  double r = fma(kf, -6.93147180369123816490e-01, x);
-  r = fma(kf, -1.90821492927058770002e-10, r);
-  double p = 2.5110095611886237e-08;
-  p = fma(p, r, 2.7632715071632255e-07);
-  p = fma(p, r, 2.7557240761739257e-06);
-  p = fma(p, r, 2.4801485278370062e-05);
-  p = fma(p, r, 1.9841269890193705e-04);
-  p = fma(p, r, 1.3888888952505406e-03);
-  p = fma(p, r, 8.333333333319546e-03);
-  p = fma(p, r, 4.166666666648738e-02);
-  p = fma(p, r, 1.666666666666668e-01);
-  p = fma(p, r, 5.000000000000019e-01);
+  double r = fma(kf, -6.93147180369123816490e-01 / 64.0, x);
+  r = fma(kf, -1.90821492927058770002e-10 / 64.0, r);
+  double p = 1.0 / 120.0;
+  p = fma(p, r, 1.0 / 24.0);
+  p = fma(p, r, 1.0 / 6.0);
+  p = fma(p, r, 0.5);
   p = fma(p, r, 1.0);
   p = fma(p, r, 1.0);
-  return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
+  p *= exp_table()[n & 63];
+  return __hiloint2double(__double2hiint(p) + ((n >> 6) << 20), __double2loint(p));
 }
 
 // 1/sqrt(a) for normal positive a: hardware seed (rsqrt.approx, ~2^-22) + one cubic Newton

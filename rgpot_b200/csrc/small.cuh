@@ -233,6 +233,7 @@ k_eam_small(SmallArgs a) {
   unsigned short* cnt16 = reinterpret_cast<unsigned short*>(perm + n);  // listed candidates per thread
   unsigned short* list = cnt16 + ((NTL + 1) & ~1);                      // lcap * NTL entries
 
+  exp_table_init();
   if (threadIdx.x == 0) {
     small_box_init(a.boxes + 9 * (size_t)sys, c_eam.rcut, sb);
     blk_flags = sb.bad ? kFlagSingularBox : 0u;  // vesin: "the box matrix is not invertible"
