@@ -36,7 +36,48 @@ class Config(C.Structure):
     ]
 
 
-# every symbol include/rgpot_b200.h declares: (name, restype, argtypes)
+# ---- include/rgpot_b200_core.h: DLPack 1.0 subset and the rgpot-core carriers (rgpot.h:76-117) ----
+class DLPackVersion(C.Structure):
+    _fields_ = [("major", C.c_uint32), ("minor", C.c_uint32)]
+
+
+class DLDevice(C.Structure):
+    _fields_ = [("device_type", C.c_int), ("device_id", C.c_int32)]
+
+
+class DLDataType(C.Structure):
+    _fields_ = [("code", C.c_uint8), ("bits", C.c_uint8), ("lanes", C.c_uint16)]
+
+
+class DLTensor(C.Structure):
+    _fields_ = [("data", C.c_void_p), ("device", DLDevice), ("ndim", C.c_int32), ("dtype", DLDataType),
+                ("shape", C.POINTER(C.c_int64)), ("strides", C.POINTER(C.c_int64)),
+                ("byte_offset", C.c_uint64)]
+
+
+class DLManagedTensorVersioned(C.Structure):
+    pass
+
+
+DLDeleter = C.CFUNCTYPE(None, C.POINTER(DLManagedTensorVersioned))
+DLManagedTensorVersioned._fields_ = [("version", DLPackVersion), ("manager_ctx", C.c_void_p),
+                                     ("deleter", DLDeleter), ("flags", C.c_uint64), ("dl_tensor", DLTensor)]
+
+
+class ForceInput(C.Structure):
+    """rgpot_force_input_t"""
+    _fields_ = [("positions", C.POINTER(DLManagedTensorVersioned)),
+                ("atomic_numbers", C.POINTER(DLManagedTensorVersioned)),
+                ("box_matrix", C.POINTER(DLManagedTensorVersioned))]
+
+
+class ForceOut(C.Structure):
+    """rgpot_force_out_t"""
+    _fields_ = [("forces", C.POINTER(DLManagedTensorVersioned)), ("energy", C.c_double),
+                ("variance", C.c_double)]
+
+
+# every symbol include/*.h declares: (name, restype, argtypes)
 _vp, _sz, _i, _l, _d = C.c_void_p, C.c_size_t, C.c_int, C.c_long, C.c_double
 SYMBOLS = [
     ("rgpot_b200_abi_version", _i, []),
@@ -58,6 +99,9 @@ SYMBOLS = [
     ("rgpot_b200_host_alloc", _vp, [_sz]),
     ("rgpot_b200_host_free", None, [_vp]),
     ("rgpot_b200_measure_fp64_tflops", _d, [_i, _i]),
+    ("rgpot_b200_core_callback", _i, [_vp, _vp, _vp]),
+    ("rgpot_b200_core_free", None, [_vp]),
+    ("rgpot_b200_core_last_error", C.c_char_p, []),
     ("rgpot_cuh2_force", _i, [C.c_int32, _vp, _vp, _vp, _vp, C.POINTER(_d)]),
     ("rgpot_fortran_last_error", _i, [C.c_char_p, _i]),
 ]

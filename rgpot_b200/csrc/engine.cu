@@ -1938,3 +1938,5 @@ int rgpot_fortran_last_error(char* buffer, int buffer_len) {
 }
 
 }  // extern "C"
+
+#include "core_abi.cuh"

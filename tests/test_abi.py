@@ -1,4 +1,4 @@
-"""The C-ABI library loads and exports every symbol include/rgpot_b200.h declares (no compute)."""
+"""The C-ABI library loads and exports every symbol include/*.h declares (no compute)."""
 import os
 import re
 
@@ -17,16 +17,22 @@ def engine():
 
 
 def declared_symbols():
-    text = open(os.path.join(ROOT, "include", "rgpot_b200.h")).read()
-    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    return sorted(set(re.findall(r"RGPOT_B200_API\s+[^;(]*?\b(rgpot_\w+)\s*\(", text)))
+    names = set()
+    inc = os.path.join(ROOT, "include")
+    for header in sorted(os.listdir(inc)):
+        if not header.endswith(".h"):
+            continue
+        text = open(os.path.join(inc, header)).read()
+        text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+        names.update(re.findall(r"RGPOT_B200_API\s+[^;(]*?\b(rgpot_\w+)\s*\(", text))
+    return sorted(names)
 
 
 def test_header_symbols_are_exported(engine):
     names = declared_symbols()
     assert len(names) >= 20
     for name in names:
-        assert hasattr(engine, name), f"{name} declared in rgpot_b200.h but not exported"
+        assert hasattr(engine, name), f"{name} declared in include/*.h but not exported"
     assert set(names) == {s[0] for s in _lib.SYMBOLS}, "python binding table out of sync with the header"
 
 
@@ -41,6 +47,15 @@ def test_abi_version_and_defaults(engine):
     assert (cfg.morse_De, cfg.morse_a, cfg.morse_re, cfg.cutoff) == (0.7102, 1.6047, 2.8970, 9.5)  # MorsePot.hpp:31-36
     engine.rgpot_b200_default_config(_lib.KIND_ZBL, cfg)
     assert (cfg.zbl_cut_inner, cfg.cutoff) == (2.0, 2.5)  # ZBLPot.hpp:29-32
+
+
+def test_core_callback_rejects_bad_input_without_a_gpu(engine):
+    """rgpot_b200_core_callback (the rgpot-core PotentialCallback) validates before it computes."""
+    import ctypes as C
+    engine.rgpot_b200_core_last_error.restype = C.c_char_p
+    out = _lib.ForceOut()
+    assert engine.rgpot_b200_core_callback(None, None, C.byref(out)) == 1  # RGPOT_INVALID_PARAMETER
+    assert b"NULL" in engine.rgpot_b200_core_last_error()
 
 
 def test_fortran_dropin_symbols_present(engine):

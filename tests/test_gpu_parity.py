@@ -590,3 +590,50 @@ def test_brick_dense_cell_falls_back_in_kernel(oracle):
     assert_energy(e, e_o)
     assert_forces(f, f_o)
     assert pot.stat("slow_atoms") > 0
+
+
+# ------------------------------------------------------- rgpot-core boundary (rgpot_b200_core.h)
+def test_core_callback_cpu_tensors(cuh2, golden, oracle):
+    """rgpot_b200_core_callback with kDLCPU DLPack tensors: CuH2PotTest.cc pin and the slab."""
+    from rgpot_b200 import core
+    g = golden("cuh2_pin4.json")
+    pos, Z, box = np.array(g["positions"]), np.array(g["Z"], np.int32), np.array(g["box"])
+    e, f, v = core.calculate(cuh2, pos, Z, box)
+    assert e == pytest.approx(g["pin_energy"], rel=1e-10) and v == 0.0  # CuH2PotTest.cc:26
+    assert np.abs(f - np.array(g["pin_forces"]).reshape(-1, 3)).max() < 1e-9
+    e2, f2, _ = cuh2(pos, Z, box.reshape(3, 3))
+    assert e == e2 and np.array_equal(f, f2)  # the same engine call underneath
+    # LJ without atomic numbers (optional tensor, potential.hpp:219-222)
+    lj = rgpot_b200.LJPot()
+    c = golden("lj13_cluster.json")
+    e, f, _ = core.calculate(lj, np.array(c["positions"]), None, np.array(c["box"]))
+    assert e == pytest.approx(c["pin_energy"], rel=1e-9)
+
+
+def test_core_callback_cuda_tensors(cuh2, oracle):
+    """kDLCUDA tensors ("any device", rgpot.h:78-88): evaluated in place, forces come back on the GPU."""
+    import torch
+
+    from rgpot_b200 import core
+    pos, Z, box = workloads.cu_slab_triclinic(cells=6, n_h2_side=2)
+    e_o, f_o = oracle.cuh2_force(pos, Z, box)
+    dev = torch.device("cuda", 0)
+    e, f, _ = core.calculate(cuh2, torch.from_numpy(pos).to(dev), torch.from_numpy(Z).to(dev), box)
+    assert f.is_cuda
+    assert_energy(e, e_o)
+    assert_forces(f.cpu().numpy(), f_o)
+
+
+def test_core_callback_errors(cuh2):
+    from rgpot_b200 import core
+    pos = np.zeros((4, 3))
+    with pytest.raises(core.CoreError) as ei:  # wrong shape
+        core.calculate(cuh2, np.zeros((4, 2)), np.full(4, 29, np.int32), np.eye(3) * 20)
+    assert ei.value.status == 1
+    with pytest.raises(core.CoreError) as ei:  # Z of the wrong length
+        core.calculate(cuh2, pos, np.full(3, 29, np.int32), np.eye(3) * 20)
+    assert ei.value.status == 1
+    with pytest.raises(core.CoreError) as ei:  # engine failure: foreign species -> status 2 message
+        core.calculate(cuh2, np.random.default_rng(0).random((4, 3)) * 5, np.array([29, 29, 8, 1], np.int32),
+                       np.eye(3) * 20)
+    assert ei.value.status == 2 and "atom 3 has atomic number 8" in str(ei.value)

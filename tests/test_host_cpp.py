@@ -33,6 +33,18 @@ def test_cpp_plugin_classes_reproduce_reference_tests():
 
 
 @pytest.mark.gpu
+def test_core_callback_from_plain_c():
+    """include/rgpot_b200_core.h compiled as C11: the rgpot-core PotentialCallback over DLPack
+    tensors reproduces CuH2PotTest.cc:11-31 and rejects a malformed tensor."""
+    exe = os.path.join(HOST, "test_core")
+    if not os.path.exists(exe):
+        subprocess.run(["make", "-s", "-C", HOST], check=True)
+    res = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert "test_core: ok" in res.stdout
+
+
+@pytest.mark.gpu
 def test_unmodified_reference_cuh2pot_runs_on_the_engine():
     """oracle/_ref/dropin_cuh2pot = the reference's FortranPots.cc linked against librgpot_b200.so
     (built only where /root/reference exists; travels to the GPU box prebuilt)."""
