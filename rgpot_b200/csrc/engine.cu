@@ -428,20 +428,34 @@ bool plan_bricks(const RgpotB200Pot* pot, const Plan& pl, long n, double rc, boo
       int threads = pot->opt_threads ? pot->opt_threads : round_up((int)ceil(pop * 1.15 * tpa), 32);
       threads = std::max(64, std::min(kBrickMaxThreads, round_up(threads, 32)));
       (void)slots;
-      // capacities: generous first; tightened when that buys a third resident block per SM (an
-      // oversized brick or list is still evaluated correctly, on the block's slow path)
-      const unsigned per_block3 = (unsigned)(pot->smem_per_sm / 3) - 1024u - 8192u;
-      for (int tight = 0; tight < 2; ++tight) {
-        const double fc = tight ? 1.15 : 1.3, fl = tight ? 1.0 : 1.4;
-        const double fcc = pot->opt_slack ? 1.0 + 0.01 * pot->opt_slack : fc;
+      // capacities: the staged halo from the mean density (or from what the last call with this
+      // signature met); the private lists as long as they can be without costing a resident block
+      // (a full list only means one more search / physics round, a full halo a cut brick)
+      {
+        const double fcc = pot->opt_slack ? 1.0 + 0.01 * pot->opt_slack : 1.2;
         bp.cap_cand = std::min(65504, round_up((int)(nhalo * mean * fcc) + 32, 32));
         const auto& m = pot->memo;
         const bool known = !pot->opt_slack && m.n == n && m.max_halo > 0 && m.nc[0] == g.nc[0] && m.nc[1] == g.nc[1] &&
                            m.nc[2] == g.nc[2] && m.bd[0] == bd[0] && m.bd[1] == bd[1] && m.bd[2] == bd[2];
         if (known) bp.cap_cand = std::min(65504, round_up((int)(m.max_halo * 1.04) + 24, 32));
-        bp.cap_list = pot->opt_list ? pot->opt_list : std::max(24, (int)(nnb / tpa * fl) + 14);
+        const int want = (int)(nnb / tpa * 2.2) + 8, least = std::max(24, (int)(nnb / tpa) + 14);
+        auto blocks_per_sm = [&](int cap_list) {
+          const size_t per_block = brick_smem_bytes(bp.cap_cand, cap_list, threads, eam) + 8192 + 1024;
+          return (int)(pot->smem_per_sm / per_block);
+        };
+        bp.cap_list = least;
+        if (pot->opt_list) {
+          bp.cap_list = pot->opt_list;
+        } else {
+          const int blocks = std::min(3, blocks_per_sm(least));  // registers allow three blocks of 256
+          for (int c = want; c > least; c -= 2) {
+            if (std::min(3, blocks_per_sm(c)) >= blocks) {
+              bp.cap_list = c;
+              break;
+            }
+          }
+        }
         bp.smem = brick_smem_bytes(bp.cap_cand, bp.cap_list, threads, eam);
-        if (bp.smem <= per_block3) break;
       }
       if ((size_t)bp.smem + 10240 <= pot->smem_optin) {
         for (int k = 0; k < 3; ++k) {
