@@ -89,6 +89,17 @@ double oracle_cuh2_drho(int kind, double r);
 double oracle_cuh2_embed(int kind, double rho);
 double oracle_cuh2_dembed(int kind, double rho);
 
+/* ------------------------------------------------------------- EAM-Al ----- */
+
+/* rgpot_eam_al_force (rgpot_eam_al_capi.f90:31-58) -> eam_al_energy_forces
+ * (rgpot_eam_al.f90:216-258).  Status 0 or a neighbor-build status with a message.    */
+int oracle_eam_al_force(int32_t natoms, const double *pos, const double *cell, double *F,
+                        double *energy, char *err, size_t errlen);
+int oracle_eam_al_force_table(int32_t natoms, const oracle_nlist_t *table, double *F, double *energy);
+/* which: 0 pair_energy, 1 pair_deriv, 2 density, 3 density_deriv (of r); 4 embedding,
+ * 5 embedding_deriv (of rho).  rgpot_eam_al.f90:125-213.                               */
+double oracle_eam_al_scalar(int which, double x);
+
 /* LJ pair math over a vesin-semantics (all images, general triclinic) list: the oracle
  * for the opt-in triclinic LJ mode.  There is NO reference implementation of this
  * (LJPot.cc ignores off-diagonal box terms): parity unpinned, self-consistency only.  */

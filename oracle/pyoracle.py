@@ -58,6 +58,11 @@ def _declare_common(lib):
                                        C.POINTER(NList), C.c_char_p, C.c_size_t]
     lib.oracle_nlist_free.restype = None
     lib.oracle_nlist_free.argtypes = [C.POINTER(NList)]
+    lib.oracle_eam_al_force.restype = C.c_int
+    lib.oracle_eam_al_force.argtypes = [C.c_int32, _f64p, _f64p, _f64p, C.POINTER(C.c_double), C.c_char_p,
+                                        C.c_size_t]
+    lib.oracle_eam_al_scalar.restype = C.c_double
+    lib.oracle_eam_al_scalar.argtypes = [C.c_int, C.c_double]
     lib.oracle_cuh2_force.restype = C.c_int
     lib.oracle_cuh2_force.argtypes = [C.c_int32, _f64p, _i32p, _f64p, _f64p, C.POINTER(C.c_double),
                                       C.c_char_p, C.c_size_t, C.POINTER(NList)]
@@ -285,6 +290,24 @@ def cuh2_force(pos, Z, box, use_ref=False, return_table=False):
     if return_table:
         return e.value, F, table
     return e.value, F
+
+
+# ------------------------------------------------------------------ EAM-Al
+def eam_al_force(pos, box):
+    """(energy, forces) of rgpot_eam_al_force (rgpot_eam_al_capi.f90:31-58); atomic numbers are not an input."""
+    pos, box = _prep(pos, box)
+    F = np.zeros_like(pos)
+    e = C.c_double(0.0)
+    err = C.create_string_buffer(512)
+    st = oracle_lib().oracle_eam_al_force(len(pos), pos, box, F, C.byref(e), err, 512)
+    if st != 0:
+        raise RuntimeError(f"EAM-Al potential failed (status {st}): {err.value.decode()}")
+    return e.value, F
+
+
+def eam_al_scalar(which, x):
+    """0 pair_energy, 1 pair_deriv, 2 density, 3 density_deriv (r); 4 embedding, 5 embedding_deriv (rho)."""
+    return oracle_lib().oracle_eam_al_scalar(int(which), float(x))
 
 
 def cuh2_scalar(name, kind, x):

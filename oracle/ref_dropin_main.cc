@@ -1,7 +1,7 @@
 // ref_dropin_main.cc -- the reference's OWN C++ face of the CuH2 kernel
 // (CppCore/rgpot/fortran/FortranPots.cc, compiled unmodified from /root/reference) linked against
-// librgpot_b200.so instead of the Fortran objects: `rgpot::fortranpots::CuH2Pot` then evaluates on
-// the B200 without a single changed line upstream.  TEST INFRASTRUCTURE (built into oracle/_ref).
+// librgpot_b200.so instead of the Fortran objects: `rgpot::fortranpots::CuH2Pot` and `EAMAlPot` then
+// evaluate on the B200 without a single changed line upstream.  TEST INFRASTRUCTURE (built into oracle/_ref).
 // Runs CppCore/tests/CuH2PotTest.cc:8-43 and the error path of FortranPots.cc:44-56.
 #include <cmath>
 #include <cstdint>
@@ -12,12 +12,12 @@
 #include "rgpot/fortran/FortranPots.hpp"
 #include "rgpot/types/AtomMatrix.hpp"
 
-// FortranPots.cc also references the seven potentials this engine does not implement
+// FortranPots.cc also references the six potentials this engine does not implement
 extern "C" {
 #define STUB5(name) int name(int32_t, const double *, const double *, double *, double *) { return 99; }
 #define STUB6(name) int name(int32_t, const double *, const int32_t *, const double *, double *, double *) { return 99; }
 STUB5(rgpot_sw_force) STUB5(rgpot_edip_force) STUB5(rgpot_lenosky_force) STUB5(rgpot_tersoff_force)
-STUB5(rgpot_eam_al_force) STUB6(rgpot_fehe_force) STUB6(rgpot_water_h_force)
+STUB6(rgpot_fehe_force) STUB6(rgpot_water_h_force)
 }
 
 int main() {
@@ -50,7 +50,19 @@ int main() {
                                  "this potential covers Cu (29) and H (1) only")
       ++bad;
   }
-  std::printf("reference fortranpots::CuH2Pot over librgpot_b200.so: E = %.16f, %s\n", energy,
+  {  // CppCore/tests/FortranPotsTest.cc:135-144 through the reference's own EAMAlPot class
+    auto al = rgpot::fortranpots::EAMAlPot();
+    AtomMatrix fcc{{7.97500, 7.97500, 7.97500}, {10.00000, 10.00000, 7.97500}, {10.00000, 7.97500, 10.00000},
+                   {7.97500, 10.00000, 10.00000}};
+    std::array<std::array<double, 3>, 3> cube{{{20.0, 0.0, 0.0}, {0.0, 20.0, 0.0}, {0.0, 0.0, 20.0}}};
+    auto [e_al, f_al, v_al] = al(fcc, std::vector<int>(4, 13), cube);
+    (void)v_al;
+    double worst = 0.0;
+    for (int i = 0; i < 4; ++i)
+      worst = std::fmax(worst, std::sqrt(f_al(i, 0) * f_al(i, 0) + f_al(i, 1) * f_al(i, 1) + f_al(i, 2) * f_al(i, 2)));
+    if (std::fabs(e_al - (-5.217864)) > 1e-4 * 5.217864 || std::fabs(worst - 0.968647) > 1e-3 * 0.968647) ++bad;
+  }
+  std::printf("reference fortranpots::CuH2Pot / EAMAlPot over librgpot_b200.so: E = %.16f, %s\n", energy,
               bad ? "MISMATCH" : "ok");
   return bad ? 1 : 0;
 }

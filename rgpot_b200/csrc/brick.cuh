@@ -30,7 +30,11 @@
 
 namespace rb {
 
-enum { TILE_LJ = 0, TILE_EAM_DENSITY = 1, TILE_EAM_FORCE = 2, TILE_PAIR = 3 };  // TILE_PAIR: Morse / ZBL on the LJ geometry
+// TILE_PAIR: Morse / ZBL on the LJ geometry; TILE_AL_*: the EAM passes with the aluminium model
+enum { TILE_LJ = 0, TILE_EAM_DENSITY = 1, TILE_EAM_FORCE = 2, TILE_PAIR = 3, TILE_AL_DENSITY = 4, TILE_AL_FORCE = 5 };
+constexpr bool tile_is_density(int pot) { return pot == TILE_EAM_DENSITY || pot == TILE_AL_DENSITY; }
+constexpr bool tile_is_force(int pot) { return pot == TILE_EAM_FORCE || pot == TILE_AL_FORCE; }
+constexpr int tile_model(int pot) { return pot >= TILE_AL_DENSITY ? EAM_AL : EAM_CUH2; }
 
 constexpr int kBrickMaxThreads = 256;
 constexpr int kBrickMaxHalo = 512;  // (4 + 2*2)^3
@@ -84,26 +88,26 @@ __device__ __noinline__ void brick_slow_atom(const GatherArgs& a, const TileOut&
       lj_pair(a.lj, zi, meta_species(mj), dx, dy, dz, d2, e, fx, fy, fz);
     };
     walk_neighbors<GEO_LJ_SHIFT, false>(a, i, pi, body);
-  } else if (POT == TILE_EAM_DENSITY) {
-    const double rc2_phys = c_eam.rc2_phys;
+  } else if (tile_is_density(POT)) {
+    const double rc2_phys = eam_par<tile_model(POT)>().rc2_phys;
     double rho = 0.0;
     auto body = [&](int, unsigned long long mj, double, double, double, double d2, int, int, int) {
       if (d2 == 0.0) coincident = true;
       if (!(d2 < rc2_phys)) return;
-      rho += eam_density_entry(meta_species(mj), d2);
+      rho += eam_density_entry<tile_model(POT)>(meta_species(mj), d2);
     };
     walk_neighbors<GEO_IMAGES, false>(a, i, pi, body);
     double emb, demb;
-    eam_embed(zi, rho, emb, demb);
+    eam_embed<tile_model(POT)>(zi, rho, emb, demb);
     o.dfd_sorted[i] = demb;
     o.eemb_sorted[i] = emb;
     return;
   } else {
-    const double rc2_phys = c_eam.rc2_phys;
+    const double rc2_phys = eam_par<tile_model(POT)>().rc2_phys;
     const double dfd_i = o.dfd_sorted[i];
     auto body = [&](int j, unsigned long long mj, double dx, double dy, double dz, double d2, int, int, int) {
       if (!(d2 < rc2_phys)) return;
-      eam_force_entry(zi, meta_species(mj), dfd_i, o.dfd_sorted[j], dx, dy, dz, d2, e, fx, fy, fz);
+      eam_force_entry<tile_model(POT)>(zi, meta_species(mj), dfd_i, o.dfd_sorted[j], dx, dy, dz, d2, e, fx, fy, fz);
     };
     walk_neighbors<GEO_IMAGES, false>(a, i, pi, body);
     e += o.eemb_sorted[i];
@@ -129,10 +133,12 @@ k_brick(const __grid_constant__ GatherArgs a, const __grid_constant__ BrickPlan 
   __shared__ int box_stack[8][6];  // boxes of cells still to do: first cell, extent
 
   if (a.st_in->flags & kFlagAtomShift) return;  // the gather kernels of gather.cuh take over
-  if (POT == TILE_EAM_DENSITY || POT == TILE_EAM_FORCE) exp_table_init();
+  if (tile_is_density(POT) || tile_is_force(POT)) exp_table_init();
   constexpr bool kPairGeo = POT == TILE_LJ || POT == TILE_PAIR;  // LJ pair search (w * q image vectors)
-  constexpr bool kForce = POT == TILE_EAM_FORCE;
-  constexpr int NV = POT == TILE_EAM_DENSITY ? 1 : 3;
+  constexpr bool kForce = tile_is_force(POT);
+  constexpr bool kDensity = tile_is_density(POT);
+  constexpr int kModel = tile_model(POT);
+  constexpr int NV = kDensity ? 1 : 3;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int nthreads = blockDim.x;
   const Grid& g = a.grid;
@@ -346,7 +352,7 @@ k_brick(const __grid_constant__ GatherArgs a, const __grid_constant__ BrickPlan 
     const int natoms = bc_astart[nbc];
 
     const double rc2 = kPairGeo ? a.lj.rc2 : a.rc2;
-    const double rc2_phys = kPairGeo ? 0.0 : c_eam.rc2_phys;
+    const double rc2_phys = kPairGeo ? 0.0 : eam_par<kModel>().rc2_phys;
     const int apb = nthreads / TPA;  // atoms per pass
     const int nrx = 2 * bp.ns[0] + 1, nry = 2 * bp.ns[1] + 1, nrows = nry * (2 * bp.ns[2] + 1);
     // private survivor list of this thread: entry k at shared byte address lsa0 + k * lstride
@@ -456,11 +462,11 @@ k_brick(const __grid_constant__ GatherArgs a, const __grid_constant__ BrickPlan 
                 }
               } else if (d2 < rc2 && sj != si) {  // vesin :1202; the atom itself is no neighbour
                 const int zj = info >> 8;
-                if (POT == TILE_EAM_DENSITY) {
+                if (kDensity) {
                   if (d2 == 0.0) coincident = true;
-                  if (d2 < rc2_phys) acc[0] += eam_density_entry(zj, d2);
+                  if (d2 < rc2_phys) acc[0] += eam_density_entry<kModel>(zj, d2);
                 } else if (d2 < rc2_phys) {
-                  eam_force_entry(zi, zj, dfd_i, c64w[sj], dx, dy, dz, d2, e_thr, acc[0], acc[1], acc[2]);
+                  eam_force_entry<kModel>(zi, zj, dfd_i, c64w[sj], dx, dy, dz, d2, e_thr, acc[0], acc[1], acc[2]);
                 }
               }
             }
@@ -474,9 +480,9 @@ k_brick(const __grid_constant__ GatherArgs a, const __grid_constant__ BrickPlan 
           for (int k = 0; k < NV; ++k) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], off);
         }
         if (active && sub == 0) {
-          if (POT == TILE_EAM_DENSITY) {
+          if (kDensity) {
             double emb, demb;
-            eam_embed(cinfo[si] >> 8, acc[0], emb, demb);
+            eam_embed<kModel>(cinfo[si] >> 8, acc[0], emb, demb);
             o.dfd_sorted[gi] = demb;
             o.eemb_sorted[gi] = emb;
           } else {
@@ -484,7 +490,7 @@ k_brick(const __grid_constant__ GatherArgs a, const __grid_constant__ BrickPlan 
             o.F[3 * (size_t)orig] = acc[0];
             o.F[3 * (size_t)orig + 1] = acc[1];
             o.F[3 * (size_t)orig + 2] = acc[2];
-            if (POT == TILE_EAM_FORCE) e_thr += o.eemb_sorted[gi];
+            if (kForce) e_thr += o.eemb_sorted[gi];
           }
         }
       }
@@ -501,7 +507,7 @@ k_brick(const __grid_constant__ GatherArgs a, const __grid_constant__ BrickPlan 
     __syncthreads();
   }
 
-  if (POT == TILE_EAM_DENSITY) {
+  if (kDensity) {
     if (coincident) atomicOr(&o.st->flags, kFlagCoincident);
   } else {
     // one energy partial per warp (fixed shuffle tree); the warps retire independently

@@ -81,6 +81,19 @@ struct HostBuf {  // pinned
 };
 
 // CuH2 defaults (rgpot_cuh2.f90:58-105) with the five cutoff shifts of cut_shifted (:118-135)
+// physics threshold on d2: d2 < rc2 (vesin) and sqrt(d2) < r_phys (the kernels' own radial test)
+// folded into one compare, plus the identities the fast radial terms rely on
+void finish_eam_params(EamParams& p, double r_phys) {
+  double T = r_phys * r_phys;
+  while (sqrt(T) >= r_phys) T = nextafter(T, 0.0);
+  while (sqrt(nextafter(T, INFINITY)) < r_phys) T = nextafter(T, INFINITY);
+  T = nextafter(T, INFINITY);  // smallest d2 whose rounded sqrt reaches r_phys
+  p.rc2_phys = T < p.rc2 ? T : p.rc2;
+  p.cu_delta = 2.0 * p.ba[0] - p.bb[0];
+  p.cucu_square = (p.aa[0] == 2.0 * p.ab[0]) ? 1 : 0;
+  p.cu_taylor = (fabs(p.cu_delta) * p.rcut < 1.0e-3) ? 1 : 0;
+}
+
 // evaluated on the host with libm, exactly like the reference does on every call.
 EamParams make_eam_params() {
   EamParams p{};
@@ -134,15 +147,44 @@ EamParams make_eam_params() {
     volatile double s = t1 + t2;
     p.rhocut[1] = t3 * s - 0.0;
   }
-  // physics threshold: d2 < rc2 (vesin) and sqrt(d2) < rcut (rgpot_cuh2.f90:522) in one compare
-  double T = p.rc2;
-  while (sqrt(T) >= p.rcut) T = nextafter(T, 0.0);
-  while (sqrt(nextafter(T, INFINITY)) < p.rcut) T = nextafter(T, INFINITY);
-  T = nextafter(T, INFINITY);  // smallest d2 whose rounded sqrt reaches rcut
-  p.rc2_phys = T < p.rc2 ? T : p.rc2;
-  p.cu_delta = 2.0 * p.ba[0] - p.bb[0];
-  p.cucu_square = (p.aa[0] == 2.0 * p.ab[0]) ? 1 : 0;
-  p.cu_taylor = (fabs(p.cu_delta) * p.rcut < 1.0e-3) ? 1 : 0;
+  finish_eam_params(p, p.rcut);  // sqrt(d2) < rcut, rgpot_cuh2.f90:522
+  return p;
+}
+
+// EAM-Al (rgpot_eam_al.f90:44-76) mapped onto slot 0 of the same tables; shifts evaluated on the
+// host with libm like the reference does (pair_shape(rcut), density_shape(rcut), :103-122).
+EamParams make_eam_al_params() {
+  EamParams p{};
+  p.gauge = -0.60647886749203;
+  p.da[0] = 2294.3609145535;
+  p.aa[0] = 3.0205380362464;
+  p.db[0] = -192.06894637533;
+  p.ab[0] = 1.5102690181232;
+  p.scale[0] = 0.87928364657088;
+  p.ba[0] = 3.3068828537934;
+  p.bb[0] = 6.6137657075868;
+  p.gamma[0] = 512.0;
+  const double c[8] = {4.4572157051836,  193.21775368064, -1173.6502684704, 4203.3500116196,
+                       -8785.1680280827, 10632.994102532, -6921.0410455328, 1875.2698365752};
+  memcpy(p.f_cu, c, sizeof c);
+  p.rcut = 7.1;
+  p.rc2 = p.rcut * p.rcut;
+  const double r = p.rcut;
+  {
+    volatile double t1 = p.da[0] * exp(-p.aa[0] * r);
+    volatile double t2 = p.db[0] * exp(-p.ab[0] * r);
+    p.phicut[0] = t1 + t2;
+  }
+  {
+    volatile double r2 = r * r;
+    volatile double r4 = r2 * r2;
+    volatile double r6 = r2 * r4;  // r**6 by square-and-multiply
+    volatile double s = exp(-p.ba[0] * r) + p.gamma[0] * exp(-p.bb[0] * r);
+    volatile double shape = r6 * s;
+    p.rhocut[0] = p.scale[0] * shape;
+  }
+  // every pair term vanishes from sqrt(0.9999) rcut on (rgpot_eam_al.f90:39-42, 94-99)
+  finish_eam_params(p, sqrt(0.9999) * p.rcut);
   return p;
 }
 
@@ -343,6 +385,9 @@ namespace {
 
 inline int div_up(long a, int b) { return (int)((a + b - 1) / b); }
 
+inline bool is_eam(int kind) { return kind == RGPOT_B200_CUH2 || kind == RGPOT_B200_EAM_AL; }
+inline double eam_rcut(int kind) { return kind == RGPOT_B200_EAM_AL ? 7.1 : 6.1; }
+
 int check_launch(RgpotB200Pot* pot, const char* what) {
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
@@ -491,7 +536,7 @@ bool plan_bricks(const RgpotB200Pot* pot, const Plan& pl, long n, double rc, boo
 template <int POT>
 int launch_brick(RgpotB200Pot* pot, const GatherArgs& ga, const BrickPlan& bp, const TileOut& to,
                  cudaStream_t st, const char* what) {
-  const unsigned smem = brick_smem_bytes(bp.cap_cand, bp.cap_list, bp.threads, POT == TILE_EAM_FORCE);
+  const unsigned smem = brick_smem_bytes(bp.cap_cand, bp.cap_list, bp.threads, tile_is_force(POT));
   auto go = [&](auto kern) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     kern<<<bp.nbricks, bp.threads, smem, st>>>(ga, bp, to);
@@ -526,10 +571,11 @@ int run_cell_path(RgpotB200Pot* pot, long n, const double* d_pos, const int* d_Z
                   double* d_E, const double* box, cudaStream_t st, const EmitArgs* emit,
                   bool allow_tile = true) {
   const int kind = pot->cfg.kind;
-  const bool eam = kind == RGPOT_B200_CUH2;
+  const bool eam = is_eam(kind);
+  const bool al = kind == RGPOT_B200_EAM_AL;
   const bool images = eam || pot->cfg.lj_all_images;
   Plan pl{};
-  const double rc = eam ? 6.1 : pot->lj_rc;
+  const double rc = eam ? eam_rcut(kind) : pot->lj_rc;
 
   CU_TRY(pot, pot->status.reserve(sizeof(Status)));
   Status init{};
@@ -666,7 +712,7 @@ int run_cell_path(RgpotB200Pot* pot, long n, const double* d_pos, const int* d_Z
   LAUNCH_CHECK(pot, "k_scatter");
   k_order_gather<<<div_up(n, 256), 256, 0, st>>>(d_pos, d_Z, pot->starts.as<int>(), pot->cell_of.as<int>(),
                                                  pot->order.as<int>(), pot->ashift.as<int>(), (int)n,
-                                                 eam ? 1 : (kind == RGPOT_B200_ZBL ? 2 : 0),
+                                                 kind == RGPOT_B200_CUH2 ? 1 : (kind == RGPOT_B200_ZBL ? 2 : 0),
                                                  pot->spos.as<double4>(), pot->scell.as<int>(), d_st);
   LAUNCH_CHECK(pot, "k_order_gather");
 
@@ -705,15 +751,23 @@ int run_cell_path(RgpotB200Pot* pot, long n, const double* d_pos, const int* d_Z
       d_part = pot->partials.as<double>();
       CU_TRY(pot, cudaMemsetAsync(d_part, 0, sizeof(double) * npart_used, st));
       TileOut to{d_F, d_part, pot->dfd.as<double>(), pot->eemb.as<double>(), d_st};
-      int ls = launch_brick<TILE_EAM_DENSITY>(pot, ga, bp, to, st, "k_brick<eam density>");
+      int ls = al ? launch_brick<TILE_AL_DENSITY>(pot, ga, bp, to, st, "k_brick<al density>")
+                  : launch_brick<TILE_EAM_DENSITY>(pot, ga, bp, to, st, "k_brick<eam density>");
       if (ls) return ls;
-      ls = launch_brick<TILE_EAM_FORCE>(pot, ga, bp, to, st, "k_brick<eam force>");
+      ls = al ? launch_brick<TILE_AL_FORCE>(pot, ga, bp, to, st, "k_brick<al force>")
+              : launch_brick<TILE_EAM_FORCE>(pot, ga, bp, to, st, "k_brick<eam force>");
       if (ls) return ls;
       ga.only_if_atom_shift = 1;
     }
-    k_eam_density<<<nblk, 128, 0, st>>>(ga, pot->dfd.as<double>(), pot->eemb.as<double>(), d_st);
-    LAUNCH_CHECK(pot, "k_eam_density");
-    k_eam_force<<<nblk, 128, 0, st>>>(ga, pot->dfd.as<double>(), pot->eemb.as<double>(), d_F, d_part);
+    if (al) {
+      k_eam_density<EAM_AL><<<nblk, 128, 0, st>>>(ga, pot->dfd.as<double>(), pot->eemb.as<double>(), d_st);
+      LAUNCH_CHECK(pot, "k_eam_density");
+      k_eam_force<EAM_AL><<<nblk, 128, 0, st>>>(ga, pot->dfd.as<double>(), pot->eemb.as<double>(), d_F, d_part);
+    } else {
+      k_eam_density<EAM_CUH2><<<nblk, 128, 0, st>>>(ga, pot->dfd.as<double>(), pot->eemb.as<double>(), d_st);
+      LAUNCH_CHECK(pot, "k_eam_density");
+      k_eam_force<EAM_CUH2><<<nblk, 128, 0, st>>>(ga, pot->dfd.as<double>(), pot->eemb.as<double>(), d_F, d_part);
+    }
     LAUNCH_CHECK(pot, "k_eam_force");
     return reduce_energy(pot, d_part, tile_ok ? npart_used : nblk, d_E, st);
   } else if (pl.geo == GEO_IMAGES) {
@@ -805,7 +859,8 @@ int launch_small(RgpotB200Pot* pot, size_t nsys, long nmax, const long long* d_o
   a.m_re = pot->cfg.morse_re;
   a.m_ecut = pot->morse_ecut;
   if (emit) a.emit = *emit;
-  if (pot->cfg.kind == RGPOT_B200_CUH2) {
+  if (is_eam(pot->cfg.kind)) {
+    const bool al = pot->cfg.kind == RGPOT_B200_EAM_AL;
     const size_t smem = eam_small_smem(nmax, maxnb);
     const int tpa = eam_small_tpa(nmax);
     int threads = (int)std::min<long>(448, ((nmax * tpa + 31) / 32) * 32);
@@ -824,10 +879,10 @@ int launch_small(RgpotB200Pot* pot, size_t nsys, long nmax, const long long* d_o
       return check_launch(pot, "k_eam_small");
     };
     switch (tpa) {
-      case 1: return launch(k_eam_small<1>);
-      case 2: return launch(k_eam_small<2>);
-      case 4: return launch(k_eam_small<4>);
-      default: return launch(k_eam_small<8>);
+      case 1: return al ? launch(k_eam_small<1, EAM_AL>) : launch(k_eam_small<1, EAM_CUH2>);
+      case 2: return al ? launch(k_eam_small<2, EAM_AL>) : launch(k_eam_small<2, EAM_CUH2>);
+      case 4: return al ? launch(k_eam_small<4, EAM_AL>) : launch(k_eam_small<4, EAM_CUH2>);
+      default: return al ? launch(k_eam_small<8, EAM_AL>) : launch(k_eam_small<8, EAM_CUH2>);
     }
   }
   const size_t smem = sizeof(double) * 3 * (size_t)nmax + sizeof(int) * (size_t)nmax + 16;
@@ -845,7 +900,7 @@ int launch_small(RgpotB200Pot* pot, size_t nsys, long nmax, const long long* d_o
 
 // can a system of n atoms run on the all-pairs kernels?
 bool small_eligible(const RgpotB200Pot* pot, long n) {
-  if (pot->cfg.kind == RGPOT_B200_CUH2) return n <= 512 && eam_small_maxnb(pot, n) > 0;
+  if (is_eam(pot->cfg.kind)) return n <= 512 && eam_small_maxnb(pot, n) > 0;
   if (pot->cfg.lj_all_images) return false;  // opt-in mode lives on the cell path only
   return n <= 2048;
 }
@@ -853,8 +908,8 @@ bool small_eligible(const RgpotB200Pot* pot, long n) {
 // status word -> ABI status + message.  Precedence follows rgpot_cuh2.f90:412-429:
 // classify (2) before the table build (1) before the coincidence guard (3).
 int map_flags(RgpotB200Pot* pot, unsigned flags, int bad_atom, int bad_z, const double* host_pos) {
-  const bool eam = pot->cfg.kind == RGPOT_B200_CUH2;
-  if (eam && (flags & kFlagForeignZ)) {
+  const bool eam = is_eam(pot->cfg.kind);
+  if (pot->cfg.kind == RGPOT_B200_CUH2 && (flags & kFlagForeignZ)) {
     char buf[256];
     snprintf(buf, sizeof buf,
              "rgpot_cuh2: atom %d has atomic number %d; this potential covers Cu (29) and H (1) only",
@@ -1019,7 +1074,7 @@ void rgpot_b200_default_config(int kind, RgpotB200Config* cfg) {
   cfg->kind = kind;
   cfg->device = -1;
   cfg->u0 = 1.0;
-  cfg->cutoff = kind == RGPOT_B200_CUH2 ? 6.1 : (kind == RGPOT_B200_MORSE ? 9.5 : (kind == RGPOT_B200_ZBL ? 2.5 : 15.0));
+  cfg->cutoff = is_eam(kind) ? eam_rcut(kind) : (kind == RGPOT_B200_MORSE ? 9.5 : (kind == RGPOT_B200_ZBL ? 2.5 : 15.0));
   cfg->zbl_cut_inner = 2.0;  // ZBLPot.hpp:29-32
   cfg->psi = 1.0;
   cfg->morse_De = 0.7102;  // MorsePot.hpp:31-36 (platinum)
@@ -1033,7 +1088,7 @@ RgpotB200Pot* rgpot_b200_create(const RgpotB200Config* cfg, char* errbuf, size_t
     return nullptr;
   };
   if (!cfg) return err("rgpot_b200_create: null config");
-  if (cfg->kind < RGPOT_B200_LJ || cfg->kind > RGPOT_B200_ZBL)
+  if (cfg->kind < RGPOT_B200_LJ || cfg->kind > RGPOT_B200_EAM_AL)
     return err("rgpot_b200_create: unknown potential kind");
   if (cfg->kind == RGPOT_B200_ZBL && (!(cfg->zbl_cut_inner > 0.0) || !(cfg->zbl_cut_inner < cfg->cutoff)))
     return err("ZBLPot: invalid cutoffs, require 0.0 < cut_inner < cut_global.");  // ZBLPot.cc:76-79
@@ -1068,12 +1123,13 @@ RgpotB200Pot* rgpot_b200_create(const RgpotB200Config* cfg, char* errbuf, size_t
     delete pot;
     return err("rgpot_b200_create: cannot create streams");
   }
-  if (cfg->kind == RGPOT_B200_CUH2) {
-    const EamParams p = make_eam_params();
+  if (is_eam(cfg->kind)) {
+    const EamParams p = cfg->kind == RGPOT_B200_EAM_AL ? make_eam_al_params() : make_eam_params();
     double tab[64];
     for (int j = 0; j < 64; ++j) tab[j] = exp2((double)j / 64.0);
     if (cudaMemcpyToSymbol(c_exp2tab, tab, sizeof tab) != cudaSuccess ||
-        cudaMemcpyToSymbol(c_eam, &p, sizeof p) != cudaSuccess) {
+        (cfg->kind == RGPOT_B200_EAM_AL ? cudaMemcpyToSymbol(c_eam_al, &p, sizeof p)
+                                        : cudaMemcpyToSymbol(c_eam, &p, sizeof p)) != cudaSuccess) {
       delete pot;
       return err("rgpot_b200_create: cannot upload the EAM coefficients");
     }
@@ -1207,7 +1263,7 @@ static int force_device_impl(RgpotB200Pot* pot, long n, const double* d_pos, con
     CU_TRY(pot, cudaMemcpyAsync(pot->b_off.p, off, sizeof off, cudaMemcpyHostToDevice, st));
     CU_TRY(pot, cudaMemcpyAsync(pot->b_boxes.p, hb, sizeof hb, cudaMemcpyHostToDevice, st));
     CU_TRY(pot, cudaMemsetAsync(pot->b_flags.p, 0, sizeof(unsigned), st));
-    const int maxnb = kind == RGPOT_B200_CUH2 ? eam_small_maxnb(pot, n) : 0;
+    const int maxnb = is_eam(kind) ? eam_small_maxnb(pot, n) : 0;
     int s = launch_small(pot, 1, n, pot->b_off.as<long long>(), pot->b_boxes.as<double>(), d_pos, d_Z,
                          d_F, d_E, pot->b_flags.as<unsigned>(), pot->b_bad.as<int>(), maxnb, st, emit);
     if (s) return s;
@@ -1279,9 +1335,10 @@ int rgpot_b200_force_device(RgpotB200Pot* pot, long nAtoms, const double* d_posi
   cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : pot->stream;
   pot->pend.active = false;
   if (nAtoms < 0 || nAtoms > kMaxAtoms) return fail(pot, kStatusArgs, "rgpot_b200: bad atom count");
-  const bool eam = pot->cfg.kind == RGPOT_B200_CUH2;
-  // reference early-outs: rgpot_cuh2_capi.f90:50 (natoms < 1), LJPot.cc:50-52, LJClusterPot.cc:43-45
-  const bool trivial = eam ? nAtoms < 1
+  const bool eam = pot->cfg.kind == RGPOT_B200_CUH2;  // (reads atomic numbers)
+  // reference early-outs: rgpot_cuh2_capi.f90:50 / rgpot_eam_al_capi.f90:50 (natoms < 1), LJPot.cc:50-52,
+  // LJClusterPot.cc:43-45
+  const bool trivial = is_eam(pot->cfg.kind) ? nAtoms < 1
                            : (nAtoms < 2 || (pot->cfg.kind != RGPOT_B200_LJ_CLUSTER && pot->cfg.kind != RGPOT_B200_ZBL && !(pot->cfg.cutoff > 0.0)));
   if (trivial) {
     if (nAtoms > 0) CU_TRY(pot, cudaMemsetAsync(d_forces, 0, sizeof(double) * 3 * nAtoms, st));
@@ -1369,8 +1426,8 @@ int rgpot_b200_force(RgpotB200Pot* pot, long nAtoms, const double* positions, co
     return fail(pot, kStatusArgs, "rgpot_b200_force: null buffer");
   CU_TRY(pot, cudaSetDevice(pot->device));
   if (nAtoms < 0 || nAtoms > kMaxAtoms) return fail(pot, kStatusArgs, "rgpot_b200: bad atom count");
-  const bool eam = pot->cfg.kind == RGPOT_B200_CUH2;
-  const bool trivial = eam ? nAtoms < 1
+  const bool eam = pot->cfg.kind == RGPOT_B200_CUH2;  // (reads atomic numbers)
+  const bool trivial = is_eam(pot->cfg.kind) ? nAtoms < 1
                            : (nAtoms < 2 || (pot->cfg.kind != RGPOT_B200_LJ_CLUSTER && pot->cfg.kind != RGPOT_B200_ZBL && !(pot->cfg.cutoff > 0.0)));
   if (trivial) return 0;
   const bool zbl = pot->cfg.kind == RGPOT_B200_ZBL;
@@ -1500,7 +1557,7 @@ static int batch_device_impl(RgpotB200Pot* pot, size_t nsys, const size_t* offse
                              const int* d_Z, const double* d_boxes, const double* h_boxes,
                              double* d_F, double* d_E, cudaStream_t st) {
   const int kind = pot->cfg.kind;
-  const bool eam = kind == RGPOT_B200_CUH2;
+  const bool eam = is_eam(kind);
   // plan: which systems fit the all-pairs kernel
   long nmax_small = 0;
   std::vector<int> small_ids, big_ids;
@@ -1713,7 +1770,7 @@ static int batch_pipeline(RgpotB200Pot* pot, size_t nsys, const size_t* rel, lon
   CU_TRY(pot, cudaEventRecord(pot->ev_ready, st0));
   for (auto& s : pot->pipe) CU_TRY(pot, cudaStreamWaitEvent(s, pot->ev_ready, 0));
 
-  const int maxnb = pot->cfg.kind == RGPOT_B200_CUH2 ? eam_small_maxnb(pot, nmax) : 0;
+  const int maxnb = is_eam(pot->cfg.kind) ? eam_small_maxnb(pot, nmax) : 0;
   size_t chunk = (nsys + 15) / 16;
   chunk = std::min<size_t>(std::max<size_t>(chunk, 256), 8192);
   const size_t nchunks = (nsys + chunk - 1) / chunk;
@@ -1940,6 +1997,30 @@ int rgpot_cuh2_force(int32_t natoms, const double* positions, const int32_t* ato
   }
   int s = rgpot_b200_force(g_cuh2, natoms, positions, atomic_numbers, forces, energy, nullptr, cell);
   if (s) g_last_fortran_error = g_cuh2->last_error;
+  return s;
+}
+
+// FortranPots.cc:26-28, rgpot_eam_al_capi.f90:31-58: no atomic numbers in this signature
+static RgpotB200Pot* g_eam_al = nullptr;
+
+int rgpot_eam_al_force(int32_t natoms, const double* positions, const double* cell, double* forces,
+                       double* energy) {
+  std::lock_guard<std::mutex> lk(g_cuh2_mu);
+  g_last_fortran_error.clear();
+  if (!g_eam_al) {
+    RgpotB200Config cfg;
+    rgpot_b200_default_config(RGPOT_B200_EAM_AL, &cfg);
+    char err[256] = {0};
+    g_eam_al = rgpot_b200_create(&cfg, err, sizeof err);
+    if (!g_eam_al) {
+      g_last_fortran_error = err;
+      if (energy) *energy = 0.0;
+      if (forces && natoms > 0) memset(forces, 0, sizeof(double) * 3 * (size_t)natoms);
+      return kStatusCuda;
+    }
+  }
+  int s = rgpot_b200_force(g_eam_al, natoms, positions, nullptr, forces, energy, nullptr, cell);
+  if (s) g_last_fortran_error = g_eam_al->last_error;
   return s;
 }
 

@@ -187,6 +187,7 @@ k_lj_gather(GatherArgs a, double* __restrict__ F, double* __restrict__ partials)
 // ---- CuH2 pass 1 + 2: density, then embedding energy and derivative ---------------------------
 // (rgpot_cuh2.f90:436-451; the embedding is per-atom work on a finished rho_i, so it rides at
 // the tail of the density kernel instead of paying a launch and an 8 B/atom round trip)
+template <int M>
 __global__ void __launch_bounds__(128)
 k_eam_density(GatherArgs a, double* __restrict__ dfd_sorted, double* __restrict__ eemb_sorted,
               Status* __restrict__ st) {
@@ -195,23 +196,24 @@ k_eam_density(GatherArgs a, double* __restrict__ dfd_sorted, double* __restrict_
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= a.n) return;
   const double4 pi = a.spos[i];
-  const double rc2_phys = c_eam.rc2_phys;
+  const double rc2_phys = eam_par<M>().rc2_phys;
   double rho = 0.0;
   bool coincident = false;
   auto body = [&](int, unsigned long long mj, double, double, double, double d2, int, int, int) {
     if (d2 == 0.0) coincident = true;  // dist <= 0 guard, rgpot_cuh2.f90:422-428
     if (!(d2 < rc2_phys)) return;      // :522 -- sqrt(d2) can round up onto the cutoff
-    rho += eam_density_entry(meta_species(mj), d2);
+    rho += eam_density_entry<M>(meta_species(mj), d2);
   };
   walk_dispatch<GEO_IMAGES>(a, i, pi, body);
   if (coincident) atomicOr(&st->flags, kFlagCoincident);
   double emb, demb;
-  eam_embed(meta_species((unsigned long long)__double_as_longlong(pi.w)), rho, emb, demb);
+  eam_embed<M>(meta_species((unsigned long long)__double_as_longlong(pi.w)), rho, emb, demb);
   dfd_sorted[i] = demb;
   eemb_sorted[i] = emb;
 }
 
 // ---- CuH2 pass 3: pair energy + whole force on each atom (rgpot_cuh2.f90:454-457) -----------
+template <int M>
 __global__ void __launch_bounds__(128)
 k_eam_force(GatherArgs a, const double* __restrict__ dfd_sorted,
             const double* __restrict__ eemb_sorted, double* __restrict__ F,
@@ -226,11 +228,11 @@ k_eam_force(GatherArgs a, const double* __restrict__ dfd_sorted,
     const unsigned long long mi = (unsigned long long)__double_as_longlong(pi.w);
     const int zi = meta_species(mi);
     const double dfd_i = dfd_sorted[i];
-    const double rc2_phys = c_eam.rc2_phys;
+    const double rc2_phys = eam_par<M>().rc2_phys;
     auto body = [&](int j, unsigned long long mj, double dx, double dy, double dz, double d2, int,
                     int, int) {
       if (!(d2 < rc2_phys)) return;
-      eam_force_entry(zi, meta_species(mj), dfd_i, dfd_sorted[j], dx, dy, dz, d2, e, fx, fy, fz);
+      eam_force_entry<M>(zi, meta_species(mj), dfd_i, dfd_sorted[j], dx, dy, dz, d2, e, fx, fy, fz);
     };
     walk_dispatch<GEO_IMAGES>(a, i, pi, body);
     e += eemb_sorted[i];

@@ -37,9 +37,24 @@ struct EamParams {
   double cu_delta;  // 2 beta_a(Cu) - beta_b(Cu)
   int cucu_square;  // alpha_A(CuCu) == 2 alpha_B(CuCu)
   int cu_taylor;    // |cu_delta| * rcut small enough for the 3-term series
+  double gauge;     // EAM-Al: g_transform (rgpot_eam_al.f90:47), 0 for CuH2
 };
 
+// Two analytic EAM models share the kernels.  EAM_CUH2: the Cu-H potential of rgpot_cuh2.f90.
+// EAM_AL: the single-species double-exponential aluminium of rgpot_eam_al.f90 -- the same pair /
+// density shapes as the Cu-Cu terms (slot 0 of every table) plus a gauge term g: phi carries
+// -2 g rho(r), the embedding +g rho (rgpot_eam_al.f90:159-171, 188-213).  Each model has its own
+// __constant__ block (handles of both kinds may run concurrently) selected at compile time, so the
+// coefficients stay immediate operands of the FP64 instructions.
+enum { EAM_CUH2 = 0, EAM_AL = 1 };
 __constant__ EamParams c_eam;
+__constant__ EamParams c_eam_al;
+
+template <int M>
+RB_D const EamParams& eam_par() {
+  if (M == EAM_AL) return c_eam_al;
+  return c_eam;
+}
 
 // ---- pair potentials on the LJ pair search ------------------------------------------------------
 // Pair energy U and fs with F_i += fs * (r_i - r_j) for one accepted pair at squared distance r2.
@@ -145,15 +160,17 @@ RB_D int pair_kind(int zi, int zj) { return zi + zj; }  // Cu=0, H=1: 0 CuCu, 1 
 struct CuDensityTerms {
   double ea, eb, r6;
 };
+template <int M = EAM_CUH2>
 RB_D CuDensityTerms cu_density_terms(double r) {
+  const EamParams& P = eam_par<M>();
   CuDensityTerms t;
-  t.ea = exp_fast(-c_eam.ba[0] * r);
-  if (c_eam.cu_taylor) {
-    const double z = c_eam.cu_delta * r;
+  t.ea = exp_fast(-P.ba[0] * r);
+  if (P.cu_taylor) {
+    const double z = P.cu_delta * r;
     const double corr = fma(z, fma(z, fma(z, 1.0 / 6.0, 0.5), 1.0), 1.0);
     t.eb = t.ea * t.ea * corr;
   } else {
-    t.eb = exp_fast(-c_eam.bb[0] * r);
+    t.eb = exp_fast(-P.bb[0] * r);
   }
   const double r2 = r * r;
   t.r6 = r2 * (r2 * r2);
@@ -161,10 +178,12 @@ RB_D CuDensityTerms cu_density_terms(double r) {
 }
 
 // density a neighbour of `species` deposits at distance r (shifted)   :228-262
+template <int M = EAM_CUH2>
 RB_D double eam_rho(int species, double r) {
-  if (species == 0) {
-    const CuDensityTerms t = cu_density_terms(r);
-    return c_eam.scale[0] * t.r6 * fma(c_eam.gamma[0], t.eb, t.ea) - c_eam.rhocut[0];
+  if (M == EAM_AL || species == 0) {
+    const EamParams& P = eam_par<M>();
+    const CuDensityTerms t = cu_density_terms<M>(r);
+    return P.scale[0] * t.r6 * fma(P.gamma[0], t.eb, t.ea) - P.rhocut[0];
   }
   // gamma_h = 0 and neta_h = 0: a single exponential (the reference multiplies exp(0) by zero)
   return c_eam.scale[1] * exp_fast(-c_eam.ba[1] * r) - c_eam.rhocut[1];
@@ -200,9 +219,23 @@ RB_D void eam_phi(int kind, double r, double rinv, double& phi, double& dphi_r) 
 
 // embedding energy and derivative, explicit powers and left-to-right sums like :298-370
 // (the Cu polynomial cancels by ~2 orders of magnitude; keep the reference's association)
+template <int M = EAM_CUH2>
 RB_D void eam_embed(int species, double x, double& emb, double& demb) {
   const double x2 = x * x, x3 = x2 * x, x4 = x3 * x, x5 = x4 * x;
-  if (species == 0) {
+  if (M == EAM_AL) {
+    // F = g rho + sum_k c_k rho^k, F' = g + c_1 + sum_{k>=2} k c_k rho^(k-1), summed in the
+    // reference's order (rgpot_eam_al.f90:188-213)
+    const double x6 = x5 * x, x7 = x6 * x, x8 = x7 * x;
+    const EamParams& P = eam_par<EAM_AL>();
+    const double* f = P.f_cu;
+    const double pw[8] = {x, x2, x3, x4, x5, x6, x7, x8};
+    emb = __dmul_rn(P.gauge, x);
+    demb = __dadd_rn(P.gauge, f[0]);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) emb = __dadd_rn(emb, __dmul_rn(f[k], pw[k]));
+#pragma unroll
+    for (int k = 1; k < 8; ++k) demb = __dadd_rn(demb, __dmul_rn(__dmul_rn(f[k], (double)(k + 1)), pw[k - 1]));
+  } else if (species == 0) {
     const double x6 = x5 * x, x7 = x6 * x, x8 = x7 * x;
     const double* f = c_eam.f_cu;
     emb = __dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(
@@ -232,34 +265,43 @@ RB_D void radial(double d2, double& r, double& rinv) {
 }
 
 // one accepted directed entry of the density pass (atom_density :518-529)
+template <int M = EAM_CUH2>
 RB_D double eam_density_entry(int zj, double d2) {
   double r, rinv;
   radial(d2, r, rinv);
-  return eam_rho(zj, r);
+  return eam_rho<M>(zj, r);
 }
 
 // one accepted directed entry of the force pass (atom_force :552-586).
 // vec = r_j - r_i + S.H ; returns half pair energy and accumulates f_i += w * vec.
+template <int M = EAM_CUH2>
 RB_D void eam_force_entry(int zi, int zj, double dfd_i, double dfd_j, double vx, double vy,
                           double vz, double d2, double& e, double& fx, double& fy, double& fz) {
   double r, rinv;
   radial(d2, r, rinv);
   double phi, w;
-  if ((zi | zj) == 0) {
-    // Cu-Cu (the bulk of every slab): every coefficient index is static, so the constants are
-    // operands of the FP64 instructions instead of separately loaded registers
-    const double eb = exp_fast(-c_eam.ab[0] * r);
-    const double ea = c_eam.cucu_square ? eb * eb : exp_fast(-c_eam.aa[0] * r);
-    const double t1 = c_eam.da[0] * ea;
-    const double t2 = c_eam.db[0] * eb;
-    phi = t1 + t2 - c_eam.phicut[0];
-    w = -fma(c_eam.aa[0], t1, c_eam.ab[0] * t2) * rinv;
-    const CuDensityTerms t = cu_density_terms(r);
-    const double g2 = c_eam.gamma[0] * t.eb;
-    const double t3 = c_eam.scale[0] * t.r6;
+  if (M == EAM_AL || (zi | zj) == 0) {
+    // Cu-Cu (the bulk of every slab) and Al-Al: every coefficient index is static, so the
+    // constants are operands of the FP64 instructions instead of separately loaded registers
+    const EamParams& P = eam_par<M>();
+    const double eb = exp_fast(-P.ab[0] * r);
+    const double ea = P.cucu_square ? eb * eb : exp_fast(-P.aa[0] * r);
+    const double t1 = P.da[0] * ea;
+    const double t2 = P.db[0] * eb;
+    phi = t1 + t2 - P.phicut[0];
+    w = -fma(P.aa[0], t1, P.ab[0] * t2) * rinv;
+    const CuDensityTerms t = cu_density_terms<M>(r);
+    const double g2 = P.gamma[0] * t.eb;
+    const double t3 = P.scale[0] * t.r6;
     const double raw = t3 * (t.ea + g2);
-    const double drho = (6.0 * raw * rinv - t3 * fma(c_eam.bb[0], g2, c_eam.ba[0] * t.ea)) * rinv;
-    w = fma(drho, dfd_i + dfd_j, w);  // the same density derivative acts at both ends
+    const double drho = (6.0 * raw * rinv - t3 * fma(P.bb[0], g2, P.ba[0] * t.ea)) * rinv;
+    if (M == EAM_AL) {
+      // gauge partner of the embedding's +g rho: phi -= 2 g rho(r), phi' -= 2 g rho'(r)
+      phi = fma(-2.0 * P.gauge, raw - P.rhocut[0], phi);
+      w = fma(drho, (dfd_i + dfd_j) - 2.0 * P.gauge, w);
+    } else {
+      w = fma(drho, dfd_i + dfd_j, w);  // the same density derivative acts at both ends
+    }
   } else {
     eam_phi(pair_kind(zi, zj), r, rinv, phi, w);
     const double drho_ij = eam_drho(zj, r, rinv);                         // what j deposits on i

@@ -197,9 +197,10 @@ struct SmallBoxF {  // FP32 mirror for the prefilter
 };
 
 
-template <int TPA>
+template <int TPA, int M>
 __global__ void __launch_bounds__(448, 2)
 k_eam_small(SmallArgs a) {
+  const EamParams& P = eam_par<M>();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ double sh32[32];
   __shared__ SmallBox sb;
@@ -235,7 +236,7 @@ k_eam_small(SmallArgs a) {
 
   exp_table_init();
   if (threadIdx.x == 0) {
-    small_box_init(a.boxes + 9 * (size_t)sys, c_eam.rcut, sb);
+    small_box_init(a.boxes + 9 * (size_t)sys, P.rcut, sb);
     blk_flags = sb.bad ? kFlagSingularBox : 0u;  // vesin: "the box matrix is not invertible"
     blk_bad[0] = INT_MAX;
     blk_bad[1] = 0;
@@ -249,8 +250,8 @@ k_eam_small(SmallArgs a) {
                   sb.H[6] == 0.0 && sb.H[7] == 0.0;
       // FP32 error of the wrapped fractional separation (~3 ulp of 1) times the cell size,
       // plus the rounding of the Cartesian norm: generous, the exact test follows anyway
-      const double margin = 1.0e-6 * hmax + 1.0e-5 * c_eam.rcut;
-      const double thr = c_eam.rcut + margin;
+      const double margin = 1.0e-6 * hmax + 1.0e-5 * P.rcut;
+      const double thr = P.rcut + margin;
       sbf.thr2 = (float)(thr * thr * (1.0 + 1.0e-6));
     }
   }
@@ -270,7 +271,7 @@ k_eam_small(SmallArgs a) {
     pos3[3 * i + 1] = y;
     pos3[3 * i + 2] = z;
     cnt[i] = 0;
-    const int zn = a.Z[base + i];
+    const int zn = M == EAM_AL ? 29 : a.Z[base + i];  // EAM-Al is single-species: atomic numbers are not read
     int sp = 0;
     if (zn == 29) {
       sp = 0;
@@ -321,7 +322,7 @@ k_eam_small(SmallArgs a) {
     return;
   }
 
-  const double rc2 = c_eam.rc2;
+  const double rc2 = P.rc2;
   const bool wrapped_atoms = (blk_flags & kFlagAtomShift) != 0;
 
   // ---- phase B
@@ -502,7 +503,7 @@ k_eam_small(SmallArgs a) {
   const int sub = threadIdx.x % TPA;
   const int grp = threadIdx.x / TPA;
   const int ngrp = blockDim.x / TPA;
-  const double rc2_phys = c_eam.rc2_phys;
+  const double rc2_phys = P.rc2_phys;
 
   double e = 0.0;
   // ---- phase D: density, embedding
@@ -527,7 +528,7 @@ k_eam_small(SmallArgs a) {
         const double d2 = xnorm2(vx, vy, vz);
         if (d2 == 0.0) coincident = true;  // dist <= 0 guard, rgpot_cuh2.f90:422-428
         if (!(d2 < rc2_phys)) continue;    // :522
-        rho += eam_density_entry((int)(en >> 14), d2);
+        rho += eam_density_entry<M>((int)(en >> 14), d2);
       }
     }
 #pragma unroll
@@ -535,7 +536,7 @@ k_eam_small(SmallArgs a) {
     if (coincident) atomicOr(&blk_flags, kFlagCoincident);
     if (vi && sub == 0) {
       double emb, demb;
-      eam_embed(spc[i], rho, emb, demb);
+      eam_embed<M>(spc[i], rho, emb, demb);
       dfd[i] = demb;
       eatom[i] = emb;
     }
@@ -573,7 +574,7 @@ k_eam_small(SmallArgs a) {
         const double vz = xadd(xsub(pj[2], zi_), sv[2]);
         const double d2 = xnorm2(vx, vy, vz);
         if (!(d2 < rc2_phys)) continue;
-        eam_force_entry(zi, (int)(en >> 14), dfd_i, dfd[j], vx, vy, vz, d2, ep, fx, fy, fz);
+        eam_force_entry<M>(zi, (int)(en >> 14), dfd_i, dfd[j], vx, vy, vz, d2, ep, fx, fy, fz);
       }
     }
 #pragma unroll

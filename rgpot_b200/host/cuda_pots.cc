@@ -39,7 +39,9 @@ Engine::Engine(int kind, const LJCudaConfig &c) {
   cfg.device = c.device;
   Fnv fp;
   fp.u64(kKernelVersion);
-  if (kind != RGPOT_B200_CUH2) {
+  if (kind == RGPOT_B200_EAM_AL) {
+    fp.u64((uint64_t)kind);  // parameter-free like CuH2; the kind keeps the two keys apart
+  } else if (kind != RGPOT_B200_CUH2) {
     cfg.u0 = c.u0;
     cfg.cutoff = c.cutoff;
     cfg.psi = c.psi;

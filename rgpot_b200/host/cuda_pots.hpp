@@ -106,6 +106,8 @@ private:
 RGPOT_B200_POT_CLASS(LJCudaPot, LJ, RGPOT_B200_LJ, "LJ", true);
 RGPOT_B200_POT_CLASS(LJClusterCudaPot, LJCluster, RGPOT_B200_LJ_CLUSTER, "LJCluster", false);
 RGPOT_B200_POT_CLASS(CuH2CudaPot, CuH2, RGPOT_B200_CUH2, "CuH2", true);
+/// fortranpots::EAMAlPot on the engine (fortran/FortranPots.hpp:43): atomic numbers are not read.
+RGPOT_B200_POT_CLASS(EAMAlCudaPot, EAMAl, RGPOT_B200_EAM_AL, "EAM-Al", true);
 
 #undef RGPOT_B200_POT_CLASS
 

@@ -181,6 +181,25 @@ int main() {
     CHECK(rgpot::ZBLCudaPot{wide}.paramsKey() != zbl.paramsKey());
   }
 
+  {  // EAM aluminium matches the eOn reference, CppCore/tests/FortranPotsTest.cc:135-144
+    rgpot::EAMAlCudaPot al;
+    AtomMatrix fcc{{7.97500, 7.97500, 7.97500}, {10.00000, 10.00000, 7.97500}, {10.00000, 7.97500, 10.00000},
+                   {7.97500, 10.00000, 10.00000}};
+    const std::vector<int> types(4, 13);
+    std::array<std::array<double, 3>, 3> cube{{{20.0, 0.0, 0.0}, {0.0, 20.0, 0.0}, {0.0, 0.0, 20.0}}};
+    auto [e, f, v] = al(fcc, types, cube);
+    (void)v;
+    CHECK(within_rel(e, -5.217864, 1e-4));
+    double worst = 0.0, net[3] = {0, 0, 0};
+    for (size_t i = 0; i < 4; ++i) {
+      worst = std::max(worst, std::sqrt(f(i, 0) * f(i, 0) + f(i, 1) * f(i, 1) + f(i, 2) * f(i, 2)));
+      for (size_t j = 0; j < 3; ++j) net[j] += f(i, j);
+    }
+    CHECK(within_rel(worst, 0.968647, 1e-3));
+    CHECK(std::fabs(net[0]) < 1e-9 && std::fabs(net[1]) < 1e-9 && std::fabs(net[2]) < 1e-9);
+    CHECK(al.get_type() == rgpot::PotType::EAMAl);
+  }
+
   std::printf(failures ? "test_host: %d FAILURES\n" : "test_host: ok\n", failures);
   return failures ? 1 : 0;
 }

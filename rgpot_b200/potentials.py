@@ -54,6 +54,7 @@ class PotType(Enum):
     Morse = 8
     LJCluster = 9
     ZBL = 10
+    EAMAl = 15
 
 
 @dataclass
@@ -124,6 +125,8 @@ def _as_positions(positions) -> np.ndarray:
 
 
 def _as_types(atom_types, n: int) -> np.ndarray:
+    if atom_types is None:  # potentials that do not read atomic numbers (LJ, Morse, EAM-Al)
+        return np.zeros(n, dtype=np.int32)
     arr = np.asarray(atom_types)
     if arr.ndim != 1 or arr.shape[0] != n:
         raise ValueError("atom_types length must match n_atoms")
@@ -155,7 +158,7 @@ class _EnginePot:
             cfg.cutoff = float(morse.cutoff)
         elif self._kind == _lib.KIND_ZBL:
             cfg.zbl_cut_inner, cfg.cutoff = float(zbl.cut_inner), float(zbl.cut_global)
-        elif self._kind != _lib.KIND_CUH2:
+        elif self._kind not in (_lib.KIND_CUH2, _lib.KIND_EAM_AL):
             cfg.u0, cfg.cutoff, cfg.psi = float(u0), float(cutoff), float(psi)
             cfg.lj_all_images = int(bool(lj_all_images))
         self._cfg = cfg
@@ -185,6 +188,8 @@ class _EnginePot:
     def paramsKey(self) -> int:
         if self._kind == _lib.KIND_CUH2:
             return _fnv1a([struct.pack("<Q", _KERNEL_VERSION)])
+        if self._kind == _lib.KIND_EAM_AL:  # parameter-free like CuH2; the kind keeps the two apart
+            return _fnv1a([struct.pack("<Q", _KERNEL_VERSION), struct.pack("<i", self._kind)])
         c = self._cfg
         if self._kind == _lib.KIND_ZBL:  # ZBLPot.cc:80-84
             return _fnv1a([struct.pack("<Q", _KERNEL_VERSION), struct.pack("<d", c.zbl_cut_inner),
@@ -412,6 +417,16 @@ class CuH2Pot(_EnginePot):
     """Cu-H embedded-atom potential (fortranpots::CuH2Pot, FortranPots.hpp:29-45)."""
 
     _kind, _label, _type = _lib.KIND_CUH2, "CuH2", PotType.CuH2
+
+    def __init__(self, device: int = -1):
+        super().__init__(device=device)
+
+
+class EAMAlPot(_EnginePot):
+    """Double-exponential embedded-atom aluminium (fortranpots::EAMAlPot, FortranPots.hpp:43,
+    rgpot_eam_al.f90).  Single species: atomic numbers are accepted and not read."""
+
+    _kind, _label, _type = _lib.KIND_EAM_AL, "EAM-Al", PotType.EAMAl
 
     def __init__(self, device: int = -1):
         super().__init__(device=device)

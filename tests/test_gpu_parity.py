@@ -637,3 +637,63 @@ def test_core_callback_errors(cuh2):
         core.calculate(cuh2, np.random.default_rng(0).random((4, 3)) * 5, np.array([29, 29, 8, 1], np.int32),
                        np.eye(3) * 20)
     assert ei.value.status == 2 and "atom 3 has atomic number 8" in str(ei.value)
+
+
+# ------------------------------------------------------------- EAM-Al
+AL_FCC = np.array([[7.975, 7.975, 7.975], [10.0, 10.0, 7.975], [10.0, 7.975, 10.0], [7.975, 10.0, 10.0]])
+
+
+def _al_crystal(cells, seed, rattle=0.08):
+    a = 4.05
+    pos = workloads._fcc(cells, a) + np.random.default_rng(seed).normal(0, rattle, (4 * cells ** 3, 3))
+    return pos, np.eye(3) * cells * a
+
+
+def test_eam_al_eon_pin_and_dropin_symbol():
+    """FortranPotsTest.cc:135-144 through the class and through rgpot_eam_al_force, the symbol
+    FortranPots.cc:26-28 binds."""
+    import ctypes as C
+
+    from rgpot_b200 import _lib
+    pot = rgpot_b200.EAMAlPot()
+    e, f, v = pot(AL_FCC, np.full(4, 13, np.int32), np.eye(3) * 20.0)
+    assert e == pytest.approx(-5.217864, rel=1e-4) and v == 0.0
+    assert np.sqrt((f ** 2).sum(1)).max() == pytest.approx(0.968647, rel=1e-3)
+    assert np.abs(f.sum(0)).max() < 1e-9
+    assert pot.get_type() == rgpot_b200.PotType.EAMAl
+    lib = _lib.lib()
+    F = np.zeros((4, 3))
+    e2 = C.c_double()
+    cell = np.ascontiguousarray(np.eye(3) * 20.0)
+    st = lib.rgpot_eam_al_force(4, AL_FCC.ctypes.data, cell.ctypes.data, F.ctypes.data, C.byref(e2))
+    assert st == 0 and e2.value == e and np.array_equal(F, f)
+
+
+@pytest.mark.parametrize("cells,path,opts", [
+    (2, 2, {}), (3, 2, {}), (3, 1, {}),            # boxes narrower than two cutoffs: several images per pair
+    (4, 2, {}), (4, 1, {}), (6, 1, {}),
+    (10, 1, {}), (10, 1, {"fine": 1}), (10, 1, {"brick_list": 5, "brick_slack": -50}),
+])
+def test_eam_al_vs_oracle(oracle, cells, path, opts):
+    pos, box = _al_crystal(cells, cells + path)
+    e_o, f_o = oracle.eam_al_force(pos, box)
+    pot = rgpot_b200.EAMAlPot()
+    pot.set_path(path)
+    _with_options(pot, opts)
+    e, f, _ = pot(pos, None, box)
+    assert_energy(e, e_o, (cells, path, opts))
+    assert_forces(f, f_o, (cells, path, opts))
+
+
+def test_eam_al_batch_and_coexistence_with_cuh2(cuh2, oracle, golden):
+    """EAM-Al and CuH2 handles alive together: each model has its own constant block."""
+    al = rgpot_b200.EAMAlPot()
+    systems = [(_al_crystal(4, s)[0], None, _al_crystal(4, s)[1]) for s in range(5)]
+    out = al.forceBatch(systems)
+    g = golden("cuh2_pin4.json")
+    e_cu, _, _ = cuh2(np.array(g["positions"]), np.array(g["Z"], np.int32), np.array(g["box"]).reshape(3, 3))
+    assert e_cu == pytest.approx(g["pin_energy"], rel=1e-10)
+    for (e, f, _), (p, _, b) in zip(out, systems):
+        e_o, f_o = oracle.eam_al_force(p, b)
+        assert_energy(e, e_o)
+        assert_forces(f, f_o)

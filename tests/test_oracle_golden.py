@@ -183,3 +183,47 @@ def test_zbl_pins(oracle):
     assert abs(e_cut) < 1e-12 and np.abs(f_cut).max() < 1e-12
     e_far, f_far, n_far = oracle.zbl_force([[5.0, 5.0, 5.0], [8.0, 5.0, 5.0]], [14, 79])
     assert n_far == 0 and e_far == 0.0 and not f_far.any()
+
+
+# ------------------------------------------------------------------------------------- EAM-Al
+AL_FCC = np.array([[7.975, 7.975, 7.975], [10.0, 10.0, 7.975], [10.0, 7.975, 10.0], [7.975, 10.0, 10.0]])
+CUBE20 = np.eye(3) * 20.0
+
+
+def test_eam_al_matches_the_eon_reference(oracle):
+    # CppCore/tests/FortranPotsTest.cc:135-144 (eOn EAMAlTest fixture al_fcc in a 20 A cube)
+    e, f = oracle.eam_al_force(AL_FCC, CUBE20)
+    assert e == pytest.approx(-5.217864, rel=1e-4)
+    assert np.sqrt((f ** 2).sum(1)).max() == pytest.approx(0.968647, rel=1e-3)
+    assert np.abs(f.sum(0)).max() < 1e-6  # requireNoNetForce
+
+
+def test_eam_al_physics_checks(oracle):
+    # the checks of CppCore/rgpot/fortran/test_eam_al.f90, re-run against the restatement:
+    # translation invariance, vanishing net force, analytic forces against central differences,
+    # every pair term zero from the truncation radius on
+    rng = np.random.default_rng(5)
+    a = 4.05
+    cell = np.eye(3) * 3 * a
+    pos = (workloads._fcc(3, a) + rng.normal(0, 0.08, (108, 3)))
+    e0, f0 = oracle.eam_al_force(pos, cell)
+    e1, f1 = oracle.eam_al_force(pos + np.array([0.37, -1.21, 2.6]), cell)
+    assert e1 == pytest.approx(e0, rel=1e-12) and np.abs(f1 - f0).max() < 1e-10
+    assert np.abs(f0.sum(0)).max() < 1e-10
+    h = 1e-5
+    for (i, c) in [(0, 0), (17, 1), (55, 2)]:
+        p, m = pos.copy(), pos.copy()
+        p[i, c] += h
+        m[i, c] -= h
+        fd = -(oracle.eam_al_force(p, cell)[0] - oracle.eam_al_force(m, cell)[0]) / (2 * h)
+        assert fd == pytest.approx(f0[i, c], abs=2e-6)
+    rt = np.sqrt(0.9999) * 7.1
+    for which in range(4):
+        assert oracle.eam_al_scalar(which, rt) == 0.0 and oracle.eam_al_scalar(which, 7.1) == 0.0
+        assert oracle.eam_al_scalar(which, np.nextafter(rt, 0.0)) != 0.0
+    # F(rho) = g rho + sum c_k rho^k and its derivative (rgpot_eam_al.f90:189-213)
+    g, c = -0.60647886749203, [4.4572157051836, 193.21775368064, -1173.6502684704, 4203.3500116196,
+                               -8785.1680280827, 10632.994102532, -6921.0410455328, 1875.2698365752]
+    for rho in (0.05, 0.4, 1.0):
+        assert oracle.eam_al_scalar(4, rho) == pytest.approx(g * rho + sum(ck * rho ** (k + 1) for k, ck in enumerate(c)), rel=1e-13)
+        assert oracle.eam_al_scalar(5, rho) == pytest.approx(g + sum((k + 1) * ck * rho ** k for k, ck in enumerate(c)), rel=1e-13)
