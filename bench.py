@@ -179,6 +179,43 @@ def cpu_reference_rate(budget_s=12.0, procs=None, configs_per_proc=4000):
             "wall_s": wall}
 
 
+def cpu_side_baseline(name):
+    """Reference CPU path for the single-system side workloads, on a bounded sample of the same
+    recipe, in a fresh interpreter (this process already holds a CUDA context).  SURVEY 8(d):
+    LJ = the reference's own LJPot object (O(N^2) scan, single thread: it has no threading);
+    CuH2 = vendored vesin + the restated Fortran passes, one process."""
+    code = (
+        "import json, sys, time; sys.path.insert(0, %r)\n"
+        "import numpy as np\n"
+        "from oracle import pyoracle as po\n"
+        "from rgpot_b200 import workloads\n"
+        "name = %r\n"
+        "ref = po.ref_available()\n"
+        "best, natoms = 1e30, 0\n"
+        "for rep in range(4):\n"
+        "    # a fresh geometry (a different atom count) per repetition: the reference's PairListCache /\n"
+        "    # vesin Verlet list must not turn a repetition into a cached O(pairs) walk\n"
+        "    if name == 'lj_fluid_1m':\n"
+        "        pos, Z, box = workloads.lj_fluid(16384 + 8 * rep)\n"
+        "        f = (lambda: po.ref_lj_force(pos, box, 1.0, 2.5, 1.0)) if ref else (lambda: po.lj_force(pos, box, 1.0, 2.5, 1.0))\n"
+        "        what = '16 384-atom LJ fluids of the same recipe (density, cutoff), cold O(N^2) scan of LJPot.cc, 1 thread'\n"
+        "    else:\n"
+        "        pos, Z, box = workloads.cu_slab_triclinic(cells=16, n_h2_side=6 + rep)\n"
+        "        f = lambda: po.cuh2_force(pos, Z, box, use_ref=ref)\n"
+        "        what = '16 400-atom triclinic Cu slabs + H2 of the same recipe, vesin + restated rgpot_cuh2.f90, 1 process'\n"
+        "    t0 = time.perf_counter(); f(); dt = time.perf_counter() - t0\n"
+        "    if rep and dt / len(pos) < best: best, natoms = dt / len(pos), len(pos)\n"
+        "print(json.dumps({'value': 1.0 / best, 'unit': 'atom-evals/s', 'cores': 1,\n"
+        "                  'kind': 'reference' if ref else 'port',\n"
+        "                  'sample': what + ', best of 3 cold calls: %%.3f s for %%d atoms' %% (best * natoms, natoms)}))\n"
+    ) % (ROOT, name)
+    try:
+        out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=240)
+        return json.loads(out.stdout.strip().splitlines()[-1])
+    except Exception as exc:  # noqa: BLE001 -- a missing baseline must not lose the GPU numbers
+        return {"value": None, "unit": UNIT, "cores": 1, "kind": "unavailable", "sample": repr(exc)[:200]}
+
+
 # ------------------------------------------------------------------------------- our workloads
 def run_cuh2_batch(args, world, rank, local):
     import torch
@@ -346,7 +383,7 @@ def run_single_system(args, name, local):
     return {"workload": name, "n_atoms": n, "value": value, "unit": UNIT, "ms_per_step": total_ms / steps,
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(pos.nbytes + Z.nbytes),
                     "d2h_bytes_per_step": int(pos.nbytes + 8)},
-            "gpu_launches": launches, "energy": e,
+            "gpu_launches": launches, "energy": e, "cpu_baseline": cpu_side_baseline(name),
             "roofline": {"bound": "fp64", "kernel": kernel, "achieved": tf, "peak": fp64_peak,
                          "unit": "TFLOP/s", "frac": tf / fp64_peak if fp64_peak else None,
                          "note": "whole step (cell build + force kernels) timed, flops of the path"},
