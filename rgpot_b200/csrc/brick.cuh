@@ -36,7 +36,7 @@ constexpr bool tile_is_density(int pot) { return pot == TILE_EAM_DENSITY || pot 
 constexpr bool tile_is_force(int pot) { return pot == TILE_EAM_FORCE || pot == TILE_AL_FORCE; }
 constexpr int tile_model(int pot) { return pot >= TILE_AL_DENSITY ? EAM_AL : EAM_CUH2; }
 
-constexpr int kBrickMaxThreads = 256;
+constexpr int kBrickMaxThreads = 384;  // 2 blocks of 384 or 3 of 256 per SM at <= 85 registers
 constexpr int kBrickMaxHalo = 512;  // (4 + 2*2)^3
 constexpr int kBrickMaxCells = 64;
 constexpr int kShiftCodes = 125;    // image counts q in [-2, 2]^3
@@ -120,7 +120,7 @@ __device__ __noinline__ void brick_slow_atom(const GatherArgs& a, const TileOut&
 
 // ---- the brick kernel ------------------------------------------------------------------------
 template <int POT, int TPA>
-__global__ void __launch_bounds__(kBrickMaxThreads, 3)
+__global__ void __launch_bounds__(kBrickMaxThreads, 2)
 k_brick(const __grid_constant__ GatherArgs a, const __grid_constant__ BrickPlan bp,
         const __grid_constant__ TileOut o) {
   extern __shared__ __align__(16) unsigned char smem_raw[];

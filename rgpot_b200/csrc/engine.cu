@@ -492,9 +492,10 @@ bool plan_bricks(const RgpotB200Pot* pot, const Plan& pl, long n, double rc, boo
         if (pot->opt_list) {
           bp.cap_list = pot->opt_list;
         } else {
-          const int blocks = std::min(3, blocks_per_sm(least));  // registers allow three blocks of 256
+          const int by_regs = std::max(1, 768 / threads);  // 85 registers per thread
+          const int blocks = std::min(by_regs, blocks_per_sm(least));
           for (int c = want; c > least; c -= 2) {
-            if (std::min(3, blocks_per_sm(c)) >= blocks) {
+            if (std::min(by_regs, blocks_per_sm(c)) >= blocks) {
               bp.cap_list = c;
               break;
             }
