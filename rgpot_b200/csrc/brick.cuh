@@ -172,6 +172,13 @@ k_brick(const __grid_constant__ GatherArgs a, const __grid_constant__ BrickPlan 
   }
   double e_thr = 0.0;
   bool coincident = false;
+#ifdef RB_BRICK_TIMING
+  long long t_mark = clock64();
+  unsigned long long t_acc[4] = {0, 0, 0, 0};
+#define RB_TICK(slot) do { const long long t_now = clock64(); t_acc[slot] += (unsigned long long)(t_now - t_mark); t_mark = t_now; } while (0)
+#else
+#define RB_TICK(slot) do { } while (0)
+#endif
 
   // A brick whose halo exceeds the staged capacity (a locally dense region) is cut in two and the
   // halves are done one after the other; every atom sees the same candidates in the same order
@@ -320,6 +327,7 @@ k_brick(const __grid_constant__ GatherArgs a, const __grid_constant__ BrickPlan 
         if (c < nbc) bc_astart[c + 1] = (unsigned short)run;
       }
     }
+    RB_TICK(0);
     // brick origin for the FP32 offsets (any nearby point serves; it only has to be common)
     double org[3] = {0.0, 0.0, 0.0};
 #pragma unroll
@@ -349,6 +357,7 @@ k_brick(const __grid_constant__ GatherArgs a, const __grid_constant__ BrickPlan 
       }
     }
     __syncthreads();
+    RB_TICK(1);
     const int natoms = bc_astart[nbc];
 
     const double rc2 = kPairGeo ? a.lj.rc2 : a.rc2;
@@ -389,6 +398,23 @@ k_brick(const __grid_constant__ GatherArgs a, const __grid_constant__ BrickPlan 
           const int hlow = hc - (bp.ns[2] * hd[1] + bp.ns[1]) * hd[0] - bp.ns[0];  // stencil corner
           int ry = sub % nry, rz = sub / nry, row = sub;
           int s = 0, s1 = 0;  // cursor in the current stencil row
+          // bounds of the next row, fetched one row ahead (their shared-memory latency then hides
+          // behind the candidates of the current row)
+          int ns0 = 0, ns1 = 0;
+          auto fetch_row = [&]() {
+            if (row < nrows) {
+              const int h0 = hlow + (rz * hd[1] + ry) * hd[0];
+              ns0 = hstart[h0];
+              ns1 = hstart[h0 + nrx];
+            }
+            row += TPA;
+            ry += TPA;
+            while (ry >= nry) {
+              ry -= nry;
+              ++rz;
+            }
+          };
+          fetch_row();
           bool more = true;
           // rounds of search-then-physics: one round unless the private list fills up first
           do {
@@ -396,24 +422,21 @@ k_brick(const __grid_constant__ GatherArgs a, const __grid_constant__ BrickPlan 
             unsigned lsa = lsa0;
             for (;;) {
               if (s == s1) {  // next row: 2 ns + 1 cells that are contiguous in the staged order
-                if (row >= nrows) {
+                if (row - TPA >= nrows) {
                   more = false;
                   break;
                 }
-                const int h0 = hlow + (rz * hd[1] + ry) * hd[0];
-                s = hstart[h0];
-                s1 = hstart[h0 + nrx];
-                row += TPA;
-                ry += TPA;
-                while (ry >= nry) {
-                  ry -= nry;
-                  ++rz;
-                }
+                s = ns0;
+                s1 = ns1;
+                fetch_row();
                 if (s == s1) continue;
               }
-              const int room = bp.cap_list - (int)(((float)(lsa - lsa0) + 0.5f) * inv_lstride);
-              const int se = min(s1, s + room);
-              if (se == s) break;  // list full: evaluate it, then come back
+              int se = s1;
+              if (lsa + (unsigned)(s1 - s) * lstride > lsa_end) {  // the row may not fit: count the free slots
+                const int room = bp.cap_list - (int)(((float)(lsa - lsa0) + 0.5f) * inv_lstride);
+                se = min(s1, s + room);
+                if (se == s) break;  // list full: evaluate it, then come back
+              }
 #pragma unroll 4
               for (; s < se; ++s) {
                 const float4 f = c32[s];
@@ -423,6 +446,7 @@ k_brick(const __grid_constant__ GatherArgs a, const __grid_constant__ BrickPlan 
               }
               if (s < s1) break;  // the row continues after the list has been evaluated
             }
+            RB_TICK(2);
             // ---- physics: exact FP64 test and pair terms for the listed candidates ------------------------
             for (unsigned la = lsa0; la < lsa; la += lstride) {
               unsigned short s16;
@@ -470,6 +494,7 @@ k_brick(const __grid_constant__ GatherArgs a, const __grid_constant__ BrickPlan 
                 }
               }
             }
+            RB_TICK(3);
           } while (more);
         }
         __syncwarp();
@@ -507,6 +532,10 @@ k_brick(const __grid_constant__ GatherArgs a, const __grid_constant__ BrickPlan 
     __syncthreads();
   }
 
+#ifdef RB_BRICK_TIMING
+  if (lane == 0)
+    for (int k = 0; k < 4; ++k) atomicAdd(&o.st->prof[k], t_acc[k]);
+#endif
   if (kDensity) {
     if (coincident) atomicOr(&o.st->flags, kFlagCoincident);
   } else {

@@ -33,6 +33,7 @@ struct Status {
   int slow_atoms;      // diagnostics: atoms a brick kernel evaluated on its slow path
   int max_halo;        // feedback: largest halo population a brick kernel met (sizes the next call)
   int pad[3];
+  unsigned long long prof[4];  // -DRB_BRICK_TIMING builds: warp-clock sums of setup / stage / search / physics
 };
 
 // Geometry of one periodic (or free) cell, prepared on the host with the reference's own

@@ -215,6 +215,7 @@ struct RgpotB200Pot {
   long opt_fine_min = 20000;  // atoms from which half-cutoff cells are used
   long launches = 0;
   long slow_atoms = 0;  // diagnostics of the last single-system call (brick slow path)
+  long prof[4] = {0, 0, 0, 0};  // RB_BRICK_TIMING builds only
   // feedback from the brick kernels: the largest halo population seen for a given (atoms, grid,
   // brick) signature sizes the staged capacity of the next call with that signature
   struct BrickMemo {
@@ -1156,6 +1157,7 @@ long rgpot_b200_stat(RgpotB200Pot* pot, const char* key) {
   if (!pot || !key) return -1;
   if (strcmp(key, "launches") == 0) return pot->launches;
   if (strcmp(key, "slow_atoms") == 0) return pot->slow_atoms;
+  if (strncmp(key, "prof", 4) == 0 && key[4] >= '0' && key[4] <= '3') return pot->prof[key[4] - '0'];
   return -1;
 }
 
@@ -1308,6 +1310,7 @@ static int finish_single(RgpotB200Pot* pot, long n, const double* d_pos, const i
     }
     flags = stt.flags;
     pot->slow_atoms = stt.slow_atoms;
+    for (int k = 0; k < 4; ++k) pot->prof[k] = (long)stt.prof[k];
     if (stt.max_halo > 0 && pot->memo_pending.n >= 0) {  // brick kernels ran: remember what they met
       const bool same = pot->memo.n == pot->memo_pending.n && !memcmp(pot->memo.nc, pot->memo_pending.nc, sizeof pot->memo.nc) &&
                         !memcmp(pot->memo.bd, pot->memo_pending.bd, sizeof pot->memo.bd);

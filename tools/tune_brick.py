@@ -58,6 +58,11 @@ def main():
         print(f"{which} {st:>18}  min {min(ms):.4f} ms  med {float(np.median(ms)):.4f} ms  "
               f"{n / np.median(ms) / 1e6:.1f} M atom-evals/ms... E={float(d_E.item()):.12e}  "
               f"max|dF| vs first {float(np.abs(F - ref_F).max()):.2e}  slow_atoms {pot.stat('slow_atoms')}", flush=True)
+        prof = [pot.stat(f"prof{k}") for k in range(4)]
+        if sum(prof) > 0:  # an -DRB_BRICK_TIMING build (RGPOT_B200_ENGINE=...): warp-clock shares of the phases
+            tot = float(sum(prof))
+            print("    warp clocks: setup %.1f%%  stage %.1f%%  search %.1f%%  physics %.1f%%" %
+                  tuple(100.0 * p / tot for p in prof), flush=True)
 
 
 if __name__ == "__main__":
