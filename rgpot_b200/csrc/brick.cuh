@@ -26,6 +26,8 @@
 // gather walk -- slower, same results, no host round trip.
 #pragma once
 
+#include <cuda_fp16.h>
+
 #include "gather.cuh"
 
 namespace rb {
@@ -64,7 +66,7 @@ struct BrickPlan {
 };
 
 RB_HD unsigned brick_smem_bytes(int cap_cand, int cap_list, int threads, bool force_pass) {
-  return (unsigned)(cap_cand * ((force_pass ? 4 : 3) * sizeof(double) + sizeof(float4) + sizeof(unsigned short)) +
+  return (unsigned)(cap_cand * ((force_pass ? 4 : 3) * sizeof(double) + sizeof(uint2) + sizeof(unsigned short)) +
                     (size_t)cap_list * threads * sizeof(unsigned short) + 16);
 }
 
@@ -145,8 +147,10 @@ k_brick(const __grid_constant__ GatherArgs a, const __grid_constant__ BrickPlan 
 
   double* c64 = reinterpret_cast<double*>(smem_raw);  // x, y, z of staged atom s at c64[3 s ..]
   double* c64w = c64 + 3 * bp.cap_cand;               // EAM force pass: F'(rho_j)
-  float4* c32 = reinterpret_cast<float4*>(c64 + (kForce ? 4 : 3) * bp.cap_cand);  // offset x, y, z, |offset|^2
-  unsigned short* cinfo = reinterpret_cast<unsigned short*>(c32 + bp.cap_cand);   // image code | species << 8
+  // FP16 offsets from the brick centre (x, y | z, 0): 8 bytes per candidate, two shared-memory
+  // wavefronts per warp load where an FP32 record needs four (the search is bound by them)
+  uint2* c16 = reinterpret_cast<uint2*>(c64 + (kForce ? 4 : 3) * bp.cap_cand);
+  unsigned short* cinfo = reinterpret_cast<unsigned short*>(c16 + bp.cap_cand);   // image code | species << 8
   unsigned short* lists = cinfo + bp.cap_cand;
 
   // image vectors; the brick of this block as the first box
@@ -352,7 +356,8 @@ k_brick(const __grid_constant__ GatherArgs a, const __grid_constant__ BrickPlan 
         c64[3 * s + 2] = p.z;
         if (kForce) c64w[s] = o.dfd_sorted[jb + s];
         const float fx = (float)(p.x + svx), fy = (float)(p.y + svy), fz = (float)(p.z + svz);
-        c32[s] = make_float4(fx, fy, fz, fmaf(fx, fx, fmaf(fy, fy, fz * fz)));
+        const __half2 hxy = __floats2half2_rn(fx, fy), hz0 = __floats2half2_rn(fz, 0.0f);
+        c16[s] = make_uint2(*reinterpret_cast<const unsigned*>(&hxy), *reinterpret_cast<const unsigned*>(&hz0));
         cinfo[s] = (unsigned short)(code | (meta_species((unsigned long long)__double_as_longlong(p.w)) << 8));
       }
     }
@@ -387,10 +392,9 @@ k_brick(const __grid_constant__ GatherArgs a, const __grid_constant__ BrickPlan 
           const int hc = center_of(c), il = ai - bc_astart[c];
           si = hstart[hc] + il;
           gi = hgstart[hc] + il;
-          // |c - f|^2 = |c|^2 + (|f|^2 - 2 c.f): three FFMA and one add per candidate
-          const float4 fi = c32[si];
-          const float m2x = -2.0f * fi.x, m2y = -2.0f * fi.y, m2z = -2.0f * fi.z;
-          const float thr = bp.thr2f - fi.w;
+          const uint2 fi = c16[si];
+          const __half2 fxy = *reinterpret_cast<const __half2*>(&fi.x), fz0 = *reinterpret_cast<const __half2*>(&fi.y);
+          const __half thr = __float2half_ru(bp.thr2f);
           const double pix = c64[3 * si], piy = c64[3 * si + 1], piz = c64[3 * si + 2];
           const int zi = cinfo[si] >> 8;
           double dfd_i = 0.0;
@@ -439,10 +443,13 @@ k_brick(const __grid_constant__ GatherArgs a, const __grid_constant__ BrickPlan 
               }
 #pragma unroll 4
               for (; s < se; ++s) {
-                const float4 f = c32[s];
-                const float t = fmaf(f.x, m2x, fmaf(f.y, m2y, fmaf(f.z, m2z, f.w)));
+                const uint2 f = c16[s];
+                const __half2 dxy = __hsub2(*reinterpret_cast<const __half2*>(&f.x), fxy);
+                const __half2 dz0 = __hsub2(*reinterpret_cast<const __half2*>(&f.y), fz0);
+                const __half2 q = __hfma2(dz0, dz0, __hmul2(dxy, dxy));  // (dx^2 + dz^2, dy^2)
+                const __half t = __hadd(__low2half(q), __high2half(q));
                 asm volatile("st.shared.u16 [%0], %1;" ::"r"(lsa), "h"((unsigned short)s));  // kept only if it passes
-                lsa += t <= thr ? lstride : 0u;
+                lsa += __hle(t, thr) ? lstride : 0u;
               }
               if (s < s1) break;  // the row continues after the list has been evaluated
             }

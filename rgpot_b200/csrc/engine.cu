@@ -422,17 +422,16 @@ float brick_threshold(const Plan& pl, const int bd[3], const int ns[3], double r
     }
     A = std::max(A, ext);
   }
-  // The search evaluates |c|^2 + (|f|^2 - 2 c.f) in FP32.  With u = 2^-24: rounding the two offsets
-  // moves a component by <= 2 A u (delta), and every one of the ~10 FP32 operations rounds a partial
-  // result of magnitude <= 4 * 3 A^2, so the computed value exceeds the exact d2 of an accepted
-  // pair by at most the bound below (doubled for safety).
-  const double u = ldexp(1.0, -24);
-  const double delta = 2.0 * A * u * 1.001;
-  const double err = 2.0 * sqrt(3.0) * rc * delta + 3.0 * delta * delta + 10.0 * u * 12.0 * A * A;
-  const double t = (rc * rc + 2.0 * err) * (1.0 + 1.0e-6);
-  float f = (float)t;
-  if ((double)f < t) f = nextafterf(f, INFINITY);
-  return nextafterf(f, INFINITY);
+  // The search works in FP16 (unit roundoff u = 2^-11): rounding the two offsets moves a component
+  // by <= 2 A u, the subtraction rounds once more (|d| <= rc + ...), so a component of the computed
+  // separation is off by <= delta; the three squares and two sums round partial results of
+  // magnitude <= ~1.2 rc^2.  The bound on the computed d2 of an accepted pair follows (half again
+  // for safety); every listed candidate still takes the exact FP64 test.
+  const double u = ldexp(1.0, -11);
+  const double delta = 2.0 * A * u * 1.001 + (rc + 4.0 * A * u) * u;
+  const double err = 2.0 * sqrt(3.0) * rc * delta + 3.0 * delta * delta + 6.0 * u * 1.2 * rc * rc;
+  const double t = (rc * rc + 1.5 * err) * (1.0 + 1.0e-6);
+  return (float)t;  // rounded up to FP16 in the kernel
 }
 
 bool plan_bricks(const RgpotB200Pot* pot, const Plan& pl, long n, double rc, bool eam, BrickPlan& bp) {
