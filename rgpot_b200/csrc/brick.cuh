@@ -5,14 +5,16 @@
 // fluid where 27 cutoff-sized cells offer 364).  Three stages, all in shared memory:
 //
 //   stage   the atoms of the brick's halo (brick + ns cells on every side, periodic images
-//           included) are copied once: FP64 positions as x / y / z arrays, and an FP32 copy of the
-//           image-shifted position relative to the brick origin (with image code and species).
-//           A brick of 108 atoms stages 864 candidates (8 per atom); a per-cell walk reads 27+.
-//   search  every thread owns an atom (kTPA threads share one and split the stencil rows): FP32
+//           included) are copied once: FP64 positions, and an FP16 copy of the image-shifted
+//           position relative to the brick centre (plus image code and species).  A brick of 108
+//           atoms stages 864 candidates (8 per atom); a per-cell walk reads 27+.
+//   search  every thread owns an atom (kTPA threads share one and split the stencil rows): FP16
 //           prefilter over the atom's own stencil -- the (2 ns + 1)^2 rows of 2 ns + 1 cells that
-//           are contiguous in the staged order -- 6 FP32 operations, a compare and a predicated
-//           16-bit store into the thread's private survivor list.  FP32 pipe only; no ballots,
-//           no queues, no compaction, no block barrier before the next stage.
+//           are contiguous in the staged order -- one 8-byte shared load, five half2 operations,
+//           a compare and a 16-bit store into the thread's private survivor list (the kernel is
+//           bound by shared-memory wavefronts: an 8-byte record costs two per warp load, a 16-byte
+//           FP32 record four).  No FP64, no ballots, no queues, no compaction, no block barrier
+//           before the next stage; the threshold carries the FP16 error bound.
 //   physics the thread walks its list: the separation is redone in FP64 with the REFERENCE's
 //           expression ((p_j - p_i) + shift, unfused norm: accept / reject is bit-exact), the pair
 //           terms are evaluated and accumulated in registers.  Every lane works on a survivor;
