@@ -141,6 +141,30 @@ RGPOT_B200_API int rgpot_b200_neighbors(RgpotB200Pot *pot, long nAtoms, const do
                                         const int *atomicNrs, const double *box, int path,
                                         long cap, int32_t *pairs, int32_t *shifts, long *n_out);
 
+/** A neighbor list in the shape of vesin's VesinNeighborList (third_party/vesin/vesin.h:111-157):
+ *  `length` pairs (i, j), the periodic shift S of each, the vector (p_j - p_i) + S.H and its
+ *  length.  Host arrays owned by the struct: release with rgpot_b200_neighbor_list_free.          */
+typedef struct RgpotB200NeighborList {
+  size_t length;
+  size_t *pairs;     /**< 2 * length */
+  int32_t *shifts;   /**< 3 * length */
+  double *distances; /**< length */
+  double *vectors;   /**< 3 * length */
+} RgpotB200NeighborList;
+
+/** vesin_neighbors on the GPU cell list (lists for model-driven potentials such
+ *  as MetatomicPot, CppCore/rgpot/MetatomicPot/MetatomicPot.cc:487-542): every pair of points and
+ *  periodic images with d2 < cutoff^2, evaluated with vesin's own expression
+ *  (vesin-single-build.cpp:1199-1202), so the pair set, the vectors and the distances are
+ *  bit-identical to vesin's.  `box`: nine doubles, one cell vector per row; `periodic`: three flags,
+ *  all set or all clear (NULL = periodic); `full`: both i->j and j->i, else vesin's half list
+ *  (:1165-1197); `sorted`: ordered by (i, j, shift).  Any handle serves (it supplies the device,
+ *  the stream and the scratch buffers); `out` must be zero-initialised or a previous result.      */
+RGPOT_B200_API int rgpot_b200_neighbor_list(RgpotB200Pot *pot, size_t n_points, const double *points,
+                                            const double *box, const int *periodic, double cutoff,
+                                            int full, int sorted, RgpotB200NeighborList *out);
+RGPOT_B200_API void rgpot_b200_neighbor_list_free(RgpotB200NeighborList *nl);
+
 /** Message of the last failure on this handle (rgpot_ferror.f90:41-56 semantics, but per
  *  handle): copies at most buffer_len - 1 bytes, NUL-terminates, returns the length. */
 RGPOT_B200_API int rgpot_b200_last_error(RgpotB200Pot *pot, char *buffer, int buffer_len);

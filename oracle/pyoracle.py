@@ -248,6 +248,37 @@ def nlist(pos, box, cutoff=6.1, skin=None, use_ref=False, n_threads=1):
     return out
 
 
+class RawList(C.Structure):
+    _fields_ = [("length", C.c_long), ("pairs", C.POINTER(C.c_longlong)), ("shifts", C.POINTER(C.c_int32)),
+                ("dists", C.POINTER(C.c_double)), ("vecs", C.POINTER(C.c_double))]
+
+
+def vesin_raw(pos, box, cutoff, full=True, periodic=True):
+    """The vendored vesin's own list (oracle/_ref only): dict of pairs (m,2), shifts (m,3), distances (m,),
+    vectors (m,3), sorted by (i, j, shift).  Self images are kept, like vesin returns them."""
+    pos, box = _prep(pos, box)
+    lib = ref_lib()
+    lib.ref_vesin_raw.restype = C.c_int
+    lib.ref_vesin_raw.argtypes = [C.c_long, _f64p, _f64p, C.c_int, C.c_double, C.c_int, C.POINTER(RawList),
+                                  C.c_char_p, C.c_size_t]
+    lib.ref_vesin_raw_free.restype = None
+    lib.ref_vesin_raw_free.argtypes = [C.POINTER(RawList)]
+    r = RawList()
+    err = C.create_string_buffer(512)
+    st = lib.ref_vesin_raw(len(pos), pos, box, int(periodic), float(cutoff), int(full), C.byref(r), err, 512)
+    if st != 0:
+        raise RuntimeError(err.value.decode())
+    m = r.length
+    out = {
+        "pairs": np.ctypeslib.as_array(r.pairs, shape=(max(m, 1), 2))[:m].astype(np.int64),
+        "shifts": np.ctypeslib.as_array(r.shifts, shape=(max(m, 1), 3))[:m].copy(),
+        "distances": np.ctypeslib.as_array(r.dists, shape=(max(m, 1),))[:m].copy(),
+        "vectors": np.ctypeslib.as_array(r.vecs, shape=(max(m, 1), 3))[:m].copy(),
+    }
+    lib.ref_vesin_raw_free(C.byref(r))
+    return out
+
+
 def canonical_pairs(table) -> np.ndarray:
     """(i, j, s0, s1, s2) rows in lexicographic order: the pair SET of a table."""
     row = table["row"]

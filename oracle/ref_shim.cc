@@ -151,6 +151,69 @@ int ref_vesin_table(void *handle, long n, const double *pos, const double *box, 
   return 0;
 }
 
+// The vendored vesin itself, raw: flat copies of VesinNeighborList for the neighbor-list parity
+// tests (full / half lists, self images kept, periodic or free).  Caller frees with ref_vesin_raw_free.
+typedef struct {
+  long length;
+  long long *pairs;  // 2 per entry
+  int32_t *shifts;   // 3 per entry
+  double *dists;
+  double *vecs;      // 3 per entry
+} ref_raw_list_t;
+
+void ref_vesin_raw_free(ref_raw_list_t *r) {
+  if (!r) return;
+  std::free(r->pairs);
+  std::free(r->shifts);
+  std::free(r->dists);
+  std::free(r->vecs);
+  std::memset(r, 0, sizeof *r);
+}
+
+int ref_vesin_raw(long n, const double *pos, const double *box, int periodic_all, double cutoff, int full,
+                  ref_raw_list_t *out, char *err, size_t errlen) {
+  std::memset(out, 0, sizeof *out);
+  VesinNeighborList list;
+  VesinOptions opt{};
+  opt.cutoff = cutoff;
+  opt.full = full != 0;
+  opt.sorted = true;
+  opt.algorithm = VesinAutoAlgorithm;
+  opt.skin = 0.0;
+  opt.n_threads = 1;
+  opt.return_shifts = true;
+  opt.return_distances = true;
+  opt.return_vectors = true;
+  const bool periodic[3] = {periodic_all != 0, periodic_all != 0, periodic_all != 0};
+  const char *msg = nullptr;
+  double cell[3][3];
+  std::memcpy(cell, box, sizeof cell);
+  int st = vesin_neighbors(reinterpret_cast<const double(*)[3]>(pos), static_cast<size_t>(n), cell, periodic,
+                           VesinDevice{VesinCPU, 0}, opt, &list, &msg);
+  if (st != 0) {
+    std::snprintf(err, errlen, "%s", msg ? msg : "vesin failed");
+    vesin_free(&list);
+    return st;
+  }
+  const size_t m = list.length, cap = m ? m : 1;
+  out->length = static_cast<long>(m);
+  out->pairs = static_cast<long long *>(std::malloc(sizeof(long long) * 2 * cap));
+  out->shifts = static_cast<int32_t *>(std::malloc(sizeof(int32_t) * 3 * cap));
+  out->dists = static_cast<double *>(std::malloc(sizeof(double) * cap));
+  out->vecs = static_cast<double *>(std::malloc(sizeof(double) * 3 * cap));
+  for (size_t p = 0; p < m; ++p) {
+    out->pairs[2 * p] = static_cast<long long>(list.pairs[p][0]);
+    out->pairs[2 * p + 1] = static_cast<long long>(list.pairs[p][1]);
+    for (int k = 0; k < 3; ++k) {
+      out->shifts[3 * p + k] = list.shifts[p][k];
+      out->vecs[3 * p + k] = list.vectors[p][k];
+    }
+    out->dists[p] = list.distances[p];
+  }
+  vesin_free(&list);
+  return 0;
+}
+
 // CuH2 as the reference evaluates it, as far as this image allows: the reference's own
 // vesin (unmodified) feeding the restated Fortran passes (oracle/cuh2_oracle.c).
 int ref_cuh2_force(void *handle, int32_t natoms, const double *pos, const int32_t *Z,

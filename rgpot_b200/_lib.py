@@ -64,6 +64,12 @@ DLManagedTensorVersioned._fields_ = [("version", DLPackVersion), ("manager_ctx",
                                      ("deleter", DLDeleter), ("flags", C.c_uint64), ("dl_tensor", DLTensor)]
 
 
+class NeighborList(C.Structure):
+    """RgpotB200NeighborList"""
+    _fields_ = [("length", C.c_size_t), ("pairs", C.POINTER(C.c_size_t)), ("shifts", C.POINTER(C.c_int32)),
+                ("distances", C.POINTER(C.c_double)), ("vectors", C.POINTER(C.c_double))]
+
+
 class ForceInput(C.Structure):
     """rgpot_force_input_t"""
     _fields_ = [("positions", C.POINTER(DLManagedTensorVersioned)),
@@ -92,6 +98,8 @@ SYMBOLS = [
     ("rgpot_b200_force_batch_device", _i, [_vp, _sz, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     ("rgpot_b200_sync_status", _i, [_vp]),
     ("rgpot_b200_neighbors", _i, [_vp, _l, _vp, _vp, _vp, _i, _l, _vp, _vp, C.POINTER(_l)]),
+    ("rgpot_b200_neighbor_list", _i, [_vp, _sz, _vp, _vp, _vp, _d, _i, _i, _vp]),
+    ("rgpot_b200_neighbor_list_free", None, [_vp]),
     ("rgpot_b200_last_error", _i, [_vp, C.c_char_p, _i]),
     ("rgpot_b200_launch_count", _l, [_vp]),
     ("rgpot_b200_stat", _l, [_vp, C.c_char_p]),

@@ -228,7 +228,7 @@ struct RgpotB200Pot {
 
   // single-system scratch
   DevBuf pos, Z, F, cell_of, rank, ashift, counts, starts, blocksums, order, order2, spos, scell, dfd, eemb,
-      partials, partials2, energy, status, mm, emit_pairs, emit_shifts, emit_count;
+      partials, partials2, energy, status, mm, emit_pairs, emit_shifts, emit_count, emit_vecs, emit_dists;
   // batch scratch
   DevBuf b_pos, b_Z, b_F, b_off, b_boxes, b_E, b_flags, b_bad, b_map;
   HostBuf h_pos, h_Z, h_F, h_off, h_boxes, h_E, h_flags, h_bad, h_small;
@@ -254,7 +254,7 @@ struct RgpotB200Pot {
     cudaSetDevice(device);
     DevBuf* d[] = {&pos, &Z, &F, &cell_of, &rank, &ashift, &counts, &starts, &blocksums, &order, &order2,
                    &spos, &scell, &dfd, &eemb, &partials, &partials2, &energy, &status, &mm, &emit_pairs,
-                   &emit_shifts, &emit_count, &b_pos, &b_Z, &b_F, &b_off, &b_boxes, &b_E, &b_flags,
+                   &emit_shifts, &emit_count, &emit_vecs, &emit_dists, &b_pos, &b_Z, &b_F, &b_off, &b_boxes, &b_E, &b_flags,
                    &b_bad, &b_map, &zbl_table};
     for (auto* b : d) b->release();
     HostBuf* h[] = {&h_pos, &h_Z, &h_F, &h_off, &h_boxes, &h_E, &h_flags, &h_bad, &h_small};
@@ -570,13 +570,16 @@ int reduce_energy(RgpotB200Pot* pot, double* d_part, int n, double* d_E, cudaStr
 // Leaves forces in d_F (original order), energy in d_E[0], flags in pot->status.
 int run_cell_path(RgpotB200Pot* pot, long n, const double* d_pos, const int* d_Z, double* d_F,
                   double* d_E, const double* box, cudaStream_t st, const EmitArgs* emit,
-                  bool allow_tile = true) {
-  const int kind = pot->cfg.kind;
+                  bool allow_tile = true, double nlist_rc = 0.0) {
+  // nlist_rc > 0: a plain vesin-shaped neighbor list of that cutoff (every image, self images kept),
+  // whatever potential the handle was created for (rgpot_b200_neighbor_list)
+  const bool nlist = nlist_rc > 0.0 && emit != nullptr;
+  const int kind = nlist ? RGPOT_B200_LJ : pot->cfg.kind;
   const bool eam = is_eam(kind);
   const bool al = kind == RGPOT_B200_EAM_AL;
-  const bool images = eam || pot->cfg.lj_all_images;
+  const bool images = eam || pot->cfg.lj_all_images || nlist;
   Plan pl{};
-  const double rc = eam ? eam_rcut(kind) : pot->lj_rc;
+  const double rc = nlist ? nlist_rc : (eam ? eam_rcut(kind) : pot->lj_rc);
 
   CU_TRY(pot, pot->status.reserve(sizeof(Status)));
   Status init{};
@@ -727,6 +730,7 @@ int run_cell_path(RgpotB200Pot* pot, long n, const double* d_pos, const int* d_Z
   ga.lj = pl.lj;
   ga.rc2 = pl.rc2;
   ga.st_in = d_st;
+  ga.keep_self_images = nlist ? 1 : 0;
 
   if (emit) {
     if (pl.geo == GEO_IMAGES)
@@ -1537,6 +1541,135 @@ int rgpot_b200_neighbors(RgpotB200Pot* pot, long nAtoms, const double* positions
   if (m > 0 && pairs && shifts) {
     CU_TRY(pot, cudaMemcpy(pairs, pot->emit_pairs.p, sizeof(int32_t) * 2 * m, cudaMemcpyDeviceToHost));
     CU_TRY(pot, cudaMemcpy(shifts, pot->emit_shifts.p, sizeof(int32_t) * 3 * m, cudaMemcpyDeviceToHost));
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// vesin-shaped neighbor lists
+// ------------------------------------------------------------------------------------------------
+void rgpot_b200_neighbor_list_free(RgpotB200NeighborList* nl) {
+  if (!nl) return;
+  free(nl->pairs);
+  free(nl->shifts);
+  free(nl->distances);
+  free(nl->vectors);
+  memset(nl, 0, sizeof *nl);
+}
+
+int rgpot_b200_neighbor_list(RgpotB200Pot* pot, size_t n_points, const double* points, const double* box,
+                             const int* periodic, double cutoff, int full, int sorted,
+                             RgpotB200NeighborList* out) {
+  if (!pot || !out) return kStatusArgs;
+  pot->last_error.clear();
+  rgpot_b200_neighbor_list_free(out);
+  if (!(cutoff > 0.0) || !std::isfinite(cutoff)) return fail(pot, kStatusArgs, "rgpot_b200_neighbor_list: cutoff must be positive and finite");
+  if (n_points > (size_t)kMaxAtoms) return fail(pot, kStatusArgs, "rgpot_b200: bad atom count");
+  if (n_points == 0) return 0;
+  if (!points) return fail(pot, kStatusArgs, "rgpot_b200_neighbor_list: null points");
+  const bool per = periodic ? (periodic[0] && periodic[1] && periodic[2]) : true;
+  const bool none = periodic && !periodic[0] && !periodic[1] && !periodic[2];
+  if (!per && !none)
+    return fail(pot, kStatusArgs, "rgpot_b200_neighbor_list: mixed periodicity is not supported (all or none)");
+  if (per && !box) return fail(pot, kStatusArgs, "rgpot_b200_neighbor_list: null box");
+  CU_TRY(pot, cudaSetDevice(pot->device));
+  cudaStream_t st = pot->stream;
+  const size_t n = n_points;
+  // A free system is searched inside a fictitious cubic cell so wide that no image comes within the
+  // cutoff: the pairs are the free ones.  The points are NOT moved: atoms outside the cell are
+  // handled by the per-pair shift bookkeeping, which for two atoms of the same image gives S = 0 and
+  // therefore exactly (p_j - p_i), vesin's expression for a free system.
+  double cell[9];
+  if (per) {
+    memcpy(cell, box, sizeof cell);
+  } else {
+    double lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY}, maxabs = 0.0;
+    for (size_t i = 0; i < n; ++i)
+      for (int k = 0; k < 3; ++k) {
+        const double v = points[3 * i + k];
+        if (!std::isfinite(v)) return fail(pot, 1, "rgpot_b200_neighbor_list: a point has a non-finite coordinate");
+        lo[k] = std::min(lo[k], v);
+        hi[k] = std::max(hi[k], v);
+        maxabs = std::max(maxabs, fabs(v));
+      }
+    double ext = 0.0;
+    for (int k = 0; k < 3; ++k) ext = std::max(ext, hi[k] - lo[k]);
+    const double L = std::max(ext + 2.5 * cutoff + 1.0, maxabs / 400.0);  // (wrap counts stay below 500)
+    memset(cell, 0, sizeof cell);
+    cell[0] = cell[4] = cell[8] = L;
+  }
+  const double* search_points = points;
+  CU_TRY(pot, pot->pos.reserve(sizeof(double) * 3 * n));
+  CU_TRY(pot, pot->F.reserve(sizeof(double) * 3 * n));
+  CU_TRY(pot, pot->energy.reserve(sizeof(double)));
+  CU_TRY(pot, pot->emit_count.reserve(sizeof(unsigned long long)));
+  CU_TRY(pot, cudaMemcpyAsync(pot->pos.p, search_points, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, st));
+  // two passes: count, then fill (the list length is not known beforehand)
+  unsigned long long cnt = 0;
+  for (int pass = 0; pass < 2; ++pass) {
+    const size_t cap = pass == 0 ? 0 : (size_t)cnt;
+    if (pass == 1) {
+      if (cnt == 0) break;
+      CU_TRY(pot, pot->emit_pairs.reserve(sizeof(int32_t) * 2 * cap));
+      CU_TRY(pot, pot->emit_shifts.reserve(sizeof(int32_t) * 3 * cap));
+      CU_TRY(pot, pot->emit_vecs.reserve(sizeof(double) * 3 * cap));
+      CU_TRY(pot, pot->emit_dists.reserve(sizeof(double) * cap));
+    }
+    CU_TRY(pot, cudaMemsetAsync(pot->emit_count.p, 0, sizeof(unsigned long long), st));
+    EmitArgs em{};
+    em.pairs = pot->emit_pairs.as<int32_t>();
+    em.shifts = pot->emit_shifts.as<int32_t>();
+    em.count = pot->emit_count.as<unsigned long long>();
+    em.cap = (long)cap;
+    em.vecs = pot->emit_vecs.as<double>();
+    em.dists = pot->emit_dists.as<double>();
+    em.half = full ? 0 : 1;
+    int s = run_cell_path(pot, (long)n, pot->pos.as<double>(), nullptr, pot->F.as<double>(),
+                          pot->energy.as<double>(), cell, st, &em, false, cutoff);
+    if (s) return s;
+    Status stt{};
+    CU_TRY(pot, cudaMemcpyAsync(&stt, pot->status.p, sizeof stt, cudaMemcpyDeviceToHost, st));
+    CU_TRY(pot, cudaMemcpyAsync(&cnt, pot->emit_count.p, sizeof cnt, cudaMemcpyDeviceToHost, st));
+    CU_TRY(pot, cudaStreamSynchronize(st));
+    if (stt.flags & (kFlagNonFinite | kFlagShiftRange | kFlagSingularBox))
+      return map_flags(pot, stt.flags & (kFlagNonFinite | kFlagShiftRange | kFlagSingularBox), stt.first_bad_atom, 0, points);
+  }
+  const size_t m = (size_t)cnt;
+  out->length = m;
+  if (m == 0) return 0;
+  std::vector<int32_t> hp(2 * m), hs(3 * m);
+  out->pairs = (size_t*)malloc(sizeof(size_t) * 2 * m);
+  out->shifts = (int32_t*)malloc(sizeof(int32_t) * 3 * m);
+  out->distances = (double*)malloc(sizeof(double) * m);
+  out->vectors = (double*)malloc(sizeof(double) * 3 * m);
+  if (!out->pairs || !out->shifts || !out->distances || !out->vectors) {
+    rgpot_b200_neighbor_list_free(out);
+    return fail(pot, kStatusArgs, "rgpot_b200_neighbor_list: out of host memory");
+  }
+  CU_TRY(pot, cudaMemcpy(hp.data(), pot->emit_pairs.p, sizeof(int32_t) * 2 * m, cudaMemcpyDeviceToHost));
+  CU_TRY(pot, cudaMemcpy(hs.data(), pot->emit_shifts.p, sizeof(int32_t) * 3 * m, cudaMemcpyDeviceToHost));
+  std::vector<size_t> order(m);
+  for (size_t k = 0; k < m; ++k) order[k] = k;
+  if (sorted)  // by the first index, like vesin (GrowableNeighborList::sort sorts on (i, j, shift))
+    std::sort(order.begin(), order.end(), [&](size_t a, size_t b) {
+      if (hp[2 * a] != hp[2 * b]) return hp[2 * a] < hp[2 * b];
+      if (hp[2 * a + 1] != hp[2 * b + 1]) return hp[2 * a + 1] < hp[2 * b + 1];
+      for (int k = 0; k < 3; ++k)
+        if (hs[3 * a + k] != hs[3 * b + k]) return hs[3 * a + k] < hs[3 * b + k];
+      return false;
+    });
+  std::vector<double> hv(3 * m), hd(m);
+  CU_TRY(pot, cudaMemcpy(hv.data(), pot->emit_vecs.p, sizeof(double) * 3 * m, cudaMemcpyDeviceToHost));
+  CU_TRY(pot, cudaMemcpy(hd.data(), pot->emit_dists.p, sizeof(double) * m, cudaMemcpyDeviceToHost));
+  for (size_t k = 0; k < m; ++k) {
+    const size_t src = order[k];
+    out->pairs[2 * k] = (size_t)hp[2 * src];
+    out->pairs[2 * k + 1] = (size_t)hp[2 * src + 1];
+    for (int c = 0; c < 3; ++c) {
+      out->shifts[3 * k + c] = hs[3 * src + c];  // (all zero for a free system)
+      out->vectors[3 * k + c] = hv[3 * src + c];
+    }
+    out->distances[k] = hd[src];
   }
   return 0;
 }

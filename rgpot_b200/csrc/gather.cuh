@@ -34,8 +34,10 @@ struct GatherArgs {
   LJParams lj;
   double rc2;           // GEO_IMAGES accept threshold (strict <)
   const Status* st_in;  // flags from binning (kFlagAtomShift selects the per-pair shift form)
-  int only_if_atom_shift;  // 1: run only when some atom sits outside the cell (the tile kernels
-                           //    of tile.cuh cover the other case)
+  int only_if_atom_shift;  // 1: run only when some atom sits outside the cell (the brick kernels
+                           //    of brick.cuh cover the other case)
+  int keep_self_images;    // GEO_IMAGES: keep (i, i, S != 0) entries like vesin does (the EAM tables
+                           //    of rgpot drop them, rgpot_neighbors.f90:132)
 };
 
 // optional pair emission for rgpot_b200_neighbors
@@ -44,6 +46,9 @@ struct EmitArgs {
   int32_t* shifts;  // 3 per entry
   unsigned long long* count;
   long cap;
+  double* vecs;     // optional: 3 per entry, (p_j - p_i) + S.H exactly as evaluated for the test
+  double* dists;    // optional: sqrt(d2) (IEEE, like vesin's)
+  int half;         // GEO_IMAGES: vesin's half list (vesin-single-build.cpp:1165-1197)
 };
 
 // Walk all candidates of sorted atom `i`.  body(j, mj, dx, dy, dz, d2, S0, S1, S2) is called for
@@ -116,7 +121,7 @@ RB_D void walk_neighbors(const GatherArgs& a, int i, const double4 pi, Body&& bo
             d2 = xnorm2(ddx, ddy, ddz);
             if (!(d2 <= a.lj.rc2)) continue;
           } else {
-            if (meta_orig(mj) == oi) continue;  // self images carry no usable direction
+            if (meta_orig(mj) == oi && !a.keep_self_images) continue;  // self images carry no usable direction
             if (ATOM_SHIFTS) {
               S0 = qx + si0 - meta_shift(mj, 0);
               S1 = qy + si1 - meta_shift(mj, 1);
@@ -125,6 +130,7 @@ RB_D void walk_neighbors(const GatherArgs& a, int i, const double4 pi, Body&& bo
               svy = shift_component(a.box.H, 1, (double)S0, (double)S1, (double)S2);
               svz = shift_component(a.box.H, 2, (double)S0, (double)S1, (double)S2);
             }
+            if (meta_orig(mj) == oi && (S0 | S1 | S2) == 0) continue;  // the atom itself
             ddx = xadd(xsub(pj.x, pi.x), svx);
             ddy = xadd(xsub(pj.y, pi.y), svy);
             ddz = xadd(xsub(pj.z, pi.z), svz);
@@ -252,10 +258,18 @@ __global__ void k_emit_pairs(GatherArgs a, EmitArgs em) {
   if (i >= a.n) return;
   const double4 pi = a.spos[i];
   const int oi = meta_orig((unsigned long long)__double_as_longlong(pi.w));
-  auto body = [&](int, unsigned long long mj, double, double, double, double, int S0, int S1,
+  auto body = [&](int, unsigned long long mj, double vx, double vy, double vz, double d2, int S0, int S1,
                   int S2) {
     const int oj = meta_orig(mj);
     if (GEO != GEO_IMAGES && oj < oi) return;  // LJ: unordered pairs, i < j
+    if (GEO == GEO_IMAGES && em.half) {
+      // vesin's half list: first <= second, and one of the two images of a self pair
+      if (oi > oj) return;
+      if (oi == oj) {
+        const int sum = S0 + S1 + S2;
+        if (sum < 0 || (sum == 0 && (S2 < 0 || (S2 == 0 && S1 < 0)))) return;
+      }
+    }
     const unsigned long long k = atomicAdd(em.count, 1ull);
     if ((long)k < em.cap) {
       em.pairs[2 * k] = oi;
@@ -263,6 +277,12 @@ __global__ void k_emit_pairs(GatherArgs a, EmitArgs em) {
       em.shifts[3 * k] = GEO == GEO_IMAGES ? S0 : 0;
       em.shifts[3 * k + 1] = GEO == GEO_IMAGES ? S1 : 0;
       em.shifts[3 * k + 2] = GEO == GEO_IMAGES ? S2 : 0;
+      if (em.vecs) {
+        em.vecs[3 * k] = vx;
+        em.vecs[3 * k + 1] = vy;
+        em.vecs[3 * k + 2] = vz;
+      }
+      if (em.dists) em.dists[k] = sqrt(d2);
     }
   };
   walk_dispatch<GEO>(a, i, pi, body);

@@ -457,6 +457,35 @@ def evaluate_cuh2(positions, atom_types, box):
     return _default(CuH2Pot)(positions, atom_types, box)
 
 
+def neighbor_list(points, box, cutoff: float, full: bool = True, sorted: bool = True, periodic: bool = True,
+                  pot=None) -> dict:
+    """vesin-shaped neighbor list from the GPU cell list (rgpot_b200_neighbor_list): dict of
+    `pairs` (m, 2) int64, `shifts` (m, 3) int32, `distances` (m,), `vectors` (m, 3).  Pair set,
+    vectors and distances are bit-identical to vesin's (third_party/vesin) for the same options."""
+    pot = pot or _default(LJPot)
+    pos = _as_positions(points)
+    cell = _as_box(box) if box is not None else np.eye(3)
+    per = (C.c_int * 3)(*([1, 1, 1] if periodic else [0, 0, 0]))
+    nl = _lib.NeighborList()
+    st = pot._lib.rgpot_b200_neighbor_list(pot._h, pos.shape[0], pos.ctypes.data, cell.ctypes.data, per,
+                                           float(cutoff), int(full), int(sorted), C.byref(nl))
+    if st != 0:
+        pot._raise(st)
+    m = nl.length
+    try:
+        if m == 0:
+            return {"pairs": np.zeros((0, 2), np.int64), "shifts": np.zeros((0, 3), np.int32),
+                    "distances": np.zeros(0), "vectors": np.zeros((0, 3))}
+        return {
+            "pairs": np.ctypeslib.as_array(nl.pairs, shape=(m, 2)).astype(np.int64),
+            "shifts": np.ctypeslib.as_array(nl.shifts, shape=(m, 3)).copy(),
+            "distances": np.ctypeslib.as_array(nl.distances, shape=(m,)).copy(),
+            "vectors": np.ctypeslib.as_array(nl.vectors, shape=(m, 3)).copy(),
+        }
+    finally:
+        pot._lib.rgpot_b200_neighbor_list_free(C.byref(nl))
+
+
 def pinned_empty(shape, dtype=np.float64) -> np.ndarray:
     """numpy array on page-locked memory from rgpot_b200_host_alloc (kept alive by the array)."""
     lib = _lib.lib()

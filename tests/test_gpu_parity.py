@@ -697,3 +697,44 @@ def test_eam_al_batch_and_coexistence_with_cuh2(cuh2, oracle, golden):
         e_o, f_o = oracle.eam_al_force(p, b)
         assert_energy(e, e_o)
         assert_forces(f, f_o)
+
+
+# ------------------------------------------------- vesin-shaped neighbor lists
+def _nl_canon(nl):
+    rec = np.column_stack([nl["pairs"], nl["shifts"].astype(np.int64)])
+    order = np.lexsort((rec[:, 4], rec[:, 3], rec[:, 2], rec[:, 1], rec[:, 0])) if len(rec) else np.zeros(0, int)
+    return rec[order], nl["vectors"][order], nl["distances"][order]
+
+
+@pytest.mark.parametrize("case", ["triclinic", "small_box", "unwrapped", "free"])
+@pytest.mark.parametrize("full", [True, False])
+def test_neighbor_list_is_bit_identical_to_vesin(oracle, case, full):
+    """rgpot_b200_neighbor_list against the vendored vesin itself: the same pair set (self images
+    included), bit-identical vectors and distances, full and half lists."""
+    if not oracle.ref_available():
+        pytest.skip("oracle/_ref/libref.so (the vendored vesin) is not built")
+    rng = np.random.default_rng(12)
+    periodic, cutoff = True, 4.2
+    if case == "triclinic":
+        pos, _, box = workloads.cu_slab_triclinic(cells=5, n_h2_side=2)
+    elif case == "small_box":  # box narrower than the cutoff: several images per pair, self images
+        box = np.array([[3.1, 0.0, 0.0], [0.4, 3.3, 0.0], [0.2, -0.3, 3.6]])
+        pos = rng.random((12, 3)) @ box
+    elif case == "unwrapped":
+        pos, _, box = workloads.cu_slab_triclinic(cells=4, n_h2_side=2)
+        pos = pos + rng.integers(-3, 4, size=pos.shape) @ box
+    else:
+        periodic = False
+        pos = rng.random((900, 3)) * 30.0 - 7.0
+        box = np.eye(3)
+    ours = rgpot_b200.neighbor_list(pos, box, cutoff, full=full, periodic=periodic)
+    ref = oracle.vesin_raw(pos, box, cutoff, full=full, periodic=periodic)
+    a, av, ad = _nl_canon(ours)
+    b, bv, bd = _nl_canon(ref)
+    assert len(a) == len(b) and len(a) > 0
+    assert np.array_equal(a, b)
+    assert np.array_equal(av, bv) and np.array_equal(ad, bd)
+    if case == "small_box":
+        assert (a[:, 0] == a[:, 1]).any()  # self images present
+    # sorted output: ordered by the first index
+    assert (np.diff(ours["pairs"][:, 0]) >= 0).all()
