@@ -59,13 +59,16 @@ enum {
                                   LJ (CppCore/rgpot/Morse/MorsePot.{hpp,cc}); SURVEY 8(f) rank 1 */
   RGPOT_B200_ZBL = 4,        /**< PotType::ZBL       -- screened nuclear repulsion with switching, free
                                   boundaries, species-pair tables (CppCore/rgpot/ZBL/ZBLPot.{hpp,cc}) */
-  RGPOT_B200_EAM_AL = 5      /**< PotType::EAMAl     -- double-exponential aluminium EAM, single species, all images
+  RGPOT_B200_EAM_AL = 5,     /**< PotType::EAMAl     -- double-exponential aluminium EAM, single species, all images
                                   inside 7.1 A (CppCore/rgpot/fortran/rgpot_eam_al.f90); SURVEY 8(f) rank 2.
                                   Atomic numbers are not read (rgpot_eam_al_capi.f90:31-35).            */
+  RGPOT_B200_FEHE = 6        /**< PotType::FeHe      -- Fe-He EAM (Ackland iron + s-band helium coupling), two density
+                                  channels, all images inside 5.4 A (CppCore/rgpot/fortran/rgpot_fehe.f90);
+                                  atomic numbers 26 / 2, anything else is status 2.  Gather kernels only.  */
 };
 
 typedef struct RgpotB200Config {
-  int kind;      /**< RGPOT_B200_LJ / _LJ_CLUSTER / _CUH2 / _MORSE / _ZBL / _EAM_AL */
+  int kind;      /**< RGPOT_B200_LJ / _LJ_CLUSTER / _CUH2 / _MORSE / _ZBL / _EAM_AL / _FEHE */
   int device;    /**< CUDA device ordinal; -1 keeps the calling thread's current device */
   double u0;     /**< LJConfig::u0     (LJPot.hpp:30-34), default 1.0  */
   double cutoff; /**< LJConfig::cutoff, default 15.0; ignored for CuH2 (fixed 6.1) and EAM-Al (7.1) */
@@ -194,6 +197,9 @@ RGPOT_B200_API int rgpot_cuh2_force(int32_t natoms, const double *positions,
 /** The reference's EAM-Al entry (FortranPots.cc:26-28, rgpot_eam_al_capi.f90:31-58). */
 RGPOT_B200_API int rgpot_eam_al_force(int32_t natoms, const double *positions, const double *cell,
                                       double *forces, double *energy);
+/** The reference's Fe-He entry (FortranPots.cc, rgpot_fehe_capi.f90:36-63). */
+RGPOT_B200_API int rgpot_fehe_force(int32_t natoms, const double *positions, const int32_t *atomic_numbers,
+                                    const double *cell, double *forces, double *energy);
 RGPOT_B200_API int rgpot_fortran_last_error(char *buffer, int buffer_len);
 
 #ifdef __cplusplus

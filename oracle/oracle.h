@@ -100,6 +100,14 @@ int oracle_eam_al_force_table(int32_t natoms, const oracle_nlist_t *table, doubl
  * 5 embedding_deriv (of rho).  rgpot_eam_al.f90:125-213.                               */
 double oracle_eam_al_scalar(int which, double x);
 
+/* ------------------------------------------------------------- FeHe ------- */
+
+/* rgpot_fehe_force (rgpot_fehe_capi.f90:36-63) -> fehe_energy_forces (rgpot_fehe.f90:573-620).
+ * Status 0, 2 (unsupported atomic number) or a neighbor-build status, message in err.      */
+int oracle_fehe_force(int32_t natoms, const double *pos, const int32_t *Z, const double *cell, double *F,
+                      double *energy, char *err, size_t errlen);
+double oracle_fehe_scalar(int which, double x); /* see fehe_oracle.c */
+
 /* LJ pair math over a vesin-semantics (all images, general triclinic) list: the oracle
  * for the opt-in triclinic LJ mode.  There is NO reference implementation of this
  * (LJPot.cc ignores off-diagonal box terms): parity unpinned, self-consistency only.  */

@@ -63,6 +63,11 @@ def _declare_common(lib):
                                         C.c_size_t]
     lib.oracle_eam_al_scalar.restype = C.c_double
     lib.oracle_eam_al_scalar.argtypes = [C.c_int, C.c_double]
+    lib.oracle_fehe_force.restype = C.c_int
+    lib.oracle_fehe_force.argtypes = [C.c_int32, _f64p, _i32p, _f64p, _f64p, C.POINTER(C.c_double), C.c_char_p,
+                                      C.c_size_t]
+    lib.oracle_fehe_scalar.restype = C.c_double
+    lib.oracle_fehe_scalar.argtypes = [C.c_int, C.c_double]
     lib.oracle_cuh2_force.restype = C.c_int
     lib.oracle_cuh2_force.argtypes = [C.c_int32, _f64p, _i32p, _f64p, _f64p, C.POINTER(C.c_double),
                                       C.c_char_p, C.c_size_t, C.POINTER(NList)]
@@ -339,6 +344,31 @@ def eam_al_force(pos, box):
 def eam_al_scalar(which, x):
     """0 pair_energy, 1 pair_deriv, 2 density, 3 density_deriv (r); 4 embedding, 5 embedding_deriv (rho)."""
     return oracle_lib().oracle_eam_al_scalar(int(which), float(x))
+
+
+# ------------------------------------------------------------------ FeHe
+class FeHeError(RuntimeError):
+    def __init__(self, status, message):
+        super().__init__(f"FeHe potential failed (status {status}): {message}")
+        self.status = status
+        self.message = message
+
+
+def fehe_force(pos, Z, box):
+    """(energy, forces) of rgpot_fehe_force (rgpot_fehe_capi.f90:36-63)."""
+    pos, box = _prep(pos, box)
+    Z = np.ascontiguousarray(Z, dtype=np.int32)
+    F = np.zeros_like(pos)
+    e = C.c_double(0.0)
+    err = C.create_string_buffer(512)
+    st = oracle_lib().oracle_fehe_force(len(pos), pos, Z, box, F, C.byref(e), err, 512)
+    if st != 0:
+        raise FeHeError(st, err.value.decode())
+    return e.value, F
+
+
+def fehe_scalar(which, x):
+    return oracle_lib().oracle_fehe_scalar(int(which), float(x))
 
 
 def cuh2_scalar(name, kind, x):

@@ -12,12 +12,12 @@
 #include "rgpot/fortran/FortranPots.hpp"
 #include "rgpot/types/AtomMatrix.hpp"
 
-// FortranPots.cc also references the six potentials this engine does not implement
+// FortranPots.cc also references the five potentials this engine does not implement
 extern "C" {
 #define STUB5(name) int name(int32_t, const double *, const double *, double *, double *) { return 99; }
 #define STUB6(name) int name(int32_t, const double *, const int32_t *, const double *, double *, double *) { return 99; }
 STUB5(rgpot_sw_force) STUB5(rgpot_edip_force) STUB5(rgpot_lenosky_force) STUB5(rgpot_tersoff_force)
-STUB6(rgpot_fehe_force) STUB6(rgpot_water_h_force)
+STUB6(rgpot_water_h_force)
 }
 
 int main() {
@@ -62,7 +62,23 @@ int main() {
       worst = std::fmax(worst, std::sqrt(f_al(i, 0) * f_al(i, 0) + f_al(i, 1) * f_al(i, 1) + f_al(i, 2) * f_al(i, 2)));
     if (std::fabs(e_al - (-5.217864)) > 1e-4 * 5.217864 || std::fabs(worst - 0.968647) > 1e-3 * 0.968647) ++bad;
   }
-  std::printf("reference fortranpots::CuH2Pot / EAMAlPot over librgpot_b200.so: E = %.16f, %s\n", energy,
+  {  // CppCore/tests/FortranPotsTest.cc:146-155 through the reference's own FeHePot class
+    auto fehe = rgpot::fortranpots::FeHePot();
+    AtomMatrix bcc{{7.13000, 7.13000, 7.13000},    {8.56500, 8.56500, 8.56500},   {7.13000, 7.13000, 10.00000},
+                   {8.56500, 8.56500, 11.43500},   {7.13000, 10.00000, 7.13000},  {8.56500, 11.43500, 8.56500},
+                   {7.13000, 10.00000, 10.00000},  {8.56500, 11.43500, 11.43500}, {10.00000, 7.13000, 7.13000},
+                   {11.43500, 8.56500, 8.56500},   {10.00000, 7.13000, 10.00000}, {11.43500, 8.56500, 11.43500},
+                   {10.00000, 10.00000, 7.13000},  {11.43500, 11.43500, 8.56500}, {10.00000, 10.00000, 10.00000},
+                   {11.43500, 11.43500, 11.43500}};
+    std::array<std::array<double, 3>, 3> cube{{{20.0, 0.0, 0.0}, {0.0, 20.0, 0.0}, {0.0, 0.0, 20.0}}};
+    auto [e_fe, f_fe, v_fe] = fehe(bcc, std::vector<int>(16, 26), cube);
+    (void)v_fe;
+    double worst = 0.0;
+    for (int i = 0; i < 16; ++i)
+      worst = std::fmax(worst, std::sqrt(f_fe(i, 0) * f_fe(i, 0) + f_fe(i, 1) * f_fe(i, 1) + f_fe(i, 2) * f_fe(i, 2)));
+    if (std::fabs(e_fe - (-43.959774)) > 1e-4 * 43.959774 || std::fabs(worst - 1.245094) > 1e-3 * 1.245094) ++bad;
+  }
+  std::printf("reference fortranpots::CuH2Pot / EAMAlPot / FeHePot over librgpot_b200.so: E = %.16f, %s\n", energy,
               bad ? "MISMATCH" : "ok");
   return bad ? 1 : 0;
 }

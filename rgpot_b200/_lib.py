@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("RGPOT_B200_ENGINE") or os.path.join(HERE, "librgpot_b200.so")
 CSRC = os.path.join(HERE, "csrc")
 
-KIND_LJ, KIND_LJ_CLUSTER, KIND_CUH2, KIND_MORSE, KIND_ZBL, KIND_EAM_AL = 0, 1, 2, 3, 4, 5
+KIND_LJ, KIND_LJ_CLUSTER, KIND_CUH2, KIND_MORSE, KIND_ZBL, KIND_EAM_AL, KIND_FEHE = 0, 1, 2, 3, 4, 5, 6
 
 
 class Config(C.Structure):
@@ -112,6 +112,7 @@ SYMBOLS = [
     ("rgpot_b200_core_last_error", C.c_char_p, []),
     ("rgpot_cuh2_force", _i, [C.c_int32, _vp, _vp, _vp, _vp, C.POINTER(_d)]),
     ("rgpot_eam_al_force", _i, [C.c_int32, _vp, _vp, _vp, C.POINTER(_d)]),
+    ("rgpot_fehe_force", _i, [C.c_int32, _vp, _vp, _vp, _vp, C.POINTER(_d)]),
     ("rgpot_fortran_last_error", _i, [C.c_char_p, _i]),
 ]
 

@@ -225,10 +225,11 @@ __global__ void k_order_gather(const double* __restrict__ pos, const int* __rest
   if (check_z == 2) {
     species = Z[i] & 15;  // ZBL: the host already mapped atomic numbers to type indices
   } else if (check_z) {
+    // check_z 1: CuH2 (29 -> 0, 1 -> 1, rgpot_cuh2.f90:463-489); 3: FeHe (26 -> 0, 2 -> 1, rgpot_fehe.f90:541-569)
     const int z = Z[i];
-    if (z == 29) {
+    if (z == (check_z == 3 ? 26 : 29)) {
       species = 0;
-    } else if (z == 1) {
+    } else if (z == (check_z == 3 ? 2 : 1)) {
       species = 1;
     } else {
       atomicOr(&st->flags, kFlagForeignZ);

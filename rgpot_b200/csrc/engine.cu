@@ -151,6 +151,59 @@ EamParams make_eam_params() {
   return p;
 }
 
+// Fe-He coefficients, rgpot_fehe.f90:47-156
+FeHeParams make_fehe_params() {
+  FeHeParams p{};
+  p.rcut_fe_pair = 5.3;
+  p.rcut_fe_rho = 4.2;
+  p.rcut_fehe_pair = 3.9028;
+  p.rcut_fehe_rho = 4.10;
+  p.rcut_he_pair = 5.4;
+  p.fe_zbl_scale = 9.7342365892908e+03;
+  const double w[4] = {0.18180, 0.50990, 0.28020, 0.02817};
+  const double d[4] = {2.8616724320005e+01, 8.4267310396064e+00, 3.6030244464156e+00, 1.8028536321603e+00};
+  const double b[4] = {7.4122709384068e+00, -6.4180690713367e-01, -2.6043547961722e+00, 6.2625393931230e-01};
+  memcpy(p.fe_zbl_weight, w, sizeof w);
+  memcpy(p.fe_zbl_decay, d, sizeof d);
+  memcpy(p.fe_bridge, b, sizeof b);
+  p.fe_bridge_lo = 1.0;
+  p.fe_bridge_hi = 2.05;
+  const double pk[13] = {2.2, 2.3, 2.4, 2.5, 2.6, 2.7, 2.8, 3.0, 3.3, 3.7, 4.2, 4.7, 5.3};
+  const double pc[13] = {-2.7444805994228e+01, 1.5738054058489e+01,  2.2077118733936e+00,  -2.4989799053251e+00,
+                         4.2099676494795e+00,  -7.7361294129713e-01, 8.0656414937789e-01,  -2.3194358924605e+00,
+                         2.6577406128280e+00,  -1.0260416933564e+00, 3.5018615891957e-01,  -5.8531821042271e-02,
+                         -3.0458824556234e-03};
+  memcpy(p.fe_pair_knot, pk, sizeof pk);
+  memcpy(p.fe_pair_coeff, pc, sizeof pc);
+  const double rk[3] = {2.4, 3.2, 4.2};
+  const double rcf[3] = {1.1686859407970e+01, -1.4710740098830e-02, 4.7193527075943e-01};
+  memcpy(p.fe_rho_knot, rk, sizeof rk);
+  memcpy(p.fe_rho_coeff, rcf, sizeof rcf);
+  p.fe_emb_quadratic = -6.7314115586063e-04;
+  p.fe_emb_quartic = 7.6514905604792e-08;
+  const double hk[8] = {1.5440, 1.6155, 1.6896, 1.8017, 2.0482, 2.3816, 3.5067, 3.9028};
+  const double hc[8] = {559.804426025391, -45.916354995728, 35.550312671661, 164.319865173340,
+                        -1.727464405060,  0.106771826237,   0.073715269849,  0.038235287677};
+  memcpy(p.fehe_knot, hk, sizeof hk);
+  memcpy(p.fehe_coeff, hc, sizeof hc);
+  p.sband_amp = 20.0;
+  p.sband_decay = 1.5312426703208 / 0.529177210818181818;
+  p.sband_emb_sqrt = 0.220813420485;
+  p.sband_emb_quadratic = 1.367508764130;
+  p.sband_emb_quartic = 3.382256025271;
+  p.he_rm = 2.9683;
+  p.he_c6 = 1.35186623;
+  p.he_c8 = 0.41495143;
+  p.he_c10 = 0.17151143;
+  p.he_aa = 186924.404;
+  p.he_alpha = 10.5717543;
+  p.he_beta = -2.07758779;
+  p.he_damp = 1.438;
+  p.he_eps = 10.956 * 1.380658e-23 / 1.602177e-19;
+  p.rho_floor = 1.0e-35;
+  return p;
+}
+
 // EAM-Al (rgpot_eam_al.f90:44-76) mapped onto slot 0 of the same tables; shifts evaluated on the
 // host with libm like the reference does (pair_shape(rcut), density_shape(rcut), :103-122).
 EamParams make_eam_al_params() {
@@ -228,7 +281,7 @@ struct RgpotB200Pot {
 
   // single-system scratch
   DevBuf pos, Z, F, cell_of, rank, ashift, counts, starts, blocksums, order, order2, spos, scell, dfd, eemb,
-      partials, partials2, energy, status, mm, emit_pairs, emit_shifts, emit_count, emit_vecs, emit_dists;
+      dfs, partials, partials2, energy, status, mm, emit_pairs, emit_shifts, emit_count, emit_vecs, emit_dists;
   // batch scratch
   DevBuf b_pos, b_Z, b_F, b_off, b_boxes, b_E, b_flags, b_bad, b_map;
   HostBuf h_pos, h_Z, h_F, h_off, h_boxes, h_E, h_flags, h_bad, h_small;
@@ -253,7 +306,7 @@ struct RgpotB200Pot {
   ~RgpotB200Pot() {
     cudaSetDevice(device);
     DevBuf* d[] = {&pos, &Z, &F, &cell_of, &rank, &ashift, &counts, &starts, &blocksums, &order, &order2,
-                   &spos, &scell, &dfd, &eemb, &partials, &partials2, &energy, &status, &mm, &emit_pairs,
+                   &spos, &scell, &dfd, &dfs, &eemb, &partials, &partials2, &energy, &status, &mm, &emit_pairs,
                    &emit_shifts, &emit_count, &emit_vecs, &emit_dists, &b_pos, &b_Z, &b_F, &b_off, &b_boxes, &b_E, &b_flags,
                    &b_bad, &b_map, &zbl_table};
     for (auto* b : d) b->release();
@@ -387,6 +440,8 @@ namespace {
 inline int div_up(long a, int b) { return (int)((a + b - 1) / b); }
 
 inline bool is_eam(int kind) { return kind == RGPOT_B200_CUH2 || kind == RGPOT_B200_EAM_AL; }
+// potentials that read atomic numbers and refuse foreign species (CuH2: 29 / 1, FeHe: 26 / 2)
+inline bool reads_species(int kind) { return kind == RGPOT_B200_CUH2 || kind == RGPOT_B200_FEHE; }
 inline double eam_rcut(int kind) { return kind == RGPOT_B200_EAM_AL ? 7.1 : 6.1; }
 
 int check_launch(RgpotB200Pot* pot, const char* what) {
@@ -577,9 +632,10 @@ int run_cell_path(RgpotB200Pot* pot, long n, const double* d_pos, const int* d_Z
   const int kind = nlist ? RGPOT_B200_LJ : pot->cfg.kind;
   const bool eam = is_eam(kind);
   const bool al = kind == RGPOT_B200_EAM_AL;
-  const bool images = eam || pot->cfg.lj_all_images || nlist;
+  const bool fehe = kind == RGPOT_B200_FEHE;
+  const bool images = eam || fehe || pot->cfg.lj_all_images || nlist;
   Plan pl{};
-  const double rc = nlist ? nlist_rc : (eam ? eam_rcut(kind) : pot->lj_rc);
+  const double rc = nlist ? nlist_rc : (fehe ? 5.4 : (eam ? eam_rcut(kind) : pot->lj_rc));
 
   CU_TRY(pot, pot->status.reserve(sizeof(Status)));
   Status init{};
@@ -693,10 +749,11 @@ int run_cell_path(RgpotB200Pot* pot, long n, const double* d_pos, const int* d_Z
   const int nblk = div_up(n, 128);
   const int npart = std::max(nblk, ncells);
   CU_TRY(pot, pot->partials.reserve(sizeof(double) * npart));
-  if (eam) {
+  if (eam || fehe) {
     CU_TRY(pot, pot->dfd.reserve(sizeof(double) * n));
     CU_TRY(pot, pot->eemb.reserve(sizeof(double) * n));
   }
+  if (fehe) CU_TRY(pot, pot->dfs.reserve(sizeof(double) * n));
 
   Status* d_st = pot->status.as<Status>();
   CU_TRY(pot, cudaMemsetAsync(pot->counts.p, 0, sizeof(int) * ((size_t)ncells + 1), st));
@@ -716,7 +773,7 @@ int run_cell_path(RgpotB200Pot* pot, long n, const double* d_pos, const int* d_Z
   LAUNCH_CHECK(pot, "k_scatter");
   k_order_gather<<<div_up(n, 256), 256, 0, st>>>(d_pos, d_Z, pot->starts.as<int>(), pot->cell_of.as<int>(),
                                                  pot->order.as<int>(), pot->ashift.as<int>(), (int)n,
-                                                 kind == RGPOT_B200_CUH2 ? 1 : (kind == RGPOT_B200_ZBL ? 2 : 0),
+                                                 kind == RGPOT_B200_CUH2 ? 1 : (kind == RGPOT_B200_ZBL ? 2 : (fehe ? 3 : 0)),
                                                  pot->spos.as<double4>(), pot->scell.as<int>(), d_st);
   LAUNCH_CHECK(pot, "k_order_gather");
 
@@ -745,6 +802,15 @@ int run_cell_path(RgpotB200Pot* pot, long n, const double* d_pos, const int* d_Z
 
   double* d_part = pot->partials.as<double>();
   int npart_used = nblk;
+  if (fehe) {
+    // Fe-He: the three passes on the gather walk (rgpot_fehe.f90:573-620)
+    k_fehe_density<<<nblk, 128, 0, st>>>(ga, pot->dfd.as<double>(), pot->dfs.as<double>(), pot->eemb.as<double>());
+    LAUNCH_CHECK(pot, "k_fehe_density");
+    k_fehe_force<<<nblk, 128, 0, st>>>(ga, pot->dfd.as<double>(), pot->dfs.as<double>(), pot->eemb.as<double>(), d_F,
+                                       d_part);
+    LAUNCH_CHECK(pot, "k_fehe_force");
+    return reduce_energy(pot, d_part, nblk, d_E, st);
+  }
   if (eam) {
     BrickPlan bp{};
     const bool tile_ok = allow_tile && plan_bricks(pot, pl, n, rc, true, bp);
@@ -905,6 +971,7 @@ int launch_small(RgpotB200Pot* pot, size_t nsys, long nmax, const long long* d_o
 
 // can a system of n atoms run on the all-pairs kernels?
 bool small_eligible(const RgpotB200Pot* pot, long n) {
+  if (pot->cfg.kind == RGPOT_B200_FEHE) return false;  // gather path only (two density channels)
   if (is_eam(pot->cfg.kind)) return n <= 512 && eam_small_maxnb(pot, n) > 0;
   if (pot->cfg.lj_all_images) return false;  // opt-in mode lives on the cell path only
   return n <= 2048;
@@ -914,6 +981,13 @@ bool small_eligible(const RgpotB200Pot* pot, long n) {
 // classify (2) before the table build (1) before the coincidence guard (3).
 int map_flags(RgpotB200Pot* pot, unsigned flags, int bad_atom, int bad_z, const double* host_pos) {
   const bool eam = is_eam(pot->cfg.kind);
+  if (pot->cfg.kind == RGPOT_B200_FEHE && (flags & kFlagForeignZ)) {
+    char buf[256];  // rgpot_fehe.f90:558-563
+    snprintf(buf, sizeof buf,
+             "rgpot_fehe: unsupported atomic number %d on atom %d; this potential covers iron (26) and helium (2) only",
+             bad_z, bad_atom + 1);
+    return fail(pot, 2, buf);
+  }
   if (pot->cfg.kind == RGPOT_B200_CUH2 && (flags & kFlagForeignZ)) {
     char buf[256];
     snprintf(buf, sizeof buf,
@@ -1079,7 +1153,7 @@ void rgpot_b200_default_config(int kind, RgpotB200Config* cfg) {
   cfg->kind = kind;
   cfg->device = -1;
   cfg->u0 = 1.0;
-  cfg->cutoff = is_eam(kind) ? eam_rcut(kind) : (kind == RGPOT_B200_MORSE ? 9.5 : (kind == RGPOT_B200_ZBL ? 2.5 : 15.0));
+  cfg->cutoff = kind == RGPOT_B200_FEHE ? 5.4 : is_eam(kind) ? eam_rcut(kind) : (kind == RGPOT_B200_MORSE ? 9.5 : (kind == RGPOT_B200_ZBL ? 2.5 : 15.0));
   cfg->zbl_cut_inner = 2.0;  // ZBLPot.hpp:29-32
   cfg->psi = 1.0;
   cfg->morse_De = 0.7102;  // MorsePot.hpp:31-36 (platinum)
@@ -1093,7 +1167,7 @@ RgpotB200Pot* rgpot_b200_create(const RgpotB200Config* cfg, char* errbuf, size_t
     return nullptr;
   };
   if (!cfg) return err("rgpot_b200_create: null config");
-  if (cfg->kind < RGPOT_B200_LJ || cfg->kind > RGPOT_B200_EAM_AL)
+  if (cfg->kind < RGPOT_B200_LJ || cfg->kind > RGPOT_B200_FEHE)
     return err("rgpot_b200_create: unknown potential kind");
   if (cfg->kind == RGPOT_B200_ZBL && (!(cfg->zbl_cut_inner > 0.0) || !(cfg->zbl_cut_inner < cfg->cutoff)))
     return err("ZBLPot: invalid cutoffs, require 0.0 < cut_inner < cut_global.");  // ZBLPot.cc:76-79
@@ -1137,6 +1211,12 @@ RgpotB200Pot* rgpot_b200_create(const RgpotB200Config* cfg, char* errbuf, size_t
                                         : cudaMemcpyToSymbol(c_eam, &p, sizeof p)) != cudaSuccess) {
       delete pot;
       return err("rgpot_b200_create: cannot upload the EAM coefficients");
+    }
+  } else if (cfg->kind == RGPOT_B200_FEHE) {
+    const FeHeParams p = make_fehe_params();
+    if (cudaMemcpyToSymbol(c_fehe, &p, sizeof p) != cudaSuccess) {
+      delete pot;
+      return err("rgpot_b200_create: cannot upload the Fe-He coefficients");
     }
   } else {
     lj_setup(pot);
@@ -1342,10 +1422,10 @@ int rgpot_b200_force_device(RgpotB200Pot* pot, long nAtoms, const double* d_posi
   cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : pot->stream;
   pot->pend.active = false;
   if (nAtoms < 0 || nAtoms > kMaxAtoms) return fail(pot, kStatusArgs, "rgpot_b200: bad atom count");
-  const bool eam = pot->cfg.kind == RGPOT_B200_CUH2;  // (reads atomic numbers)
+  const bool eam = reads_species(pot->cfg.kind);  // (reads atomic numbers)
   // reference early-outs: rgpot_cuh2_capi.f90:50 / rgpot_eam_al_capi.f90:50 (natoms < 1), LJPot.cc:50-52,
   // LJClusterPot.cc:43-45
-  const bool trivial = is_eam(pot->cfg.kind) ? nAtoms < 1
+  const bool trivial = (is_eam(pot->cfg.kind) || pot->cfg.kind == RGPOT_B200_FEHE) ? nAtoms < 1
                            : (nAtoms < 2 || (pot->cfg.kind != RGPOT_B200_LJ_CLUSTER && pot->cfg.kind != RGPOT_B200_ZBL && !(pot->cfg.cutoff > 0.0)));
   if (trivial) {
     if (nAtoms > 0) CU_TRY(pot, cudaMemsetAsync(d_forces, 0, sizeof(double) * 3 * nAtoms, st));
@@ -1433,8 +1513,8 @@ int rgpot_b200_force(RgpotB200Pot* pot, long nAtoms, const double* positions, co
     return fail(pot, kStatusArgs, "rgpot_b200_force: null buffer");
   CU_TRY(pot, cudaSetDevice(pot->device));
   if (nAtoms < 0 || nAtoms > kMaxAtoms) return fail(pot, kStatusArgs, "rgpot_b200: bad atom count");
-  const bool eam = pot->cfg.kind == RGPOT_B200_CUH2;  // (reads atomic numbers)
-  const bool trivial = is_eam(pot->cfg.kind) ? nAtoms < 1
+  const bool eam = reads_species(pot->cfg.kind);  // (reads atomic numbers)
+  const bool trivial = (is_eam(pot->cfg.kind) || pot->cfg.kind == RGPOT_B200_FEHE) ? nAtoms < 1
                            : (nAtoms < 2 || (pot->cfg.kind != RGPOT_B200_LJ_CLUSTER && pot->cfg.kind != RGPOT_B200_ZBL && !(pot->cfg.cutoff > 0.0)));
   if (trivial) return 0;
   const bool zbl = pot->cfg.kind == RGPOT_B200_ZBL;
@@ -1487,7 +1567,7 @@ int rgpot_b200_neighbors(RgpotB200Pot* pot, long nAtoms, const double* positions
   if (nAtoms < 1) return 0;
   cudaStream_t st = pot->stream;
   const size_t n = (size_t)nAtoms;
-  const bool eam = pot->cfg.kind == RGPOT_B200_CUH2;
+  const bool eam = reads_species(pot->cfg.kind);
   CU_TRY(pot, pot->pos.reserve(sizeof(double) * 3 * n));
   CU_TRY(pot, pot->F.reserve(sizeof(double) * 3 * n));
   CU_TRY(pot, pot->energy.reserve(sizeof(double)));
@@ -1842,7 +1922,7 @@ int rgpot_b200_force_batch_device(RgpotB200Pot* pot, size_t nSystems, const size
   if (nSystems == 0) return 0;
   if (!offsets || !d_boxes || !d_positions || !d_forces || !d_energies)
     return fail(pot, kStatusArgs, "rgpot_b200_force_batch_device: null buffer");
-  if (pot->cfg.kind == RGPOT_B200_CUH2 && !d_atomicNrs)
+  if (reads_species(pot->cfg.kind) && !d_atomicNrs)
     return fail(pot, kStatusArgs, "rgpot_b200: CuH2 needs atomic numbers");
   if (pot->cfg.kind == RGPOT_B200_ZBL)
     return fail(pot, kStatusArgs, "rgpot_b200: ZBL batches go through the host entry points "
@@ -1887,7 +1967,7 @@ template <class StageIn, class StageOut>
 static int batch_pipeline(RgpotB200Pot* pot, size_t nsys, const size_t* rel, long nmax, const double* h_pos,
                           const int* h_Z, const double* h_boxes, double* h_F, double* h_E, int* statuses,
                           StageIn&& stage_in, StageOut&& stage_out) {
-  const bool eam = pot->cfg.kind == RGPOT_B200_CUH2 || pot->cfg.kind == RGPOT_B200_ZBL;  // has a Z array
+  const bool eam = reads_species(pot->cfg.kind) || pot->cfg.kind == RGPOT_B200_ZBL;  // has a Z array
   const size_t total = rel[nsys];
   CU_TRY(pot, pot->b_pos.reserve(sizeof(double) * 3 * std::max<size_t>(total, 1)));
   CU_TRY(pot, pot->b_F.reserve(sizeof(double) * 3 * std::max<size_t>(total, 1)));
@@ -1995,7 +2075,7 @@ int rgpot_b200_force_batch_packed(RgpotB200Pot* pot, size_t nSystems, const size
   if (!offsets || !positions || !boxes || !forces || !energies)
     return fail(pot, kStatusArgs, "rgpot_b200_force_batch_packed: null buffer");
   const bool zbl = pot->cfg.kind == RGPOT_B200_ZBL;
-  const bool eam = pot->cfg.kind == RGPOT_B200_CUH2 || zbl;  // "carries a per-atom integer array"
+  const bool eam = reads_species(pot->cfg.kind) || zbl;  // "carries a per-atom integer array"
   if (eam && !atomicNrs) return fail(pot, kStatusArgs, "rgpot_b200: this potential needs atomic numbers");
   CU_TRY(pot, cudaSetDevice(pot->device));
   cudaStream_t st = pot->stream;
@@ -2058,7 +2138,7 @@ int rgpot_b200_force_batch(RgpotB200Pot* pot, size_t nSystems, const size_t* nAt
   if (!nAtoms || !positions || !forces || !energies)
     return fail(pot, kStatusArgs, "rgpot_b200_force_batch: null buffer");
   const bool zbl = pot->cfg.kind == RGPOT_B200_ZBL;
-  const bool eam = pot->cfg.kind == RGPOT_B200_CUH2 || zbl;  // carries a per-atom integer array
+  const bool eam = reads_species(pot->cfg.kind) || zbl;  // carries a per-atom integer array
   if (eam && !atomicNrs) return fail(pot, kStatusArgs, "rgpot_b200: this potential needs atomic numbers");
   CU_TRY(pot, cudaSetDevice(pot->device));
   std::vector<size_t> off(nSystems + 1, 0);
@@ -2157,6 +2237,30 @@ int rgpot_eam_al_force(int32_t natoms, const double* positions, const double* ce
   }
   int s = rgpot_b200_force(g_eam_al, natoms, positions, nullptr, forces, energy, nullptr, cell);
   if (s) g_last_fortran_error = g_eam_al->last_error;
+  return s;
+}
+
+// FortranPots.cc: rgpot_fehe_force(natoms, positions, atomic_numbers, cell, forces, energy), rgpot_fehe_capi.f90:36-63
+static RgpotB200Pot* g_fehe = nullptr;
+
+int rgpot_fehe_force(int32_t natoms, const double* positions, const int32_t* atomic_numbers, const double* cell,
+                     double* forces, double* energy) {
+  std::lock_guard<std::mutex> lk(g_cuh2_mu);
+  g_last_fortran_error.clear();
+  if (!g_fehe) {
+    RgpotB200Config cfg;
+    rgpot_b200_default_config(RGPOT_B200_FEHE, &cfg);
+    char err[256] = {0};
+    g_fehe = rgpot_b200_create(&cfg, err, sizeof err);
+    if (!g_fehe) {
+      g_last_fortran_error = err;
+      if (energy) *energy = 0.0;
+      if (forces && natoms > 0) memset(forces, 0, sizeof(double) * 3 * (size_t)natoms);
+      return kStatusCuda;
+    }
+  }
+  int s = rgpot_b200_force(g_fehe, natoms, positions, atomic_numbers, forces, energy, nullptr, cell);
+  if (s) g_last_fortran_error = g_fehe->last_error;
   return s;
 }
 

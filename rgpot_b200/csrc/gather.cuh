@@ -251,6 +251,67 @@ k_eam_force(GatherArgs a, const double* __restrict__ dfd_sorted,
   if (threadIdx.x == 0) partials[blockIdx.x] = bs;
 }
 
+// ---- Fe-He (rgpot_fehe.f90:573-620): the three passes on the gather walk ---------------------------
+// First correct CUDA path of this potential: thread per atom, all system sizes (the brick and
+// batch kernels do not carry its two density channels yet).
+__global__ void __launch_bounds__(128)
+k_fehe_density(GatherArgs a, double* __restrict__ dfd_sorted, double* __restrict__ dfs_sorted,
+               double* __restrict__ eemb_sorted) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.n) return;
+  const double4 pi = a.spos[i];
+  const int zi = meta_species((unsigned long long)__double_as_longlong(pi.w));
+  double rho_d = 0.0, rho_s = 0.0;
+  auto body = [&](int, unsigned long long mj, double, double, double, double d2, int, int, int) {
+    double rho, drho;
+    const int ch = fehe_density(zi, meta_species(mj), sqrt(d2), rho, drho);  // atom_densities :480-500
+    if (ch == 0) rho_d += rho;
+    if (ch == 1) rho_s += rho;
+  };
+  walk_dispatch<GEO_IMAGES>(a, i, pi, body);
+  double e, dfd, dfs;
+  fehe_embed(zi, rho_d, rho_s, e, dfd, dfs);
+  dfd_sorted[i] = dfd;
+  dfs_sorted[i] = dfs;
+  eemb_sorted[i] = e;
+}
+
+__global__ void __launch_bounds__(128)
+k_fehe_force(GatherArgs a, const double* __restrict__ dfd_sorted, const double* __restrict__ dfs_sorted,
+             const double* __restrict__ eemb_sorted, double* __restrict__ F, double* __restrict__ partials) {
+  __shared__ double sh32[32];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  double e = 0.0, fx = 0.0, fy = 0.0, fz = 0.0;
+  if (i < a.n) {
+    const double4 pi = a.spos[i];
+    const unsigned long long mi = (unsigned long long)__double_as_longlong(pi.w);
+    const int zi = meta_species(mi);
+    const double dfd_i = dfd_sorted[i], dfs_i = dfs_sorted[i];
+    auto body = [&](int j, unsigned long long mj, double dx, double dy, double dz, double d2, int, int, int) {
+      const int zj = meta_species(mj);
+      const double r = sqrt(d2);  // table%dist
+      double v, dv, rho, drho;
+      fehe_pair(zi, zj, r, v, dv);
+      const int ch = fehe_density(zi, zj, r, rho, drho);
+      e += 0.5 * v;  // atom_contribution :509-538
+      double radial = dv;
+      if (ch == 0) radial += (dfd_i + dfd_sorted[j]) * drho;
+      if (ch == 1) radial += (dfs_i + dfs_sorted[j]) * drho;
+      fx += radial * (dx / r);
+      fy += radial * (dy / r);
+      fz += radial * (dz / r);
+    };
+    walk_dispatch<GEO_IMAGES>(a, i, pi, body);
+    e += eemb_sorted[i];
+    const int o = meta_orig(mi);
+    F[3 * (size_t)o] = fx;
+    F[3 * (size_t)o + 1] = fy;
+    F[3 * (size_t)o + 2] = fz;
+  }
+  const double bs = block_sum(e, sh32);
+  if (threadIdx.x == 0) partials[blockIdx.x] = bs;
+}
+
 // ---- neighbor-table emission (pair-set parity, list consumers) ----------------------------------
 template <int GEO>
 __global__ void k_emit_pairs(GatherArgs a, EmitArgs em) {

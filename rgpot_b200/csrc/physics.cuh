@@ -314,4 +314,121 @@ RB_D void eam_force_entry(int zi, int zj, double dfd_i, double dfd_j, double vx,
   fz = fma(w, vz, fz);
 }
 
+// ---- Fe-He EAM (CppCore/rgpot/fortran/rgpot_fehe.f90) ----------------------------------------------
+// Three pair terms, two density channels (d-band: Fe-Fe pairs, embedded on Fe; s-band: Fe-He pairs,
+// embedded on both), five cutoffs.  Every branch of the reference is a comparison on r = sqrt(d2)
+// (the table's IEEE square root), so the kernels take the same correctly rounded sqrt and compare
+// the same way: which term, which spline piece and which cutoff applies is decided exactly as
+// upstream.  Species: 0 Fe, 1 He.
+struct FeHeParams {
+  double rcut_fe_pair, rcut_fe_rho, rcut_fehe_pair, rcut_fehe_rho, rcut_he_pair;
+  double fe_zbl_scale, fe_zbl_weight[4], fe_zbl_decay[4];
+  double fe_bridge[4], fe_bridge_lo, fe_bridge_hi;
+  double fe_pair_knot[13], fe_pair_coeff[13];
+  double fe_rho_knot[3], fe_rho_coeff[3];
+  double fe_emb_quadratic, fe_emb_quartic;
+  double fehe_knot[8], fehe_coeff[8];
+  double sband_amp, sband_decay, sband_emb_sqrt, sband_emb_quadratic, sband_emb_quartic;
+  double he_rm, he_c6, he_c8, he_c10, he_aa, he_alpha, he_beta, he_damp, he_eps;
+  double rho_floor;
+};
+__constant__ FeHeParams c_fehe;
+
+template <int N>
+RB_D void knot_spline(const double* knot, const double* coeff, double r, double& v, double& dv) {
+  // sum_k a_k max(r_k - r, 0)^3 and its derivative -3 sum_k a_k max(r_k - r, 0)^2   :194, :223
+  double s3 = 0.0, s2 = 0.0;
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
+    const double t = fmax(knot[k] - r, 0.0);
+    const double t2 = t * t;
+    s2 += coeff[k] * t2;
+    s3 += coeff[k] * (t2 * t);
+  }
+  v = s3;
+  dv = -3.0 * s2;
+}
+
+// pair energy and dV/dr of the species combination   :182-304, :421-438
+RB_D void fehe_pair(int zi, int zj, double r, double& v, double& dv) {
+  const FeHeParams& P = c_fehe;
+  v = dv = 0.0;
+  if ((zi | zj) == 0) {  // Fe-Fe
+    if (r > P.rcut_fe_pair) return;
+    if (r < P.fe_bridge_lo) {
+      double s1 = 0.0, s2 = 0.0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const double sc = P.fe_zbl_weight[k] * exp(-P.fe_zbl_decay[k] * r);
+        s1 += sc;
+        s2 += P.fe_zbl_decay[k] * sc;
+      }
+      v = P.fe_zbl_scale / r * s1;
+      dv = -P.fe_zbl_scale / (r * r) * s1 - P.fe_zbl_scale / r * s2;
+    } else if (r < P.fe_bridge_hi) {
+      const double expo = exp(P.fe_bridge[0] + P.fe_bridge[1] * r + P.fe_bridge[2] * r * r + P.fe_bridge[3] * r * r * r);
+      v = expo;
+      dv = expo * (P.fe_bridge[1] + 2.0 * P.fe_bridge[2] * r + 3.0 * P.fe_bridge[3] * r * r);
+    } else {
+      knot_spline<13>(P.fe_pair_knot, P.fe_pair_coeff, r, v, dv);
+    }
+  } else if ((zi & zj) == 1) {  // He-He, HFD-B
+    if (r > P.rcut_he_pair) return;
+    const double x = r / P.he_rm;
+    const double x2 = x * x, x4 = x2 * x2, x6 = x2 * x4, x8 = x4 * x4, x10 = x2 * x8;
+    const double dispersion = P.he_c6 / x6 + P.he_c8 / x8 + P.he_c10 / x10;
+    const double ddispersion = -(6.0 * P.he_c6 / (x6 * x) + 8.0 * P.he_c8 / (x8 * x) + 10.0 * P.he_c10 / (x10 * x));
+    const double core = P.he_aa * exp(-P.he_alpha * x + P.he_beta * x * x);
+    double damp = 1.0, ddamp = 0.0;
+    if (x < P.he_damp) {
+      const double q = P.he_damp / x - 1.0;
+      damp = exp(-(q * q));
+      ddamp = damp * 2.0 * P.he_damp * q / (x * x);
+    }
+    v = P.he_eps * (core - damp * dispersion);
+    dv = P.he_eps * (core * (-P.he_alpha + 2.0 * P.he_beta * x) - ddamp * dispersion - damp * ddispersion) / P.he_rm;
+  } else {  // Fe-He
+    if (r > P.rcut_fehe_pair) return;
+    knot_spline<8>(P.fehe_knot, P.fehe_coeff, r, v, dv);
+  }
+}
+
+// density the pair feeds into ITS channel (d-band for Fe-Fe, s-band for Fe-He, none for He-He) and
+// the radial derivative   :311-355, :442-473.  Returns the channel: 0 d-band, 1 s-band, -1 none.
+RB_D int fehe_density(int zi, int zj, double r, double& rho, double& drho) {
+  const FeHeParams& P = c_fehe;
+  rho = drho = 0.0;
+  if ((zi | zj) == 0) {
+    if (!(r > P.rcut_fe_rho)) knot_spline<3>(P.fe_rho_knot, P.fe_rho_coeff, r, rho, drho);
+    return 0;
+  }
+  if (zi != zj) {
+    if (!(r > P.rcut_fehe_rho)) {
+      const double ex = exp(-2.0 * P.sband_decay * r);
+      rho = P.sband_amp * (r * (r * r)) * ex;
+      drho = P.sband_amp * (r * r) * ex * (3.0 - 2.0 * P.sband_decay * r);
+    }
+    return 1;
+  }
+  return -1;
+}
+
+// embedding of both channels   :363-413
+RB_D void fehe_embed(int species, double rho_d, double rho_s, double& e, double& dfd, double& dfs) {
+  const FeHeParams& P = c_fehe;
+  double ed = 0.0, es = 0.0;
+  dfd = dfs = 0.0;
+  if (species == 0 && !(rho_d < P.rho_floor)) {
+    const double sq = sqrt(rho_d), r2 = rho_d * rho_d;
+    ed = -sq + P.fe_emb_quadratic * r2 + P.fe_emb_quartic * (r2 * r2);
+    dfd = -0.5 / sq + 2.0 * P.fe_emb_quadratic * rho_d + 4.0 * P.fe_emb_quartic * (rho_d * r2);
+  }
+  if (!(rho_s < P.rho_floor)) {
+    const double sq = sqrt(rho_s), r2 = rho_s * rho_s;
+    es = P.sband_emb_sqrt * sq + P.sband_emb_quadratic * r2 + P.sband_emb_quartic * (r2 * r2);
+    dfs = 0.5 * P.sband_emb_sqrt / sq + 2.0 * P.sband_emb_quadratic * rho_s + 4.0 * P.sband_emb_quartic * (rho_s * r2);
+  }
+  e = ed + es;
+}
+
 }  // namespace rb

@@ -39,7 +39,7 @@ Engine::Engine(int kind, const LJCudaConfig &c) {
   cfg.device = c.device;
   Fnv fp;
   fp.u64(kKernelVersion);
-  if (kind == RGPOT_B200_EAM_AL) {
+  if (kind == RGPOT_B200_EAM_AL || kind == RGPOT_B200_FEHE) {
     fp.u64((uint64_t)kind);  // parameter-free like CuH2; the kind keeps the two keys apart
   } else if (kind != RGPOT_B200_CUH2) {
     cfg.u0 = c.u0;

@@ -108,6 +108,8 @@ RGPOT_B200_POT_CLASS(LJClusterCudaPot, LJCluster, RGPOT_B200_LJ_CLUSTER, "LJClus
 RGPOT_B200_POT_CLASS(CuH2CudaPot, CuH2, RGPOT_B200_CUH2, "CuH2", true);
 /// fortranpots::EAMAlPot on the engine (fortran/FortranPots.hpp:43): atomic numbers are not read.
 RGPOT_B200_POT_CLASS(EAMAlCudaPot, EAMAl, RGPOT_B200_EAM_AL, "EAM-Al", true);
+/// fortranpots::FeHePot on the engine (fortran/FortranPots.hpp:44): atomic numbers 26 / 2.
+RGPOT_B200_POT_CLASS(FeHeCudaPot, FeHe, RGPOT_B200_FEHE, "FeHe", true);
 
 #undef RGPOT_B200_POT_CLASS
 

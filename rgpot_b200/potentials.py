@@ -55,6 +55,7 @@ class PotType(Enum):
     LJCluster = 9
     ZBL = 10
     EAMAl = 15
+    FeHe = 16
 
 
 @dataclass
@@ -158,7 +159,7 @@ class _EnginePot:
             cfg.cutoff = float(morse.cutoff)
         elif self._kind == _lib.KIND_ZBL:
             cfg.zbl_cut_inner, cfg.cutoff = float(zbl.cut_inner), float(zbl.cut_global)
-        elif self._kind not in (_lib.KIND_CUH2, _lib.KIND_EAM_AL):
+        elif self._kind not in (_lib.KIND_CUH2, _lib.KIND_EAM_AL, _lib.KIND_FEHE):
             cfg.u0, cfg.cutoff, cfg.psi = float(u0), float(cutoff), float(psi)
             cfg.lj_all_images = int(bool(lj_all_images))
         self._cfg = cfg
@@ -188,7 +189,7 @@ class _EnginePot:
     def paramsKey(self) -> int:
         if self._kind == _lib.KIND_CUH2:
             return _fnv1a([struct.pack("<Q", _KERNEL_VERSION)])
-        if self._kind == _lib.KIND_EAM_AL:  # parameter-free like CuH2; the kind keeps the two apart
+        if self._kind in (_lib.KIND_EAM_AL, _lib.KIND_FEHE):  # parameter-free like CuH2; the kind keeps them apart
             return _fnv1a([struct.pack("<Q", _KERNEL_VERSION), struct.pack("<i", self._kind)])
         c = self._cfg
         if self._kind == _lib.KIND_ZBL:  # ZBLPot.cc:80-84
@@ -427,6 +428,16 @@ class EAMAlPot(_EnginePot):
     rgpot_eam_al.f90).  Single species: atomic numbers are accepted and not read."""
 
     _kind, _label, _type = _lib.KIND_EAM_AL, "EAM-Al", PotType.EAMAl
+
+    def __init__(self, device: int = -1):
+        super().__init__(device=device)
+
+
+class FeHePot(_EnginePot):
+    """Fe-He embedded-atom potential (fortranpots::FeHePot, FortranPots.hpp:44, rgpot_fehe.f90):
+    atomic numbers 26 and 2, anything else raises (status 2)."""
+
+    _kind, _label, _type = _lib.KIND_FEHE, "FeHe", PotType.FeHe
 
     def __init__(self, device: int = -1):
         super().__init__(device=device)

@@ -738,3 +738,81 @@ def test_neighbor_list_is_bit_identical_to_vesin(oracle, case, full):
         assert (a[:, 0] == a[:, 1]).any()  # self images present
     # sorted output: ordered by the first index
     assert (np.diff(ours["pairs"][:, 0]) >= 0).all()
+
+
+# ------------------------------------------------------------- FeHe
+FE_BCC = np.array([[7.13, 7.13, 7.13], [8.565, 8.565, 8.565], [7.13, 7.13, 10.0], [8.565, 8.565, 11.435],
+                   [7.13, 10.0, 7.13], [8.565, 11.435, 8.565], [7.13, 10.0, 10.0], [8.565, 11.435, 11.435],
+                   [10.0, 7.13, 7.13], [11.435, 8.565, 8.565], [10.0, 7.13, 10.0], [11.435, 8.565, 11.435],
+                   [10.0, 10.0, 7.13], [11.435, 11.435, 8.565], [10.0, 10.0, 10.0], [11.435, 11.435, 11.435]])
+
+
+def _fehe_cell(n_side, n_he, seed, rattle=0.04, box=None):
+    a = 2.8553
+    base = np.array([[0.0, 0.0, 0.0], [0.5, 0.5, 0.5]])
+    cells = np.stack(np.meshgrid(*[np.arange(n_side)] * 3, indexing="ij"), -1).reshape(-1, 3)
+    frac = (cells[:, None, :] + base[None, :, :]).reshape(-1, 3) / n_side
+    rng = np.random.default_rng(seed)
+    H = np.eye(3) * n_side * a if box is None else box
+    pos = frac @ H + rng.normal(0, rattle, frac.shape)
+    Z = np.full(len(pos), 26, np.int32)
+    Z[rng.choice(len(pos), size=n_he, replace=False)] = 2
+    return pos, Z, H
+
+
+def test_fehe_eon_pin_and_dropin_symbol():
+    """FortranPotsTest.cc:146-155 through the class and through rgpot_fehe_force."""
+    import ctypes as C
+
+    from rgpot_b200 import _lib
+    pot = rgpot_b200.FeHePot()
+    Z = np.full(16, 26, np.int32)
+    e, f, v = pot(FE_BCC, Z, np.eye(3) * 20.0)
+    assert e == pytest.approx(-43.959774, rel=1e-4) and v == 0.0
+    assert np.sqrt((f ** 2).sum(1)).max() == pytest.approx(1.245094, rel=1e-3)
+    assert np.abs(f.sum(0)).max() < 1e-9
+    assert pot.get_type() == rgpot_b200.PotType.FeHe
+    F = np.zeros((16, 3))
+    e2 = C.c_double()
+    cell = np.ascontiguousarray(np.eye(3) * 20.0)
+    st = _lib.lib().rgpot_fehe_force(16, FE_BCC.ctypes.data, Z.ctypes.data, cell.ctypes.data, F.ctypes.data, C.byref(e2))
+    assert st == 0 and e2.value == e and np.array_equal(F, f)
+
+
+@pytest.mark.parametrize("n_side,n_he,triclinic", [(2, 2, False), (3, 6, False), (4, 2, False), (6, 40, False),
+                                                   (5, 25, True), (10, 200, False)])
+def test_fehe_vs_oracle(oracle, n_side, n_he, triclinic):
+    """All three pair channels and both density channels, boxes narrower than two cutoffs (several
+    images per pair), a sheared cell, unwrapped input."""
+    box = None
+    if triclinic:
+        a = 2.8553 * n_side
+        box = np.array([[a, 0.0, 0.0], [0.2 * a, a, 0.0], [0.1 * a, -0.15 * a, a]])
+    pos, Z, H = _fehe_cell(n_side, n_he, 100 + n_side, box=box)
+    e_o, f_o = oracle.fehe_force(pos, Z, H)
+    pot = rgpot_b200.FeHePot()
+    e, f, _ = pot(pos, Z, H)
+    assert_energy(e, e_o)
+    assert_forces(f, f_o)
+    moved = pos + np.random.default_rng(1).integers(-2, 3, size=pos.shape) @ H
+    e2, f2, _ = pot(moved, Z, H)
+    e2_o, f2_o = oracle.fehe_force(moved, Z, H)
+    assert_energy(e2, e2_o)
+    assert_forces(f2, f2_o)
+
+
+def test_fehe_errors_and_batch(oracle):
+    pot = rgpot_b200.FeHePot()
+    pos, Z, H = _fehe_cell(3, 4, 7)
+    bad = Z.copy()
+    bad[5] = 29
+    with pytest.raises(rgpot_b200.PotentialError) as ei:
+        pot(pos, bad, H)
+    assert ei.value.status == 2
+    assert "rgpot_fehe: unsupported atomic number 29 on atom 6; this potential covers iron (26) and helium (2) only" in str(ei.value)
+    systems = [_fehe_cell(3, k + 1, 20 + k) for k in range(4)]
+    out = pot.forceBatch(systems)
+    for (e, f, _), (p, z, h) in zip(out, systems):
+        e_o, f_o = oracle.fehe_force(p, z, h)
+        assert_energy(e, e_o)
+        assert_forces(f, f_o)

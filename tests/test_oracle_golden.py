@@ -227,3 +227,56 @@ def test_eam_al_physics_checks(oracle):
     for rho in (0.05, 0.4, 1.0):
         assert oracle.eam_al_scalar(4, rho) == pytest.approx(g * rho + sum(ck * rho ** (k + 1) for k, ck in enumerate(c)), rel=1e-13)
         assert oracle.eam_al_scalar(5, rho) == pytest.approx(g + sum((k + 1) * ck * rho ** k for k, ck in enumerate(c)), rel=1e-13)
+
+
+# ------------------------------------------------------------------------------------- FeHe
+FE_BCC = np.array([[7.13, 7.13, 7.13], [8.565, 8.565, 8.565], [7.13, 7.13, 10.0], [8.565, 8.565, 11.435],
+                   [7.13, 10.0, 7.13], [8.565, 11.435, 8.565], [7.13, 10.0, 10.0], [8.565, 11.435, 11.435],
+                   [10.0, 7.13, 7.13], [11.435, 8.565, 8.565], [10.0, 7.13, 10.0], [11.435, 8.565, 11.435],
+                   [10.0, 10.0, 7.13], [11.435, 11.435, 8.565], [10.0, 10.0, 10.0], [11.435, 11.435, 11.435]])
+
+
+def fehe_test_cell(n_side=4, rattle=0.03, seed=3):
+    """test_fehe.f90: bcc iron, lattice 2.8553, two substitutional He on a <111>/2 bond, rattled."""
+    a = 2.8553
+    base = np.array([[0.0, 0.0, 0.0], [0.5, 0.5, 0.5]])
+    cells = np.stack(np.meshgrid(*[np.arange(n_side)] * 3, indexing="ij"), -1).reshape(-1, 3)
+    pos = ((cells[:, None, :] + base[None, :, :]).reshape(-1, 3)) * a
+    Z = np.full(len(pos), 26, np.int32)
+    Z[:2] = 2
+    pos = pos + np.random.default_rng(seed).normal(0, rattle, pos.shape)
+    return pos, Z, np.eye(3) * n_side * a
+
+
+def test_fehe_matches_the_eon_reference(oracle):
+    # CppCore/tests/FortranPotsTest.cc:146-155
+    e, f = oracle.fehe_force(FE_BCC, np.full(16, 26, np.int32), CUBE20)
+    assert e == pytest.approx(-43.959774, rel=1e-4)
+    assert np.sqrt((f ** 2).sum(1)).max() == pytest.approx(1.245094, rel=1e-3)
+    assert np.abs(f.sum(0)).max() < 1e-6
+
+
+def test_fehe_physics_checks(oracle):
+    # CppCore/rgpot/fortran/test_fehe.f90 re-run against the restatement
+    pos, Z, cell = fehe_test_cell()
+    e0, f0 = oracle.fehe_force(pos, Z, cell)
+    e1, f1 = oracle.fehe_force(pos + 0.37, Z, cell)
+    assert e1 == pytest.approx(e0, abs=1e-8) and np.abs(f0.sum(0)).max() < 1e-9
+    h = 1e-5
+    for (i, c) in [(0, 0), (0, 1), (1, 2), (2, 0), (8, 0), (32, 1), (42, 2), (16, 0), (99, 2)]:
+        p, m = pos.copy(), pos.copy()
+        p[i, c] += h
+        m[i, c] -= h
+        fd = -(oracle.fehe_force(p, Z, cell)[0] - oracle.fehe_force(m, Z, cell)[0]) / (2 * h)
+        assert fd == pytest.approx(f0[i, c], abs=5e-6)
+    assert np.abs(f0[:2]).max() > 1e-3  # the helium atoms feel force through all channels
+    bad = Z.copy()
+    bad[5] = 29
+    with pytest.raises(oracle.FeHeError) as ei:
+        oracle.fehe_force(pos, bad, cell)
+    assert ei.value.status == 2 and "unsupported atomic number 29 on atom 6" in ei.value.message
+    # every term is continuous across its branch points and vanishes beyond its cutoff
+    for which, rc in [(0, 5.3), (2, 3.9028), (6, 4.2), (8, 4.10), (4, 5.4)]:
+        assert oracle.fehe_scalar(which, np.nextafter(rc, np.inf)) == 0.0
+    for r in (1.0, 2.05):
+        assert oracle.fehe_scalar(0, np.nextafter(r, 0)) == pytest.approx(oracle.fehe_scalar(0, r), rel=2e-3)
