@@ -275,6 +275,24 @@ __global__ void k_gather_sorted(const double* __restrict__ pos, const int* __res
   scell[s] = cell_of[i];
 }
 
+// ---- species bookkeeping for table-driven pair potentials (ZBL) on device-resident input ---------
+// which atomic numbers occur (bit z of an 8-word bitmap; bit 0 of word 8 flags a number outside 0..255)
+__global__ void k_species_present(const int* __restrict__ Z, int n, unsigned* __restrict__ bitmap) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int z = Z[i];
+    if (z < 0 || z > 255)
+      atomicOr(&bitmap[8], 1u);
+    else if (!((bitmap[z >> 5] >> (z & 31)) & 1u))  // (a stale read only costs a redundant atomic)
+      atomicOr(&bitmap[z >> 5], 1u << (z & 31));
+  }
+}
+
+// atomic number -> type index through a 256-entry table
+__global__ void k_map_types(const int* __restrict__ Z, int n, const int* __restrict__ lut, int* __restrict__ types) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) types[i] = lut[Z[i] & 255];
+}
+
 // ---- deterministic energy reduction --------------------------------------------------------
 // per-block partial sums were written by the force kernels in block order; one block folds them
 // in a fixed tree.  out[0] = sum

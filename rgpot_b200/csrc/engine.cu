@@ -255,7 +255,7 @@ struct RgpotB200Pot {
   double lj_shiftU = 0.0;
   double morse_ecut = 0.0;  // MorsePot.hpp:56-61
   std::vector<int> zbl_species;  // sorted unique atomic numbers of the cached table (ZBLPot.cc:150-166)
-  DevBuf zbl_table;
+  DevBuf zbl_table, zbl_bitmap;
   double lj_rc = 0.0;  // effective cutoff (cluster: <= 0 -> 1e6)
   int forced_path = 0;
   // tuning overrides of the brick kernels (0 = automatic), rgpot_b200_set_option
@@ -308,7 +308,7 @@ struct RgpotB200Pot {
     DevBuf* d[] = {&pos, &Z, &F, &cell_of, &rank, &ashift, &counts, &starts, &blocksums, &order, &order2,
                    &spos, &scell, &dfd, &dfs, &eemb, &partials, &partials2, &energy, &status, &mm, &emit_pairs,
                    &emit_shifts, &emit_count, &emit_vecs, &emit_dists, &b_pos, &b_Z, &b_F, &b_off, &b_boxes, &b_E, &b_flags,
-                   &b_bad, &b_map, &zbl_table};
+                   &b_bad, &b_map, &zbl_table, &zbl_bitmap};
     for (auto* b : d) b->release();
     HostBuf* h[] = {&h_pos, &h_Z, &h_F, &h_off, &h_boxes, &h_E, &h_flags, &h_bad, &h_small};
     for (auto* b : h) b->release();
@@ -1053,6 +1053,8 @@ double zbl_d2e(const ZblCoeffs& p, double r) {
 
 // Map atomic numbers to type indices (sorted unique, ZBLPot.cc:186-196) and make sure the device
 // table matches the species set.  `types` receives one index per atom.
+int zbl_table_for(RgpotB200Pot* pot, const std::vector<int>& uniq, cudaStream_t st);
+
 int zbl_prepare(RgpotB200Pot* pot, size_t n, const int* Z, int* types, cudaStream_t st) {
   std::vector<int> uniq(Z, Z + n);
   std::sort(uniq.begin(), uniq.end());
@@ -1061,6 +1063,41 @@ int zbl_prepare(RgpotB200Pot* pot, size_t n, const int* Z, int* types, cudaStrea
     return fail(pot, kStatusSpecies, "rgpot_b200: ZBL handles at most 16 distinct atomic numbers per call");
   for (size_t k = 0; k < n; ++k)
     types[k] = (int)(std::lower_bound(uniq.begin(), uniq.end(), Z[k]) - uniq.begin());
+  return zbl_table_for(pot, uniq, st);
+}
+
+// Device-resident atomic numbers: the species set is read off a 288-bit presence bitmap (one small
+// D2H instead of a round trip of the whole array) and the atoms are mapped to type indices on the
+// device.  Leaves the type indices in pot->Z.
+int zbl_prepare_device(RgpotB200Pot* pot, size_t n, const int* d_Z, cudaStream_t st) {
+  CU_TRY(pot, pot->zbl_bitmap.reserve(sizeof(unsigned) * 9 + sizeof(int) * 256));
+  unsigned* d_bits = pot->zbl_bitmap.as<unsigned>();
+  int* d_lut = reinterpret_cast<int*>(d_bits + 9);
+  CU_TRY(pot, cudaMemsetAsync(d_bits, 0, sizeof(unsigned) * 9, st));
+  k_species_present<<<std::min(div_up((long)n, 256), 8 * pot->sm_count), 256, 0, st>>>(d_Z, (int)n, d_bits);
+  LAUNCH_CHECK(pot, "k_species_present");
+  unsigned bits[9];
+  CU_TRY(pot, cudaMemcpyAsync(bits, d_bits, sizeof bits, cudaMemcpyDeviceToHost, st));
+  CU_TRY(pot, cudaStreamSynchronize(st));
+  std::vector<int> uniq;
+  for (int z = 0; z < 256; ++z)
+    if ((bits[z >> 5] >> (z & 31)) & 1u) uniq.push_back(z);
+  if (bits[8] || uniq.size() > 16)
+    return fail(pot, kStatusSpecies, bits[8] ? "rgpot_b200: ZBL atomic numbers must lie in 0..255"
+                                            : "rgpot_b200: ZBL handles at most 16 distinct atomic numbers per call");
+  int s = zbl_table_for(pot, uniq, st);
+  if (s) return s;
+  int lut[256] = {0};
+  for (size_t k = 0; k < uniq.size(); ++k) lut[uniq[k]] = (int)k;
+  CU_TRY(pot, cudaMemcpyAsync(d_lut, lut, sizeof lut, cudaMemcpyHostToDevice, st));
+  CU_TRY(pot, pot->Z.reserve(sizeof(int) * n));
+  k_map_types<<<div_up((long)n, 256), 256, 0, st>>>(d_Z, (int)n, d_lut, pot->Z.as<int>());
+  LAUNCH_CHECK(pot, "k_map_types");
+  CU_TRY(pot, cudaStreamSynchronize(st));  // (lut lives on this stack frame)
+  return 0;
+}
+
+int zbl_table_for(RgpotB200Pot* pot, const std::vector<int>& uniq, cudaStream_t st) {
   if (uniq == pot->zbl_species && pot->zbl_table.p) return 0;
   const size_t nt = uniq.size();
   const double cut_inner = pot->cfg.zbl_cut_inner, cut_global = pot->cfg.cutoff;
@@ -1436,14 +1473,9 @@ int rgpot_b200_force_device(RgpotB200Pot* pot, long nAtoms, const double* d_posi
   if ((eam || zbl) && !d_atomicNrs)
     return fail(pot, kStatusArgs, "rgpot_b200: this potential needs atomic numbers");
   if (zbl) {
-    // the species set decides the coefficient table: one round trip of the atomic numbers
-    std::vector<int> hz((size_t)nAtoms), types((size_t)nAtoms);
-    CU_TRY(pot, cudaMemcpyAsync(hz.data(), d_atomicNrs, sizeof(int) * nAtoms, cudaMemcpyDeviceToHost, st));
-    CU_TRY(pot, cudaStreamSynchronize(st));
-    int zs = zbl_prepare(pot, (size_t)nAtoms, hz.data(), types.data(), st);
+    // the species set decides the coefficient table (ZBLPot.cc:150-196): presence bitmap + device mapping
+    int zs = zbl_prepare_device(pot, (size_t)nAtoms, d_atomicNrs, st);
     if (zs) return zs;
-    CU_TRY(pot, pot->Z.reserve(sizeof(int) * nAtoms));
-    CU_TRY(pot, cudaMemcpy(pot->Z.p, types.data(), sizeof(int) * nAtoms, cudaMemcpyHostToDevice));
     d_atomicNrs = pot->Z.as<int>();
   }
   int s = force_device_impl(pot, nAtoms, d_positions, d_atomicNrs, d_forces, d_energy, box, st,

@@ -816,3 +816,23 @@ def test_fehe_errors_and_batch(oracle):
         e_o, f_o = oracle.fehe_force(p, z, h)
         assert_energy(e, e_o)
         assert_forces(f, f_o)
+
+
+def test_zbl_device_entry_maps_species_on_the_device(oracle):
+    """rgpot_b200_force_device for ZBL: species set from a presence bitmap, type indices mapped on the
+    device; same numbers as the host-buffer call."""
+    import torch
+    rng = np.random.default_rng(8)
+    n = 3000
+    pos = rng.random((n, 3)) * (n / 0.09) ** (1 / 3)
+    Z = rng.choice([1, 8, 14, 29, 79], n).astype(np.int32)
+    pot = rgpot_b200.ZBLPot()
+    e_h, f_h, _ = pot(pos, Z, np.eye(3))
+    dev = torch.device("cuda", 0)
+    d_pos, d_Z = torch.from_numpy(pos).to(dev), torch.from_numpy(Z).to(dev)
+    d_F = torch.empty((n, 3), dtype=torch.float64, device=dev)
+    d_E = torch.empty(1, dtype=torch.float64, device=dev)
+    pot.force_device(d_pos, d_Z, np.eye(3), d_F, d_E)
+    assert float(d_E.item()) == e_h and np.array_equal(d_F.cpu().numpy(), f_h)
+    e_o, f_o, _ = oracle.zbl_force(pos, Z)
+    assert_energy(e_h, e_o)

@@ -1,0 +1,101 @@
+#!/usr/bin/env python
+"""Device-resident throughput of the widened rows: Morse, ZBL, EAM-Al, FeHe, and the
+vesin-shaped neighbor list.  One JSON line per workload (atom-evals/s, CUDA events on the launching
+stream, 256 MB L2 flush between timed calls); `python tools/bench_widened.py > profiles/rNN_widened.json`.
+"""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import rgpot_b200  # noqa: E402
+from rgpot_b200 import workloads  # noqa: E402
+
+
+def fcc(cells, a, seed, rattle):
+    pos = workloads._fcc(cells, a) + np.random.default_rng(seed).normal(0, rattle, (4 * cells ** 3, 3))
+    return pos, np.eye(3) * cells * a
+
+
+def bcc_fehe(n_side, frac_he, seed):
+    a = 2.8553
+    base = np.array([[0.0, 0.0, 0.0], [0.5, 0.5, 0.5]])
+    cells = np.stack(np.meshgrid(*[np.arange(n_side)] * 3, indexing="ij"), -1).reshape(-1, 3)
+    pos = (cells[:, None, :] + base[None, :, :]).reshape(-1, 3) * a
+    rng = np.random.default_rng(seed)
+    pos = pos + rng.normal(0, 0.04, pos.shape)
+    Z = np.full(len(pos), 26, np.int32)
+    Z[rng.choice(len(pos), size=int(frac_he * len(pos)), replace=False)] = 2
+    return pos, Z, np.eye(3) * n_side * a
+
+
+def timed(pot, pos, Z, box, steps=5):
+    dev = torch.device("cuda", 0)
+    n = len(pos)
+    d_pos = torch.from_numpy(np.ascontiguousarray(pos)).to(dev)
+    d_Z = torch.from_numpy(np.ascontiguousarray(Z, dtype=np.int32)).to(dev)
+    d_F = torch.empty((n, 3), dtype=torch.float64, device=dev)
+    d_E = torch.empty(1, dtype=torch.float64, device=dev)
+    ts = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(ts)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    for _ in range(3):
+        pot.force_device(d_pos, d_Z, box, d_F, d_E, ts.cuda_stream)
+    ms = []
+    for _ in range(steps):
+        flush.zero_()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        pot.force_device(d_pos, d_Z, box, d_F, d_E, ts.cuda_stream, sync=False)
+        t1.record()
+        torch.cuda.synchronize()
+        ms.append(t0.elapsed_time(t1))
+    assert pot.sync_status() == 0
+    return float(np.median(ms)), float(d_E.item())
+
+
+def main():
+    out = []
+    # Morse: a loose Pt-like fcc crystal, 9.5 A cutoff (MorsePot defaults)
+    pos, box = fcc(40, 4.1, 1, 0.08)
+    ms, e = timed(rgpot_b200.MorsePot(), pos, np.full(len(pos), 78), box)
+    out.append({"workload": "morse_fcc_256k", "kernel": "k_brick<PAIR>", "n_atoms": len(pos), "ms_per_step": ms,
+                "value": len(pos) / ms * 1e3, "energy": e})
+    # ZBL: a random gas, 2.5 A cutoff, five species, free boundaries
+    rng = np.random.default_rng(2)
+    n = 500_000
+    pos = rng.random((n, 3)) * (n / 0.09) ** (1 / 3)
+    Z = rng.choice([1, 8, 14, 29, 79], n).astype(np.int32)
+    ms, e = timed(rgpot_b200.ZBLPot(), pos, Z, np.eye(3))
+    out.append({"workload": "zbl_gas_500k", "kernel": "k_brick<PAIR>", "n_atoms": n, "ms_per_step": ms,
+                "value": n / ms * 1e3, "energy": e})
+    # EAM-Al: fcc aluminium 40^3 cells, 7.1 A cutoff
+    pos, box = fcc(40, 4.05, 3, 0.08)
+    ms, e = timed(rgpot_b200.EAMAlPot(), pos, np.full(len(pos), 13), box)
+    out.append({"workload": "eam_al_fcc_256k", "kernel": "k_brick<AL_DENSITY> + k_brick<AL_FORCE>",
+                "n_atoms": len(pos), "ms_per_step": ms, "value": len(pos) / ms * 1e3, "energy": e})
+    # FeHe: bcc iron 40^3 cells with 1 % substitutional helium, gather kernels
+    pos, Z, box = bcc_fehe(40, 0.01, 4)
+    ms, e = timed(rgpot_b200.FeHePot(), pos, Z, box)
+    out.append({"workload": "fehe_bcc_128k", "kernel": "k_fehe_density + k_fehe_force (gather)", "n_atoms": len(pos),
+                "ms_per_step": ms, "value": len(pos) / ms * 1e3, "energy": e})
+    # neighbor list: the Cu slab, 6.1 A, full list, unsorted (host-buffer call: two passes + D2H of the list)
+    pos, Zs, box = workloads.cu_slab_triclinic(cells=20)
+    rgpot_b200.neighbor_list(pos, box, 6.1, full=True, sorted=False)
+    t0 = time.perf_counter()
+    nl = rgpot_b200.neighbor_list(pos, box, 6.1, full=True, sorted=False)
+    dt = time.perf_counter() - t0
+    out.append({"workload": "neighbor_list_cu_slab_32k_6.1A_full", "kernel": "k_emit_pairs<GEO_IMAGES> (two passes)",
+                "n_atoms": len(pos), "entries": int(len(nl["distances"])), "seconds_host_call": dt,
+                "value": len(pos) / dt, "note": "host call incl. H2D, two emit passes, D2H of 44 B per entry"})
+    for rec in out:
+        rec["unit"] = "atom-evals/s"
+        print(json.dumps(rec), flush=True)
+
+
+if __name__ == "__main__":
+    main()
