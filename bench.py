@@ -98,12 +98,35 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------- distributed glue
+def bind_to_gpu_numa_node(local):
+    """Pin this rank to the CPUs of its GPU's NUMA node before any pinned host memory is allocated:
+    the end-to-end path is DMA traffic between pinned buffers and the GPU, and with eight ranks on one
+    box a buffer on the far socket crosses the inter-socket link on every step.  Best effort."""
+    try:
+        import torch
+        p = torch.cuda.get_device_properties(local)
+        bdf = "%04x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+        cpus = open(f"/sys/bus/pci/devices/{bdf}/local_cpulist").read().strip()
+        ids = set()
+        for part in cpus.split(","):
+            lo, _, hi = part.partition("-")
+            ids.update(range(int(lo), int(hi or lo) + 1))
+        ids &= os.sched_getaffinity(0)
+        if ids:
+            os.sched_setaffinity(0, ids)
+            return f"{bdf}: cpus {cpus}"
+    except Exception:  # noqa: BLE001
+        pass
+    return None
+
+
 def dist_setup(n_gpus):
     import torch
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
+        bind_to_gpu_numa_node(local)
         import torch.distributed as dist
         torch.cuda.set_device(local)
         dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local))
