@@ -58,7 +58,37 @@ def timed(pot, pos, Z, box, steps=5):
     return float(np.median(ms)), float(d_E.item())
 
 
+def cpu_baselines():
+    """The CPU oracle (C restatements of the reference kernels; Morse / ZBL with the reference's O(N^2)
+    pair scan, the EAMs over the restated vesin cell list) on a smaller sample of each recipe, one
+    process, before this process touches CUDA.  atom-evals/s."""
+    from oracle import pyoracle as po
+    res = {}
+
+    def rate(f, n):
+        f()
+        t0 = time.perf_counter()
+        f()
+        return n / (time.perf_counter() - t0)
+
+    pos, box = fcc(12, 4.1, 1, 0.08)
+    res["morse_fcc_256k"] = {"value": rate(lambda: po.morse_force(pos, box), len(pos)), "sample": f"{len(pos)}-atom crystal"}
+    rng = np.random.default_rng(2)
+    n = 8000
+    p2 = rng.random((n, 3)) * (n / 0.09) ** (1 / 3)
+    z2 = rng.choice([1, 8, 14, 29, 79], n).astype(np.int32)
+    res["zbl_gas_500k"] = {"value": rate(lambda: po.zbl_force(p2, z2), n), "sample": f"{n}-atom gas (O(N^2) scan)"}
+    pos3, box3 = fcc(12, 4.05, 3, 0.08)
+    res["eam_al_fcc_256k"] = {"value": rate(lambda: po.eam_al_force(pos3, box3), len(pos3)), "sample": f"{len(pos3)}-atom crystal"}
+    pos4, z4, box4 = bcc_fehe(14, 0.01, 4)
+    res["fehe_bcc_128k"] = {"value": rate(lambda: po.fehe_force(pos4, z4, box4), len(pos4)), "sample": f"{len(pos4)}-atom crystal"}
+    for v in res.values():
+        v.update({"unit": "atom-evals/s", "cores": 1, "kind": "port"})  # the C restatements of oracle/
+    return res
+
+
 def main():
+    cpu = cpu_baselines()
     out = []
     # Morse: a loose Pt-like fcc crystal, 9.5 A cutoff (MorsePot defaults)
     pos, box = fcc(40, 4.1, 1, 0.08)
@@ -94,6 +124,8 @@ def main():
                 "value": len(pos) / dt, "note": "host call incl. H2D, two emit passes, D2H of 44 B per entry"})
     for rec in out:
         rec["unit"] = "atom-evals/s"
+        if rec["workload"] in cpu:
+            rec["cpu_baseline"] = cpu[rec["workload"]]
         print(json.dumps(rec), flush=True)
 
 
