@@ -48,7 +48,7 @@ constexpr int kShiftCodes = 125;    // image counts q in [-2, 2]^3
 
 struct TileOut {
   double* F;            // forces, original order (LJ, EAM force)
-  double* partials;     // per-brick energy partials (LJ, EAM force)
+  double* eatom;        // per-atom energies, sorted order (LJ, EAM force): folded in one fixed order
   double* dfd_sorted;   // EAM: F'(rho), sorted order (written by density, read by force)
   double* eemb_sorted;  // EAM: F(rho)
   Status* st;
@@ -80,46 +80,134 @@ RB_D double rcp_fast(double a) {
   return fma(y, fma(e, e, e), y);
 }
 
-// ---- per-atom gather walk (the in-kernel slow path of an oversized brick) -----------------------
-template <int POT>
-__device__ __noinline__ void brick_slow_atom(const GatherArgs& a, const TileOut& o, int i, double& e, bool& coincident) {
+// ---- pair terms shared by the brick kernel and its slow path ------------------------------------
+// One candidate at exact separation (dx, dy, dz), d2 = |d|^2 in the reference's arithmetic; `other`
+// is false for the atom itself.  acc: force components (density pass: acc[0] = rho).
+template <int POT, class DfdJ>
+RB_D void brick_pair(const GatherArgs& a, double rc2, double rc2_phys, bool other, int zi, int zj, double dfd_i,
+                     DfdJ&& dfd_j, double dx, double dy, double dz, double d2, double& e, double* acc,
+                     bool& coincident) {
+  if (POT == TILE_LJ) {
+    if (d2 <= rc2 && other) {  // vesin_visit.hpp:104
+      const double invR2 = rcp_fast(d2);
+      const double sr2 = a.lj.psi2 * invR2;
+      const double a6 = sr2 * sr2 * sr2;
+      const double bb = 4.0 * a.lj.u0 * a6;
+      e += 0.5 * (bb * (a6 - 1.0) - a.lj.shiftU);
+      const double fs = 6.0 * bb * invR2 * (2.0 * a6 - 1.0);
+      acc[0] = fma(-fs, dx, acc[0]);
+      acc[1] = fma(-fs, dy, acc[1]);
+      acc[2] = fma(-fs, dz, acc[2]);
+    }
+  } else if (POT == TILE_PAIR) {
+    if (d2 <= rc2 && other) {
+      double u, fs;
+      pair_eval(a.lj, d2, zi, zj, u, fs);
+      e += 0.5 * u;
+      acc[0] = fma(-fs, dx, acc[0]);
+      acc[1] = fma(-fs, dy, acc[1]);
+      acc[2] = fma(-fs, dz, acc[2]);
+    }
+  } else if (d2 < rc2 && other) {  // vesin :1202; the atom itself is no neighbour
+    if (tile_is_density(POT)) {
+      if (d2 == 0.0) coincident = true;
+      if (d2 < rc2_phys) acc[0] += eam_density_entry<tile_model(POT)>(zj, d2);
+    } else if (d2 < rc2_phys) {
+      eam_force_entry<tile_model(POT)>(zi, zj, dfd_i, dfd_j(), dx, dy, dz, d2, e, acc[0], acc[1], acc[2]);
+    }
+  }
+}
+
+// ---- per-atom walk straight from global memory (the in-kernel slow path) -------------------------
+// For the atoms of a single cell whose stencil does not fit the staged capacity.  It visits the
+// candidates in the order the brick kernel does -- stencil row `row` belongs to partial sum
+// row % TPA, rows ascending, cells along x, atoms in sorted order -- and folds the TPA partial sums
+// in the kernel's shuffle tree, so an atom gets the same bits whichever path evaluated it.
+template <int POT, int TPA>
+__device__ __noinline__ void brick_slow_atom(const GatherArgs& a, const BrickPlan& bp, const TileOut& o,
+                                             const double (*svtab)[3], int i, bool& coincident) {
+  constexpr bool kPairGeo = POT == TILE_LJ || POT == TILE_PAIR;
+  constexpr bool kForce = tile_is_force(POT);
+  constexpr bool kDensity = tile_is_density(POT);
+  constexpr int NV = kDensity ? 1 : 3;
+  const Grid& g = a.grid;
+  const int cell = a.scell[i];
+  const int c[3] = {cell % g.nc[0], (cell / g.nc[0]) % g.nc[1], cell / (g.nc[0] * g.nc[1])};
   const double4 pi = a.spos[i];
   const unsigned long long mi = (unsigned long long)__double_as_longlong(pi.w);
   const int zi = meta_species(mi);
-  double fx = 0.0, fy = 0.0, fz = 0.0;
-  if (POT == TILE_LJ || POT == TILE_PAIR) {
-    auto body = [&](int, unsigned long long mj, double dx, double dy, double dz, double d2, int, int, int) {
-      lj_pair(a.lj, zi, meta_species(mj), dx, dy, dz, d2, e, fx, fy, fz);
-    };
-    walk_neighbors<GEO_LJ_SHIFT, false>(a, i, pi, body);
-  } else if (tile_is_density(POT)) {
-    const double rc2_phys = eam_par<tile_model(POT)>().rc2_phys;
-    double rho = 0.0;
-    auto body = [&](int, unsigned long long mj, double, double, double, double d2, int, int, int) {
-      if (d2 == 0.0) coincident = true;
-      if (!(d2 < rc2_phys)) return;
-      rho += eam_density_entry<tile_model(POT)>(meta_species(mj), d2);
-    };
-    walk_neighbors<GEO_IMAGES, false>(a, i, pi, body);
+  const double rc2 = kPairGeo ? a.lj.rc2 : a.rc2;
+  const double rc2_phys = kPairGeo ? 0.0 : eam_par<tile_model(POT)>().rc2_phys;
+  double dfd_i = 0.0;
+  if (kForce) dfd_i = o.dfd_sorted[i];
+  const int nrx = 2 * bp.ns[0] + 1, nry = 2 * bp.ns[1] + 1, nrows = nry * (2 * bp.ns[2] + 1);
+  double part[TPA][4];
+#pragma unroll
+  for (int sub = 0; sub < TPA; ++sub) {
+    double acc[3] = {0.0, 0.0, 0.0}, e = 0.0;
+    for (int row = sub; row < nrows; row += TPA) {
+      const int hy = row % nry, hz = row / nry;
+      for (int hx = 0; hx < nrx; ++hx) {
+        const int hc[3] = {hx, hy, hz};
+        int q[3], r[3];
+        bool valid = true;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          q[k] = 0;
+          r[k] = c[k] - bp.ns[k] + hc[k];
+          if (a.box.periodic[k]) {
+            while (r[k] < 0) {
+              r[k] += g.nc[k];
+              --q[k];
+            }
+            while (r[k] >= g.nc[k]) {
+              r[k] -= g.nc[k];
+              ++q[k];
+            }
+          } else if (r[k] < 0 || r[k] >= g.nc[k]) {
+            valid = false;
+          }
+        }
+        if (!valid) continue;
+        const int nb = (r[2] * g.nc[1] + r[1]) * g.nc[0] + r[0];
+        const int jb = a.starts[nb], je = a.starts[nb + 1];
+        const int code = (q[2] + 2) * 25 + (q[1] + 2) * 5 + (q[0] + 2);
+        const double svx = svtab[code][0], svy = svtab[code][1], svz = svtab[code][2];
+        for (int j = jb; j < je; ++j) {
+          const double4 pj = a.spos[j];
+          // (p_j - p_i) + 0 is p_j - p_i: the kernel's unshifted boxes skip the addition
+          const double dx = xadd(xsub(pj.x, pi.x), svx), dy = xadd(xsub(pj.y, pi.y), svy),
+                       dz = xadd(xsub(pj.z, pi.z), svz);
+          const double d2 = xnorm2(dx, dy, dz);
+          const int zj = meta_species((unsigned long long)__double_as_longlong(pj.w));
+          brick_pair<POT>(a, rc2, rc2_phys, j != i || code != kShiftCodes / 2, zi, zj, dfd_i,
+                          [&]() { return o.dfd_sorted[j]; }, dx, dy, dz, d2, e, acc, coincident);
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) part[sub][k] = acc[k];
+    part[sub][3] = e;
+  }
+#pragma unroll
+  for (int off = 1; off < TPA; off <<= 1)
+#pragma unroll
+    for (int sub = 0; sub < TPA; sub += 2 * off)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) part[sub][k] += part[sub + off][k];
+  if (kDensity) {
     double emb, demb;
-    eam_embed<tile_model(POT)>(zi, rho, emb, demb);
+    eam_embed<tile_model(POT)>(zi, part[0][0], emb, demb);
     o.dfd_sorted[i] = demb;
     o.eemb_sorted[i] = emb;
     return;
-  } else {
-    const double rc2_phys = eam_par<tile_model(POT)>().rc2_phys;
-    const double dfd_i = o.dfd_sorted[i];
-    auto body = [&](int j, unsigned long long mj, double dx, double dy, double dz, double d2, int, int, int) {
-      if (!(d2 < rc2_phys)) return;
-      eam_force_entry<tile_model(POT)>(zi, meta_species(mj), dfd_i, o.dfd_sorted[j], dx, dy, dz, d2, e, fx, fy, fz);
-    };
-    walk_neighbors<GEO_IMAGES, false>(a, i, pi, body);
-    e += o.eemb_sorted[i];
   }
   const int orig = meta_orig(mi);
-  o.F[3 * (size_t)orig] = fx;
-  o.F[3 * (size_t)orig + 1] = fy;
-  o.F[3 * (size_t)orig + 2] = fz;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) o.F[3 * (size_t)orig + k] = part[0][k];
+  double e = part[0][3];
+  if (kForce) e += o.eemb_sorted[i];
+  o.eatom[i] = e;
 }
 
 // ---- the brick kernel ------------------------------------------------------------------------
@@ -176,7 +264,6 @@ k_brick(const __grid_constant__ GatherArgs a, const __grid_constant__ BrickPlan 
       box_stack[0][3 + k] = min(bp.bd[k], g.nc[k] - b[k] * bp.bd[k]);
     }
   }
-  double e_thr = 0.0;
   bool coincident = false;
 #ifdef RB_BRICK_TIMING
   long long t_mark = clock64();
@@ -293,7 +380,7 @@ k_brick(const __grid_constant__ GatherArgs a, const __grid_constant__ BrickPlan 
       const int cell = (r[2] * g.nc[1] + r[1]) * g.nc[0] + r[0];
       const int jb = a.starts[cell], je = a.starts[cell + 1];
       if (tid == 0 && je > jb) atomicAdd(&o.st->slow_atoms, je - jb);
-      for (int j = jb + tid; j < je; j += nthreads) brick_slow_atom<POT>(a, o, j, e_thr, coincident);
+      for (int j = jb + tid; j < je; j += nthreads) brick_slow_atom<POT, TPA>(a, bp, o, svtab, j, coincident);
       if (--sp == 0) break;
       __syncthreads();
       continue;
@@ -384,6 +471,7 @@ k_brick(const __grid_constant__ GatherArgs a, const __grid_constant__ BrickPlan 
         const int ai = a0 + tid / TPA;
         const int sub = tid % TPA;
         double acc[3] = {0.0, 0.0, 0.0};
+        double e_thr = 0.0;  // this thread's share of the atom's energy
         int si = 0, gi = 0;
         const bool active = ai < natoms;
         if (active) {
@@ -472,36 +560,8 @@ k_brick(const __grid_constant__ GatherArgs a, const __grid_constant__ BrickPlan 
                 dz = xadd(dz, svtab[code][2]);
               }
               const double d2 = xnorm2(dx, dy, dz);
-              if (POT == TILE_LJ) {
-                if (d2 <= rc2 && sj != si) {  // vesin_visit.hpp:104
-                  const double invR2 = rcp_fast(d2);
-                  const double sr2 = a.lj.psi2 * invR2;
-                  const double a6 = sr2 * sr2 * sr2;
-                  const double bb = 4.0 * a.lj.u0 * a6;
-                  e_thr += 0.5 * (bb * (a6 - 1.0) - a.lj.shiftU);
-                  const double fs = 6.0 * bb * invR2 * (2.0 * a6 - 1.0);
-                  acc[0] = fma(-fs, dx, acc[0]);
-                  acc[1] = fma(-fs, dy, acc[1]);
-                  acc[2] = fma(-fs, dz, acc[2]);
-                }
-              } else if (POT == TILE_PAIR) {
-                if (d2 <= rc2 && sj != si) {
-                  double u, fs;
-                  pair_eval(a.lj, d2, zi, info >> 8, u, fs);
-                  e_thr += 0.5 * u;
-                  acc[0] = fma(-fs, dx, acc[0]);
-                  acc[1] = fma(-fs, dy, acc[1]);
-                  acc[2] = fma(-fs, dz, acc[2]);
-                }
-              } else if (d2 < rc2 && sj != si) {  // vesin :1202; the atom itself is no neighbour
-                const int zj = info >> 8;
-                if (kDensity) {
-                  if (d2 == 0.0) coincident = true;
-                  if (d2 < rc2_phys) acc[0] += eam_density_entry<kModel>(zj, d2);
-                } else if (d2 < rc2_phys) {
-                  eam_force_entry<kModel>(zi, zj, dfd_i, c64w[sj], dx, dy, dz, d2, e_thr, acc[0], acc[1], acc[2]);
-                }
-              }
+              brick_pair<POT>(a, rc2, rc2_phys, sj != si, zi, info >> 8, dfd_i, [&]() { return c64w[sj]; }, dx, dy,
+                              dz, d2, e_thr, acc, coincident);
             }
             RB_TICK(3);
           } while (more);
@@ -512,6 +572,7 @@ k_brick(const __grid_constant__ GatherArgs a, const __grid_constant__ BrickPlan 
         for (int off = 1; off < TPA; off <<= 1) {
 #pragma unroll
           for (int k = 0; k < NV; ++k) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], off);
+          if (!kDensity) e_thr += __shfl_xor_sync(0xffffffffu, e_thr, off);
         }
         if (active && sub == 0) {
           if (kDensity) {
@@ -525,6 +586,9 @@ k_brick(const __grid_constant__ GatherArgs a, const __grid_constant__ BrickPlan 
             o.F[3 * (size_t)orig + 1] = acc[1];
             o.F[3 * (size_t)orig + 2] = acc[2];
             if (kForce) e_thr += o.eemb_sorted[gi];
+            // per-atom energy in sorted order: the fold over them has one order, whatever brick or
+            // box evaluated the atom
+            o.eatom[gi] = e_thr;
           }
         }
       }
@@ -545,14 +609,7 @@ k_brick(const __grid_constant__ GatherArgs a, const __grid_constant__ BrickPlan 
   if (lane == 0)
     for (int k = 0; k < 4; ++k) atomicAdd(&o.st->prof[k], t_acc[k]);
 #endif
-  if (kDensity) {
-    if (coincident) atomicOr(&o.st->flags, kFlagCoincident);
-  } else {
-    // one energy partial per warp (fixed shuffle tree); the warps retire independently
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) e_thr += __shfl_down_sync(0xffffffffu, e_thr, off);
-    if (lane == 0) o.partials[blockIdx.x * (kBrickMaxThreads / 32) + wid] = e_thr;
-  }
+  if (kDensity && coincident) atomicOr(&o.st->flags, kFlagCoincident);
 }
 
 }  // namespace rb

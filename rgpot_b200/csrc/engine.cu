@@ -274,9 +274,49 @@ struct RgpotB200Pot {
   struct BrickMemo {
     long n = -1;
     int nc[3] = {0, 0, 0};
-    int bd[3] = {0, 0, 0};
+    int bd[3] = {0, 0, 0};  // memo_pending: the brick of the plan in flight; memo: of the last record
     int max_halo = 0;
+    // one record per brick shape met with this (n, nc): a shape that no longer fits shared memory
+    // with its own record makes the planner shrink the brick, and the smaller shape keeps its own
+    struct Shape {
+      int bd[3];
+      int max_halo;
+    } shapes[8];
+    int nshapes = 0;
+    bool matches(long n_, const int* nc_) const { return n == n_ && nc[0] == nc_[0] && nc[1] == nc_[1] && nc[2] == nc_[2]; }
+    // largest halo recorded for this shape; failing that, for the smallest recorded shape that
+    // contains it (a bound in all but pathological alignments -- and a short capacity only cuts)
+    int lookup(const int* bd_) const {
+      int best = 0;
+      long best_vol = 0;
+      for (int s = 0; s < nshapes; ++s) {
+        const int* b = shapes[s].bd;
+        if (b[0] == bd_[0] && b[1] == bd_[1] && b[2] == bd_[2]) return shapes[s].max_halo;
+        if (b[0] >= bd_[0] && b[1] >= bd_[1] && b[2] >= bd_[2]) {
+          const long vol = (long)b[0] * b[1] * b[2];
+          if (best == 0 || vol < best_vol) {
+            best = shapes[s].max_halo;
+            best_vol = vol;
+          }
+        }
+      }
+      return best;
+    }
+    void record(const int* bd_, int halo) {
+      for (int s = 0; s < nshapes; ++s) {
+        int* b = shapes[s].bd;
+        if (b[0] == bd_[0] && b[1] == bd_[1] && b[2] == bd_[2]) {
+          shapes[s].max_halo = std::max(shapes[s].max_halo, halo);
+          return;
+        }
+      }
+      if (nshapes == 8) nshapes = 0;
+      Shape& sh = shapes[nshapes++];
+      for (int k = 0; k < 3; ++k) sh.bd[k] = bd_[k];
+      sh.max_halo = halo;
+    }
   } memo, memo_pending;
+  int last_cap_cand = 0, last_cap_list = 0;  // what the last brick plan chose (rgpot_b200_stat)
   std::string last_error;
 
   // single-system scratch
@@ -397,8 +437,9 @@ void finish_grid(Plan& pl, double rc, long n, bool images, int fine) {
     if (c > 1024.0) c = 1024.0;
     ncd[k] = c;
   }
-  // bound the cell count (memory and empty-cell overhead): about one cell per atom at most
-  const double cap = std::max(64.0, 2.0 * (double)n);
+  // bound the cell count (memory and empty-cell overhead): about one cell per atom, but never so
+  // few that a mostly empty box (a droplet, a particle in vacuum) is left with oversized cells
+  const double cap = std::max(262144.0, 2.0 * (double)n);
   double total = ncd[0] * ncd[1] * ncd[2];
   while (total > cap) {
     int kmax = 0;
@@ -423,8 +464,11 @@ void finish_grid(Plan& pl, double rc, long n, bool images, int fine) {
       pl.grid.ns_lo[k] = nc >= 3 ? 1 : 0;
       pl.grid.ns_hi[k] = nc >= 2 ? 1 : 0;
     } else {
-      // fine periodic grids are only kept by the caller when nc >= 2 * fine + 1 (distinct cells)
-      pl.grid.ns_lo[k] = pl.grid.ns_hi[k] = fine;
+      // fine periodic grids are only kept by the caller when nc >= 2 * fine + 1 (distinct cells);
+      // a direction whose cells ended up wider than the cutoff (cell-count bound) needs one layer
+      const double width = pl.box.periodic[k] ? pl.box.face[k] : pl.box.ext[k];
+      const int ns = (int)ceil(rcm * (double)nc / width);
+      pl.grid.ns_lo[k] = pl.grid.ns_hi[k] = std::max(1, std::min(ns, fine));
     }
   }
   pl.grid.ncells = pl.grid.nc[0] * pl.grid.nc[1] * pl.grid.nc[2];
@@ -535,9 +579,9 @@ bool plan_bricks(const RgpotB200Pot* pot, const Plan& pl, long n, double rc, boo
         const double fcc = pot->opt_slack ? 1.0 + 0.01 * pot->opt_slack : 1.2;
         bp.cap_cand = std::min(65504, round_up((int)(nhalo * mean * fcc) + 32, 32));
         const auto& m = pot->memo;
-        const bool known = !pot->opt_slack && m.n == n && m.max_halo > 0 && m.nc[0] == g.nc[0] && m.nc[1] == g.nc[1] &&
-                           m.nc[2] == g.nc[2] && m.bd[0] == bd[0] && m.bd[1] == bd[1] && m.bd[2] == bd[2];
-        if (known) bp.cap_cand = std::min(65504, round_up((int)(m.max_halo * 1.04) + 24, 32));
+        const int seen = (!pot->opt_slack && m.matches(n, g.nc)) ? m.lookup(bd) : 0;
+        const bool known = seen > 0;
+        if (known) bp.cap_cand = std::min(65504, round_up((int)(seen * 1.04) + 24, 32));
         const int want = (int)(nnb / tpa * 2.2) + 8, least = std::max(24, (int)(nnb / tpa) + 14);
         auto blocks_per_sm = [&](int cap_list) {
           const size_t per_block = brick_smem_bytes(bp.cap_cand, cap_list, threads, eam) + 8192 + 1024;
@@ -573,6 +617,8 @@ bool plan_bricks(const RgpotB200Pot* pot, const Plan& pl, long n, double rc, boo
             mp.bd[k] = bd[k];
           }
           mp.max_halo = 0;
+          const_cast<RgpotB200Pot*>(pot)->last_cap_cand = bp.cap_cand;
+          const_cast<RgpotB200Pot*>(pot)->last_cap_list = bp.cap_list;
         }
         bp.tpa = tpa;
         bp.threads = threads;
@@ -609,11 +655,11 @@ int launch_brick(RgpotB200Pot* pot, const GatherArgs& ga, const BrickPlan& bp, c
 // fixed-order fold of the energy partials: long arrays in two stages
 int reduce_energy(RgpotB200Pot* pot, double* d_part, int n, double* d_E, cudaStream_t st) {
   if (n > 4096) {
-    const int nb = 128, per = (n + nb - 1) / nb;
+    const int nb = n < 262144 ? 128 : 1024, per = (n + nb - 1) / nb;  // (a function of n only: one fixed order)
     CU_TRY(pot, pot->partials2.reserve(sizeof(double) * nb));
     k_reduce_slices<<<nb, 256, 0, st>>>(d_part, n, per, pot->partials2.as<double>());
     LAUNCH_CHECK(pot, "k_reduce_slices");
-    k_reduce_partials<<<1, 128, 0, st>>>(pot->partials2.as<double>(), nb, d_E);
+    k_reduce_partials<<<1, 128, 0, st>>>(pot->partials2.as<double>(), nb, d_E);  // blockDim need not cover nb
   } else {
     k_reduce_partials<<<1, 1024, 0, st>>>(d_part, n, d_E);
   }
@@ -747,8 +793,7 @@ int run_cell_path(RgpotB200Pot* pot, long n, const double* d_pos, const int* d_Z
   CU_TRY(pot, pot->spos.reserve(sizeof(double4) * n));
   CU_TRY(pot, pot->scell.reserve(sizeof(int) * n));
   const int nblk = div_up(n, 128);
-  const int npart = std::max(nblk, ncells);
-  CU_TRY(pot, pot->partials.reserve(sizeof(double) * npart));
+  CU_TRY(pot, pot->partials.reserve(sizeof(double) * n));  // per-atom energies, sorted order
   if (eam || fehe) {
     CU_TRY(pot, pot->dfd.reserve(sizeof(double) * n));
     CU_TRY(pot, pot->eemb.reserve(sizeof(double) * n));
@@ -800,8 +845,7 @@ int run_cell_path(RgpotB200Pot* pot, long n, const double* d_pos, const int* d_Z
     return 0;
   }
 
-  double* d_part = pot->partials.as<double>();
-  int npart_used = nblk;
+  double* d_part = pot->partials.as<double>();  // every atom's energy is written by exactly one kernel
   if (fehe) {
     // Fe-He: the three passes on the gather walk (rgpot_fehe.f90:573-620)
     k_fehe_density<<<nblk, 128, 0, st>>>(ga, pot->dfd.as<double>(), pot->dfs.as<double>(), pot->eemb.as<double>());
@@ -809,7 +853,7 @@ int run_cell_path(RgpotB200Pot* pot, long n, const double* d_pos, const int* d_Z
     k_fehe_force<<<nblk, 128, 0, st>>>(ga, pot->dfd.as<double>(), pot->dfs.as<double>(), pot->eemb.as<double>(), d_F,
                                        d_part);
     LAUNCH_CHECK(pot, "k_fehe_force");
-    return reduce_energy(pot, d_part, nblk, d_E, st);
+    return reduce_energy(pot, d_part, (int)n, d_E, st);
   }
   if (eam) {
     BrickPlan bp{};
@@ -817,10 +861,6 @@ int run_cell_path(RgpotB200Pot* pot, long n, const double* d_pos, const int* d_Z
     if (tile_ok) {
       // brick kernels; the gather kernels cover atoms outside the cell (per-pair image shifts) --
       // each side returns at once when the binning flag is not its own
-      npart_used = std::max(nblk, bp.nbricks * (kBrickMaxThreads / 32));
-      CU_TRY(pot, pot->partials.reserve(sizeof(double) * npart_used));
-      d_part = pot->partials.as<double>();
-      CU_TRY(pot, cudaMemsetAsync(d_part, 0, sizeof(double) * npart_used, st));
       TileOut to{d_F, d_part, pot->dfd.as<double>(), pot->eemb.as<double>(), d_st};
       int ls = al ? launch_brick<TILE_AL_DENSITY>(pot, ga, bp, to, st, "k_brick<al density>")
                   : launch_brick<TILE_EAM_DENSITY>(pot, ga, bp, to, st, "k_brick<eam density>");
@@ -840,17 +880,13 @@ int run_cell_path(RgpotB200Pot* pot, long n, const double* d_pos, const int* d_Z
       k_eam_force<EAM_CUH2><<<nblk, 128, 0, st>>>(ga, pot->dfd.as<double>(), pot->eemb.as<double>(), d_F, d_part);
     }
     LAUNCH_CHECK(pot, "k_eam_force");
-    return reduce_energy(pot, d_part, tile_ok ? npart_used : nblk, d_E, st);
+    return reduce_energy(pot, d_part, (int)n, d_E, st);
   } else if (pl.geo == GEO_IMAGES) {
     k_lj_gather<GEO_IMAGES><<<nblk, 128, 0, st>>>(ga, d_F, d_part);
     LAUNCH_CHECK(pot, "k_lj_gather<images>");
   } else if (BrickPlan bp{}; pl.geo == GEO_LJ_SHIFT && allow_tile && plan_bricks(pot, pl, n, rc, false, bp)) {
     // brick kernel; the literal-fold gather kernel covers the (rare) case of atoms outside the
     // cell -- each of the two returns at once when the binning flag is not its own
-    npart_used = std::max(nblk, bp.nbricks * (kBrickMaxThreads / 32));
-    CU_TRY(pot, pot->partials.reserve(sizeof(double) * npart_used));
-    d_part = pot->partials.as<double>();
-    CU_TRY(pot, cudaMemsetAsync(d_part, 0, sizeof(double) * npart_used, st));
     TileOut to{d_F, d_part, nullptr, nullptr, d_st};
     int ls = pl.lj.morse ? launch_brick<TILE_PAIR>(pot, ga, bp, to, st, "k_brick<pair>")
                          : launch_brick<TILE_LJ>(pot, ga, bp, to, st, "k_brick<lj>");
@@ -858,7 +894,7 @@ int run_cell_path(RgpotB200Pot* pot, long n, const double* d_pos, const int* d_Z
     ga.only_if_atom_shift = 1;
     k_lj_gather<GEO_LJ_SHIFT><<<nblk, 128, 0, st>>>(ga, d_F, d_part);
     LAUNCH_CHECK(pot, "k_lj_gather<shift>");
-    return reduce_energy(pot, d_part, npart_used, d_E, st);
+    return reduce_energy(pot, d_part, (int)n, d_E, st);
   } else if (pl.geo == GEO_LJ_SHIFT) {
     k_lj_gather<GEO_LJ_SHIFT><<<nblk, 128, 0, st>>>(ga, d_F, d_part);
     LAUNCH_CHECK(pot, "k_lj_gather<shift>");
@@ -866,7 +902,7 @@ int run_cell_path(RgpotB200Pot* pot, long n, const double* d_pos, const int* d_Z
     k_lj_gather<GEO_LJ_FOLD><<<nblk, 128, 0, st>>>(ga, d_F, d_part);
     LAUNCH_CHECK(pot, "k_lj_gather<fold>");
   }
-  return reduce_energy(pot, d_part, nblk, d_E, st);
+  return reduce_energy(pot, d_part, (int)n, d_E, st);
 }
 
 // shared memory a k_eam_small block needs
@@ -1277,6 +1313,10 @@ long rgpot_b200_stat(RgpotB200Pot* pot, const char* key) {
   if (!pot || !key) return -1;
   if (strcmp(key, "launches") == 0) return pot->launches;
   if (strcmp(key, "slow_atoms") == 0) return pot->slow_atoms;
+  if (strcmp(key, "max_halo") == 0) return pot->memo.max_halo;
+  if (strcmp(key, "brick") == 0) return pot->memo.bd[0] * 100 + pot->memo.bd[1] * 10 + pot->memo.bd[2];
+  if (strcmp(key, "cap_cand") == 0) return pot->last_cap_cand;
+  if (strcmp(key, "cap_list") == 0) return pot->last_cap_list;
   if (strncmp(key, "prof", 4) == 0 && key[4] >= '0' && key[4] <= '3') return pot->prof[key[4] - '0'];
   return -1;
 }
@@ -1432,11 +1472,14 @@ static int finish_single(RgpotB200Pot* pot, long n, const double* d_pos, const i
     pot->slow_atoms = stt.slow_atoms;
     for (int k = 0; k < 4; ++k) pot->prof[k] = (long)stt.prof[k];
     if (stt.max_halo > 0 && pot->memo_pending.n >= 0) {  // brick kernels ran: remember what they met
-      const bool same = pot->memo.n == pot->memo_pending.n && !memcmp(pot->memo.nc, pot->memo_pending.nc, sizeof pot->memo.nc) &&
-                        !memcmp(pot->memo.bd, pot->memo_pending.bd, sizeof pot->memo.bd);
-      const int prev = same ? pot->memo.max_halo : 0;
-      pot->memo = pot->memo_pending;
-      pot->memo.max_halo = std::max(prev, stt.max_halo);
+      const auto& mp = pot->memo_pending;
+      if (!pot->memo.matches(mp.n, mp.nc)) {
+        pot->memo = mp;
+        pot->memo.nshapes = 0;
+      }
+      pot->memo.record(mp.bd, stt.max_halo);
+      for (int k = 0; k < 3; ++k) pot->memo.bd[k] = mp.bd[k];
+      pot->memo.max_halo = pot->memo.lookup(mp.bd);
     }
     bad = stt.first_bad_atom;
     if ((flags & kFlagForeignZ) && bad != INT_MAX) {

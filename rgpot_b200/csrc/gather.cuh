@@ -170,8 +170,7 @@ RB_D void walk_dispatch(const GatherArgs& a, int i, const double4 pi, Body&& bod
 // GEO_LJ_SHIFT / GEO_LJ_FOLD: reference semantics.  GEO_IMAGES: opt-in all-image triclinic LJ.
 template <int GEO>
 __global__ void __launch_bounds__(128)
-k_lj_gather(GatherArgs a, double* __restrict__ F, double* __restrict__ partials) {
-  __shared__ double sh32[32];
+k_lj_gather(GatherArgs a, double* __restrict__ F, double* __restrict__ eatom) {
   if (a.only_if_atom_shift && !(a.st_in->flags & kFlagAtomShift)) return;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   double e = 0.0, fx = 0.0, fy = 0.0, fz = 0.0;
@@ -185,9 +184,8 @@ k_lj_gather(GatherArgs a, double* __restrict__ F, double* __restrict__ partials)
     F[3 * (size_t)o] = fx;
     F[3 * (size_t)o + 1] = fy;
     F[3 * (size_t)o + 2] = fz;
+    eatom[i] = e;  // per-atom energies in sorted order: the fold has one order whatever path wrote them
   }
-  const double bs = block_sum(e, sh32);
-  if (threadIdx.x == 0) partials[blockIdx.x] = bs;
 }
 
 // ---- CuH2 pass 1 + 2: density, then embedding energy and derivative ---------------------------
@@ -223,8 +221,7 @@ template <int M>
 __global__ void __launch_bounds__(128)
 k_eam_force(GatherArgs a, const double* __restrict__ dfd_sorted,
             const double* __restrict__ eemb_sorted, double* __restrict__ F,
-            double* __restrict__ partials) {
-  __shared__ double sh32[32];
+            double* __restrict__ eatom) {
   if (a.only_if_atom_shift && !(a.st_in->flags & kFlagAtomShift)) return;
   exp_table_init();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -246,9 +243,8 @@ k_eam_force(GatherArgs a, const double* __restrict__ dfd_sorted,
     F[3 * (size_t)o] = fx;
     F[3 * (size_t)o + 1] = fy;
     F[3 * (size_t)o + 2] = fz;
+    eatom[i] = e;
   }
-  const double bs = block_sum(e, sh32);
-  if (threadIdx.x == 0) partials[blockIdx.x] = bs;
 }
 
 // ---- Fe-He (rgpot_fehe.f90:573-620): the three passes on the gather walk ---------------------------
@@ -278,8 +274,7 @@ k_fehe_density(GatherArgs a, double* __restrict__ dfd_sorted, double* __restrict
 
 __global__ void __launch_bounds__(128)
 k_fehe_force(GatherArgs a, const double* __restrict__ dfd_sorted, const double* __restrict__ dfs_sorted,
-             const double* __restrict__ eemb_sorted, double* __restrict__ F, double* __restrict__ partials) {
-  __shared__ double sh32[32];
+             const double* __restrict__ eemb_sorted, double* __restrict__ F, double* __restrict__ eatom) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   double e = 0.0, fx = 0.0, fy = 0.0, fz = 0.0;
   if (i < a.n) {
@@ -307,9 +302,8 @@ k_fehe_force(GatherArgs a, const double* __restrict__ dfd_sorted, const double* 
     F[3 * (size_t)o] = fx;
     F[3 * (size_t)o + 1] = fy;
     F[3 * (size_t)o + 2] = fz;
+    eatom[i] = e;
   }
-  const double bs = block_sum(e, sh32);
-  if (threadIdx.x == 0) partials[blockIdx.x] = bs;
 }
 
 // ---- neighbor-table emission (pair-set parity, list consumers) ----------------------------------

@@ -836,3 +836,57 @@ def test_zbl_device_entry_maps_species_on_the_device(oracle):
     assert float(d_E.item()) == e_h and np.array_equal(d_F.cpu().numpy(), f_h)
     e_o, f_o, _ = oracle.zbl_force(pos, Z)
     assert_energy(e_h, e_o)
+
+
+# ------------------------------------------------ inhomogeneous large systems on the automatic path
+def test_brick_auto_path_inhomogeneous_lj(oracle):
+    """A dense droplet in a dilute gas, 24 000 atoms, periodic: half-cutoff cells and bricks are
+    chosen automatically, the mean density badly underestimates the droplet (bricks are cut on the
+    first call, sized from the feedback on the second); both calls match the oracle bit-identically
+    to each other."""
+    rng = np.random.default_rng(21)
+    L = 120.0
+    m = 28
+    g = np.stack(np.meshgrid(*[np.arange(m)] * 3, indexing="ij"), -1).reshape(-1, 3)
+    g = g[((g - (m - 1) / 2) ** 2).sum(1) <= (m / 2) ** 2]  # a ball of a simple-cubic lattice, spacing 1.1
+    drop = g * 1.1 + 40.0 + rng.normal(0, 0.05, g.shape)
+    n_gas = 24000 - len(drop)
+    gm = int(np.ceil(n_gas ** (1 / 3)))
+    gas = (np.stack(np.meshgrid(*[np.arange(gm)] * 3, indexing="ij"), -1).reshape(-1, 3)[:n_gas] + 0.5) * (L / gm)
+    gas = gas[(((gas - 55.4) ** 2).sum(1)) > 20.0 ** 2]  # keep the gas out of the droplet
+    pos = np.vstack([drop, gas])
+    box = np.diag([L, L, L])
+    z = np.ones(len(pos), np.int32)
+    pot = rgpot_b200.LJPot(rgpot_b200.LJConfig(1.0, 2.5, 1.0))
+    e1, f1, _ = pot(pos, z, box)
+    e2, f2, _ = pot(pos, z, box)
+    e_o, f_o, _ = oracle.lj_force(pos, box, 1.0, 2.5, 1.0)
+    assert_energy(e1, e_o)
+    assert_forces(f1, f_o)
+    assert e1 == e2 and np.array_equal(f1, f2)
+    assert pot.stat("slow_atoms") == 0
+
+
+def test_brick_auto_path_nanoparticle_cuh2(oracle):
+    """A 22 000-atom Cu nanoparticle with adsorbed H in a large triclinic cell (mostly vacuum)."""
+    a = 3.615
+    cells = 22
+    cu = workloads._fcc(cells, a)
+    c = cu.mean(0)
+    cu = cu[((cu - c) ** 2).sum(1) <= (0.5 * cells * a) ** 2]
+    rng = np.random.default_rng(22)
+    cu = cu + rng.normal(0, 0.03, cu.shape)
+    shell = rng.normal(size=(300, 3))
+    h = c + shell / np.linalg.norm(shell, axis=1)[:, None] * (0.5 * cells * a + 1.6)
+    pos = np.vstack([cu, h]) + 30.0
+    Z = np.concatenate([np.full(len(cu), 29), np.full(len(h), 1)]).astype(np.int32)
+    Lb = cells * a + 60.0
+    box = np.array([[Lb, 0.0, 0.0], [0.15 * Lb, Lb, 0.0], [0.1 * Lb, -0.2 * Lb, Lb]])
+    assert len(pos) > 20000
+    pot = rgpot_b200.CuH2Pot()
+    e1, f1, _ = pot(pos, Z, box)
+    e2, f2, _ = pot(pos, Z, box)
+    e_o, f_o = oracle.cuh2_force(pos, Z, box)
+    assert_energy(e1, e_o)
+    assert_forces(f1, f_o)
+    assert e1 == e2 and np.array_equal(f1, f2)
