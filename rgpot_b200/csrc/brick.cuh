@@ -52,7 +52,15 @@ struct TileOut {
   double* dfd_sorted;   // EAM: F'(rho), sorted order (written by density, read by force)
   double* eemb_sorted;  // EAM: F(rho)
   Status* st;
+  // EAM: the density pass hands its survivor lists to the force pass (same plan, same boxes, same
+  // thread per atom), which then skips the search.  pool: 16-bit staged indices in warp-interleaved
+  // chunks (entry k of lane l at chunk + 32 k + l); lref[atom * TPA + sub] = chunk | count << 40,
+  // kNoList where the search has to be repeated (list took several rounds, pool exhausted).
+  unsigned short* pool;
+  unsigned long long* lref;
+  unsigned long long pool_cap;  // entries
 };
+constexpr unsigned long long kNoList = ~0ull;
 
 struct BrickPlan {
   int bd[3];      // cells per brick and direction
@@ -474,6 +482,8 @@ k_brick(const __grid_constant__ GatherArgs a, const __grid_constant__ BrickPlan 
         double e_thr = 0.0;  // this thread's share of the atom's energy
         int si = 0, gi = 0;
         const bool active = ai < natoms;
+        unsigned lsa = lsa0;  // end of the list of the last round
+        int rounds = 0;
         if (active) {
           int c = 0;
 #pragma unroll
@@ -510,10 +520,31 @@ k_brick(const __grid_constant__ GatherArgs a, const __grid_constant__ BrickPlan 
           };
           fetch_row();
           bool more = true;
+          // force pass: the list the density pass left for this thread, if it did
+          bool have = false;
+          unsigned lsa_pre = lsa0;
+          if (kForce && o.pool != nullptr) {
+            const unsigned long long ref = o.lref[(size_t)gi * TPA + sub];
+            if (ref != kNoList) {
+              const unsigned cnt = (unsigned)(ref >> 40);
+              const unsigned short* src = o.pool + (ref & ((1ull << 40) - 1ull)) + lane;
+#pragma unroll 4
+              for (unsigned k = 0; k < cnt; ++k, lsa_pre += lstride) {
+                const unsigned short v = __ldg(src + 32u * k);
+                asm volatile("st.shared.u16 [%0], %1;" ::"r"(lsa_pre), "h"(v));
+              }
+              have = true;
+            }
+          }
           // rounds of search-then-physics: one round unless the private list fills up first
           do {
             // ---- search: this thread's rows of the atom's stencil, FP32 ----------------------------------
-            unsigned lsa = lsa0;
+            lsa = lsa0;
+            ++rounds;
+            if (have) {
+              lsa = lsa_pre;
+              more = false;
+            } else
             for (;;) {
               if (s == s1) {  // next row: 2 ns + 1 cells that are contiguous in the staged order
                 if (row - TPA >= nrows) {
@@ -567,6 +598,28 @@ k_brick(const __grid_constant__ GatherArgs a, const __grid_constant__ BrickPlan 
           } while (more);
         }
         __syncwarp();
+        if (kDensity && o.pool != nullptr) {
+          // hand the lists of this warp to the force pass: one chunk, as long as its longest list
+          const unsigned cnt = (active && rounds == 1) ? (unsigned)(((float)(lsa - lsa0) + 0.5f) * inv_lstride) : 0u;
+          unsigned wmax = cnt;
+#pragma unroll
+          for (int off = 16; off > 0; off >>= 1) wmax = max(wmax, __shfl_xor_sync(0xffffffffu, wmax, off));
+          unsigned long long chunk = 0;
+          if (lane == 0 && wmax) chunk = atomicAdd(&o.st->pool_used, (unsigned long long)wmax * 32ull);
+          chunk = __shfl_sync(0xffffffffu, chunk, 0);
+          const bool fits = chunk + (unsigned long long)wmax * 32ull <= o.pool_cap;
+          if (fits) {
+            unsigned short* dst = o.pool + chunk + lane;
+            unsigned la = lsa0;
+#pragma unroll 4
+            for (unsigned k = 0; k < wmax; ++k, la += lstride) {
+              unsigned short v;
+              asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(la));
+              dst[32u * k] = v;
+            }
+          }
+          if (active) o.lref[(size_t)gi * TPA + sub] = (fits && rounds == 1) ? (chunk | (unsigned long long)cnt << 40) : kNoList;
+        }
         // the TPA threads of an atom fold their partial sums in a fixed tree
 #pragma unroll
         for (int off = 1; off < TPA; off <<= 1) {

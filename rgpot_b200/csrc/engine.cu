@@ -265,8 +265,10 @@ struct RgpotB200Pot {
   int opt_list = 0;
   int opt_slack = 0;  // percent of extra staged capacity over the mean halo population (0 = automatic)
   int opt_fine = 0;          // 1: never use half-cutoff cells
+  int opt_handoff = 1;        // EAM brick kernels: the force pass reuses the density pass's survivor lists
   long opt_fine_min = 20000;  // atoms from which half-cutoff cells are used
   long launches = 0;
+  long pool_used = 0;   // survivor-list entries the density pass handed to the force pass
   long slow_atoms = 0;  // diagnostics of the last single-system call (brick slow path)
   long prof[4] = {0, 0, 0, 0};  // RB_BRICK_TIMING builds only
   // feedback from the brick kernels: the largest halo population seen for a given (atoms, grid,
@@ -321,7 +323,7 @@ struct RgpotB200Pot {
 
   // single-system scratch
   DevBuf pos, Z, F, cell_of, rank, ashift, counts, starts, blocksums, order, order2, spos, scell, dfd, eemb,
-      dfs, partials, partials2, energy, status, mm, emit_pairs, emit_shifts, emit_count, emit_vecs, emit_dists;
+      dfs, partials, partials2, energy, status, mm, listpool, listref, emit_pairs, emit_shifts, emit_count, emit_vecs, emit_dists;
   // batch scratch
   DevBuf b_pos, b_Z, b_F, b_off, b_boxes, b_E, b_flags, b_bad, b_map;
   HostBuf h_pos, h_Z, h_F, h_off, h_boxes, h_E, h_flags, h_bad, h_small;
@@ -346,7 +348,7 @@ struct RgpotB200Pot {
   ~RgpotB200Pot() {
     cudaSetDevice(device);
     DevBuf* d[] = {&pos, &Z, &F, &cell_of, &rank, &ashift, &counts, &starts, &blocksums, &order, &order2,
-                   &spos, &scell, &dfd, &dfs, &eemb, &partials, &partials2, &energy, &status, &mm, &emit_pairs,
+                   &spos, &scell, &dfd, &dfs, &eemb, &partials, &partials2, &energy, &status, &mm, &listpool, &listref, &emit_pairs,
                    &emit_shifts, &emit_count, &emit_vecs, &emit_dists, &b_pos, &b_Z, &b_F, &b_off, &b_boxes, &b_E, &b_flags,
                    &b_bad, &b_map, &zbl_table, &zbl_bitmap};
     for (auto* b : d) b->release();
@@ -861,7 +863,21 @@ int run_cell_path(RgpotB200Pot* pot, long n, const double* d_pos, const int* d_Z
     if (tile_ok) {
       // brick kernels; the gather kernels cover atoms outside the cell (per-pair image shifts) --
       // each side returns at once when the binning flag is not its own
-      TileOut to{d_F, d_part, pot->dfd.as<double>(), pot->eemb.as<double>(), d_st};
+      TileOut to{d_F, d_part, pot->dfd.as<double>(), pot->eemb.as<double>(), d_st, nullptr, nullptr, 0};
+      if (pot->opt_handoff) {
+        // survivor lists handed from the density to the force pass: room for every thread's list at
+        // its capacity in half-filled warps (a shortfall only makes some threads search again)
+        const unsigned long long want = (unsigned long long)n * bp.tpa * bp.cap_list * 3ull / 2ull + 4096ull;
+        const unsigned long long cap = std::min(want, 1ull << 32);
+        if (pot->listpool.reserve(sizeof(unsigned short) * cap) == cudaSuccess &&
+            pot->listref.reserve(sizeof(unsigned long long) * (size_t)n * bp.tpa) == cudaSuccess) {
+          to.pool = pot->listpool.as<unsigned short>();
+          to.lref = pot->listref.as<unsigned long long>();
+          to.pool_cap = cap;
+        } else {
+          cudaGetLastError();
+        }
+      }
       int ls = al ? launch_brick<TILE_AL_DENSITY>(pot, ga, bp, to, st, "k_brick<al density>")
                   : launch_brick<TILE_EAM_DENSITY>(pot, ga, bp, to, st, "k_brick<eam density>");
       if (ls) return ls;
@@ -887,7 +903,7 @@ int run_cell_path(RgpotB200Pot* pot, long n, const double* d_pos, const int* d_Z
   } else if (BrickPlan bp{}; pl.geo == GEO_LJ_SHIFT && allow_tile && plan_bricks(pot, pl, n, rc, false, bp)) {
     // brick kernel; the literal-fold gather kernel covers the (rare) case of atoms outside the
     // cell -- each of the two returns at once when the binning flag is not its own
-    TileOut to{d_F, d_part, nullptr, nullptr, d_st};
+    TileOut to{d_F, d_part, nullptr, nullptr, d_st, nullptr, nullptr, 0};
     int ls = pl.lj.morse ? launch_brick<TILE_PAIR>(pot, ga, bp, to, st, "k_brick<pair>")
                          : launch_brick<TILE_LJ>(pot, ga, bp, to, st, "k_brick<lj>");
     if (ls) return ls;
@@ -1313,6 +1329,7 @@ long rgpot_b200_stat(RgpotB200Pot* pot, const char* key) {
   if (!pot || !key) return -1;
   if (strcmp(key, "launches") == 0) return pot->launches;
   if (strcmp(key, "slow_atoms") == 0) return pot->slow_atoms;
+  if (strcmp(key, "pool_used") == 0) return pot->pool_used;
   if (strcmp(key, "max_halo") == 0) return pot->memo.max_halo;
   if (strcmp(key, "brick") == 0) return pot->memo.bd[0] * 100 + pot->memo.bd[1] * 10 + pot->memo.bd[2];
   if (strcmp(key, "cap_cand") == 0) return pot->last_cap_cand;
@@ -1351,6 +1368,10 @@ int rgpot_b200_set_option(RgpotB200Pot* pot, const char* key, long value) {
   }
   if (strcmp(key, "fine_min") == 0) {
     pot->opt_fine_min = value;
+    return 0;
+  }
+  if (strcmp(key, "handoff") == 0) {
+    pot->opt_handoff = (int)value;
     return 0;
   }
   if (strcmp(key, "brick_threads") == 0) {
@@ -1470,6 +1491,7 @@ static int finish_single(RgpotB200Pot* pot, long n, const double* d_pos, const i
     }
     flags = stt.flags;
     pot->slow_atoms = stt.slow_atoms;
+    pot->pool_used = (long)stt.pool_used;
     for (int k = 0; k < 4; ++k) pot->prof[k] = (long)stt.prof[k];
     if (stt.max_halo > 0 && pot->memo_pending.n >= 0) {  // brick kernels ran: remember what they met
       const auto& mp = pot->memo_pending;

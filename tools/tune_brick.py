@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Time the large-system path (device-resident) under different brick-kernel settings.
 
-    python tools/tune_brick.py lj|slab [brick:tpa:threads ...]      e.g.  lj 0:0:0 222:2:256 221:4:256
+    python tools/tune_brick.py lj|slab [brick:tpa:threads:fine:list:slack:nohandoff ...]   e.g.  lj 0 222:2:256 slab 0:0:0:0:0:0:1
 """
 import os
 import sys
@@ -33,7 +33,8 @@ def main():
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     ref_F = None
     for st in settings:
-        b, tpa, thr, fine, lst, slack = (int(x) for x in (st.split(":") + ["0", "0", "0"])[:6])
+        b, tpa, thr, fine, lst, slack, nohand = (int(x) for x in (st.split(":") + ["0"] * 7)[:7])
+        pot.set_option("handoff", 0 if nohand else 1)
         pot.set_option("fine", fine)
         pot.set_option("brick_list", lst)
         pot.set_option("brick_slack", slack)
@@ -57,7 +58,7 @@ def main():
             ref_F = F
         print(f"{which} {st:>18}  min {min(ms):.4f} ms  med {float(np.median(ms)):.4f} ms  "
               f"{n / np.median(ms) / 1e6:.1f} M atom-evals/ms... E={float(d_E.item()):.12e}  "
-              f"max|dF| vs first {float(np.abs(F - ref_F).max()):.2e}  slow_atoms {pot.stat('slow_atoms')}", flush=True)
+              f"max|dF| vs first {float(np.abs(F - ref_F).max()):.2e}  slow_atoms {pot.stat('slow_atoms')} pool {pot.stat('pool_used')}", flush=True)
         prof = [pot.stat(f"prof{k}") for k in range(4)]
         if sum(prof) > 0:  # an -DRB_BRICK_TIMING build (RGPOT_B200_ENGINE=...): warp-clock shares of the phases
             tot = float(sum(prof))
