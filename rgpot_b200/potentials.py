@@ -329,6 +329,28 @@ class _EnginePot:
     def sync_status(self) -> int:
         return int(self._lib.rgpot_b200_sync_status(self._h))
 
+    def force_torch(self, positions, atom_types, box, sync: bool = True):
+        """torch interop: `positions` a CUDA float64 (n, 3) tensor, `atom_types` a
+        CUDA int32 (n,) tensor or None; nothing crosses PCIe.  Runs on torch's current stream of that
+        device and returns (energy, forces): forces a new CUDA tensor; energy a float when `sync`, else
+        a one-element CUDA tensor (collect the status later with ``sync_status``)."""
+        import torch
+
+        if not (positions.is_cuda and positions.dtype == torch.float64 and positions.dim() == 2 and
+                positions.shape[1] == 3):
+            raise ValueError("positions must be a CUDA float64 tensor of shape (n_atoms, 3)")
+        positions = positions.contiguous()
+        if atom_types is not None:
+            if not (atom_types.is_cuda and atom_types.shape == (positions.shape[0],)):
+                raise ValueError("atom_types must be a CUDA tensor of shape (n_atoms,)")
+            atom_types = atom_types.to(torch.int32).contiguous()
+        forces = torch.empty_like(positions)
+        energy = torch.empty(1, dtype=torch.float64, device=positions.device)
+        stream = torch.cuda.current_stream(positions.device).cuda_stream
+        self.force_device(positions, atom_types, box, forces, energy, stream, sync=sync)
+        self.force_calls += 1
+        return (float(energy.item()) if sync else energy), forces
+
     # -- neighbor table --------------------------------------------------------------------------
     def neighbors(self, positions, atom_types, box, path: int = 0):
         """(pairs (m, 2), shifts (m, 3)) of the table the kernels act on, unspecified order."""
@@ -466,6 +488,18 @@ def evaluate_lj(positions, atom_types, box):
 def evaluate_cuh2(positions, atom_types, box):
     """Same call shape for the CuH2 EAM (the reference module exposes LJ only)."""
     return _default(CuH2Pot)(positions, atom_types, box)
+
+
+_BY_NAME = {"LJ": LJPot, "LJCluster": LJClusterPot, "Morse": MorsePot, "ZBL": ZBLPot, "CuH2": CuH2Pot,
+            "EAMAl": EAMAlPot, "FeHe": FeHePot}  # the server's selector strings (server.cpp:208-220) and kin
+
+
+def evaluate_batch(systems, potential="CuH2"):
+    """[(energy, forces, variance)] for independent systems [(positions, atom_types, box), ...] in ONE
+    engine call (ForceBatch semantics, ForceStructs.hpp:39-54; the reference module has no batch
+    function).  `potential`: a selector string or a potential object."""
+    pot = _default(_BY_NAME[potential]) if isinstance(potential, str) else potential
+    return pot.forceBatch(systems)
 
 
 def neighbor_list(points, box, cutoff: float, full: bool = True, sorted: bool = True, periodic: bool = True,

@@ -890,3 +890,34 @@ def test_brick_auto_path_nanoparticle_cuh2(oracle):
     assert_energy(e1, e_o)
     assert_forces(f1, f_o)
     assert e1 == e2 and np.array_equal(f1, f2)
+
+
+def test_torch_interop_and_evaluate_batch(cuh2, golden, oracle):
+    """CUDA tensors in, CUDA tensors out on torch's current stream (nothing
+    crosses PCIe but the box), and the module-level batch function."""
+    import torch
+
+    s = golden("cuh2_slab218.json")
+    pos, Z, box = np.array(s["positions"]), np.array(s["Z"], np.int32), np.array(s["box"]).reshape(3, 3)
+    e_h, f_h, _ = cuh2(pos, Z, box)
+    dev = torch.device("cuda", 0)
+    side = torch.cuda.Stream(device=dev)
+    with torch.cuda.stream(side):
+        d_pos, d_Z = torch.from_numpy(pos).to(dev), torch.from_numpy(Z).to(dev)
+        e_t, f_t = cuh2.force_torch(d_pos, d_Z, box)
+        e_a, f_a = cuh2.force_torch(d_pos, d_Z.to(torch.int64), box, sync=False)  # other integer types are converted
+        assert cuh2.sync_status() == 0
+    assert f_t.is_cuda and f_t.shape == (len(pos), 3)
+    assert_energy(e_t, e_h)
+    assert_forces(f_t.cpu().numpy(), f_h)
+    assert float(e_a.item()) == e_t and torch.equal(f_a, f_t)
+    with pytest.raises(ValueError):
+        cuh2.force_torch(torch.from_numpy(pos), d_Z, box)  # host tensor
+    c13 = golden("lj13_cluster.json")
+    lj_pos, lj_box = np.array(c13["positions"]), np.array(c13["box"]).reshape(3, 3)
+    out = rgpot_b200.evaluate_batch([(pos, Z, box), (pos + 0.01, Z, box)])
+    assert out[0][0] == pytest.approx(e_h, rel=1e-12) and len(out) == 2
+    out_lj = rgpot_b200.evaluate_batch([(lj_pos, np.ones(len(lj_pos), np.int32), lj_box)], potential="LJ")
+    e_o, f_o, _ = oracle.lj_force(lj_pos, lj_box, 1.0, 15.0, 1.0)
+    assert_energy(out_lj[0][0], e_o)
+    assert_forces(out_lj[0][1], f_o)
