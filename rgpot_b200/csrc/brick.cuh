@@ -88,6 +88,23 @@ RB_D double rcp_fast(double a) {
   return fma(y, fma(e, e, e), y);
 }
 
+// image vector S.H in the reference's arithmetic: w * q per direction for the LJ family (its fold
+// subtracts w * round(d / w)), vesin's shift product for the all-image tables
+template <bool PAIR_GEO>
+RB_D void image_vector(const GatherArgs& a, int q0, int q1, int q2, double sv[3]) {
+  if (PAIR_GEO) {
+    sv[0] = xmul(a.lj.w[0], (double)q0);
+    sv[1] = xmul(a.lj.w[1], (double)q1);
+    sv[2] = xmul(a.lj.w[2], (double)q2);
+  } else {
+    sv[0] = shift_component(a.box.H, 0, (double)q0, (double)q1, (double)q2);
+    sv[1] = shift_component(a.box.H, 1, (double)q0, (double)q1, (double)q2);
+    sv[2] = shift_component(a.box.H, 2, (double)q0, (double)q1, (double)q2);
+  }
+}
+// an atom's own wrap counts (each in [-1, 1]) as an offset in the 5 x 5 x 5 image-code space
+RB_D int wrap_offset(unsigned long long m) { return meta_shift(m, 2) * 25 + meta_shift(m, 1) * 5 + meta_shift(m, 0); }
+
 // ---- pair terms shared by the brick kernel and its slow path ------------------------------------
 // One candidate at exact separation (dx, dy, dz), d2 = |d|^2 in the reference's arithmetic; `other`
 // is false for the atom itself.  acc: force components (density pass: acc[0] = rho).
@@ -133,7 +150,7 @@ RB_D void brick_pair(const GatherArgs& a, double rc2, double rc2_phys, bool othe
 // in the kernel's shuffle tree, so an atom gets the same bits whichever path evaluated it.
 template <int POT, int TPA>
 __device__ __noinline__ void brick_slow_atom(const GatherArgs& a, const BrickPlan& bp, const TileOut& o,
-                                             const double (*svtab)[3], int i, bool& coincident) {
+                                             const double (*svtab)[3], bool ashift, int i, bool& coincident) {
   constexpr bool kPairGeo = POT == TILE_LJ || POT == TILE_PAIR;
   constexpr bool kForce = tile_is_force(POT);
   constexpr bool kDensity = tile_is_density(POT);
@@ -180,9 +197,18 @@ __device__ __noinline__ void brick_slow_atom(const GatherArgs& a, const BrickPla
         const int nb = (r[2] * g.nc[1] + r[1]) * g.nc[0] + r[0];
         const int jb = a.starts[nb], je = a.starts[nb + 1];
         const int code = (q[2] + 2) * 25 + (q[1] + 2) * 5 + (q[0] + 2);
-        const double svx = svtab[code][0], svy = svtab[code][1], svz = svtab[code][2];
+        double svx = svtab[code][0], svy = svtab[code][1], svz = svtab[code][2];
         for (int j = jb; j < je; ++j) {
           const double4 pj = a.spos[j];
+          if (ashift) {  // image = cell image + s_i - s_j (vesin :1497)
+            const unsigned long long mj = (unsigned long long)__double_as_longlong(pj.w);
+            double sv[3];
+            image_vector<kPairGeo>(a, q[0] + meta_shift(mi, 0) - meta_shift(mj, 0), q[1] + meta_shift(mi, 1) - meta_shift(mj, 1),
+                                   q[2] + meta_shift(mi, 2) - meta_shift(mj, 2), sv);
+            svx = sv[0];
+            svy = sv[1];
+            svz = sv[2];
+          }
           // (p_j - p_i) + 0 is p_j - p_i: the kernel's unshifted boxes skip the addition
           const double dx = xadd(xsub(pj.x, pi.x), svx), dy = xadd(xsub(pj.y, pi.y), svy),
                        dz = xadd(xsub(pj.z, pi.z), svz);
@@ -232,7 +258,11 @@ k_brick(const __grid_constant__ GatherArgs a, const __grid_constant__ BrickPlan 
   __shared__ int s_shifted, s_ntot;
   __shared__ int box_stack[8][6];  // boxes of cells still to do: first cell, extent
 
-  if (a.st_in->flags & kFlagAtomShift) return;  // the gather kernels of gather.cuh take over
+  if (a.st_in->flags & kFlagBigShift) return;  // the gather kernels of gather.cuh take over
+  // atoms up to one cell vector outside the cell: the wrap count s_j of a staged atom is folded into
+  // its image code (q - s_j), that of the atom being evaluated is added pair by pair
+  // (re-read where needed instead of being kept in a register through the whole kernel)
+#define RB_ASHIFT ((a.st_in->flags & kFlagAtomShift) != 0)
   if (tile_is_density(POT) || tile_is_force(POT)) exp_table_init();
   constexpr bool kPairGeo = POT == TILE_LJ || POT == TILE_PAIR;  // LJ pair search (w * q image vectors)
   constexpr bool kForce = tile_is_force(POT);
@@ -253,16 +283,7 @@ k_brick(const __grid_constant__ GatherArgs a, const __grid_constant__ BrickPlan 
 
   // image vectors; the brick of this block as the first box
   for (int t = tid; t < kShiftCodes; t += nthreads) {
-    const double q0 = (double)(t % 5 - 2), q1 = (double)((t / 5) % 5 - 2), q2 = (double)(t / 25 - 2);
-    if (kPairGeo) {
-      svtab[t][0] = xmul(a.lj.w[0], q0);
-      svtab[t][1] = xmul(a.lj.w[1], q1);
-      svtab[t][2] = xmul(a.lj.w[2], q2);
-    } else {
-      svtab[t][0] = shift_component(a.box.H, 0, q0, q1, q2);
-      svtab[t][1] = shift_component(a.box.H, 1, q0, q1, q2);
-      svtab[t][2] = shift_component(a.box.H, 2, q0, q1, q2);
-    }
+    image_vector<kPairGeo>(a, t % 5 - 2, (t / 5) % 5 - 2, t / 25 - 2, svtab[t]);
   }
   if (tid == 0) {
     const int b[3] = {(int)blockIdx.x % bp.nb[0], ((int)blockIdx.x / bp.nb[0]) % bp.nb[1],
@@ -388,7 +409,7 @@ k_brick(const __grid_constant__ GatherArgs a, const __grid_constant__ BrickPlan 
       const int cell = (r[2] * g.nc[1] + r[1]) * g.nc[0] + r[0];
       const int jb = a.starts[cell], je = a.starts[cell + 1];
       if (tid == 0 && je > jb) atomicAdd(&o.st->slow_atoms, je - jb);
-      for (int j = jb + tid; j < je; j += nthreads) brick_slow_atom<POT, TPA>(a, bp, o, svtab, j, coincident);
+      for (int j = jb + tid; j < je; j += nthreads) brick_slow_atom<POT, TPA>(a, bp, o, svtab, RB_ASHIFT, j, coincident);
       if (--sp == 0) break;
       __syncthreads();
       continue;
@@ -442,22 +463,42 @@ k_brick(const __grid_constant__ GatherArgs a, const __grid_constant__ BrickPlan 
       }
     }
     // ---- stage the halo: a thread copies whole halo cells ----------------------------------------------
-    for (int h = tid; h < nh; h += nthreads) {
-      const int sb = hstart[h], se = hstart[h + 1], jb = hgstart[h] - sb;
-      const int code = hcode[h];
-      const double svx = svtab[code][0] - org[0], svy = svtab[code][1] - org[1], svz = svtab[code][2] - org[2];
-      for (int s = sb; s < se; ++s) {
-        const double4 p = a.spos[jb + s];
-        c64[3 * s] = p.x;
-        c64[3 * s + 1] = p.y;
-        c64[3 * s + 2] = p.z;
-        if (kForce) c64w[s] = o.dfd_sorted[jb + s];
-        const float fx = (float)(p.x + svx), fy = (float)(p.y + svy), fz = (float)(p.z + svz);
-        const __half2 hxy = __floats2half2_rn(fx, fy), hz0 = __floats2half2_rn(fz, 0.0f);
-        c16[s] = make_uint2(*reinterpret_cast<const unsigned*>(&hxy), *reinterpret_cast<const unsigned*>(&hz0));
-        cinfo[s] = (unsigned short)(code | (meta_species((unsigned long long)__double_as_longlong(p.w)) << 8));
+    auto stage = [&](auto ashift_tag) {
+      constexpr bool ASHIFT = decltype(ashift_tag)::value;
+      for (int h = tid; h < nh; h += nthreads) {
+        const int sb = hstart[h], se = hstart[h + 1], jb = hgstart[h] - sb;
+        const int code = hcode[h];
+        const double svx = svtab[code][0] - org[0], svy = svtab[code][1] - org[1], svz = svtab[code][2] - org[2];
+        for (int s = sb; s < se; ++s) {
+          const double4 p = a.spos[jb + s];
+          const unsigned long long mj = (unsigned long long)__double_as_longlong(p.w);
+          int cj = code;
+          double sx = svx, sy = svy, sz = svz;
+          if (ASHIFT) {
+            const int wo = wrap_offset(mj);
+            if (wo != 0) {  // vesin :1497: shift = cell shift + s_i - s_j
+              cj = code - wo;
+              sx = svtab[cj][0] - org[0];
+              sy = svtab[cj][1] - org[1];
+              sz = svtab[cj][2] - org[2];
+              s_shifted = 1;
+            }
+          }
+          c64[3 * s] = p.x;
+          c64[3 * s + 1] = p.y;
+          c64[3 * s + 2] = p.z;
+          if (kForce) c64w[s] = o.dfd_sorted[jb + s];
+          const float fx = (float)(p.x + sx), fy = (float)(p.y + sy), fz = (float)(p.z + sz);
+          const __half2 hxy = __floats2half2_rn(fx, fy), hz0 = __floats2half2_rn(fz, 0.0f);
+          c16[s] = make_uint2(*reinterpret_cast<const unsigned*>(&hxy), *reinterpret_cast<const unsigned*>(&hz0));
+          cinfo[s] = (unsigned short)(cj | (meta_species(mj) << 8));
+        }
       }
-    }
+    };
+    if (RB_ASHIFT)
+      stage(BoolTag<true>{});
+    else
+      stage(BoolTag<false>{});
     __syncthreads();
     RB_TICK(1);
     const int natoms = bc_astart[nbc];
@@ -472,8 +513,9 @@ k_brick(const __grid_constant__ GatherArgs a, const __grid_constant__ BrickPlan 
     const float inv_lstride = 1.0f / (float)lstride;
     // SHIFTED: some halo cell of this box is a periodic image (only bricks at the box faces);
     // elsewhere (p_j - p_i) + 0 is p_j - p_i and the image-vector lookup is skipped
-    auto evaluate = [&](auto shifted_tag) {
+    auto evaluate = [&](auto shifted_tag, auto ashift_tag) {
       constexpr bool SHIFTED = decltype(shifted_tag)::value;
+      constexpr bool ASHIFT = decltype(ashift_tag)::value;  // some atoms carry wrap counts (SHIFTED then)
       constexpr bool kNeedInfo = SHIFTED || POT != TILE_LJ;
       for (int a0 = 0; a0 < natoms; a0 += apb) {
         const int ai = a0 + tid / TPA;
@@ -499,6 +541,8 @@ k_brick(const __grid_constant__ GatherArgs a, const __grid_constant__ BrickPlan 
           const int zi = cinfo[si] >> 8;
           double dfd_i = 0.0;
           if (kForce) dfd_i = c64w[si];
+          int wi = 0;  // own wrap counts (rare): the image vector is then worked out pair by pair
+          if (ASHIFT) wi = wrap_offset((unsigned long long)__double_as_longlong(a.spos[gi].w));
           const int hlow = hc - (bp.ns[2] * hd[1] + bp.ns[1]) * hd[0] - bp.ns[0];  // stencil corner
           int ry = sub % nry, rz = sub / nry, row = sub;
           int s = 0, s1 = 0;  // cursor in the current stencil row
@@ -586,9 +630,18 @@ k_brick(const __grid_constant__ GatherArgs a, const __grid_constant__ BrickPlan 
               double dx = xsub(pj[0], pix), dy = xsub(pj[1], piy), dz = xsub(pj[2], piz);
               if (SHIFTED) {
                 const int code = info & 127;
-                dx = xadd(dx, svtab[code][0]);
-                dy = xadd(dy, svtab[code][1]);
-                dz = xadd(dz, svtab[code][2]);
+                if (!ASHIFT || wi == 0) {
+                  dx = xadd(dx, svtab[code][0]);
+                  dy = xadd(dy, svtab[code][1]);
+                  dz = xadd(dz, svtab[code][2]);
+                } else {
+                  const int wc = wi + kShiftCodes / 2;  // the wrap counts as a code
+                  double sv[3];
+                  image_vector<kPairGeo>(a, code % 5 + wc % 5 - 4, (code / 5) % 5 + (wc / 5) % 5 - 4, code / 25 + wc / 25 - 4, sv);
+                  dx = xadd(dx, sv[0]);
+                  dy = xadd(dy, sv[1]);
+                  dz = xadd(dz, sv[2]);
+                }
               }
               const double d2 = xnorm2(dx, dy, dz);
               brick_pair<POT>(a, rc2, rc2_phys, sj != si, zi, info >> 8, dfd_i, [&]() { return c64w[sj]; }, dx, dy,
@@ -647,10 +700,12 @@ k_brick(const __grid_constant__ GatherArgs a, const __grid_constant__ BrickPlan 
       }
     };
     if (natoms > 0) {
-      if (s_shifted)
-        evaluate(BoolTag<true>{});
+      if (!s_shifted)
+        evaluate(BoolTag<false>{}, BoolTag<false>{});
+      else if (!RB_ASHIFT)
+        evaluate(BoolTag<true>{}, BoolTag<false>{});
       else
-        evaluate(BoolTag<false>{});
+        evaluate(BoolTag<true>{}, BoolTag<true>{});
     }
     // the stack only changes when a box is cut (all threads, before any evaluation), so every
     // thread knows whether boxes remain: the last box needs no barrier and the warps retire alone
@@ -662,6 +717,7 @@ k_brick(const __grid_constant__ GatherArgs a, const __grid_constant__ BrickPlan 
   if (lane == 0)
     for (int k = 0; k < 4; ++k) atomicAdd(&o.st->prof[k], t_acc[k]);
 #endif
+#undef RB_ASHIFT
   if (kDensity && coincident) atomicOr(&o.st->flags, kFlagCoincident);
 }
 

@@ -101,6 +101,7 @@ __global__ void k_bin(const double* __restrict__ pos, int n, Box box, Grid g,
   locate(box, g, x, y, z, c, s);
   unsigned fl = 0;
   if ((s[0] | s[1] | s[2]) != 0) fl |= kFlagAtomShift;
+  if (abs(s[0]) > 1 || abs(s[1]) > 1 || abs(s[2]) > 1) fl |= kFlagBigShift;  // the brick kernels cover +-1
   if (abs(s[0]) > 511 || abs(s[1]) > 511 || abs(s[2]) > 511) fl |= kFlagShiftRange;
   if (fl) atomicOr(&st->flags, fl);
   const int cell = (c[2] * g.nc[1] + c[1]) * g.nc[0] + c[0];

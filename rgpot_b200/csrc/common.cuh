@@ -24,6 +24,7 @@ constexpr unsigned kFlagCoincident = 4u;   // -> status 3
 constexpr unsigned kFlagShiftRange = 8u;   // atom further than +-511 cells outside the box
 constexpr unsigned kFlagListOverflow = 16u;  // per-system, internal: retry on the slow path
 constexpr unsigned kFlagAtomShift = 32u;   // informational: some atom sits outside the cell
+constexpr unsigned kFlagBigShift = 128u;    // informational: some atom sits more than one cell vector outside
 constexpr unsigned kFlagSingularBox = 64u;  // -> status 1 (vesin: box matrix not invertible)
 
 struct Status {

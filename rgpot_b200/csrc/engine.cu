@@ -540,6 +540,9 @@ bool plan_bricks(const RgpotB200Pot* pot, const Plan& pl, long n, double rc, boo
   int ns[3];
   for (int k = 0; k < 3; ++k) {
     if (g.ns_lo[k] != g.ns_hi[k] || g.ns_lo[k] < 1 || g.ns_lo[k] > 2) return false;
+    // a halo cell is at most one image away (the kernels fold an atom's own wrap count of +-1 into
+    // the 5 x 5 x 5 image codes)
+    if (pl.box.periodic[k] && g.nc[k] < g.ns_lo[k]) return false;
     ns[k] = g.ns_lo[k];
   }
   const double mean = (double)n / (double)g.ncells;
@@ -884,7 +887,7 @@ int run_cell_path(RgpotB200Pot* pot, long n, const double* d_pos, const int* d_Z
       ls = al ? launch_brick<TILE_AL_FORCE>(pot, ga, bp, to, st, "k_brick<al force>")
               : launch_brick<TILE_EAM_FORCE>(pot, ga, bp, to, st, "k_brick<eam force>");
       if (ls) return ls;
-      ga.only_if_atom_shift = 1;
+      ga.only_if_big_shift = 1;
     }
     if (al) {
       k_eam_density<EAM_AL><<<nblk, 128, 0, st>>>(ga, pot->dfd.as<double>(), pot->eemb.as<double>(), d_st);
@@ -907,7 +910,7 @@ int run_cell_path(RgpotB200Pot* pot, long n, const double* d_pos, const int* d_Z
     int ls = pl.lj.morse ? launch_brick<TILE_PAIR>(pot, ga, bp, to, st, "k_brick<pair>")
                          : launch_brick<TILE_LJ>(pot, ga, bp, to, st, "k_brick<lj>");
     if (ls) return ls;
-    ga.only_if_atom_shift = 1;
+    ga.only_if_big_shift = 1;
     k_lj_gather<GEO_LJ_SHIFT><<<nblk, 128, 0, st>>>(ga, d_F, d_part);
     LAUNCH_CHECK(pot, "k_lj_gather<shift>");
     return reduce_energy(pot, d_part, (int)n, d_E, st);
@@ -1982,7 +1985,7 @@ static int batch_finish(RgpotB200Pot* pot, size_t nsys, const size_t* offsets, c
       }
     }
     int status = 0;
-    if (f & ~(kFlagAtomShift)) {
+    if (f & ~(kFlagAtomShift | kFlagBigShift)) {
       if ((f & kFlagForeignZ) && bad != INT_MAX && bad >= 0) {
         if (host_Z) {
           badz = host_Z[o + bad];

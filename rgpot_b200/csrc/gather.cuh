@@ -34,8 +34,8 @@ struct GatherArgs {
   LJParams lj;
   double rc2;           // GEO_IMAGES accept threshold (strict <)
   const Status* st_in;  // flags from binning (kFlagAtomShift selects the per-pair shift form)
-  int only_if_atom_shift;  // 1: run only when some atom sits outside the cell (the brick kernels
-                           //    of brick.cuh cover the other case)
+  int only_if_big_shift;   // 1: run only when some atom sits more than one cell vector outside the
+                           //    cell (the brick kernels of brick.cuh cover everything else)
   int keep_self_images;    // GEO_IMAGES: keep (i, i, S != 0) entries like vesin does (the EAM tables
                            //    of rgpot drop them, rgpot_neighbors.f90:132)
 };
@@ -171,7 +171,7 @@ RB_D void walk_dispatch(const GatherArgs& a, int i, const double4 pi, Body&& bod
 template <int GEO>
 __global__ void __launch_bounds__(128)
 k_lj_gather(GatherArgs a, double* __restrict__ F, double* __restrict__ eatom) {
-  if (a.only_if_atom_shift && !(a.st_in->flags & kFlagAtomShift)) return;
+  if (a.only_if_big_shift && !(a.st_in->flags & kFlagBigShift)) return;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   double e = 0.0, fx = 0.0, fy = 0.0, fz = 0.0;
   if (i < a.n) {
@@ -195,7 +195,7 @@ template <int M>
 __global__ void __launch_bounds__(128)
 k_eam_density(GatherArgs a, double* __restrict__ dfd_sorted, double* __restrict__ eemb_sorted,
               Status* __restrict__ st) {
-  if (a.only_if_atom_shift && !(a.st_in->flags & kFlagAtomShift)) return;
+  if (a.only_if_big_shift && !(a.st_in->flags & kFlagBigShift)) return;
   exp_table_init();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= a.n) return;
@@ -222,7 +222,7 @@ __global__ void __launch_bounds__(128)
 k_eam_force(GatherArgs a, const double* __restrict__ dfd_sorted,
             const double* __restrict__ eemb_sorted, double* __restrict__ F,
             double* __restrict__ eatom) {
-  if (a.only_if_atom_shift && !(a.st_in->flags & kFlagAtomShift)) return;
+  if (a.only_if_big_shift && !(a.st_in->flags & kFlagBigShift)) return;
   exp_table_init();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   double e = 0.0, fx = 0.0, fy = 0.0, fz = 0.0;

@@ -921,3 +921,53 @@ def test_torch_interop_and_evaluate_batch(cuh2, golden, oracle):
     e_o, f_o, _ = oracle.lj_force(lj_pos, lj_box, 1.0, 15.0, 1.0)
     assert_energy(out_lj[0][0], e_o)
     assert_forces(out_lj[0][1], f_o)
+
+
+def _scatter_outside(pos, box, rng, far=0):
+    """Atoms that left the cell, as they do in a molecular-dynamics run without re-wrapping: about a
+    tenth moved by one cell vector (any direction), `far` atoms by two."""
+    pos = pos.copy()
+    n = len(pos)
+    who = rng.choice(n, n // 10, replace=False)
+    pos[who] += rng.integers(-1, 2, (len(who), 3)) @ box
+    if far:
+        pos[rng.choice(n, far, replace=False)] += np.array([2, 0, -2]) @ box
+    return pos
+
+
+@pytest.mark.parametrize("far", [0, 3])
+def test_brick_atoms_outside_the_cell_lj(oracle, far):
+    """The brick kernels take atoms up to one cell vector outside the cell (their wrap counts are
+    folded into the image codes); further out, the gather kernels take over.  Same results, and the
+    same as for the wrapped positions up to the reference's own rounding of r_j - r_i."""
+    pos, Z, box = workloads.lj_fluid(24_000)
+    rng = np.random.default_rng(31)
+    out = _scatter_outside(pos, box, rng, far)
+    pot = rgpot_b200.LJPot(rgpot_b200.LJConfig(1.0, 2.5, 1.0))
+    e, f, _ = pot(out, Z, box)
+    assert (pot.stat("max_halo") > 0) == (far == 0)  # which kernels did the work
+    e_o, f_o, _ = oracle.lj_force(out, box, 1.0, 2.5, 1.0)
+    assert_energy(e, e_o)
+    assert_forces(f, f_o)
+    pot.set_path(1)  # gather kernels, literal fold
+    e_g, f_g, _ = pot(out, Z, box)
+    assert_energy(e, e_g)
+    assert_forces(f, f_g)
+
+
+@pytest.mark.parametrize("far", [0, 2])
+def test_brick_atoms_outside_the_cell_cuh2(oracle, far):
+    pos, Z, box = workloads.cu_slab_triclinic(cells=18)
+    assert len(pos) > 20000
+    rng = np.random.default_rng(32)
+    out = _scatter_outside(pos, box, rng, far)
+    pot = rgpot_b200.CuH2Pot()
+    e, f, _ = pot(out, Z, box)
+    assert (pot.stat("max_halo") > 0) == (far == 0)
+    e_o, f_o = oracle.cuh2_force(out, Z, box)
+    assert_energy(e, e_o)
+    assert_forces(f, f_o)
+    pot.set_path(1)  # gather kernels (vesin's per-pair shift form)
+    e_g, f_g, _ = pot(out, Z, box)
+    assert_energy(e, e_g)
+    assert_forces(f, f_g)

@@ -24,6 +24,13 @@ if OUTER:
     sys.argv.remove("--outer")
 
 
+SKIP = None  # --skip N: the N-th result of a report that holds several kernels
+for _a in list(sys.argv):
+    if _a.startswith("--skip="):
+        SKIP = int(_a.split("=")[1])
+        sys.argv.remove(_a)
+
+
 def disasm_lines(func_sub):
     tmp = tempfile.mkdtemp()
     subprocess.run(["cuobjdump", "-xelf", "all", os.path.join(ROOT, "rgpot_b200", "librgpot_b200.so")],
@@ -58,7 +65,8 @@ def disasm_lines(func_sub):
 def main():
     rep, func = sys.argv[1], sys.argv[2]
     top = int(sys.argv[3]) if len(sys.argv) > 3 else 40
-    txt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+    sel = ["--launch-skip", str(SKIP), "--launch-count", "1"] if SKIP is not None else []
+    txt = subprocess.run(["ncu", "-i", rep, *sel, "--page", "source", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(txt)))
     hdr = next(i for i, r in enumerate(rows) if "Instructions Executed" in r)
     H = rows[hdr]
