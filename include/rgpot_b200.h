@@ -174,13 +174,19 @@ RGPOT_B200_API int rgpot_b200_last_error(RgpotB200Pot *pot, char *buffer, int bu
 
 /** Kernels this handle has launched since creation (evidence for bench.py's gpu_launches). */
 RGPOT_B200_API long rgpot_b200_launch_count(RgpotB200Pot *pot);
-/** Diagnostics: "launches" (as above), "slow_atoms" (atoms of the last finished single-system call
- *  that a brick kernel evaluated on its in-kernel slow path; 0 in normal operation).  -1: unknown key. */
+/** Diagnostics of the last finished single-system call: "launches" (as above), "slow_atoms" (atoms a
+ *  brick kernel evaluated on its in-kernel slow path; 0 once the capacities follow the recorded halo
+ *  populations), "max_halo" / "brick" / "cap_cand" / "cap_list" (largest halo population met, brick
+ *  shape as decimal xyz, staged and list capacities of the plan; max_halo > 0 means the brick
+ *  kernels did the work), "pool_used" (survivor-list entries the EAM density pass handed to the
+ *  force pass).  -1: unknown key. */
 RGPOT_B200_API long rgpot_b200_stat(RgpotB200Pot *pot, const char *key);
 /** Tuning / test hooks: force a code path for subsequent calls.
  *  key "path": 0 auto, 1 cell-list, 2 all-pairs; "fine": 1 = never use half-cutoff cells;
  *  "fine_min": atoms from which half-cutoff cells are used; "brick" (cells per brick, decimal
- *  xyz), "brick_tpa", "brick_threads": brick-kernel tuning, 0 = automatic.                 */
+ *  xyz), "brick_tpa", "brick_threads", "brick_list", "brick_slack": brick-kernel tuning, 0 = automatic;
+ *  "handoff": 0 = the EAM force pass repeats the candidate search instead of reusing the density
+ *  pass's lists (default 1).                                                                */
 RGPOT_B200_API int rgpot_b200_set_option(RgpotB200Pot *pot, const char *key, long value);
 
 /** Page-locked host memory for the batch entry points. */
