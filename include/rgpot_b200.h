@@ -168,6 +168,23 @@ RGPOT_B200_API int rgpot_b200_neighbor_list(RgpotB200Pot *pot, size_t n_points, 
                                             int full, int sorted, RgpotB200NeighborList *out);
 RGPOT_B200_API void rgpot_b200_neighbor_list_free(RgpotB200NeighborList *nl);
 
+/** Result-cache keys of a packed batch: keys[i] is bit-identical to
+ *  Potential<D>::cacheKey(in[i]) of the reference (CppCore/rgpot/Potential.hpp:324-336) --
+ *  XXH3_64bits (xxHash 0.8.3, subprojects/xxhash.wrap) of the positions, the atomic numbers and the
+ *  box, XOR the hashes of `pot_type` (the PotType enumerator as size_t) and `params_key`
+ *  (paramsKey()) -- so the hit / miss compaction of Potential::forceBatch (:251-306) can hash a
+ *  whole batch in one launch and still address the entries the CPU path wrote.  Host buffers;
+ *  the _device variant takes device pointers for positions / atomicNrs / boxes / keys (offsets stay
+ *  on the host), enqueues on `cuda_stream` and does not synchronise.                          */
+RGPOT_B200_API int rgpot_b200_cache_keys(RgpotB200Pot *pot, size_t nSystems, const size_t *offsets,
+                                         const double *positions, const int *atomicNrs,
+                                         const double *boxes, uint64_t pot_type, uint64_t params_key,
+                                         uint64_t *keys);
+RGPOT_B200_API int rgpot_b200_cache_keys_device(RgpotB200Pot *pot, size_t nSystems, const size_t *offsets,
+                                                const double *d_positions, const int *d_atomicNrs,
+                                                const double *d_boxes, uint64_t pot_type,
+                                                uint64_t params_key, uint64_t *d_keys, void *cuda_stream);
+
 /** Message of the last failure on this handle (rgpot_ferror.f90:41-56 semantics, but per
  *  handle): copies at most buffer_len - 1 bytes, NUL-terminates, returns the length. */
 RGPOT_B200_API int rgpot_b200_last_error(RgpotB200Pot *pot, char *buffer, int buffer_len);

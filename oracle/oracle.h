@@ -115,6 +115,14 @@ int oracle_lj_force_allimages(long n, const double *pos, const double *box, doub
                               double cutoff, double psi, double *F, double *energy, char *err,
                               size_t errlen);
 
+/* --------------------------------------------------- result-cache key --- */
+
+/* XXH3_64bits of xxHash 0.8.3 (seed 0, default secret) -- the hash inside Potential<D>::cacheKey. */
+uint64_t oracle_xxh3_64(const void *data, size_t len);
+/* Potential<D>::cacheKey, CppCore/rgpot/Potential.hpp:324-336.                                   */
+uint64_t oracle_cache_key(size_t n, const double *pos, const int *atmnrs, const double *box, size_t pot_type,
+                          uint64_t params_key);
+
 #ifdef __cplusplus
 }
 #endif

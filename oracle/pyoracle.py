@@ -66,6 +66,10 @@ def _declare_common(lib):
     lib.oracle_fehe_force.restype = C.c_int
     lib.oracle_fehe_force.argtypes = [C.c_int32, _f64p, _i32p, _f64p, _f64p, C.POINTER(C.c_double), C.c_char_p,
                                       C.c_size_t]
+    lib.oracle_xxh3_64.restype = C.c_uint64
+    lib.oracle_xxh3_64.argtypes = [C.c_char_p, C.c_size_t]
+    lib.oracle_cache_key.restype = C.c_uint64
+    lib.oracle_cache_key.argtypes = [C.c_size_t, _f64p, _i32p, _f64p, C.c_size_t, C.c_uint64]
     lib.oracle_fehe_scalar.restype = C.c_double
     lib.oracle_fehe_scalar.argtypes = [C.c_int, C.c_double]
     lib.oracle_cuh2_force.restype = C.c_int
@@ -344,6 +348,20 @@ def eam_al_force(pos, box):
 def eam_al_scalar(which, x):
     """0 pair_energy, 1 pair_deriv, 2 density, 3 density_deriv (r); 4 embedding, 5 embedding_deriv (rho)."""
     return oracle_lib().oracle_eam_al_scalar(int(which), float(x))
+
+
+# ------------------------------------------------------------------ result-cache key
+def xxh3_64(data: bytes) -> int:
+    """XXH3_64bits (xxHash 0.8.3, seed 0) -- oracle/xxh3_oracle.c."""
+    return int(oracle_lib().oracle_xxh3_64(data, len(data)))
+
+
+def cache_key(pos, Z, box, pot_type: int, params_key: int) -> int:
+    """Potential<D>::cacheKey (Potential.hpp:324-336)."""
+    pos = np.ascontiguousarray(pos, dtype=np.float64).reshape(-1, 3)
+    Z = np.ascontiguousarray(Z, dtype=np.int32)
+    box = np.ascontiguousarray(box, dtype=np.float64).reshape(3, 3)
+    return int(oracle_lib().oracle_cache_key(len(pos), pos, Z, box, int(pot_type), int(params_key)))
 
 
 # ------------------------------------------------------------------ FeHe

@@ -23,6 +23,7 @@
 #include "physics.cuh"
 #include "small.cuh"
 #include "brick.cuh"
+#include "hash.cuh"
 
 using namespace rb;
 
@@ -2043,6 +2044,69 @@ int rgpot_b200_force_batch_device(RgpotB200Pot* pot, size_t nSystems, const size
   pd.E = d_energies;
   pd.d_boxes = d_boxes;
   pd.st = st;
+  return 0;
+}
+
+// ---- result-cache keys (hash.cuh) ----------------------------------------------------------------
+static int cache_keys_enqueue(RgpotB200Pot* pot, size_t nSystems, const size_t* offsets, const double* d_pos,
+                              const int* d_Z, const double* d_boxes, uint64_t pot_type, uint64_t params_key,
+                              uint64_t* d_keys, cudaStream_t st) {
+  CU_TRY(pot, pot->b_off.reserve(sizeof(size_t) * (nSystems + 1)));
+  CU_TRY(pot, cudaMemcpyAsync(pot->b_off.p, offsets, sizeof(size_t) * (nSystems + 1), cudaMemcpyHostToDevice, st));
+  // Potential.hpp:330-334: the type as size_t and the parameter fingerprint, eight bytes each
+  const uint64_t tail = rb::xxh3_host(reinterpret_cast<const unsigned char*>(&pot_type), 8) ^
+                        rb::xxh3_host(reinterpret_cast<const unsigned char*>(&params_key), 8);
+  rb::KeyArgs ka{pot->b_off.as<size_t>(), d_pos, d_Z, d_boxes, tail, d_keys, nSystems};
+  const int warps = 8;
+  k_cache_keys<<<(unsigned)((nSystems + warps - 1) / warps), 32 * warps, 0, st>>>(ka);
+  LAUNCH_CHECK(pot, "k_cache_keys");
+  return 0;
+}
+
+int rgpot_b200_cache_keys_device(RgpotB200Pot* pot, size_t nSystems, const size_t* offsets, const double* d_positions,
+                                 const int* d_atomicNrs, const double* d_boxes, uint64_t pot_type, uint64_t params_key,
+                                 uint64_t* d_keys, void* cuda_stream) {
+  if (!pot) return kStatusArgs;
+  pot->last_error.clear();
+  if (nSystems == 0) return 0;
+  if (!offsets || !d_positions || !d_atomicNrs || !d_boxes || !d_keys)
+    return fail(pot, kStatusArgs, "rgpot_b200_cache_keys_device: null buffer");
+  for (size_t i = 0; i < nSystems; ++i)
+    if (offsets[i + 1] < offsets[i]) return fail(pot, kStatusArgs, "rgpot_b200_cache_keys: offsets must not decrease");
+  CU_TRY(pot, cudaSetDevice(pot->device));
+  cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : pot->stream;
+  return cache_keys_enqueue(pot, nSystems, offsets, d_positions, d_atomicNrs, d_boxes, pot_type, params_key, d_keys, st);
+}
+
+int rgpot_b200_cache_keys(RgpotB200Pot* pot, size_t nSystems, const size_t* offsets, const double* positions,
+                          const int* atomicNrs, const double* boxes, uint64_t pot_type, uint64_t params_key,
+                          uint64_t* keys) {
+  if (!pot) return kStatusArgs;
+  pot->last_error.clear();
+  if (nSystems == 0) return 0;
+  if (!offsets || !positions || !atomicNrs || !boxes || !keys)
+    return fail(pot, kStatusArgs, "rgpot_b200_cache_keys: null buffer");
+  for (size_t i = 0; i < nSystems; ++i)
+    if (offsets[i + 1] < offsets[i]) return fail(pot, kStatusArgs, "rgpot_b200_cache_keys: offsets must not decrease");
+  CU_TRY(pot, cudaSetDevice(pot->device));
+  cudaStream_t st = pot->stream;
+  const size_t o0 = offsets[0], total = offsets[nSystems] - o0;
+  CU_TRY(pot, pot->b_pos.reserve(sizeof(double) * 3 * std::max<size_t>(total, 1)));
+  CU_TRY(pot, pot->b_Z.reserve(sizeof(int) * std::max<size_t>(total, 1)));
+  CU_TRY(pot, pot->b_boxes.reserve(sizeof(double) * 9 * nSystems));
+  CU_TRY(pot, pot->b_E.reserve(sizeof(uint64_t) * nSystems));
+  if (total) {
+    CU_TRY(pot, cudaMemcpyAsync(pot->b_pos.p, positions + 3 * o0, sizeof(double) * 3 * total, cudaMemcpyHostToDevice, st));
+    CU_TRY(pot, cudaMemcpyAsync(pot->b_Z.p, atomicNrs + o0, sizeof(int) * total, cudaMemcpyHostToDevice, st));
+  }
+  CU_TRY(pot, cudaMemcpyAsync(pot->b_boxes.p, boxes, sizeof(double) * 9 * nSystems, cudaMemcpyHostToDevice, st));
+  std::vector<size_t> rel(nSystems + 1);
+  for (size_t i = 0; i <= nSystems; ++i) rel[i] = offsets[i] - o0;
+  int s = cache_keys_enqueue(pot, nSystems, rel.data(), pot->b_pos.as<double>(), pot->b_Z.as<int>(),
+                             pot->b_boxes.as<double>(), pot_type, params_key, pot->b_E.as<uint64_t>(), st);
+  if (s) return s;
+  CU_TRY(pot, cudaMemcpyAsync(keys, pot->b_E.p, sizeof(uint64_t) * nSystems, cudaMemcpyDeviceToHost, st));
+  CU_TRY(pot, cudaStreamSynchronize(st));
   return 0;
 }
 

@@ -2,6 +2,7 @@
 #include "cuda_pots.hpp"
 
 #include <array>
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 #include <stdexcept>
@@ -137,6 +138,26 @@ void Engine::forceBatch(const char *label, const ForceBatch &batch) const {
     batch.out[i].variance = 0.0;
   }
   if (status != 0) raise(label, status);
+}
+
+std::vector<uint64_t> Engine::cacheKeys(const char *label, const ForceBatch &batch, PotType type) const {
+  const size_t n = batch.nSystems;
+  std::vector<uint64_t> keys(n);
+  if (n == 0) return keys;
+  // pack the systems back to back (the engine hashes one contiguous batch in one launch)
+  std::vector<size_t> offsets(n + 1, 0);
+  for (size_t i = 0; i < n; ++i) offsets[i + 1] = offsets[i] + batch.in[i].nAtoms;
+  std::vector<double> pos(3 * offsets[n] + 1), boxes(9 * n);
+  std::vector<int> z(offsets[n] + 1);
+  for (size_t i = 0; i < n; ++i) {
+    std::copy(batch.in[i].pos, batch.in[i].pos + 3 * batch.in[i].nAtoms, pos.begin() + 3 * offsets[i]);
+    std::copy(batch.in[i].atmnrs, batch.in[i].atmnrs + batch.in[i].nAtoms, z.begin() + offsets[i]);
+    std::copy(batch.in[i].box, batch.in[i].box + 9, boxes.begin() + 9 * i);
+  }
+  const int status = rgpot_b200_cache_keys(h_, n, offsets.data(), pos.data(), z.data(), boxes.data(),
+                                           static_cast<uint64_t>(static_cast<size_t>(type)), key_, keys.data());
+  if (status != 0) raise(label, status);
+  return keys;
 }
 
 } // namespace b200detail

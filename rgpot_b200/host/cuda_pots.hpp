@@ -65,6 +65,10 @@ public:
   Engine &operator=(const Engine &) = delete;
   void force(const char *label, const ForceInput &in, ForceOut *out) const;
   void forceBatch(const char *label, const ForceBatch &batch) const;
+  /// Result-cache keys of a batch, one launch: keys[i] equals
+  /// Potential<D>::cacheKey(batch.in[i]) (Potential.hpp:324-336, XXH3 over geometry, species, cell,
+  /// type and paramsKey), so forceBatch's hit / miss compaction (:251-306) can be fed from the GPU.
+  [[nodiscard]] std::vector<uint64_t> cacheKeys(const char *label, const ForceBatch &batch, PotType type) const;
   [[nodiscard]] uint64_t paramsKey() const noexcept { return key_; }
 
 private:
@@ -96,6 +100,9 @@ private:
       return c;                                                                                    \
     }                                                                                              \
     [[nodiscard]] uint64_t paramsKey() const noexcept override { return m_engine->paramsKey(); }   \
+    [[nodiscard]] std::vector<uint64_t> cacheKeys(const ForceBatch &batch) const {                 \
+      return m_engine->cacheKeys(Label, batch, get_type());                                        \
+    }                                                                                              \
     [[nodiscard]] const LJCudaConfig &config() const noexcept { return m_config; }                 \
                                                                                                    \
   private:                                                                                         \
@@ -128,6 +135,9 @@ public:
     return c;
   }
   [[nodiscard]] uint64_t paramsKey() const noexcept override { return m_engine->paramsKey(); }
+  [[nodiscard]] std::vector<uint64_t> cacheKeys(const ForceBatch &batch) const {
+    return m_engine->cacheKeys("Morse", batch, get_type());
+  }
   [[nodiscard]] const MorseCudaConfig &config() const noexcept { return m_config; }
   [[nodiscard]] double energyShift() const noexcept;
 
@@ -153,6 +163,9 @@ public:
     return c;
   }
   [[nodiscard]] uint64_t paramsKey() const noexcept override { return m_engine->paramsKey(); }
+  [[nodiscard]] std::vector<uint64_t> cacheKeys(const ForceBatch &batch) const {
+    return m_engine->cacheKeys("ZBL", batch, get_type());
+  }
   [[nodiscard]] const ZBLCudaConfig &config() const noexcept { return m_config; }
 
 private:

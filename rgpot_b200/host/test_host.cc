@@ -68,6 +68,11 @@ int main() {
   CHECK(within_rel(f1(0, 0), -7.5565221, 1e-6) && within_rel(f1(1, 0), 7.5565221, 1e-6));
   CHECK(out[2].energy == out[0].energy);
   CHECK(rgpot::registry<rgpot::CuH2CudaPot>::forceCalls.load() == 4);
+  {  // result-cache keys of the same batch (Potential.hpp:324-336): equal systems, equal keys; the
+     // potential type enters the key
+    const std::vector<uint64_t> keys = cuh2.cacheKeys(rgpot::ForceBatch{3, in, out});
+    CHECK(keys.size() == 3 && keys[0] == keys[2] && keys[0] != keys[1] && keys[0] != 0);
+  }
 
   // ---- LJClusterPotTest.cc:55-126
   AtomMatrix cluster{{50.594227, 52.017165, 52.277482}, {51.578540, 52.642148, 51.195222},

@@ -351,6 +351,50 @@ class _EnginePot:
         self.force_calls += 1
         return (float(energy.item()) if sync else energy), forces
 
+    # -- result cache (Potential.hpp:251-336) ------------------------------------------------------
+    def cacheKeys(self, systems) -> np.ndarray:
+        """uint64 cache keys of independent systems [(positions, atom_types, box), ...], each equal to
+        the reference's ``Potential::cacheKey`` (XXH3 of geometry, species and cell, XOR the hashes of
+        the potential type and ``paramsKey()``): one launch for the whole batch."""
+        n = len(systems)
+        if n == 0:
+            return np.zeros(0, dtype=np.uint64)
+        pos = [_as_positions(s[0]) for s in systems]
+        typ = [_as_types(s[1], p.shape[0]) for s, p in zip(systems, pos)]
+        offsets = np.zeros(n + 1, dtype=np.uint64)
+        offsets[1:] = np.cumsum([p.shape[0] for p in pos])
+        P = np.ascontiguousarray(np.concatenate(pos)) if offsets[-1] else np.zeros((1, 3))
+        T = np.ascontiguousarray(np.concatenate(typ)) if offsets[-1] else np.zeros(1, np.int32)
+        B = np.ascontiguousarray(np.stack([_as_box(s[2]) for s in systems]))
+        keys = np.zeros(n, dtype=np.uint64)
+        st = self._lib.rgpot_b200_cache_keys(self._h, n, offsets.ctypes.data, P.ctypes.data, T.ctypes.data,
+                                             B.ctypes.data, int(self.get_type().value), int(self.paramsKey()),
+                                             keys.ctypes.data)
+        if st != 0:
+            self._raise(st)
+        return keys
+
+    def forceBatchCached(self, systems, cache: dict):
+        """``Potential::forceBatch`` with a result cache (Potential.hpp:251-306): every system is keyed
+        on its own, hits are served from `cache` (a mapping key -> (energy, forces)), only the misses
+        reach the kernel as one compact batch, and their results are written back.  Returns
+        ([(energy, forces, variance)], number of misses)."""
+        keys = self.cacheKeys(systems)
+        out = [None] * len(systems)
+        misses = []
+        for i, k in enumerate(keys.tolist()):
+            hit = cache.get(k)
+            if hit is not None:
+                out[i] = (hit[0], hit[1].copy(), 0.0)
+            else:
+                misses.append(i)
+        if misses:
+            res = self.forceBatch([systems[i] for i in misses])
+            for i, r in zip(misses, res):
+                out[i] = r
+                cache[int(keys[i])] = (r[0], r[1].copy())
+        return out, len(misses)
+
     # -- neighbor table --------------------------------------------------------------------------
     def neighbors(self, positions, atom_types, box, path: int = 0):
         """(pairs (m, 2), shifts (m, 3)) of the table the kernels act on, unspecified order."""

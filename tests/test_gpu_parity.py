@@ -971,3 +971,49 @@ def test_brick_atoms_outside_the_cell_cuh2(oracle, far):
     e_g, f_g, _ = pot(out, Z, box)
     assert_energy(e, e_g)
     assert_forces(f, f_g)
+
+
+def test_cache_keys_bit_identical_to_reference_hash(cuh2, oracle, golden):
+    """SURVEY 8(f) rank 4: rgpot_b200_cache_keys == Potential::cacheKey (XXH3 of positions, species,
+    box, type, paramsKey) for every input-length class: empty systems, 1..12 atoms (short forms of
+    both arrays), 61 atoms (long form for the species array starts at 61), 218, 1000 (several
+    1024-byte blocks), and the committed xxhash vectors."""
+    rng = np.random.default_rng(41)
+    box = np.diag([15.3456, 21.702, 100.0])
+    systems = []
+    for n in [0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 42, 43, 60, 61, 64, 128, 218, 219, 1000, 2731]:
+        pos = rng.random((n, 3)) * 20.0
+        Z = np.where(rng.random(n) < 0.1, 1, 29).astype(np.int32)
+        systems.append((pos, Z, box * (1.0 + 0.01 * n)))
+    keys = cuh2.cacheKeys(systems)
+    for (pos, Z, b), k in zip(systems, keys.tolist()):
+        assert k == oracle.cache_key(pos, Z, b, rgpot_b200.PotType.CuH2.value, cuh2.paramsKey()), len(pos)
+    for c in golden("xxh3_vectors.json")["cache_keys"]:  # digests of libxxhash itself
+        class Fixed(type(cuh2)):
+            def paramsKey(self):
+                return c["params_key"]
+        pot = Fixed()
+        k = pot.cacheKeys([(np.array(c["positions"]).reshape(-1, 3), np.array(c["Z"], np.int32),
+                            np.array(c["box"]).reshape(3, 3))])
+        assert int(k[0]) == int(c["key"])
+    lj = rgpot_b200.LJPot()
+    assert lj.cacheKeys(systems[5:6])[0] != keys[5]  # type and parameter fingerprint enter the key
+
+
+def test_force_batch_cached_compacts_misses(cuh2, golden):
+    """Potential::forceBatch with a cache (Potential.hpp:251-306): hits are served, only the misses
+    reach the kernel, results are written back."""
+    s = golden("cuh2_slab218.json")
+    pos, Z, box = np.array(s["positions"]), np.array(s["Z"], np.int32), np.array(s["box"]).reshape(3, 3)
+    rng = np.random.default_rng(42)
+    band = [(pos + rng.normal(0, 0.02, pos.shape), Z, box) for _ in range(6)]
+    cache = {}
+    first, missed = cuh2.forceBatchCached(band, cache)
+    assert missed == 6 and len(cache) == 6
+    band[2] = (band[2][0] + 0.01, Z, box)  # one image moved
+    calls = cuh2.force_calls
+    again, missed = cuh2.forceBatchCached(band, cache)
+    assert missed == 1 and cuh2.force_calls == calls + 1
+    direct = cuh2.forceBatch(band)
+    for a, d in zip(again, direct):
+        assert a[0] == d[0] and np.array_equal(a[1], d[1])

@@ -280,3 +280,21 @@ def test_fehe_physics_checks(oracle):
         assert oracle.fehe_scalar(which, np.nextafter(rc, np.inf)) == 0.0
     for r in (1.0, 2.05):
         assert oracle.fehe_scalar(0, np.nextafter(r, 0)) == pytest.approx(oracle.fehe_scalar(0, r), rel=2e-3)
+
+
+# ------------------------------------------------------------------ result-cache key
+def test_xxh3_restatement_matches_xxhash_vectors(oracle, golden):
+    """oracle/xxh3_oracle.c against digests of libxxhash (tests/golden/make_xxh3_golden.py): every
+    length class of XXH3_64bits, and Potential::cacheKey assembled as Potential.hpp:324-336 does."""
+    g = golden("xxh3_vectors.json")
+
+    def pattern(n):
+        return bytes(((i * 131 + n * 31 + (i >> 8) * 7) & 0xFF) for i in range(n))
+
+    assert len(g["digests"]) > 260
+    for n, digest in g["digests"]:
+        assert oracle.xxh3_64(pattern(n)) == int(digest), n
+    for c in g["cache_keys"]:
+        key = oracle.cache_key(np.array(c["positions"]).reshape(-1, 3), np.array(c["Z"], np.int32),
+                               np.array(c["box"]).reshape(3, 3), c["pot_type"], c["params_key"])
+        assert key == int(c["key"])
