@@ -156,17 +156,28 @@ __device__ inline uint64_t xxh3_long_group(const unsigned char* in, size_t len, 
   const unsigned char* s = c_xxh_secret;
   const uint64_t init[8] = {kP32_3, kP64_1, kP64_2, kP64_3, kP64_4, kP32_2, kP64_5, kP32_1};
   uint64_t acc = init[l];
-  auto stripe = [&](const unsigned char* p, uint64_t key) {
-    const uint64_t v = in64(p + 8 * l);
+  auto absorb = [&](uint64_t v, uint64_t key) {
     const uint64_t other = __shfl_xor_sync(mask, v, 1);  // adjacent lanes swap their input words
     const uint64_t k = v ^ key;
     acc += other + (k & 0xffffffffull) * (k >> 32);
   };
+  auto stripe = [&](const unsigned char* p, uint64_t key) { absorb(in64(p + 8 * l), key); };
+  const bool aligned8 = (reinterpret_cast<uintptr_t>(in) & 7) == 0;
   const size_t block = 64 * 16, nblocks = (len - 1) / block;
   const uint64_t scramble_key = sw[16 + l];
   for (size_t b = 0; b < nblocks; ++b) {
-#pragma unroll 4
-    for (int t = 0; t < 16; ++t) stripe(in + b * block + 64 * t, sw[t + l]);
+    // a block of 16 stripes: all sixteen loads of this lane are issued before the first is used
+    uint64_t v[16];
+    const unsigned char* p = in + b * block + 8 * l;
+    if (aligned8) {
+#pragma unroll
+      for (int t = 0; t < 16; ++t) v[t] = __ldg(reinterpret_cast<const unsigned long long*>(p + 64 * t));
+    } else {
+#pragma unroll
+      for (int t = 0; t < 16; ++t) v[t] = in64(p + 64 * t);
+    }
+#pragma unroll
+    for (int t = 0; t < 16; ++t) absorb(v[t], sw[t + l]);
     acc = ((acc ^ (acc >> 47)) ^ scramble_key) * kP32_1;
   }
   const int nstripes = (int)(((len - 1) - block * nblocks) / 64);

@@ -374,6 +374,15 @@ class _EnginePot:
             self._raise(st)
         return keys
 
+    def cache_keys_device(self, offsets, d_pos, d_Z, d_boxes, d_keys, stream=None):
+        """Device-resident form (torch CUDA tensors; `d_keys` int64/uint64 of nSystems): enqueue only."""
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        s = self._lib.rgpot_b200_cache_keys_device(
+            self._h, len(offsets) - 1, offsets.ctypes.data, d_pos.data_ptr(), d_Z.data_ptr(), d_boxes.data_ptr(),
+            int(self.get_type().value), int(self.paramsKey()), d_keys.data_ptr(), stream)
+        if s != 0:
+            self._raise(s)
+
     def forceBatchCached(self, systems, cache: dict):
         """``Potential::forceBatch`` with a result cache (Potential.hpp:251-306): every system is keyed
         on its own, hits are served from `cache` (a mapping key -> (energy, forces)), only the misses

@@ -122,6 +122,42 @@ def main():
     out.append({"workload": "neighbor_list_cu_slab_32k_6.1A_full", "kernel": "k_emit_pairs<GEO_IMAGES> (two passes)",
                 "n_atoms": len(pos), "entries": int(len(nl["distances"])), "seconds_host_call": dt,
                 "value": len(pos) / dt, "note": "host call incl. H2D, two emit passes, D2H of 44 B per entry"})
+    # result-cache keys (XXH3) of a 65 536 x 218-atom batch, device-resident: HBM-bound byte work
+    from oracle import pyoracle
+    nsys, na = 65536, 218
+    dev = torch.device("cuda", 0)
+    g = torch.Generator(device=dev).manual_seed(5)
+    d_pos = torch.rand((nsys * na, 3), dtype=torch.float64, device=dev, generator=g) * 20.0
+    d_Z = torch.full((nsys * na,), 29, dtype=torch.int32, device=dev)
+    d_boxes = torch.eye(3, dtype=torch.float64, device=dev).repeat(nsys, 1).contiguous() * 25.0
+    d_keys = torch.zeros(nsys, dtype=torch.int64, device=dev)
+    offsets = np.arange(nsys + 1, dtype=np.uint64) * na
+    pot = rgpot_b200.CuH2Pot()
+    ts = torch.cuda.current_stream(dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    for _ in range(3):
+        pot.cache_keys_device(offsets, d_pos, d_Z, d_boxes, d_keys, ts.cuda_stream)
+    ms = []
+    for _ in range(5):
+        flush.zero_()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        pot.cache_keys_device(offsets, d_pos, d_Z, d_boxes, d_keys, ts.cuda_stream)
+        t1.record()
+        torch.cuda.synchronize()
+        ms.append(t0.elapsed_time(t1))
+    nbytes = nsys * (na * 28 + 72)
+    hp, hz, hb = d_pos[:na].cpu().numpy(), d_Z[:na].cpu().numpy(), d_boxes[:3].cpu().numpy()
+    assert int(d_keys[0].item()) & (2**64 - 1) == pyoracle.cache_key(hp, hz, hb, 1, pot.paramsKey())
+    t0 = time.perf_counter()
+    for _ in range(2000):
+        pyoracle.cache_key(hp, hz, hb, 1, pot.paramsKey())
+    cpu_rate = 2000 * (na * 28 + 72) / (time.perf_counter() - t0)
+    out.append({"workload": "cache_keys_65536x218", "kernel": "k_cache_keys", "bytes": nbytes,
+                "ms_per_step": float(np.median(ms)), "GB_per_s": nbytes / float(np.median(ms)) / 1e6,
+                "value": nsys * na / float(np.median(ms)) * 1e3,
+                "cpu_baseline": {"value": cpu_rate / 1e9, "unit": "GB/s", "cores": 1, "kind": "port",
+                                 "sample": "2000 keys of one 218-atom system through oracle/xxh3_oracle.c (ctypes call included)"}})
     for rec in out:
         rec["unit"] = "atom-evals/s"
         if rec["workload"] in cpu:
