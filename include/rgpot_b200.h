@@ -202,7 +202,7 @@ RGPOT_B200_API long rgpot_b200_stat(RgpotB200Pot *pot, const char *key);
  *  key "path": 0 auto, 1 cell-list, 2 all-pairs; "fine": 1 = never use half-cutoff cells;
  *  "fine_min": atoms from which half-cutoff cells are used; "brick" (cells per brick, decimal
  *  xyz), "brick_tpa", "brick_threads", "brick_list", "brick_slack": brick-kernel tuning, 0 = automatic;
- *  "handoff": 0 = the EAM force pass repeats the candidate search instead of reusing the density
+ *  "bricks": 0 = gather kernels only; "handoff": 0 = the EAM force pass repeats the candidate search instead of reusing the density
  *  pass's lists (default 1).                                                                */
 RGPOT_B200_API int rgpot_b200_set_option(RgpotB200Pot *pot, const char *key, long value);
 

@@ -34,11 +34,18 @@
 
 namespace rb {
 
-// TILE_PAIR: Morse / ZBL on the LJ geometry; TILE_AL_*: the EAM passes with the aluminium model
-enum { TILE_LJ = 0, TILE_EAM_DENSITY = 1, TILE_EAM_FORCE = 2, TILE_PAIR = 3, TILE_AL_DENSITY = 4, TILE_AL_FORCE = 5 };
-constexpr bool tile_is_density(int pot) { return pot == TILE_EAM_DENSITY || pot == TILE_AL_DENSITY; }
-constexpr bool tile_is_force(int pot) { return pot == TILE_EAM_FORCE || pot == TILE_AL_FORCE; }
-constexpr int tile_model(int pot) { return pot >= TILE_AL_DENSITY ? EAM_AL : EAM_CUH2; }
+// TILE_PAIR: Morse / ZBL on the LJ geometry; TILE_AL_*: the EAM passes with the aluminium model;
+// TILE_FEHE_*: the Fe-He passes (two density channels, so two F'(rho) per staged atom)
+enum {
+  TILE_LJ = 0, TILE_EAM_DENSITY = 1, TILE_EAM_FORCE = 2, TILE_PAIR = 3, TILE_AL_DENSITY = 4, TILE_AL_FORCE = 5,
+  TILE_FEHE_DENSITY = 6, TILE_FEHE_FORCE = 7
+};
+constexpr bool tile_is_density(int pot) { return pot == TILE_EAM_DENSITY || pot == TILE_AL_DENSITY || pot == TILE_FEHE_DENSITY; }
+constexpr bool tile_is_force(int pot) { return pot == TILE_EAM_FORCE || pot == TILE_AL_FORCE || pot == TILE_FEHE_FORCE; }
+constexpr bool tile_is_fehe(int pot) { return pot == TILE_FEHE_DENSITY || pot == TILE_FEHE_FORCE; }
+constexpr int tile_model(int pot) { return (pot == TILE_AL_DENSITY || pot == TILE_AL_FORCE) ? EAM_AL : EAM_CUH2; }
+// FP64 words staged per halo atom: position, + F'(rho) in a force pass, + the second channel's (Fe-He)
+constexpr int tile_words(int pot) { return pot == TILE_FEHE_FORCE ? 5 : (tile_is_force(pot) ? 4 : 3); }
 
 constexpr int kBrickMaxThreads = 384;  // 2 blocks of 384 or 3 of 256 per SM at <= 85 registers
 constexpr int kBrickMaxHalo = 512;  // (4 + 2*2)^3
@@ -51,6 +58,7 @@ struct TileOut {
   double* eatom;        // per-atom energies, sorted order (LJ, EAM force): folded in one fixed order
   double* dfd_sorted;   // EAM: F'(rho), sorted order (written by density, read by force)
   double* eemb_sorted;  // EAM: F(rho)
+  double* dfs_sorted;   // Fe-He: F'(rho) of the s-band channel
   Status* st;
   // EAM: the density pass hands its survivor lists to the force pass (same plan, same boxes, same
   // thread per atom), which then skips the search.  pool: 16-bit staged indices in warp-interleaved
@@ -75,8 +83,8 @@ struct BrickPlan {
   unsigned smem;  // dynamic shared memory per block
 };
 
-RB_HD unsigned brick_smem_bytes(int cap_cand, int cap_list, int threads, bool force_pass) {
-  return (unsigned)(cap_cand * ((force_pass ? 4 : 3) * sizeof(double) + sizeof(uint2) + sizeof(unsigned short)) +
+RB_HD unsigned brick_smem_bytes(int cap_cand, int cap_list, int threads, int words) {
+  return (unsigned)(cap_cand * (words * sizeof(double) + sizeof(uint2) + sizeof(unsigned short)) +
                     (size_t)cap_list * threads * sizeof(unsigned short) + 16);
 }
 
@@ -108,10 +116,33 @@ RB_D int wrap_offset(unsigned long long m) { return meta_shift(m, 2) * 25 + meta
 // ---- pair terms shared by the brick kernel and its slow path ------------------------------------
 // One candidate at exact separation (dx, dy, dz), d2 = |d|^2 in the reference's arithmetic; `other`
 // is false for the atom itself.  acc: force components (density pass: acc[0] = rho).
-template <int POT, class DfdJ>
+template <int POT, class DfdJ, class DfsJ>
 RB_D void brick_pair(const GatherArgs& a, double rc2, double rc2_phys, bool other, int zi, int zj, double dfd_i,
-                     DfdJ&& dfd_j, double dx, double dy, double dz, double d2, double& e, double* acc,
-                     bool& coincident) {
+                     DfdJ&& dfd_j, double dfs_i, DfsJ&& dfs_j, double dx, double dy, double dz, double d2, double& e,
+                     double* acc, bool& coincident) {
+  if (tile_is_fehe(POT)) {
+    // rgpot_fehe.f90: every branch is a comparison on r = sqrt(d2), the table's IEEE square root
+    if (d2 < rc2 && other) {
+      const double r = sqrt(d2);
+      double rho, drho;
+      const int ch = fehe_density(zi, zj, r, rho, drho);  // 0 d-band, 1 s-band, -1 none
+      if (tile_is_density(POT)) {  // atom_densities :480-500
+        if (ch == 0) acc[0] += rho;
+        if (ch == 1) acc[1] += rho;
+      } else {  // atom_contribution :509-538
+        double v, dv;
+        fehe_pair(zi, zj, r, v, dv);
+        e += 0.5 * v;
+        double radial = dv;
+        if (ch == 0) radial += (dfd_i + dfd_j()) * drho;
+        if (ch == 1) radial += (dfs_i + dfs_j()) * drho;
+        acc[0] += radial * (dx / r);
+        acc[1] += radial * (dy / r);
+        acc[2] += radial * (dz / r);
+      }
+    }
+    return;
+  }
   if (POT == TILE_LJ) {
     if (d2 <= rc2 && other) {  // vesin_visit.hpp:104
       const double invR2 = rcp_fast(d2);
@@ -154,7 +185,8 @@ __device__ __noinline__ void brick_slow_atom(const GatherArgs& a, const BrickPla
   constexpr bool kPairGeo = POT == TILE_LJ || POT == TILE_PAIR;
   constexpr bool kForce = tile_is_force(POT);
   constexpr bool kDensity = tile_is_density(POT);
-  constexpr int NV = kDensity ? 1 : 3;
+  constexpr bool kFeHe = tile_is_fehe(POT);
+  constexpr int NV = kDensity ? (kFeHe ? 2 : 1) : 3;
   const Grid& g = a.grid;
   const int cell = a.scell[i];
   const int c[3] = {cell % g.nc[0], (cell / g.nc[0]) % g.nc[1], cell / (g.nc[0] * g.nc[1])};
@@ -163,8 +195,9 @@ __device__ __noinline__ void brick_slow_atom(const GatherArgs& a, const BrickPla
   const int zi = meta_species(mi);
   const double rc2 = kPairGeo ? a.lj.rc2 : a.rc2;
   const double rc2_phys = kPairGeo ? 0.0 : eam_par<tile_model(POT)>().rc2_phys;
-  double dfd_i = 0.0;
+  double dfd_i = 0.0, dfs_i = 0.0;
   if (kForce) dfd_i = o.dfd_sorted[i];
+  if (kForce && kFeHe) dfs_i = o.dfs_sorted[i];
   const int nrx = 2 * bp.ns[0] + 1, nry = 2 * bp.ns[1] + 1, nrows = nry * (2 * bp.ns[2] + 1);
   double part[TPA][4];
 #pragma unroll
@@ -215,7 +248,8 @@ __device__ __noinline__ void brick_slow_atom(const GatherArgs& a, const BrickPla
           const double d2 = xnorm2(dx, dy, dz);
           const int zj = meta_species((unsigned long long)__double_as_longlong(pj.w));
           brick_pair<POT>(a, rc2, rc2_phys, j != i || code != kShiftCodes / 2, zi, zj, dfd_i,
-                          [&]() { return o.dfd_sorted[j]; }, dx, dy, dz, d2, e, acc, coincident);
+                          [&]() { return o.dfd_sorted[j]; }, dfs_i, [&]() { return o.dfs_sorted[j]; }, dx, dy, dz, d2,
+                          e, acc, coincident);
         }
       }
     }
@@ -231,7 +265,13 @@ __device__ __noinline__ void brick_slow_atom(const GatherArgs& a, const BrickPla
       for (int k = 0; k < 4; ++k) part[sub][k] += part[sub + off][k];
   if (kDensity) {
     double emb, demb;
-    eam_embed<tile_model(POT)>(zi, part[0][0], emb, demb);
+    if (kFeHe) {
+      double dems;
+      fehe_embed(zi, part[0][0], part[0][1], emb, demb, dems);
+      o.dfs_sorted[i] = dems;
+    } else {
+      eam_embed<tile_model(POT)>(zi, part[0][0], emb, demb);
+    }
     o.dfd_sorted[i] = demb;
     o.eemb_sorted[i] = emb;
     return;
@@ -268,16 +308,18 @@ k_brick(const __grid_constant__ GatherArgs a, const __grid_constant__ BrickPlan 
   constexpr bool kForce = tile_is_force(POT);
   constexpr bool kDensity = tile_is_density(POT);
   constexpr int kModel = tile_model(POT);
-  constexpr int NV = kDensity ? 1 : 3;
+  constexpr bool kFeHe = tile_is_fehe(POT);
+  constexpr int NV = kDensity ? (kFeHe ? 2 : 1) : 3;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int nthreads = blockDim.x;
   const Grid& g = a.grid;
 
   double* c64 = reinterpret_cast<double*>(smem_raw);  // x, y, z of staged atom s at c64[3 s ..]
   double* c64w = c64 + 3 * bp.cap_cand;               // EAM force pass: F'(rho_j)
+  double* c64w2 = c64 + 4 * bp.cap_cand;              // Fe-He force pass: F'(rho_j) of the s-band
   // FP16 offsets from the brick centre (x, y | z, 0): 8 bytes per candidate, two shared-memory
   // wavefronts per warp load where an FP32 record needs four (the search is bound by them)
-  uint2* c16 = reinterpret_cast<uint2*>(c64 + (kForce ? 4 : 3) * bp.cap_cand);
+  uint2* c16 = reinterpret_cast<uint2*>(c64 + tile_words(POT) * bp.cap_cand);
   unsigned short* cinfo = reinterpret_cast<unsigned short*>(c16 + bp.cap_cand);   // image code | species << 8
   unsigned short* lists = cinfo + bp.cap_cand;
 
@@ -488,6 +530,7 @@ k_brick(const __grid_constant__ GatherArgs a, const __grid_constant__ BrickPlan 
           c64[3 * s + 1] = p.y;
           c64[3 * s + 2] = p.z;
           if (kForce) c64w[s] = o.dfd_sorted[jb + s];
+          if (kForce && kFeHe) c64w2[s] = o.dfs_sorted[jb + s];
           const float fx = (float)(p.x + sx), fy = (float)(p.y + sy), fz = (float)(p.z + sz);
           const __half2 hxy = __floats2half2_rn(fx, fy), hz0 = __floats2half2_rn(fz, 0.0f);
           c16[s] = make_uint2(*reinterpret_cast<const unsigned*>(&hxy), *reinterpret_cast<const unsigned*>(&hz0));
@@ -504,7 +547,7 @@ k_brick(const __grid_constant__ GatherArgs a, const __grid_constant__ BrickPlan 
     const int natoms = bc_astart[nbc];
 
     const double rc2 = kPairGeo ? a.lj.rc2 : a.rc2;
-    const double rc2_phys = kPairGeo ? 0.0 : eam_par<kModel>().rc2_phys;
+    const double rc2_phys = (kPairGeo || kFeHe) ? 0.0 : eam_par<kModel>().rc2_phys;
     const int apb = nthreads / TPA;  // atoms per pass
     const int nrx = 2 * bp.ns[0] + 1, nry = 2 * bp.ns[1] + 1, nrows = nry * (2 * bp.ns[2] + 1);
     // private survivor list of this thread: entry k at shared byte address lsa0 + k * lstride
@@ -539,8 +582,9 @@ k_brick(const __grid_constant__ GatherArgs a, const __grid_constant__ BrickPlan 
           const __half thr = __float2half_ru(bp.thr2f);
           const double pix = c64[3 * si], piy = c64[3 * si + 1], piz = c64[3 * si + 2];
           const int zi = cinfo[si] >> 8;
-          double dfd_i = 0.0;
+          double dfd_i = 0.0, dfs_i = 0.0;
           if (kForce) dfd_i = c64w[si];
+          if (kForce && kFeHe) dfs_i = c64w2[si];
           int wi = 0;  // own wrap counts (rare): the image vector is then worked out pair by pair
           if (ASHIFT) wi = wrap_offset((unsigned long long)__double_as_longlong(a.spos[gi].w));
           const int hlow = hc - (bp.ns[2] * hd[1] + bp.ns[1]) * hd[0] - bp.ns[0];  // stencil corner
@@ -644,8 +688,8 @@ k_brick(const __grid_constant__ GatherArgs a, const __grid_constant__ BrickPlan 
                 }
               }
               const double d2 = xnorm2(dx, dy, dz);
-              brick_pair<POT>(a, rc2, rc2_phys, sj != si, zi, info >> 8, dfd_i, [&]() { return c64w[sj]; }, dx, dy,
-                              dz, d2, e_thr, acc, coincident);
+              brick_pair<POT>(a, rc2, rc2_phys, sj != si, zi, info >> 8, dfd_i, [&]() { return c64w[sj]; }, dfs_i,
+                              [&]() { return c64w2[sj]; }, dx, dy, dz, d2, e_thr, acc, coincident);
             }
             RB_TICK(3);
           } while (more);
@@ -683,7 +727,13 @@ k_brick(const __grid_constant__ GatherArgs a, const __grid_constant__ BrickPlan 
         if (active && sub == 0) {
           if (kDensity) {
             double emb, demb;
-            eam_embed<kModel>(cinfo[si] >> 8, acc[0], emb, demb);
+            if (kFeHe) {
+              double dems;
+              fehe_embed(cinfo[si] >> 8, acc[0], acc[1], emb, demb, dems);
+              o.dfs_sorted[gi] = dems;
+            } else {
+              eam_embed<kModel>(cinfo[si] >> 8, acc[0], emb, demb);
+            }
             o.dfd_sorted[gi] = demb;
             o.eemb_sorted[gi] = emb;
           } else {

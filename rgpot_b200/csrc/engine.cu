@@ -266,6 +266,7 @@ struct RgpotB200Pot {
   int opt_list = 0;
   int opt_slack = 0;  // percent of extra staged capacity over the mean halo population (0 = automatic)
   int opt_fine = 0;          // 1: never use half-cutoff cells
+  int opt_bricks = 1;         // 0: gather kernels only (test hook)
   int opt_handoff = 1;        // EAM brick kernels: the force pass reuses the density pass's survivor lists
   long opt_fine_min = 20000;  // atoms from which half-cutoff cells are used
   long launches = 0;
@@ -536,7 +537,7 @@ float brick_threshold(const Plan& pl, const int bd[3], const int ns[3], double r
   return (float)t;  // rounded up to FP16 in the kernel
 }
 
-bool plan_bricks(const RgpotB200Pot* pot, const Plan& pl, long n, double rc, bool eam, BrickPlan& bp) {
+bool plan_bricks(const RgpotB200Pot* pot, const Plan& pl, long n, double rc, int words, BrickPlan& bp) {
   const Grid& g = pl.grid;
   int ns[3];
   for (int k = 0; k < 3; ++k) {
@@ -590,7 +591,7 @@ bool plan_bricks(const RgpotB200Pot* pot, const Plan& pl, long n, double rc, boo
         if (known) bp.cap_cand = std::min(65504, round_up((int)(seen * 1.04) + 24, 32));
         const int want = (int)(nnb / tpa * 2.2) + 8, least = std::max(24, (int)(nnb / tpa) + 14);
         auto blocks_per_sm = [&](int cap_list) {
-          const size_t per_block = brick_smem_bytes(bp.cap_cand, cap_list, threads, eam) + 8192 + 1024;
+          const size_t per_block = brick_smem_bytes(bp.cap_cand, cap_list, threads, words) + 8192 + 1024;
           return (int)(pot->smem_per_sm / per_block);
         };
         bp.cap_list = least;
@@ -606,7 +607,7 @@ bool plan_bricks(const RgpotB200Pot* pot, const Plan& pl, long n, double rc, boo
             }
           }
         }
-        bp.smem = brick_smem_bytes(bp.cap_cand, bp.cap_list, threads, eam);
+        bp.smem = brick_smem_bytes(bp.cap_cand, bp.cap_list, threads, words);
       }
       if ((size_t)bp.smem + 10240 <= pot->smem_optin) {
         for (int k = 0; k < 3; ++k) {
@@ -644,7 +645,7 @@ bool plan_bricks(const RgpotB200Pot* pot, const Plan& pl, long n, double rc, boo
 template <int POT>
 int launch_brick(RgpotB200Pot* pot, const GatherArgs& ga, const BrickPlan& bp, const TileOut& to,
                  cudaStream_t st, const char* what) {
-  const unsigned smem = brick_smem_bytes(bp.cap_cand, bp.cap_list, bp.threads, tile_is_force(POT));
+  const unsigned smem = brick_smem_bytes(bp.cap_cand, bp.cap_list, bp.threads, tile_words(POT));
   auto go = [&](auto kern) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     kern<<<bp.nbricks, bp.threads, smem, st>>>(ga, bp, to);
@@ -681,6 +682,7 @@ int run_cell_path(RgpotB200Pot* pot, long n, const double* d_pos, const int* d_Z
   // nlist_rc > 0: a plain vesin-shaped neighbor list of that cutoff (every image, self images kept),
   // whatever potential the handle was created for (rgpot_b200_neighbor_list)
   const bool nlist = nlist_rc > 0.0 && emit != nullptr;
+  if (!pot->opt_bricks) allow_tile = false;
   const int kind = nlist ? RGPOT_B200_LJ : pot->cfg.kind;
   const bool eam = is_eam(kind);
   const bool al = kind == RGPOT_B200_EAM_AL;
@@ -852,22 +854,14 @@ int run_cell_path(RgpotB200Pot* pot, long n, const double* d_pos, const int* d_Z
   }
 
   double* d_part = pot->partials.as<double>();  // every atom's energy is written by exactly one kernel
-  if (fehe) {
-    // Fe-He: the three passes on the gather walk (rgpot_fehe.f90:573-620)
-    k_fehe_density<<<nblk, 128, 0, st>>>(ga, pot->dfd.as<double>(), pot->dfs.as<double>(), pot->eemb.as<double>());
-    LAUNCH_CHECK(pot, "k_fehe_density");
-    k_fehe_force<<<nblk, 128, 0, st>>>(ga, pot->dfd.as<double>(), pot->dfs.as<double>(), pot->eemb.as<double>(), d_F,
-                                       d_part);
-    LAUNCH_CHECK(pot, "k_fehe_force");
-    return reduce_energy(pot, d_part, (int)n, d_E, st);
-  }
-  if (eam) {
+  if (eam || fehe) {
     BrickPlan bp{};
-    const bool tile_ok = allow_tile && plan_bricks(pot, pl, n, rc, true, bp);
+    const bool tile_ok = allow_tile && plan_bricks(pot, pl, n, rc, fehe ? 5 : 4, bp);
     if (tile_ok) {
       // brick kernels; the gather kernels cover atoms outside the cell (per-pair image shifts) --
       // each side returns at once when the binning flag is not its own
-      TileOut to{d_F, d_part, pot->dfd.as<double>(), pot->eemb.as<double>(), d_st, nullptr, nullptr, 0};
+      TileOut to{d_F, d_part, pot->dfd.as<double>(), pot->eemb.as<double>(), fehe ? pot->dfs.as<double>() : nullptr,
+                 d_st, nullptr, nullptr, 0};
       if (pot->opt_handoff) {
         // survivor lists handed from the density to the force pass: room for every thread's list at
         // its capacity in half-filled warps (a shortfall only makes some threads search again)
@@ -882,15 +876,23 @@ int run_cell_path(RgpotB200Pot* pot, long n, const double* d_pos, const int* d_Z
           cudaGetLastError();
         }
       }
-      int ls = al ? launch_brick<TILE_AL_DENSITY>(pot, ga, bp, to, st, "k_brick<al density>")
-                  : launch_brick<TILE_EAM_DENSITY>(pot, ga, bp, to, st, "k_brick<eam density>");
+      int ls = fehe ? launch_brick<TILE_FEHE_DENSITY>(pot, ga, bp, to, st, "k_brick<fehe density>")
+               : al ? launch_brick<TILE_AL_DENSITY>(pot, ga, bp, to, st, "k_brick<al density>")
+                    : launch_brick<TILE_EAM_DENSITY>(pot, ga, bp, to, st, "k_brick<eam density>");
       if (ls) return ls;
-      ls = al ? launch_brick<TILE_AL_FORCE>(pot, ga, bp, to, st, "k_brick<al force>")
-              : launch_brick<TILE_EAM_FORCE>(pot, ga, bp, to, st, "k_brick<eam force>");
+      ls = fehe ? launch_brick<TILE_FEHE_FORCE>(pot, ga, bp, to, st, "k_brick<fehe force>")
+           : al ? launch_brick<TILE_AL_FORCE>(pot, ga, bp, to, st, "k_brick<al force>")
+                : launch_brick<TILE_EAM_FORCE>(pot, ga, bp, to, st, "k_brick<eam force>");
       if (ls) return ls;
       ga.only_if_big_shift = 1;
     }
-    if (al) {
+    if (fehe) {
+      // Fe-He on the gather walk (rgpot_fehe.f90:573-620): the general path
+      k_fehe_density<<<nblk, 128, 0, st>>>(ga, pot->dfd.as<double>(), pot->dfs.as<double>(), pot->eemb.as<double>());
+      LAUNCH_CHECK(pot, "k_fehe_density");
+      k_fehe_force<<<nblk, 128, 0, st>>>(ga, pot->dfd.as<double>(), pot->dfs.as<double>(), pot->eemb.as<double>(), d_F,
+                                         d_part);
+    } else if (al) {
       k_eam_density<EAM_AL><<<nblk, 128, 0, st>>>(ga, pot->dfd.as<double>(), pot->eemb.as<double>(), d_st);
       LAUNCH_CHECK(pot, "k_eam_density");
       k_eam_force<EAM_AL><<<nblk, 128, 0, st>>>(ga, pot->dfd.as<double>(), pot->eemb.as<double>(), d_F, d_part);
@@ -904,10 +906,10 @@ int run_cell_path(RgpotB200Pot* pot, long n, const double* d_pos, const int* d_Z
   } else if (pl.geo == GEO_IMAGES) {
     k_lj_gather<GEO_IMAGES><<<nblk, 128, 0, st>>>(ga, d_F, d_part);
     LAUNCH_CHECK(pot, "k_lj_gather<images>");
-  } else if (BrickPlan bp{}; pl.geo == GEO_LJ_SHIFT && allow_tile && plan_bricks(pot, pl, n, rc, false, bp)) {
+  } else if (BrickPlan bp{}; pl.geo == GEO_LJ_SHIFT && allow_tile && plan_bricks(pot, pl, n, rc, 3, bp)) {
     // brick kernel; the literal-fold gather kernel covers the (rare) case of atoms outside the
     // cell -- each of the two returns at once when the binning flag is not its own
-    TileOut to{d_F, d_part, nullptr, nullptr, d_st, nullptr, nullptr, 0};
+    TileOut to{d_F, d_part, nullptr, nullptr, nullptr, d_st, nullptr, nullptr, 0};
     int ls = pl.lj.morse ? launch_brick<TILE_PAIR>(pot, ga, bp, to, st, "k_brick<pair>")
                          : launch_brick<TILE_LJ>(pot, ga, bp, to, st, "k_brick<lj>");
     if (ls) return ls;
@@ -1372,6 +1374,10 @@ int rgpot_b200_set_option(RgpotB200Pot* pot, const char* key, long value) {
   }
   if (strcmp(key, "fine_min") == 0) {
     pot->opt_fine_min = value;
+    return 0;
+  }
+  if (strcmp(key, "bricks") == 0) {
+    pot->opt_bricks = (int)value;
     return 0;
   }
   if (strcmp(key, "handoff") == 0) {

@@ -253,6 +253,7 @@ k_eam_force(GatherArgs a, const double* __restrict__ dfd_sorted,
 __global__ void __launch_bounds__(128)
 k_fehe_density(GatherArgs a, double* __restrict__ dfd_sorted, double* __restrict__ dfs_sorted,
                double* __restrict__ eemb_sorted) {
+  if (a.only_if_big_shift && !(a.st_in->flags & kFlagBigShift)) return;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= a.n) return;
   const double4 pi = a.spos[i];
@@ -275,6 +276,7 @@ k_fehe_density(GatherArgs a, double* __restrict__ dfd_sorted, double* __restrict
 __global__ void __launch_bounds__(128)
 k_fehe_force(GatherArgs a, const double* __restrict__ dfd_sorted, const double* __restrict__ dfs_sorted,
              const double* __restrict__ eemb_sorted, double* __restrict__ F, double* __restrict__ eatom) {
+  if (a.only_if_big_shift && !(a.st_in->flags & kFlagBigShift)) return;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   double e = 0.0, fx = 0.0, fy = 0.0, fz = 0.0;
   if (i < a.n) {

@@ -801,6 +801,33 @@ def test_fehe_vs_oracle(oracle, n_side, n_he, triclinic):
     assert_forces(f2, f2_o)
 
 
+@pytest.mark.parametrize("triclinic", [False, True])
+def test_fehe_brick_kernels_large(oracle, triclinic):
+    """21 296 atoms, 1 % helium: half-cutoff cells and the brick kernels (two density channels staged
+    with the halo), against the oracle and against the gather kernels; a tenth of the atoms outside
+    the cell."""
+    n_side = 22
+    box = None
+    if triclinic:
+        a = 2.8553 * n_side
+        box = np.array([[a, 0.0, 0.0], [0.2 * a, a, 0.0], [0.1 * a, -0.15 * a, a]])
+    pos, Z, H = _fehe_cell(n_side, 213, 7, box=box)
+    assert len(pos) > 20000
+    frac = pos @ np.linalg.inv(H)
+    pos = (frac - np.floor(frac)) @ H  # wrapped, then a tenth of the atoms one cell vector outside
+    pos = _scatter_outside(pos, H, np.random.default_rng(8))
+    pot = rgpot_b200.FeHePot()
+    e, f, _ = pot(pos, Z, H)
+    assert pot.stat("max_halo") > 0 and pot.stat("pool_used") > 0  # bricks ran, lists were handed on
+    e_o, f_o = oracle.fehe_force(pos, Z, H)
+    assert_energy(e, e_o)
+    assert_forces(f, f_o)
+    pot.set_option("bricks", 0)
+    e_g, f_g, _ = pot(pos, Z, H)
+    assert_energy(e, e_g)
+    assert_forces(f, f_g)
+
+
 def test_fehe_errors_and_batch(oracle):
     pot = rgpot_b200.FeHePot()
     pos, Z, H = _fehe_cell(3, 4, 7)
@@ -949,7 +976,7 @@ def test_brick_atoms_outside_the_cell_lj(oracle, far):
     e_o, f_o, _ = oracle.lj_force(out, box, 1.0, 2.5, 1.0)
     assert_energy(e, e_o)
     assert_forces(f, f_o)
-    pot.set_path(1)  # gather kernels, literal fold
+    pot.set_option("bricks", 0)  # gather kernels, literal fold
     e_g, f_g, _ = pot(out, Z, box)
     assert_energy(e, e_g)
     assert_forces(f, f_g)
@@ -967,7 +994,7 @@ def test_brick_atoms_outside_the_cell_cuh2(oracle, far):
     e_o, f_o = oracle.cuh2_force(out, Z, box)
     assert_energy(e, e_o)
     assert_forces(f, f_o)
-    pot.set_path(1)  # gather kernels (vesin's per-pair shift form)
+    pot.set_option("bricks", 0)  # gather kernels (vesin's per-pair shift form)
     e_g, f_g, _ = pot(out, Z, box)
     assert_energy(e, e_g)
     assert_forces(f, f_g)

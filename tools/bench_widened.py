@@ -108,10 +108,10 @@ def main():
     ms, e = timed(rgpot_b200.EAMAlPot(), pos, np.full(len(pos), 13), box)
     out.append({"workload": "eam_al_fcc_256k", "kernel": "k_brick<AL_DENSITY> + k_brick<AL_FORCE>",
                 "n_atoms": len(pos), "ms_per_step": ms, "value": len(pos) / ms * 1e3, "energy": e})
-    # FeHe: bcc iron 40^3 cells with 1 % substitutional helium, gather kernels
+    # FeHe: bcc iron 40^3 cells with 1 % substitutional helium
     pos, Z, box = bcc_fehe(40, 0.01, 4)
     ms, e = timed(rgpot_b200.FeHePot(), pos, Z, box)
-    out.append({"workload": "fehe_bcc_128k", "kernel": "k_fehe_density + k_fehe_force (gather)", "n_atoms": len(pos),
+    out.append({"workload": "fehe_bcc_128k", "kernel": "k_brick<FEHE_DENSITY> + k_brick<FEHE_FORCE>", "n_atoms": len(pos),
                 "ms_per_step": ms, "value": len(pos) / ms * 1e3, "energy": e})
     # neighbor list: the Cu slab, 6.1 A, full list, unsorted (host-buffer call: two passes + D2H of the list)
     pos, Zs, box = workloads.cu_slab_triclinic(cells=20)
