@@ -21,11 +21,13 @@
 //           the sums have a fixed order (stencil order, then a fixed shuffle tree over the kTPA
 //           threads): bit-reproducible, no atomics.
 //
-// The kernels are valid for the fast geometry only (no atom outside the cell; LJ: every periodic
-// direction >= 2 ns + 1 cells); they return immediately when the binning flags say otherwise and
-// the gather kernels of gather.cuh take over.  A brick whose halo does not fit the staged capacity,
-// or an atom whose survivors overflow its list, is evaluated by the same block with the per-atom
-// gather walk -- slower, same results, no host round trip.
+// Geometry: atoms up to one cell vector outside the cell are taken (wrap counts folded into the
+// image codes); the kernels return at once when the binning flags report an atom further out and
+// the gather kernels of gather.cuh take over.  A brick whose halo does not fit the staged capacity is
+// cut in two; a single cell that still does not fit is walked straight from global memory by the
+// same block (brick_slow_atom: same candidate order, same pair terms, same summation tree, hence
+// the same bits); a full private list only means another search / physics round.  The EAM density
+// pass hands its lists to the force pass through a global pool, so the search runs once.
 #pragma once
 
 #include <cuda_fp16.h>

@@ -562,13 +562,12 @@ bool plan_bricks(const RgpotB200Pot* pot, const Plan& pl, long n, double rc, int
   const double nnb = mean / cellvol * (4.0 / 3.0) * M_PI * rc * rc * rc + 1.0;
   int tpa = pot->opt_tpa ? pot->opt_tpa : (nnb > 64.0 ? 4 : 2);  // long lists: more threads per atom
   if (tpa != 1 && tpa != 2 && tpa != 4) tpa = 2;
-  const double slots = (double)kBrickMaxThreads / tpa;
   int bd[3] = {1, 1, 1};
   if (pot->opt_brick[0] > 0) {
     for (int k = 0; k < 3; ++k) bd[k] = std::max(1, std::min({pot->opt_brick[k], g.nc[k], 4}));
   } else {
     // the largest brick (up to 4 cells a side) shared memory allows: staging and table work per
-    // atom shrink with the brick; a brick with more atoms than slots takes several passes
+    // atom shrink with the brick; a brick with more atoms than threads / tpa takes several passes
     for (int k = 0; k < 3; ++k) bd[k] = g.nc[k] >= 4 ? 4 : (g.nc[k] >= 2 ? 2 : 1);
   }
   for (;;) {
@@ -578,7 +577,6 @@ bool plan_bricks(const RgpotB200Pot* pot, const Plan& pl, long n, double rc, int
       const double pop = mean * ncell;
       int threads = pot->opt_threads ? pot->opt_threads : round_up((int)ceil(pop * 1.15 * tpa), 32);
       threads = std::max(64, std::min(kBrickMaxThreads, round_up(threads, 32)));
-      (void)slots;
       // capacities: the staged halo from the mean density (or from what the last call with this
       // signature met); the private lists as long as they can be without costing a resident block
       // (a full list only means one more search / physics round, a full halo a cut brick)
@@ -1492,13 +1490,6 @@ static int finish_single(RgpotB200Pot* pot, long n, const double* d_pos, const i
     Status stt{};
     CU_TRY(pot, cudaMemcpyAsync(&stt, pot->status.p, sizeof stt, cudaMemcpyDeviceToHost, st));
     CU_TRY(pot, cudaStreamSynchronize(st));
-    if (stt.flags & kFlagListOverflow) {
-      // a tile kernel ran out of piece slots (very sparse survivors): redo on the gather kernels
-      int s = run_cell_path(pot, n, d_pos, d_Z, d_F, d_E, box, st, nullptr, false);
-      if (s) return s;
-      CU_TRY(pot, cudaMemcpyAsync(&stt, pot->status.p, sizeof stt, cudaMemcpyDeviceToHost, st));
-      CU_TRY(pot, cudaStreamSynchronize(st));
-    }
     flags = stt.flags;
     pot->slow_atoms = stt.slow_atoms;
     pot->pool_used = (long)stt.pool_used;
