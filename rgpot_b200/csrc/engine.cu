@@ -2054,8 +2054,8 @@ static int cache_keys_enqueue(RgpotB200Pot* pot, size_t nSystems, const size_t* 
   const uint64_t tail = rb::xxh3_host(reinterpret_cast<const unsigned char*>(&pot_type), 8) ^
                         rb::xxh3_host(reinterpret_cast<const unsigned char*>(&params_key), 8);
   rb::KeyArgs ka{pot->b_off.as<size_t>(), d_pos, d_Z, d_boxes, tail, d_keys, nSystems};
-  const int warps = 8;
-  k_cache_keys<<<(unsigned)((nSystems + warps - 1) / warps), 32 * warps, 0, st>>>(ka);
+  const int warps = 8, per_block = 4 * warps;  // eight lanes per system
+  k_cache_keys<<<(unsigned)((nSystems + per_block - 1) / per_block), 32 * warps, 0, st>>>(ka);
   LAUNCH_CHECK(pot, "k_cache_keys");
   return 0;
 }

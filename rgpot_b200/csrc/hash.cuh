@@ -5,9 +5,9 @@
 // as keys made by the reference on the CPU, so `forceBatch`'s hit / miss compaction
 // (Potential.hpp:251-306) can hash a whole batch in one launch from device-resident inputs.
 //
-// One warp per system: lanes 0-7 are the eight accumulators of the long-input loop over the
-// positions, lanes 8-15 the same over the atomic numbers, lane 16 hashes the box; inputs of at most
-// 240 bytes take the short forms on the first lane of their group.
+// Eight lanes per system (four systems per warp): the lanes are the eight accumulators of the
+// long-input loop, first over the positions, then over the atomic numbers; the first lane hashes
+// the box; inputs of at most 240 bytes take the short forms on the first lane of the group.
 #pragma once
 #include <cstddef>
 #include <cstdint>
@@ -161,7 +161,6 @@ __device__ inline uint64_t xxh3_long_group(const unsigned char* in, size_t len, 
     const uint64_t k = v ^ key;
     acc += other + (k & 0xffffffffull) * (k >> 32);
   };
-  auto stripe = [&](const unsigned char* p, uint64_t key) { absorb(in64(p + 8 * l), key); };
   const bool aligned8 = (reinterpret_cast<uintptr_t>(in) & 7) == 0;
   const size_t block = 64 * 16, nblocks = (len - 1) / block;
   const uint64_t scramble_key = sw[16 + l];
@@ -181,8 +180,18 @@ __device__ inline uint64_t xxh3_long_group(const unsigned char* in, size_t len, 
     acc = ((acc ^ (acc >> 47)) ^ scramble_key) * kP32_1;
   }
   const int nstripes = (int)(((len - 1) - block * nblocks) / 64);
-  for (int t = 0; t < nstripes; ++t) stripe(in + nblocks * block + 64 * t, sw[t + l]);
-  stripe(in + len - 64, rd64(s + 192 - 64 - 7 + 8 * l));
+  {
+    // the partial block (up to 15 stripes) and the last stripe: loads first, as above
+    uint64_t v[16];
+    const unsigned char* p = in + nblocks * block + 8 * l;
+#pragma unroll
+    for (int t = 0; t < 15; ++t) v[t] = t < nstripes ? in64(p + 64 * t) : 0ull;
+    v[15] = in64(in + len - 64 + 8 * l);
+#pragma unroll
+    for (int t = 0; t < 15; ++t)
+      if (t < nstripes) absorb(v[t], sw[t + l]);  // (uniform over the eight lanes of the group)
+    absorb(v[15], rd64(s + 192 - 64 - 7 + 8 * l));
+  }
   // merge: pairs of accumulators, then the sum over the four pairs in order
   const uint64_t keyed = acc ^ rd64(s + 11 + 8 * l);
   const uint64_t partner = __shfl_xor_sync(mask, keyed, 1);
@@ -203,35 +212,33 @@ struct KeyArgs {
   size_t nsys;
 };
 
-__global__ void __launch_bounds__(256) k_cache_keys(const KeyArgs a) {
+__global__ void __launch_bounds__(256, 4) k_cache_keys(const KeyArgs a) {
   __shared__ uint64_t sw[24];
   if (threadIdx.x < 24) sw[threadIdx.x] = rd64(c_xxh_secret + 8 * threadIdx.x);
   __syncthreads();
-  const size_t sys = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (sys >= a.nsys) return;  // whole warps leave together
-  const int lane = threadIdx.x & 31;
+  // four systems per warp, eight lanes each (the eight accumulators of the long form)
+  const int lane = threadIdx.x & 31, grp = lane >> 3, l = lane & 7;
+  const size_t sys = ((size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 4 + grp;
+  if (sys >= a.nsys) return;  // whole groups leave together
+  const unsigned mask = 0xffu << (8 * grp);
   const size_t o = a.offsets[sys], n = a.offsets[sys + 1] - o;
   const unsigned char* pp = reinterpret_cast<const unsigned char*>(a.pos + 3 * o);
   const unsigned char* zp = reinterpret_cast<const unsigned char*>(a.Z + o);
   const size_t plen = 24 * n, zlen = 4 * n;
-  uint64_t h = 0;
-  // the branch conditions are warp-uniform except for the lane ranges, which are fixed
-  if (lane < 8) {
-    if (plen > 240)
-      h = xxh3_long_group(pp, plen, lane, 0, 0x000000ffu, sw);
-    else if (lane == 0)
-      h = xxh3_short(pp, plen);
-  } else if (lane < 16) {
-    if (zlen > 240)
-      h = xxh3_long_group(zp, zlen, lane - 8, 8, 0x0000ff00u, sw);
-    else if (lane == 8)
-      h = xxh3_short(zp, zlen);
-  } else if (lane == 16) {
-    h = xxh3_short(reinterpret_cast<const unsigned char*>(a.boxes + 9 * sys), 72);
+  // the branch conditions are uniform over a group
+  uint64_t hp = 0, hz = 0;
+  if (plen > 240)
+    hp = xxh3_long_group(pp, plen, l, 8 * grp, mask, sw);
+  else if (l == 0)
+    hp = xxh3_short(pp, plen);
+  if (zlen > 240)
+    hz = xxh3_long_group(zp, zlen, l, 8 * grp, mask, sw);
+  else if (l == 0)
+    hz = xxh3_short(zp, zlen);
+  if (l == 0) {
+    const uint64_t hb = xxh3_short(reinterpret_cast<const unsigned char*>(a.boxes + 9 * sys), 72);
+    a.keys[sys] = hp ^ hz ^ hb ^ a.tail;
   }
-  const uint64_t hp = __shfl_sync(0xffffffffu, h, 0), hz = __shfl_sync(0xffffffffu, h, 8),
-                 hb = __shfl_sync(0xffffffffu, h, 16);
-  if (lane == 0) a.keys[sys] = hp ^ hz ^ hb ^ a.tail;
 }
 
 }  // namespace rb
