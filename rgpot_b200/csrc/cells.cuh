@@ -310,9 +310,13 @@ __global__ void k_reduce_partials(const double* __restrict__ partials, int n, do
   if (threadIdx.x == 0) out[0] = sh[0];
 }
 
-// first stage for long partial arrays: block b folds the fixed slice [b * per, (b + 1) * per)
-__global__ void k_reduce_slices(const double* __restrict__ partials, int n, int per, double* __restrict__ out) {
+// long arrays, one launch: block b folds the fixed slice [b * per, (b + 1) * per); the block that
+// finishes last (a ticket in the status word) folds the slice sums the way k_reduce_partials would
+// with 128 threads -- the order of every addition is a function of n alone
+__global__ void k_reduce_slices(const double* __restrict__ partials, int n, int per, double* __restrict__ slice_sums,
+                                Status* __restrict__ st, double* __restrict__ out) {
   __shared__ double sh[256];
+  __shared__ int last;
   const int lo = blockIdx.x * per, hi = min(n, lo + per);
   double acc = 0.0;
   for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) acc += partials[i];
@@ -322,7 +326,28 @@ __global__ void k_reduce_slices(const double* __restrict__ partials, int n, int 
     if (threadIdx.x < off) sh[threadIdx.x] += sh[threadIdx.x + off];
     __syncthreads();
   }
-  if (threadIdx.x == 0) out[blockIdx.x] = sh[0];
+  if (threadIdx.x == 0) {
+    slice_sums[blockIdx.x] = sh[0];
+    __threadfence();
+    last = atomicAdd(&st->ticket, 1) == (int)gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  const int nb = gridDim.x;
+  acc = 0.0;
+  if (threadIdx.x < 128)
+    for (int i = threadIdx.x; i < nb; i += 128) acc += __ldcg(slice_sums + i);
+  sh[threadIdx.x] = threadIdx.x < 128 ? acc : 0.0;
+  __syncthreads();
+  for (int off = 64; off > 0; off >>= 1) {
+    if (threadIdx.x < off) sh[threadIdx.x] += sh[threadIdx.x + off];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    out[0] = sh[0];
+    st->ticket = 0;  // the ticket serves the next fold of this call (density / force passes share the status)
+  }
 }
 
 // fixed-order block sum helper used by the force kernels (blockDim multiple of 32, <= 1024)

@@ -33,7 +33,7 @@ struct Status {
   int bad_value;       // its atomic number (ForeignZ)
   int slow_atoms;      // diagnostics: atoms a brick kernel evaluated on its slow path
   int max_halo;        // feedback: largest halo population a brick kernel met (sizes the next call)
-  int pad;
+  int ticket;          // k_reduce_slices: blocks that have delivered their slice sum
   unsigned long long pool_used;  // survivor-list pool of the EAM brick kernels: entries handed out
   unsigned long long prof[4];  // -DRB_BRICK_TIMING builds: warp-clock sums of setup / stage / search / physics
 };

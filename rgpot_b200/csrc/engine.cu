@@ -662,9 +662,9 @@ int reduce_energy(RgpotB200Pot* pot, double* d_part, int n, double* d_E, cudaStr
   if (n > 4096) {
     const int nb = n < 262144 ? 128 : 1024, per = (n + nb - 1) / nb;  // (a function of n only: one fixed order)
     CU_TRY(pot, pot->partials2.reserve(sizeof(double) * nb));
-    k_reduce_slices<<<nb, 256, 0, st>>>(d_part, n, per, pot->partials2.as<double>());
+    k_reduce_slices<<<nb, 256, 0, st>>>(d_part, n, per, pot->partials2.as<double>(), pot->status.as<Status>(), d_E);
     LAUNCH_CHECK(pot, "k_reduce_slices");
-    k_reduce_partials<<<1, 128, 0, st>>>(pot->partials2.as<double>(), nb, d_E);  // blockDim need not cover nb
+    return 0;
   } else {
     k_reduce_partials<<<1, 1024, 0, st>>>(d_part, n, d_E);
   }
@@ -798,7 +798,10 @@ int run_cell_path(RgpotB200Pot* pot, long n, const double* d_pos, const int* d_Z
   CU_TRY(pot, pot->order.reserve(sizeof(int) * n));
   CU_TRY(pot, pot->spos.reserve(sizeof(double4) * n));
   CU_TRY(pot, pot->scell.reserve(sizeof(int) * n));
-  const int nblk = div_up(n, 128);
+  int nblk = div_up(n, 128);
+  // the gather kernels as a stand-by behind the brick kernels (they return at once unless an atom lies
+  // far outside the cell): a few blocks per SM, grid-stride
+  const int nblk_standby = std::min(nblk, 8 * pot->sm_count);
   CU_TRY(pot, pot->partials.reserve(sizeof(double) * n));  // per-atom energies, sorted order
   if (eam || fehe) {
     CU_TRY(pot, pot->dfd.reserve(sizeof(double) * n));
@@ -883,6 +886,7 @@ int run_cell_path(RgpotB200Pot* pot, long n, const double* d_pos, const int* d_Z
                 : launch_brick<TILE_EAM_FORCE>(pot, ga, bp, to, st, "k_brick<eam force>");
       if (ls) return ls;
       ga.only_if_big_shift = 1;
+      nblk = nblk_standby;
     }
     if (fehe) {
       // Fe-He on the gather walk (rgpot_fehe.f90:573-620): the general path
@@ -912,7 +916,7 @@ int run_cell_path(RgpotB200Pot* pot, long n, const double* d_pos, const int* d_Z
                          : launch_brick<TILE_LJ>(pot, ga, bp, to, st, "k_brick<lj>");
     if (ls) return ls;
     ga.only_if_big_shift = 1;
-    k_lj_gather<GEO_LJ_SHIFT><<<nblk, 128, 0, st>>>(ga, d_F, d_part);
+    k_lj_gather<GEO_LJ_SHIFT><<<nblk_standby, 128, 0, st>>>(ga, d_F, d_part);
     LAUNCH_CHECK(pot, "k_lj_gather<shift>");
     return reduce_energy(pot, d_part, (int)n, d_E, st);
   } else if (pl.geo == GEO_LJ_SHIFT) {

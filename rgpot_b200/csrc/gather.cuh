@@ -172,9 +172,9 @@ template <int GEO>
 __global__ void __launch_bounds__(128)
 k_lj_gather(GatherArgs a, double* __restrict__ F, double* __restrict__ eatom) {
   if (a.only_if_big_shift && !(a.st_in->flags & kFlagBigShift)) return;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  double e = 0.0, fx = 0.0, fy = 0.0, fz = 0.0;
-  if (i < a.n) {
+  // grid-stride: as a stand-by behind the brick kernels the launch is a few blocks per SM
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += gridDim.x * blockDim.x) {
+    double e = 0.0, fx = 0.0, fy = 0.0, fz = 0.0;
     const double4 pi = a.spos[i];
     const int ti = meta_species((unsigned long long)__double_as_longlong(pi.w));
     auto body = [&](int, unsigned long long mj, double dx, double dy, double dz, double d2, int, int,
@@ -197,23 +197,23 @@ k_eam_density(GatherArgs a, double* __restrict__ dfd_sorted, double* __restrict_
               Status* __restrict__ st) {
   if (a.only_if_big_shift && !(a.st_in->flags & kFlagBigShift)) return;
   exp_table_init();
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= a.n) return;
-  const double4 pi = a.spos[i];
   const double rc2_phys = eam_par<M>().rc2_phys;
-  double rho = 0.0;
-  bool coincident = false;
-  auto body = [&](int, unsigned long long mj, double, double, double, double d2, int, int, int) {
-    if (d2 == 0.0) coincident = true;  // dist <= 0 guard, rgpot_cuh2.f90:422-428
-    if (!(d2 < rc2_phys)) return;      // :522 -- sqrt(d2) can round up onto the cutoff
-    rho += eam_density_entry<M>(meta_species(mj), d2);
-  };
-  walk_dispatch<GEO_IMAGES>(a, i, pi, body);
-  if (coincident) atomicOr(&st->flags, kFlagCoincident);
-  double emb, demb;
-  eam_embed<M>(meta_species((unsigned long long)__double_as_longlong(pi.w)), rho, emb, demb);
-  dfd_sorted[i] = demb;
-  eemb_sorted[i] = emb;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += gridDim.x * blockDim.x) {
+    const double4 pi = a.spos[i];
+    double rho = 0.0;
+    bool coincident = false;
+    auto body = [&](int, unsigned long long mj, double, double, double, double d2, int, int, int) {
+      if (d2 == 0.0) coincident = true;  // dist <= 0 guard, rgpot_cuh2.f90:422-428
+      if (!(d2 < rc2_phys)) return;      // :522 -- sqrt(d2) can round up onto the cutoff
+      rho += eam_density_entry<M>(meta_species(mj), d2);
+    };
+    walk_dispatch<GEO_IMAGES>(a, i, pi, body);
+    if (coincident) atomicOr(&st->flags, kFlagCoincident);
+    double emb, demb;
+    eam_embed<M>(meta_species((unsigned long long)__double_as_longlong(pi.w)), rho, emb, demb);
+    dfd_sorted[i] = demb;
+    eemb_sorted[i] = emb;
+  }
 }
 
 // ---- CuH2 pass 3: pair energy + whole force on each atom (rgpot_cuh2.f90:454-457) -----------
@@ -224,14 +224,13 @@ k_eam_force(GatherArgs a, const double* __restrict__ dfd_sorted,
             double* __restrict__ eatom) {
   if (a.only_if_big_shift && !(a.st_in->flags & kFlagBigShift)) return;
   exp_table_init();
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  double e = 0.0, fx = 0.0, fy = 0.0, fz = 0.0;
-  if (i < a.n) {
+  const double rc2_phys = eam_par<M>().rc2_phys;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += gridDim.x * blockDim.x) {
+    double e = 0.0, fx = 0.0, fy = 0.0, fz = 0.0;
     const double4 pi = a.spos[i];
     const unsigned long long mi = (unsigned long long)__double_as_longlong(pi.w);
     const int zi = meta_species(mi);
     const double dfd_i = dfd_sorted[i];
-    const double rc2_phys = eam_par<M>().rc2_phys;
     auto body = [&](int j, unsigned long long mj, double dx, double dy, double dz, double d2, int,
                     int, int) {
       if (!(d2 < rc2_phys)) return;
@@ -254,32 +253,31 @@ __global__ void __launch_bounds__(128)
 k_fehe_density(GatherArgs a, double* __restrict__ dfd_sorted, double* __restrict__ dfs_sorted,
                double* __restrict__ eemb_sorted) {
   if (a.only_if_big_shift && !(a.st_in->flags & kFlagBigShift)) return;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= a.n) return;
-  const double4 pi = a.spos[i];
-  const int zi = meta_species((unsigned long long)__double_as_longlong(pi.w));
-  double rho_d = 0.0, rho_s = 0.0;
-  auto body = [&](int, unsigned long long mj, double, double, double, double d2, int, int, int) {
-    double rho, drho;
-    const int ch = fehe_density(zi, meta_species(mj), sqrt(d2), rho, drho);  // atom_densities :480-500
-    if (ch == 0) rho_d += rho;
-    if (ch == 1) rho_s += rho;
-  };
-  walk_dispatch<GEO_IMAGES>(a, i, pi, body);
-  double e, dfd, dfs;
-  fehe_embed(zi, rho_d, rho_s, e, dfd, dfs);
-  dfd_sorted[i] = dfd;
-  dfs_sorted[i] = dfs;
-  eemb_sorted[i] = e;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += gridDim.x * blockDim.x) {
+    const double4 pi = a.spos[i];
+    const int zi = meta_species((unsigned long long)__double_as_longlong(pi.w));
+    double rho_d = 0.0, rho_s = 0.0;
+    auto body = [&](int, unsigned long long mj, double, double, double, double d2, int, int, int) {
+      double rho, drho;
+      const int ch = fehe_density(zi, meta_species(mj), sqrt(d2), rho, drho);  // atom_densities :480-500
+      if (ch == 0) rho_d += rho;
+      if (ch == 1) rho_s += rho;
+    };
+    walk_dispatch<GEO_IMAGES>(a, i, pi, body);
+    double e, dfd, dfs;
+    fehe_embed(zi, rho_d, rho_s, e, dfd, dfs);
+    dfd_sorted[i] = dfd;
+    dfs_sorted[i] = dfs;
+    eemb_sorted[i] = e;
+  }
 }
 
 __global__ void __launch_bounds__(128)
 k_fehe_force(GatherArgs a, const double* __restrict__ dfd_sorted, const double* __restrict__ dfs_sorted,
              const double* __restrict__ eemb_sorted, double* __restrict__ F, double* __restrict__ eatom) {
   if (a.only_if_big_shift && !(a.st_in->flags & kFlagBigShift)) return;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  double e = 0.0, fx = 0.0, fy = 0.0, fz = 0.0;
-  if (i < a.n) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += gridDim.x * blockDim.x) {
+    double e = 0.0, fx = 0.0, fy = 0.0, fz = 0.0;
     const double4 pi = a.spos[i];
     const unsigned long long mi = (unsigned long long)__double_as_longlong(pi.w);
     const int zi = meta_species(mi);
