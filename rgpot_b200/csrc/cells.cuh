@@ -132,35 +132,26 @@ __global__ void k_scan_partial(const int* __restrict__ counts, int n, int* __res
   }
 }
 
-// single block: exclusive scan of the block sums in place (serial over chunks of 1024)
-__global__ void k_scan_blocks(int* __restrict__ block_sums, int nblocks) {
-  __shared__ int sh[kScanBlock];
-  __shared__ int carry;
-  if (threadIdx.x == 0) carry = 0;
-  __syncthreads();
-  for (int base = 0; base < nblocks; base += kScanBlock) {
-    const int idx = base + threadIdx.x;
-    const int v = idx < nblocks ? block_sums[idx] : 0;
-    sh[threadIdx.x] = v;
-    __syncthreads();
-    for (int off = 1; off < kScanBlock; off <<= 1) {
-      const int add = threadIdx.x >= off ? sh[threadIdx.x - off] : 0;
-      __syncthreads();
-      sh[threadIdx.x] += add;
-      __syncthreads();
-    }
-    const int incl = sh[threadIdx.x];
-    if (idx < nblocks) block_sums[idx] = carry + incl - v;
-    __syncthreads();
-    if (threadIdx.x == kScanBlock - 1) carry += incl;
-    __syncthreads();
-  }
-}
-
-// starts[c] = exclusive prefix of counts; starts[n] = total
-__global__ void k_scan_final(const int* __restrict__ counts, int n, const int* __restrict__ block_offs,
+// starts[c] = exclusive prefix of counts; starts[n] = total.  Every block adds up the sums of the
+// blocks before it on its own (a few hundred integers at most) instead of waiting for a scan launch.
+__global__ void k_scan_final(const int* __restrict__ counts, int n, const int* __restrict__ block_sums,
                              int* __restrict__ starts) {
   __shared__ int sh[kScanBlock];
+  __shared__ int wsum[32];
+  __shared__ int block_off;
+  {
+    int part = 0;
+    for (int j = threadIdx.x; j < (int)blockIdx.x; j += kScanBlock) part += block_sums[j];
+    for (int off = 16; off > 0; off >>= 1) part += __shfl_down_sync(0xffffffffu, part, off);
+    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = part;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      int w = wsum[threadIdx.x];
+      for (int off = 16; off > 0; off >>= 1) w += __shfl_down_sync(0xffffffffu, w, off);
+      if (threadIdx.x == 0) block_off = w;
+    }
+    __syncthreads();
+  }
   const int base = blockIdx.x * kScanBlock * kScanItems;
   int v[kScanItems];
   int sum = 0;
@@ -177,7 +168,7 @@ __global__ void k_scan_final(const int* __restrict__ counts, int n, const int* _
     sh[threadIdx.x] += add;
     __syncthreads();
   }
-  int run = block_offs[blockIdx.x] + sh[threadIdx.x] - sum;
+  int run = block_off + sh[threadIdx.x] - sum;
   for (int t = 0; t < kScanItems; ++t) {
     const int idx = base + threadIdx.x * kScanItems + t;
     if (idx < n) starts[idx] = run;

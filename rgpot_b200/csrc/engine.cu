@@ -817,8 +817,6 @@ int run_cell_path(RgpotB200Pot* pot, long n, const double* d_pos, const int* d_Z
   LAUNCH_CHECK(pot, "k_bin");
   k_scan_partial<<<nscan, kScanBlock, 0, st>>>(pot->counts.as<int>(), ncells, pot->blocksums.as<int>());
   LAUNCH_CHECK(pot, "k_scan_partial");
-  k_scan_blocks<<<1, kScanBlock, 0, st>>>(pot->blocksums.as<int>(), nscan);
-  LAUNCH_CHECK(pot, "k_scan_blocks");
   k_scan_final<<<nscan, kScanBlock, 0, st>>>(pot->counts.as<int>(), ncells, pot->blocksums.as<int>(),
                                              pot->starts.as<int>());
   LAUNCH_CHECK(pot, "k_scan_final");
