@@ -185,6 +185,11 @@ RGPOT_B200_API int rgpot_b200_cache_keys_device(RgpotB200Pot *pot, size_t nSyste
                                                 const double *d_boxes, uint64_t pot_type,
                                                 uint64_t params_key, uint64_t *d_keys, void *cuda_stream);
 
+/** XXH3_64bits (xxHash 0.8.3, seed 0) of a host buffer, computed on the host by the same source the
+ *  kernel compiles for its short inputs (hash.cuh): the engine uses it for the two words every key
+ *  of a handle shares; hosts can use it to key single systems without a launch.  No GPU needed. */
+RGPOT_B200_API uint64_t rgpot_b200_hash64(const void *data, size_t len);
+
 /** Message of the last failure on this handle (rgpot_ferror.f90:41-56 semantics, but per
  *  handle): copies at most buffer_len - 1 bytes, NUL-terminates, returns the length. */
 RGPOT_B200_API int rgpot_b200_last_error(RgpotB200Pot *pot, char *buffer, int buffer_len);

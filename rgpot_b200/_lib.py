@@ -102,6 +102,7 @@ SYMBOLS = [
     ("rgpot_b200_neighbor_list_free", None, [_vp]),
     ("rgpot_b200_cache_keys", _i, [_vp, _sz, _vp, _vp, _vp, _vp, C.c_uint64, C.c_uint64, _vp]),
     ("rgpot_b200_cache_keys_device", _i, [_vp, _sz, _vp, _vp, _vp, _vp, C.c_uint64, C.c_uint64, _vp, _vp]),
+    ("rgpot_b200_hash64", C.c_uint64, [C.c_char_p, _sz]),
     ("rgpot_b200_last_error", _i, [_vp, C.c_char_p, _i]),
     ("rgpot_b200_launch_count", _l, [_vp]),
     ("rgpot_b200_stat", _l, [_vp, C.c_char_p]),

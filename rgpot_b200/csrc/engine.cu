@@ -2046,6 +2046,11 @@ int rgpot_b200_force_batch_device(RgpotB200Pot* pot, size_t nSystems, const size
   return 0;
 }
 
+uint64_t rgpot_b200_hash64(const void* data, size_t len) {
+  static const unsigned char none = 0;
+  return rb::xxh3_host(len ? static_cast<const unsigned char*>(data) : &none, data ? len : 0);
+}
+
 // ---- result-cache keys (hash.cuh) ----------------------------------------------------------------
 static int cache_keys_enqueue(RgpotB200Pot* pot, size_t nSystems, const size_t* offsets, const double* d_pos,
                               const int* d_Z, const double* d_boxes, uint64_t pot_type, uint64_t params_key,

@@ -11,6 +11,7 @@
 #pragma once
 #include <cstddef>
 #include <cstdint>
+#include <cstring>
 
 #include "common.cuh"
 
@@ -50,9 +51,15 @@ RB_HD uint32_t rd32(const unsigned char* p) {
   return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
 }
 RB_HD uint64_t rd64(const unsigned char* p) { return (uint64_t)rd32(p) | ((uint64_t)rd32(p + 4) << 32); }
-RB_HD uint64_t in64(const unsigned char* p) {  // input words: two aligned 32-bit loads
-  const uint32_t* q = reinterpret_cast<const uint32_t*>(p);
+RB_HD uint64_t in64(const unsigned char* p) {
+#ifdef __CUDA_ARCH__
+  const uint32_t* q = reinterpret_cast<const uint32_t*>(p);  // device inputs are 4-byte aligned: two word loads
   return (uint64_t)q[0] | ((uint64_t)q[1] << 32);
+#else
+  uint64_t v;  // host: any alignment, any length
+  memcpy(&v, p, 8);
+  return v;
+#endif
 }
 RB_HD uint64_t mul_fold(uint64_t a, uint64_t b) {
 #ifdef __CUDA_ARCH__
@@ -83,7 +90,8 @@ RB_HD uint64_t mix16(const unsigned char* in, const unsigned char* sec) {
   return mul_fold(in64(in) ^ rd64(sec), in64(in + 8) ^ rd64(sec + 8));
 }
 
-// inputs of at most 240 bytes (xxhash.h XXH3_len_0to16 / 17to128 / 129to240, seed 0); len % 4 == 0
+// inputs of at most 240 bytes (xxhash.h XXH3_len_0to16 / 17to128 / 129to240, seed 0); on the device
+// len % 4 == 0 (arrays of doubles and ints)
 RB_HD uint64_t xxh3_short(const unsigned char* in, size_t len) {
   const unsigned char* s = xxh_secret();
   if (len == 0) return xxh64_avalanche(rd64(s + 56) ^ rd64(s + 64));

@@ -86,3 +86,21 @@ def test_engine_sources_do_not_touch_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cc", "Makefile")):
                 text = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "pyoracle" not in text and "liboracle" not in text and "oracle/" not in text, f
+
+
+def test_host_hash_matches_xxhash_vectors():
+    """rgpot_b200_hash64 -- the host build of the source the kernel compiles for its short inputs
+    (hash.cuh) -- against the committed libxxhash digests, every length class.  No GPU involved."""
+    import json
+
+    from rgpot_b200 import _lib
+
+    lib = _lib.lib()
+    with open(os.path.join(ROOT, "tests", "golden", "xxh3_vectors.json")) as fh:
+        g = json.load(fh)
+
+    def pattern(n):
+        return bytes(((i * 131 + n * 31 + (i >> 8) * 7) & 0xFF) for i in range(n))
+
+    for n, digest in g["digests"]:
+        assert lib.rgpot_b200_hash64(pattern(n), n) == int(digest), n
