@@ -31,6 +31,17 @@ def test_lj_fluid_1m_properties(oracle):
     e2, f2, _ = pot(moved, Z, box)
     assert abs(e2 - e) <= 1e-10 * abs(e)
     assert _close(f2, f, rtol=1e-9, atol=1e-8).all()  # the fold loses a few ulp at |x| ~ 3 L
+    # a tenth of the atoms one box vector outside (the state of an MD run that does not re-wrap): the
+    # brick kernels fold the wrap counts into their image codes and stay on duty
+    near = pos.copy()
+    rng = np.random.default_rng(6)
+    who = rng.choice(n, n // 10, replace=False)
+    near[who] += rng.integers(-1, 2, (len(who), 3)) * L
+    fresh = rgpot_b200.LJPot(rgpot_b200.LJConfig(1.0, 2.5, 1.0))
+    e4, f4, _ = fresh(near, Z, box)
+    assert fresh.stat("max_halo") > 0  # brick kernels, not the gather stand-by
+    assert abs(e4 - e) <= 1e-10 * abs(e)
+    assert _close(f4, f, rtol=1e-9, atol=1e-8).all()
     # relabelling the atoms permutes the forces and leaves the energy alone
     perm = np.random.default_rng(5).permutation(n)
     e3, f3, _ = pot(pos[perm], Z, box)
@@ -62,6 +73,13 @@ def test_cuh2_slab_256k_properties(oracle):
     e2, f2, _ = pot(moved, Z, box)
     assert abs(e2 - e) <= 1e-10 * abs(e)
     assert _close(f2, f, rtol=1e-9, atol=1e-8).all()
+    # one cell vector at most: the brick kernels keep the case (wrap counts in the image codes)
+    near = pos + (rng.random((len(pos), 1)) < 0.1) * (rng.integers(-1, 2, size=pos.shape) @ box)
+    fresh = rgpot_b200.CuH2Pot()
+    e3, f3, _ = fresh(near, Z, box)
+    assert fresh.stat("max_halo") > 0 and fresh.stat("pool_used") > 0
+    assert abs(e3 - e) <= 1e-10 * abs(e)
+    assert _close(f3, f, rtol=1e-9, atol=1e-8).all()
     # pin the absolute physics at this size through the commensurate-shear identity:
     # a perfect 40^3 fcc crystal has the bulk energy per atom the oracle gives for 4^3 cells
     # (-906.183991113513 eV / 256 atoms), in the cubic cell and in any lattice-commensurate shear
