@@ -173,7 +173,8 @@ RGPOT_B200_API void rgpot_b200_neighbor_list_free(RgpotB200NeighborList *nl);
  *  XXH3_64bits (xxHash 0.8.3, subprojects/xxhash.wrap) of the positions, the atomic numbers and the
  *  box, XOR the hashes of `pot_type` (the PotType enumerator as size_t) and `params_key`
  *  (paramsKey()) -- so the hit / miss compaction of Potential::forceBatch (:251-306) can hash a
- *  whole batch in one launch and still address the entries the CPU path wrote.  Host buffers;
+ *  whole batch in one launch; with the CPU potential's params_key the keys address the entries the
+ *  CPU path wrote, with the plugin classes' own (salted) paramsKey() they stay apart.  Host buffers;
  *  the _device variant takes device pointers for positions / atomicNrs / boxes / keys (offsets stay
  *  on the host), enqueues on `cuda_stream` and does not synchronise.                          */
 RGPOT_B200_API int rgpot_b200_cache_keys(RgpotB200Pot *pot, size_t nSystems, const size_t *offsets,

@@ -1,8 +1,8 @@
 // hash.cuh -- the result-cache key of rgpot's Potential (CppCore/rgpot/Potential.hpp:324-336) on
 // the GPU: XXH3_64bits (xxHash 0.8.3, the reference's pinned subproject, default secret, seed 0)
 // over a system's positions, atomic numbers and box, XOR the hashes of the potential type and the
-// parameter fingerprint.  Bit-exact integer work: keys made here address the same cache entries
-// as keys made by the reference on the CPU, so `forceBatch`'s hit / miss compaction
+// parameter fingerprint.  Bit-exact integer work: for the same type and fingerprint a key made
+// here equals the key the reference makes on the CPU, so `forceBatch`'s hit / miss compaction
 // (Potential.hpp:251-306) can hash a whole batch in one launch from device-resident inputs.
 //
 // Eight lanes per system (four systems per warp): the lanes are the eight accumulators of the
