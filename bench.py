@@ -202,6 +202,19 @@ def cpu_reference_rate(budget_s=12.0, procs=None, configs_per_proc=4000):
             "wall_s": wall}
 
 
+def cpu_leg_rate(func, args, units, reps=1):
+    """cpu_baseline leg shared with the auxiliary benches under tools/ (widened rows, latencies): the
+    oracle function `func` (oracle/pyoracle.py) timed on `args` after one warm call, `units` per call
+    per second.  The oracle is the CPU baseline here, never part of what the GPU arm measures."""
+    from oracle import pyoracle as po
+    f = getattr(po, func)
+    f(*args)
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        f(*args)
+    return units * reps / (time.perf_counter() - t0)
+
+
 def cpu_side_baseline(name):
     """Reference CPU path for the single-system side workloads, on a bounded sample of the same
     recipe, in a fresh interpreter (this process already holds a CUDA context).  SURVEY 8(d):

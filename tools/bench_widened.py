@@ -59,29 +59,22 @@ def timed(pot, pos, Z, box, steps=5):
 
 
 def cpu_baselines():
-    """The CPU oracle (C restatements of the reference kernels; Morse / ZBL with the reference's O(N^2)
-    pair scan, the EAMs over the restated vesin cell list) on a smaller sample of each recipe, one
-    process, before this process touches CUDA.  atom-evals/s."""
-    from oracle import pyoracle as po
+    """bench.py's cpu_baseline leg (the C restatements of the reference kernels; Morse / ZBL with the
+    reference's O(N^2) pair scan, the EAMs over the restated vesin cell list) on a smaller sample of
+    each recipe, one process, before this process touches CUDA.  atom-evals/s."""
+    from bench import cpu_leg_rate
     res = {}
-
-    def rate(f, n):
-        f()
-        t0 = time.perf_counter()
-        f()
-        return n / (time.perf_counter() - t0)
-
     pos, box = fcc(12, 4.1, 1, 0.08)
-    res["morse_fcc_256k"] = {"value": rate(lambda: po.morse_force(pos, box), len(pos)), "sample": f"{len(pos)}-atom crystal"}
+    res["morse_fcc_256k"] = {"value": cpu_leg_rate("morse_force", (pos, box), len(pos)), "sample": f"{len(pos)}-atom crystal"}
     rng = np.random.default_rng(2)
     n = 8000
     p2 = rng.random((n, 3)) * (n / 0.09) ** (1 / 3)
     z2 = rng.choice([1, 8, 14, 29, 79], n).astype(np.int32)
-    res["zbl_gas_500k"] = {"value": rate(lambda: po.zbl_force(p2, z2), n), "sample": f"{n}-atom gas (O(N^2) scan)"}
+    res["zbl_gas_500k"] = {"value": cpu_leg_rate("zbl_force", (p2, z2), n), "sample": f"{n}-atom gas (O(N^2) scan)"}
     pos3, box3 = fcc(12, 4.05, 3, 0.08)
-    res["eam_al_fcc_256k"] = {"value": rate(lambda: po.eam_al_force(pos3, box3), len(pos3)), "sample": f"{len(pos3)}-atom crystal"}
+    res["eam_al_fcc_256k"] = {"value": cpu_leg_rate("eam_al_force", (pos3, box3), len(pos3)), "sample": f"{len(pos3)}-atom crystal"}
     pos4, z4, box4 = bcc_fehe(14, 0.01, 4)
-    res["fehe_bcc_128k"] = {"value": rate(lambda: po.fehe_force(pos4, z4, box4), len(pos4)), "sample": f"{len(pos4)}-atom crystal"}
+    res["fehe_bcc_128k"] = {"value": cpu_leg_rate("fehe_force", (pos4, z4, box4), len(pos4)), "sample": f"{len(pos4)}-atom crystal"}
     for v in res.values():
         v.update({"unit": "atom-evals/s", "cores": 1, "kind": "port"})  # the C restatements of oracle/
     return res
@@ -123,7 +116,7 @@ def main():
                 "n_atoms": len(pos), "entries": int(len(nl["distances"])), "seconds_host_call": dt,
                 "value": len(pos) / dt, "note": "host call incl. H2D, two emit passes, D2H of 44 B per entry"})
     # result-cache keys (XXH3) of a 65 536 x 218-atom batch, device-resident: HBM-bound byte work
-    from oracle import pyoracle
+    from bench import cpu_leg_rate
     nsys, na = 65536, 218
     dev = torch.device("cuda", 0)
     g = torch.Generator(device=dev).manual_seed(5)
@@ -148,11 +141,7 @@ def main():
         ms.append(t0.elapsed_time(t1))
     nbytes = nsys * (na * 28 + 72)
     hp, hz, hb = d_pos[:na].cpu().numpy(), d_Z[:na].cpu().numpy(), d_boxes[:3].cpu().numpy()
-    assert int(d_keys[0].item()) & (2**64 - 1) == pyoracle.cache_key(hp, hz, hb, 1, pot.paramsKey())
-    t0 = time.perf_counter()
-    for _ in range(2000):
-        pyoracle.cache_key(hp, hz, hb, 1, pot.paramsKey())
-    cpu_rate = 2000 * (na * 28 + 72) / (time.perf_counter() - t0)
+    cpu_rate = cpu_leg_rate("cache_key", (hp, hz, hb, 1, pot.paramsKey()), na * 28 + 72, reps=2000)
     out.append({"workload": "cache_keys_65536x218", "kernel": "k_cache_keys", "bytes": nbytes,
                 "ms_per_step": float(np.median(ms)), "GB_per_s": nbytes / float(np.median(ms)) / 1e6,
                 "value": nsys * na / float(np.median(ms)) * 1e3,
