@@ -252,6 +252,28 @@ def cpu_side_baseline(name):
         return {"value": None, "unit": UNIT, "cores": 1, "kind": "unavailable", "sample": repr(exc)[:200]}
 
 
+def cpu_lj_linear_comparator():
+    """SURVEY 8(d), LJ: the linear-scaling "reference components" comparator at the full C3 size -- the
+    vendored vesin cell list (half list, all host threads) feeding the pair lambda of LJPot.cc:61-81.
+    NOT the reference algorithm (LJPot scans all pairs); labelled so.  Fresh interpreter, oracle/_ref."""
+    code = (
+        "import json, os, sys, time; sys.path.insert(0, %r)\n"
+        "from oracle import pyoracle as po\n"
+        "from rgpot_b200 import workloads\n"
+        "pos, Z, box = workloads.lj_fluid()\n"
+        "t0 = time.perf_counter(); e, F, m = po.lj_vesin_force(pos, box, 1.0, 2.5, 1.0, 0); dt = time.perf_counter() - t0\n"
+        "print(json.dumps({'value': len(pos) / dt, 'unit': 'atom-evals/s', 'cores': os.cpu_count(), 'kind': 'reference-components',\n"
+        "                  'energy': e, 'pairs': m,\n"
+        "                  'sample': 'the full 1 000 000-atom fluid, one cold call: vendored vesin half list (n_threads = all) + the '\n"
+        "                            'LJPot.cc pair lambda, %%.2f s -- not the reference algorithm, which is the O(N^2) scan' %% dt}))\n"
+    ) % (ROOT,)
+    try:
+        out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=240)
+        return json.loads(out.stdout.strip().splitlines()[-1])
+    except Exception as exc:  # noqa: BLE001
+        return {"value": None, "unit": UNIT, "kind": "unavailable", "sample": repr(exc)[:200]}
+
+
 # ------------------------------------------------------------------------------- our workloads
 def run_cuh2_batch(args, world, rank, local):
     import torch
@@ -416,7 +438,7 @@ def run_single_system(args, name, local):
     assert abs(e - float(d_E.item())) <= 1e-12 * abs(e)
     fp64_peak = rgpot_b200.measure_fp64_tflops(local)
     tf = FLOPS_PER_ATOM[name] * value / 1e12
-    return {"workload": name, "n_atoms": n, "value": value, "unit": UNIT, "ms_per_step": total_ms / steps,
+    rec = {"workload": name, "n_atoms": n, "value": value, "unit": UNIT, "ms_per_step": total_ms / steps,
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(pos.nbytes + Z.nbytes),
                     "d2h_bytes_per_step": int(pos.nbytes + 8)},
             "gpu_launches": launches, "energy": e, "cpu_baseline": cpu_side_baseline(name),
@@ -424,6 +446,9 @@ def run_single_system(args, name, local):
                          "unit": "TFLOP/s", "frac": tf / fp64_peak if fp64_peak else None,
                          "note": "whole step (cell build + force kernels) timed, flops of the path"},
             "l2": "256 MB flush write between timed iterations"}
+    if name == "lj_fluid_1m":
+        rec["cpu_baseline_linear"] = cpu_lj_linear_comparator()
+    return rec
 
 
 def measured_traffic_per_atom(kernel_substr, atoms_in_capture):

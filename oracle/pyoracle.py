@@ -288,6 +288,23 @@ def vesin_raw(pos, box, cutoff, full=True, periodic=True):
     return out
 
 
+def lj_vesin_force(pos, box, u0=1.0, cutoff=2.5, psi=1.0, n_threads=0):
+    """(energy, forces, n_pairs) of the linear-scaling LJ comparator (oracle/_ref only): vendored vesin half
+    list + the pair lambda of LJPot.cc:61-81.  Not the reference algorithm (that is the O(N^2) scan)."""
+    pos, box = _prep(pos, box)
+    lib = ref_lib()
+    lib.ref_lj_vesin_force.restype = C.c_int
+    lib.ref_lj_vesin_force.argtypes = [C.c_long, _f64p, _f64p, C.c_double, C.c_double, C.c_double, C.c_int, _f64p,
+                                       C.POINTER(C.c_double), C.POINTER(C.c_long), C.c_char_p, C.c_size_t]
+    F = np.zeros_like(pos)
+    e, m = C.c_double(0.0), C.c_long(0)
+    err = C.create_string_buffer(512)
+    st = lib.ref_lj_vesin_force(len(pos), pos, box, u0, cutoff, psi, int(n_threads), F, C.byref(e), C.byref(m), err, 512)
+    if st != 0:
+        raise RuntimeError(err.value.decode())
+    return e.value, F, m.value
+
+
 def canonical_pairs(table) -> np.ndarray:
     """(i, j, s0, s1, s2) rows in lexicographic order: the pair SET of a table."""
     row = table["row"]

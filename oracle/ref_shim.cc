@@ -5,6 +5,7 @@
 // No reference source is copied into this repository; this file only calls their API.
 #include <array>
 #include <cstdint>
+#include <cmath>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -210,6 +211,60 @@ int ref_vesin_raw(long n, const double *pos, const double *box, int periodic_all
     }
     out->dists[p] = list.distances[p];
   }
+  vesin_free(&list);
+  return 0;
+}
+
+// Linear-scaling LJ comparator ("reference components"): the vendored vesin cell list
+// (half list, all host threads for the filter) feeding the pair lambda of LJPot.cc:61-81.  NOT the
+// reference algorithm -- LJPot scans all N^2/2 pairs -- but what the reference's own parts give when
+// put together; same pair set and pair terms for boxes wider than two cutoffs.
+int ref_lj_vesin_force(long n, const double *pos, const double *box, double u0, double cutoff, double psi,
+                       int n_threads, double *F, double *energy, long *n_pairs, char *err, size_t errlen) {
+  *energy = 0.0;
+  if (n_pairs) *n_pairs = 0;
+  for (long i = 0; i < 3 * n; ++i) F[i] = 0.0;
+  if (n < 2) return 0;
+  VesinNeighborList list;
+  VesinOptions opt{};
+  opt.cutoff = cutoff;
+  opt.full = false;
+  opt.sorted = false;
+  opt.algorithm = VesinAutoAlgorithm;
+  opt.skin = 0.0;
+  opt.n_threads = n_threads;
+  opt.return_shifts = false;
+  opt.return_distances = true;
+  opt.return_vectors = true;
+  const bool periodic[3] = {true, true, true};
+  const char *msg = nullptr;
+  double cell[3][3] = {{box[0], 0, 0}, {0, box[4], 0}, {0, 0, box[8]}};  // LJPot.cc:52-56: the diagonal only
+  int st = vesin_neighbors(reinterpret_cast<const double(*)[3]>(pos), static_cast<size_t>(n), cell, periodic,
+                           VesinDevice{VesinCPU, 0}, opt, &list, &msg);
+  if (st != 0) {
+    std::snprintf(err, errlen, "%s", msg ? msg : "vesin failed");
+    vesin_free(&list);
+    return st;
+  }
+  const double a_c = std::pow(psi / cutoff, 6.0), cut_u = 4.0 * u0 * a_c * (a_c - 1.0);  // LJPot.hpp:45-60
+  const double psi2 = psi * psi;
+  double e = 0.0;
+  for (size_t p = 0; p < list.length; ++p) {
+    const size_t i = list.pairs[p][0], j = list.pairs[p][1];
+    const double dx = -list.vectors[p][0], dy = -list.vectors[p][1], dz = -list.vectors[p][2];  // r_i - r_j
+    const double r2 = dx * dx + dy * dy + dz * dz;
+    const double inv = 1.0 / r2, sr2 = psi2 * inv, a = sr2 * sr2 * sr2, b = 4.0 * u0 * a;
+    e += b * (a - 1.0) - cut_u;
+    const double fs = 6.0 * b * inv * (2.0 * a - 1.0);
+    F[3 * i] += fs * dx;
+    F[3 * i + 1] += fs * dy;
+    F[3 * i + 2] += fs * dz;
+    F[3 * j] -= fs * dx;
+    F[3 * j + 1] -= fs * dy;
+    F[3 * j + 2] -= fs * dz;
+  }
+  *energy = e;
+  if (n_pairs) *n_pairs = static_cast<long>(list.length);
   vesin_free(&list);
   return 0;
 }

@@ -23,6 +23,14 @@ def test_lj_fluid_1m_properties(oracle):
     assert np.isfinite(e) and np.isfinite(f).all()
     # Newton's third law holds pair by pair in the reference's scatter form: zero net force
     assert np.abs(f.sum(0)).max() < 1e-6
+    # the whole system against the reference's own components put together -- the vendored vesin cell
+    # list (half list) feeding the pair lambda of LJPot.cc:61-81 (oracle/_ref, a few seconds of CPU):
+    # same pair count as the GPU's accepted pairs, energy to 1e-10, every force component
+    if oracle.ref_available():
+        e_ref, f_ref, n_pairs = oracle.lj_vesin_force(pos, box, 1.0, 2.5, 1.0)
+        assert n_pairs == 27_263_076
+        assert abs(e - e_ref) <= 1e-10 * abs(e_ref)
+        assert _close(f, f_ref).all()
     # same physics with half the atoms moved by whole box vectors: the literal-fold gather kernel
     # runs instead of the tile kernel and must agree
     L = box[0, 0]
