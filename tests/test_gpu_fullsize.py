@@ -1,5 +1,6 @@
-"""BASELINE.json's full sizes, checked through size-independent properties (the CPU oracle is
-O(N^2) for LJ and minutes for 14M atom-evals, so it only samples here)."""
+"""BASELINE.json's full sizes: size-independent properties, and -- where the CPU path scales
+linearly -- the whole system against it (LJ 1M through the reference's vesin + pair lambda, Cu slab
+256k through vesin + the restated Fortran passes); the 14M-atom-eval batch is sampled."""
 import numpy as np
 import pytest
 
@@ -73,8 +74,13 @@ def test_cuh2_slab_256k_properties(oracle):
     pos, Z, box = workloads.cu_slab_triclinic()
     assert len(pos) == 256_512
     pot = rgpot_b200.CuH2Pot()
-    e, f, _ = pot(pos, Z, box)  # tile kernels
+    e, f, _ = pot(pos, Z, box)  # brick kernels
     assert np.isfinite(e) and np.abs(f.sum(0)).max() < 1e-6
+    # the whole system through the CPU path (the reference's vesin where oracle/_ref exists, feeding
+    # the restated rgpot_cuh2.f90 passes; about ten seconds): energy to 1e-10, every force component
+    e_o, f_o = oracle.cuh2_force(pos, Z, box, use_ref=oracle.ref_available())
+    assert abs(e - e_o) <= 1e-10 * abs(e_o)
+    assert _close(f, f_o).all()
     # atoms pushed out of the cell by whole cell vectors: per-pair image shifts, gather kernels
     rng = np.random.default_rng(2)
     moved = pos + rng.integers(-2, 3, size=pos.shape) @ box
