@@ -20,7 +20,7 @@ def test_lj_fluid_1m_properties(oracle):
     n = len(pos)
     assert n == 1_000_000
     pot = rgpot_b200.LJPot(rgpot_b200.LJConfig(1.0, 2.5, 1.0))
-    e, f, _ = pot(pos, Z, box)  # tile kernels (every atom inside the cell)
+    e, f, _ = pot(pos, Z, box)  # brick kernels (every atom inside the cell)
     assert np.isfinite(e) and np.isfinite(f).all()
     # Newton's third law holds pair by pair in the reference's scatter form: zero net force
     assert np.abs(f.sum(0)).max() < 1e-6
@@ -33,7 +33,7 @@ def test_lj_fluid_1m_properties(oracle):
         assert abs(e - e_ref) <= 1e-10 * abs(e_ref)
         assert _close(f, f_ref).all()
     # same physics with half the atoms moved by whole box vectors: the literal-fold gather kernel
-    # runs instead of the tile kernel and must agree
+    # runs instead of the brick kernel and must agree
     L = box[0, 0]
     moved = pos.copy()
     moved[::2] += np.array([L, -2 * L, 3 * L])
