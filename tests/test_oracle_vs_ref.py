@@ -96,3 +96,17 @@ def test_zbl_restatement_is_bit_exact(ref):
         e_r, f_r = ref.ref_zbl_force(pos, Z, np.eye(3) * 3.0)  # the cell is ignored
         e_o, f_o, _ = ref.zbl_force(pos, Z)
         assert e_o == e_r and np.array_equal(f_o, f_r)
+
+
+def test_linear_lj_comparator_agrees_with_the_reference_object(ref):
+    """The "reference components" comparator (vendored vesin half list + the LJPot.cc pair lambda) used
+    for the full-size LJ check and as `cpu_baseline_linear`, against the reference's own LJPot object on
+    a system its O(N^2) scan can afford: same pair count, energy to 1e-12, forces to 1e-10 (the two sum
+    in different orders).  Box wider than two cutoffs, atoms outside the cell included."""
+    pos, Z, box = workloads.lj_fluid(6000)
+    pos = pos + np.random.default_rng(3).integers(-1, 2, size=pos.shape) @ box * (np.arange(len(pos)) % 9 == 0)[:, None]
+    e_r, f_r = ref.ref_lj_force(pos, box, 1.0, 2.5, 1.0)
+    e_c, f_c, m = ref.lj_vesin_force(pos, box, 1.0, 2.5, 1.0, n_threads=2)
+    assert m == ref.lj_force(pos, box, 1.0, 2.5, 1.0)[2]
+    assert abs(e_c - e_r) <= 1e-12 * abs(e_r)
+    assert np.abs(f_c - f_r).max() <= 1e-10 * max(1.0, np.abs(f_r).max())
