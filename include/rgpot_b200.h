@@ -46,7 +46,7 @@ extern "C" {
 #endif
 
 #define RGPOT_B200_API __attribute__((visibility("default")))
-#define RGPOT_B200_ABI_VERSION 2
+#define RGPOT_B200_ABI_VERSION 3
 
 typedef struct RgpotB200Pot RgpotB200Pot;
 
@@ -69,7 +69,8 @@ enum {
 
 typedef struct RgpotB200Config {
   int kind;      /**< RGPOT_B200_LJ / _LJ_CLUSTER / _CUH2 / _MORSE / _ZBL / _EAM_AL / _FEHE */
-  int device;    /**< CUDA device ordinal; -1 keeps the calling thread's current device */
+  int device;    /**< CUDA device ordinal; -1 keeps the calling thread's current device;
+                      -2: every usable device of the box (same as n_devices = all)             */
   double u0;     /**< LJConfig::u0     (LJPot.hpp:30-34), default 1.0  */
   double cutoff; /**< LJConfig::cutoff, default 15.0; ignored for CuH2 (fixed 6.1) and EAM-Al (7.1) */
   double psi;    /**< LJConfig::psi,    default 1.0  */
@@ -77,7 +78,18 @@ typedef struct RgpotB200Config {
    *  1: opt-in general triclinic LJ: every periodic image with d2 < rc2 (vesin semantics);
    *     no reference counterpart exists for this mode.                                      */
   int lj_all_images;
-  int reserved[7];
+  /** Batches on several GPUs of one box (the systems of a ForceBatch are independent,
+   *  CppCore/rgpot/ForceStructs.hpp:42-48, Potential.hpp:231-233): with n_devices > 1 (or device = -2)
+   *  ONE rgpot_b200_force_batch[_packed] call cuts the batch into contiguous ranges balanced by the
+   *  atom count, one per device of `devices`, and drives each range from its own host thread
+   *  (streams, pinned staging and helper threads on the CPUs next to that GPU), results written
+   *  straight into the caller's buffers; no collective.  Single systems and the *_device entry points
+   *  use devices[0].  0 or 1: single device (`device`).                                        */
+  int n_devices;
+  /** Host threads that move ForceBatch buffers to and from pinned staging, per device (0 = automatic:
+   *  the usable CPUs divided by the number of devices, at most 12). */
+  int host_threads;
+  int reserved[5];
   /** MorseConfig (Morse/MorsePot.hpp:31-36): De, a, re; the cutoff goes in `cutoff` (default 9.5).
    *  Defaults 0.7102 eV, 1.6047 1/A, 2.8970 A (platinum).  Unused by the other kinds.        */
   double morse_De, morse_a, morse_re;
@@ -85,6 +97,7 @@ typedef struct RgpotB200Config {
    *  create fails unless 0 < cut_inner < cut_global (ZBLPot.cc:76-79).  At most 16 distinct
    *  atomic numbers per call.                                                                */
   double zbl_cut_inner;
+  int devices[16]; /**< CUDA ordinals of the batch devices when n_devices > 1 */
 } RgpotB200Config;
 
 RGPOT_B200_API int rgpot_b200_abi_version(void);
@@ -122,7 +135,11 @@ RGPOT_B200_API int rgpot_b200_force_batch_packed(RgpotB200Pot *pot, size_t nSyst
 /** Device-resident variants: every pointer except `box` (9 host doubles) and `offsets` (host
  *  array of nSystems + 1 atom offsets) is a device pointer on the handle's device; work is
  *  enqueued on `cuda_stream` (a cudaStream_t, NULL = the handle's own stream) and the call
- *  returns without synchronising.  Status flags are checked by rgpot_b200_sync_status.      */
+ *  returns without synchronising.  Status flags are checked by rgpot_b200_sync_status.
+ *  Lifetime: d_positions / d_atomicNrs / d_forces / d_energy must stay allocated and unchanged until
+ *  rgpot_b200_sync_status has returned (a system the all-pairs kernel cannot hold is re-run from
+ *  them there), and a handle carries ONE call in flight: the next *_device call on the same handle
+ *  reuses its scratch buffers.                                                               */
 RGPOT_B200_API int rgpot_b200_force_device(RgpotB200Pot *pot, long nAtoms, const double *d_positions,
                                            const int *d_atomicNrs, double *d_forces,
                                            double *d_energy, const double *box, void *cuda_stream);
@@ -218,6 +235,12 @@ RGPOT_B200_API void rgpot_b200_host_free(void *ptr);
 
 /** Sustained FP64 FMA rate of the device (TFLOP/s): the measured roofline denominator. */
 RGPOT_B200_API double rgpot_b200_measure_fp64_tflops(int device, int iters);
+
+/** Aggregate host<->device copy rate (GB/s) of `n_devices` GPUs moving h2d_bytes in and d2h_bytes out
+ *  EACH, both directions and all devices at once, from page-locked buffers placed next to each GPU:
+ *  the ceiling of every end-to-end batch number on this box (best of `reps` passes). */
+RGPOT_B200_API double rgpot_b200_measure_copy_gbs(const int *devices, int n_devices, size_t h2d_bytes,
+                                                  size_t d2h_bytes, int reps);
 
 /* ---- exact drop-in for the reference's Fortran entry (FortranPots.cc:33-40) ------------ */
 RGPOT_B200_API int rgpot_cuh2_force(int32_t natoms, const double *positions,

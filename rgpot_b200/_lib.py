@@ -28,11 +28,14 @@ class Config(C.Structure):
         ("cutoff", C.c_double),
         ("psi", C.c_double),
         ("lj_all_images", C.c_int),
-        ("reserved", C.c_int * 7),
+        ("n_devices", C.c_int),
+        ("host_threads", C.c_int),
+        ("reserved", C.c_int * 5),
         ("morse_De", C.c_double),
         ("morse_a", C.c_double),
         ("morse_re", C.c_double),
         ("zbl_cut_inner", C.c_double),
+        ("devices", C.c_int * 16),
     ]
 
 
@@ -110,6 +113,7 @@ SYMBOLS = [
     ("rgpot_b200_host_alloc", _vp, [_sz]),
     ("rgpot_b200_host_free", None, [_vp]),
     ("rgpot_b200_measure_fp64_tflops", _d, [_i, _i]),
+    ("rgpot_b200_measure_copy_gbs", _d, [_vp, _i, _sz, _sz, _i]),
     ("rgpot_b200_core_callback", _i, [_vp, _vp, _vp]),
     ("rgpot_b200_core_free", None, [_vp]),
     ("rgpot_b200_core_last_error", C.c_char_p, []),

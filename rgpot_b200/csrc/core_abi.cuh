@@ -151,6 +151,17 @@ enum rgpot_status_t rgpot_b200_core_callback(void* user_data, const struct rgpot
       }
       boxp = box;
     }
+    // periodic kinds need the cell (the host entry refuses a missing one too); a NULL box_matrix is
+    // a caller error, not an engine failure
+    if (!boxp && pot->cfg.kind != RGPOT_B200_LJ_CLUSTER && pot->cfg.kind != RGPOT_B200_ZBL)
+      return bad("rgpot_b200_core_callback: box_matrix is NULL, but this potential is periodic");
+    // the forces tensor and the scratch below live on the handle's device, whatever device the
+    // calling thread had current; the caller's choice is put back on exit
+    DevGuard guard(pot->device);
+    if (guard.err != cudaSuccess) {
+      g_core_error = "rgpot_b200_core_callback: cannot select the engine's device";
+      return RGPOT_INTERNAL_ERROR;
+    }
     DLManagedTensorVersioned* F = make_forces_tensor(n, on_device, pot->device);
     if (!F) {
       g_core_error = "rgpot_b200_core_callback: cannot allocate the forces tensor";

@@ -12,6 +12,9 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
+#include <functional>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -24,6 +27,7 @@
 #include "small.cuh"
 #include "brick.cuh"
 #include "hash.cuh"
+#include "hostpipe.hpp"
 
 using namespace rb;
 
@@ -329,6 +333,26 @@ struct RgpotB200Pot {
   // batch scratch
   DevBuf b_pos, b_Z, b_F, b_off, b_boxes, b_E, b_flags, b_bad, b_map;
   HostBuf h_pos, h_Z, h_F, h_off, h_boxes, h_E, h_flags, h_bad, h_small;
+  // ---- host side of the batch entry points (hostpipe.hpp) ----
+  // helper threads that pack / unpack ForceBatch buffers into pinned staging (created on first use,
+  // placed on the CPUs next to this device when the topology can be read)
+  std::unique_ptr<rb::Team> team;
+  int host_threads = 0;       // 0 = automatic
+  int small_attr_set = 0;     // batch kernels whose dynamic shared-memory limit has been raised on this device
+  size_t msg_sys_base = 0;    // index of this range's first system in the caller's batch (messages)
+  DevBuf b_Z0;                // atomic numbers of one system, shared by a homogeneous batch
+  // single small systems: one page-locked block the kernel reads and writes in place (zero copy)
+  HostBuf h_fast;
+  // pageable single systems: pinned ring for the staged H2D / D2H of large arrays
+  HostBuf h_ring;
+  cudaEvent_t ring_ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  // batches cut across several GPUs: one single-device handle + one persistent host thread per device
+  struct Shard {
+    RgpotB200Pot* pot = nullptr;
+    std::unique_ptr<rb::Worker> worker;
+    int status = 0;
+  };
+  std::vector<Shard> shards;
   // outstanding async (device API) call, resolved by rgpot_b200_sync_status
   struct Pending {
     bool active = false;
@@ -348,7 +372,18 @@ struct RgpotB200Pot {
   } pend;
 
   ~RgpotB200Pot() {
+    for (auto& sh : shards) {
+      sh.worker.reset();  // joins the device's host thread
+      delete sh.pot;
+    }
+    shards.clear();
+    team.reset();
     cudaSetDevice(device);
+    b_Z0.release();
+    h_fast.release();
+    h_ring.release();
+    for (auto& e : ring_ev)
+      if (e) cudaEventDestroy(e);
     DevBuf* d[] = {&pos, &Z, &F, &cell_of, &rank, &ashift, &counts, &starts, &blocksums, &order, &order2,
                    &spos, &scell, &dfd, &dfs, &eemb, &partials, &partials2, &energy, &status, &mm, &listpool, &listref, &emit_pairs,
                    &emit_shifts, &emit_count, &emit_vecs, &emit_dists, &b_pos, &b_Z, &b_F, &b_off, &b_boxes, &b_E, &b_flags,
@@ -374,6 +409,34 @@ namespace {
       return kStatusCuda;                                                                   \
     }                                                                                       \
   } while (0)
+
+// RAII: make the handle's device current for the duration of an entry point, then put the caller's back
+struct DevGuard {
+  int prev = -1;
+  cudaError_t err;
+  explicit DevGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    err = cudaSetDevice(dev);
+  }
+  ~DevGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+// helper threads of a handle (created on first use; on the CPUs next to the device when sysfs says
+// which those are, so the pinned staging they fill is local to the GPU's PCIe root)
+rb::Team* get_team(RgpotB200Pot* pot) {
+  if (!pot->team) {
+    int want = pot->host_threads > 0 ? pot->host_threads : std::max(1, std::min(12, rb::usable_cpus()));
+    cpu_set_t allowed, local;
+    CPU_ZERO(&allowed);
+    const bool place = sched_getaffinity(0, sizeof allowed, &allowed) == 0 &&
+                       rb::gpu_local_cpus(pot->device, allowed, local);
+    if (place) want = std::min(want, std::max(1, CPU_COUNT(&local)));
+    pot->team.reset(new rb::Team(want - 1, place ? &local : nullptr));
+  }
+  return pot->team.get();
+}
 
 int fail(RgpotB200Pot* pot, int status, const std::string& msg) {
   pot->last_error = msg;
@@ -962,8 +1025,9 @@ int eam_small_maxnb(const RgpotB200Pot* pot, long nmax) {
 int launch_small(RgpotB200Pot* pot, size_t nsys, long nmax, const long long* d_off,
                  const double* d_boxes, const double* d_pos, const int* d_Z, double* d_F,
                  double* d_E, unsigned* d_flags, int* d_bad, int maxnb, cudaStream_t st,
-                 const EmitArgs* emit) {
+                 const EmitArgs* emit, bool z_shared = false) {
   SmallArgs a{};
+  a.z_shared = z_shared ? 1 : 0;
   a.pos = d_pos;
   a.Z = d_Z;
   a.off = d_off;
@@ -994,15 +1058,19 @@ int launch_small(RgpotB200Pot* pot, size_t nsys, long nmax, const long long* d_o
     const int tpa = eam_small_tpa(nmax);
     int threads = (int)std::min<long>(448, ((nmax * tpa + 31) / 32) * 32);
     if (threads < 32) threads = 32;
+    const int attr_bit = 1 << ((tpa == 1 ? 0 : tpa == 2 ? 1 : tpa == 4 ? 2 : 3) * 2 + (al ? 1 : 0));
     auto launch = [&](auto kern) -> int {
-      cudaFuncAttributes fa;
-      cudaError_t e = cudaFuncGetAttributes(&fa, kern);
-      if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)(pot->smem_optin - fa.sharedSizeBytes));
-      if (e != cudaSuccess) {
-        pot->last_error = std::string("CUDA failure: ") + cudaGetErrorString(e);
-        return kStatusCuda;
+      if (!(pot->small_attr_set & attr_bit)) {  // once per handle and kernel: the calls cost microseconds
+        cudaFuncAttributes fa;
+        cudaError_t e = cudaFuncGetAttributes(&fa, kern);
+        if (e == cudaSuccess)
+          e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)(pot->smem_optin - fa.sharedSizeBytes));
+        if (e != cudaSuccess) {
+          pot->last_error = std::string("CUDA failure: ") + cudaGetErrorString(e);
+          return kStatusCuda;
+        }
+        pot->small_attr_set |= attr_bit;
       }
       kern<<<(unsigned)nsys, threads, smem, st>>>(a);
       return check_launch(pot, "k_eam_small");
@@ -1015,12 +1083,15 @@ int launch_small(RgpotB200Pot* pot, size_t nsys, long nmax, const long long* d_o
     }
   }
   const size_t smem = sizeof(double) * 3 * (size_t)nmax + sizeof(int) * (size_t)nmax + 16;
-  cudaFuncAttributes fa;
-  cudaError_t e = cudaFuncGetAttributes(&fa, k_lj_small);
-  if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(k_lj_small, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)(pot->smem_optin - fa.sharedSizeBytes));
-  if (e != cudaSuccess) return fail(pot, kStatusCuda, std::string("CUDA failure: ") + cudaGetErrorString(e));
+  if (!(pot->small_attr_set & (1 << 30))) {
+    cudaFuncAttributes fa;
+    cudaError_t e = cudaFuncGetAttributes(&fa, k_lj_small);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(k_lj_small, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)(pot->smem_optin - fa.sharedSizeBytes));
+    if (e != cudaSuccess) return fail(pot, kStatusCuda, std::string("CUDA failure: ") + cudaGetErrorString(e));
+    pot->small_attr_set |= 1 << 30;
+  }
   int threads = (int)std::min<long>(256, ((nmax + 31) / 32) * 32);
   if (threads < 32) threads = 32;
   k_lj_small<<<(unsigned)nsys, threads, smem, st>>>(a);
@@ -1053,7 +1124,7 @@ int map_flags(RgpotB200Pot* pot, unsigned flags, int bad_atom, int bad_z, const 
              bad_atom + 1, bad_z);
     return fail(pot, 2, buf);
   }
-  const bool images = eam || pot->cfg.lj_all_images;
+  const bool images = eam || pot->cfg.kind == RGPOT_B200_FEHE || pot->cfg.lj_all_images;
   if (images && (flags & kFlagSingularBox))
     return fail(pot, 1, "rgpot_neighbors: vesin build failed: the box matrix is not invertible");
   if (images && (flags & kFlagNonFinite)) {
@@ -1076,8 +1147,11 @@ int map_flags(RgpotB200Pot* pot, unsigned flags, int bad_atom, int bad_z, const 
   }
   if (flags & kFlagShiftRange)
     return fail(pot, kStatusRange, "rgpot_b200: an atom lies more than 500 cell widths outside the box");
+  // rgpot_cuh2.f90:422-428.  The aluminium kernel has no such guard upstream (it would return NaN
+  // forces): refusing the input there is a documented deviation, under its own name.
   if (eam && (flags & kFlagCoincident))
-    return fail(pot, 3, "rgpot_cuh2: two atoms occupy the same position");
+    return fail(pot, 3, pot->cfg.kind == RGPOT_B200_EAM_AL ? "rgpot_eam_al: two atoms occupy the same position"
+                                                          : "rgpot_cuh2: two atoms occupy the same position");
   return 0;
 }
 
@@ -1256,6 +1330,59 @@ void rgpot_b200_default_config(int kind, RgpotB200Config* cfg) {
   cfg->morse_re = 2.8970;
 }
 
+// one single-device handle on `dev` (its streams, its copy of the coefficient tables)
+static RgpotB200Pot* create_on_device(const RgpotB200Config* cfg, int dev, std::string& msg) {
+  cudaDeviceProp prop;
+  if (cudaSetDevice(dev) != cudaSuccess || cudaGetDeviceProperties(&prop, dev) != cudaSuccess) {
+    cudaGetLastError();
+    msg = "rgpot_b200_create: cannot select the device";
+    return nullptr;
+  }
+  if (prop.major < 10) {
+    msg = "rgpot_b200_create: the engine is built for sm_100a (B200) only";
+    return nullptr;
+  }
+  auto* pot = new RgpotB200Pot();
+  pot->cfg = *cfg;
+  pot->cfg.device = dev;
+  pot->device = dev;
+  pot->host_threads = cfg->host_threads > 0 ? cfg->host_threads : 0;
+  pot->sm_count = prop.multiProcessorCount;
+  pot->smem_optin = prop.sharedMemPerBlockOptin;
+  pot->smem_per_sm = prop.sharedMemPerMultiprocessor;
+  bool ok = cudaStreamCreateWithFlags(&pot->stream, cudaStreamNonBlocking) == cudaSuccess;
+  for (auto& s : pot->pipe) ok = ok && cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) == cudaSuccess;
+  ok = ok && cudaEventCreateWithFlags(&pot->ev_ready, cudaEventDisableTiming) == cudaSuccess;
+  for (auto& e : pot->ring_ev) ok = ok && cudaEventCreateWithFlags(&e, cudaEventDisableTiming) == cudaSuccess;
+  if (!ok) {
+    delete pot;
+    msg = "rgpot_b200_create: cannot create streams";
+    return nullptr;
+  }
+  if (is_eam(cfg->kind)) {
+    const EamParams p = cfg->kind == RGPOT_B200_EAM_AL ? make_eam_al_params() : make_eam_params();
+    double tab[64];
+    for (int j = 0; j < 64; ++j) tab[j] = exp2((double)j / 64.0);
+    if (cudaMemcpyToSymbol(c_exp2tab, tab, sizeof tab) != cudaSuccess ||
+        (cfg->kind == RGPOT_B200_EAM_AL ? cudaMemcpyToSymbol(c_eam_al, &p, sizeof p)
+                                        : cudaMemcpyToSymbol(c_eam, &p, sizeof p)) != cudaSuccess) {
+      delete pot;
+      msg = "rgpot_b200_create: cannot upload the EAM coefficients";
+      return nullptr;
+    }
+  } else if (cfg->kind == RGPOT_B200_FEHE) {
+    const FeHeParams p = make_fehe_params();
+    if (cudaMemcpyToSymbol(c_fehe, &p, sizeof p) != cudaSuccess) {
+      delete pot;
+      msg = "rgpot_b200_create: cannot upload the Fe-He coefficients";
+      return nullptr;
+    }
+  } else {
+    lj_setup(pot);
+  }
+  return pot;
+}
+
 RgpotB200Pot* rgpot_b200_create(const RgpotB200Config* cfg, char* errbuf, size_t errlen) {
   auto err = [&](const std::string& m) -> RgpotB200Pot* {
     if (errbuf && errlen) snprintf(errbuf, errlen, "%s", m.c_str());
@@ -1274,47 +1401,66 @@ RgpotB200Pot* rgpot_b200_create(const RgpotB200Config* cfg, char* errbuf, size_t
                (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0") +
                "); this engine has no CPU fallback");
   }
-  int dev = cfg->device;
-  if (dev < 0) {
-    if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
-  }
-  if (dev >= ndev) return err("rgpot_b200_create: device ordinal out of range");
-  cudaDeviceProp prop;
-  if (cudaSetDevice(dev) != cudaSuccess || cudaGetDeviceProperties(&prop, dev) != cudaSuccess)
-    return err("rgpot_b200_create: cannot select the device");
-  if (prop.major < 10)
-    return err("rgpot_b200_create: the engine is built for sm_100a (B200) only");
-  auto* pot = new RgpotB200Pot();
-  pot->cfg = *cfg;
-  pot->device = dev;
-  pot->sm_count = prop.multiProcessorCount;
-  pot->smem_optin = prop.sharedMemPerBlockOptin;
-  pot->smem_per_sm = prop.sharedMemPerMultiprocessor;
-  bool ok = cudaStreamCreateWithFlags(&pot->stream, cudaStreamNonBlocking) == cudaSuccess;
-  for (auto& s : pot->pipe) ok = ok && cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) == cudaSuccess;
-  ok = ok && cudaEventCreateWithFlags(&pot->ev_ready, cudaEventDisableTiming) == cudaSuccess;
-  if (!ok) {
-    delete pot;
-    return err("rgpot_b200_create: cannot create streams");
-  }
-  if (is_eam(cfg->kind)) {
-    const EamParams p = cfg->kind == RGPOT_B200_EAM_AL ? make_eam_al_params() : make_eam_params();
-    double tab[64];
-    for (int j = 0; j < 64; ++j) tab[j] = exp2((double)j / 64.0);
-    if (cudaMemcpyToSymbol(c_exp2tab, tab, sizeof tab) != cudaSuccess ||
-        (cfg->kind == RGPOT_B200_EAM_AL ? cudaMemcpyToSymbol(c_eam_al, &p, sizeof p)
-                                        : cudaMemcpyToSymbol(c_eam, &p, sizeof p)) != cudaSuccess) {
-      delete pot;
-      return err("rgpot_b200_create: cannot upload the EAM coefficients");
+  int prev_dev = -1;
+  if (cudaGetDevice(&prev_dev) != cudaSuccess) prev_dev = -1;
+  struct Restore {  // the caller's current device is left as it was
+    int d;
+    ~Restore() {
+      if (d >= 0) cudaSetDevice(d);
     }
-  } else if (cfg->kind == RGPOT_B200_FEHE) {
-    const FeHeParams p = make_fehe_params();
-    if (cudaMemcpyToSymbol(c_fehe, &p, sizeof p) != cudaSuccess) {
-      delete pot;
-      return err("rgpot_b200_create: cannot upload the Fe-He coefficients");
+  } restore{prev_dev};
+  // the batch devices: an explicit list, every usable device (device = -2), or just one
+  std::vector<int> devs;
+  if (cfg->n_devices > 1) {
+    if (cfg->n_devices > 16) return err("rgpot_b200_create: at most 16 devices");
+    for (int k = 0; k < cfg->n_devices; ++k) {
+      const int d = cfg->devices[k];
+      if (d < 0 || d >= ndev) return err("rgpot_b200_create: device ordinal out of range");
+      if (std::find(devs.begin(), devs.end(), d) != devs.end())
+        return err("rgpot_b200_create: a device is listed twice");
+      devs.push_back(d);
     }
+  } else if (cfg->device == -2) {
+    for (int d = 0; d < ndev && (int)devs.size() < 16; ++d) {
+      cudaDeviceProp p;
+      if (cudaGetDeviceProperties(&p, d) == cudaSuccess && p.major >= 10) devs.push_back(d);
+    }
+    if (devs.empty()) return err("rgpot_b200_create: the engine is built for sm_100a (B200) only");
   } else {
-    lj_setup(pot);
+    int dev = cfg->device;
+    if (dev < 0) dev = prev_dev >= 0 ? prev_dev : 0;
+    if (dev >= ndev) return err("rgpot_b200_create: device ordinal out of range");
+    devs.push_back(dev);
+  }
+  std::string msg;
+  RgpotB200Pot* pot = create_on_device(cfg, devs[0], msg);
+  if (!pot) return err(msg);
+  if (devs.size() > 1) {
+    cpu_set_t allowed;
+    CPU_ZERO(&allowed);
+    const bool have_mask = sched_getaffinity(0, sizeof allowed, &allowed) == 0;
+    int per_dev = cfg->host_threads;
+    if (per_dev <= 0) per_dev = std::max(1, std::min(12, rb::usable_cpus() / (int)devs.size()));
+    pot->host_threads = per_dev;
+    for (int d : devs) {
+      RgpotB200Config c1 = *cfg;
+      c1.n_devices = 0;
+      c1.device = d;
+      c1.host_threads = per_dev;
+      RgpotB200Pot* sp = create_on_device(&c1, d, msg);
+      if (!sp) {
+        delete pot;
+        return err(msg);
+      }
+      RgpotB200Pot::Shard sh;
+      sh.pot = sp;
+      cpu_set_t local;
+      if (have_mask && rb::gpu_local_cpus(d, allowed, local))
+        sh.worker.reset(new rb::Worker(&local));
+      else
+        sh.worker.reset(new rb::Worker(nullptr));
+      pot->shards.push_back(std::move(sh));
+    }
   }
   return pot;
 }
@@ -1433,6 +1579,85 @@ double rgpot_b200_measure_fp64_tflops(int device, int iters) {
   return best;
 }
 
+// What the host side of the box can move: every listed device copies h2d_bytes from and d2h_bytes into
+// its own page-locked buffers (allocated by a thread on the CPUs next to that device), both directions
+// at once, all devices at once; returns the aggregate GB/s of the slowest-finishing device set
+// (bytes of all devices / wall time between a common start and the last finish).  This is the ceiling
+// of any end-to-end number of a batch: bench.py prints it beside `e2e`.
+double rgpot_b200_measure_copy_gbs(const int* devices, int n_devices, size_t h2d_bytes, size_t d2h_bytes,
+                                   int reps) {
+  if (n_devices < 1 || !devices || reps < 1) return 0.0;
+  struct Lane {
+    int dev;
+    void *h_in = nullptr, *h_out = nullptr, *d_in = nullptr, *d_out = nullptr;
+    cudaStream_t s_in = nullptr, s_out = nullptr;
+    bool ok = true;
+  };
+  std::vector<Lane> lanes(n_devices);
+  cpu_set_t allowed;
+  CPU_ZERO(&allowed);
+  const bool have_mask = sched_getaffinity(0, sizeof allowed, &allowed) == 0;
+  std::vector<std::unique_ptr<rb::Worker>> workers;
+  for (int k = 0; k < n_devices; ++k) {
+    lanes[k].dev = devices[k];
+    cpu_set_t local;
+    const bool place = have_mask && rb::gpu_local_cpus(devices[k], allowed, local);
+    workers.emplace_back(new rb::Worker(place ? &local : nullptr));
+  }
+  auto all = [&](const std::function<void(Lane&)>& f) {
+    for (int k = 0; k < n_devices; ++k) workers[k]->submit([&, k] { f(lanes[k]); });
+    for (int k = 0; k < n_devices; ++k) workers[k]->wait();
+  };
+  all([&](Lane& l) {
+    l.ok = cudaSetDevice(l.dev) == cudaSuccess && cudaMallocHost(&l.h_in, std::max<size_t>(h2d_bytes, 1)) == cudaSuccess &&
+           cudaMallocHost(&l.h_out, std::max<size_t>(d2h_bytes, 1)) == cudaSuccess &&
+           cudaMalloc(&l.d_in, std::max<size_t>(h2d_bytes, 1)) == cudaSuccess &&
+           cudaMalloc(&l.d_out, std::max<size_t>(d2h_bytes, 1)) == cudaSuccess &&
+           cudaStreamCreateWithFlags(&l.s_in, cudaStreamNonBlocking) == cudaSuccess &&
+           cudaStreamCreateWithFlags(&l.s_out, cudaStreamNonBlocking) == cudaSuccess;
+    if (l.ok) {
+      memset(l.h_in, 1, std::max<size_t>(h2d_bytes, 1));
+      memset(l.h_out, 1, std::max<size_t>(d2h_bytes, 1));
+    }
+  });
+  bool ok = true;
+  for (auto& l : lanes) ok = ok && l.ok;
+  double best = 0.0;
+  if (ok) {
+    auto pass = [&](Lane& l) {
+      cudaSetDevice(l.dev);
+      // sixteen slices each way, like a pipelined batch
+      const int slices = 16;
+      for (int c = 0; c < slices; ++c) {
+        const size_t i0 = h2d_bytes * c / slices, i1 = h2d_bytes * (c + 1) / slices;
+        const size_t o0 = d2h_bytes * c / slices, o1 = d2h_bytes * (c + 1) / slices;
+        if (i1 > i0) cudaMemcpyAsync((char*)l.d_in + i0, (char*)l.h_in + i0, i1 - i0, cudaMemcpyHostToDevice, l.s_in);
+        if (o1 > o0) cudaMemcpyAsync((char*)l.h_out + o0, (char*)l.d_out + o0, o1 - o0, cudaMemcpyDeviceToHost, l.s_out);
+      }
+      cudaStreamSynchronize(l.s_in);
+      cudaStreamSynchronize(l.s_out);
+    };
+    all(pass);  // warm-up
+    for (int r = 0; r < reps; ++r) {
+      const auto t0 = std::chrono::steady_clock::now();
+      all(pass);
+      const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+      const double gbs = (double)(h2d_bytes + d2h_bytes) * n_devices / dt / 1e9;
+      best = std::max(best, gbs);
+    }
+  }
+  all([&](Lane& l) {
+    cudaSetDevice(l.dev);
+    if (l.s_in) cudaStreamDestroy(l.s_in);
+    if (l.s_out) cudaStreamDestroy(l.s_out);
+    if (l.h_in) cudaFreeHost(l.h_in);
+    if (l.h_out) cudaFreeHost(l.h_out);
+    if (l.d_in) cudaFree(l.d_in);
+    if (l.d_out) cudaFree(l.d_out);
+  });
+  return ok ? best : 0.0;
+}
+
 // ------------------------------------------------------------------------------------------------
 // device-resident entry points
 // ------------------------------------------------------------------------------------------------
@@ -1523,7 +1748,8 @@ int rgpot_b200_force_device(RgpotB200Pot* pot, long nAtoms, const double* d_posi
                             const double* box, void* cuda_stream) {
   if (!pot) return kStatusArgs;
   pot->last_error.clear();
-  CU_TRY(pot, cudaSetDevice(pot->device));
+  DevGuard guard(pot->device);
+  CU_TRY(pot, guard.err);
   cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : pot->stream;
   pot->pend.active = false;
   if (nAtoms < 0 || nAtoms > kMaxAtoms) return fail(pot, kStatusArgs, "rgpot_b200: bad atom count");
@@ -1540,6 +1766,8 @@ int rgpot_b200_force_device(RgpotB200Pot* pot, long nAtoms, const double* d_posi
   const bool zbl = pot->cfg.kind == RGPOT_B200_ZBL;
   if ((eam || zbl) && !d_atomicNrs)
     return fail(pot, kStatusArgs, "rgpot_b200: this potential needs atomic numbers");
+  if (pot->cfg.kind != RGPOT_B200_LJ_CLUSTER && !zbl && !box)
+    return fail(pot, kStatusArgs, "rgpot_b200_force_device: null box");
   if (zbl) {
     // the species set decides the coefficient table (ZBLPot.cc:150-196): presence bitmap + device mapping
     int zs = zbl_prepare_device(pot, (size_t)nAtoms, d_atomicNrs, st);
@@ -1572,7 +1800,8 @@ static int batch_sync_status(RgpotB200Pot* pot);
 
 int rgpot_b200_sync_status(RgpotB200Pot* pot) {
   if (!pot) return kStatusArgs;
-  CU_TRY(pot, cudaSetDevice(pot->device));
+  DevGuard guard(pot->device);
+  CU_TRY(pot, guard.err);
   RgpotB200Pot::Pending& pd = pot->pend;
   if (!pd.active) {
     CU_TRY(pot, cudaStreamSynchronize(pot->stream));
@@ -1593,6 +1822,127 @@ int rgpot_b200_sync_status(RgpotB200Pot* pot) {
 // ------------------------------------------------------------------------------------------------
 // host-buffer single system
 // ------------------------------------------------------------------------------------------------
+// Large host arrays: page-locked memory is copied by the DMA engine straight from / into the caller's
+// array; pageable memory (what Potential::operator() hands over, CppCore/rgpot/Potential.hpp:165-211)
+// goes through a ring of pinned slices filled / drained by the helper threads, slice k + 1 on the CPU
+// while slice k is on the bus.
+constexpr size_t kRingSlice = 4u << 20;
+constexpr int kRingSlots = 4;
+
+static int upload_array(RgpotB200Pot* pot, void* d_dst, const void* h_src, size_t bytes, cudaStream_t st) {
+  if (bytes < (1u << 20) || rb::host_ptr_is_pinned(h_src)) {
+    CU_TRY(pot, cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, st));
+    return 0;
+  }
+  CU_TRY(pot, pot->h_ring.reserve(kRingSlice * kRingSlots));
+  rb::Team* team = get_team(pot);
+  char* ring = pot->h_ring.as<char>();
+  const size_t nslices = (bytes + kRingSlice - 1) / kRingSlice;
+  for (size_t i = 0; i < nslices; ++i) {
+    const int slot = (int)(i % kRingSlots);
+    const size_t o = i * kRingSlice, len = std::min(kRingSlice, bytes - o);
+    if (i >= (size_t)kRingSlots) CU_TRY(pot, cudaEventSynchronize(pot->ring_ev[slot]));
+    char* dst = ring + (size_t)slot * kRingSlice;
+    const char* src = static_cast<const char*>(h_src) + o;
+    team->run(len, 256u << 10, [&](size_t b0, size_t b1) { memcpy(dst + b0, src + b0, b1 - b0); });
+    CU_TRY(pot, cudaMemcpyAsync(static_cast<char*>(d_dst) + o, dst, len, cudaMemcpyHostToDevice, st));
+    CU_TRY(pot, cudaEventRecord(pot->ring_ev[slot], st));
+  }
+  // the ring may be reused by the next call only after these copies: the download below (same
+  // stream) or the final synchronisation of the caller orders that
+  return 0;
+}
+
+static int download_array(RgpotB200Pot* pot, void* h_dst, const void* d_src, size_t bytes, cudaStream_t st) {
+  if (bytes < (1u << 20) || rb::host_ptr_is_pinned(h_dst)) {
+    CU_TRY(pot, cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, st));
+    return 0;
+  }
+  CU_TRY(pot, pot->h_ring.reserve(kRingSlice * kRingSlots));
+  rb::Team* team = get_team(pot);
+  char* ring = pot->h_ring.as<char>();
+  const size_t nslices = (bytes + kRingSlice - 1) / kRingSlice;
+  auto issue = [&](size_t i) -> cudaError_t {
+    const int slot = (int)(i % kRingSlots);
+    const size_t o = i * kRingSlice, len = std::min(kRingSlice, bytes - o);
+    cudaError_t e = cudaMemcpyAsync(ring + (size_t)slot * kRingSlice, static_cast<const char*>(d_src) + o, len,
+                                    cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaEventRecord(pot->ring_ev[slot], st);
+    return e;
+  };
+  for (size_t i = 0; i < std::min<size_t>(nslices, kRingSlots); ++i) CU_TRY(pot, issue(i));
+  for (size_t i = 0; i < nslices; ++i) {
+    const int slot = (int)(i % kRingSlots);
+    const size_t o = i * kRingSlice, len = std::min(kRingSlice, bytes - o);
+    CU_TRY(pot, cudaEventSynchronize(pot->ring_ev[slot]));
+    const char* src = ring + (size_t)slot * kRingSlice;
+    char* dst = static_cast<char*>(h_dst) + o;
+    team->run(len, 256u << 10, [&](size_t b0, size_t b1) { memcpy(dst + b0, src + b0, b1 - b0); });
+    if (i + kRingSlots < nslices) CU_TRY(pot, issue(i + kRingSlots));
+  }
+  return 0;
+}
+
+// Single small systems (BASELINE configs[0] / [1], the reference's PotBench sizes): the whole call is
+// ONE kernel launch.  Inputs are written into a page-locked block that the kernel reads in place over
+// PCIe (a few kilobytes, read once), forces / energy / status come back the same way: no copy
+// commands, no flag reset, one synchronisation.  Returns -1 when the system has to take the general
+// path instead (list overflow: far images, crowded atoms).
+static int force_small_fast(RgpotB200Pot* pot, long nAtoms, const double* positions, const int* atomicNrs,
+                            double* forces, double* energy, const double* box) {
+  const size_t n = (size_t)nAtoms;
+  const bool eam = reads_species(pot->cfg.kind);
+  // layout (8-byte units): off[2] | box[9] | pos[3n] | F[3n] | E | flags, bad[2] (as 2 words) | Z[n ints]
+  const size_t words = 2 + 9 + 3 * n + 3 * n + 1 + 2 + (n + 1) / 2 + 1;
+  if (pot->h_fast.cap < words * 8) {
+    if (pot->h_fast.p) cudaFreeHost(pot->h_fast.p);
+    pot->h_fast.p = nullptr;
+    pot->h_fast.cap = 0;
+    const size_t want = std::max<size_t>(words * 8 * 2, 64u << 10);
+    CU_TRY(pot, cudaHostAlloc(&pot->h_fast.p, want, cudaHostAllocMapped | cudaHostAllocPortable));
+    pot->h_fast.cap = want;
+  }
+  void* dbase = nullptr;
+  CU_TRY(pot, cudaHostGetDevicePointer(&dbase, pot->h_fast.p, 0));
+  double* h = pot->h_fast.as<double>();
+  double* d = static_cast<double*>(dbase);
+  long long* h_off = reinterpret_cast<long long*>(h);
+  double* h_box = h + 2;
+  double* h_pos = h + 11;
+  double* h_F = h_pos + 3 * n;
+  double* h_E = h_F + 3 * n;
+  unsigned* h_flags = reinterpret_cast<unsigned*>(h_E + 1);
+  int* h_bad = reinterpret_cast<int*>(h_E + 2);
+  int* h_Z = reinterpret_cast<int*>(h_E + 3);
+  h_off[0] = 0;
+  h_off[1] = (long long)n;
+  if (box)
+    memcpy(h_box, box, 9 * sizeof(double));
+  else
+    memset(h_box, 0, 9 * sizeof(double));
+  memcpy(h_pos, positions, sizeof(double) * 3 * n);
+  if (eam) memcpy(h_Z, atomicNrs, sizeof(int) * n);
+  *h_flags = 0xffffffffu;
+  h_bad[0] = INT_MAX;
+  h_bad[1] = 0;
+  const size_t iE = 11 + 6 * n;
+  const int maxnb = is_eam(pot->cfg.kind) ? eam_small_maxnb(pot, nAtoms) : 0;
+  cudaStream_t st = pot->stream;
+  int s = launch_small(pot, 1, nAtoms, reinterpret_cast<const long long*>(d), d + 2, d + 11,
+                       eam ? reinterpret_cast<const int*>(d + iE + 3) : nullptr, d + 11 + 3 * n, d + iE,
+                       reinterpret_cast<unsigned*>(d + iE + 1), reinterpret_cast<int*>(d + iE + 2), maxnb, st, nullptr);
+  if (s) return s;
+  CU_TRY(pot, cudaStreamSynchronize(st));
+  const unsigned flags = *h_flags;
+  if (flags == 0xffffffffu) return fail(pot, kStatusCuda, "rgpot_b200: the single-system kernel left no status");
+  if (flags & kFlagListOverflow) return -1;
+  s = map_flags(pot, flags, h_bad[0], h_bad[1], positions);
+  if (s) return s;
+  memcpy(forces, h_F, sizeof(double) * 3 * n);
+  *energy = *h_E;
+  return 0;
+}
+
 int rgpot_b200_force(RgpotB200Pot* pot, long nAtoms, const double* positions, const int* atomicNrs,
                      double* forces, double* energy, double* variance, const double* box) {
   if (!pot) return kStatusArgs;
@@ -1611,7 +1961,8 @@ int rgpot_b200_force(RgpotB200Pot* pot, long nAtoms, const double* positions, co
   } zero{forces, nAtoms > 0 ? (size_t)nAtoms : 0};
   if (!energy || (nAtoms > 0 && (!positions || !forces)))
     return fail(pot, kStatusArgs, "rgpot_b200_force: null buffer");
-  CU_TRY(pot, cudaSetDevice(pot->device));
+  DevGuard guard(pot->device);
+  CU_TRY(pot, guard.err);
   if (nAtoms < 0 || nAtoms > kMaxAtoms) return fail(pot, kStatusArgs, "rgpot_b200: bad atom count");
   const bool eam = reads_species(pot->cfg.kind);  // (reads atomic numbers)
   const bool trivial = (is_eam(pot->cfg.kind) || pot->cfg.kind == RGPOT_B200_FEHE) ? nAtoms < 1
@@ -1621,16 +1972,32 @@ int rgpot_b200_force(RgpotB200Pot* pot, long nAtoms, const double* positions, co
   if ((eam || zbl) && !atomicNrs) return fail(pot, kStatusArgs, "rgpot_b200: this potential needs atomic numbers");
   if (pot->cfg.kind != RGPOT_B200_LJ_CLUSTER && pot->cfg.kind != RGPOT_B200_ZBL && !box)
     return fail(pot, kStatusArgs, "rgpot_b200_force: null box");
+  if (!zbl && pot->forced_path != 1 && small_eligible(pot, nAtoms)) {
+    const int fs = force_small_fast(pot, nAtoms, positions, atomicNrs, forces, energy, box);
+    if (fs == 0) {
+      zero.armed = false;
+      return 0;
+    }
+    if (fs > 0) {
+      *energy = 0.0;
+      return fs;
+    }
+    // fs < 0: the all-pairs kernel bowed out; the cell-list kernels below take the system
+  }
   cudaStream_t st = pot->stream;
   const size_t n = (size_t)nAtoms;
   CU_TRY(pot, pot->pos.reserve(sizeof(double) * 3 * n));
   CU_TRY(pot, pot->F.reserve(sizeof(double) * 3 * n));
   CU_TRY(pot, pot->energy.reserve(sizeof(double)));
-  CU_TRY(pot, cudaMemcpyAsync(pot->pos.p, positions, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, st));
+  {
+    int us = upload_array(pot, pot->pos.p, positions, sizeof(double) * 3 * n, st);
+    if (us) return us;
+  }
   const int* d_Z = nullptr;
   if (eam) {
     CU_TRY(pot, pot->Z.reserve(sizeof(int) * n));
-    CU_TRY(pot, cudaMemcpyAsync(pot->Z.p, atomicNrs, sizeof(int) * n, cudaMemcpyHostToDevice, st));
+    int us = upload_array(pot, pot->Z.p, atomicNrs, sizeof(int) * n, st);
+    if (us) return us;
     d_Z = pot->Z.as<int>();
   } else if (zbl) {
     // species-pair tables are keyed on the set of atomic numbers (ZBLPot.cc:150-196)
@@ -1641,13 +2008,17 @@ int rgpot_b200_force(RgpotB200Pot* pot, long nAtoms, const double* positions, co
     CU_TRY(pot, cudaMemcpy(pot->Z.p, types.data(), sizeof(int) * n, cudaMemcpyHostToDevice));
     d_Z = pot->Z.as<int>();
   }
+  const int saved_path = pot->forced_path;
+  if (!zbl && small_eligible(pot, nAtoms) && pot->forced_path != 2) pot->forced_path = 1;  // (the fast path bowed out)
   int s = force_device_impl(pot, nAtoms, pot->pos.as<double>(), d_Z, pot->F.as<double>(),
                             pot->energy.as<double>(), box, st, nullptr, 0);
+  pot->forced_path = saved_path;
   if (s) return s;
   s = finish_single(pot, nAtoms, pot->pos.as<double>(), d_Z, pot->F.as<double>(),
                     pot->energy.as<double>(), box, st, positions, atomicNrs);
   if (s) return s;  // outputs stay zeroed, like the reference
-  CU_TRY(pot, cudaMemcpyAsync(forces, pot->F.p, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost, st));
+  s = download_array(pot, forces, pot->F.p, sizeof(double) * 3 * n, st);
+  if (s) return s;
   CU_TRY(pot, cudaMemcpyAsync(energy, pot->energy.p, sizeof(double), cudaMemcpyDeviceToHost, st));
   CU_TRY(pot, cudaStreamSynchronize(st));
   zero.armed = false;
@@ -1663,7 +2034,8 @@ int rgpot_b200_neighbors(RgpotB200Pot* pot, long nAtoms, const double* positions
   if (!pot || !n_out) return kStatusArgs;
   pot->last_error.clear();
   *n_out = 0;
-  CU_TRY(pot, cudaSetDevice(pot->device));
+  DevGuard guard(pot->device);
+  CU_TRY(pot, guard.err);
   if (nAtoms < 1) return 0;
   cudaStream_t st = pot->stream;
   const size_t n = (size_t)nAtoms;
@@ -1752,7 +2124,8 @@ int rgpot_b200_neighbor_list(RgpotB200Pot* pot, size_t n_points, const double* p
   if (!per && !none)
     return fail(pot, kStatusArgs, "rgpot_b200_neighbor_list: mixed periodicity is not supported (all or none)");
   if (per && !box) return fail(pot, kStatusArgs, "rgpot_b200_neighbor_list: null box");
-  CU_TRY(pot, cudaSetDevice(pot->device));
+  DevGuard guard(pot->device);
+  CU_TRY(pot, guard.err);
   cudaStream_t st = pot->stream;
   const size_t n = n_points;
   // A free system is searched inside a fictitious cubic cell so wide that no image comes within the
@@ -1950,8 +2323,9 @@ static int batch_device_impl(RgpotB200Pot* pot, size_t nsys, const size_t* offse
 // Returns the first non-zero status.  h_* describe where the data of the batch lives.
 static int batch_finish(RgpotB200Pot* pot, size_t nsys, const size_t* offsets, const double* d_pos,
                         const int* d_Z, const double* h_boxes, const double* d_boxes, double* d_F,
-                        double* d_E, cudaStream_t st, const double* host_pos, const int* host_Z,
-                        int* statuses, std::vector<size_t>* touched = nullptr) {
+                        double* d_E, cudaStream_t st, const double* host_pos,
+                        const std::function<const int*(size_t)>& host_Z_of, int* statuses,
+                        std::vector<size_t>* touched = nullptr) {
   CU_TRY(pot, pot->h_flags.reserve(sizeof(unsigned) * nsys));
   CU_TRY(pot, pot->h_bad.reserve(sizeof(int) * 2 * nsys));
   unsigned* hf = pot->h_flags.as<unsigned>();
@@ -1971,6 +2345,11 @@ static int batch_finish(RgpotB200Pot* pot, size_t nsys, const size_t* offsets, c
       double hbox[9];
       int rs = fetch_box(pot, h_boxes, d_boxes, s, hbox);
       if (rs) return rs;
+      if (host_Z_of && d_Z && n > 0) {
+        // a homogeneous batch shares one copy of the atomic numbers: this member's own were never uploaded
+        const int* src = host_Z_of(s);
+        if (src) CU_TRY(pot, cudaMemcpyAsync(const_cast<int*>(d_Z) + o, src, sizeof(int) * n, cudaMemcpyHostToDevice, st));
+      }
       rs = run_cell_path(pot, n, d_pos + 3 * o, d_Z ? d_Z + o : nullptr, d_F + 3 * o, d_E + s, hbox, st,
                          nullptr, false);
       if (rs >= kStatusCuda) return rs;
@@ -1987,8 +2366,9 @@ static int batch_finish(RgpotB200Pot* pot, size_t nsys, const size_t* offsets, c
     int status = 0;
     if (f & ~(kFlagAtomShift | kFlagBigShift)) {
       if ((f & kFlagForeignZ) && bad != INT_MAX && bad >= 0) {
-        if (host_Z) {
-          badz = host_Z[o + bad];
+        const int* zsrc = host_Z_of ? host_Z_of(s) : nullptr;
+        if (zsrc) {
+          badz = zsrc[bad];
         } else if (d_Z) {
           CU_TRY(pot, cudaMemcpy(&badz, d_Z + o + bad, sizeof(int), cudaMemcpyDeviceToHost));
         }
@@ -2001,7 +2381,7 @@ static int batch_finish(RgpotB200Pot* pot, size_t nsys, const size_t* offsets, c
         if (!first) {
           first = status;
           char pre[64];
-          snprintf(pre, sizeof pre, "system %zu: ", s);
+          snprintf(pre, sizeof pre, "system %zu: ", s + pot->msg_sys_base);
           first_msg = pre + pot->last_error;
         }
       }
@@ -2027,7 +2407,8 @@ int rgpot_b200_force_batch_device(RgpotB200Pot* pot, size_t nSystems, const size
   if (pot->cfg.kind == RGPOT_B200_ZBL)
     return fail(pot, kStatusArgs, "rgpot_b200: ZBL batches go through the host entry points "
                                   "(the species table is built from the atomic numbers on the host)");
-  CU_TRY(pot, cudaSetDevice(pot->device));
+  DevGuard guard(pot->device);
+  CU_TRY(pot, guard.err);
   cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : pot->stream;
   int s = batch_device_impl(pot, nSystems, offsets, d_positions, d_atomicNrs, d_boxes, nullptr, d_forces,
                             d_energies, st);
@@ -2077,7 +2458,8 @@ int rgpot_b200_cache_keys_device(RgpotB200Pot* pot, size_t nSystems, const size_
     return fail(pot, kStatusArgs, "rgpot_b200_cache_keys_device: null buffer");
   for (size_t i = 0; i < nSystems; ++i)
     if (offsets[i + 1] < offsets[i]) return fail(pot, kStatusArgs, "rgpot_b200_cache_keys: offsets must not decrease");
-  CU_TRY(pot, cudaSetDevice(pot->device));
+  DevGuard guard(pot->device);
+  CU_TRY(pot, guard.err);
   cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : pot->stream;
   return cache_keys_enqueue(pot, nSystems, offsets, d_positions, d_atomicNrs, d_boxes, pot_type, params_key, d_keys, st);
 }
@@ -2092,7 +2474,8 @@ int rgpot_b200_cache_keys(RgpotB200Pot* pot, size_t nSystems, const size_t* offs
     return fail(pot, kStatusArgs, "rgpot_b200_cache_keys: null buffer");
   for (size_t i = 0; i < nSystems; ++i)
     if (offsets[i + 1] < offsets[i]) return fail(pot, kStatusArgs, "rgpot_b200_cache_keys: offsets must not decrease");
-  CU_TRY(pot, cudaSetDevice(pot->device));
+  DevGuard guard(pot->device);
+  CU_TRY(pot, guard.err);
   cudaStream_t st = pot->stream;
   const size_t o0 = offsets[0], total = offsets[nSystems] - o0;
   CU_TRY(pot, pot->b_pos.reserve(sizeof(double) * 3 * std::max<size_t>(total, 1)));
@@ -2117,7 +2500,7 @@ int rgpot_b200_cache_keys(RgpotB200Pot* pot, size_t nSystems, const size_t* offs
 static int batch_sync_status(RgpotB200Pot* pot) {
   RgpotB200Pot::Pending& pd = pot->pend;
   int s = batch_finish(pot, pd.nsys, pd.offsets.data(), pd.pos, pd.Z, nullptr, pd.d_boxes, pd.F, pd.E,
-                       pd.st, nullptr, nullptr, nullptr);
+                       pd.st, nullptr, {}, nullptr);
   cudaStreamSynchronize(pd.st);
   return s;
 }
@@ -2131,9 +2514,15 @@ static int batch_sync_status(RgpotB200Pot* pot) {
 // ------------------------------------------------------------------------------------------------
 }  // extern "C" (templates need C++ linkage)
 
+// `stage_in(c0, c1)` is called right before chunk [c0, c1) is copied (the pointer-array entry packs
+// the chunk into pinned staging there) and returns whether every system of the chunk carries the
+// atomic numbers `z0` of the batch's first system (then the chunk's own are not uploaded: the kernel
+// reads the shared copy); `stage_out(c0, c1)` is called once the chunk's results are on the host --
+// for chunk k - 2 while the copies and kernels of chunks k - 1 and k are in flight.
 template <class StageIn, class StageOut>
 static int batch_pipeline(RgpotB200Pot* pot, size_t nsys, const size_t* rel, long nmax, const double* h_pos,
                           const int* h_Z, const double* h_boxes, double* h_F, double* h_E, int* statuses,
+                          const int* z0, const std::function<const int*(size_t)>& host_Z_of,
                           StageIn&& stage_in, StageOut&& stage_out) {
   const bool eam = reads_species(pot->cfg.kind) || pot->cfg.kind == RGPOT_B200_ZBL;  // has a Z array
   const size_t total = rel[nsys];
@@ -2150,13 +2539,19 @@ static int batch_pipeline(RgpotB200Pot* pot, size_t nsys, const size_t* rel, lon
   for (size_t s = 0; s <= nsys; ++s) ho[s] = (long long)rel[s];
   cudaStream_t st0 = pot->stream;
   CU_TRY(pot, cudaMemcpyAsync(pot->b_off.p, ho, sizeof(long long) * (nsys + 1), cudaMemcpyHostToDevice, st0));
-  CU_TRY(pot, cudaMemsetAsync(pot->b_flags.p, 0, sizeof(unsigned) * nsys, st0));
+  const size_t n0 = rel[1] - rel[0];
+  if (!eam || n0 == 0) z0 = nullptr;
+  if (z0) {
+    CU_TRY(pot, pot->b_Z0.reserve(sizeof(int) * n0));
+    CU_TRY(pot, cudaMemcpyAsync(pot->b_Z0.p, z0, sizeof(int) * n0, cudaMemcpyHostToDevice, st0));
+  }
   CU_TRY(pot, cudaEventRecord(pot->ev_ready, st0));
   for (auto& s : pot->pipe) CU_TRY(pot, cudaStreamWaitEvent(s, pot->ev_ready, 0));
 
   const int maxnb = is_eam(pot->cfg.kind) ? eam_small_maxnb(pot, nmax) : 0;
+  // chunks: about sixteen per batch, but never so short that a chunk's kernel is a few partial waves
   size_t chunk = (nsys + 15) / 16;
-  chunk = std::min<size_t>(std::max<size_t>(chunk, 256), 8192);
+  chunk = std::min<size_t>(std::max<size_t>(chunk, (size_t)8 * pot->sm_count), 8192);
   const size_t nchunks = (nsys + chunk - 1) / chunk;
   std::vector<cudaEvent_t> done(nchunks, nullptr);
   int rc = 0;
@@ -2165,11 +2560,23 @@ static int batch_pipeline(RgpotB200Pot* pot, size_t nsys, const size_t* rel, lon
   double* d_boxes = pot->b_boxes.as<double>();
   double* d_F = pot->b_F.as<double>();
   double* d_E = pot->b_E.as<double>();
+  size_t retired = 0;
+  auto retire = [&](size_t upto) {  // unpack chunks [retired, upto) as their results arrive
+    for (; retired < upto; ++retired) {
+      if (!done[retired]) continue;
+      if (rc == 0 && cudaEventSynchronize(done[retired]) == cudaSuccess) {
+        const size_t c0 = retired * chunk, c1 = std::min(nsys, c0 + chunk);
+        stage_out(c0, c1);
+      }
+      cudaEventDestroy(done[retired]);
+      done[retired] = nullptr;
+    }
+  };
   for (size_t k = 0; k < nchunks && rc == 0; ++k) {
     const size_t c0 = k * chunk, c1 = std::min(nsys, c0 + chunk);
     const size_t a0 = rel[c0], a1 = rel[c1];
     cudaStream_t st = pot->pipe[k % 3];
-    stage_in(c0, c1);
+    const bool shared = stage_in(c0, c1) && z0 != nullptr;
     auto cu = [&](cudaError_t err, const char* what) {
       if (err != cudaSuccess && rc == 0) {
         pot->last_error = std::string("CUDA failure: ") + cudaGetErrorString(err) + " at " + what;
@@ -2178,33 +2585,28 @@ static int batch_pipeline(RgpotB200Pot* pot, size_t nsys, const size_t* rel, lon
     };
     if (a1 > a0) {
       cu(cudaMemcpyAsync(d_pos + 3 * a0, h_pos + 3 * a0, sizeof(double) * 3 * (a1 - a0), cudaMemcpyHostToDevice, st), "H2D positions");
-      if (eam) cu(cudaMemcpyAsync(d_Z + a0, h_Z + a0, sizeof(int) * (a1 - a0), cudaMemcpyHostToDevice, st), "H2D atomic numbers");
+      if (eam && !shared) cu(cudaMemcpyAsync(d_Z + a0, h_Z + a0, sizeof(int) * (a1 - a0), cudaMemcpyHostToDevice, st), "H2D atomic numbers");
     }
     cu(cudaMemcpyAsync(d_boxes + 9 * c0, h_boxes + 9 * c0, sizeof(double) * 9 * (c1 - c0), cudaMemcpyHostToDevice, st), "H2D boxes");
     if (rc) break;
-    rc = launch_small(pot, c1 - c0, nmax, pot->b_off.as<long long>() + c0, d_boxes + 9 * c0, d_pos, d_Z, d_F,
-                      d_E + c0, pot->b_flags.as<unsigned>() + c0, pot->b_bad.as<int>() + 2 * c0, maxnb, st, nullptr);
+    rc = launch_small(pot, c1 - c0, nmax, pot->b_off.as<long long>() + c0, d_boxes + 9 * c0, d_pos,
+                      shared ? pot->b_Z0.as<int>() : d_Z, d_F, d_E + c0, pot->b_flags.as<unsigned>() + c0,
+                      pot->b_bad.as<int>() + 2 * c0, maxnb, st, nullptr, shared);
     if (rc) break;
     if (a1 > a0)
       cu(cudaMemcpyAsync(h_F + 3 * a0, d_F + 3 * a0, sizeof(double) * 3 * (a1 - a0), cudaMemcpyDeviceToHost, st), "D2H forces");
     cu(cudaMemcpyAsync(h_E + c0, d_E + c0, sizeof(double) * (c1 - c0), cudaMemcpyDeviceToHost, st), "D2H energies");
     cu(cudaEventCreateWithFlags(&done[k], cudaEventDisableTiming), "event");
     if (done[k]) cu(cudaEventRecord(done[k], st), "event record");
+    if (k >= 2) retire(k - 1);  // chunk k - 2 is unpacked while chunks k - 1 and k are in flight
   }
-  for (size_t k = 0; k < nchunks; ++k) {
-    if (!done[k]) continue;
-    if (rc == 0 && cudaEventSynchronize(done[k]) == cudaSuccess) {
-      const size_t c0 = k * chunk, c1 = std::min(nsys, c0 + chunk);
-      stage_out(c0, c1);
-    }
-    cudaEventDestroy(done[k]);
-  }
+  retire(nchunks);
   for (auto& s : pot->pipe) cudaStreamSynchronize(s);
   if (rc) return rc;
 
   // statuses; list-overflow members rerun on the cell path; failed members are zeroed
   std::vector<size_t> touched;
-  int s = batch_finish(pot, nsys, rel, d_pos, d_Z, h_boxes, d_boxes, d_F, d_E, st0, h_pos, h_Z, statuses, &touched);
+  int s = batch_finish(pot, nsys, rel, d_pos, d_Z, h_boxes, d_boxes, d_F, d_E, st0, h_pos, host_Z_of, statuses, &touched);
   if (s >= kStatusCuda) return s;
   for (size_t id : touched) {
     const size_t a0 = rel[id], a1 = rel[id + 1];
@@ -2234,6 +2636,156 @@ static long batch_all_small(const RgpotB200Pot* pot, size_t nsys, const size_t* 
   return nmax;
 }
 
+static const double kFreeBox[9] = {1e6, 0, 0, 0, 1e6, 0, 0, 0, 1e6};
+
+}  // extern "C" (templates need C++ linkage)
+
+// One batch on ONE device whose buffers are (or may be) pageable: every system is copied into pinned
+// staging by the handle's helper threads, chunk by chunk, overlapped with the copies and kernels of the
+// chunks before it, and the results are copied back the same way (ForceBatch semantics: the caller
+// owns nSystems separate allocations, CppCore/rgpot/ForceStructs.hpp:40-54).
+// pos_of / Z_of / box_of / F_of return the host pointers of system s (box_of may return NULL = free).
+template <class PosOf, class ZOf, class BoxOf, class FOf>
+static int batch_staged(RgpotB200Pot* pot, size_t nsys, const size_t* off, PosOf&& pos_of, ZOf&& Z_of,
+                        BoxOf&& box_of, FOf&& F_of, double* energies, int* statuses) {
+  const bool zbl = pot->cfg.kind == RGPOT_B200_ZBL;
+  const bool eam = reads_species(pot->cfg.kind) || zbl;  // carries a per-atom integer array
+  const size_t total = off[nsys];
+  CU_TRY(pot, pot->h_pos.reserve(sizeof(double) * 3 * std::max<size_t>(total, 1)));
+  CU_TRY(pot, pot->h_F.reserve(sizeof(double) * 3 * std::max<size_t>(total, 1)));
+  CU_TRY(pot, pot->h_boxes.reserve(sizeof(double) * 9 * nsys));
+  CU_TRY(pot, pot->h_E.reserve(sizeof(double) * nsys));
+  if (eam) CU_TRY(pot, pot->h_Z.reserve(sizeof(int) * std::max<size_t>(total, 1)));
+  double* hp = pot->h_pos.as<double>();
+  double* hbx = pot->h_boxes.as<double>();
+  int* hz = pot->h_Z.as<int>();
+  double* hF = pot->h_F.as<double>();
+  double* hE = pot->h_E.as<double>();
+  rb::Team* team = get_team(pot);
+  const size_t n0 = nsys ? off[1] - off[0] : 0;
+  const int* z0 = (eam && !zbl && n0 > 0) ? Z_of(0) : nullptr;  // candidate for the shared copy
+  auto pack = [&](size_t c0, size_t c1) -> bool {
+    std::atomic<int> same{z0 ? 1 : 0};
+    team->run(c1 - c0, 32, [&](size_t b, size_t e) {
+      bool eq = true;
+      for (size_t s = c0 + b; s < c0 + e; ++s) {
+        const size_t n = off[s + 1] - off[s];
+        if (n > 0) {
+          memcpy(hp + 3 * off[s], pos_of(s), sizeof(double) * 3 * n);
+          if (eam) {
+            const int* z = Z_of(s);
+            if (z0 && n == n0 && (z == z0 || memcmp(z, z0, sizeof(int) * n) == 0)) {
+              // same species as the first system: nothing to copy if the whole chunk is like this
+            } else {
+              eq = false;
+              memcpy(hz + off[s], z, sizeof(int) * n);
+            }
+          }
+        } else if (eam) {
+          eq = false;
+        }
+        const double* bx = box_of(s);
+        memcpy(hbx + 9 * s, bx ? bx : kFreeBox, sizeof(double) * 9);
+      }
+      if (!eq) same.store(0, std::memory_order_relaxed);
+    });
+    if (eam && z0 && !same.load()) {  // a mixed chunk uploads its own atomic numbers: fill in the skipped ones
+      team->run(c1 - c0, 64, [&](size_t b, size_t e) {
+        for (size_t s = c0 + b; s < c0 + e; ++s) {
+          const size_t n = off[s + 1] - off[s];
+          if (n > 0) memcpy(hz + off[s], Z_of(s), sizeof(int) * n);
+        }
+      });
+    }
+    return same.load() != 0;
+  };
+  auto unpack = [&](size_t c0, size_t c1) {
+    team->run(c1 - c0, 32, [&](size_t b, size_t e) {
+      for (size_t s = c0 + b; s < c0 + e; ++s) {
+        const size_t n = off[s + 1] - off[s];
+        if (n > 0) memcpy(F_of(s), hF + 3 * off[s], sizeof(double) * 3 * n);
+        energies[s] = hE[s];
+      }
+    });
+  };
+  std::function<const int*(size_t)> host_Z_of;
+  if (eam) host_Z_of = [&](size_t s) -> const int* { return Z_of(s); };
+  const long nmax = batch_all_small(pot, nsys, off);
+  if (nmax >= 0 && !zbl)
+    return batch_pipeline(pot, nsys, off, nmax, hp, eam ? hz : nullptr, hbx, hF, hE, statuses, z0, host_Z_of,
+                          pack, unpack);
+  // mixed or large members: pack everything, run, unpack everything
+  z0 = nullptr;
+  pack(0, nsys);
+  int st = rgpot_b200_force_batch_packed(pot, nsys, off, hp, eam ? hz : nullptr, hbx, hF, hE, statuses);
+  if (st >= kStatusCuda) return st;
+  unpack(0, nsys);
+  return st;
+}
+
+// cut [0, nsys) into `parts` contiguous ranges balanced by the atom count
+static std::vector<size_t> cut_by_atoms(size_t nsys, const std::function<size_t(size_t)>& atoms_before, size_t parts) {
+  std::vector<size_t> cut(parts + 1, nsys);
+  cut[0] = 0;
+  const size_t total = atoms_before(nsys);
+  size_t s = 0;
+  for (size_t p = 1; p < parts; ++p) {
+    const size_t target = (size_t)((double)total * (double)p / (double)parts);
+    while (s < nsys && atoms_before(s) < target) ++s;
+    // nearest boundary to the target
+    if (s > cut[p - 1] && s <= nsys && target - atoms_before(s - 1) < atoms_before(s) - target && s - 1 >= cut[p - 1]) --s;
+    cut[p] = std::max(s, cut[p - 1]);
+  }
+  return cut;
+}
+
+// run `job(shard index, first system, one past the last)` on every device's host thread and join;
+// returns the first non-zero status in batch order (its message becomes the handle's)
+template <class Job>
+static int run_on_shards(RgpotB200Pot* pot, const std::vector<size_t>& cut, Job&& job) {
+  const size_t parts = cut.size() - 1;
+  for (size_t p = 0; p < parts; ++p) {
+    auto& sh = pot->shards[p];
+    sh.status = 0;
+    if (cut[p + 1] == cut[p]) continue;
+    sh.pot->msg_sys_base = cut[p];
+    sh.worker->submit([&, p] {
+      auto& me = pot->shards[p];
+      DevGuard g(me.pot->device);
+      me.status = job(me.pot, cut[p], cut[p + 1]);
+    });
+  }
+  for (size_t p = 0; p < parts; ++p)
+    if (cut[p + 1] > cut[p]) pot->shards[p].worker->wait();
+  int first = 0;
+  for (size_t p = 0; p < parts; ++p) {
+    const auto& sh = pot->shards[p];
+    if (sh.status >= kStatusCuda) {  // an engine failure outranks per-system statuses
+      pot->last_error = sh.pot->last_error;
+      return sh.status;
+    }
+    if (sh.status && !first) {
+      first = sh.status;
+      pot->last_error = sh.pot->last_error;
+    }
+  }
+  return first;
+}
+
+// how many of the handle's devices a batch of this size is worth cutting across
+static size_t shards_for(const RgpotB200Pot* pot, size_t nsys, size_t total_atoms) {
+  if (pot->shards.size() < 2) return 1;
+  size_t parts = std::min(pot->shards.size(), nsys);
+  parts = std::min(parts, std::max<size_t>(1, total_atoms / 16384));
+  return std::max<size_t>(parts, 1);
+}
+
+extern "C" {
+
+static int force_batch_packed_one(RgpotB200Pot* pot, size_t nSystems, const size_t* offsets,
+                                  const double* positions, const int* atomicNrs, const double* boxes,
+                                  double* forces, double* energies, int* statuses);
+
 int rgpot_b200_force_batch_packed(RgpotB200Pot* pot, size_t nSystems, const size_t* offsets,
                                   const double* positions, const int* atomicNrs, const double* boxes,
                                   double* forces, double* energies, int* statuses) {
@@ -2245,7 +2797,35 @@ int rgpot_b200_force_batch_packed(RgpotB200Pot* pot, size_t nSystems, const size
   const bool zbl = pot->cfg.kind == RGPOT_B200_ZBL;
   const bool eam = reads_species(pot->cfg.kind) || zbl;  // "carries a per-atom integer array"
   if (eam && !atomicNrs) return fail(pot, kStatusArgs, "rgpot_b200: this potential needs atomic numbers");
-  CU_TRY(pot, cudaSetDevice(pot->device));
+  for (size_t i = 0; i < nSystems; ++i)
+    if (offsets[i + 1] < offsets[i]) return fail(pot, kStatusArgs, "rgpot_b200_force_batch_packed: offsets must not decrease");
+  const size_t parts = shards_for(pot, nSystems, offsets[nSystems] - offsets[0]);
+  if (parts > 1 && !zbl) {
+    // one range per device, each driven by its own host thread; offsets / positions / forces are
+    // indexed absolutely, so a range is the same arrays with a later first system
+    const size_t base = offsets[0];
+    const std::vector<size_t> cut =
+        cut_by_atoms(nSystems, [&](size_t s) { return offsets[s] - base; }, parts);
+    return run_on_shards(pot, cut, [&](RgpotB200Pot* sp, size_t s0, size_t s1) {
+      return force_batch_packed_one(sp, s1 - s0, offsets + s0, positions, atomicNrs, boxes + 9 * s0, forces,
+                                    energies + s0, statuses ? statuses + s0 : nullptr);
+    });
+  }
+  RgpotB200Pot* target = pot->shards.empty() ? pot : pot->shards[0].pot;
+  DevGuard g(target->device);
+  if (g.err != cudaSuccess) return fail(pot, kStatusCuda, std::string("CUDA failure: ") + cudaGetErrorString(g.err));
+  target->msg_sys_base = 0;
+  const int st = force_batch_packed_one(target, nSystems, offsets, positions, atomicNrs, boxes, forces, energies, statuses);
+  if (target != pot) pot->last_error = target->last_error;
+  return st;
+}
+
+static int force_batch_packed_one(RgpotB200Pot* pot, size_t nSystems, const size_t* offsets,
+                                  const double* positions, const int* atomicNrs, const double* boxes,
+                                  double* forces, double* energies, int* statuses) {
+  pot->last_error.clear();
+  const bool zbl = pot->cfg.kind == RGPOT_B200_ZBL;
+  const bool eam = reads_species(pot->cfg.kind) || zbl;
   cudaStream_t st = pot->stream;
   const size_t base = offsets[0];
   const size_t total = offsets[nSystems] - base;
@@ -2261,11 +2841,41 @@ int rgpot_b200_force_batch_packed(RgpotB200Pot* pot, size_t nSystems, const size
   }
 
   const long nmax = batch_all_small(pot, nSystems, rel.data());
+  // page-locked arrays are copied by the DMA engines straight from / into the caller's memory;
+  // pageable ones go through the handle's pinned staging like a ForceBatch does
+  const bool pinned = rb::host_ptr_is_pinned(positions + 3 * base) && rb::host_ptr_is_pinned(forces + 3 * base) &&
+                      (!eam || zbl || rb::host_ptr_is_pinned(atomicNrs + base)) && rb::host_ptr_is_pinned(boxes) &&
+                      rb::host_ptr_is_pinned(energies);
+  if (nmax >= 0 && !zbl && !pinned && total >= 4096) {
+    return batch_staged(pot, nSystems, rel.data(),
+                        [&](size_t s) { return positions + 3 * offsets[s]; },
+                        [&](size_t s) { return atomicNrs + offsets[s]; },
+                        [&](size_t s) { return boxes + 9 * s; },
+                        [&](size_t s) { return forces + 3 * offsets[s]; }, energies, statuses);
+  }
   if (nmax >= 0) {
+    const size_t n0 = rel[1] - rel[0];
+    const int* z0 = (eam && !zbl && n0 > 0) ? atomicNrs + base : nullptr;
+    rb::Team* team = (z0 && nSystems >= 1024) ? get_team(pot) : nullptr;
+    // homogeneous batches (NEB / dimer images: one species array repeated): the kernel reads ONE copy
+    auto check = [&](size_t c0, size_t c1) -> bool {
+      if (!team) return false;
+      std::atomic<int> same{1};
+      team->run(c1 - c0, 128, [&](size_t b, size_t e) {
+        for (size_t s = c0 + b; s < c0 + e; ++s)
+          if (rel[s + 1] - rel[s] != n0 || memcmp(atomicNrs + offsets[s], z0, sizeof(int) * n0) != 0) {
+            same.store(0, std::memory_order_relaxed);
+            return;
+          }
+      });
+      return same.load() != 0;
+    };
     auto nop = [](size_t, size_t) {};
+    std::function<const int*(size_t)> host_Z_of;
+    if (eam) host_Z_of = [&](size_t s) -> const int* { return atomicNrs + offsets[s]; };
     return batch_pipeline(pot, nSystems, rel.data(), nmax, positions + 3 * base,
                           atomicNrs ? atomicNrs + base : nullptr, boxes, forces + 3 * base, energies,
-                          statuses, nop, nop);
+                          statuses, team ? z0 : nullptr, host_Z_of, check, nop);
   }
 
   CU_TRY(pot, pot->b_pos.reserve(sizeof(double) * 3 * std::max<size_t>(total, 1)));
@@ -2284,16 +2894,30 @@ int rgpot_b200_force_batch_packed(RgpotB200Pot* pot, size_t nSystems, const size
   int s = batch_device_impl(pot, nSystems, rel.data(), pot->b_pos.as<double>(), d_Z,
                             pot->b_boxes.as<double>(), boxes, pot->b_F.as<double>(), pot->b_E.as<double>(), st);
   if (s) return s;
+  std::function<const int*(size_t)> host_Z_of;
+  if (eam) host_Z_of = [&](size_t k) -> const int* { return atomicNrs + offsets[k]; };
   s = batch_finish(pot, nSystems, rel.data(), pot->b_pos.as<double>(), d_Z, boxes,
                    pot->b_boxes.as<double>(), pot->b_F.as<double>(), pot->b_E.as<double>(), st,
-                   positions + 3 * base, atomicNrs ? atomicNrs + base : nullptr,
-                   statuses);
+                   positions + 3 * base, host_Z_of, statuses);
   if (s >= kStatusCuda) return s;
   CU_TRY(pot, cudaMemcpyAsync(forces + 3 * base, pot->b_F.p, sizeof(double) * 3 * total,
                               cudaMemcpyDeviceToHost, st));
   CU_TRY(pot, cudaMemcpyAsync(energies, pot->b_E.p, sizeof(double) * nSystems, cudaMemcpyDeviceToHost, st));
   CU_TRY(pot, cudaStreamSynchronize(st));
   return s;
+}
+
+static int force_batch_one(RgpotB200Pot* pot, size_t nSystems, const size_t* nAtoms,
+                           const double* const* positions, const int* const* atomicNrs,
+                           const double* const* boxes, double* const* forces, double* energies,
+                           int* statuses) {
+  pot->last_error.clear();
+  std::vector<size_t> off(nSystems + 1, 0);
+  for (size_t s = 0; s < nSystems; ++s) off[s + 1] = off[s] + nAtoms[s];
+  return batch_staged(pot, nSystems, off.data(), [&](size_t s) { return positions[s]; },
+                      [&](size_t s) { return atomicNrs[s]; },
+                      [&](size_t s) -> const double* { return boxes ? boxes[s] : nullptr; },
+                      [&](size_t s) { return forces[s]; }, energies, statuses);
 }
 
 int rgpot_b200_force_batch(RgpotB200Pot* pot, size_t nSystems, const size_t* nAtoms,
@@ -2308,50 +2932,27 @@ int rgpot_b200_force_batch(RgpotB200Pot* pot, size_t nSystems, const size_t* nAt
   const bool zbl = pot->cfg.kind == RGPOT_B200_ZBL;
   const bool eam = reads_species(pot->cfg.kind) || zbl;  // carries a per-atom integer array
   if (eam && !atomicNrs) return fail(pot, kStatusArgs, "rgpot_b200: this potential needs atomic numbers");
-  CU_TRY(pot, cudaSetDevice(pot->device));
-  std::vector<size_t> off(nSystems + 1, 0);
+  std::vector<size_t> before(nSystems + 1, 0);
   for (size_t s = 0; s < nSystems; ++s) {
-    off[s + 1] = off[s] + nAtoms[s];
+    before[s + 1] = before[s] + nAtoms[s];
     if (nAtoms[s] > 0 && (!positions[s] || !forces[s] || (eam && !atomicNrs[s])))
       return fail(pot, kStatusArgs, "rgpot_b200_force_batch: null system buffer");
   }
-  const size_t total = off[nSystems];
-  // ForceBatch buffers are independent allocations in general: gather through pinned staging
-  CU_TRY(pot, pot->h_pos.reserve(sizeof(double) * 3 * std::max<size_t>(total, 1)));
-  CU_TRY(pot, pot->h_F.reserve(sizeof(double) * 3 * std::max<size_t>(total, 1)));
-  CU_TRY(pot, pot->h_boxes.reserve(sizeof(double) * 9 * nSystems));
-  CU_TRY(pot, pot->h_E.reserve(sizeof(double) * nSystems));
-  if (eam) CU_TRY(pot, pot->h_Z.reserve(sizeof(int) * std::max<size_t>(total, 1)));
-  double* hp = pot->h_pos.as<double>();
-  double* hbx = pot->h_boxes.as<double>();
-  int* hz = pot->h_Z.as<int>();
-  double* hF = pot->h_F.as<double>();
-  double* hE = pot->h_E.as<double>();
-  static const double free_box[9] = {1e6, 0, 0, 0, 1e6, 0, 0, 0, 1e6};
-  auto pack = [&](size_t c0, size_t c1) {
-    for (size_t s = c0; s < c1; ++s) {
-      if (nAtoms[s] > 0) {
-        memcpy(hp + 3 * off[s], positions[s], sizeof(double) * 3 * nAtoms[s]);
-        if (eam) memcpy(hz + off[s], atomicNrs[s], sizeof(int) * nAtoms[s]);
-      }
-      const double* b = (boxes && boxes[s]) ? boxes[s] : free_box;
-      memcpy(hbx + 9 * s, b, sizeof(double) * 9);
-    }
-  };
-  auto unpack = [&](size_t c0, size_t c1) {
-    for (size_t s = c0; s < c1; ++s) {
-      if (nAtoms[s] > 0) memcpy(forces[s], hF + 3 * off[s], sizeof(double) * 3 * nAtoms[s]);
-      energies[s] = hE[s];
-    }
-  };
-  const long nmax = batch_all_small(pot, nSystems, off.data());
-  if (nmax >= 0 && !zbl)  // packing of chunk k+1 overlaps the copies and kernels of chunk k
-    return batch_pipeline(pot, nSystems, off.data(), nmax, hp, eam ? hz : nullptr, hbx, hF, hE, statuses, pack,
-                          unpack);
-  pack(0, nSystems);
-  int st = rgpot_b200_force_batch_packed(pot, nSystems, off.data(), hp, eam ? hz : nullptr, hbx, hF, hE, statuses);
-  if (st >= kStatusCuda) return st;
-  unpack(0, nSystems);
+  const size_t parts = shards_for(pot, nSystems, before[nSystems]);
+  if (parts > 1 && !zbl) {
+    const std::vector<size_t> cut = cut_by_atoms(nSystems, [&](size_t s) { return before[s]; }, parts);
+    return run_on_shards(pot, cut, [&](RgpotB200Pot* sp, size_t s0, size_t s1) {
+      return force_batch_one(sp, s1 - s0, nAtoms + s0, positions + s0, atomicNrs ? atomicNrs + s0 : nullptr,
+                             boxes ? boxes + s0 : nullptr, forces + s0, energies + s0,
+                             statuses ? statuses + s0 : nullptr);
+    });
+  }
+  RgpotB200Pot* target = pot->shards.empty() ? pot : pot->shards[0].pot;
+  DevGuard g(target->device);
+  if (g.err != cudaSuccess) return fail(pot, kStatusCuda, std::string("CUDA failure: ") + cudaGetErrorString(g.err));
+  target->msg_sys_base = 0;
+  const int st = force_batch_one(target, nSystems, nAtoms, positions, atomicNrs, boxes, forces, energies, statuses);
+  if (target != pot) pot->last_error = target->last_error;
   return st;
 }
 

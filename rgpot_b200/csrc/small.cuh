@@ -28,6 +28,7 @@ struct SmallArgs {
   int* sys_bad;            // per-system {first bad atom, its Z} (2 ints)
   int nsys;
   int maxnb;               // neighbor-list capacity per atom (EAM)
+  int z_shared;            // homogeneous batch: Z holds the atomic numbers of ONE system, shared by all
   int cluster;             // LJ: free boundaries
   double u0, psi2, shiftU, cutoff;  // LJ
   int morse;                        // 1 Morse, 2 ZBL instead of LJ
@@ -50,7 +51,7 @@ k_lj_small(SmallArgs a) {
   int* tp = reinterpret_cast<int*>(smem + 3 * n);  // ZBL: type index per atom
   for (int t = threadIdx.x; t < 3 * n; t += blockDim.x) px[t] = a.pos[3 * base + t];
   if (a.morse == 2)
-    for (int t = threadIdx.x; t < n; t += blockDim.x) tp[t] = a.Z[base + t];
+    for (int t = threadIdx.x; t < n; t += blockDim.x) tp[t] = a.Z[(a.z_shared ? 0 : base) + t];
 
   // fold parameters: PairListCache.hpp:176-184 ; LJClusterPot.cc:46-55 (no fold at all)
   LJParams p;
@@ -103,7 +104,10 @@ k_lj_small(SmallArgs a) {
     a.F[3 * (base + i) + 2] = fz;
   }
   const double bs = block_sum(e, sh32);
-  if (threadIdx.x == 0) a.E[sys] = bs;
+  if (threadIdx.x == 0) {
+    a.E[sys] = bs;
+    a.sys_flags[sys] = 0u;  // (every exit of the batch kernels writes the flag word: no reset copy needed)
+  }
 }
 
 // ---------------------------------------------------------------------------------------- CuH2
@@ -211,6 +215,7 @@ k_eam_small(SmallArgs a) {
 
   const int sys = blockIdx.x;
   const long long base = a.off[sys];
+  const long long zbase = a.z_shared ? 0 : base;
   const int n = (int)(a.off[sys + 1] - base);
   const int maxnb = a.maxnb;
   const int lane = threadIdx.x & 31;
@@ -271,7 +276,7 @@ k_eam_small(SmallArgs a) {
     pos3[3 * i + 1] = y;
     pos3[3 * i + 2] = z;
     cnt[i] = 0;
-    const int zn = M == EAM_AL ? 29 : a.Z[base + i];  // EAM-Al is single-species: atomic numbers are not read
+    const int zn = M == EAM_AL ? 29 : a.Z[zbase + i];  // EAM-Al is single-species: atomic numbers are not read
     int sp = 0;
     if (zn == 29) {
       sp = 0;
@@ -317,7 +322,7 @@ k_eam_small(SmallArgs a) {
       a.sys_flags[sys] = blk_flags;
       a.sys_bad[2 * sys] = blk_bad[0];
       a.sys_bad[2 * sys + 1] =
-          ((blk_flags & kFlagForeignZ) && blk_bad[0] != INT_MAX) ? a.Z[base + blk_bad[0]] : 0;
+          ((blk_flags & kFlagForeignZ) && blk_bad[0] != INT_MAX) ? a.Z[zbase + blk_bad[0]] : 0;
     }
     return;
   }

@@ -149,11 +149,26 @@ class _EnginePot:
     _type = PotType.LJ
 
     def __init__(self, u0=1.0, cutoff=15.0, psi=1.0, device: int = -1, lj_all_images: bool = False,
-                 morse=None, zbl=None):
+                 morse=None, zbl=None, devices=None, host_threads: int = 0):
         self._lib = _lib.lib()
         cfg = _lib.Config()
         self._lib.rgpot_b200_default_config(self._kind, C.byref(cfg))
         cfg.device = int(device)
+        cfg.host_threads = int(host_threads)
+        # batches on several GPUs of the box through ONE call (RgpotB200Config.devices): a list of
+        # ordinals, or "all"
+        if isinstance(devices, str):
+            if devices != "all":
+                raise ValueError('devices must be a list of CUDA ordinals or "all"')
+            cfg.device = -2
+        elif devices is not None:
+            devices = [int(d) for d in devices]
+            if not 1 <= len(devices) <= 16:
+                raise ValueError("devices must name 1 to 16 CUDA ordinals")
+            cfg.device = devices[0]
+            cfg.n_devices = len(devices)
+            for k, d in enumerate(devices):
+                cfg.devices[k] = d
         if self._kind == _lib.KIND_MORSE:
             cfg.morse_De, cfg.morse_a, cfg.morse_re = float(morse.De), float(morse.a), float(morse.re)
             cfg.cutoff = float(morse.cutoff)
@@ -278,6 +293,34 @@ class _EnginePot:
         out = [(float(energies[i]), frc[i], 0.0) for i in range(n)]
         return (out, statuses) if return_statuses else out
 
+    def prepareForceBatch(self, systems, forces=None):
+        """The ``ForceBatch`` a C++ caller hands to ``Potential::forceBatch`` (ForceStructs.hpp:50-54),
+        built once: parallel arrays of pointers to every system's own (separately allocated,
+        pageable) buffers.  ``forceBatchPrepared`` then is one rgpot_b200_force_batch call with no
+        Python marshalling in it."""
+        n = len(systems)
+        pos = [_as_positions(s[0]) for s in systems]
+        typ = [_as_types(s[1], p.shape[0]) for s, p in zip(systems, pos)]
+        box = [_as_box(s[2]) for s in systems]
+        frc = forces if forces is not None else [np.zeros_like(p) for p in pos]
+        fb = {"n": n, "pos": pos, "typ": typ, "box": box, "forces": frc,
+              "natoms": (C.c_size_t * n)(*[p.shape[0] for p in pos]),
+              "pp": (C.c_void_p * n)(*[p.ctypes.data for p in pos]),
+              "zz": (C.c_void_p * n)(*[t.ctypes.data for t in typ]),
+              "bb": (C.c_void_p * n)(*[b.ctypes.data for b in box]),
+              "ff": (C.c_void_p * n)(*[f.ctypes.data for f in frc]),
+              "energies": np.zeros(n), "statuses": np.zeros(n, dtype=np.int32)}
+        return fb
+
+    def forceBatchPrepared(self, fb, check: bool = True) -> int:
+        """Evaluate a prepared ForceBatch in place (forces in fb["forces"], energies in fb["energies"])."""
+        st = self._lib.rgpot_b200_force_batch(self._h, fb["n"], fb["natoms"], fb["pp"], fb["zz"], fb["bb"],
+                                              fb["ff"], fb["energies"].ctypes.data, fb["statuses"].ctypes.data)
+        if st != 0 and check:
+            self._raise(st)
+        self.force_calls += fb["n"]
+        return int(st)
+
     def forceBatchPacked(self, offsets, positions, atom_types, boxes, forces=None, energies=None,
                          statuses=None):
         """Back-to-back layout (rgpot_b200_force_batch_packed); buffers may be pinned arrays from
@@ -327,7 +370,9 @@ class _EnginePot:
             self._raise(s)
 
     def sync_status(self) -> int:
-        return int(self._lib.rgpot_b200_sync_status(self._h))
+        st = int(self._lib.rgpot_b200_sync_status(self._h))
+        self._inflight = None
+        return st
 
     def force_torch(self, positions, atom_types, box, sync: bool = True):
         """torch interop: `positions` a CUDA float64 (n, 3) tensor, `atom_types` a
@@ -348,6 +393,9 @@ class _EnginePot:
         energy = torch.empty(1, dtype=torch.float64, device=positions.device)
         stream = torch.cuda.current_stream(positions.device).cuda_stream
         self.force_device(positions, atom_types, box, forces, energy, stream, sync=sync)
+        # the engine may re-read its inputs in sync_status (include/rgpot_b200.h, *_device lifetime
+        # rule): the converted tensors must outlive this call when it only enqueues
+        self._inflight = None if sync else (positions, atom_types, forces, energy)
         self.force_calls += 1
         return (float(energy.item()) if sync else energy), forces
 
@@ -430,10 +478,11 @@ class LJPot(_EnginePot):
 
     _kind, _label, _type = _lib.KIND_LJ, "LJ", PotType.LJ
 
-    def __init__(self, config: LJConfig | None = None, device: int = -1, all_images: bool = False):
+    def __init__(self, config: LJConfig | None = None, device: int = -1, all_images: bool = False,
+                 devices=None, host_threads: int = 0):
         c = config or LJConfig()
         self._config = c
-        super().__init__(c.u0, c.cutoff, c.psi, device, all_images)
+        super().__init__(c.u0, c.cutoff, c.psi, device, all_images, devices=devices, host_threads=host_threads)
 
     def config(self) -> LJConfig:
         return self._config
@@ -494,8 +543,8 @@ class CuH2Pot(_EnginePot):
 
     _kind, _label, _type = _lib.KIND_CUH2, "CuH2", PotType.CuH2
 
-    def __init__(self, device: int = -1):
-        super().__init__(device=device)
+    def __init__(self, device: int = -1, devices=None, host_threads: int = 0):
+        super().__init__(device=device, devices=devices, host_threads=host_threads)
 
 
 class EAMAlPot(_EnginePot):
@@ -609,3 +658,10 @@ def pinned_empty(shape, dtype=np.float64) -> np.ndarray:
 
 def measure_fp64_tflops(device: int = -1, iters: int = 20000) -> float:
     return float(_lib.lib().rgpot_b200_measure_fp64_tflops(device, iters))
+
+
+def measure_copy_gbs(devices, h2d_bytes: int, d2h_bytes: int, reps: int = 3) -> float:
+    """Aggregate pinned host<->device copy rate of `devices` (GB/s), both directions and all devices at
+    once (rgpot_b200_measure_copy_gbs): what bounds every end-to-end batch number on this box."""
+    devs = (C.c_int * len(devices))(*[int(d) for d in devices])
+    return float(_lib.lib().rgpot_b200_measure_copy_gbs(devs, len(devices), int(h2d_bytes), int(d2h_bytes), int(reps)))

@@ -1,4 +1,5 @@
 """The C-ABI library loads and exports every symbol include/*.h declares (no compute)."""
+import ctypes as C
 import os
 import re
 
@@ -37,7 +38,8 @@ def test_header_symbols_are_exported(engine):
 
 
 def test_abi_version_and_defaults(engine):
-    assert engine.rgpot_b200_abi_version() == 2
+    assert engine.rgpot_b200_abi_version() == 3
+    assert C.sizeof(_lib.Config) == 160  # RgpotB200Config incl. the device list (ABI 3)
     cfg = _lib.Config()
     engine.rgpot_b200_default_config(_lib.KIND_LJ, cfg)
     assert (cfg.u0, cfg.cutoff, cfg.psi, cfg.device) == (1.0, 15.0, 1.0, -1)  # LJPot.hpp:30-34
