@@ -69,6 +69,9 @@ struct TileOut {
   unsigned short* pool;
   unsigned long long* lref;
   unsigned long long pool_cap;  // entries
+  // tile kernels (tile.cu): the pool holds the survivor bit masks of a 16-atom pass, word w of lane l
+  // at chunk + 32 w + l; lref[sorted index of the pass's first atom] = chunk, kNoList = search again
+  unsigned* poolw;
 };
 constexpr unsigned long long kNoList = ~0ull;
 

@@ -32,7 +32,7 @@ RB_HD double dkey_inv(unsigned long long k) {
 }
 
 // mm[0..2] = min keys, mm[3..5] = max keys (pre-initialised to ~0 / 0)
-__global__ void k_bbox(const double* __restrict__ pos, int n, unsigned long long* __restrict__ mm) {
+static __global__ void k_bbox(const double* __restrict__ pos, int n, unsigned long long* __restrict__ mm) {
   unsigned long long lo[3] = {~0ull, ~0ull, ~0ull}, hi[3] = {0ull, 0ull, 0ull};
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
 #pragma unroll
@@ -83,7 +83,7 @@ RB_D void locate(const Box& box, const Grid& g, double x, double y, double z, in
   }
 }
 
-__global__ void k_bin(const double* __restrict__ pos, int n, Box box, Grid g,
+static __global__ void k_bin(const double* __restrict__ pos, int n, Box box, Grid g,
                       int* __restrict__ cell_of, int* __restrict__ rank, int* __restrict__ ashift,
                       int* __restrict__ counts, Status* __restrict__ st) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -114,7 +114,7 @@ __global__ void k_bin(const double* __restrict__ pos, int n, Box box, Grid g,
 constexpr int kScanBlock = 1024;
 constexpr int kScanItems = 4;  // per thread -> 4096 cells per block
 
-__global__ void k_scan_partial(const int* __restrict__ counts, int n, int* __restrict__ block_sums) {
+static __global__ void k_scan_partial(const int* __restrict__ counts, int n, int* __restrict__ block_sums) {
   __shared__ int warp_sums[32];
   const int base = blockIdx.x * kScanBlock * kScanItems;
   int v = 0;
@@ -134,7 +134,7 @@ __global__ void k_scan_partial(const int* __restrict__ counts, int n, int* __res
 
 // starts[c] = exclusive prefix of counts; starts[n] = total.  Every block adds up the sums of the
 // blocks before it on its own (a few hundred integers at most) instead of waiting for a scan launch.
-__global__ void k_scan_final(const int* __restrict__ counts, int n, const int* __restrict__ block_sums,
+static __global__ void k_scan_final(const int* __restrict__ counts, int n, const int* __restrict__ block_sums,
                              int* __restrict__ starts) {
   __shared__ int sh[kScanBlock];
   __shared__ int wsum[32];
@@ -178,7 +178,7 @@ __global__ void k_scan_final(const int* __restrict__ counts, int n, const int* _
 }
 
 // ---- scatter + deterministic per-cell order --------------------------------------------------
-__global__ void k_scatter(const int* __restrict__ cell_of, const int* __restrict__ rank,
+static __global__ void k_scatter(const int* __restrict__ cell_of, const int* __restrict__ rank,
                           const int* __restrict__ starts, int n, int* __restrict__ order) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) order[starts[cell_of[i]] + rank[i]] = i;
@@ -187,7 +187,7 @@ __global__ void k_scatter(const int* __restrict__ cell_of, const int* __restrict
 // deterministic order inside a cell: every atom finds its rank among the atoms of its cell (the
 // number of cell mates with a smaller original index) and moves there.  One thread per atom, so
 // the cost does not depend on how few cells there are.
-__global__ void k_cell_order(const int* __restrict__ starts, const int* __restrict__ cell_of,
+static __global__ void k_cell_order(const int* __restrict__ starts, const int* __restrict__ cell_of,
                              const int* __restrict__ order_in, int n, int* __restrict__ order_out) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= n) return;
@@ -201,7 +201,7 @@ __global__ void k_cell_order(const int* __restrict__ starts, const int* __restri
 
 // k_cell_order and k_gather_sorted in one pass: the atom finds its rank inside its cell and writes
 // its sorted record there directly
-__global__ void k_order_gather(const double* __restrict__ pos, const int* __restrict__ Z,
+static __global__ void k_order_gather(const double* __restrict__ pos, const int* __restrict__ Z,
                                const int* __restrict__ starts, const int* __restrict__ cell_of,
                                const int* __restrict__ order_in, const int* __restrict__ ashift, int n,
                                int check_z, double4* __restrict__ spos, int* __restrict__ scell,
@@ -237,7 +237,7 @@ __global__ void k_order_gather(const double* __restrict__ pos, const int* __rest
 }
 
 // sorted records; species from atomic numbers (rgpot_cuh2.f90:463-489 classify) when check_z
-__global__ void k_gather_sorted(const double* __restrict__ pos, const int* __restrict__ Z,
+static __global__ void k_gather_sorted(const double* __restrict__ pos, const int* __restrict__ Z,
                                 const int* __restrict__ order, const int* __restrict__ cell_of,
                                 const int* __restrict__ ashift, int n, int check_z,
                                 double4* __restrict__ spos, int* __restrict__ scell,
@@ -269,7 +269,7 @@ __global__ void k_gather_sorted(const double* __restrict__ pos, const int* __res
 
 // ---- species bookkeeping for table-driven pair potentials (ZBL) on device-resident input ---------
 // which atomic numbers occur (bit z of an 8-word bitmap; bit 0 of word 8 flags a number outside 0..255)
-__global__ void k_species_present(const int* __restrict__ Z, int n, unsigned* __restrict__ bitmap) {
+static __global__ void k_species_present(const int* __restrict__ Z, int n, unsigned* __restrict__ bitmap) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const int z = Z[i];
     if (z < 0 || z > 255)
@@ -280,7 +280,7 @@ __global__ void k_species_present(const int* __restrict__ Z, int n, unsigned* __
 }
 
 // atomic number -> type index through a 256-entry table
-__global__ void k_map_types(const int* __restrict__ Z, int n, const int* __restrict__ lut, int* __restrict__ types) {
+static __global__ void k_map_types(const int* __restrict__ Z, int n, const int* __restrict__ lut, int* __restrict__ types) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) types[i] = lut[Z[i] & 255];
 }
@@ -288,7 +288,7 @@ __global__ void k_map_types(const int* __restrict__ Z, int n, const int* __restr
 // ---- deterministic energy reduction --------------------------------------------------------
 // per-block partial sums were written by the force kernels in block order; one block folds them
 // in a fixed tree.  out[0] = sum
-__global__ void k_reduce_partials(const double* __restrict__ partials, int n, double* __restrict__ out) {
+static __global__ void k_reduce_partials(const double* __restrict__ partials, int n, double* __restrict__ out) {
   __shared__ double sh[1024];
   double acc = 0.0;
   for (int i = threadIdx.x; i < n; i += blockDim.x) acc += partials[i];
@@ -304,7 +304,7 @@ __global__ void k_reduce_partials(const double* __restrict__ partials, int n, do
 // long arrays, one launch: block b folds the fixed slice [b * per, (b + 1) * per); the block that
 // finishes last (a ticket in the status word) folds the slice sums the way k_reduce_partials would
 // with 128 threads -- the order of every addition is a function of n alone
-__global__ void k_reduce_slices(const double* __restrict__ partials, int n, int per, double* __restrict__ slice_sums,
+static __global__ void k_reduce_slices(const double* __restrict__ partials, int n, int per, double* __restrict__ slice_sums,
                                 Status* __restrict__ st, double* __restrict__ out) {
   __shared__ double sh[256];
   __shared__ int last;

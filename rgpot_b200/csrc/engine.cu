@@ -28,6 +28,7 @@
 #include "brick.cuh"
 #include "hash.cuh"
 #include "hostpipe.hpp"
+#include "tile_api.hpp"
 
 using namespace rb;
 
@@ -272,6 +273,11 @@ struct RgpotB200Pot {
   int opt_fine = 0;          // 1: never use half-cutoff cells
   int opt_bricks = 1;         // 0: gather kernels only (test hook)
   int opt_handoff = 1;        // EAM brick kernels: the force pass reuses the density pass's survivor lists
+  int opt_tile = 0;           // 1: large systems on the tile kernels (tile.cu, opt-in); 0 = the brick kernels
+  int opt_tile_group = 0;     // cells per group as decimal xyz (0 = automatic)
+  int opt_tile_brick = 0;     // cells per brick as decimal xyz (0 = automatic)
+  int opt_tile_cap = 0;       // staged capacity override (test hook: small values exercise cut boxes / the slow path)
+  int opt_tile_wcap = 0;      // window chunk override
   long opt_fine_min = 20000;  // atoms from which half-cutoff cells are used
   long launches = 0;
   long pool_used = 0;   // survivor-list entries the density pass handed to the force pass
@@ -325,6 +331,7 @@ struct RgpotB200Pot {
     }
   } memo, memo_pending;
   int last_cap_cand = 0, last_cap_list = 0;  // what the last brick plan chose (rgpot_b200_stat)
+  int last_used_tile = 0;                    // the last cell-list call ran on the tile kernels (tile.cu)
   std::string last_error;
 
   // single-system scratch
@@ -720,6 +727,144 @@ int launch_brick(RgpotB200Pot* pot, const GatherArgs& ga, const BrickPlan& bp, c
   return check_launch(pot, what);
 }
 
+// ---- tile kernels (tile.cu): plan and launch ---------------------------------------------------
+// Threshold of the tensor-core prefilter: a superset of the exact accept test.  Staged positions are
+// FP16 offsets from the box centre, |component| <= A, each rounded once (error <= A 2^-11), so a
+// component of the separation is off by <= delta = 2 A 2^-11 and |d~|^2 <= (|d| + sqrt(3) delta)^2;
+// the products are exact in FP32, the seven-term accumulation rounds partial sums of magnitude
+// <= ~8 A^2 (slack term).  Every kept candidate still takes the exact FP64 test.
+float tile_threshold(const Plan& pl, const int bd[3], const int ns[3], double rc) {
+  double A = 0.0;
+  for (int k = 0; k < 3; ++k) {
+    double ext = 0.0;
+    for (int d = 0; d < 3; ++d) {
+      const double comp = pl.box.periodic[d] ? fabs(pl.box.H[3 * d + k]) : (d == k ? pl.box.ext[d] : 0.0);
+      ext += (0.5 * bd[d] + ns[d] + 0.01) * comp / pl.grid.nc[d];
+    }
+    A = std::max(A, ext);
+  }
+  const double delta = 2.0 * A * ldexp(1.0, -11) * 1.001;
+  const double slack = 16.0 * (8.0 * A * A + rc * rc) * ldexp(1.0, -24) + 1.0e-4 * rc * rc * 1.0e-2;
+  const double t = rc * rc + 2.0 * sqrt(3.0) * rc * delta + 3.0 * delta * delta + slack;
+  return (float)(t * (1.0 + 1.0e-6));
+}
+
+bool plan_tiles(RgpotB200Pot* pot, const Plan& pl, long n, double rc, int words, TilePlan& tp) {
+  const Grid& g = pl.grid;
+  for (int k = 0; k < 3; ++k) {
+    if (g.ns_lo[k] != g.ns_hi[k] || g.ns_lo[k] < 1 || g.ns_lo[k] > 2) return false;
+    // a halo cell is at most one image away (an atom's own wrap count of +-1 is folded into the
+    // 5 x 5 x 5 image codes)
+    if (pl.box.periodic[k] && g.nc[k] < g.ns_lo[k]) return false;
+    tp.ns[k] = g.ns_lo[k];
+  }
+  const double mean = (double)n / (double)g.ncells;
+  // cells per group: the shape that tests the fewest candidates per atom with passes of sixteen
+  int best[3] = {1, 1, 1};
+  if (pot->opt_tile_group > 0) {
+    best[0] = std::max(1, std::min({(pot->opt_tile_group / 100) % 10, g.nc[0], 4}));
+    best[1] = std::max(1, std::min({(pot->opt_tile_group / 10) % 10, g.nc[1], 4}));
+    best[2] = std::max(1, std::min({pot->opt_tile_group % 10, g.nc[2], 4}));
+    while (best[0] * best[1] * best[2] > kTileMaxGroupCells) best[2] = std::max(1, best[2] - 1);
+  } else {
+    double best_cost = 1e300;
+    for (int gz = 1; gz <= std::min(4, g.nc[2]); ++gz)
+      for (int gy = 1; gy <= std::min(4, g.nc[1]); ++gy)
+        for (int gx = 1; gx <= std::min(4, g.nc[0]); ++gx) {
+          if (gx * gy * gz > kTileMaxGroupCells) continue;
+          const double m = mean * gx * gy * gz;
+          const double passes = ceil(std::max(m * 1.1, 1.0) / 16.0);
+          const double window = mean * (gx + 2 * tp.ns[0]) * (gy + 2 * tp.ns[1]) * (gz + 2 * tp.ns[2]);
+          // per atom: tensor-core tiles of the search plus the physics' idle quads when a pass is short
+          const double fill = std::min(1.0, m / (16.0 * passes));
+          const double cost = passes * window / std::max(m, 1e-9) + 120.0 / std::max(fill, 0.05);
+          if (cost < best_cost - 1e-9) {
+            best_cost = cost;
+            best[0] = gx;
+            best[1] = gy;
+            best[2] = gz;
+          }
+        }
+  }
+  for (int k = 0; k < 3; ++k) tp.gd[k] = best[k];
+  // cells per brick: two groups a side (eight groups: one per warp), fewer where the grid is narrow
+  int bd[3];
+  for (int k = 0; k < 3; ++k) {
+    int want = 2 * tp.gd[k];
+    if (pot->opt_tile_brick > 0) {
+      const int v = k == 0 ? (pot->opt_tile_brick / 100) % 10 : (k == 1 ? (pot->opt_tile_brick / 10) % 10 : pot->opt_tile_brick % 10);
+      want = std::max(tp.gd[k], (v / tp.gd[k]) * tp.gd[k]);
+    }
+    bd[k] = std::min(want, ((g.nc[k] + tp.gd[k] - 1) / tp.gd[k]) * tp.gd[k]);
+  }
+  for (;;) {
+    const int nhalo = (bd[0] + 2 * tp.ns[0]) * (bd[1] + 2 * tp.ns[1]) * (bd[2] + 2 * tp.ns[2]);
+    if (nhalo <= kTileMaxHalo) {
+      const double fcc = 1.2;
+      int cap = std::min(65000, round_up((int)(nhalo * mean * fcc) + 32, 8));
+      const auto& m = pot->memo;
+      const int seen = m.matches(n, g.nc) ? m.lookup(bd) : 0;
+      if (seen > 0) cap = std::min(65000, round_up((int)(seen * 1.04) + 24, 8));
+      if (pot->opt_tile_cap > 0) cap = round_up(pot->opt_tile_cap, 8);
+      const double window = mean * (tp.gd[0] + 2 * tp.ns[0]) * (tp.gd[1] + 2 * tp.ns[1]) * (tp.gd[2] + 2 * tp.ns[2]);
+      int wcap = std::max(128, std::min(1024, round_up((int)(window * 1.25) + 16, 64)));
+      if (seen > 0) {  // the densest halo met last time, scaled to a window: dense regions of an uneven system
+        const double wfrac = (double)((tp.gd[0] + 2 * tp.ns[0]) * (tp.gd[1] + 2 * tp.ns[1]) * (tp.gd[2] + 2 * tp.ns[2])) / (double)nhalo;
+        wcap = std::max(wcap, std::min(1024, round_up((int)(seen * wfrac * 1.1) + 16, 64)));
+      }
+      if (pot->opt_tile_wcap > 0) wcap = std::max(64, round_up(pot->opt_tile_wcap, 64));
+      const unsigned smem = tile_smem_bytes(cap, wcap, kTileThreads, words);
+      if ((size_t)smem + 12 * 1024 <= pot->smem_optin) {
+        for (int k = 0; k < 3; ++k) {
+          tp.bd[k] = bd[k];
+          tp.nb[k] = (g.nc[k] + bd[k] - 1) / bd[k];
+        }
+        tp.nbricks = tp.nb[0] * tp.nb[1] * tp.nb[2];
+        tp.cap_cand = cap;
+        tp.wcap = wcap;
+        tp.threads = kTileThreads;
+        tp.smem = smem;
+        tp.thr2 = tile_threshold(pl, bd, tp.ns, rc);
+        auto& mp = pot->memo_pending;
+        mp.n = n;
+        for (int k = 0; k < 3; ++k) {
+          mp.nc[k] = g.nc[k];
+          mp.bd[k] = bd[k];
+        }
+        mp.max_halo = 0;
+        pot->last_cap_cand = cap;
+        pot->last_cap_list = wcap;
+        return true;
+      }
+    }
+    // too large for shared memory: shrink the brick by one group, largest direction first
+    int kmax = -1;
+    for (int k = 0; k < 3; ++k)
+      if (bd[k] > tp.gd[k] && (kmax < 0 || bd[k] > bd[kmax])) kmax = k;
+    if (kmax < 0) return false;
+    bd[kmax] -= tp.gd[kmax];
+  }
+}
+
+// lower bound on the 16-atom passes of a grid: one per non-empty group at least
+unsigned long long g_min_passes(const Grid& g, const TilePlan& tp) {
+  unsigned long long ng = 1;
+  for (int k = 0; k < 3; ++k) ng *= (unsigned long long)((g.nc[k] + tp.gd[k] - 1) / tp.gd[k]);
+  return ng;
+}
+
+int launch_tile(RgpotB200Pot* pot, int tile_pot, const GatherArgs& ga, const TilePlan& tp, const TileOut& to,
+                cudaStream_t st, const char* what) {
+  pot->last_used_tile = 1;
+  const cudaError_t e = rb::tile_launch(tile_pot, ga, tp, to, st);
+  if (e != cudaSuccess) {
+    pot->last_error = std::string("CUDA launch failure (") + what + "): " + cudaGetErrorString(e);
+    return kStatusCuda;
+  }
+  pot->launches++;
+  return 0;
+}
+
 // fixed-order fold of the energy partials: long arrays in two stages
 int reduce_energy(RgpotB200Pot* pot, double* d_part, int n, double* d_E, cudaStream_t st) {
   if (n > 4096) {
@@ -743,6 +888,7 @@ int run_cell_path(RgpotB200Pot* pot, long n, const double* d_pos, const int* d_Z
   // nlist_rc > 0: a plain vesin-shaped neighbor list of that cutoff (every image, self images kept),
   // whatever potential the handle was created for (rgpot_b200_neighbor_list)
   const bool nlist = nlist_rc > 0.0 && emit != nullptr;
+  pot->last_used_tile = 0;
   if (!pot->opt_bricks) allow_tile = false;
   const int kind = nlist ? RGPOT_B200_LJ : pot->cfg.kind;
   const bool eam = is_eam(kind);
@@ -918,12 +1064,38 @@ int run_cell_path(RgpotB200Pot* pot, long n, const double* d_pos, const int* d_Z
   double* d_part = pot->partials.as<double>();  // every atom's energy is written by exactly one kernel
   if (eam || fehe) {
     BrickPlan bp{};
-    const bool tile_ok = allow_tile && plan_bricks(pot, pl, n, rc, fehe ? 5 : 4, bp);
-    if (tile_ok) {
+    TilePlan tpl{};
+    if (allow_tile && pot->opt_tile && plan_tiles(pot, pl, n, rc, fehe ? 5 : 4, tpl)) {
+      // tile kernels (tile.cu): density + embedding, then forces; the gather kernels stand by for atoms
+      // more than one cell vector outside the cell
+      TileOut to{d_F, d_part, pot->dfd.as<double>(), pot->eemb.as<double>(), fehe ? pot->dfs.as<double>() : nullptr,
+                 d_st, nullptr, nullptr, 0, nullptr};
+      if (pot->opt_handoff) {
+        // survivor masks handed from the density to the force pass: 32 lanes x (window / 64) words per
+        // 16-atom pass; a shortfall only makes some passes search again
+        const unsigned long long per_pass = 32ull * (unsigned long long)(tpl.wcap / 64);
+        const unsigned long long want = ((unsigned long long)n / 6ull + (unsigned long long)g_min_passes(pl.grid, tpl)) * per_pass + 4096ull;
+        const unsigned long long cap = std::min(want, 1ull << 31);
+        if (pot->listpool.reserve(sizeof(unsigned) * cap) == cudaSuccess &&
+            pot->listref.reserve(sizeof(unsigned long long) * (size_t)n) == cudaSuccess) {
+          to.poolw = pot->listpool.as<unsigned>();
+          to.lref = pot->listref.as<unsigned long long>();
+          to.pool_cap = cap;
+        } else {
+          cudaGetLastError();
+        }
+      }
+      int ls = launch_tile(pot, fehe ? TILE_FEHE_DENSITY : (al ? TILE_AL_DENSITY : TILE_EAM_DENSITY), ga, tpl, to, st, "k_tile<density>");
+      if (ls) return ls;
+      ls = launch_tile(pot, fehe ? TILE_FEHE_FORCE : (al ? TILE_AL_FORCE : TILE_EAM_FORCE), ga, tpl, to, st, "k_tile<force>");
+      if (ls) return ls;
+      ga.only_if_big_shift = 1;
+      nblk = nblk_standby;
+    } else if (allow_tile && plan_bricks(pot, pl, n, rc, fehe ? 5 : 4, bp)) {
       // brick kernels; the gather kernels cover atoms outside the cell (per-pair image shifts) --
       // each side returns at once when the binning flag is not its own
       TileOut to{d_F, d_part, pot->dfd.as<double>(), pot->eemb.as<double>(), fehe ? pot->dfs.as<double>() : nullptr,
-                 d_st, nullptr, nullptr, 0};
+                 d_st, nullptr, nullptr, 0, nullptr};
       if (pot->opt_handoff) {
         // survivor lists handed from the density to the force pass: room for every thread's list at
         // its capacity in half-filled warps (a shortfall only makes some threads search again)
@@ -969,10 +1141,19 @@ int run_cell_path(RgpotB200Pot* pot, long n, const double* d_pos, const int* d_Z
   } else if (pl.geo == GEO_IMAGES) {
     k_lj_gather<GEO_IMAGES><<<nblk, 128, 0, st>>>(ga, d_F, d_part);
     LAUNCH_CHECK(pot, "k_lj_gather<images>");
+  } else if (TilePlan tpl{}; pl.geo == GEO_LJ_SHIFT && allow_tile && pot->opt_tile && plan_tiles(pot, pl, n, rc, 3, tpl)) {
+    // tile kernel (tile.cu); the literal-fold gather kernel covers atoms far outside the cell
+    TileOut to{d_F, d_part, nullptr, nullptr, nullptr, d_st, nullptr, nullptr, 0, nullptr};
+    int ls = launch_tile(pot, pl.lj.morse ? TILE_PAIR : TILE_LJ, ga, tpl, to, st, "k_tile<lj>");
+    if (ls) return ls;
+    ga.only_if_big_shift = 1;
+    k_lj_gather<GEO_LJ_SHIFT><<<nblk_standby, 128, 0, st>>>(ga, d_F, d_part);
+    LAUNCH_CHECK(pot, "k_lj_gather<shift>");
+    return reduce_energy(pot, d_part, (int)n, d_E, st);
   } else if (BrickPlan bp{}; pl.geo == GEO_LJ_SHIFT && allow_tile && plan_bricks(pot, pl, n, rc, 3, bp)) {
     // brick kernel; the literal-fold gather kernel covers the (rare) case of atoms outside the
     // cell -- each of the two returns at once when the binning flag is not its own
-    TileOut to{d_F, d_part, nullptr, nullptr, nullptr, d_st, nullptr, nullptr, 0};
+    TileOut to{d_F, d_part, nullptr, nullptr, nullptr, d_st, nullptr, nullptr, 0, nullptr};
     int ls = pl.lj.morse ? launch_brick<TILE_PAIR>(pot, ga, bp, to, st, "k_brick<pair>")
                          : launch_brick<TILE_LJ>(pot, ga, bp, to, st, "k_brick<lj>");
     if (ls) return ls;
@@ -1365,14 +1546,16 @@ static RgpotB200Pot* create_on_device(const RgpotB200Config* cfg, int dev, std::
     for (int j = 0; j < 64; ++j) tab[j] = exp2((double)j / 64.0);
     if (cudaMemcpyToSymbol(c_exp2tab, tab, sizeof tab) != cudaSuccess ||
         (cfg->kind == RGPOT_B200_EAM_AL ? cudaMemcpyToSymbol(c_eam_al, &p, sizeof p)
-                                        : cudaMemcpyToSymbol(c_eam, &p, sizeof p)) != cudaSuccess) {
+                                        : cudaMemcpyToSymbol(c_eam, &p, sizeof p)) != cudaSuccess ||
+        rb::tile_upload_constants(cfg->kind == RGPOT_B200_EAM_AL ? 1 : 0, &p, sizeof p, tab) != cudaSuccess) {
       delete pot;
       msg = "rgpot_b200_create: cannot upload the EAM coefficients";
       return nullptr;
     }
   } else if (cfg->kind == RGPOT_B200_FEHE) {
     const FeHeParams p = make_fehe_params();
-    if (cudaMemcpyToSymbol(c_fehe, &p, sizeof p) != cudaSuccess) {
+    if (cudaMemcpyToSymbol(c_fehe, &p, sizeof p) != cudaSuccess ||
+        rb::tile_upload_constants(2, &p, sizeof p, nullptr) != cudaSuccess) {
       delete pot;
       msg = "rgpot_b200_create: cannot upload the Fe-He coefficients";
       return nullptr;
@@ -1486,6 +1669,7 @@ long rgpot_b200_stat(RgpotB200Pot* pot, const char* key) {
   if (strcmp(key, "brick") == 0) return pot->memo.bd[0] * 100 + pot->memo.bd[1] * 10 + pot->memo.bd[2];
   if (strcmp(key, "cap_cand") == 0) return pot->last_cap_cand;
   if (strcmp(key, "cap_list") == 0) return pot->last_cap_list;
+  if (strcmp(key, "tile_used") == 0) return pot->last_used_tile;
   if (strncmp(key, "prof", 4) == 0 && key[4] >= '0' && key[4] <= '3') return pot->prof[key[4] - '0'];
   return -1;
 }
@@ -1532,6 +1716,26 @@ int rgpot_b200_set_option(RgpotB200Pot* pot, const char* key, long value) {
   }
   if (strcmp(key, "brick_threads") == 0) {
     pot->opt_threads = (int)value;
+    return 0;
+  }
+  if (strcmp(key, "tile") == 0) {
+    pot->opt_tile = (int)value;
+    return 0;
+  }
+  if (strcmp(key, "tile_group") == 0) {
+    pot->opt_tile_group = (int)value;
+    return 0;
+  }
+  if (strcmp(key, "tile_brick") == 0) {
+    pot->opt_tile_brick = (int)value;
+    return 0;
+  }
+  if (strcmp(key, "tile_cap") == 0) {
+    pot->opt_tile_cap = (int)value;
+    return 0;
+  }
+  if (strcmp(key, "tile_wcap") == 0) {
+    pot->opt_tile_wcap = (int)value;
     return 0;
   }
   return kStatusArgs;
@@ -1844,7 +2048,10 @@ static int upload_array(RgpotB200Pot* pot, void* d_dst, const void* h_src, size_
     if (i >= (size_t)kRingSlots) CU_TRY(pot, cudaEventSynchronize(pot->ring_ev[slot]));
     char* dst = ring + (size_t)slot * kRingSlice;
     const char* src = static_cast<const char*>(h_src) + o;
-    team->run(len, 256u << 10, [&](size_t b0, size_t b1) { memcpy(dst + b0, src + b0, b1 - b0); });
+    team->run(len, 64u << 10, [&](size_t b0, size_t b1) {
+      rb::copy_stream(dst + b0, src + b0, b1 - b0);
+      rb::copy_stream_fence();
+    });
     CU_TRY(pot, cudaMemcpyAsync(static_cast<char*>(d_dst) + o, dst, len, cudaMemcpyHostToDevice, st));
     CU_TRY(pot, cudaEventRecord(pot->ring_ev[slot], st));
   }
@@ -1877,7 +2084,10 @@ static int download_array(RgpotB200Pot* pot, void* h_dst, const void* d_src, siz
     CU_TRY(pot, cudaEventSynchronize(pot->ring_ev[slot]));
     const char* src = ring + (size_t)slot * kRingSlice;
     char* dst = static_cast<char*>(h_dst) + o;
-    team->run(len, 256u << 10, [&](size_t b0, size_t b1) { memcpy(dst + b0, src + b0, b1 - b0); });
+    team->run(len, 64u << 10, [&](size_t b0, size_t b1) {
+      rb::copy_stream(dst + b0, src + b0, b1 - b0);
+      rb::copy_stream_fence();
+    });
     if (i + kRingSlots < nslices) CU_TRY(pot, issue(i + kRingSlots));
   }
   return 0;
@@ -2671,7 +2881,7 @@ static int batch_staged(RgpotB200Pot* pot, size_t nsys, const size_t* off, PosOf
       for (size_t s = c0 + b; s < c0 + e; ++s) {
         const size_t n = off[s + 1] - off[s];
         if (n > 0) {
-          memcpy(hp + 3 * off[s], pos_of(s), sizeof(double) * 3 * n);
+          rb::copy_stream(hp + 3 * off[s], pos_of(s), sizeof(double) * 3 * n);
           if (eam) {
             const int* z = Z_of(s);
             if (z0 && n == n0 && (z == z0 || memcmp(z, z0, sizeof(int) * n) == 0)) {
@@ -2687,6 +2897,7 @@ static int batch_staged(RgpotB200Pot* pot, size_t nsys, const size_t* off, PosOf
         const double* bx = box_of(s);
         memcpy(hbx + 9 * s, bx ? bx : kFreeBox, sizeof(double) * 9);
       }
+      rb::copy_stream_fence();  // the DMA engine reads the staging next
       if (!eq) same.store(0, std::memory_order_relaxed);
     });
     if (eam && z0 && !same.load()) {  // a mixed chunk uploads its own atomic numbers: fill in the skipped ones
@@ -2703,9 +2914,10 @@ static int batch_staged(RgpotB200Pot* pot, size_t nsys, const size_t* off, PosOf
     team->run(c1 - c0, 32, [&](size_t b, size_t e) {
       for (size_t s = c0 + b; s < c0 + e; ++s) {
         const size_t n = off[s + 1] - off[s];
-        if (n > 0) memcpy(F_of(s), hF + 3 * off[s], sizeof(double) * 3 * n);
+        if (n > 0) rb::copy_stream(F_of(s), hF + 3 * off[s], sizeof(double) * 3 * n);
         energies[s] = hE[s];
       }
+      rb::copy_stream_fence();
     });
   };
   std::function<const int*(size_t)> host_Z_of;

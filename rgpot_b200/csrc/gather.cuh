@@ -249,7 +249,7 @@ k_eam_force(GatherArgs a, const double* __restrict__ dfd_sorted,
 // ---- Fe-He (rgpot_fehe.f90:573-620): the three passes on the gather walk ---------------------------
 // First correct CUDA path of this potential: thread per atom, all system sizes (the brick and
 // batch kernels do not carry its two density channels yet).
-__global__ void __launch_bounds__(128)
+static __global__ void __launch_bounds__(128)
 k_fehe_density(GatherArgs a, double* __restrict__ dfd_sorted, double* __restrict__ dfs_sorted,
                double* __restrict__ eemb_sorted) {
   if (a.only_if_big_shift && !(a.st_in->flags & kFlagBigShift)) return;
@@ -272,7 +272,7 @@ k_fehe_density(GatherArgs a, double* __restrict__ dfd_sorted, double* __restrict
   }
 }
 
-__global__ void __launch_bounds__(128)
+static __global__ void __launch_bounds__(128)
 k_fehe_force(GatherArgs a, const double* __restrict__ dfd_sorted, const double* __restrict__ dfs_sorted,
              const double* __restrict__ eemb_sorted, double* __restrict__ F, double* __restrict__ eatom) {
   if (a.only_if_big_shift && !(a.st_in->flags & kFlagBigShift)) return;

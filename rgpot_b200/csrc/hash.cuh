@@ -220,7 +220,7 @@ struct KeyArgs {
   size_t nsys;
 };
 
-__global__ void __launch_bounds__(256, 4) k_cache_keys(const KeyArgs a) {
+static __global__ void __launch_bounds__(256, 4) k_cache_keys(const KeyArgs a) {
   __shared__ uint64_t sw[24];
   if (threadIdx.x < 24) sw[threadIdx.x] = rd64(c_xxh_secret + 8 * threadIdx.x);
   __syncthreads();

@@ -16,6 +16,10 @@
 #include <string.h>
 #include <unistd.h>
 
+#if defined(__x86_64__)
+#include <emmintrin.h>
+#endif
+
 #include <atomic>
 #include <condition_variable>
 #include <functional>
@@ -237,6 +241,50 @@ class Worker {
   bool has_ = false, busy_ = false, stop_ = false, pinned_ = false;
   cpu_set_t cpus_;
 };
+
+// memcpy whose stores bypass the cache (SSE2 streaming stores, part of baseline x86-64).  Packing a
+// batch moves hundreds of megabytes that the CPU never reads again: an ordinary store first reads the
+// destination line into the cache (read for ownership), so the copy costs three memory transfers per
+// byte where a streaming store costs two -- and the host's memory system, shared with the GPUs' DMA,
+// is what bounds the pageable entry points.  Call copy_stream_fence() before anything else (a DMA
+// engine, another thread) reads the destination.
+inline void copy_stream(void* dst, const void* src, size_t n) {
+#if defined(__x86_64__)
+  char* d = static_cast<char*>(dst);
+  const char* s = static_cast<const char*>(src);
+  if (n < 256) {
+    memcpy(d, s, n);
+    return;
+  }
+  size_t head = (16 - (reinterpret_cast<uintptr_t>(d) & 15)) & 15;
+  if (head) {
+    memcpy(d, s, head);
+    d += head;
+    s += head;
+    n -= head;
+  }
+  size_t blocks = n / 64;
+  for (; blocks; --blocks, d += 64, s += 64) {
+    const __m128i a = _mm_loadu_si128(reinterpret_cast<const __m128i*>(s));
+    const __m128i b = _mm_loadu_si128(reinterpret_cast<const __m128i*>(s + 16));
+    const __m128i c = _mm_loadu_si128(reinterpret_cast<const __m128i*>(s + 32));
+    const __m128i e = _mm_loadu_si128(reinterpret_cast<const __m128i*>(s + 48));
+    _mm_stream_si128(reinterpret_cast<__m128i*>(d), a);
+    _mm_stream_si128(reinterpret_cast<__m128i*>(d + 16), b);
+    _mm_stream_si128(reinterpret_cast<__m128i*>(d + 32), c);
+    _mm_stream_si128(reinterpret_cast<__m128i*>(d + 48), e);
+  }
+  n &= 63;
+  if (n) memcpy(d, s, n);
+#else
+  memcpy(dst, src, n);
+#endif
+}
+inline void copy_stream_fence() {
+#if defined(__x86_64__)
+  _mm_sfence();
+#endif
+}
 
 // Is this host pointer page-locked (cudaMallocHost / cudaHostRegister)?  Pageable memory cannot be
 // DMA'd: it goes through pinned staging.

@@ -40,7 +40,7 @@ struct SmallArgs {
 };
 
 // ------------------------------------------------------------------------------------------ LJ
-__global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(256)
 k_lj_small(SmallArgs a) {
   extern __shared__ double smem[];
   __shared__ double sh32[32];

@@ -495,6 +495,7 @@ BRICK_VARIANTS = [
 
 def _with_options(pot, opts):
     pot.set_option("fine_min", 0)
+    pot.set_option("tile", 0)  # these are the brick kernels' tests (tests/test_gpu_tile.py has the tile kernels')
     for key in ("fine", "brick_list", "brick_slack", "brick", "brick_threads", "brick_tpa"):
         pot.set_option(key, opts.get(key, 0))
 

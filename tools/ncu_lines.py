@@ -35,9 +35,11 @@ def disasm_lines(func_sub):
     tmp = tempfile.mkdtemp()
     subprocess.run(["cuobjdump", "-xelf", "all", os.path.join(ROOT, "rgpot_b200", "librgpot_b200.so")],
                    cwd=tmp, check=True, stdout=subprocess.DEVNULL)
-    cubin = [f for f in os.listdir(tmp) if f.endswith(".cubin")][0]
-    out = subprocess.run(["nvdisasm", "-gi", os.path.join(tmp, cubin)], check=True, capture_output=True,
-                         text=True).stdout
+    # the engine is several translation units: disassemble every cubin, the function is in one of them
+    out = ""
+    for cubin in sorted(f for f in os.listdir(tmp) if f.endswith(".cubin")):
+        out += subprocess.run(["nvdisasm", "-gi", os.path.join(tmp, cubin)], check=True, capture_output=True,
+                              text=True).stdout
     mapping = {}
     in_func, cur, block_open = False, None, False
     for line in out.splitlines():
