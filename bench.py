@@ -4,19 +4,27 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
                     [--workload cuh2_batch|lj_fluid_1m|cuh2_slab_256k] [--configs C]
 
-Headline workload (BASELINE.json configs[4]): a batch of C = 65 536 perturbed copies of the
-218-atom Cu slab + H2 (NEB / dimer images) PER GPU, evaluated by the CuH2 EAM in one engine call.
-A "step" is one pass of the hot path over the batch.  Ranks are independent (no collective on the
-data path): weak scaling, value = total atoms evaluated by all ranks / max-over-ranks time.
+Headline workload (BASELINE.json configs[4]): ONE batch of C = 65 536 perturbed copies of the 218-atom
+Cu slab + H2 (NEB / dimer images) evaluated by the CuH2 EAM, cut across the N GPUs of the box
+(strong scaling: the global batch is fixed).  A "step" is one pass of the hot path over the batch.
 
-  value     device-resident: inputs already in HBM, CUDA events on the launching stream
-  e2e       the same metric through the public host-buffer call (pinned host arrays in, host
-            arrays out), H2D / D2H copies inside the timed region
-  roofline  algorithmic FP64 work of the dominant kernel / measured DFMA peak (measured live
-            here: MEASURED_PEAKS.json carries no FP64 figure), plus the HBM fraction
+  value     device-resident: every rank holds its contiguous range of the batch (rgpot_b200.sharding,
+            balanced by atoms) in HBM; CUDA events on the launching stream, max over ranks
+  e2e       the same batch through the reference-shaped entry: ONE rgpot_b200_force_batch call -- what
+            Potential::forceBatch(const ForceBatch&) hands over: 65 536 separately allocated PAGEABLE
+            systems (CppCore/rgpot/Potential.hpp:225-240) -- made by rank 0, whose engine handle lists
+            all N devices (RgpotB200Config.devices) and drives one host thread + pipeline per GPU;
+            H2D / D2H copies and the packing into pinned staging are inside the timed region.
+            e2e_pinned: the packed entry on page-locked arrays (no host packing); e2e_per_rank: every
+            rank pushes its own range through the pointer entry (process-per-GPU, max over ranks);
+            copy_ceiling: what plain pinned copies of the same bytes reach on these N GPUs at once
+  roofline  algorithmic FP64 work of the dominant kernel / measured DFMA peak (measured live here:
+            MEASURED_PEAKS.json carries no FP64 figure) and / nominal peak, the executed FP64 work from
+            the committed ncu capture beside it, plus the HBM fraction
   cpu_baseline / --impl reference: the reference CPU path (its own vesin neighbor search from
-            oracle/_ref feeding the restated Fortran passes; one process per host core because
-            the reference potential is ProcessSerial) on a bounded sample of the same workload
+            oracle/_ref feeding a C restatement of rgpot_cuh2.f90 -- the Fortran cannot be built here,
+            hence kind "port+ref-vesin"; one process per host core because the reference potential is
+            ProcessSerial) on a bounded sample of the same workload
 """
 from __future__ import annotations
 
@@ -40,6 +48,8 @@ UNIT = "atom-evals/s"
 # algorithmic work per atom-eval (exp counted as 30 flops, FMA as 2)
 FLOPS_PER_ATOM = {"cuh2_batch": 23000.0, "lj_fluid_1m": 8503.0, "cuh2_slab_256k": 41200.0}
 BYTES_PER_ATOM = {"cuh2_batch": 76.0, "lj_fluid_1m": 52.0, "cuh2_slab_256k": 76.0}
+# nominal FP64 vector peak of a B200: 148 SMs x 64 FMA / clk x 2 flop x 1.965 GHz
+FP64_NOMINAL_TF = 148 * 64 * 2 * 1.965e9 / 1e12
 
 
 # ------------------------------------------------------------------------------------- clocks
@@ -120,8 +130,12 @@ def bind_to_gpu_numa_node(local):
     return None
 
 
+_HOST_GROUP = None
+
+
 def dist_setup(n_gpus):
     import torch
+    global _HOST_GROUP
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -130,9 +144,21 @@ def dist_setup(n_gpus):
         import torch.distributed as dist
         torch.cuda.set_device(local)
         dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local))
+        _HOST_GROUP = dist.new_group(backend="gloo")  # waits that must not put a kernel on the GPU
     else:
         torch.cuda.set_device(0)
     return world, rank, local
+
+
+def host_barrier(world):
+    """A barrier that waits on the CPU only.  While rank 0 drives ALL GPUs from one process, the other
+    ranks must not sit in an NCCL barrier: that is a kernel spinning on their GPU, in another process
+    than the one whose kernels it would have to share the GPU with."""
+    import torch
+    torch.cuda.synchronize()
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier(group=_HOST_GROUP)
 
 
 def barrier(world):
@@ -165,41 +191,45 @@ def sum_over_ranks(x, world):
 
 # ------------------------------------------------------------------------------ CPU reference
 def _cpu_worker(args):
-    """One process = one ProcessSerial reference potential looping over its slice."""
-    seed, n_configs, budget_s = args
+    """One process = one ProcessSerial reference potential looping over its slice (a FIXED number of
+    configurations, so every repetition does the same work)."""
+    seed, n_configs = args
     from oracle import pyoracle as po
     from rgpot_b200 import workloads
     offsets, pos, Z, boxes = workloads.cuh2_batch(n_configs, seed=seed)
     use_ref = po.ref_available()
-    done = 0
     t0 = time.perf_counter()
     for s in range(n_configs):
         a, b = int(offsets[s]), int(offsets[s + 1])
         po.cuh2_force(pos[a:b], Z[a:b], boxes[s].reshape(3, 3), use_ref=use_ref)
-        done += b - a
-        if time.perf_counter() - t0 > budget_s:
-            break
-    return done, time.perf_counter() - t0
+    return int(offsets[-1]), time.perf_counter() - t0
 
 
-def cpu_reference_rate(budget_s=12.0, procs=None, configs_per_proc=4000):
-    """atom-evals/s of the reference CPU path on this host: P processes, bounded sample."""
+def cpu_reference_rate(budget_s=12.0, procs=None, reps=3):
+    """atom-evals/s of the reference CPU path on this host: P processes, a bounded sample of a fixed
+    size (calibrated once to about budget_s / reps of work), best of `reps` -- a fork pool timed by
+    its slowest member moves by 30 % from run to run otherwise."""
     import multiprocessing as mp
     from oracle import pyoracle as po
     procs = procs or os.cpu_count() or 1
     ctx = mp.get_context("fork")
-    t0 = time.perf_counter()
     with ctx.Pool(procs) as pool:
-        res = pool.map(_cpu_worker, [(9000 + p, configs_per_proc, budget_s) for p in range(procs)])
-    wall = time.perf_counter() - t0
-    atoms = sum(r[0] for r in res)
-    busy = max(r[1] for r in res)
-    kind = "reference" if po.ref_available() else "port"
-    sample = (f"{atoms // 218} perturbed 218-atom CuH2 configs over {procs} processes, {busy:.1f} s each "
-              f"({'vendored vesin from oracle/_ref + ' if kind == 'reference' else ''}"
+        cal = pool.map(_cpu_worker, [(8000 + p, 40) for p in range(procs)])  # warm-up + calibration
+        per_cfg = max(r[1] for r in cal) / 40.0
+        n_cfg = int(max(40, min(20000, (budget_s / reps) / max(per_cfg, 1e-6))))
+        best, wall = 0.0, 0.0
+        for rep in range(reps):
+            t0 = time.perf_counter()
+            res = pool.map(_cpu_worker, [(9000 + 97 * rep + p, n_cfg) for p in range(procs)])
+            w = time.perf_counter() - t0
+            rate = sum(r[0] for r in res) / max(r[1] for r in res)
+            if rate > best:
+                best, wall = rate, w
+    kind = "port+ref-vesin" if po.ref_available() else "port"
+    sample = (f"{n_cfg} perturbed 218-atom CuH2 configs per process x {procs} processes, best of {reps} "
+              f"({'vendored vesin from oracle/_ref + ' if po.ref_available() else ''}"
               f"C restatement of rgpot_cuh2.f90; the Fortran kernel cannot be built here)")
-    return {"value": atoms / busy, "unit": UNIT, "cores": procs, "kind": kind, "sample": sample,
-            "wall_s": wall}
+    return {"value": best, "unit": UNIT, "cores": procs, "kind": kind, "sample": sample, "wall_s": wall}
 
 
 def cpu_leg_rate(func, args, units, reps=1):
@@ -242,7 +272,7 @@ def cpu_side_baseline(name):
         "    t0 = time.perf_counter(); f(); dt = time.perf_counter() - t0\n"
         "    if rep and dt / len(pos) < best: best, natoms = dt / len(pos), len(pos)\n"
         "print(json.dumps({'value': 1.0 / best, 'unit': 'atom-evals/s', 'cores': 1,\n"
-        "                  'kind': 'reference' if ref else 'port',\n"
+        "                  'kind': (('reference' if name == 'lj_fluid_1m' else 'port+ref-vesin') if ref else 'port'),\n"
         "                  'sample': what + ', best of 3 cold calls: %%.3f s for %%d atoms' %% (best * natoms, natoms)}))\n"
     ) % (ROOT, name)
     try:
@@ -279,19 +309,22 @@ def run_cuh2_batch(args, world, rank, local):
     import torch
 
     import rgpot_b200
-    from rgpot_b200 import workloads
+    from rgpot_b200 import sharding, workloads
 
-    n_cfg = args.configs
-    offsets, pos, Z, boxes = workloads.cuh2_batch(n_cfg, seed=1000 + rank)
-    n_atoms = int(offsets[-1])
-    pot = rgpot_b200.CuH2Pot(device=local)
+    n_cfg = args.configs  # GLOBAL batch (strong scaling): every rank builds the same deterministic batch
+    offsets, pos, Z, boxes = workloads.cuh2_batch(n_cfg, seed=1000)
+    n_atoms_global = int(offsets[-1])
+    s0, s1, a0, a1 = sharding.local_slice(offsets, rank, world)
+    my_off = (offsets[s0:s1 + 1] - offsets[s0]).astype(np.uint64)
+    my_atoms = a1 - a0
+    pot = rgpot_b200.CuH2Pot(device=local, host_threads=max(1, min(12, (os.cpu_count() or 1) // world)))
 
     dev = torch.device("cuda", local)
-    d_pos = torch.from_numpy(pos).to(dev)
-    d_Z = torch.from_numpy(Z).to(dev)
-    d_boxes = torch.from_numpy(np.ascontiguousarray(boxes)).to(dev)
-    d_F = torch.empty((n_atoms, 3), dtype=torch.float64, device=dev)
-    d_E = torch.empty(n_cfg, dtype=torch.float64, device=dev)
+    d_pos = torch.from_numpy(pos[a0:a1]).to(dev)
+    d_Z = torch.from_numpy(Z[a0:a1]).to(dev)
+    d_boxes = torch.from_numpy(np.ascontiguousarray(boxes[s0:s1])).to(dev)
+    d_F = torch.empty((my_atoms, 3), dtype=torch.float64, device=dev)
+    d_E = torch.empty(s1 - s0, dtype=torch.float64, device=dev)
     # a dedicated (non-default) stream: the engine launches on it and the CUDA events below are
     # recorded on it, so they bracket exactly the engine's kernels
     tstream = torch.cuda.Stream(device=dev)
@@ -299,7 +332,7 @@ def run_cuh2_batch(args, world, rank, local):
     stream = tstream.cuda_stream
 
     def step():
-        pot.force_batch_device(offsets, d_pos, d_Z, d_boxes, d_F, d_E, stream)
+        pot.force_batch_device(my_off, d_pos, d_Z, d_boxes, d_F, d_E, stream)
 
     for _ in range(args.warmup):
         step()
@@ -321,70 +354,144 @@ def run_cuh2_batch(args, world, rank, local):
     dev_ms = t0.elapsed_time(t1)
     launches = pot.launch_count() - launches0
     assert pot.sync_status() == 0
-    checksum = float(d_E.sum().item())
+    checksum = sum_over_ranks(float(d_E.sum().item()), world)
 
-    # ---- end to end through the public host-buffer call, pinned host memory
-    h_pos = rgpot_b200.pinned_empty((n_atoms, 3))
-    h_Z = rgpot_b200.pinned_empty((n_atoms,), np.int32)
-    h_boxes = rgpot_b200.pinned_empty((n_cfg, 9))
-    h_F = rgpot_b200.pinned_empty((n_atoms, 3))
-    h_E = rgpot_b200.pinned_empty((n_cfg,))
-    h_pos[:] = pos
-    h_Z[:] = Z
-    h_boxes[:] = boxes
+    # ---- sustained: the same step back to back for >= 2.5 s (does the burst number survive at power?)
+    sustained = None
+    if world == 1 and not args.no_extras:
+        reps = max(args.steps, int(2.5e3 / max(dev_ms / args.steps, 1e-3)) + 1)
+        u0, u1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        u0.record()
+        for _ in range(reps):
+            step()
+        u1.record()
+        torch.cuda.synchronize()
+        assert pot.sync_status() == 0
+        sus_ms = u0.elapsed_time(u1)
+        sustained = {"steps": reps, "seconds": sus_ms * 1e-3, "value": my_atoms * reps / (sus_ms * 1e-3), "unit": UNIT}
+
+    # ---- end to end, process per GPU: every rank pushes ITS range through the pointer-array entry
+    # (separately allocated pageable systems), H2D / D2H and packing inside the timed region
     e2e_steps = max(1, min(args.steps, 5))
-    pot.forceBatchPacked(offsets, h_pos, h_Z, h_boxes, h_F, h_E)  # warm-up (allocations)
+    my_systems = [(pos[int(offsets[s]):int(offsets[s + 1])].copy(), Z[int(offsets[s]):int(offsets[s + 1])].copy(),
+                   boxes[s].reshape(3, 3).copy()) for s in range(s0, s1)]
+    fb = pot.prepareForceBatch(my_systems)
+    pot.forceBatchPrepared(fb)  # warm-up (allocations, helper threads)
     barrier(world)
     w0 = time.perf_counter()
     for _ in range(e2e_steps):
-        pot.forceBatchPacked(offsets, h_pos, h_Z, h_boxes, h_F, h_E)
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - w0
+        pot.forceBatchPrepared(fb)
+    rank_s = time.perf_counter() - w0
     barrier(world)
-    assert abs(float(h_E.sum()) - checksum) <= 1e-9 * abs(checksum)
+    assert abs(sum_over_ranks(float(fb["energies"].sum()), world) - checksum) <= 1e-9 * abs(checksum)
+    del fb, my_systems
     clocks = sampler.stop() if rank == 0 else None
-
     dev_ms = max_over_ranks(dev_ms, world)
-    e2e_s = max_over_ranks(e2e_s, world)
-    total_atoms = sum_over_ranks(float(n_atoms), world)
-    value = total_atoms * args.steps / (dev_ms * 1e-3)
-    e2e_value = total_atoms * e2e_steps / e2e_s
-    h2d = pos.nbytes + Z.nbytes + boxes.nbytes + offsets.nbytes
-    d2h = h_F.nbytes + h_E.nbytes
+    rank_s = max_over_ranks(rank_s, world)
+    checksum = float(checksum)
+    del pot, d_pos, d_Z, d_boxes, d_F, d_E
+    torch.cuda.empty_cache()
 
-    # roofline of the dominant kernel (k_eam_small: the whole step is one launch of it)
+    # ---- end to end, ONE call: rank 0's handle lists all N devices; the other ranks wait on the CPU
+    host_barrier(world)
+    one_call = None
+    if rank == 0:
+        try:
+            os.sched_setaffinity(0, range(os.cpu_count() or 1))  # the engine places its own threads next to each GPU
+        except OSError:
+            pass
+        ncpu_all = len(os.sched_getaffinity(0))
+        per_dev = max(1, min(12, ncpu_all // world))
+        multi = rgpot_b200.CuH2Pot(devices=list(range(world)), host_threads=per_dev) if world > 1 else \
+            rgpot_b200.CuH2Pot(device=0, host_threads=per_dev)
+        systems = [(pos[int(offsets[s]):int(offsets[s + 1])].copy(), Z[int(offsets[s]):int(offsets[s + 1])].copy(),
+                    boxes[s].reshape(3, 3).copy()) for s in range(n_cfg)]
+        fb = multi.prepareForceBatch(systems)
+        multi.forceBatchPrepared(fb)  # warm-up
+        w0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            multi.forceBatchPrepared(fb)
+        one_s = time.perf_counter() - w0
+        assert abs(float(fb["energies"].sum()) - checksum) <= 1e-9 * abs(checksum)
+        del fb, systems
+        # the packed entry on page-locked arrays (no host packing at all)
+        h_pos = rgpot_b200.pinned_empty((n_atoms_global, 3))
+        h_Z = rgpot_b200.pinned_empty((n_atoms_global,), np.int32)
+        h_boxes = rgpot_b200.pinned_empty((n_cfg, 9))
+        h_F = rgpot_b200.pinned_empty((n_atoms_global, 3))
+        h_E = rgpot_b200.pinned_empty((n_cfg,))
+        h_pos[:], h_Z[:], h_boxes[:] = pos, Z, boxes
+        multi.forceBatchPacked(offsets, h_pos, h_Z, h_boxes, h_F, h_E)
+        w0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            multi.forceBatchPacked(offsets, h_pos, h_Z, h_boxes, h_F, h_E)
+        pin_s = time.perf_counter() - w0
+        assert abs(float(h_E.sum()) - checksum) <= 1e-9 * abs(checksum)
+        del h_pos, h_Z, h_boxes, h_F, h_E
+        h2d = pos.nbytes + boxes.nbytes + offsets.nbytes  # one copy of the species array is shared by the batch
+        d2h = pos.nbytes + n_cfg * 8
+        gbs = rgpot_b200.measure_copy_gbs(list(range(world)), h2d // world, d2h // world)
+        one_call = {"one_s": one_s, "pin_s": pin_s, "h2d": h2d, "d2h": d2h, "copy_gbs": gbs, "host_threads_per_gpu": per_dev,
+                    "cpus": ncpu_all}
+        del multi
+    host_barrier(world)
+
+    value = n_atoms_global * args.steps / (dev_ms * 1e-3)
+    if rank != 0:
+        return None
+    e2e_value = n_atoms_global * e2e_steps / one_call["one_s"]
+    ceiling_s = (one_call["h2d"] + one_call["d2h"]) / (one_call["copy_gbs"] * 1e9) if one_call["copy_gbs"] else None
+
+    # roofline of the dominant kernel (k_eam_small: the whole step is one launch of it per rank)
     kernel_s = dev_ms * 1e-3 / args.steps
-    fp64_peak = rgpot_b200.measure_fp64_tflops(local) if rank == 0 else 0.0
-    achieved_tf = FLOPS_PER_ATOM["cuh2_batch"] * n_atoms / kernel_s / 1e12
+    fp64_peak = rgpot_b200.measure_fp64_tflops(local)
+    launches = launches * world  # every rank launches the same kernels on its range
+    achieved_tf = FLOPS_PER_ATOM["cuh2_batch"] * n_atoms_global / world / kernel_s / 1e12
     peaks = load_peaks()
-    hbm_gbs = BYTES_PER_ATOM["cuh2_batch"] * n_atoms / kernel_s / 1e9
+    hbm_gbs = BYTES_PER_ATOM["cuh2_batch"] * n_atoms_global / world / kernel_s / 1e9
+    executed = executed_fp64_per_atom("k_eam_small")
     roofline = {"bound": "fp64", "kernel": "k_eam_small", "achieved": achieved_tf, "peak": fp64_peak,
                 "unit": "TFLOP/s", "frac": achieved_tf / fp64_peak if fp64_peak else None,
-                "peak_source": "DFMA microbenchmark measured in this run (MEASURED_PEAKS.json has no FP64 entry)",
+                "peak_nominal": FP64_NOMINAL_TF, "frac_nominal": achieved_tf / FP64_NOMINAL_TF,
+                "peak_source": "DFMA microbenchmark measured in this run (MEASURED_PEAKS.json has no FP64 entry); "
+                               "nominal = 148 SM x 64 FMA/clk x 2 x 1.965 GHz",
                 "flops_per_atom_eval": FLOPS_PER_ATOM["cuh2_batch"],
-                "traffic": (lambda t: None if t is None else t * n_atoms)(
-                    measured_traffic_per_atom("k_eam_small", 16384 * 218)),
+                "fp64_executed": executed,
+                "traffic": (lambda t: None if t is None else t * n_atoms_global / world)(
+                    measured_traffic_per_atom("k_eam_small")),
                 "traffic_note": "DRAM read+write bytes of one k_eam_small launch, scaled per atom from the "
-                                "committed ncu capture (profiles/, 16384 configs); algorithmic bytes are "
-                                "76 B/atom-eval",
+                                "committed ncu capture (profiles/); algorithmic bytes are 76 B/atom-eval",
+                "per_gpu": world > 1,
                 "hbm": {"achieved": hbm_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                         "frac": hbm_gbs / peaks["hbm_gbs"], "peak_source": peaks["source"]}}
     return {
         "value": value, "ms_per_step": dev_ms / args.steps, "gpu_launches": launches,
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
-                "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
-                "api": "CuH2Pot.forceBatchPacked -> rgpot_b200_force_batch_packed (pinned host buffers)"},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(one_call["h2d"]),
+                "d2h_bytes_per_step": int(one_call["d2h"]), "steps": e2e_steps,
+                "api": "CuH2Pot.forceBatchPrepared -> ONE rgpot_b200_force_batch call on %d separately allocated "
+                       "pageable systems (ForceBatch semantics), handle with devices = 0..%d" % (n_cfg, world - 1),
+                "host_threads_per_gpu": one_call["host_threads_per_gpu"], "host_cpus": one_call["cpus"]},
+        "e2e_pinned": {"value": n_atoms_global * e2e_steps / one_call["pin_s"], "unit": UNIT,
+                       "api": "one rgpot_b200_force_batch_packed call on page-locked packed arrays, same handle",
+                       "ratio_e2e_over_pinned": one_call["pin_s"] / one_call["one_s"]},
+        "e2e_per_rank": {"value": n_atoms_global * e2e_steps / rank_s, "unit": UNIT,
+                         "api": "every rank: rgpot_b200_force_batch on its own range (process per GPU, max over ranks)"},
+        "copy_ceiling": {"gb_per_s": one_call["copy_gbs"], "unit": "GB/s",
+                         "value_at_ceiling": (n_atoms_global / ceiling_s) if ceiling_s else None,
+                         "e2e_pinned_over_ceiling": (ceiling_s * e2e_steps / one_call["pin_s"]) if ceiling_s else None,
+                         "what": "plain pinned cudaMemcpyAsync of the same H2D + D2H bytes on these %d GPUs at once" % world},
+        "sustained": sustained,
         "roofline": roofline, "clocks": clocks,
-        "config": {"workload": f"cuh2_batch: {n_cfg} perturbed 218-atom Cu slab + H2 configs per GPU "
-                               f"(BASELINE configs[4])",
-                   "configs_per_gpu": n_cfg, "atoms_per_config": 218, "global_configs": n_cfg * world,
-                   "parallelism": f"{world} independent rank(s), batch sharded, no collective",
+        "config": {"workload": f"cuh2_batch: {n_cfg} perturbed 218-atom Cu slab + H2 configs, ONE global batch cut "
+                               f"across {world} GPU(s) (BASELINE configs[4])",
+                   "global_configs": n_cfg, "atoms_per_config": 218,
+                   "parallelism": f"batch cut by atoms into {world} contiguous range(s), no collective",
                    "l2": "inputs + outputs (0.7 GB per step) exceed the 126 MB L2"},
     }
 
 
 def run_single_system(args, name, local):
-    """LJ 1M fluid / Cu slab 256k on one GPU: device-resident value + e2e."""
+    """LJ 1M fluid / Cu slab 256k on one GPU: device-resident value + e2e from pageable and pinned arrays."""
     import torch
 
     import rgpot_b200
@@ -424,7 +531,14 @@ def run_single_system(args, name, local):
     assert pot.sync_status() == 0
     launches = pot.launch_count() - l0
     value = n * steps / (total_ms * 1e-3)
-    # end to end through the public call, pinned host arrays in and out
+    # end to end through the public call: pageable numpy arrays in and out (what Potential::operator()
+    # hands over), and page-locked arrays for comparison
+    F_page = np.zeros_like(pos)
+    pot(pos, Z, box, out=F_page)
+    w0 = time.perf_counter()
+    for _ in range(5):
+        e, f, _ = pot(pos, Z, box, out=F_page)
+    e2e = n * 5 / (time.perf_counter() - w0)
     h_pos = rgpot_b200.pinned_empty((n, 3))
     h_Z = rgpot_b200.pinned_empty((n,), np.int32)
     h_F = rgpot_b200.pinned_empty((n, 3))
@@ -433,17 +547,22 @@ def run_single_system(args, name, local):
     pot(h_pos, h_Z, box, out=h_F)
     w0 = time.perf_counter()
     for _ in range(5):
-        e, f, _ = pot(h_pos, h_Z, box, out=h_F)
-    e2e = n * 5 / (time.perf_counter() - w0)
+        e_p, _, _ = pot(h_pos, h_Z, box, out=h_F)
+    e2e_pinned = n * 5 / (time.perf_counter() - w0)
+    assert e == e_p and np.array_equal(F_page, h_F)
     assert abs(e - float(d_E.item())) <= 1e-12 * abs(e)
     fp64_peak = rgpot_b200.measure_fp64_tflops(local)
     tf = FLOPS_PER_ATOM[name] * value / 1e12
     rec = {"workload": name, "n_atoms": n, "value": value, "unit": UNIT, "ms_per_step": total_ms / steps,
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(pos.nbytes + Z.nbytes),
-                    "d2h_bytes_per_step": int(pos.nbytes + 8)},
+                    "d2h_bytes_per_step": int(pos.nbytes + 8),
+                    "api": "Potential::operator() shape: rgpot_b200_force on pageable arrays"},
+            "e2e_pinned": {"value": e2e_pinned, "unit": UNIT, "ratio_e2e_over_pinned": e2e / e2e_pinned},
             "gpu_launches": launches, "energy": e, "cpu_baseline": cpu_side_baseline(name),
             "roofline": {"bound": "fp64", "kernel": kernel, "achieved": tf, "peak": fp64_peak,
                          "unit": "TFLOP/s", "frac": tf / fp64_peak if fp64_peak else None,
+                         "peak_nominal": FP64_NOMINAL_TF, "frac_nominal": tf / FP64_NOMINAL_TF,
+                         "fp64_executed": executed_fp64_per_atom("k_brick<0" if name == "lj_fluid_1m" else "k_brick<2"),
                          "note": "whole step (cell build + force kernels) timed, flops of the path"},
             "l2": "256 MB flush write between timed iterations"}
     if name == "lj_fluid_1m":
@@ -451,9 +570,90 @@ def run_single_system(args, name, local):
     return rec
 
 
-def measured_traffic_per_atom(kernel_substr, atoms_in_capture):
-    """DRAM bytes per atom-eval of the dominant kernel from the committed `ncu --set full` capture
-    (profiles/r01_*_summary.json, dram__bytes_read.sum + dram__bytes_write.sum), or None."""
+# ------------------------------------------------------------------- single small configurations
+def potbench_lj500():
+    """CppCore/tests/PotBench.cc:128-193: 500 atoms, fcc 5^3 cells in a 32 A cube, rc = 15 (rc ~ L/2)."""
+    from rgpot_b200 import workloads
+    a = 32.0 / 5.0
+    pos = workloads._fcc(5, a) + workloads._sin_jitter(500, 0.05)
+    return np.ascontiguousarray(pos), np.ones(500, np.int32), np.diag([32.0, 32.0, 32.0])
+
+
+def potbench_cuh2_130():
+    """CppCore/tests/PotBench.cc:262-321: 128 Cu (4 x 4 x 2 fcc cells) + 2 H, box 14.46 x 14.46 x 30."""
+    from rgpot_b200 import workloads
+    a = 3.615
+    ix, iy, iz = np.meshgrid(np.arange(4.0), np.arange(4.0), np.arange(2.0), indexing="ij")
+    corner = np.stack([ix.ravel(), iy.ravel(), iz.ravel()], axis=1)
+    cu = a * (corner[:, None, :] + workloads._FCC_BASIS[None, :, :]).reshape(-1, 3)
+    top = cu[:, 2].max()
+    h = np.array([[7.0 - 0.37, 7.0, top + 2.0], [7.0 + 0.37, 7.0, top + 2.0]])
+    pos = np.concatenate([cu, h]) + workloads._sin_jitter(130, 0.02)
+    Z = np.concatenate([np.full(128, 29, np.int32), np.ones(2, np.int32)])
+    return np.ascontiguousarray(pos), Z, np.diag([14.46, 14.46, 30.0])
+
+
+def run_small_configs(local):
+    """BASELINE configs[0] / configs[1] and the reference's own benchmark definitions: microseconds per
+    call of the public single-system entry (rgpot_b200_force on host arrays, one launch), with the
+    reference CPU path (the reference's own LJ objects from oracle/_ref; vesin + restated Fortran for
+    CuH2) timed beside it on one core."""
+    import ctypes as C
+
+    import rgpot_b200
+    from oracle import pyoracle as po
+    from rgpot_b200 import _lib, workloads
+    ref = po.ref_available()
+    cases = [
+        ("lj13_cluster LJClusterPot (configs[0])", rgpot_b200.LJClusterPot(device=local), workloads.lj13_cluster(),
+         (lambda p, z, b: po.ref_lj_force(p, b, 1.0, 15.0, 1.0, cluster=True)) if ref else
+         (lambda p, z, b: po.lj_force(p, b, 1.0, 15.0, 1.0, cluster=True))),
+        ("cuh2_pin4 (configs[1], CuH2PotTest.cc:11-22)", rgpot_b200.CuH2Pot(device=local), workloads.cuh2_pin4(),
+         lambda p, z, b: po.cuh2_force(p, z, b, use_ref=ref)),
+        ("cuh2_slab218 (configs[1], tmp.con)", rgpot_b200.CuH2Pot(device=local), workloads.cuh2_slab218(),
+         lambda p, z, b: po.cuh2_force(p, z, b, use_ref=ref)),
+        ("PotBench LJ 500 atoms, rc = 15 in a 32 A cube (PotBench.cc:128-193)", rgpot_b200.LJPot(device=local),
+         potbench_lj500(),
+         (lambda p, z, b: po.ref_lj_force(p, b, 1.0, 15.0, 1.0)) if ref else (lambda p, z, b: po.lj_force(p, b, 1.0, 15.0, 1.0))),
+        ("PotBench CuH2 128 Cu + 2 H (PotBench.cc:262-321)", rgpot_b200.CuH2Pot(device=local), potbench_cuh2_130(),
+         lambda p, z, b: po.cuh2_force(p, z, b, use_ref=ref)),
+    ]
+    lib = _lib.lib()
+    out = []
+    for name, pot, (pos, Z, box), cpu in cases:
+        pos = np.ascontiguousarray(pos, dtype=np.float64)
+        Z = np.ascontiguousarray(Z, dtype=np.int32)
+        box = np.ascontiguousarray(box, dtype=np.float64)
+        F = np.zeros_like(pos)
+        e, v = C.c_double(0.0), C.c_double(0.0)
+        args_ = (pot._h, len(pos), pos.ctypes.data, Z.ctypes.data, F.ctypes.data, C.byref(e), C.byref(v), box.ctypes.data)
+        for _ in range(50):
+            assert lib.rgpot_b200_force(*args_) == 0
+        l0 = pot.launch_count()
+        reps = 2000
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            lib.rgpot_b200_force(*args_)
+        us = (time.perf_counter() - t0) / reps * 1e6
+        launches = (pot.launch_count() - l0) / reps
+        # the reference CPU path: a fresh (jittered) geometry per call so no neighbor-list cache turns it
+        # into a warm walk; best of 5
+        best = 1e30
+        for rep in range(6):
+            p2 = pos + 1e-3 * np.sin(np.arange(pos.size).reshape(pos.shape) + rep)
+            t0 = time.perf_counter()
+            cpu(p2, Z, box)
+            dt = time.perf_counter() - t0
+            if rep:
+                best = min(best, dt)
+        out.append({"case": name, "n_atoms": len(pos), "us_per_call": us, "launches_per_call": launches,
+                    "energy": e.value, "cpu_us_per_call": best * 1e6, "cpu_cores": 1,
+                    "cpu_kind": ("reference" if "LJ" in name else "port+ref-vesin") if ref else "port"})
+    return out
+
+
+def _latest_summary(kernel_substr):
+    """the newest committed `ncu --set full` summary record (profiles/r*_summary.json) of a kernel"""
     import glob
     for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_summary.json")), reverse=True):
         try:
@@ -462,11 +662,40 @@ def measured_traffic_per_atom(kernel_substr, atoms_in_capture):
             continue
         for r in recs:
             if kernel_substr in r.get("kernel", "") and "dram_read" in r:
-                scale = {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}
-                tot = r["dram_read"] * scale.get(r.get("dram_read_unit", "byte"), 1.0) + \
-                    r["dram_write"] * scale.get(r.get("dram_write_unit", "byte"), 1.0)
-                return tot / atoms_in_capture
-    return None
+                return r, os.path.basename(path)
+    return None, None
+
+
+def _atoms_in_capture(r):
+    if "atoms_in_capture" in r:
+        return float(r["atoms_in_capture"])
+    k = r.get("kernel", "")
+    if "k_eam_small" in k:
+        return float(r.get("grid", 16384.0)) * 218.0  # one block per 218-atom system
+    return 1.0e6 if "<0" in k else 256512.0
+
+
+def measured_traffic_per_atom(kernel_substr):
+    """DRAM bytes per atom-eval of the dominant kernel from the committed `ncu --set full` capture
+    (dram__bytes_read.sum + dram__bytes_write.sum), or None."""
+    r, _ = _latest_summary(kernel_substr)
+    if r is None:
+        return None
+    scale = {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}
+    tot = r["dram_read"] * scale.get(r.get("dram_read_unit", "byte"), 1.0) + \
+        r["dram_write"] * scale.get(r.get("dram_write_unit", "byte"), 1.0)
+    return tot / _atoms_in_capture(r)
+
+
+def executed_fp64_per_atom(kernel_substr):
+    """SURVEY 8(d) cross-check: FP64 flops the kernel EXECUTED per atom-eval (DFMA x 2 + DADD + DMUL from
+    smsp__sass_thread_inst_executed_op_d*_pred_on in the committed ncu capture) beside the algorithmic
+    count the roofline uses (which books an exponential as 30 flops; the kernels' table exp is ~20)."""
+    r, path = _latest_summary(kernel_substr)
+    if r is None or "fp64_flops" not in r:
+        return None
+    return {"flops_per_atom_eval": r["fp64_flops"] / _atoms_in_capture(r), "fp64_pipe_busy_pct": r.get("fp64_pipe_pct"),
+            "source": "profiles/" + path}
 
 
 def load_peaks():
@@ -487,10 +716,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cuh2_batch",
                     choices=["cuh2_batch", "lj_fluid_1m", "cuh2_slab_256k"])
-    ap.add_argument("--configs", type=int, default=65536, help="configurations per GPU")
+    ap.add_argument("--configs", type=int, default=65536, help="configurations of the GLOBAL batch")
     ap.add_argument("--lj-atoms", type=int, default=1_000_000)
     ap.add_argument("--slab-cells", type=int, default=40)
-    ap.add_argument("--no-extras", action="store_true", help="skip the LJ 1M / Cu 256k side lines")
+    ap.add_argument("--no-extras", action="store_true", help="skip the side lines (LJ 1M, Cu 256k, small configs)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -499,20 +728,20 @@ def main():
         rank = int(os.environ.get("RANK", "0"))
         if rank != 0:
             return
-        per_step = max(2.0, min(20.0, 120.0 / max(1, args.steps + min(args.warmup, 1))))
-        cpu_reference_rate(budget_s=1.0, configs_per_proc=50)  # warm-up
+        per_step = max(3.0, min(20.0, 120.0 / max(1, args.steps + min(args.warmup, 1))))
         rates, walls = [], []
+        r = None
         for _ in range(args.steps):
-            r = cpu_reference_rate(budget_s=per_step)
+            r = cpu_reference_rate(budget_s=per_step, reps=3)
             rates.append(r["value"])
             walls.append(r["wall_s"])
-        value = float(np.mean(rates))
+        value = float(np.median(rates))
         line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(np.mean(walls)) * 1e3,
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic",
                 "config": {"workload": "cuh2_batch: perturbed 218-atom Cu slab + H2 configs (BASELINE configs[4]); "
-                                       "each step a bounded sample on all host cores"},
+                                       "each step a bounded sample on all host cores (a rate: independent of the batch size)"},
                 "cpu_baseline": {"value": value, "unit": UNIT, "cores": r["cores"], "kind": r["kind"],
                                  "sample": r["sample"]},
                 "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -530,19 +759,25 @@ def main():
     else:
         r = run_single_system(args, args.workload, local)
         res = {"value": r["value"], "ms_per_step": r["ms_per_step"], "gpu_launches": r["gpu_launches"],
-               "e2e": r["e2e"], "roofline": r["roofline"], "clocks": None,
+               "e2e": r["e2e"], "e2e_pinned": r["e2e_pinned"], "roofline": r["roofline"], "clocks": None,
                "config": {"workload": args.workload, "n_atoms": r["n_atoms"], "l2": r["l2"]}}
     if rank == 0:
         line = {"metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "scaling": "strong" if args.workload == "cuh2_batch" else "weak", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic",
                 "config": res["config"], "e2e": res["e2e"], "gpu_launches": res["gpu_launches"],
                 "roofline": res["roofline"], "clocks": res["clocks"]}
+        for key in ("e2e_pinned", "e2e_per_rank", "copy_ceiling", "sustained"):
+            if res.get(key) is not None:
+                line[key] = res[key]
         if world == 1:
             line["cpu_baseline"] = cpu_base
             if args.workload == "cuh2_batch" and not args.no_extras:
                 line["also"] = [run_single_system(args, "lj_fluid_1m", local),
-                                run_single_system(args, "cuh2_slab_256k", local)]
+                                run_single_system(args, "cuh2_slab_256k", local),
+                                {"workload": "single small configurations (microseconds per call)",
+                                 "cases": run_small_configs(local)}]
         print(json.dumps(line))
     if world > 1:
         import torch.distributed as dist

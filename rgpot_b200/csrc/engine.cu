@@ -352,7 +352,9 @@ struct RgpotB200Pot {
   HostBuf h_fast;
   // pageable single systems: pinned ring for the staged H2D / D2H of large arrays
   HostBuf h_ring;
-  cudaEvent_t ring_ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ring_ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  bool ring_busy[8] = {false, false, false, false, false, false, false, false};  // a copy out of / into the slot may still be in flight
+  unsigned ring_next = 0;                             // slots are handed out round robin across calls
   // batches cut across several GPUs: one single-device handle + one persistent host thread per device
   struct Shard {
     RgpotB200Pot* pot = nullptr;
@@ -2030,8 +2032,18 @@ int rgpot_b200_sync_status(RgpotB200Pot* pot) {
 // array; pageable memory (what Potential::operator() hands over, CppCore/rgpot/Potential.hpp:165-211)
 // goes through a ring of pinned slices filled / drained by the helper threads, slice k + 1 on the CPU
 // while slice k is on the bus.
-constexpr size_t kRingSlice = 4u << 20;
-constexpr int kRingSlots = 4;
+constexpr size_t kRingSlice = 1u << 20;
+constexpr int kRingSlots = 8;
+
+// take the next ring slot, waiting for whatever copy still uses it
+static int ring_acquire(RgpotB200Pot* pot, int& slot) {
+  slot = (int)(pot->ring_next++ % kRingSlots);
+  if (pot->ring_busy[slot]) {
+    CU_TRY(pot, cudaEventSynchronize(pot->ring_ev[slot]));
+    pot->ring_busy[slot] = false;
+  }
+  return 0;
+}
 
 static int upload_array(RgpotB200Pot* pot, void* d_dst, const void* h_src, size_t bytes, cudaStream_t st) {
   if (bytes < (1u << 20) || rb::host_ptr_is_pinned(h_src)) {
@@ -2043,20 +2055,20 @@ static int upload_array(RgpotB200Pot* pot, void* d_dst, const void* h_src, size_
   char* ring = pot->h_ring.as<char>();
   const size_t nslices = (bytes + kRingSlice - 1) / kRingSlice;
   for (size_t i = 0; i < nslices; ++i) {
-    const int slot = (int)(i % kRingSlots);
+    int slot = 0;
+    int rs = ring_acquire(pot, slot);
+    if (rs) return rs;
     const size_t o = i * kRingSlice, len = std::min(kRingSlice, bytes - o);
-    if (i >= (size_t)kRingSlots) CU_TRY(pot, cudaEventSynchronize(pot->ring_ev[slot]));
     char* dst = ring + (size_t)slot * kRingSlice;
     const char* src = static_cast<const char*>(h_src) + o;
-    team->run(len, 64u << 10, [&](size_t b0, size_t b1) {
+    team->run(len, 32u << 10, [&](size_t b0, size_t b1) {
       rb::copy_stream(dst + b0, src + b0, b1 - b0);
       rb::copy_stream_fence();
     });
     CU_TRY(pot, cudaMemcpyAsync(static_cast<char*>(d_dst) + o, dst, len, cudaMemcpyHostToDevice, st));
     CU_TRY(pot, cudaEventRecord(pot->ring_ev[slot], st));
+    pot->ring_busy[slot] = true;
   }
-  // the ring may be reused by the next call only after these copies: the download below (same
-  // stream) or the final synchronisation of the caller orders that
   return 0;
 }
 
@@ -2069,26 +2081,38 @@ static int download_array(RgpotB200Pot* pot, void* h_dst, const void* d_src, siz
   rb::Team* team = get_team(pot);
   char* ring = pot->h_ring.as<char>();
   const size_t nslices = (bytes + kRingSlice - 1) / kRingSlice;
-  auto issue = [&](size_t i) -> cudaError_t {
-    const int slot = (int)(i % kRingSlots);
+  int slots[kRingSlots];
+  auto issue = [&](size_t i) -> int {
+    int slot = 0;
+    int rs = ring_acquire(pot, slot);
+    if (rs) return rs;
+    slots[i % kRingSlots] = slot;
     const size_t o = i * kRingSlice, len = std::min(kRingSlice, bytes - o);
-    cudaError_t e = cudaMemcpyAsync(ring + (size_t)slot * kRingSlice, static_cast<const char*>(d_src) + o, len,
-                                    cudaMemcpyDeviceToHost, st);
-    if (e == cudaSuccess) e = cudaEventRecord(pot->ring_ev[slot], st);
-    return e;
+    CU_TRY(pot, cudaMemcpyAsync(ring + (size_t)slot * kRingSlice, static_cast<const char*>(d_src) + o, len,
+                                cudaMemcpyDeviceToHost, st));
+    CU_TRY(pot, cudaEventRecord(pot->ring_ev[slot], st));
+    pot->ring_busy[slot] = true;
+    return 0;
   };
-  for (size_t i = 0; i < std::min<size_t>(nslices, kRingSlots); ++i) CU_TRY(pot, issue(i));
+  for (size_t i = 0; i < std::min<size_t>(nslices, kRingSlots); ++i) {
+    int rs = issue(i);
+    if (rs) return rs;
+  }
   for (size_t i = 0; i < nslices; ++i) {
-    const int slot = (int)(i % kRingSlots);
+    const int slot = slots[i % kRingSlots];
     const size_t o = i * kRingSlice, len = std::min(kRingSlice, bytes - o);
     CU_TRY(pot, cudaEventSynchronize(pot->ring_ev[slot]));
+    pot->ring_busy[slot] = false;
     const char* src = ring + (size_t)slot * kRingSlice;
     char* dst = static_cast<char*>(h_dst) + o;
-    team->run(len, 64u << 10, [&](size_t b0, size_t b1) {
+    team->run(len, 32u << 10, [&](size_t b0, size_t b1) {
       rb::copy_stream(dst + b0, src + b0, b1 - b0);
       rb::copy_stream_fence();
     });
-    if (i + kRingSlots < nslices) CU_TRY(pot, issue(i + kRingSlots));
+    if (i + kRingSlots < nslices) {
+      int rs = issue(i + kRingSlots);
+      if (rs) return rs;
+    }
   }
   return 0;
 }
