@@ -350,6 +350,8 @@ struct RgpotB200Pot {
   DevBuf b_Z0;                // atomic numbers of one system, shared by a homogeneous batch
   // single small systems: one page-locked block the kernel reads and writes in place (zero copy)
   HostBuf h_fast;
+  void* h_fast_dev = nullptr;  // its address as the device sees it
+  DevBuf d_fast;              // device copy of the inputs + block partials + ticket (one system over many blocks)
   // pageable single systems: pinned ring for the staged H2D / D2H of large arrays
   HostBuf h_ring;
   cudaEvent_t ring_ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -389,6 +391,7 @@ struct RgpotB200Pot {
     team.reset();
     cudaSetDevice(device);
     b_Z0.release();
+    d_fast.release();
     h_fast.release();
     h_ring.release();
     for (auto& e : ring_ev)
@@ -422,10 +425,14 @@ namespace {
 // RAII: make the handle's device current for the duration of an entry point, then put the caller's back
 struct DevGuard {
   int prev = -1;
-  cudaError_t err;
+  cudaError_t err = cudaSuccess;
   explicit DevGuard(int dev) {
     if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
-    err = cudaSetDevice(dev);
+    if (prev == dev)
+      prev = -1;  // already current: nothing to select, nothing to put back (a single small system's
+                  // whole call is ~20 microseconds; two cudaSetDevice calls would be a tenth of it)
+    else
+      err = cudaSetDevice(dev);
   }
   ~DevGuard() {
     if (prev >= 0) cudaSetDevice(prev);
@@ -1208,9 +1215,14 @@ int eam_small_maxnb(const RgpotB200Pot* pot, long nmax) {
 int launch_small(RgpotB200Pot* pot, size_t nsys, long nmax, const long long* d_off,
                  const double* d_boxes, const double* d_pos, const int* d_Z, double* d_F,
                  double* d_E, unsigned* d_flags, int* d_bad, int maxnb, cudaStream_t st,
-                 const EmitArgs* emit, bool z_shared = false) {
+                 const EmitArgs* emit, bool z_shared = false, int single_n = 0, int split = 0,
+                 double* e_parts = nullptr, int* ticket = nullptr) {
   SmallArgs a{};
   a.z_shared = z_shared ? 1 : 0;
+  a.single_n = single_n;
+  a.split = split;
+  a.e_parts = e_parts;
+  a.ticket = ticket;
   a.pos = d_pos;
   a.Z = d_Z;
   a.off = d_off;
@@ -1277,7 +1289,10 @@ int launch_small(RgpotB200Pot* pot, size_t nsys, long nmax, const long long* d_o
   }
   int threads = (int)std::min<long>(256, ((nmax + 31) / 32) * 32);
   if (threads < 32) threads = 32;
-  k_lj_small<<<(unsigned)nsys, threads, smem, st>>>(a);
+  if (split > 1)
+    k_lj_small<<<(unsigned)split, 128, smem, st>>>(a);  // one system, 32 atoms per block
+  else
+    k_lj_small<<<(unsigned)nsys, threads, smem, st>>>(a);
   return check_launch(pot, "k_lj_small");
 }
 
@@ -2135,11 +2150,11 @@ static int force_small_fast(RgpotB200Pot* pot, long nAtoms, const double* positi
     const size_t want = std::max<size_t>(words * 8 * 2, 64u << 10);
     CU_TRY(pot, cudaHostAlloc(&pot->h_fast.p, want, cudaHostAllocMapped | cudaHostAllocPortable));
     pot->h_fast.cap = want;
+    pot->h_fast_dev = nullptr;
   }
-  void* dbase = nullptr;
-  CU_TRY(pot, cudaHostGetDevicePointer(&dbase, pot->h_fast.p, 0));
+  if (!pot->h_fast_dev) CU_TRY(pot, cudaHostGetDevicePointer(&pot->h_fast_dev, pot->h_fast.p, 0));
   double* h = pot->h_fast.as<double>();
-  double* d = static_cast<double*>(dbase);
+  double* d = static_cast<double*>(pot->h_fast_dev);
   long long* h_off = reinterpret_cast<long long*>(h);
   double* h_box = h + 2;
   double* h_pos = h + 11;
@@ -2162,11 +2177,48 @@ static int force_small_fast(RgpotB200Pot* pot, long nAtoms, const double* positi
   const size_t iE = 11 + 6 * n;
   const int maxnb = is_eam(pot->cfg.kind) ? eam_small_maxnb(pot, nAtoms) : 0;
   cudaStream_t st = pot->stream;
-  int s = launch_small(pot, 1, nAtoms, reinterpret_cast<const long long*>(d), d + 2, d + 11,
-                       eam ? reinterpret_cast<const int*>(d + iE + 3) : nullptr, d + 11 + 3 * n, d + iE,
-                       reinterpret_cast<unsigned*>(d + iE + 1), reinterpret_cast<int*>(d + iE + 2), maxnb, st, nullptr);
+  int s = 0;
+  if (!is_eam(pot->cfg.kind) && nAtoms >= 128) {
+    // a pair potential on a few hundred atoms: one block would leave 147 SMs idle.  The inputs go to
+    // the device in ONE copy (every block reads all of them), the atoms are spread over the blocks,
+    // results land in the mapped block.
+    const int split = (int)((nAtoms + 31) / 32);
+    const size_t in_words = 11 + 3 * n, need = sizeof(double) * (in_words + (size_t)split) + 64;
+    if (pot->d_fast.cap < need) {
+      CU_TRY(pot, pot->d_fast.reserve(need * 2));
+      CU_TRY(pot, cudaMemsetAsync(pot->d_fast.p, 0, pot->d_fast.cap, st));  // (the ticket starts at zero)
+    }
+    double* dd = pot->d_fast.as<double>();
+    // layout: ticket (8 bytes) | inputs | block partials
+    CU_TRY(pot, cudaMemcpyAsync(dd + 1, h, sizeof(double) * in_words, cudaMemcpyHostToDevice, st));
+    s = launch_small(pot, 1, nAtoms, nullptr, dd + 1 + 2, dd + 1 + 11, nullptr, d + 11 + 3 * n, d + iE,
+                     reinterpret_cast<unsigned*>(d + iE + 1), reinterpret_cast<int*>(d + iE + 2), maxnb, st, nullptr, false,
+                     (int)nAtoms, split, dd + 1 + in_words, reinterpret_cast<int*>(dd));
+  } else {
+    s = launch_small(pot, 1, nAtoms, reinterpret_cast<const long long*>(d), d + 2, d + 11,
+                     eam ? reinterpret_cast<const int*>(d + iE + 3) : nullptr, d + 11 + 3 * n, d + iE,
+                     reinterpret_cast<unsigned*>(d + iE + 1), reinterpret_cast<int*>(d + iE + 2), maxnb, st, nullptr, false,
+                     (int)nAtoms);
+  }
   if (s) return s;
-  CU_TRY(pot, cudaStreamSynchronize(st));
+  {
+    // the kernel writes the status word last, behind a system-scope fence: poll it in place (a stream
+    // synchronisation costs several microseconds more), with the driver as the fallback
+    volatile unsigned* vf = h_flags;
+    const auto t_start = std::chrono::steady_clock::now();
+    unsigned spins = 0;
+    while (*vf == 0xffffffffu) {
+      if ((++spins & 1023u) == 0 &&
+          std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count() > 2.0e-3) {
+        CU_TRY(pot, cudaStreamSynchronize(st));
+        break;
+      }
+#if defined(__x86_64__)
+      __builtin_ia32_pause();
+#endif
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);
+  }
   const unsigned flags = *h_flags;
   if (flags == 0xffffffffu) return fail(pot, kStatusCuda, "rgpot_b200: the single-system kernel left no status");
   if (flags & kFlagListOverflow) return -1;

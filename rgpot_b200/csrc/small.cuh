@@ -29,6 +29,11 @@ struct SmallArgs {
   int nsys;
   int maxnb;               // neighbor-list capacity per atom (EAM)
   int z_shared;            // homogeneous batch: Z holds the atomic numbers of ONE system, shared by all
+  int single_n;            // > 0: ONE system of this many atoms starting at atom 0 (the offsets are not read:
+                           //      one dependent fetch less when the inputs sit in mapped host memory)
+  int split;               // k_lj_small, single system: blocks the atoms are spread over (0 / 1 = one block)
+  double* e_parts;         // split: per-block energy partials ...
+  int* ticket;             // ... and the counter that tells the last block to fold them (left at zero)
   int cluster;             // LJ: free boundaries
   double u0, psi2, shiftU, cutoff;  // LJ
   int morse;                        // 1 Morse, 2 ZBL instead of LJ
@@ -44,9 +49,10 @@ static __global__ void __launch_bounds__(256)
 k_lj_small(SmallArgs a) {
   extern __shared__ double smem[];
   __shared__ double sh32[32];
-  const int sys = blockIdx.x;
-  const long long base = a.off[sys];
-  const int n = (int)(a.off[sys + 1] - base);
+  const bool split = a.split > 1;
+  const int sys = split ? 0 : blockIdx.x;
+  const long long base = a.single_n > 0 ? 0 : a.off[sys];
+  const int n = a.single_n > 0 ? a.single_n : (int)(a.off[sys + 1] - base);
   double* px = smem;  // 3n interleaved
   int* tp = reinterpret_cast<int*>(smem + 3 * n);  // ZBL: type index per atom
   for (int t = threadIdx.x; t < 3 * n; t += blockDim.x) px[t] = a.pos[3 * base + t];
@@ -78,35 +84,90 @@ k_lj_small(SmallArgs a) {
   __syncthreads();
 
   double e = 0.0;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    const double xi = px[3 * i], yi = px[3 * i + 1], zi = px[3 * i + 2];
-    const int ti = a.morse == 2 ? tp[i] : 0;
-    double fx = 0.0, fy = 0.0, fz = 0.0;
-    for (int j = 0; j < n; ++j) {
-      if (j == i) continue;
-      const double dx = fold_component(xsub(px[3 * j], xi), p.w[0], p.inv[0]);
-      const double dy = fold_component(xsub(px[3 * j + 1], yi), p.w[1], p.inv[1]);
-      const double dz = fold_component(xsub(px[3 * j + 2], zi), p.w[2], p.inv[2]);
-      const double r2 = xnorm2(dx, dy, dz);
-      if (!(r2 <= p.rc2)) continue;
-      lj_pair(p, ti, a.morse == 2 ? tp[j] : 0, dx, dy, dz, r2, e, fx, fy, fz);
-      if (a.emit.pairs != nullptr && i < j) {
-        const unsigned long long k = atomicAdd(a.emit.count, 1ull);
-        if ((long)k < a.emit.cap) {
-          a.emit.pairs[2 * k] = i;
-          a.emit.pairs[2 * k + 1] = j;
-          a.emit.shifts[3 * k] = a.emit.shifts[3 * k + 1] = a.emit.shifts[3 * k + 2] = 0;
+  if (!split) {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const double xi = px[3 * i], yi = px[3 * i + 1], zi = px[3 * i + 2];
+      const int ti = a.morse == 2 ? tp[i] : 0;
+      double fx = 0.0, fy = 0.0, fz = 0.0;
+      for (int j = 0; j < n; ++j) {
+        if (j == i) continue;
+        const double dx = fold_component(xsub(px[3 * j], xi), p.w[0], p.inv[0]);
+        const double dy = fold_component(xsub(px[3 * j + 1], yi), p.w[1], p.inv[1]);
+        const double dz = fold_component(xsub(px[3 * j + 2], zi), p.w[2], p.inv[2]);
+        const double r2 = xnorm2(dx, dy, dz);
+        if (!(r2 <= p.rc2)) continue;
+        lj_pair(p, ti, a.morse == 2 ? tp[j] : 0, dx, dy, dz, r2, e, fx, fy, fz);
+        if (a.emit.pairs != nullptr && i < j) {
+          const unsigned long long k = atomicAdd(a.emit.count, 1ull);
+          if ((long)k < a.emit.cap) {
+            a.emit.pairs[2 * k] = i;
+            a.emit.pairs[2 * k + 1] = j;
+            a.emit.shifts[3 * k] = a.emit.shifts[3 * k + 1] = a.emit.shifts[3 * k + 2] = 0;
+          }
         }
       }
+      a.F[3 * (base + i)] = fx;
+      a.F[3 * (base + i) + 1] = fy;
+      a.F[3 * (base + i) + 2] = fz;
     }
-    a.F[3 * (base + i)] = fx;
-    a.F[3 * (base + i) + 1] = fy;
-    a.F[3 * (base + i) + 2] = fz;
+  } else {
+    // ONE system spread over the blocks of the grid (a single 500-atom system on one SM would leave 147
+    // idle): four lanes share an atom and take every fourth partner, the four partial sums are folded by
+    // two shuffles (a fixed tree), block b owns atoms [b T / 4, (b + 1) T / 4)
+    const int apb = blockDim.x >> 2, sub = threadIdx.x & 3;
+    const int i = blockIdx.x * apb + (threadIdx.x >> 2);
+    double fx = 0.0, fy = 0.0, fz = 0.0;
+    if (i < n) {
+      const double xi = px[3 * i], yi = px[3 * i + 1], zi = px[3 * i + 2];
+      const int ti = a.morse == 2 ? tp[i] : 0;
+      for (int j = sub; j < n; j += 4) {
+        if (j == i) continue;
+        const double dx = fold_component(xsub(px[3 * j], xi), p.w[0], p.inv[0]);
+        const double dy = fold_component(xsub(px[3 * j + 1], yi), p.w[1], p.inv[1]);
+        const double dz = fold_component(xsub(px[3 * j + 2], zi), p.w[2], p.inv[2]);
+        const double r2 = xnorm2(dx, dy, dz);
+        if (!(r2 <= p.rc2)) continue;
+        lj_pair(p, ti, a.morse == 2 ? tp[j] : 0, dx, dy, dz, r2, e, fx, fy, fz);
+      }
+    }
+#pragma unroll
+    for (int off = 1; off < 4; off <<= 1) {
+      fx += __shfl_xor_sync(0xffffffffu, fx, off);
+      fy += __shfl_xor_sync(0xffffffffu, fy, off);
+      fz += __shfl_xor_sync(0xffffffffu, fz, off);
+    }
+    if (i < n && sub == 0) {
+      a.F[3 * i] = fx;
+      a.F[3 * i + 1] = fy;
+      a.F[3 * i + 2] = fz;
+    }
   }
   const double bs = block_sum(e, sh32);
+  if (!split) {
+    if (threadIdx.x == 0) {
+      a.E[sys] = bs;
+      __threadfence_system();  // (a host that polls the flag word must find the results behind it)
+      a.sys_flags[sys] = 0u;   // every exit of the batch kernels writes the flag word: no reset copy needed
+    }
+    return;
+  }
+  // split: the block that finishes last adds the block sums in block order and signs off
+  __shared__ int last;
+  __threadfence_system();  // this block's forces before its ticket
   if (threadIdx.x == 0) {
-    a.E[sys] = bs;
-    a.sys_flags[sys] = 0u;  // (every exit of the batch kernels writes the flag word: no reset copy needed)
+    a.e_parts[blockIdx.x] = bs;
+    __threadfence();
+    last = atomicAdd(a.ticket, 1) == (int)gridDim.x - 1;
+  }
+  __syncthreads();
+  if (last && threadIdx.x == 0) {
+    __threadfence();
+    double tot = 0.0;
+    for (unsigned b = 0; b < gridDim.x; ++b) tot += __ldcg(a.e_parts + b);
+    a.E[0] = tot;
+    *a.ticket = 0;
+    __threadfence_system();
+    a.sys_flags[0] = 0u;
   }
 }
 
@@ -214,9 +275,9 @@ k_eam_small(SmallArgs a) {
   __shared__ int hist[256];
 
   const int sys = blockIdx.x;
-  const long long base = a.off[sys];
+  const long long base = a.single_n > 0 ? 0 : a.off[sys];
   const long long zbase = a.z_shared ? 0 : base;
-  const int n = (int)(a.off[sys + 1] - base);
+  const int n = a.single_n > 0 ? a.single_n : (int)(a.off[sys + 1] - base);
   const int maxnb = a.maxnb;
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -317,12 +378,15 @@ k_eam_small(SmallArgs a) {
   if (blk_flags & (kFlagForeignZ | kFlagNonFinite | kFlagShiftRange | kFlagSingularBox)) {
     // the reference leaves energy and forces zeroed on failure
     for (int t = threadIdx.x; t < 3 * n; t += blockDim.x) a.F[3 * base + t] = 0.0;
+    __threadfence_system();
+    __syncthreads();
     if (threadIdx.x == 0) {
       a.E[sys] = 0.0;
-      a.sys_flags[sys] = blk_flags;
       a.sys_bad[2 * sys] = blk_bad[0];
       a.sys_bad[2 * sys + 1] =
           ((blk_flags & kFlagForeignZ) && blk_bad[0] != INT_MAX) ? a.Z[zbase + blk_bad[0]] : 0;
+      __threadfence_system();
+      a.sys_flags[sys] = blk_flags;
     }
     return;
   }
@@ -549,8 +613,11 @@ k_eam_small(SmallArgs a) {
   __syncthreads();
   if (blk_flags & kFlagCoincident) {
     for (int t = threadIdx.x; t < 3 * n; t += blockDim.x) a.F[3 * base + t] = 0.0;
+    __threadfence_system();
+    __syncthreads();
     if (threadIdx.x == 0) {
       a.E[sys] = 0.0;
+      __threadfence_system();
       a.sys_flags[sys] = kFlagCoincident;
     }
     return;
@@ -596,11 +663,13 @@ k_eam_small(SmallArgs a) {
       eatom[i] += ep;
     }
   }
+  if (a.single_n > 0) __threadfence_system();  // (a host that polls the flag word must find the forces behind it)
   __syncthreads();
   for (int i = threadIdx.x; i < n; i += blockDim.x) e += eatom[i];  // atom order: reproducible
   const double bs = block_sum(e, sh32);
   if (threadIdx.x == 0) {
     a.E[sys] = bs;
+    __threadfence_system();
     a.sys_flags[sys] = 0u;
   }
 }
