@@ -570,6 +570,8 @@ inline bool is_eam(int kind) { return kind == RGPOT_B200_CUH2 || kind == RGPOT_B
 // potentials that read atomic numbers and refuse foreign species (CuH2: 29 / 1, FeHe: 26 / 2)
 inline bool reads_species(int kind) { return kind == RGPOT_B200_CUH2 || kind == RGPOT_B200_FEHE; }
 inline double eam_rcut(int kind) { return kind == RGPOT_B200_EAM_AL ? 7.1 : 6.1; }
+// potentials whose small systems run on k_eam_small (list-based block-per-system kernel)
+inline bool uses_eam_small(int kind) { return is_eam(kind) || kind == RGPOT_B200_FEHE; }
 
 int check_launch(RgpotB200Pot* pot, const char* what) {
   cudaError_t e = cudaGetLastError();
@@ -1247,13 +1249,14 @@ int launch_small(RgpotB200Pot* pot, size_t nsys, long nmax, const long long* d_o
   a.m_re = pot->cfg.morse_re;
   a.m_ecut = pot->morse_ecut;
   if (emit) a.emit = *emit;
-  if (is_eam(pot->cfg.kind)) {
+  if (uses_eam_small(pot->cfg.kind)) {
     const bool al = pot->cfg.kind == RGPOT_B200_EAM_AL;
+    const bool fehe = pot->cfg.kind == RGPOT_B200_FEHE;
     const size_t smem = eam_small_smem(nmax, maxnb);
     const int tpa = eam_small_tpa(nmax);
     int threads = (int)std::min<long>(448, ((nmax * tpa + 31) / 32) * 32);
     if (threads < 32) threads = 32;
-    const int attr_bit = 1 << ((tpa == 1 ? 0 : tpa == 2 ? 1 : tpa == 4 ? 2 : 3) * 2 + (al ? 1 : 0));
+    const int attr_bit = 1 << ((tpa == 1 ? 0 : tpa == 2 ? 1 : tpa == 4 ? 2 : 3) * 3 + (al ? 1 : (fehe ? 2 : 0)));
     auto launch = [&](auto kern) -> int {
       if (!(pot->small_attr_set & attr_bit)) {  // once per handle and kernel: the calls cost microseconds
         cudaFuncAttributes fa;
@@ -1271,10 +1274,10 @@ int launch_small(RgpotB200Pot* pot, size_t nsys, long nmax, const long long* d_o
       return check_launch(pot, "k_eam_small");
     };
     switch (tpa) {
-      case 1: return al ? launch(k_eam_small<1, EAM_AL>) : launch(k_eam_small<1, EAM_CUH2>);
-      case 2: return al ? launch(k_eam_small<2, EAM_AL>) : launch(k_eam_small<2, EAM_CUH2>);
-      case 4: return al ? launch(k_eam_small<4, EAM_AL>) : launch(k_eam_small<4, EAM_CUH2>);
-      default: return al ? launch(k_eam_small<8, EAM_AL>) : launch(k_eam_small<8, EAM_CUH2>);
+      case 1: return fehe ? launch(k_eam_small<1, EAM_FEHE>) : al ? launch(k_eam_small<1, EAM_AL>) : launch(k_eam_small<1, EAM_CUH2>);
+      case 2: return fehe ? launch(k_eam_small<2, EAM_FEHE>) : al ? launch(k_eam_small<2, EAM_AL>) : launch(k_eam_small<2, EAM_CUH2>);
+      case 4: return fehe ? launch(k_eam_small<4, EAM_FEHE>) : al ? launch(k_eam_small<4, EAM_AL>) : launch(k_eam_small<4, EAM_CUH2>);
+      default: return fehe ? launch(k_eam_small<8, EAM_FEHE>) : al ? launch(k_eam_small<8, EAM_AL>) : launch(k_eam_small<8, EAM_CUH2>);
     }
   }
   const size_t smem = sizeof(double) * 3 * (size_t)nmax + sizeof(int) * (size_t)nmax + 16;
@@ -1298,8 +1301,7 @@ int launch_small(RgpotB200Pot* pot, size_t nsys, long nmax, const long long* d_o
 
 // can a system of n atoms run on the all-pairs kernels?
 bool small_eligible(const RgpotB200Pot* pot, long n) {
-  if (pot->cfg.kind == RGPOT_B200_FEHE) return false;  // gather path only (two density channels)
-  if (is_eam(pot->cfg.kind)) return n <= 512 && eam_small_maxnb(pot, n) > 0;
+  if (uses_eam_small(pot->cfg.kind)) return n <= 512 && eam_small_maxnb(pot, n) > 0;
   if (pot->cfg.lj_all_images) return false;  // opt-in mode lives on the cell path only
   return n <= 2048;
 }
@@ -1903,7 +1905,7 @@ static int force_device_impl(RgpotB200Pot* pot, long n, const double* d_pos, con
     CU_TRY(pot, cudaMemcpyAsync(pot->b_off.p, off, sizeof off, cudaMemcpyHostToDevice, st));
     CU_TRY(pot, cudaMemcpyAsync(pot->b_boxes.p, hb, sizeof hb, cudaMemcpyHostToDevice, st));
     CU_TRY(pot, cudaMemsetAsync(pot->b_flags.p, 0, sizeof(unsigned), st));
-    const int maxnb = is_eam(kind) ? eam_small_maxnb(pot, n) : 0;
+    const int maxnb = uses_eam_small(kind) ? eam_small_maxnb(pot, n) : 0;
     int s = launch_small(pot, 1, n, pot->b_off.as<long long>(), pot->b_boxes.as<double>(), d_pos, d_Z,
                          d_F, d_E, pot->b_flags.as<unsigned>(), pot->b_bad.as<int>(), maxnb, st, emit);
     if (s) return s;
@@ -2175,10 +2177,10 @@ static int force_small_fast(RgpotB200Pot* pot, long nAtoms, const double* positi
   h_bad[0] = INT_MAX;
   h_bad[1] = 0;
   const size_t iE = 11 + 6 * n;
-  const int maxnb = is_eam(pot->cfg.kind) ? eam_small_maxnb(pot, nAtoms) : 0;
+  const int maxnb = uses_eam_small(pot->cfg.kind) ? eam_small_maxnb(pot, nAtoms) : 0;
   cudaStream_t st = pot->stream;
   int s = 0;
-  if (!is_eam(pot->cfg.kind) && nAtoms >= 128) {
+  if (!uses_eam_small(pot->cfg.kind) && nAtoms >= 128) {
     // a pair potential on a few hundred atoms: one block would leave 147 SMs idle.  The inputs go to
     // the device in ONE copy (every block reads all of them), the atoms are spread over the blocks,
     // results land in the mapped block.
@@ -2556,7 +2558,7 @@ static int batch_device_impl(RgpotB200Pot* pot, size_t nsys, const size_t* offse
   CU_TRY(pot, cudaMemsetAsync(pot->b_flags.p, 0, sizeof(unsigned) * nsys, st));
 
   if (!small_ids.empty()) {
-    const int maxnb = eam ? eam_small_maxnb(pot, nmax_small) : 0;
+    const int maxnb = uses_eam_small(kind) ? eam_small_maxnb(pot, nmax_small) : 0;
     if (small_ids.size() == nsys) {
       int s = launch_small(pot, nsys, nmax_small, pot->b_off.as<long long>(), d_boxes, d_pos, d_Z, d_F,
                            d_E, pot->b_flags.as<unsigned>(), pot->b_bad.as<int>(), maxnb, st, nullptr);
@@ -2576,7 +2578,7 @@ static int batch_device_impl(RgpotB200Pot* pot, size_t nsys, const size_t* offse
   for (int id : big_ids) {
     const long n = (long)(offsets[id + 1] - offsets[id]);
     const size_t o = offsets[id];
-    const bool trivial = eam ? n < 1 : (n < 2 || (kind != RGPOT_B200_LJ_CLUSTER && kind != RGPOT_B200_ZBL && !(pot->cfg.cutoff > 0.0)));
+    const bool trivial = uses_eam_small(kind) ? n < 1 : (n < 2 || (kind != RGPOT_B200_LJ_CLUSTER && kind != RGPOT_B200_ZBL && !(pot->cfg.cutoff > 0.0)));
     if (trivial) {
       if (n > 0) CU_TRY(pot, cudaMemsetAsync(d_F + 3 * o, 0, sizeof(double) * 3 * n, st));
       CU_TRY(pot, cudaMemsetAsync(d_E + id, 0, sizeof(double), st));
@@ -2834,7 +2836,7 @@ static int batch_pipeline(RgpotB200Pot* pot, size_t nsys, const size_t* rel, lon
   CU_TRY(pot, cudaEventRecord(pot->ev_ready, st0));
   for (auto& s : pot->pipe) CU_TRY(pot, cudaStreamWaitEvent(s, pot->ev_ready, 0));
 
-  const int maxnb = is_eam(pot->cfg.kind) ? eam_small_maxnb(pot, nmax) : 0;
+  const int maxnb = uses_eam_small(pot->cfg.kind) ? eam_small_maxnb(pot, nmax) : 0;
   // chunks: about sixteen per batch, but never so short that a chunk's kernel is a few partial waves
   size_t chunk = (nsys + 15) / 16;
   chunk = std::min<size_t>(std::max<size_t>(chunk, (size_t)8 * pot->sm_count), 8192);

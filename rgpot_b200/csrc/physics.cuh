@@ -46,7 +46,7 @@ struct EamParams {
 // -2 g rho(r), the embedding +g rho (rgpot_eam_al.f90:159-171, 188-213).  Each model has its own
 // __constant__ block (handles of both kinds may run concurrently) selected at compile time, so the
 // coefficients stay immediate operands of the FP64 instructions.
-enum { EAM_CUH2 = 0, EAM_AL = 1 };
+enum { EAM_CUH2 = 0, EAM_AL = 1, EAM_FEHE = 2 };  // (EAM_FEHE: the batch kernel only; its terms are the fehe_* functions below)
 __constant__ EamParams c_eam;
 __constant__ EamParams c_eam_al;
 
@@ -54,6 +54,12 @@ template <int M>
 RB_D const EamParams& eam_par() {
   if (M == EAM_AL) return c_eam_al;
   return c_eam;
+}
+// table cutoff of a model (rgpot_fehe.f90:167-176: the largest of the five Fe-He cutoffs)
+template <int M>
+RB_D double model_rcut() {
+  if (M == EAM_FEHE) return 5.4;
+  return eam_par<M>().rcut;
 }
 
 // ---- pair potentials on the LJ pair search ------------------------------------------------------

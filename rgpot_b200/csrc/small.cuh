@@ -265,7 +265,8 @@ struct SmallBoxF {  // FP32 mirror for the prefilter
 template <int TPA, int M>
 __global__ void __launch_bounds__(448, 2)
 k_eam_small(SmallArgs a) {
-  const EamParams& P = eam_par<M>();
+  constexpr bool kFeHe = M == EAM_FEHE;  // two density channels, branches on r = sqrt(d2) (rgpot_fehe.f90)
+  const double model_rc = model_rcut<M>();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ double sh32[32];
   __shared__ SmallBox sb;
@@ -302,7 +303,7 @@ k_eam_small(SmallArgs a) {
 
   exp_table_init();
   if (threadIdx.x == 0) {
-    small_box_init(a.boxes + 9 * (size_t)sys, P.rcut, sb);
+    small_box_init(a.boxes + 9 * (size_t)sys, model_rc, sb);
     blk_flags = sb.bad ? kFlagSingularBox : 0u;  // vesin: "the box matrix is not invertible"
     blk_bad[0] = INT_MAX;
     blk_bad[1] = 0;
@@ -316,8 +317,8 @@ k_eam_small(SmallArgs a) {
                   sb.H[6] == 0.0 && sb.H[7] == 0.0;
       // FP32 error of the wrapped fractional separation (~3 ulp of 1) times the cell size,
       // plus the rounding of the Cartesian norm: generous, the exact test follows anyway
-      const double margin = 1.0e-6 * hmax + 1.0e-5 * P.rcut;
-      const double thr = P.rcut + margin;
+      const double margin = 1.0e-6 * hmax + 1.0e-5 * model_rc;
+      const double thr = model_rc + margin;
       sbf.thr2 = (float)(thr * thr * (1.0 + 1.0e-6));
     }
   }
@@ -339,9 +340,9 @@ k_eam_small(SmallArgs a) {
     cnt[i] = 0;
     const int zn = M == EAM_AL ? 29 : a.Z[zbase + i];  // EAM-Al is single-species: atomic numbers are not read
     int sp = 0;
-    if (zn == 29) {
+    if (zn == (kFeHe ? 26 : 29)) {  // rgpot_cuh2.f90:463-489 / rgpot_fehe.f90:541-569
       sp = 0;
-    } else if (zn == 1) {
+    } else if (zn == (kFeHe ? 2 : 1)) {
       sp = 1;
     } else {
       atomicOr(&blk_flags, kFlagForeignZ);
@@ -391,7 +392,7 @@ k_eam_small(SmallArgs a) {
     return;
   }
 
-  const double rc2 = P.rc2;
+  const double rc2 = xmul(model_rc, model_rc);
   const bool wrapped_atoms = (blk_flags & kFlagAtomShift) != 0;
 
   // ---- phase B
@@ -568,24 +569,27 @@ k_eam_small(SmallArgs a) {
   }
   __syncthreads();
   double* eatom = g3;  // per-atom energies (the fractional coordinates are no longer needed)
+  double* dfs = g3 + n;  // Fe-He: F'(rho) of the s-band channel
 
   const int sub = threadIdx.x % TPA;
   const int grp = threadIdx.x / TPA;
   const int ngrp = blockDim.x / TPA;
-  const double rc2_phys = P.rc2_phys;
+  double rc2_phys = rc2;
+  if (!kFeHe) rc2_phys = eam_par<M == EAM_FEHE ? EAM_CUH2 : M>().rc2_phys;
 
   double e = 0.0;
   // ---- phase D: density, embedding
   for (int ib = 0; ib < n; ib += ngrp) {
     const int slot = ib + grp;
     const bool vi = slot < n;
-    double rho = 0.0;
+    double rho = 0.0, rho_s = 0.0;
     bool coincident = false;
     int i = 0;
     if (vi) {
       i = perm[slot];
       const int c = cnt16[i * TPA + sub];
-      const double xi = pos3[3 * i], yi = pos3[3 * i + 1], zi = pos3[3 * i + 2];
+      const int zi = spc[i];
+      const double xi = pos3[3 * i], yi = pos3[3 * i + 1], zi_ = pos3[3 * i + 2];
       const unsigned short* row = list + i * TPA + sub;
       for (int s = 0; s < c; ++s) {
         const unsigned en = row[s * NTL];
@@ -593,19 +597,36 @@ k_eam_small(SmallArgs a) {
         const double* sv = svt + 3 * ((en >> 9) & 31u);
         const double vx = xadd(xsub(pj[0], xi), sv[0]);
         const double vy = xadd(xsub(pj[1], yi), sv[1]);
-        const double vz = xadd(xsub(pj[2], zi), sv[2]);
+        const double vz = xadd(xsub(pj[2], zi_), sv[2]);
         const double d2 = xnorm2(vx, vy, vz);
-        if (d2 == 0.0) coincident = true;  // dist <= 0 guard, rgpot_cuh2.f90:422-428
-        if (!(d2 < rc2_phys)) continue;    // :522
-        rho += eam_density_entry<M>((int)(en >> 14), d2);
+        if (kFeHe) {
+          if (!(d2 < rc2)) continue;  // vesin :1202; every term then checks its own cutoff on sqrt(d2)
+          double r1, dr1;
+          const int ch = fehe_density(zi, (int)(en >> 14), sqrt(d2), r1, dr1);  // atom_densities :480-500
+          if (ch == 0) rho += r1;
+          if (ch == 1) rho_s += r1;
+        } else {
+          if (d2 == 0.0) coincident = true;  // dist <= 0 guard, rgpot_cuh2.f90:422-428
+          if (!(d2 < rc2_phys)) continue;    // :522
+          rho += eam_density_entry<M == EAM_FEHE ? EAM_CUH2 : M>((int)(en >> 14), d2);
+        }
       }
     }
 #pragma unroll
-    for (int off = TPA / 2; off > 0; off >>= 1) rho += __shfl_xor_sync(0xffffffffu, rho, off);
+    for (int off = TPA / 2; off > 0; off >>= 1) {
+      rho += __shfl_xor_sync(0xffffffffu, rho, off);
+      if (kFeHe) rho_s += __shfl_xor_sync(0xffffffffu, rho_s, off);
+    }
     if (coincident) atomicOr(&blk_flags, kFlagCoincident);
     if (vi && sub == 0) {
       double emb, demb;
-      eam_embed<M>(spc[i], rho, emb, demb);
+      if (kFeHe) {
+        double dems;
+        fehe_embed(spc[i], rho, rho_s, emb, demb, dems);
+        dfs[i] = dems;
+      } else {
+        eam_embed<M == EAM_FEHE ? EAM_CUH2 : M>(spc[i], rho, emb, demb);
+      }
       dfd[i] = demb;
       eatom[i] = emb;
     }
@@ -645,8 +666,24 @@ k_eam_small(SmallArgs a) {
         const double vy = xadd(xsub(pj[1], yi), sv[1]);
         const double vz = xadd(xsub(pj[2], zi_), sv[2]);
         const double d2 = xnorm2(vx, vy, vz);
-        if (!(d2 < rc2_phys)) continue;
-        eam_force_entry<M>(zi, (int)(en >> 14), dfd_i, dfd[j], vx, vy, vz, d2, ep, fx, fy, fz);
+        if (kFeHe) {
+          if (!(d2 < rc2)) continue;
+          const double r = sqrt(d2);
+          const int zj = (int)(en >> 14);
+          double v, dv, r1, dr1;
+          fehe_pair(zi, zj, r, v, dv);  // atom_contribution :509-538
+          const int ch = fehe_density(zi, zj, r, r1, dr1);
+          ep += 0.5 * v;
+          double radial = dv;
+          if (ch == 0) radial += (dfd_i + dfd[j]) * dr1;
+          if (ch == 1) radial += (dfs[i] + dfs[j]) * dr1;
+          fx += radial * (vx / r);
+          fy += radial * (vy / r);
+          fz += radial * (vz / r);
+        } else {
+          if (!(d2 < rc2_phys)) continue;
+          eam_force_entry<M == EAM_FEHE ? EAM_CUH2 : M>(zi, (int)(en >> 14), dfd_i, dfd[j], vx, vy, vz, d2, ep, fx, fy, fz);
+        }
       }
     }
 #pragma unroll

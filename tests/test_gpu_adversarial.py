@@ -58,7 +58,7 @@ def lj_fluid_with_boundary_pairs(n, rc, ulps, seed):
 @pytest.mark.parametrize("ulps", [0, 1, 2, 8, -1, -2, -8])
 def test_brick_lj_pairs_at_the_cutoff(oracle, ulps):
     rc = 2.5
-    pos, box = lj_fluid_with_boundary_pairs(4000, rc, ulps, 31 + ulps)
+    pos, box = lj_fluid_with_boundary_pairs(4000, rc, ulps, 131 + ulps)
     z = np.ones(len(pos), np.int32)
     e_o, f_o, _ = oracle.lj_force(pos, box, 1.0, rc, 1.0)
     for opts in ({"brick_tpa": 1}, {"brick_tpa": 2}, {"brick_tpa": 4}, {"fine": 1, "brick_tpa": 2}, {"brick": 222},
@@ -123,7 +123,7 @@ def sheared_cu_with_boundary_pairs(cells, ulps, seed, shear_deg=60.0):
 
 @pytest.mark.parametrize("ulps", [0, 1, 8, -1, -8])
 def test_brick_eam_pairs_at_the_cutoff_in_a_sheared_cell(oracle, ulps):
-    pos, Z, box = sheared_cu_with_boundary_pairs(7, ulps, 5 + ulps)
+    pos, Z, box = sheared_cu_with_boundary_pairs(7, ulps, 105 + ulps)
     e_o, f_o = oracle.cuh2_force(pos, Z, box)
     for opts in ({"brick_tpa": 2}, {"brick_tpa": 4}, {"fine": 1, "brick_tpa": 4}, {"handoff": 0, "brick_tpa": 4}):
         pot = rgpot_b200.CuH2Pot()
