@@ -432,8 +432,9 @@ def run_cuh2_batch(args, world, rank, local):
         d2h = pos.nbytes + n_cfg * 8
         gbs = rgpot_b200.measure_copy_gbs(list(range(world)), h2d // world, d2h // world)
         one_call = {"one_s": one_s, "pin_s": pin_s, "h2d": h2d, "d2h": d2h, "copy_gbs": gbs, "host_threads_per_gpu": per_dev,
-                    "cpus": ncpu_all}
+                    "cpus": ncpu_all, "cxx": None}
         del multi
+        one_call["cxx"] = cxx_plugin_line(n_cfg, e2e_steps, world, per_dev)
     host_barrier(world)
 
     value = n_atoms_global * args.steps / (dev_ms * 1e-3)
@@ -480,7 +481,7 @@ def run_cuh2_batch(args, world, rank, local):
                          "value_at_ceiling": (n_atoms_global / ceiling_s) if ceiling_s else None,
                          "e2e_pinned_over_ceiling": (ceiling_s * e2e_steps / one_call["pin_s"]) if ceiling_s else None,
                          "what": "plain pinned cudaMemcpyAsync of the same H2D + D2H bytes on these %d GPUs at once" % world},
-        "sustained": sustained,
+        "sustained": sustained, "cxx_plugin": one_call["cxx"],
         "roofline": roofline, "clocks": clocks,
         "config": {"workload": f"cuh2_batch: {n_cfg} perturbed 218-atom Cu slab + H2 configs, ONE global batch cut "
                                f"across {world} GPU(s) (BASELINE configs[4])",
@@ -488,6 +489,30 @@ def run_cuh2_batch(args, world, rank, local):
                    "parallelism": f"batch cut by atoms into {world} contiguous range(s), no collective",
                    "l2": "inputs + outputs (0.7 GB per step) exceed the 126 MB L2"},
     }
+
+
+def cxx_plugin_line(n_cfg, steps, n_dev, host_threads):
+    """The same batch through the C++ plugin class itself: rgpot::CuH2CudaPot::forceBatch(const ForceBatch&)
+    on separately heap-allocated systems, timed inside a C++ program (rgpot_b200/host/bench_host.cc)."""
+    import tempfile
+    from rgpot_b200 import workloads
+    exe = os.path.join(ROOT, "rgpot_b200", "host", "bench_host")
+    if not os.path.exists(exe):
+        return {"unavailable": "rgpot_b200/host/bench_host is not built"}
+    pos, Z, box = workloads.cuh2_slab218()
+    with tempfile.NamedTemporaryFile(suffix=".bin", delete=False) as fh:
+        fh.write(np.ascontiguousarray(pos, dtype=np.float64).tobytes())
+        fh.write(np.ascontiguousarray(Z, dtype=np.int32).tobytes())
+        fh.write(np.ascontiguousarray(box, dtype=np.float64).tobytes())
+        path = fh.name
+    try:
+        out = subprocess.run([exe, path, str(n_cfg), str(steps), str(n_dev), str(host_threads)], capture_output=True,
+                             text=True, timeout=300)
+        return json.loads(out.stdout.strip().splitlines()[-1])
+    except Exception as exc:  # noqa: BLE001
+        return {"unavailable": repr(exc)[:200]}
+    finally:
+        os.unlink(path)
 
 
 def run_single_system(args, name, local):
@@ -768,7 +793,7 @@ def main():
                 "dtype": "f64", "data": "synthetic",
                 "config": res["config"], "e2e": res["e2e"], "gpu_launches": res["gpu_launches"],
                 "roofline": res["roofline"], "clocks": res["clocks"]}
-        for key in ("e2e_pinned", "e2e_per_rank", "copy_ceiling", "sustained"):
+        for key in ("e2e_pinned", "e2e_per_rank", "copy_ceiling", "sustained", "cxx_plugin"):
             if res.get(key) is not None:
                 line[key] = res[key]
         if world == 1:

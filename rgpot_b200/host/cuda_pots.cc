@@ -38,6 +38,13 @@ Engine::Engine(int kind, const LJCudaConfig &c) {
   RgpotB200Config cfg;
   rgpot_b200_default_config(kind, &cfg);
   cfg.device = c.device;
+  cfg.host_threads = c.host_threads;
+  if (c.devices.size() > 16) throw std::invalid_argument("rgpot_b200: at most 16 devices");
+  if (!c.devices.empty()) {
+    cfg.device = c.devices[0];
+    cfg.n_devices = static_cast<int>(c.devices.size());
+    for (size_t k = 0; k < c.devices.size(); ++k) cfg.devices[k] = c.devices[k];
+  }
   Fnv fp;
   fp.u64(kKernelVersion);
   if (kind == RGPOT_B200_EAM_AL || kind == RGPOT_B200_FEHE) {

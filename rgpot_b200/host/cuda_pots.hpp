@@ -22,6 +22,7 @@
 #include <cstdint>
 #include <memory>
 #include <string>
+#include <vector>
 
 #include "../../include/rgpot_b200.h"
 
@@ -34,6 +35,10 @@ struct LJCudaConfig {
   double psi = 1.0;
   int device = -1;
   bool all_images = false; ///< opt-in triclinic LJ (no reference counterpart)
+  /// Batches on several GPUs of the box: with more than one ordinal here (or device = -2 for "all"),
+  /// ONE forceBatch call cuts the batch across them (RgpotB200Config.devices); single systems use the first.
+  std::vector<int> devices;
+  int host_threads = 0; ///< helper threads per device for packing ForceBatch buffers (0 = automatic)
 };
 
 /// MorseConfig-compatible aggregate (Morse/MorsePot.hpp:31-36) plus the device ordinal.
