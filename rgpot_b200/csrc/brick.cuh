@@ -49,6 +49,10 @@ constexpr int tile_model(int pot) { return (pot == TILE_AL_DENSITY || pot == TIL
 // FP64 words staged per halo atom: position, + F'(rho) in a force pass, + the second channel's (Fe-He)
 constexpr int tile_words(int pot) { return pot == TILE_FEHE_FORCE ? 5 : (tile_is_force(pot) ? 4 : 3); }
 
+#ifndef RB_PHYS_UNROLL
+#define RB_PHYS_UNROLL 1
+#endif
+constexpr int kPhysUnroll = RB_PHYS_UNROLL;  // survivors per trip of the physics loop (tuning knob)
 constexpr int kBrickMaxThreads = 384;  // 2 blocks of 384 or 3 of 256 per SM at <= 85 registers
 constexpr int kBrickMaxHalo = 512;  // (4 + 2*2)^3
 constexpr int kBrickMaxCells = 64;
@@ -179,6 +183,44 @@ RB_D void brick_pair(const GatherArgs& a, double rc2, double rc2_phys, bool othe
   }
 }
 
+// One candidate of the large-system kernels (brick.cuh, tile.cu) at exact separation (dx, dy, dz), d2 = |d|^2 in the reference's
+// arithmetic.  For every potential but plain LJ this is brick_pair.  LJ (LJPot.cc:61-81) keeps RAW sums
+// and scales once per atom (tile_finish): with a = (psi^2 / r^2)^3 the pair energy is 4 u0 a (a - 1) - U_c
+// and the force factor 24 u0 a (2 a - 1) / r^2, so the loop accumulates a (a - 1), the pair count and
+// a (2 a - 1) / r^2 * d: three FP64 instructions fewer per pair than forming b = 4 u0 a first, a few ulp
+// from the reference's association, far inside the 1e-10 budget; accept / reject is untouched.
+template <int POT, class DfdJ, class DfsJ>
+RB_D void tile_pair(const GatherArgs& a, double rc2, double rc2_phys, bool other, int zi, int zj, double dfd_i,
+                    DfdJ&& dfd_j, double dfs_i, DfsJ&& dfs_j, double dx, double dy, double dz, double d2, double& e,
+                    double* acc, int& npair, bool& coincident) {
+  if (POT == TILE_LJ) {
+    if (d2 <= rc2 && other) {  // vesin_visit.hpp:104
+      const double invR2 = rcp_fast(d2);
+      const double sr2 = a.lj.psi2 * invR2;
+      const double a6 = sr2 * sr2 * sr2;
+      e = fma(a6, a6 - 1.0, e);
+      ++npair;
+      const double t = (a6 * invR2) * fma(2.0, a6, -1.0);
+      acc[0] = fma(t, dx, acc[0]);
+      acc[1] = fma(t, dy, acc[1]);
+      acc[2] = fma(t, dz, acc[2]);
+    }
+  } else {
+    brick_pair<POT>(a, rc2, rc2_phys, other, zi, zj, dfd_i, dfd_j, dfs_i, dfs_j, dx, dy, dz, d2, e, acc, coincident);
+  }
+}
+// raw LJ sums -> half the pair energy and the force on the atom (d = r_j - r_i, so F_i = -24 u0 sum)
+template <int POT>
+RB_D void tile_finish(const GatherArgs& a, double* acc, double& e, int npair) {
+  if (POT == TILE_LJ) {
+    const double c = -24.0 * a.lj.u0;
+    acc[0] *= c;
+    acc[1] *= c;
+    acc[2] *= c;
+    e = fma(2.0 * a.lj.u0, e, -(0.5 * a.lj.shiftU) * (double)npair);
+  }
+}
+
 // ---- per-atom walk straight from global memory (the in-kernel slow path) -------------------------
 // For the atoms of a single cell whose stencil does not fit the staged capacity.  It visits the
 // candidates in the order the brick kernel does -- stencil row `row` belongs to partial sum
@@ -205,6 +247,7 @@ __device__ __noinline__ void brick_slow_atom(const GatherArgs& a, const BrickPla
   if (kForce && kFeHe) dfs_i = o.dfs_sorted[i];
   const int nrx = 2 * bp.ns[0] + 1, nry = 2 * bp.ns[1] + 1, nrows = nry * (2 * bp.ns[2] + 1);
   double part[TPA][4];
+  int npair = 0;
 #pragma unroll
   for (int sub = 0; sub < TPA; ++sub) {
     double acc[3] = {0.0, 0.0, 0.0}, e = 0.0;
@@ -252,9 +295,9 @@ __device__ __noinline__ void brick_slow_atom(const GatherArgs& a, const BrickPla
                        dz = xadd(xsub(pj.z, pi.z), svz);
           const double d2 = xnorm2(dx, dy, dz);
           const int zj = meta_species((unsigned long long)__double_as_longlong(pj.w));
-          brick_pair<POT>(a, rc2, rc2_phys, j != i || code != kShiftCodes / 2, zi, zj, dfd_i,
-                          [&]() { return o.dfd_sorted[j]; }, dfs_i, [&]() { return o.dfs_sorted[j]; }, dx, dy, dz, d2,
-                          e, acc, coincident);
+          tile_pair<POT>(a, rc2, rc2_phys, j != i || code != kShiftCodes / 2, zi, zj, dfd_i,
+                         [&]() { return o.dfd_sorted[j]; }, dfs_i, [&]() { return o.dfs_sorted[j]; }, dx, dy, dz, d2,
+                         e, acc, npair, coincident);
         }
       }
     }
@@ -268,6 +311,7 @@ __device__ __noinline__ void brick_slow_atom(const GatherArgs& a, const BrickPla
     for (int sub = 0; sub < TPA; sub += 2 * off)
 #pragma unroll
       for (int k = 0; k < 4; ++k) part[sub][k] += part[sub + off][k];
+  tile_finish<POT>(a, part[0], part[0][3], npair);
   if (kDensity) {
     double emb, demb;
     if (kFeHe) {
@@ -570,6 +614,7 @@ k_brick(const __grid_constant__ GatherArgs a, const __grid_constant__ BrickPlan 
         const int sub = tid % TPA;
         double acc[3] = {0.0, 0.0, 0.0};
         double e_thr = 0.0;  // this thread's share of the atom's energy
+        int npair = 0;       // LJ: accepted pairs (the cutoff shift is applied once per atom)
         int si = 0, gi = 0;
         const bool active = ai < natoms;
         unsigned lsa = lsa0;  // end of the list of the last round
@@ -669,6 +714,7 @@ k_brick(const __grid_constant__ GatherArgs a, const __grid_constant__ BrickPlan 
             }
             RB_TICK(2);
             // ---- physics: exact FP64 test and pair terms for the listed candidates ------------------------
+#pragma unroll kPhysUnroll
             for (unsigned la = lsa0; la < lsa; la += lstride) {
               unsigned short s16;
               asm volatile("ld.shared.u16 %0, [%1];" : "=h"(s16) : "r"(la));
@@ -693,8 +739,8 @@ k_brick(const __grid_constant__ GatherArgs a, const __grid_constant__ BrickPlan 
                 }
               }
               const double d2 = xnorm2(dx, dy, dz);
-              brick_pair<POT>(a, rc2, rc2_phys, sj != si, zi, info >> 8, dfd_i, [&]() { return c64w[sj]; }, dfs_i,
-                              [&]() { return c64w2[sj]; }, dx, dy, dz, d2, e_thr, acc, coincident);
+              tile_pair<POT>(a, rc2, rc2_phys, sj != si, zi, info >> 8, dfd_i, [&]() { return c64w[sj]; }, dfs_i,
+                             [&]() { return c64w2[sj]; }, dx, dy, dz, d2, e_thr, acc, npair, coincident);
             }
             RB_TICK(3);
           } while (more);
@@ -728,8 +774,10 @@ k_brick(const __grid_constant__ GatherArgs a, const __grid_constant__ BrickPlan 
 #pragma unroll
           for (int k = 0; k < NV; ++k) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], off);
           if (!kDensity) e_thr += __shfl_xor_sync(0xffffffffu, e_thr, off);
+          if (POT == TILE_LJ) npair += __shfl_xor_sync(0xffffffffu, npair, off);
         }
         if (active && sub == 0) {
+          if (!kDensity) tile_finish<POT>(a, acc, e_thr, npair);
           if (kDensity) {
             double emb, demb;
             if (kFeHe) {

@@ -278,6 +278,7 @@ struct RgpotB200Pot {
   int opt_tile_brick = 0;     // cells per brick as decimal xyz (0 = automatic)
   int opt_tile_cap = 0;       // staged capacity override (test hook: small values exercise cut boxes / the slow path)
   int opt_tile_wcap = 0;      // window chunk override
+  int opt_batch_chunk = 0;    // systems per pipeline chunk of a host batch (0 = automatic)
   long opt_fine_min = 20000;  // atoms from which half-cutoff cells are used
   long launches = 0;
   long pool_used = 0;   // survivor-list entries the density pass handed to the force pass
@@ -1757,6 +1758,11 @@ int rgpot_b200_set_option(RgpotB200Pot* pot, const char* key, long value) {
     pot->opt_tile_wcap = (int)value;
     return 0;
   }
+  if (strcmp(key, "batch_chunk") == 0) {
+    pot->opt_batch_chunk = (int)value;
+    for (auto& sh : pot->shards) sh.pot->opt_batch_chunk = (int)value;
+    return 0;
+  }
   return kStatusArgs;
 }
 
@@ -2837,9 +2843,11 @@ static int batch_pipeline(RgpotB200Pot* pot, size_t nsys, const size_t* rel, lon
   for (auto& s : pot->pipe) CU_TRY(pot, cudaStreamWaitEvent(s, pot->ev_ready, 0));
 
   const int maxnb = uses_eam_small(pot->cfg.kind) ? eam_small_maxnb(pot, nmax) : 0;
-  // chunks: about sixteen per batch, but never so short that a chunk's kernel is a few partial waves
-  size_t chunk = (nsys + 15) / 16;
+  // chunks: about thirty-two per batch (the first upload and the last download are not hidden behind
+  // anything: the shorter they are the better), but never so short that a kernel is a few partial waves
+  size_t chunk = (nsys + 31) / 32;
   chunk = std::min<size_t>(std::max<size_t>(chunk, (size_t)8 * pot->sm_count), 8192);
+  if (pot->opt_batch_chunk > 0) chunk = (size_t)pot->opt_batch_chunk;
   const size_t nchunks = (nsys + chunk - 1) / chunk;
   std::vector<cudaEvent_t> done(nchunks, nullptr);
   int rc = 0;

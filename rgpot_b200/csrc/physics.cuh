@@ -138,12 +138,19 @@ RB_D double exp_fast(double x) {
   const double kf = t - kMagic;
   double r = fma(kf, -6.93147180369123816490e-01 / 64.0, x);
   r = fma(kf, -1.90821492927058770002e-10 / 64.0, r);
+#ifdef RB_EXP_ESTRIN
+  // e^r = (1 + r) + r^2 ((1/2 + r/6) + r^2 (1/24 + r/120)): three levels instead of a five-deep chain
+  const double r2 = r * r;
+  const double q0 = 1.0 + r, q1 = fma(r, 1.0 / 6.0, 0.5), q2 = fma(r, 1.0 / 120.0, 1.0 / 24.0);
+  double p = fma(r2, fma(r2, q2, q1), q0);
+#else
   double p = 1.0 / 120.0;
   p = fma(p, r, 1.0 / 24.0);
   p = fma(p, r, 1.0 / 6.0);
   p = fma(p, r, 0.5);
   p = fma(p, r, 1.0);
   p = fma(p, r, 1.0);
+#endif
   p *= exp_table()[n & 63];
   return __hiloint2double(__double2hiint(p) + ((n >> 6) << 20), __double2loint(p));
 }

@@ -17,6 +17,11 @@
 
 namespace rb {
 
+#ifndef RB_SMALL_UNROLL
+#define RB_SMALL_UNROLL 1
+#endif
+constexpr int kSmallUnroll = RB_SMALL_UNROLL;  // list entries per trip of the density / force loops (tuning knob)
+
 struct SmallArgs {
   const double* pos;       // packed positions of all systems
   const int* Z;            // packed atomic numbers (may be null for LJ)
@@ -146,7 +151,7 @@ k_lj_small(SmallArgs a) {
   if (!split) {
     if (threadIdx.x == 0) {
       a.E[sys] = bs;
-      __threadfence_system();  // (a host that polls the flag word must find the results behind it)
+      if (a.single_n > 0) __threadfence_system();  // (a host that polls the flag word must find the results behind it)
       a.sys_flags[sys] = 0u;   // every exit of the batch kernels writes the flag word: no reset copy needed
     }
     return;
@@ -266,7 +271,9 @@ template <int TPA, int M>
 __global__ void __launch_bounds__(448, 2)
 k_eam_small(SmallArgs a) {
   constexpr bool kFeHe = M == EAM_FEHE;  // two density channels, branches on r = sqrt(d2) (rgpot_fehe.f90)
-  const double model_rc = model_rcut<M>();
+  // (compile-time selections: for the two analytic models every bound below stays the constant-memory
+  // operand it always was)
+  const double model_rc = kFeHe ? 5.4 : eam_par<kFeHe ? EAM_CUH2 : M>().rcut;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ double sh32[32];
   __shared__ SmallBox sb;
@@ -379,20 +386,20 @@ k_eam_small(SmallArgs a) {
   if (blk_flags & (kFlagForeignZ | kFlagNonFinite | kFlagShiftRange | kFlagSingularBox)) {
     // the reference leaves energy and forces zeroed on failure
     for (int t = threadIdx.x; t < 3 * n; t += blockDim.x) a.F[3 * base + t] = 0.0;
-    __threadfence_system();
+    if (a.single_n > 0) __threadfence_system();
     __syncthreads();
     if (threadIdx.x == 0) {
       a.E[sys] = 0.0;
       a.sys_bad[2 * sys] = blk_bad[0];
       a.sys_bad[2 * sys + 1] =
           ((blk_flags & kFlagForeignZ) && blk_bad[0] != INT_MAX) ? a.Z[zbase + blk_bad[0]] : 0;
-      __threadfence_system();
+      if (a.single_n > 0) __threadfence_system();
       a.sys_flags[sys] = blk_flags;
     }
     return;
   }
 
-  const double rc2 = xmul(model_rc, model_rc);
+  const double rc2 = kFeHe ? xmul(5.4, 5.4) : eam_par<kFeHe ? EAM_CUH2 : M>().rc2;
   const bool wrapped_atoms = (blk_flags & kFlagAtomShift) != 0;
 
   // ---- phase B
@@ -574,8 +581,7 @@ k_eam_small(SmallArgs a) {
   const int sub = threadIdx.x % TPA;
   const int grp = threadIdx.x / TPA;
   const int ngrp = blockDim.x / TPA;
-  double rc2_phys = rc2;
-  if (!kFeHe) rc2_phys = eam_par<M == EAM_FEHE ? EAM_CUH2 : M>().rc2_phys;
+  const double rc2_phys = kFeHe ? rc2 : eam_par<kFeHe ? EAM_CUH2 : M>().rc2_phys;
 
   double e = 0.0;
   // ---- phase D: density, embedding
@@ -591,6 +597,7 @@ k_eam_small(SmallArgs a) {
       const int zi = spc[i];
       const double xi = pos3[3 * i], yi = pos3[3 * i + 1], zi_ = pos3[3 * i + 2];
       const unsigned short* row = list + i * TPA + sub;
+#pragma unroll kSmallUnroll
       for (int s = 0; s < c; ++s) {
         const unsigned en = row[s * NTL];
         const double* pj = pos3 + 3 * (en & 511u);
@@ -634,11 +641,11 @@ k_eam_small(SmallArgs a) {
   __syncthreads();
   if (blk_flags & kFlagCoincident) {
     for (int t = threadIdx.x; t < 3 * n; t += blockDim.x) a.F[3 * base + t] = 0.0;
-    __threadfence_system();
+    if (a.single_n > 0) __threadfence_system();
     __syncthreads();
     if (threadIdx.x == 0) {
       a.E[sys] = 0.0;
-      __threadfence_system();
+      if (a.single_n > 0) __threadfence_system();
       a.sys_flags[sys] = kFlagCoincident;
     }
     return;
@@ -657,6 +664,7 @@ k_eam_small(SmallArgs a) {
       const double dfd_i = dfd[i];
       const double xi = pos3[3 * i], yi = pos3[3 * i + 1], zi_ = pos3[3 * i + 2];
       const unsigned short* row = list + i * TPA + sub;
+#pragma unroll kSmallUnroll
       for (int s = 0; s < c; ++s) {
         const unsigned en = row[s * NTL];
         const int j = (int)(en & 511u);
@@ -706,7 +714,7 @@ k_eam_small(SmallArgs a) {
   const double bs = block_sum(e, sh32);
   if (threadIdx.x == 0) {
     a.E[sys] = bs;
-    __threadfence_system();
+    if (a.single_n > 0) __threadfence_system();  // (only a polling host needs the order; a batch must not pay for it)
     a.sys_flags[sys] = 0u;
   }
 }

@@ -93,44 +93,6 @@ RB_D unsigned a_pair_empty(int t) {
 
 constexpr unsigned kRowEmpty = 0xffffu;
 
-// One candidate of the tile kernels at exact separation (dx, dy, dz), d2 = |d|^2 in the reference's
-// arithmetic.  For every potential but plain LJ this is brick_pair.  LJ (LJPot.cc:61-81) keeps RAW sums
-// and scales once per atom (tile_finish): with a = (psi^2 / r^2)^3 the pair energy is 4 u0 a (a - 1) - U_c
-// and the force factor 24 u0 a (2 a - 1) / r^2, so the loop accumulates a (a - 1), the pair count and
-// a (2 a - 1) / r^2 * d: three FP64 instructions fewer per pair than forming b = 4 u0 a first, a few ulp
-// from the reference's association, far inside the 1e-10 budget; accept / reject is untouched.
-template <int POT, class DfdJ, class DfsJ>
-RB_D void tile_pair(const GatherArgs& a, double rc2, double rc2_phys, bool other, int zi, int zj, double dfd_i,
-                    DfdJ&& dfd_j, double dfs_i, DfsJ&& dfs_j, double dx, double dy, double dz, double d2, double& e,
-                    double* acc, int& npair, bool& coincident) {
-  if (POT == TILE_LJ) {
-    if (d2 <= rc2 && other) {  // vesin_visit.hpp:104
-      const double invR2 = rcp_fast(d2);
-      const double sr2 = a.lj.psi2 * invR2;
-      const double a6 = sr2 * sr2 * sr2;
-      e = fma(a6, a6 - 1.0, e);
-      ++npair;
-      const double t = (a6 * invR2) * fma(2.0, a6, -1.0);
-      acc[0] = fma(t, dx, acc[0]);
-      acc[1] = fma(t, dy, acc[1]);
-      acc[2] = fma(t, dz, acc[2]);
-    }
-  } else {
-    brick_pair<POT>(a, rc2, rc2_phys, other, zi, zj, dfd_i, dfd_j, dfs_i, dfs_j, dx, dy, dz, d2, e, acc, coincident);
-  }
-}
-// raw LJ sums -> half the pair energy and the force on the atom (d = r_j - r_i, so F_i = -24 u0 sum)
-template <int POT>
-RB_D void tile_finish(const GatherArgs& a, double* acc, double& e, int npair) {
-  if (POT == TILE_LJ) {
-    const double c = -24.0 * a.lj.u0;
-    acc[0] *= c;
-    acc[1] *= c;
-    acc[2] *= c;
-    e = fma(2.0 * a.lj.u0, e, -(0.5 * a.lj.shiftU) * (double)npair);
-  }
-}
-
 // ---- per-atom walk straight from global memory (the in-kernel slow path) --------------------------
 // For a single group whose window does not fit the staged capacity.  It visits the group's window in
 // the kernel's order -- rows (z, y), cells along x, atoms in sorted order -- assigns window position w

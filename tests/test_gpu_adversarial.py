@@ -40,12 +40,21 @@ def lj_fluid_with_boundary_pairs(n, rc, ulps, seed):
     cells = int(np.floor(2 * L / (rc * (1 + 1e-6))))
     edge = L / cells
     extra = []
-    for trial in range(24):
+    trial = 0
+    while len(extra) < 48:
+        trial += 1
         corner = rng.integers(0, cells, size=3) * edge
         p0 = corner + (1e-9 if trial % 2 else -1e-9)
         u = rng.normal(size=3)
         u /= np.linalg.norm(u)
-        extra += [p0, p0 + u * np.sqrt(nudge(rc * rc, ulps))]
+        p1 = p0 + u * np.sqrt(nudge(rc * rc, ulps))
+        ok = True
+        for q in extra:  # no two inserted atoms on top of each other (periodic distance)
+            for p in (p0, p1):
+                d = np.mod(p - q + 0.5 * L, L) - 0.5 * L
+                ok = ok and (d ** 2).sum() > 0.9
+        if ok:
+            extra += [p0, p1]
     ins = np.mod(np.array(extra), L)
     keep = np.ones(n, bool)
     for p in ins:  # thin the fluid around the inserted atoms so forces stay moderate
