@@ -25,6 +25,7 @@
 #include "gather.cuh"
 #include "physics.cuh"
 #include "small.cuh"
+#include "single.cuh"
 #include "brick.cuh"
 #include "hash.cuh"
 #include "hostpipe.hpp"
@@ -279,6 +280,7 @@ struct RgpotB200Pot {
   int opt_tile_cap = 0;       // staged capacity override (test hook: small values exercise cut boxes / the slow path)
   int opt_tile_wcap = 0;      // window chunk override
   int opt_batch_chunk = 0;    // systems per pipeline chunk of a host batch (0 = automatic)
+  int opt_one = 1;            // single EAM systems of 64 .. 512 atoms on the many-block kernels (single.cuh)
   long opt_fine_min = 20000;  // atoms from which half-cutoff cells are used
   long launches = 0;
   long pool_used = 0;   // survivor-list entries the density pass handed to the force pass
@@ -352,6 +354,7 @@ struct RgpotB200Pot {
   // single small systems: one page-locked block the kernel reads and writes in place (zero copy)
   HostBuf h_fast;
   void* h_fast_dev = nullptr;  // its address as the device sees it
+  unsigned one_call_id = 0;    // single.cuh: calls so far (the kernels' fallback word compares against it)
   DevBuf d_fast;              // device copy of the inputs + block partials + ticket (one system over many blocks)
   // pageable single systems: pinned ring for the staged H2D / D2H of large arrays
   HostBuf h_ring;
@@ -1565,6 +1568,7 @@ static RgpotB200Pot* create_on_device(const RgpotB200Config* cfg, int dev, std::
     double tab[64];
     for (int j = 0; j < 64; ++j) tab[j] = exp2((double)j / 64.0);
     if (cudaMemcpyToSymbol(c_exp2tab, tab, sizeof tab) != cudaSuccess ||
+        cudaMemcpyToSymbol(g_exp2tab, tab, sizeof tab) != cudaSuccess ||
         (cfg->kind == RGPOT_B200_EAM_AL ? cudaMemcpyToSymbol(c_eam_al, &p, sizeof p)
                                         : cudaMemcpyToSymbol(c_eam, &p, sizeof p)) != cudaSuccess ||
         rb::tile_upload_constants(cfg->kind == RGPOT_B200_EAM_AL ? 1 : 0, &p, sizeof p, tab) != cudaSuccess) {
@@ -1756,6 +1760,10 @@ int rgpot_b200_set_option(RgpotB200Pot* pot, const char* key, long value) {
   }
   if (strcmp(key, "tile_wcap") == 0) {
     pot->opt_tile_wcap = (int)value;
+    return 0;
+  }
+  if (strcmp(key, "one") == 0) {
+    pot->opt_one = (int)value;
     return 0;
   }
   if (strcmp(key, "batch_chunk") == 0) {
@@ -2140,6 +2148,90 @@ static int download_array(RgpotB200Pot* pot, void* h_dst, const void* d_src, siz
   return 0;
 }
 
+// ONE EAM system of 64 .. 512 atoms on many blocks (single.cuh): one upload, two launches, results in the
+// mapped block.  Returns 0, a status, or -1 when the system is not the clean case (the batch kernel then
+// takes it and does the error reporting).
+static int force_one_eam(RgpotB200Pot* pot, long nAtoms, const double* positions, const int* atomicNrs,
+                         double* forces, double* energy, const double* box) {
+  const size_t n = (size_t)nAtoms;
+  const bool al = pot->cfg.kind == RGPOT_B200_EAM_AL;
+  const int nb = (int)((nAtoms + kOneAtomsPerBlock - 1) / kOneAtomsPerBlock);
+  // mapped block (8-byte words): box[9] | pos[3n] | Z[(n + 1) / 2] || F[3n] | E | flags
+  const size_t in_words = 9 + 3 * n + (n + 1) / 2, words = in_words + 3 * n + 2;
+  if (pot->h_fast.cap < words * 8) {
+    if (pot->h_fast.p) cudaFreeHost(pot->h_fast.p);
+    pot->h_fast.p = nullptr;
+    pot->h_fast.cap = 0;
+    const size_t want = std::max<size_t>(words * 8 * 2, 64u << 10);
+    CU_TRY(pot, cudaHostAlloc(&pot->h_fast.p, want, cudaHostAllocMapped | cudaHostAllocPortable));
+    pot->h_fast.cap = want;
+    pot->h_fast_dev = nullptr;
+  }
+  if (!pot->h_fast_dev) CU_TRY(pot, cudaHostGetDevicePointer(&pot->h_fast_dev, pot->h_fast.p, 0));
+  cudaStream_t st = pot->stream;
+  // device scratch (8-byte words): ticket | fallback | inputs | dfd[n] | eemb[n] | block energies
+  const size_t dev_words = 2 + in_words + 2 * n + (size_t)nb;
+  if (pot->d_fast.cap < dev_words * 8) {
+    CU_TRY(pot, pot->d_fast.reserve(dev_words * 8 * 2));
+    CU_TRY(pot, cudaMemsetAsync(pot->d_fast.p, 0, pot->d_fast.cap, st));
+    pot->one_call_id = 0;
+  }
+  double* h = pot->h_fast.as<double>();
+  double* hd = static_cast<double*>(pot->h_fast_dev);
+  memcpy(h, box, 9 * sizeof(double));
+  memcpy(h + 9, positions, sizeof(double) * 3 * n);
+  if (!al) memcpy(h + 9 + 3 * n, atomicNrs, sizeof(int) * n);
+  volatile unsigned* h_flags = reinterpret_cast<unsigned*>(h + in_words + 3 * n + 1);
+  *h_flags = 0xffffffffu;
+  double* dd = pot->d_fast.as<double>();
+  CU_TRY(pot, cudaMemcpyAsync(dd + 2, h, sizeof(double) * in_words, cudaMemcpyHostToDevice, st));
+  OneArgs a{};
+  a.box = dd + 2;
+  a.pos = dd + 2 + 9;
+  a.Z = reinterpret_cast<const int*>(dd + 2 + 9 + 3 * n);
+  a.n = (int)nAtoms;
+  a.dfd = dd + 2 + in_words;
+  a.eemb = a.dfd + n;
+  a.e_parts = a.eemb + n;
+  a.ticket = reinterpret_cast<int*>(dd);
+  a.fallback = reinterpret_cast<unsigned*>(dd + 1);
+  a.call_id = ++pot->one_call_id;
+  a.F = hd + in_words;
+  a.E = hd + in_words + 3 * n;
+  a.flags = reinterpret_cast<unsigned*>(hd + in_words + 3 * n + 1);
+  const size_t smem = one_smem_bytes((int)nAtoms);
+  const int threads = kOneAtomsPerBlock * kOneLanes;
+  if (!one_prepare_box(box, eam_rcut(pot->cfg.kind), a.sb, a.sbf)) return -1;  // singular / narrow cell: the batch kernel's case
+  {
+    // a cooperative launch: all blocks resident, so the grid barrier between the passes cannot hang
+    void* kargs[] = {(void*)&a};
+    const void* fn = al ? (const void*)k_eam_one<EAM_AL> : (const void*)k_eam_one<EAM_CUH2>;
+    CU_TRY(pot, cudaLaunchCooperativeKernel(fn, dim3(nb), dim3(threads), kargs, smem, st));
+  }
+  LAUNCH_CHECK(pot, "k_eam_one");
+  {
+    const auto t_start = std::chrono::steady_clock::now();
+    unsigned spins = 0;
+    while (*h_flags == 0xffffffffu) {
+      if ((++spins & 1023u) == 0 &&
+          std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count() > 2.0e-3) {
+        CU_TRY(pot, cudaStreamSynchronize(st));
+        break;
+      }
+#if defined(__x86_64__)
+      __builtin_ia32_pause();
+#endif
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);
+  }
+  const unsigned flags = *h_flags;
+  if (flags == 0xffffffffu) return fail(pot, kStatusCuda, "rgpot_b200: the single-system kernels left no status");
+  if (flags != 0u) return -1;
+  memcpy(forces, h + in_words, sizeof(double) * 3 * n);
+  *energy = h[in_words + 3 * n];
+  return 0;
+}
+
 // Single small systems (BASELINE configs[0] / [1], the reference's PotBench sizes): the whole call is
 // ONE kernel launch.  Inputs are written into a page-locked block that the kernel reads in place over
 // PCIe (a few kilobytes, read once), forces / energy / status come back the same way: no copy
@@ -2266,6 +2358,19 @@ int rgpot_b200_force(RgpotB200Pot* pot, long nAtoms, const double* positions, co
   if ((eam || zbl) && !atomicNrs) return fail(pot, kStatusArgs, "rgpot_b200: this potential needs atomic numbers");
   if (pot->cfg.kind != RGPOT_B200_LJ_CLUSTER && pot->cfg.kind != RGPOT_B200_ZBL && !box)
     return fail(pot, kStatusArgs, "rgpot_b200_force: null box");
+  if (is_eam(pot->cfg.kind) && pot->forced_path == 0 && pot->opt_one && nAtoms >= 64 && small_eligible(pot, nAtoms)) {
+    // one EAM system of a few hundred atoms: many blocks, two launches (single.cuh)
+    const int fo = force_one_eam(pot, nAtoms, positions, atomicNrs, forces, energy, box);
+    if (fo == 0) {
+      zero.armed = false;
+      return 0;
+    }
+    if (fo > 0) {
+      *energy = 0.0;
+      return fo;
+    }
+    // fo < 0: not the clean case; the batch kernel below takes the system
+  }
   if (!zbl && pot->forced_path != 1 && small_eligible(pot, nAtoms)) {
     const int fs = force_small_fast(pot, nAtoms, positions, atomicNrs, forces, energy, box);
     if (fs == 0) {

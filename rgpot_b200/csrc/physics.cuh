@@ -119,6 +119,10 @@ RB_D void lj_pair(const LJParams& p, int ti, int tj, double dx, double dy, doubl
 // About 1 ulp; 10 FP64 instructions and one shared-memory load, no branch.  (The radial terms of
 // the EAM are exp-bound: this is 6 FP64 instructions fewer than a table-free degree-11 kernel.)
 __constant__ double c_exp2tab[64];
+// the same table in global memory: a block fills its shared copy with ONE coalesced 512-byte load
+// (64 lanes reading 64 different __constant__ addresses are serialised by the constant cache, eight
+// line misses per warp: microseconds at the head of every block)
+__device__ double g_exp2tab[64];
 
 RB_D double* exp_table() {
   __shared__ double tab[64];
@@ -127,7 +131,7 @@ RB_D double* exp_table() {
 // every thread of the block calls this once, before any thread returns; includes the barrier
 RB_D void exp_table_init() {
   double* tab = exp_table();
-  for (int t = threadIdx.x; t < 64; t += blockDim.x) tab[t] = c_exp2tab[t];
+  for (int t = threadIdx.x; t < 64; t += blockDim.x) tab[t] = g_exp2tab[t];
   __syncthreads();
 }
 

@@ -703,6 +703,7 @@ cudaError_t launch_one(const GatherArgs& ga, const TilePlan& tp, const TileOut& 
 cudaError_t tile_upload_constants(int kind, const void* params, size_t bytes, const double* exp2tab) {
   cudaError_t e = cudaSuccess;
   if (exp2tab) e = cudaMemcpyToSymbol(c_exp2tab, exp2tab, sizeof(double) * 64);
+  if (exp2tab && e == cudaSuccess) e = cudaMemcpyToSymbol(g_exp2tab, exp2tab, sizeof(double) * 64);
   if (e != cudaSuccess) return e;
   if (kind == 0 && bytes == sizeof(EamParams)) return cudaMemcpyToSymbol(c_eam, params, bytes);
   if (kind == 1 && bytes == sizeof(EamParams)) return cudaMemcpyToSymbol(c_eam_al, params, bytes);

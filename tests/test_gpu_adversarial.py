@@ -171,8 +171,14 @@ def test_batch_kernel_pairs_at_the_cutoff(oracle, cells, ulps):
         assert abs(e - er) <= 1e-10 * abs(er), (cells, ulps)
         assert_forces(f, fr, (cells, ulps))
     assert out[0][0] == out[2][0] and np.array_equal(out[0][1], out[2][1])
-    e1, f1, _ = pot(pos, Z, box)  # the one-launch single-system path: same kernel, same bits
+    e1, f1, _ = pot(pos, Z, box)  # forced all-pairs path: the one-launch single-system call runs the same kernel
     assert e1 == out[0][0] and np.array_equal(f1, out[0][1])
+    # the automatic single-system path (several blocks per system, single.cuh): other summation order
+    auto = rgpot_b200.CuH2Pot()
+    for p_, (er, fr) in ((pos, (e_o, f_o)), (moved, (e_m, f_m))):
+        e2, f2, _ = auto(p_, Z, box)
+        assert abs(e2 - er) <= 1e-10 * abs(er), (cells, ulps)
+        assert_forces(f2, fr, (cells, ulps))
 
 
 @pytest.mark.parametrize("ulps", [0, 2, -2])

@@ -148,9 +148,15 @@ def test_small_single_fast_path(oracle, golden):
     p, z, b = workloads.cuh2_slab218()
     l0 = cu.launch_count()
     e218, f218, _ = cu(p, z, b)
-    assert cu.launch_count() - l0 == 1
+    assert cu.launch_count() - l0 == 1  # ONE cooperative launch over fourteen blocks (single.cuh)
     e_o, f_o = oracle.cuh2_force(p, z, b)
     assert abs(e218 - e_o) <= 1e-10 * abs(e_o) and np.abs(f218 - f_o).max() <= 1e-9
+    cu.set_option("one", 0)  # the batch kernel on one block: one launch, same tolerance
+    l0 = cu.launch_count()
+    e1b, f1b, _ = cu(p, z, b)
+    assert cu.launch_count() - l0 == 1
+    assert abs(e1b - e_o) <= 1e-10 * abs(e_o) and np.abs(f1b - f_o).max() <= 1e-9
+    cu.set_option("one", 1)
     # a repeated call reuses the block; a different size regrows it; errors still come back
     for n_side in (2, 3):
         pp, zz, bb = workloads.cu_slab_with_h2(cells=n_side)
