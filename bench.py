@@ -431,7 +431,8 @@ def run_cuh2_batch(args, world, rank, local):
         h2d = pos.nbytes + boxes.nbytes + offsets.nbytes  # one copy of the species array is shared by the batch
         d2h = pos.nbytes + n_cfg * 8
         gbs = rgpot_b200.measure_copy_gbs(list(range(world)), h2d // world, d2h // world)
-        one_call = {"one_s": one_s, "pin_s": pin_s, "h2d": h2d, "d2h": d2h, "copy_gbs": gbs, "host_threads_per_gpu": per_dev,
+        host_gbs = rgpot_b200.measure_host_copy_gbs(per_dev * world, pos.nbytes, 3)
+        one_call = {"host_gbs": host_gbs, "one_s": one_s, "pin_s": pin_s, "h2d": h2d, "d2h": d2h, "copy_gbs": gbs, "host_threads_per_gpu": per_dev,
                     "cpus": ncpu_all, "cxx": None}
         del multi
         one_call["cxx"] = cxx_plugin_line(n_cfg, e2e_steps, world, per_dev)
@@ -481,6 +482,11 @@ def run_cuh2_batch(args, world, rank, local):
                          "value_at_ceiling": (n_atoms_global / ceiling_s) if ceiling_s else None,
                          "e2e_pinned_over_ceiling": (ceiling_s * e2e_steps / one_call["pin_s"]) if ceiling_s else None,
                          "what": "plain pinned cudaMemcpyAsync of the same H2D + D2H bytes on these %d GPUs at once" % world},
+        "host_copy_ceiling": {"gb_per_s": one_call["host_gbs"], "threads": one_call["host_threads_per_gpu"] * world,
+                              "value_at_ceiling": (n_atoms_global / (2.0 * pos.nbytes / (one_call["host_gbs"] * 1e9)))
+                              if one_call["host_gbs"] else None,
+                              "what": "the same host threads packing the batch's positions into page-locked memory and "
+                                      "unpacking as many bytes of forces, no GPU involved: the pageable entry cannot be faster"},
         "sustained": sustained, "cxx_plugin": one_call["cxx"],
         "roofline": roofline, "clocks": clocks,
         "config": {"workload": f"cuh2_batch: {n_cfg} perturbed 218-atom Cu slab + H2 configs, ONE global batch cut "
@@ -587,7 +593,7 @@ def run_single_system(args, name, local):
             "roofline": {"bound": "fp64", "kernel": kernel, "achieved": tf, "peak": fp64_peak,
                          "unit": "TFLOP/s", "frac": tf / fp64_peak if fp64_peak else None,
                          "peak_nominal": FP64_NOMINAL_TF, "frac_nominal": tf / FP64_NOMINAL_TF,
-                         "fp64_executed": executed_fp64_per_atom("k_brick<0" if name == "lj_fluid_1m" else "k_brick<2"),
+                         "fp64_executed": executed_fp64_per_atom("k_brick<0" if name == "lj_fluid_1m" else ["k_brick<1", "k_brick<2"]),
                          "note": "whole step (cell build + force kernels) timed, flops of the path"},
             "l2": "256 MB flush write between timed iterations"}
     if name == "lj_fluid_1m":
@@ -716,11 +722,17 @@ def executed_fp64_per_atom(kernel_substr):
     """SURVEY 8(d) cross-check: FP64 flops the kernel EXECUTED per atom-eval (DFMA x 2 + DADD + DMUL from
     smsp__sass_thread_inst_executed_op_d*_pred_on in the committed ncu capture) beside the algorithmic
     count the roofline uses (which books an exponential as 30 flops; the kernels' table exp is ~20)."""
-    r, path = _latest_summary(kernel_substr)
-    if r is None or "fp64_flops" not in r:
-        return None
-    return {"flops_per_atom_eval": r["fp64_flops"] / _atoms_in_capture(r), "fp64_pipe_busy_pct": r.get("fp64_pipe_pct"),
-            "source": "profiles/" + path}
+    names = kernel_substr if isinstance(kernel_substr, (list, tuple)) else [kernel_substr]
+    total, busy, paths = 0.0, [], set()
+    for name in names:  # several kernels of one step (density + force): their flops add up
+        r, path = _latest_summary(name)
+        if r is None or "fp64_flops" not in r:
+            return None
+        total += r["fp64_flops"] / _atoms_in_capture(r)
+        busy.append(r.get("fp64_pipe_pct"))
+        paths.add("profiles/" + path)
+    return {"flops_per_atom_eval": total, "fp64_pipe_busy_pct": busy if len(busy) > 1 else busy[0],
+            "source": sorted(paths)}
 
 
 def load_peaks():
@@ -793,7 +805,7 @@ def main():
                 "dtype": "f64", "data": "synthetic",
                 "config": res["config"], "e2e": res["e2e"], "gpu_launches": res["gpu_launches"],
                 "roofline": res["roofline"], "clocks": res["clocks"]}
-        for key in ("e2e_pinned", "e2e_per_rank", "copy_ceiling", "sustained", "cxx_plugin"):
+        for key in ("e2e_pinned", "e2e_per_rank", "copy_ceiling", "host_copy_ceiling", "sustained", "cxx_plugin"):
             if res.get(key) is not None:
                 line[key] = res[key]
         if world == 1:

@@ -242,6 +242,11 @@ RGPOT_B200_API double rgpot_b200_measure_fp64_tflops(int device, int iters);
 RGPOT_B200_API double rgpot_b200_measure_copy_gbs(const int *devices, int n_devices, size_t h2d_bytes,
                                                   size_t d2h_bytes, int reps);
 
+/** Payload rate (GB/s) at which `threads` host threads move `bytes` from pageable into page-locked
+ *  memory and back in 5 KB pieces with the engine's streaming copy: what bounds the pageable
+ *  ForceBatch entry when the GPUs are not the limit (best of `reps`). */
+RGPOT_B200_API double rgpot_b200_measure_host_copy_gbs(int threads, size_t bytes, int reps);
+
 /* ---- exact drop-in for the reference's Fortran entry (FortranPots.cc:33-40) ------------ */
 RGPOT_B200_API int rgpot_cuh2_force(int32_t natoms, const double *positions,
                                     const int32_t *atomic_numbers, const double *cell,

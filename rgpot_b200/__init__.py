@@ -11,9 +11,9 @@ Everything is computed by librgpot_b200.so (include/rgpot_b200.h).  No CPU fallb
 """
 from .potentials import (CuH2Pot, EAMAlPot, FeHePot, LJClusterConfig, LJClusterPot, LJConfig, LJPot, MorseConfig, MorsePot, PotCaps, ZBLConfig, ZBLPot,
                          PotentialError, PotType, Reentrancy, evaluate_batch, evaluate_cuh2, evaluate_lj,
-                         measure_copy_gbs, measure_fp64_tflops, neighbor_list, pinned_empty)
+                         measure_copy_gbs, measure_fp64_tflops, measure_host_copy_gbs, neighbor_list, pinned_empty)
 
 __version__ = "0.1.0"
 __all__ = ["CuH2Pot", "EAMAlPot", "FeHePot", "LJClusterConfig", "LJClusterPot", "LJConfig", "LJPot", "MorseConfig", "MorsePot", "PotCaps", "ZBLConfig", "ZBLPot",
            "PotentialError", "PotType", "Reentrancy", "evaluate_batch", "evaluate_cuh2", "evaluate_lj",
-           "measure_copy_gbs", "measure_fp64_tflops", "neighbor_list", "pinned_empty", "__version__"]
+           "measure_copy_gbs", "measure_fp64_tflops", "measure_host_copy_gbs", "neighbor_list", "pinned_empty", "__version__"]

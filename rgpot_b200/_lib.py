@@ -114,6 +114,7 @@ SYMBOLS = [
     ("rgpot_b200_host_free", None, [_vp]),
     ("rgpot_b200_measure_fp64_tflops", _d, [_i, _i]),
     ("rgpot_b200_measure_copy_gbs", _d, [_vp, _i, _sz, _sz, _i]),
+    ("rgpot_b200_measure_host_copy_gbs", _d, [_i, _sz, _i]),
     ("rgpot_b200_core_callback", _i, [_vp, _vp, _vp]),
     ("rgpot_b200_core_free", None, [_vp]),
     ("rgpot_b200_core_last_error", C.c_char_p, []),

@@ -1481,18 +1481,24 @@ void lj_setup(RgpotB200Pot* pot) {
 }
 
 // ---- FP64 peak microbenchmark ------------------------------------------------------------------
+// Eight independent chains per thread, sixteen rounds per trip: 128 DFMA per loop branch, so the loop's
+// own integer instructions are ~2 % of the issue slots (an FP64 instruction holds the dispatch port for
+// two cycles: every other instruction comes out of the FP64 pipe's share).  ncu: FP64 pipe >= 95 % busy.
 __global__ void k_dfma_peak(double* out, int iters, double a, double b) {
   double x0 = threadIdx.x * 1e-9, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5,
          x6 = x0 + 6, x7 = x0 + 7;
-  for (int i = 0; i < iters; ++i) {
-    x0 = fma(x0, a, b);
-    x1 = fma(x1, a, b);
-    x2 = fma(x2, a, b);
-    x3 = fma(x3, a, b);
-    x4 = fma(x4, a, b);
-    x5 = fma(x5, a, b);
-    x6 = fma(x6, a, b);
-    x7 = fma(x7, a, b);
+  for (int i = 0; i < iters; i += 16) {
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      x0 = fma(x0, a, b);
+      x1 = fma(x1, a, b);
+      x2 = fma(x2, a, b);
+      x3 = fma(x3, a, b);
+      x4 = fma(x4, a, b);
+      x5 = fma(x5, a, b);
+      x6 = fma(x6, a, b);
+      x7 = fma(x7, a, b);
+    }
   }
   out[blockIdx.x * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
 }
@@ -1799,6 +1805,7 @@ double rgpot_b200_measure_fp64_tflops(int device, int iters) {
   cudaEventCreate(&t0);
   cudaEventCreate(&t1);
   if (iters < 1000) iters = 1000;
+  iters = (iters + 15) / 16 * 16;  // (the kernel runs sixteen rounds per trip)
   double best = 0.0;
   for (int rep = 0; rep < 5; ++rep) {
     cudaEventRecord(t0);
@@ -1813,6 +1820,38 @@ double rgpot_b200_measure_fp64_tflops(int device, int iters) {
   cudaEventDestroy(t0);
   cudaEventDestroy(t1);
   cudaFree(out);
+  return best;
+}
+
+// What the host's memory system gives a pack / unpack: `threads` threads copy `bytes` from pageable
+// memory into page-locked memory and back with the engine's own streaming copy, in 5 KB pieces like the
+// systems of a batch; returns GB/s of payload (bytes moved one way + bytes moved back) / time, best of
+// `reps`.  The ceiling of the pageable ForceBatch entry when the GPUs are not the limit.
+double rgpot_b200_measure_host_copy_gbs(int threads, size_t bytes, int reps) {
+  if (threads < 1 || bytes < (1u << 20) || reps < 1) return 0.0;
+  void* pinned = nullptr;
+  if (cudaMallocHost(&pinned, bytes) != cudaSuccess) {
+    cudaGetLastError();
+    return 0.0;
+  }
+  std::vector<char> src(bytes, 1), dst(bytes, 0);
+  rb::Team team(threads - 1, nullptr);
+  const size_t piece = 5232, npieces = bytes / piece;
+  double best = 0.0;
+  for (int r = 0; r <= reps; ++r) {
+    const auto t0 = std::chrono::steady_clock::now();
+    team.run(npieces, 32, [&](size_t b, size_t e) {
+      for (size_t k = b; k < e; ++k) rb::copy_stream(static_cast<char*>(pinned) + k * piece, src.data() + k * piece, piece);
+      rb::copy_stream_fence();
+    });
+    team.run(npieces, 32, [&](size_t b, size_t e) {
+      for (size_t k = b; k < e; ++k) rb::copy_stream(dst.data() + k * piece, static_cast<char*>(pinned) + k * piece, piece);
+      rb::copy_stream_fence();
+    });
+    const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    if (r > 0) best = std::max(best, 2.0 * (double)(npieces * piece) / dt / 1e9);
+  }
+  cudaFreeHost(pinned);
   return best;
 }
 

@@ -665,3 +665,9 @@ def measure_copy_gbs(devices, h2d_bytes: int, d2h_bytes: int, reps: int = 3) -> 
     once (rgpot_b200_measure_copy_gbs): what bounds every end-to-end batch number on this box."""
     devs = (C.c_int * len(devices))(*[int(d) for d in devices])
     return float(_lib.lib().rgpot_b200_measure_copy_gbs(devs, len(devices), int(h2d_bytes), int(d2h_bytes), int(reps)))
+
+
+def measure_host_copy_gbs(threads: int, nbytes: int, reps: int = 3) -> float:
+    """Payload GB/s of `threads` host threads packing `nbytes` into page-locked memory and unpacking them
+    again (rgpot_b200_measure_host_copy_gbs): the host-side ceiling of the pageable ForceBatch entry."""
+    return float(_lib.lib().rgpot_b200_measure_host_copy_gbs(int(threads), int(nbytes), int(reps)))
