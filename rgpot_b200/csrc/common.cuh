@@ -95,6 +95,33 @@ RB_D double shift_component(const double* __restrict__ H, int k, double s0, doub
   return xadd(xadd(xmul(s0, H[k]), xmul(s1, H[3 + k])), xmul(s2, H[6 + k]));
 }
 
+// stage stamps of the single-system kernels (tuning builds only: -DRB_STAMPS, tools/build_stamps.sh)
+#ifdef RB_STAMPS
+static __device__ unsigned long long g_stamps[32];
+#define RB_STAMP(k)                                                   \
+  do {                                                                \
+    if (blockIdx.x == 0 && threadIdx.x == 0) {                        \
+      unsigned long long t_;                                          \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)::"memory"); \
+      g_stamps[k] = t_;                                               \
+    }                                                                 \
+  } while (0)
+// (any block: the caller restricts the thread)
+#define RB_STAMP_ANY(k)                                             \
+  do {                                                              \
+    unsigned long long t_;                                          \
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)::"memory"); \
+    g_stamps[k] = t_;                                               \
+  } while (0)
+#else
+#define RB_STAMP(k) \
+  do {              \
+  } while (0)
+#define RB_STAMP_ANY(k) \
+  do {                  \
+  } while (0)
+#endif
+
 // vesin_visit.hpp:23-25 fold: d - w * (double)(long long)(d*inv + copysign(0.5, d*inv)).
 RB_D double fold_component(double d, double w, double inv) {
   const double t = xmul(d, inv);

@@ -1222,13 +1222,22 @@ int launch_small(RgpotB200Pot* pot, size_t nsys, long nmax, const long long* d_o
                  const double* d_boxes, const double* d_pos, const int* d_Z, double* d_F,
                  double* d_E, unsigned* d_flags, int* d_bad, int maxnb, cudaStream_t st,
                  const EmitArgs* emit, bool z_shared = false, int single_n = 0, int split = 0,
-                 double* e_parts = nullptr, int* ticket = nullptr) {
+                 double* e_parts = nullptr, int* ticket = nullptr, int lanes = 0, const double* host_box = nullptr,
+                 double* f_stage = nullptr) {
   SmallArgs a{};
   a.z_shared = z_shared ? 1 : 0;
   a.single_n = single_n;
   a.split = split;
+  a.lanes = lanes;
   a.e_parts = e_parts;
   a.ticket = ticket;
+  a.f_stage = f_stage;
+  if (host_box && uses_eam_small(pot->cfg.kind)) {  // one system: invert the cell here, not on one GPU thread
+    const double rc = pot->cfg.kind == RGPOT_B200_FEHE ? 5.4 : eam_rcut(pot->cfg.kind);
+    small_box_init(host_box, rc, a.sb);
+    if (!a.sb.bad) small_boxf_init(a.sb, rc, a.sbf);
+    a.box_ready = 1;
+  }
   a.pos = d_pos;
   a.Z = d_Z;
   a.off = d_off;
@@ -1296,10 +1305,12 @@ int launch_small(RgpotB200Pot* pot, size_t nsys, long nmax, const long long* d_o
   }
   int threads = (int)std::min<long>(256, ((nmax + 31) / 32) * 32);
   if (threads < 32) threads = 32;
-  if (split > 1)
-    k_lj_small<<<(unsigned)split, 128, smem, st>>>(a);  // one system, 32 atoms per block
-  else
+  if (split > 0) {  // one system: `lanes` lanes per atom, spread over `split` blocks
+    const int t1 = (int)std::min<long>(256, (((long)single_n * lanes + 31) / 32) * 32);
+    k_lj_small<<<(unsigned)split, split > 1 ? 256 : t1, smem, st>>>(a);
+  } else {
     k_lj_small<<<(unsigned)nsys, threads, smem, st>>>(a);
+  }
   return check_launch(pot, "k_lj_small");
 }
 
@@ -2208,8 +2219,8 @@ static int force_one_eam(RgpotB200Pot* pot, long nAtoms, const double* positions
   }
   if (!pot->h_fast_dev) CU_TRY(pot, cudaHostGetDevicePointer(&pot->h_fast_dev, pot->h_fast.p, 0));
   cudaStream_t st = pot->stream;
-  // device scratch (8-byte words): ticket | fallback | inputs | dfd[n] | eemb[n] | block energies
-  const size_t dev_words = 2 + in_words + 2 * n + (size_t)nb;
+  // device scratch (8-byte words): ticket | fallback | inputs | dfd[n] | eemb[n] | staged forces[3n] | block energies
+  const size_t dev_words = 2 + in_words + 5 * n + (size_t)nb;
   if (pot->d_fast.cap < dev_words * 8) {
     CU_TRY(pot, pot->d_fast.reserve(dev_words * 8 * 2));
     CU_TRY(pot, cudaMemsetAsync(pot->d_fast.p, 0, pot->d_fast.cap, st));
@@ -2231,7 +2242,8 @@ static int force_one_eam(RgpotB200Pot* pot, long nAtoms, const double* positions
   a.n = (int)nAtoms;
   a.dfd = dd + 2 + in_words;
   a.eemb = a.dfd + n;
-  a.e_parts = a.eemb + n;
+  a.f_stage = a.eemb + n;
+  a.e_parts = a.f_stage + 3 * n;
   a.ticket = reinterpret_cast<int*>(dd);
   a.fallback = reinterpret_cast<unsigned*>(dd + 1);
   a.call_id = ++pot->one_call_id;
@@ -2280,8 +2292,10 @@ static int force_small_fast(RgpotB200Pot* pot, long nAtoms, const double* positi
                             double* forces, double* energy, const double* box) {
   const size_t n = (size_t)nAtoms;
   const bool eam = reads_species(pot->cfg.kind);
-  // layout (8-byte units): off[2] | box[9] | pos[3n] | F[3n] | E | flags, bad[2] (as 2 words) | Z[n ints]
-  const size_t words = 2 + 9 + 3 * n + 3 * n + 1 + 2 + (n + 1) / 2 + 1;
+  // host block (8-byte words): off[2] | box[9] | - | pos[3n] | Z[(n + 1) / 2] || F[3n] | E | flags, - | bad[2]
+  // (the pad word puts the positions on a 16-byte boundary: vector loads in the kernels)
+  const size_t z_words = eam ? (n + 1) / 2 : 0, in_words = 12 + 3 * n + z_words;
+  const size_t words = in_words + 3 * n + 3;
   if (pot->h_fast.cap < words * 8) {
     if (pot->h_fast.p) cudaFreeHost(pot->h_fast.p);
     pot->h_fast.p = nullptr;
@@ -2296,12 +2310,12 @@ static int force_small_fast(RgpotB200Pot* pot, long nAtoms, const double* positi
   double* d = static_cast<double*>(pot->h_fast_dev);
   long long* h_off = reinterpret_cast<long long*>(h);
   double* h_box = h + 2;
-  double* h_pos = h + 11;
-  double* h_F = h_pos + 3 * n;
+  double* h_pos = h + 12;
+  int* h_Z = reinterpret_cast<int*>(h + 12 + 3 * n);
+  double* h_F = h + in_words;
   double* h_E = h_F + 3 * n;
   unsigned* h_flags = reinterpret_cast<unsigned*>(h_E + 1);
   int* h_bad = reinterpret_cast<int*>(h_E + 2);
-  int* h_Z = reinterpret_cast<int*>(h_E + 3);
   h_off[0] = 0;
   h_off[1] = (long long)n;
   if (box)
@@ -2313,32 +2327,35 @@ static int force_small_fast(RgpotB200Pot* pot, long nAtoms, const double* positi
   *h_flags = 0xffffffffu;
   h_bad[0] = INT_MAX;
   h_bad[1] = 0;
-  const size_t iE = 11 + 6 * n;
+  const size_t iE = in_words + 3 * n;
   const int maxnb = uses_eam_small(pot->cfg.kind) ? eam_small_maxnb(pot, nAtoms) : 0;
   cudaStream_t st = pot->stream;
-  int s = 0;
-  if (!uses_eam_small(pot->cfg.kind) && nAtoms >= 128) {
-    // a pair potential on a few hundred atoms: one block would leave 147 SMs idle.  The inputs go to
-    // the device in ONE copy (every block reads all of them), the atoms are spread over the blocks,
-    // results land in the mapped block.
-    const int split = (int)((nAtoms + 31) / 32);
-    const size_t in_words = 11 + 3 * n, need = sizeof(double) * (in_words + (size_t)split) + 64;
-    if (pot->d_fast.cap < need) {
-      CU_TRY(pot, pot->d_fast.reserve(need * 2));
-      CU_TRY(pot, cudaMemsetAsync(pot->d_fast.p, 0, pot->d_fast.cap, st));  // (the ticket starts at zero)
-    }
-    double* dd = pot->d_fast.as<double>();
-    // layout: ticket (8 bytes) | inputs | block partials
-    CU_TRY(pot, cudaMemcpyAsync(dd + 1, h, sizeof(double) * in_words, cudaMemcpyHostToDevice, st));
-    s = launch_small(pot, 1, nAtoms, nullptr, dd + 1 + 2, dd + 1 + 11, nullptr, d + 11 + 3 * n, d + iE,
-                     reinterpret_cast<unsigned*>(d + iE + 1), reinterpret_cast<int*>(d + iE + 2), maxnb, st, nullptr, false,
-                     (int)nAtoms, split, dd + 1 + in_words, reinterpret_cast<int*>(dd));
-  } else {
-    s = launch_small(pot, 1, nAtoms, reinterpret_cast<const long long*>(d), d + 2, d + 11,
-                     eam ? reinterpret_cast<const int*>(d + iE + 3) : nullptr, d + 11 + 3 * n, d + iE,
-                     reinterpret_cast<unsigned*>(d + iE + 1), reinterpret_cast<int*>(d + iE + 2), maxnb, st, nullptr, false,
-                     (int)nAtoms);
+  // The inputs go to the device in ONE copy command (a kernel that reads them in place pays a PCIe round
+  // trip of ~1.5 us per dependent fetch, and one per 128 bytes and warp beyond the first); the results
+  // land in the mapped block behind a system-scope fence.
+  const bool pairpot = !uses_eam_small(pot->cfg.kind);
+  int lanes = 0, split = 0;
+  if (pairpot) {
+    // lanes per atom: a warp for anything but the smallest clusters (every lane then has a partner or two)
+    lanes = 32;
+    while (lanes > 1 && lanes / 2 >= nAtoms) lanes >>= 1;
+    if (nAtoms > 1024) lanes = 16;
+    const int apb = 256 / lanes;
+    split = (long)nAtoms * lanes <= 256 ? 1 : (int)((nAtoms + apb - 1) / apb);
   }
+  // device block (8-byte words): ticket | - | inputs | block partials | staged forces
+  const size_t need = sizeof(double) * (2 + in_words + (size_t)split + 3 * n) + 64;
+  if (pot->d_fast.cap < need) {
+    CU_TRY(pot, pot->d_fast.reserve(need * 2));
+    CU_TRY(pot, cudaMemsetAsync(pot->d_fast.p, 0, pot->d_fast.cap, st));  // (the ticket starts at zero)
+    pot->one_call_id = 0;  // (force_one_eam shares the block)
+  }
+  double* dd = pot->d_fast.as<double>() + 2;
+  CU_TRY(pot, cudaMemcpyAsync(dd, h, sizeof(double) * in_words, cudaMemcpyHostToDevice, st));
+  int s = launch_small(pot, 1, nAtoms, nullptr, dd + 2, dd + 12, eam ? reinterpret_cast<const int*>(dd + 12 + 3 * n) : nullptr,
+                       d + in_words, d + iE, reinterpret_cast<unsigned*>(d + iE + 1), reinterpret_cast<int*>(d + iE + 2),
+                       maxnb, st, nullptr, false, (int)nAtoms, split, dd + in_words, reinterpret_cast<int*>(dd - 2), lanes,
+                       box ? h_box : nullptr, dd + in_words + split);
   if (s) return s;
   {
     // the kernel writes the status word last, behind a system-scope fence: poll it in place (a stream
@@ -3486,3 +3503,11 @@ int rgpot_fortran_last_error(char* buffer, int buffer_len) {
 }  // extern "C"
 
 #include "core_abi.cuh"
+
+#ifdef RB_STAMPS
+// tuning builds only: the stage stamps of the last single-system kernel (nanoseconds, %globaltimer)
+extern "C" __attribute__((visibility("default"))) int rgpot_b200_debug_stamps(unsigned long long* out, int n) {
+  if (n > 32) n = 32;
+  return (int)cudaMemcpyFromSymbol(out, rb::g_stamps, sizeof(unsigned long long) * (size_t)n);
+}
+#endif

@@ -38,14 +38,15 @@ struct OneArgs {
   unsigned* fallback;  // device word: == call_id means "the batch kernel has to take this system"
   unsigned call_id;    // increases with every call, so the word never needs a reset
   double* F;           // 3 n, mapped host memory
+  double* f_stage;     // 3 n, device scratch: the last block moves the forces to F (one system-scope fence per call)
   double* E;           // 1, mapped host memory
   unsigned* flags;     // mapped host status word (written last, behind a system fence)
   double* e_parts;     // per-block energies
   int* ticket;         // blocks that have delivered (left at zero)
 };
 
-constexpr int kOneAtomsPerBlock = 16;
-constexpr int kOneLanes = 16;
+constexpr int kOneAtomsPerBlock = 8;
+constexpr int kOneLanes = 32;
 constexpr unsigned kOneFallback = 0x40000000u;  // flags value: "rerun on the batch kernel"
 
 // shared setup of both kernels: positions, species, wrapped fractional coordinates (FP32), wrap counts,
@@ -192,10 +193,13 @@ __global__ void __launch_bounds__(kOneAtomsPerBlock* kOneLanes) k_eam_one(const 
   int* ash = reinterpret_cast<int*>(g32 + n);
   int* spc = ash + n;
   cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+  RB_STAMP(0);
   exp_table_init();
+  RB_STAMP(1);
   const bool ok = one_setup<M>(a, pos3, g32, ash, spc, svt, a.sb, bad);
   const EamParams& P = eam_par<M>();
   const int i = blockIdx.x * kOneAtomsPerBlock + (int)(threadIdx.x / kOneLanes), sub = threadIdx.x % kOneLanes;
+  RB_STAMP(2);
   // ---- density, embedding
   {
     double rho = 0.0;
@@ -216,7 +220,9 @@ __global__ void __launch_bounds__(kOneAtomsPerBlock* kOneLanes) k_eam_one(const 
       a.eemb[i] = emb;
     }
   }
+  RB_STAMP(3);
   grid.sync();  // every atom's F'(rho) is in memory
+  RB_STAMP(4);
   if (__ldcg(a.fallback) == a.call_id) {
     // not this kernel's case: the batch kernel takes the system (and owns the error reporting)
     if (blockIdx.x == 0 && threadIdx.x == 0) *a.flags = kOneFallback;
@@ -224,6 +230,7 @@ __global__ void __launch_bounds__(kOneAtomsPerBlock* kOneLanes) k_eam_one(const 
   }
   for (int t = threadIdx.x; t < n; t += blockDim.x) dfd[t] = __ldcg(a.dfd + t);
   __syncthreads();
+  RB_STAMP(5);
   // ---- pair energy, forces
   double fx = 0.0, fy = 0.0, fz = 0.0, ep = 0.0;
   if (i < n) {
@@ -242,26 +249,41 @@ __global__ void __launch_bounds__(kOneAtomsPerBlock* kOneLanes) k_eam_one(const 
   }
   double e = 0.0;
   if (i < n && sub == 0) {
-    a.F[3 * i] = fx;
-    a.F[3 * i + 1] = fy;
-    a.F[3 * i + 2] = fz;
+    a.f_stage[3 * i] = fx;
+    a.f_stage[3 * i + 1] = fy;
+    a.f_stage[3 * i + 2] = fz;
     e = ep + __ldcg(a.eemb + i);
   }
-  const double bs = block_sum(e, sh32);
-  __threadfence_system();  // this block's forces before its ticket
+  RB_STAMP(6);
+  const double bs = block_sum(e, sh32);  // (its barriers put every thread's force stores before thread 0's fence)
+  RB_STAMP(7);
   if (threadIdx.x == 0) {
     a.e_parts[blockIdx.x] = bs;
-    __threadfence();
+    __threadfence();  // this block's staged forces before its ticket
+    RB_STAMP(8);
     last = atomicAdd(a.ticket, 1) == (int)gridDim.x - 1;
   }
   __syncthreads();
-  if (last && threadIdx.x == 0) {
-    __threadfence();
-    double tot = 0.0;
-    for (unsigned b = 0; b < gridDim.x; ++b) tot += __ldcg(a.e_parts + b);
+  if (!last) return;
+  if (threadIdx.x == 0) RB_STAMP_ANY(9);
+  __threadfence();
+  for (int t = threadIdx.x; t < 3 * n; t += blockDim.x) a.F[t] = __ldcg(a.f_stage + t);
+  double tot = 0.0;
+  if (threadIdx.x < 32) {
+    // block order, one fixed chain; the loads go out together
+    for (unsigned b0 = 0; b0 < gridDim.x; b0 += 32) {
+      const unsigned b = b0 + threadIdx.x;
+      const double v = b < gridDim.x ? __ldcg(a.e_parts + b) : 0.0;
+      for (int l = 0; l < 32; ++l) tot += __shfl_sync(0xffffffffu, v, l);
+    }
+  }
+  __syncthreads();  // every thread's force stores before thread 0's fence
+  if (threadIdx.x == 0) {
     a.E[0] = tot;
     *a.ticket = 0;
+    RB_STAMP_ANY(10);
     __threadfence_system();
+    RB_STAMP_ANY(11);
     *a.flags = 0u;
   }
 }

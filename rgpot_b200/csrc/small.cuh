@@ -22,6 +22,64 @@ namespace rb {
 #endif
 constexpr int kSmallUnroll = RB_SMALL_UNROLL;  // list entries per trip of the density / force loops (tuning knob)
 
+struct SmallBox {
+  double H[9], Hinv[9];
+  double q[3];  // rc / face distance (+ margin): |fractional separation| bound per direction
+  int fast;     // every q < 0.5: at most one image per pair and direction
+  int bad;      // singular box
+};
+
+// vesin Matrix::determinant / inverse (:100-128) and face distances (:258-275)
+RB_HD void small_box_init(const double* b, double rc, SmallBox& sb) {
+  for (int k = 0; k < 9; ++k) sb.H[k] = b[k];
+  const double* m = sb.H;
+  const double det = m[0] * (m[4] * m[8] - m[7] * m[5]) - m[1] * (m[3] * m[8] - m[5] * m[6]) +
+                     m[2] * (m[3] * m[7] - m[4] * m[6]);
+  sb.bad = !(fabs(det) >= 1e-30);
+  if (sb.bad) {
+    sb.fast = 0;
+    return;
+  }
+  double* v = sb.Hinv;
+  v[0] = (m[4] * m[8] - m[7] * m[5]) / det;
+  v[1] = (m[2] * m[7] - m[1] * m[8]) / det;
+  v[2] = (m[1] * m[5] - m[2] * m[4]) / det;
+  v[3] = (m[5] * m[6] - m[3] * m[8]) / det;
+  v[4] = (m[0] * m[8] - m[2] * m[6]) / det;
+  v[5] = (m[3] * m[2] - m[0] * m[5]) / det;
+  v[6] = (m[3] * m[7] - m[6] * m[4]) / det;
+  v[7] = (m[6] * m[1] - m[0] * m[7]) / det;
+  v[8] = (m[0] * m[4] - m[3] * m[1]) / det;
+  // face distance k = 1 / |column k of Hinv|  (equivalent to |n_k . H_k| with n_k the unit normal)
+  sb.fast = 1;
+  for (int k = 0; k < 3; ++k) {
+    const double cn = sqrt(v[k] * v[k] + v[3 + k] * v[3 + k] + v[6 + k] * v[6 + k]);
+    sb.q[k] = rc * cn * (1.0 + 1e-9) + 1e-9;
+    if (!(sb.q[k] < 0.4999)) sb.fast = 0;
+  }
+}
+
+struct SmallBoxF {  // FP32 mirror for the prefilter
+  float h[9];
+  float thr2;  // (rc + margin)^2
+  int ortho;   // diagonal cell: three multiplies instead of a 3x3 product
+};
+
+// the FP32 mirror and the search threshold of a cell (host: once per single-system call; device: once per block)
+RB_HD void small_boxf_init(const SmallBox& sb, double rc, SmallBoxF& sbf) {
+  double hmax = 0.0;
+  for (int k = 0; k < 9; ++k) {
+    sbf.h[k] = (float)sb.H[k];
+    hmax += fabs(sb.H[k]);
+  }
+  sbf.ortho = sb.H[1] == 0.0 && sb.H[2] == 0.0 && sb.H[3] == 0.0 && sb.H[5] == 0.0 && sb.H[6] == 0.0 && sb.H[7] == 0.0;
+  // FP32 error of the wrapped fractional separation (~3 ulp of 1) times the cell size,
+  // plus the rounding of the Cartesian norm: generous, the exact test follows anyway
+  const double margin = 1.0e-6 * hmax + 1.0e-5 * rc;
+  const double thr = rc + margin;
+  sbf.thr2 = (float)(thr * thr * (1.0 + 1.0e-6));
+}
+
 struct SmallArgs {
   const double* pos;       // packed positions of all systems
   const int* Z;            // packed atomic numbers (may be null for LJ)
@@ -36,9 +94,15 @@ struct SmallArgs {
   int z_shared;            // homogeneous batch: Z holds the atomic numbers of ONE system, shared by all
   int single_n;            // > 0: ONE system of this many atoms starting at atom 0 (the offsets are not read:
                            //      one dependent fetch less when the inputs sit in mapped host memory)
-  int split;               // k_lj_small, single system: blocks the atoms are spread over (0 / 1 = one block)
+  int split;               // k_lj_small, single system: blocks the atoms are spread over (0 = batch mapping)
+  int lanes;               // ... and the lanes that share an atom there (a power of two <= 32)
   double* e_parts;         // split: per-block energy partials ...
   int* ticket;             // ... and the counter that tells the last block to fold them (left at zero)
+  double* f_stage;         // split > 1: device scratch for the forces; the last block moves them to F (mapped host
+                           //            memory) in one sweep, so the call pays ONE system-scope fence, not one per block
+  int box_ready;           // k_eam_small, single system: the cell has been prepared by the host (sb, sbf below)
+  SmallBox sb;
+  SmallBoxF sbf;
   int cluster;             // LJ: free boundaries
   double u0, psi2, shiftU, cutoff;  // LJ
   int morse;                        // 1 Morse, 2 ZBL instead of LJ
@@ -54,13 +118,22 @@ static __global__ void __launch_bounds__(256)
 k_lj_small(SmallArgs a) {
   extern __shared__ double smem[];
   __shared__ double sh32[32];
-  const bool split = a.split > 1;
+  const bool split = a.split > 0;
   const int sys = split ? 0 : blockIdx.x;
   const long long base = a.single_n > 0 ? 0 : a.off[sys];
   const int n = a.single_n > 0 ? a.single_n : (int)(a.off[sys + 1] - base);
+  RB_STAMP(0);
   double* px = smem;  // 3n interleaved
   int* tp = reinterpret_cast<int*>(smem + 3 * n);  // ZBL: type index per atom
-  for (int t = threadIdx.x; t < 3 * n; t += blockDim.x) px[t] = a.pos[3 * base + t];
+  if (split && ((reinterpret_cast<uintptr_t>(a.pos) & 15) == 0)) {  // (every block of a spread system reads all of it)
+    const double2* src = reinterpret_cast<const double2*>(a.pos);
+    double2* dst = reinterpret_cast<double2*>(px);
+    const int n2 = (3 * n) >> 1;
+    for (int t = threadIdx.x; t < n2; t += blockDim.x) dst[t] = src[t];
+    if (((3 * n) & 1) && threadIdx.x == 0) px[3 * n - 1] = a.pos[3 * n - 1];
+  } else {
+    for (int t = threadIdx.x; t < 3 * n; t += blockDim.x) px[t] = a.pos[3 * base + t];
+  }
   if (a.morse == 2)
     for (int t = threadIdx.x; t < n; t += blockDim.x) tp[t] = a.Z[(a.z_shared ? 0 : base) + t];
 
@@ -87,6 +160,7 @@ k_lj_small(SmallArgs a) {
     p.inv[k] = (!a.cluster && p.w[k] != 0.0) ? 1.0 / p.w[k] : 0.0;
   }
   __syncthreads();
+  RB_STAMP(1);
 
   double e = 0.0;
   if (!split) {
@@ -116,16 +190,17 @@ k_lj_small(SmallArgs a) {
       a.F[3 * (base + i) + 2] = fz;
     }
   } else {
-    // ONE system spread over the blocks of the grid (a single 500-atom system on one SM would leave 147
-    // idle): four lanes share an atom and take every fourth partner, the four partial sums are folded by
-    // two shuffles (a fixed tree), block b owns atoms [b T / 4, (b + 1) T / 4)
-    const int apb = blockDim.x >> 2, sub = threadIdx.x & 3;
-    const int i = blockIdx.x * apb + (threadIdx.x >> 2);
+    // ONE system spread over the lanes of the grid (a single 500-atom system in one block would leave 147
+    // SMs idle, and thirteen atoms in thirteen threads a dependent chain of twelve pairs each): a.lanes
+    // lanes share an atom and take every a.lanes-th partner, their partial sums are folded by shuffles
+    // (a fixed tree), block b owns atoms [b T / lanes, (b + 1) T / lanes)
+    const int lanes = a.lanes, apb = blockDim.x / lanes, sub = threadIdx.x & (lanes - 1);
+    const int i = blockIdx.x * apb + (int)threadIdx.x / lanes;
     double fx = 0.0, fy = 0.0, fz = 0.0;
     if (i < n) {
       const double xi = px[3 * i], yi = px[3 * i + 1], zi = px[3 * i + 2];
       const int ti = a.morse == 2 ? tp[i] : 0;
-      for (int j = sub; j < n; j += 4) {
+      for (int j = sub; j < n; j += lanes) {
         if (j == i) continue;
         const double dx = fold_component(xsub(px[3 * j], xi), p.w[0], p.inv[0]);
         const double dy = fold_component(xsub(px[3 * j + 1], yi), p.w[1], p.inv[1]);
@@ -135,40 +210,52 @@ k_lj_small(SmallArgs a) {
         lj_pair(p, ti, a.morse == 2 ? tp[j] : 0, dx, dy, dz, r2, e, fx, fy, fz);
       }
     }
-#pragma unroll
-    for (int off = 1; off < 4; off <<= 1) {
+    for (int off = 1; off < lanes; off <<= 1) {
       fx += __shfl_xor_sync(0xffffffffu, fx, off);
       fy += __shfl_xor_sync(0xffffffffu, fy, off);
       fz += __shfl_xor_sync(0xffffffffu, fz, off);
     }
     if (i < n && sub == 0) {
-      a.F[3 * i] = fx;
-      a.F[3 * i + 1] = fy;
-      a.F[3 * i + 2] = fz;
+      double* Fo = gridDim.x > 1 ? a.f_stage : a.F;
+      Fo[3 * i] = fx;
+      Fo[3 * i + 1] = fy;
+      Fo[3 * i + 2] = fz;
     }
   }
-  const double bs = block_sum(e, sh32);
-  if (!split) {
+  RB_STAMP(2);
+  const double bs = block_sum(e, sh32);  // (its barriers also put every thread's force stores before thread 0's fence)
+  RB_STAMP(3);
+  if (!split || gridDim.x == 1) {
     if (threadIdx.x == 0) {
       a.E[sys] = bs;
       if (a.single_n > 0) __threadfence_system();  // (a host that polls the flag word must find the results behind it)
+      RB_STAMP(4);
       a.sys_flags[sys] = 0u;   // every exit of the batch kernels writes the flag word: no reset copy needed
     }
     return;
   }
-  // split: the block that finishes last adds the block sums in block order and signs off
+  // split: the block that finishes last adds the block sums in block order, moves the forces to the host and signs off
   __shared__ int last;
-  __threadfence_system();  // this block's forces before its ticket
   if (threadIdx.x == 0) {
     a.e_parts[blockIdx.x] = bs;
-    __threadfence();
+    __threadfence();  // this block's staged forces (ordered before this thread by the barrier) before its ticket
     last = atomicAdd(a.ticket, 1) == (int)gridDim.x - 1;
   }
   __syncthreads();
-  if (last && threadIdx.x == 0) {
-    __threadfence();
-    double tot = 0.0;
-    for (unsigned b = 0; b < gridDim.x; ++b) tot += __ldcg(a.e_parts + b);
+  if (!last) return;
+  __threadfence();
+  for (int t = threadIdx.x; t < 3 * n; t += blockDim.x) a.F[t] = __ldcg(a.f_stage + t);
+  double tot = 0.0;
+  if (threadIdx.x < 32) {
+    // block order, one fixed chain; the loads go out together
+    for (unsigned b0 = 0; b0 < gridDim.x; b0 += 32) {
+      const unsigned b = b0 + threadIdx.x;
+      const double v = b < gridDim.x ? __ldcg(a.e_parts + b) : 0.0;
+      for (int l = 0; l < 32; ++l) tot += __shfl_sync(0xffffffffu, v, l);
+    }
+  }
+  __syncthreads();  // every thread's force stores before thread 0's fence
+  if (threadIdx.x == 0) {
     a.E[0] = tot;
     *a.ticket = 0;
     __threadfence_system();
@@ -177,43 +264,6 @@ k_lj_small(SmallArgs a) {
 }
 
 // ---------------------------------------------------------------------------------------- CuH2
-struct SmallBox {
-  double H[9], Hinv[9];
-  double q[3];  // rc / face distance (+ margin): |fractional separation| bound per direction
-  int fast;     // every q < 0.5: at most one image per pair and direction
-  int bad;      // singular box
-};
-
-// vesin Matrix::determinant / inverse (:100-128) and face distances (:258-275)
-RB_D void small_box_init(const double* b, double rc, SmallBox& sb) {
-  for (int k = 0; k < 9; ++k) sb.H[k] = b[k];
-  const double* m = sb.H;
-  const double det = m[0] * (m[4] * m[8] - m[7] * m[5]) - m[1] * (m[3] * m[8] - m[5] * m[6]) +
-                     m[2] * (m[3] * m[7] - m[4] * m[6]);
-  sb.bad = !(fabs(det) >= 1e-30);
-  if (sb.bad) {
-    sb.fast = 0;
-    return;
-  }
-  double* v = sb.Hinv;
-  v[0] = (m[4] * m[8] - m[7] * m[5]) / det;
-  v[1] = (m[2] * m[7] - m[1] * m[8]) / det;
-  v[2] = (m[1] * m[5] - m[2] * m[4]) / det;
-  v[3] = (m[5] * m[6] - m[3] * m[8]) / det;
-  v[4] = (m[0] * m[8] - m[2] * m[6]) / det;
-  v[5] = (m[3] * m[2] - m[0] * m[5]) / det;
-  v[6] = (m[3] * m[7] - m[6] * m[4]) / det;
-  v[7] = (m[6] * m[1] - m[0] * m[7]) / det;
-  v[8] = (m[0] * m[4] - m[3] * m[1]) / det;
-  // face distance k = 1 / |column k of Hinv|  (equivalent to |n_k . H_k| with n_k the unit normal)
-  sb.fast = 1;
-  for (int k = 0; k < 3; ++k) {
-    const double cn = sqrt(v[k] * v[k] + v[3 + k] * v[3 + k] + v[6 + k] * v[6 + k]);
-    sb.q[k] = rc * cn * (1.0 + 1e-9) + 1e-9;
-    if (!(sb.q[k] < 0.4999)) sb.fast = 0;
-  }
-}
-
 // list entry: j (16 bits) | (S0+16) << 16 | (S1+16) << 21 | (S2+16) << 26
 RB_D unsigned pack_entry(int j, int s0, int s1, int s2) {
   return (unsigned)j | ((unsigned)(s0 + 16) << 16) | ((unsigned)(s1 + 16) << 21) |
@@ -260,11 +310,6 @@ RB_D double entry_vec(const SmallBox& sb, const double* px, const double* py, co
 //             box) or a full list raise kFlagListOverflow and the system reruns on the cell-list
 //             kernels.
 // --------------------------------------------------------------------------------------------
-struct SmallBoxF {  // FP32 mirror for the prefilter
-  float h[9];
-  float thr2;  // (rc + margin)^2
-  int ortho;   // diagonal cell: three multiplies instead of a 3x3 product
-};
 
 
 template <int TPA, int M>
@@ -308,25 +353,26 @@ k_eam_small(SmallArgs a) {
   unsigned short* cnt16 = reinterpret_cast<unsigned short*>(perm + n);  // listed candidates per thread
   unsigned short* list = cnt16 + ((NTL + 1) & ~1);                      // lcap * NTL entries
 
-  exp_table_init();
+  RB_STAMP(0);
+  {  // the table of the exponential (exp_table_init without its barrier: the one after the cell follows)
+    double* tab = exp_table();
+    for (int t = threadIdx.x; t < 64; t += blockDim.x) tab[t] = g_exp2tab[t];
+  }
+  RB_STAMP(1);
   if (threadIdx.x == 0) {
-    small_box_init(a.boxes + 9 * (size_t)sys, model_rc, sb);
+    if (a.box_ready) {
+      sb = a.sb;  // one system: the host has inverted the cell (microseconds of FP64 divisions on one thread here)
+    } else {
+      small_box_init(a.boxes + 9 * (size_t)sys, model_rc, sb);
+    }
     blk_flags = sb.bad ? kFlagSingularBox : 0u;  // vesin: "the box matrix is not invertible"
     blk_bad[0] = INT_MAX;
     blk_bad[1] = 0;
     if (!sb.bad) {
-      double hmax = 0.0;
-      for (int k = 0; k < 9; ++k) {
-        sbf.h[k] = (float)sb.H[k];
-        hmax += fabs(sb.H[k]);
-      }
-      sbf.ortho = sb.H[1] == 0.0 && sb.H[2] == 0.0 && sb.H[3] == 0.0 && sb.H[5] == 0.0 &&
-                  sb.H[6] == 0.0 && sb.H[7] == 0.0;
-      // FP32 error of the wrapped fractional separation (~3 ulp of 1) times the cell size,
-      // plus the rounding of the Cartesian norm: generous, the exact test follows anyway
-      const double margin = 1.0e-6 * hmax + 1.0e-5 * model_rc;
-      const double thr = model_rc + margin;
-      sbf.thr2 = (float)(thr * thr * (1.0 + 1.0e-6));
+      if (a.box_ready)
+        sbf = a.sbf;
+      else
+        small_boxf_init(sb, model_rc, sbf);
     }
   }
   __syncthreads();
@@ -338,6 +384,7 @@ k_eam_small(SmallArgs a) {
     svt[3 * threadIdx.x + 2] = shift_component(sb.H, 2, s0, s1, s2);
   }
 
+  RB_STAMP(2);
   // ---- phase A
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     const double x = a.pos[3 * (base + i)], y = a.pos[3 * (base + i) + 1], z = a.pos[3 * (base + i) + 2];
@@ -386,8 +433,7 @@ k_eam_small(SmallArgs a) {
   if (blk_flags & (kFlagForeignZ | kFlagNonFinite | kFlagShiftRange | kFlagSingularBox)) {
     // the reference leaves energy and forces zeroed on failure
     for (int t = threadIdx.x; t < 3 * n; t += blockDim.x) a.F[3 * base + t] = 0.0;
-    if (a.single_n > 0) __threadfence_system();
-    __syncthreads();
+    __syncthreads();  // (every thread's stores before thread 0's fence)
     if (threadIdx.x == 0) {
       a.E[sys] = 0.0;
       a.sys_bad[2 * sys] = blk_bad[0];
@@ -399,6 +445,7 @@ k_eam_small(SmallArgs a) {
     return;
   }
 
+  RB_STAMP(3);
   const double rc2 = kFeHe ? xmul(5.4, 5.4) : eam_par<kFeHe ? EAM_CUH2 : M>().rc2;
   const bool wrapped_atoms = (blk_flags & kFlagAtomShift) != 0;
 
@@ -543,38 +590,45 @@ k_eam_small(SmallArgs a) {
     }
   }
 
+  RB_STAMP(4);
   // ---- phase C: order atoms by decreasing neighbor count (counting sort).  The order only decides
   // which lanes work on which atom; every per-atom result, and the energy sum below (taken in atom
   // order), is independent of it, so the integer atomics do not disturb reproducibility.
-  for (int b = threadIdx.x; b < 256; b += blockDim.x) hist[b] = 0;
-  __syncthreads();
-  int my_rank[2] = {0, 0};  // blockDim >= n / 2 for every launch configuration (n <= 511, >= 256 threads)
-  {
-    int k = 0;
-    for (int i = threadIdx.x; i < n; i += blockDim.x, ++k) my_rank[k & 1] = atomicAdd(&hist[min(cnt[i], 255)], 1);
-  }
-  __syncthreads();
-  if (warp == 0) {  // exclusive scan over the bins, largest count first
-    int carry = 0;
-    for (int base = 255; base >= 0; base -= 32) {
-      const int b = base - lane;
-      const int v = hist[b];
-      int incl = v;
-#pragma unroll
-      for (int off = 1; off < 32; off <<= 1) {
-        const int t = __shfl_up_sync(0xffffffffu, incl, off);
-        if (lane >= off) incl += t;
-      }
-      hist[b] = carry + incl - v;
-      carry += __shfl_sync(0xffffffffu, incl, 31);
+  if (blockDim.x == 32) {
+    // one warp: the order cannot change which lanes wait for which (a handful of atoms, a single small system)
+    for (int i = threadIdx.x; i < n; i += blockDim.x) perm[i] = i;
+    __syncthreads();
+  } else {
+    for (int b = threadIdx.x; b < 256; b += blockDim.x) hist[b] = 0;
+    __syncthreads();
+    int my_rank[2] = {0, 0};  // blockDim >= n / 2 for every launch configuration (n <= 511, >= 256 threads)
+    {
+      int k = 0;
+      for (int i = threadIdx.x; i < n; i += blockDim.x, ++k) my_rank[k & 1] = atomicAdd(&hist[min(cnt[i], 255)], 1);
     }
+    __syncthreads();
+    if (warp == 0) {  // exclusive scan over the bins, largest count first
+      int carry = 0;
+      for (int base = 255; base >= 0; base -= 32) {
+        const int b = base - lane;
+        const int v = hist[b];
+        int incl = v;
+  #pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+          const int t = __shfl_up_sync(0xffffffffu, incl, off);
+          if (lane >= off) incl += t;
+        }
+        hist[b] = carry + incl - v;
+        carry += __shfl_sync(0xffffffffu, incl, 31);
+      }
+    }
+    __syncthreads();
+    {
+      int k = 0;
+      for (int i = threadIdx.x; i < n; i += blockDim.x, ++k) perm[hist[min(cnt[i], 255)] + my_rank[k & 1]] = i;
+    }
+    __syncthreads();
   }
-  __syncthreads();
-  {
-    int k = 0;
-    for (int i = threadIdx.x; i < n; i += blockDim.x, ++k) perm[hist[min(cnt[i], 255)] + my_rank[k & 1]] = i;
-  }
-  __syncthreads();
   double* eatom = g3;  // per-atom energies (the fractional coordinates are no longer needed)
   double* dfs = g3 + n;  // Fe-He: F'(rho) of the s-band channel
 
@@ -584,6 +638,7 @@ k_eam_small(SmallArgs a) {
   const double rc2_phys = kFeHe ? rc2 : eam_par<kFeHe ? EAM_CUH2 : M>().rc2_phys;
 
   double e = 0.0;
+  RB_STAMP(5);
   // ---- phase D: density, embedding
   for (int ib = 0; ib < n; ib += ngrp) {
     const int slot = ib + grp;
@@ -641,7 +696,6 @@ k_eam_small(SmallArgs a) {
   __syncthreads();
   if (blk_flags & kFlagCoincident) {
     for (int t = threadIdx.x; t < 3 * n; t += blockDim.x) a.F[3 * base + t] = 0.0;
-    if (a.single_n > 0) __threadfence_system();
     __syncthreads();
     if (threadIdx.x == 0) {
       a.E[sys] = 0.0;
@@ -651,6 +705,7 @@ k_eam_small(SmallArgs a) {
     return;
   }
 
+  RB_STAMP(6);
   // ---- phase E: pair energy and forces
   for (int ib = 0; ib < n; ib += ngrp) {
     const int slot = ib + grp;
@@ -708,13 +763,16 @@ k_eam_small(SmallArgs a) {
       eatom[i] += ep;
     }
   }
-  if (a.single_n > 0) __threadfence_system();  // (a host that polls the flag word must find the forces behind it)
-  __syncthreads();
+  RB_STAMP(7);
+  __syncthreads();  // (also: every thread's force stores are ordered before thread 0's system fence below)
+  RB_STAMP(8);
   for (int i = threadIdx.x; i < n; i += blockDim.x) e += eatom[i];  // atom order: reproducible
   const double bs = block_sum(e, sh32);
   if (threadIdx.x == 0) {
     a.E[sys] = bs;
+    RB_STAMP(9);
     if (a.single_n > 0) __threadfence_system();  // (only a polling host needs the order; a batch must not pay for it)
+    RB_STAMP(10);
     a.sys_flags[sys] = 0u;
   }
 }
