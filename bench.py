@@ -485,8 +485,15 @@ def run_cuh2_batch(args, world, rank, local):
         "host_copy_ceiling": {"gb_per_s": one_call["host_gbs"], "threads": one_call["host_threads_per_gpu"] * world,
                               "value_at_ceiling": (n_atoms_global / (2.0 * pos.nbytes / (one_call["host_gbs"] * 1e9)))
                               if one_call["host_gbs"] else None,
+                              "value_at_ceiling_with_dma": (n_atoms_global / (2.0 * pos.nbytes / (one_call["host_gbs"] * 1e9)) * 4.0 / 6.0)
+                              if one_call["host_gbs"] else None,
+                              "e2e_over_ceiling_with_dma": (e2e_value / (n_atoms_global / (2.0 * pos.nbytes / (one_call["host_gbs"] * 1e9)) * 4.0 / 6.0))
+                              if one_call["host_gbs"] else None,
                               "what": "the same host threads packing the batch's positions into page-locked memory and "
-                                      "unpacking as many bytes of forces, no GPU involved: the pageable entry cannot be faster"},
+                                      "unpacking as many bytes of forces, no GPU involved: the pageable entry cannot be faster. "
+                                      "Pack + unpack are 4 of the 6 times a byte of the pageable entry crosses host memory "
+                                      "(the DMA engines read the staged positions and write the staged forces): "
+                                      "value_at_ceiling_with_dma = value_at_ceiling x 4 / 6"},
         "sustained": sustained, "cxx_plugin": one_call["cxx"],
         "roofline": roofline, "clocks": clocks,
         "config": {"workload": f"cuh2_batch: {n_cfg} perturbed 218-atom Cu slab + H2 configs, ONE global batch cut "

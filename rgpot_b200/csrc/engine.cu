@@ -3421,6 +3421,14 @@ int rgpot_b200_force_batch(RgpotB200Pot* pot, size_t nSystems, const size_t* nAt
 // ------------------------------------------------------------------------------------------------
 static std::mutex g_cuh2_mu;
 static RgpotB200Pot* g_cuh2 = nullptr;
+// the handle-less entries take their GPU from the environment (RGPOT_B200_DEVICE, default 0)
+static void dropin_device(RgpotB200Config* cfg) {
+  if (const char* e = getenv("RGPOT_B200_DEVICE")) {
+    char* end = nullptr;
+    const long d = strtol(e, &end, 10);
+    if (end != e && d >= 0 && d < 1024) cfg->device = (int)d;
+  }
+}
 static thread_local std::string g_last_fortran_error;
 
 int rgpot_cuh2_force(int32_t natoms, const double* positions, const int32_t* atomic_numbers,
@@ -3430,6 +3438,7 @@ int rgpot_cuh2_force(int32_t natoms, const double* positions, const int32_t* ato
   if (!g_cuh2) {
     RgpotB200Config cfg;
     rgpot_b200_default_config(RGPOT_B200_CUH2, &cfg);
+    dropin_device(&cfg);
     char err[256] = {0};
     g_cuh2 = rgpot_b200_create(&cfg, err, sizeof err);
     if (!g_cuh2) {
@@ -3454,6 +3463,7 @@ int rgpot_eam_al_force(int32_t natoms, const double* positions, const double* ce
   if (!g_eam_al) {
     RgpotB200Config cfg;
     rgpot_b200_default_config(RGPOT_B200_EAM_AL, &cfg);
+    dropin_device(&cfg);
     char err[256] = {0};
     g_eam_al = rgpot_b200_create(&cfg, err, sizeof err);
     if (!g_eam_al) {
@@ -3478,6 +3488,7 @@ int rgpot_fehe_force(int32_t natoms, const double* positions, const int32_t* ato
   if (!g_fehe) {
     RgpotB200Config cfg;
     rgpot_b200_default_config(RGPOT_B200_FEHE, &cfg);
+    dropin_device(&cfg);
     char err[256] = {0};
     g_fehe = rgpot_b200_create(&cfg, err, sizeof err);
     if (!g_fehe) {
