@@ -280,6 +280,7 @@ struct RgpotB200Pot {
   int opt_tile_cap = 0;       // staged capacity override (test hook: small values exercise cut boxes / the slow path)
   int opt_tile_wcap = 0;      // window chunk override
   int opt_batch_chunk = 0;    // systems per pipeline chunk of a host batch (0 = automatic)
+  int opt_half = 1;           // batch kernel: every pair once (half lists + fixed-point scatter); 0 = full lists
   int opt_one = 1;            // single EAM systems of 64 .. 512 atoms on the many-block kernels (single.cuh)
   long opt_fine_min = 20000;  // atoms from which half-cutoff cells are used
   long launches = 0;
@@ -1196,7 +1197,7 @@ int eam_small_tpa(long nmax) {  // lanes per atom: fill about 448 threads
 size_t eam_small_smem(long n, int maxnb) {  // must match the layout in k_eam_small
   const int tpa = eam_small_tpa(n);
   const size_t ntl = (size_t)n * tpa, lcap = (size_t)(maxnb + tpa - 1) / tpa + 4;
-  size_t bytes = sizeof(double) * (7 * (size_t)n + 81);
+  size_t bytes = sizeof(double) * (10 * (size_t)n + 81);
   bytes = (bytes + 15) & ~(size_t)15;
   return bytes + sizeof(float) * 4 * (size_t)n + sizeof(int) * 4 * (size_t)n +
          sizeof(unsigned short) * (((ntl + 1) & ~(size_t)1) + lcap * ntl) + 16;
@@ -1232,6 +1233,7 @@ int launch_small(RgpotB200Pot* pot, size_t nsys, long nmax, const long long* d_o
   a.e_parts = e_parts;
   a.ticket = ticket;
   a.f_stage = f_stage;
+  a.half = pot->opt_half;
   if (host_box && uses_eam_small(pot->cfg.kind)) {  // one system: invert the cell here, not on one GPU thread
     const double rc = pot->cfg.kind == RGPOT_B200_FEHE ? 5.4 : eam_rcut(pot->cfg.kind);
     small_box_init(host_box, rc, a.sb);
@@ -1781,6 +1783,11 @@ int rgpot_b200_set_option(RgpotB200Pot* pot, const char* key, long value) {
   }
   if (strcmp(key, "one") == 0) {
     pot->opt_one = (int)value;
+    return 0;
+  }
+  if (strcmp(key, "half") == 0) {
+    pot->opt_half = (int)value;
+    for (auto& sh : pot->shards) sh.pot->opt_half = (int)value;
     return 0;
   }
   if (strcmp(key, "batch_chunk") == 0) {

@@ -291,12 +291,12 @@ RB_D double eam_density_entry(int zj, double d2) {
 
 // one accepted directed entry of the force pass (atom_force :552-586).
 // vec = r_j - r_i + S.H ; returns half pair energy and accumulates f_i += w * vec.
+// the pair energy phi and the radial factor w of one accepted pair (symmetric in i <-> j: the same w acts on
+// both atoms with opposite sign, which is what the half-list mode of the batch kernel uses)
 template <int M = EAM_CUH2>
-RB_D void eam_force_entry(int zi, int zj, double dfd_i, double dfd_j, double vx, double vy,
-                          double vz, double d2, double& e, double& fx, double& fy, double& fz) {
+RB_D void eam_force_pair(int zi, int zj, double dfd_i, double dfd_j, double d2, double& phi, double& w) {
   double r, rinv;
   radial(d2, r, rinv);
-  double phi, w;
   if (M == EAM_AL || (zi | zj) == 0) {
     // Cu-Cu (the bulk of every slab) and Al-Al: every coefficient index is static, so the
     // constants are operands of the FP64 instructions instead of separately loaded registers
@@ -325,6 +325,13 @@ RB_D void eam_force_entry(int zi, int zj, double dfd_i, double dfd_j, double vx,
     const double drho_ji = (zi == zj) ? drho_ij : eam_drho(zi, r, rinv);  // what i deposits on j
     w = w + drho_ij * dfd_i + drho_ji * dfd_j;
   }
+}
+
+template <int M = EAM_CUH2>
+RB_D void eam_force_entry(int zi, int zj, double dfd_i, double dfd_j, double vx, double vy,
+                          double vz, double d2, double& e, double& fx, double& fy, double& fz) {
+  double phi, w;
+  eam_force_pair<M>(zi, zj, dfd_i, dfd_j, d2, phi, w);
   e += 0.5 * phi;
   fx = fma(w, vx, fx);
   fy = fma(w, vy, fy);

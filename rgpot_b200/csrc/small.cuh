@@ -100,6 +100,7 @@ struct SmallArgs {
   int* ticket;             // ... and the counter that tells the last block to fold them (left at zero)
   double* f_stage;         // split > 1: device scratch for the forces; the last block moves them to F (mapped host
                            //            memory) in one sweep, so the call pays ONE system-scope fence, not one per block
+  int half;                // k_eam_small: every pair once (half lists, fixed-point scatter to the partner); see the kernel
   int box_ready;           // k_eam_small, single system: the cell has been prepared by the host (sb, sbf below)
   SmallBox sb;
   SmallBoxF sbf;
@@ -312,6 +313,16 @@ RB_D double entry_vec(const SmallBox& sb, const double* px, const double* py, co
 // --------------------------------------------------------------------------------------------
 
 
+// 64-bit fixed-point accumulation in shared memory.  A 64-bit shared-memory atomic add compiles to a
+// compare-and-swap loop; two native 32-bit adds with the carry taken from the value the first one returns give
+// the same sum (every wrap of the low word is seen by exactly one caller) without a loop.
+RB_D void fixed_add(long long* acc, long long q) {
+  unsigned* p = reinterpret_cast<unsigned*>(acc);
+  const unsigned lo = (unsigned)q, hi = (unsigned)((unsigned long long)q >> 32);
+  const unsigned old = atomicAdd(p, lo);
+  atomicAdd(p + 1, hi + ((old + lo) < lo ? 1u : 0u));
+}
+
 template <int TPA, int M>
 __global__ void __launch_bounds__(448, 2)
 k_eam_small(SmallArgs a) {
@@ -343,7 +354,8 @@ k_eam_small(SmallArgs a) {
   double* g3 = pos3 + 3 * n;                            // wrapped fractional coordinates
   double* dfd = g3 + 3 * n;
   double* svt = dfd + n;                                // 27 image vectors, 3 doubles each
-  size_t off_bytes = sizeof(double) * (7 * (size_t)n + 81);
+  long long* facc = reinterpret_cast<long long*>(svt + 81);  // half-list mode: fixed-point force accumulators, 3 per atom
+  size_t off_bytes = sizeof(double) * (10 * (size_t)n + 81);
   off_bytes = (off_bytes + 15) & ~(size_t)15;
   float4* g32 = reinterpret_cast<float4*>(smem_raw + off_bytes);  // FP32 copy of the wrapped fractional coordinates
   int* ash = reinterpret_cast<int*>(g32 + n);      // packed wrap counts (10 bits each, biased 512)
@@ -376,6 +388,15 @@ k_eam_small(SmallArgs a) {
     }
   }
   __syncthreads();
+  // Half-list mode (one image per pair only): atom i owns the partners i + 1 ... i + (n - 1) / 2 (indices mod n; for
+  // even n the pair at distance n / 2 belongs to the smaller index), evaluates each of its pairs ONCE and hands the
+  // partner its share through 64-bit FIXED-POINT atomics in shared memory -- integer addition is associative, so
+  // the sums do not depend on the order the lanes arrive in and results stay bit-reproducible.  Scales: density
+  // 2^-53 (terms < 0.25), forces 2^-40 eV/A (terms < 1024): the rounding, 1e-16 and 9e-13 absolute, is far inside
+  // the 1e-10 / 1e-9 budget; a term outside those ranges (atoms almost on top of each other) sends the system to
+  // the general path (kFlagListOverflow) like a full list does.
+  const bool half = !kFeHe && a.half != 0 && sb.fast != 0 && !sb.bad && a.emit.pairs == nullptr;
+  long long* rho_acc = reinterpret_cast<long long*>(g3 + 2 * n);
   if (threadIdx.x < 27 && !sb.bad) {
     const int t = (int)threadIdx.x;
     const double s0 = (double)(t % 3 - 1), s1 = (double)((t / 3) % 3 - 1), s2 = (double)(t / 9 - 1);
@@ -456,11 +477,42 @@ k_eam_small(SmallArgs a) {
     const float thr2 = sbf.thr2;
     const bool ortho = sbf.ortho != 0;
     const unsigned lbase = (unsigned)__cvta_generic_to_shared(list), lstride = 2u * (unsigned)NTL;
+    if (half) {  // (the FP64 fractional coordinates in g3 are not read again in this mode)
+      for (int t = threadIdx.x; t < n; t += blockDim.x) rho_acc[t] = 0;
+      for (int t = threadIdx.x; t < 3 * n; t += blockDim.x) facc[t] = 0;
+    }
     for (int t = threadIdx.x; t < NTL; t += blockDim.x) {
       const int i = t / TPA, sub = t - i * TPA;
       const float4 gi = g32[i];
       const unsigned la0 = lbase + 2u * (unsigned)t, la_last = la0 + (unsigned)(lcap - 1) * lstride;
       unsigned la = la0;  // list cursor (shared byte address); the last slot doubles as the overflow sink
+      auto search_half = [&](auto ortho_tag) {
+        constexpr bool ORTHO = decltype(ortho_tag)::value;
+        const int dmax = ((n - 1) >> 1) + (((n & 1) == 0 && i < (n >> 1)) ? 1 : 0);
+#pragma unroll 4
+        for (int d = 1 + sub; d <= dmax; d += TPA) {
+          int j = i + d;
+          j -= j >= n ? n : 0;
+          const float4 c = g32[j];
+          float t0 = c.x - gi.x, t1 = c.y - gi.y, t2 = c.z - gi.z;
+          t0 -= rintf(t0);
+          t1 -= rintf(t1);
+          t2 -= rintf(t2);
+          float dx, dy, dz;
+          if (ORTHO) {
+            dx = t0 * h0;
+            dy = t1 * h4;
+            dz = t2 * h8;
+          } else {
+            dx = fmaf(t0, h0, fmaf(t1, h3, t2 * h6));
+            dy = fmaf(t0, h1, fmaf(t1, h4, t2 * h7));
+            dz = fmaf(t0, h2, fmaf(t1, h5, t2 * h8));
+          }
+          const bool pass = fmaf(dx, dx, fmaf(dy, dy, dz * dz)) <= thr2;
+          asm volatile("st.shared.u16 [%0], %1;" ::"r"(la), "h"((unsigned short)j));  // kept only if it passes
+          la = min(la + (pass ? lstride : 0u), la_last);
+        }
+      };
       auto search = [&](auto ortho_tag) {
         constexpr bool ORTHO = decltype(ortho_tag)::value;
 #pragma unroll 4
@@ -485,10 +537,16 @@ k_eam_small(SmallArgs a) {
           la = min(la + (pass ? lstride : 0u), la_last);
         }
       };
-      if (ortho)
+      if (half) {
+        if (ortho)
+          search_half(BoolTag<true>{});
+        else
+          search_half(BoolTag<false>{});
+      } else if (ortho) {
         search(BoolTag<true>{});
-      else
+      } else {
         search(BoolTag<false>{});
+      }
       if (la == la_last) atomicOr(&blk_flags, kFlagListOverflow);
       const int c = (int)(((float)(la - la0) + 0.5f) / (float)lstride);
       // second sweep: image index S' = -rint(g_j - g_i) (the search's choice, recomputed the same
@@ -640,6 +698,61 @@ k_eam_small(SmallArgs a) {
   double e = 0.0;
   RB_STAMP(5);
   // ---- phase D: density, embedding
+  constexpr int MM = kFeHe ? EAM_CUH2 : M;  // (the half-list branches are never taken for Fe-He)
+  const double kFixMagic = 6755399441055744.0;  // 1.5 * 2^52: fma(v, scale, magic) holds rint(v * scale) in its low bits
+  if (half) {
+    for (int ib = 0; ib < n; ib += ngrp) {
+      const int slot = ib + grp;
+      const bool vi = slot < n;
+      double rho = 0.0;
+      bool coincident = false, range = false;
+      int i = 0;
+      if (vi) {
+        i = perm[slot];
+        const int c = cnt16[i * TPA + sub];
+        const int zi = spc[i];
+        const double xi = pos3[3 * i], yi = pos3[3 * i + 1], zi_ = pos3[3 * i + 2];
+        const unsigned short* row = list + i * TPA + sub;
+#pragma unroll kSmallUnroll
+        for (int s = 0; s < c; ++s) {
+          const unsigned en = row[s * NTL];
+          const int j = (int)(en & 511u);
+          const double* pj = pos3 + 3 * j;
+          const double* sv = svt + 3 * ((en >> 9) & 31u);
+          const double vx = xadd(xsub(pj[0], xi), sv[0]);
+          const double vy = xadd(xsub(pj[1], yi), sv[1]);
+          const double vz = xadd(xsub(pj[2], zi_), sv[2]);
+          const double d2 = xnorm2(vx, vy, vz);
+          if (d2 == 0.0) coincident = true;  // dist <= 0 guard, rgpot_cuh2.f90:422-428
+          if (!(d2 < rc2_phys)) continue;    // :522
+          const int zj = (int)(en >> 14);
+          double r, rinv;
+          radial(d2, r, rinv);
+          const double on_i = eam_rho<MM>(zj, r);                                       // what j deposits on i
+          const double on_j = (MM == EAM_AL || zi == zj) ? on_i : eam_rho<MM>(zi, r);  // what i deposits on j
+          rho += on_i;
+          range |= !(fabs(on_j) < 0.25);
+          const long long q = __double_as_longlong(fma(on_j, 0x1p53, kFixMagic)) - __double_as_longlong(kFixMagic);
+          fixed_add(rho_acc + j, q);
+        }
+      }
+#pragma unroll
+      for (int off = TPA / 2; off > 0; off >>= 1) rho += __shfl_xor_sync(0xffffffffu, rho, off);
+      if (coincident) atomicOr(&blk_flags, kFlagCoincident);
+      if (vi && sub == 0) {
+        range |= !(fabs(rho) < 128.0);
+        fixed_add(rho_acc + i, __double2ll_rn(rho * 0x1p53));
+      }
+      if (range) atomicOr(&blk_flags, kFlagListOverflow);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      double emb, demb;
+      eam_embed<MM>(spc[i], (double)rho_acc[i] * 0x1p-53, emb, demb);
+      dfd[i] = demb;
+      eatom[i] = emb;
+    }
+  } else
   for (int ib = 0; ib < n; ib += ngrp) {
     const int slot = ib + grp;
     const bool vi = slot < n;
@@ -707,6 +820,69 @@ k_eam_small(SmallArgs a) {
 
   RB_STAMP(6);
   // ---- phase E: pair energy and forces
+  if (half) {
+    for (int ib = 0; ib < n; ib += ngrp) {
+      const int slot = ib + grp;
+      const bool vi = slot < n;
+      double fx = 0.0, fy = 0.0, fz = 0.0, ep = 0.0;
+      bool range = false;
+      int i = 0;
+      if (vi) {
+        i = perm[slot];
+        const int c = cnt16[i * TPA + sub];
+        const int zi = spc[i];
+        const double dfd_i = dfd[i];
+        const double xi = pos3[3 * i], yi = pos3[3 * i + 1], zi_ = pos3[3 * i + 2];
+        const unsigned short* row = list + i * TPA + sub;
+#pragma unroll kSmallUnroll
+        for (int s = 0; s < c; ++s) {
+          const unsigned en = row[s * NTL];
+          const int j = (int)(en & 511u);
+          const double* pj = pos3 + 3 * j;
+          const double* sv = svt + 3 * ((en >> 9) & 31u);
+          const double vx = xadd(xsub(pj[0], xi), sv[0]);
+          const double vy = xadd(xsub(pj[1], yi), sv[1]);
+          const double vz = xadd(xsub(pj[2], zi_), sv[2]);
+          const double d2 = xnorm2(vx, vy, vz);
+          if (!(d2 < rc2_phys)) continue;
+          double phi, w;
+          eam_force_pair<MM>(zi, (int)(en >> 14), dfd_i, dfd[j], d2, phi, w);
+          ep += phi;  // the whole pair energy: the partner does not see this pair
+          const double tx = w * vx, ty = w * vy, tz = w * vz;
+          fx += tx;
+          fy += ty;
+          fz += tz;
+          range |= !(fabs(w) < 128.0);  // |v| <= rc < 8: every component term below 1024
+          long long* fj = facc + 3 * j;
+          fixed_add(fj, __double_as_longlong(fma(-tx, 0x1p40, kFixMagic)) - __double_as_longlong(kFixMagic));
+          fixed_add(fj + 1, __double_as_longlong(fma(-ty, 0x1p40, kFixMagic)) - __double_as_longlong(kFixMagic));
+          fixed_add(fj + 2, __double_as_longlong(fma(-tz, 0x1p40, kFixMagic)) - __double_as_longlong(kFixMagic));
+        }
+      }
+#pragma unroll
+      for (int off = TPA / 2; off > 0; off >>= 1) {
+        fx += __shfl_xor_sync(0xffffffffu, fx, off);
+        fy += __shfl_xor_sync(0xffffffffu, fy, off);
+        fz += __shfl_xor_sync(0xffffffffu, fz, off);
+        ep += __shfl_xor_sync(0xffffffffu, ep, off);
+      }
+      if (vi && sub == 0) {
+        range |= !(fabs(fx) < 0x1p20 && fabs(fy) < 0x1p20 && fabs(fz) < 0x1p20);
+        long long* fi = facc + 3 * i;
+        fixed_add(fi, __double2ll_rn(fx * 0x1p40));
+        fixed_add(fi + 1, __double2ll_rn(fy * 0x1p40));
+        fixed_add(fi + 2, __double2ll_rn(fz * 0x1p40));
+        eatom[i] += ep;
+      }
+      if (range) atomicOr(&blk_flags, kFlagListOverflow);
+    }
+    __syncthreads();
+    if (blk_flags & kFlagListOverflow) {
+      if (threadIdx.x == 0) a.sys_flags[sys] = kFlagListOverflow;  // out of the fixed-point range: the general path takes it
+      return;
+    }
+    for (int t = threadIdx.x; t < 3 * n; t += blockDim.x) a.F[3 * base + t] = (double)facc[t] * 0x1p-40;
+  } else
   for (int ib = 0; ib < n; ib += ngrp) {
     const int slot = ib + grp;
     const bool vi = slot < n;

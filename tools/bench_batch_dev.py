@@ -20,10 +20,15 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--configs", type=int, default=16384)
     ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--options", default="", help="engine options, e.g. half=0")
     args = ap.parse_args()
     offsets, pos, Z, boxes = workloads.cuh2_batch(args.configs, seed=1000)
     n_atoms = int(offsets[-1])
     pot = rgpot_b200.CuH2Pot(device=0)
+    for kv in args.options.split(","):
+        if kv:
+            k, v = kv.split("=")
+            pot.set_option(k, int(v))
     dev = torch.device("cuda", 0)
     d_pos = torch.from_numpy(pos).to(dev)
     d_Z = torch.from_numpy(Z).to(dev)
@@ -44,7 +49,7 @@ def main():
     assert pot.sync_status() == 0
     ms = t0.elapsed_time(t1) / args.steps
     print(json.dumps({"what": "cuh2_batch_dev", "configs": args.configs, "ms": ms, "atom_evals_per_s": n_atoms / (ms * 1e-3),
-                      "e_sum": float(d_E.sum().item()), "f_abs_sum": float(d_F.abs().sum().item())}))
+                      "options": args.options, "e_sum": float(d_E.sum().item()), "f_abs_sum": float(d_F.abs().sum().item())}))
 
 
 if __name__ == "__main__":
