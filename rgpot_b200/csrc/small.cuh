@@ -337,6 +337,13 @@ k_eam_small(SmallArgs a) {
   __shared__ unsigned blk_flags;
   __shared__ int blk_bad[2];
   __shared__ int hist[256];
+  // half-list mode: pairs with a hydrogen partner are set aside and evaluated afterwards by consecutive threads
+  // (inside the list walk a single such entry drags its whole warp through the mixed-species code at one or two
+  // active lanes); their energies go through a fixed-point accumulator, so nothing depends on the queue order
+  constexpr int kDeferCap = 512;
+  __shared__ unsigned dq[kDeferCap];
+  __shared__ int dq_n;
+  __shared__ long long e_acc;
 
   const int sys = blockIdx.x;
   const long long base = a.single_n > 0 ? 0 : a.off[sys];
@@ -380,6 +387,8 @@ k_eam_small(SmallArgs a) {
     blk_flags = sb.bad ? kFlagSingularBox : 0u;  // vesin: "the box matrix is not invertible"
     blk_bad[0] = INT_MAX;
     blk_bad[1] = 0;
+    dq_n = 0;
+    e_acc = 0;
     if (!sb.bad) {
       if (a.box_ready)
         sbf = a.sbf;
@@ -712,7 +721,8 @@ k_eam_small(SmallArgs a) {
         const int c = cnt16[i * TPA + sub];
         const int zi = spc[i];
         const double xi = pos3[3 * i], yi = pos3[3 * i + 1], zi_ = pos3[3 * i + 2];
-        const unsigned short* row = list + i * TPA + sub;
+        unsigned short* row = list + i * TPA + sub;
+        int kept = 0;  // entries that pass the exact test are written back in place: the force pass walks only those
 #pragma unroll kSmallUnroll
         for (int s = 0; s < c; ++s) {
           const unsigned en = row[s * NTL];
@@ -726,6 +736,15 @@ k_eam_small(SmallArgs a) {
           if (d2 == 0.0) coincident = true;  // dist <= 0 guard, rgpot_cuh2.f90:422-428
           if (!(d2 < rc2_phys)) continue;    // :522
           const int zj = (int)(en >> 14);
+          if (MM != EAM_AL && (zi | zj) != 0) {
+            const int slot = atomicAdd(&dq_n, 1);
+            if (slot < kDeferCap) {
+              dq[slot] = ((unsigned)i << 16) | en;
+              continue;
+            }  // (queue full: the entry stays in the list and is evaluated in place)
+          }
+          row[kept * NTL] = (unsigned short)en;  // (kept <= s: never ahead of the read cursor)
+          ++kept;
           double r, rinv;
           radial(d2, r, rinv);
           const double on_i = eam_rho<MM>(zj, r);                                       // what j deposits on i
@@ -735,6 +754,7 @@ k_eam_small(SmallArgs a) {
           const long long q = __double_as_longlong(fma(on_j, 0x1p53, kFixMagic)) - __double_as_longlong(kFixMagic);
           fixed_add(rho_acc + j, q);
         }
+        cnt16[i * TPA + sub] = (unsigned short)kept;  // (read again by this thread only)
       }
 #pragma unroll
       for (int off = TPA / 2; off > 0; off >>= 1) rho += __shfl_xor_sync(0xffffffffu, rho, off);
@@ -744,6 +764,27 @@ k_eam_small(SmallArgs a) {
         fixed_add(rho_acc + i, __double2ll_rn(rho * 0x1p53));
       }
       if (range) atomicOr(&blk_flags, kFlagListOverflow);
+    }
+    if (MM != EAM_AL) {
+      __syncthreads();
+      const int nq = min(dq_n, kDeferCap);
+      for (int k = threadIdx.x; k < nq; k += blockDim.x) {
+        const unsigned q = dq[k];
+        const int i = (int)(q >> 16), j = (int)(q & 511u), zi = spc[i], zj = (int)((q >> 14) & 3u);
+        const double* pi = pos3 + 3 * i;
+        const double* pj = pos3 + 3 * j;
+        const double* sv = svt + 3 * ((q >> 9) & 31u);
+        const double vx = xadd(xsub(pj[0], pi[0]), sv[0]);
+        const double vy = xadd(xsub(pj[1], pi[1]), sv[1]);
+        const double vz = xadd(xsub(pj[2], pi[2]), sv[2]);
+        double r, rinv;
+        radial(xnorm2(vx, vy, vz), r, rinv);
+        const double on_i = eam_rho<MM>(zj, r);
+        const double on_j = zi == zj ? on_i : eam_rho<MM>(zi, r);
+        if (!(fabs(on_i) < 0.25 && fabs(on_j) < 0.25)) atomicOr(&blk_flags, kFlagListOverflow);
+        fixed_add(rho_acc + i, __double_as_longlong(fma(on_i, 0x1p53, kFixMagic)) - __double_as_longlong(kFixMagic));
+        fixed_add(rho_acc + j, __double_as_longlong(fma(on_j, 0x1p53, kFixMagic)) - __double_as_longlong(kFixMagic));
+      }
     }
     __syncthreads();
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
@@ -843,8 +884,7 @@ k_eam_small(SmallArgs a) {
           const double vx = xadd(xsub(pj[0], xi), sv[0]);
           const double vy = xadd(xsub(pj[1], yi), sv[1]);
           const double vz = xadd(xsub(pj[2], zi_), sv[2]);
-          const double d2 = xnorm2(vx, vy, vz);
-          if (!(d2 < rc2_phys)) continue;
+          const double d2 = xnorm2(vx, vy, vz);  // (d2 < rc2_phys: the density pass kept only those)
           double phi, w;
           eam_force_pair<MM>(zi, (int)(en >> 14), dfd_i, dfd[j], d2, phi, w);
           ep += phi;  // the whole pair energy: the partner does not see this pair
@@ -875,6 +915,29 @@ k_eam_small(SmallArgs a) {
         eatom[i] += ep;
       }
       if (range) atomicOr(&blk_flags, kFlagListOverflow);
+    }
+    if (MM != EAM_AL) {
+      const int nq = min(dq_n, kDeferCap);
+      for (int k = threadIdx.x; k < nq; k += blockDim.x) {
+        const unsigned q = dq[k];
+        const int i = (int)(q >> 16), j = (int)(q & 511u);
+        const double* pi = pos3 + 3 * i;
+        const double* pj = pos3 + 3 * j;
+        const double* sv = svt + 3 * ((q >> 9) & 31u);
+        const double vx = xadd(xsub(pj[0], pi[0]), sv[0]);
+        const double vy = xadd(xsub(pj[1], pi[1]), sv[1]);
+        const double vz = xadd(xsub(pj[2], pi[2]), sv[2]);
+        double phi, w;
+        eam_force_pair<MM>(spc[i], (int)((q >> 14) & 3u), dfd[i], dfd[j], xnorm2(vx, vy, vz), phi, w);
+        if (!(fabs(w) < 128.0 && fabs(phi) < 1024.0)) atomicOr(&blk_flags, kFlagListOverflow);
+        const double t[3] = {w * vx, w * vy, w * vz};
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          fixed_add(facc + 3 * i + c, __double_as_longlong(fma(t[c], 0x1p40, kFixMagic)) - __double_as_longlong(kFixMagic));
+          fixed_add(facc + 3 * j + c, __double_as_longlong(fma(-t[c], 0x1p40, kFixMagic)) - __double_as_longlong(kFixMagic));
+        }
+        fixed_add(&e_acc, __double_as_longlong(fma(phi, 0x1p40, kFixMagic)) - __double_as_longlong(kFixMagic));
+      }
     }
     __syncthreads();
     if (blk_flags & kFlagListOverflow) {
@@ -945,7 +1008,7 @@ k_eam_small(SmallArgs a) {
   for (int i = threadIdx.x; i < n; i += blockDim.x) e += eatom[i];  // atom order: reproducible
   const double bs = block_sum(e, sh32);
   if (threadIdx.x == 0) {
-    a.E[sys] = bs;
+    a.E[sys] = half ? bs + (double)e_acc * 0x1p-40 : bs;  // (+ the pair energies of the set-aside entries)
     RB_STAMP(9);
     if (a.single_n > 0) __threadfence_system();  // (only a polling host needs the order; a batch must not pay for it)
     RB_STAMP(10);
