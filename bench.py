@@ -458,7 +458,15 @@ def run_cuh2_batch(args, world, rank, local):
                 "peak_source": "DFMA microbenchmark measured in this run (MEASURED_PEAKS.json has no FP64 entry); "
                                "nominal = 148 SM x 64 FMA/clk x 2 x 1.965 GHz",
                 "flops_per_atom_eval": FLOPS_PER_ATOM["cuh2_batch"],
+                "convention": "algorithmic flops of SURVEY 8(d): a full-list gather (every pair evaluated from both "
+                              "ends, exp = 30 flops, candidate tests in FP64).  The kernel evaluates every pair ONCE "
+                              "(half lists, the partner's share through fixed-point atomics), tests candidates in FP32 "
+                              "and spends 10 FP64 instructions on an exp, so `frac` measures the path against a machine "
+                              "doing the reference's arithmetic at DFMA peak; frac_executed is the FP64 work actually "
+                              "issued (ncu) against the same peak",
                 "fp64_executed": executed,
+                "frac_executed": (executed["flops_per_atom_eval"] * n_atoms_global / world / kernel_s / 1e12 / fp64_peak)
+                if (executed and fp64_peak) else None,
                 "traffic": (lambda t: None if t is None else t * n_atoms_global / world)(
                     measured_traffic_per_atom("k_eam_small")),
                 "traffic_note": "DRAM read+write bytes of one k_eam_small launch, scaled per atom from the "

@@ -1233,7 +1233,7 @@ int launch_small(RgpotB200Pot* pot, size_t nsys, long nmax, const long long* d_o
   a.e_parts = e_parts;
   a.ticket = ticket;
   a.f_stage = f_stage;
-  a.half = pot->opt_half;
+  a.half = single_n > 0 ? 0 : pot->opt_half;  // (one system on one block is a latency case: the extra barriers of the half-list mode cost it a microsecond)
   if (host_box && uses_eam_small(pot->cfg.kind)) {  // one system: invert the cell here, not on one GPU thread
     const double rc = pot->cfg.kind == RGPOT_B200_FEHE ? 5.4 : eam_rcut(pot->cfg.kind);
     small_box_init(host_box, rc, a.sb);
