@@ -50,7 +50,7 @@ def _cu_block(n_cu, n_h, seed, box_pad=8.0):
 
 
 @pytest.mark.parametrize("n_cu,n_h", [(1, 0), (2, 0), (3, 1), (7, 2), (32, 0), (63, 2), (64, 2), (107, 6), (216, 2), (255, 0),
-                                      (256, 4), (300, 30)])
+                                      (256, 4), (300, 30), (490, 10), (512, 0)])
 def test_half_lists_match_the_oracle_and_the_full_lists(oracle, n_cu, n_h):
     pos, Z, box = _cu_block(n_cu, n_h, 5 + n_cu)
     e_o, f_o = oracle.cuh2_force(pos, Z, box)
