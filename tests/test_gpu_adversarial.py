@@ -155,7 +155,7 @@ def test_brick_eam_pairs_at_the_cutoff_in_a_sheared_cell(oracle, ulps):
 
 @pytest.mark.parametrize("cells,ulps", [(3, 0), (3, 2), (3, -2), (4, 1), (4, -1), (5, 0), (5, 8), (5, -8)])
 def test_batch_kernel_pairs_at_the_cutoff(oracle, cells, ulps):
-    """k_eam_small (FP32 search in fractional space): 60-degree cell, pairs on the cutoff, systems sized
+    """k_eam_small (FP32 search in fractional space, half lists in a batch, full lists for one system): 60-degree cell, pairs on the cutoff, systems sized
     for 4 / 2 / 1 lanes per atom; a batch of the system and of copies moved by whole cell vectors"""
     pos, Z, box = sheared_cu_with_boundary_pairs(cells, ulps, 40 + cells + ulps)
     if len(pos) > 500:
@@ -171,8 +171,16 @@ def test_batch_kernel_pairs_at_the_cutoff(oracle, cells, ulps):
         assert abs(e - er) <= 1e-10 * abs(er), (cells, ulps)
         assert_forces(f, fr, (cells, ulps))
     assert out[0][0] == out[2][0] and np.array_equal(out[0][1], out[2][1])
-    e1, f1, _ = pot(pos, Z, box)  # forced all-pairs path: the one-launch single-system call runs the same kernel
-    assert e1 == out[0][0] and np.array_equal(f1, out[0][1])
+    # forced all-pairs path: the one-launch single-system call runs the same kernel with full lists (a batch
+    # evaluates every pair once and hands the partner its share in fixed point: another summation order)
+    e1, f1, _ = pot(pos, Z, box)
+    assert abs(e1 - e_o) <= 1e-10 * abs(e_o), (cells, ulps)
+    assert_forces(f1, f_o, (cells, ulps))
+    assert np.abs(f1 - out[0][1]).max() <= 1e-10
+    pot.set_option("half", 0)
+    full = pot.forceBatch([(pos, Z, box)])
+    assert e1 == full[0][0] and np.array_equal(f1, full[0][1])  # full lists in both: the same bits
+    pot.set_option("half", 1)
     # the automatic single-system path (several blocks per system, single.cuh): other summation order
     auto = rgpot_b200.CuH2Pot()
     for p_, (er, fr) in ((pos, (e_o, f_o)), (moved, (e_m, f_m))):
