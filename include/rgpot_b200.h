@@ -226,7 +226,11 @@ RGPOT_B200_API long rgpot_b200_stat(RgpotB200Pot *pot, const char *key);
  *  "fine_min": atoms from which half-cutoff cells are used; "brick" (cells per brick, decimal
  *  xyz), "brick_tpa", "brick_threads", "brick_list", "brick_slack": brick-kernel tuning, 0 = automatic;
  *  "bricks": 0 = gather kernels only; "handoff": 0 = the EAM force pass repeats the candidate search instead of reusing the density
- *  pass's lists (default 1).                                                                */
+ *  pass's lists (default 1); "half": 0 = the batch kernel of the EAMs evaluates every pair from both ends (full lists) instead of
+ *  once with a fixed-point hand-over to the partner (default 1); "one": 0 = single EAM systems of 64..512 atoms use the batch
+ *  kernel (one block) instead of the many-block kernel; "tile": 1 = the tensor-core tile kernel for large LJ systems (default 0:
+ *  the brick kernel is faster); "batch_chunk": systems per pipeline chunk of the host-buffer batch entries (0 = automatic).
+ *  The handle-less Fortran drop-in entries below take their GPU from the environment variable RGPOT_B200_DEVICE (default 0). */
 RGPOT_B200_API int rgpot_b200_set_option(RgpotB200Pot *pot, const char *key, long value);
 
 /** Page-locked host memory for the batch entry points. */
