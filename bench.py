@@ -47,6 +47,7 @@ UNIT = "atom-evals/s"
 
 # algorithmic work per atom-eval (exp counted as 30 flops, FMA as 2)
 FLOPS_PER_ATOM = {"cuh2_batch": 23000.0, "lj_fluid_1m": 8503.0, "cuh2_slab_256k": 41200.0}
+FLOPS_PER_ATOM_HALF_LIST = 108.5 * 20 + 27.4 * (3 * 30 + 13 + 42 + 2 * 13) + 40  # = 6895 (batch of 218-atom slabs)
 BYTES_PER_ATOM = {"cuh2_batch": 76.0, "lj_fluid_1m": 52.0, "cuh2_slab_256k": 76.0}
 # nominal FP64 vector peak of a B200: 148 SMs x 64 FMA / clk x 2 flop x 1.965 GHz
 FP64_NOMINAL_TF = 148 * 64 * 2 * 1.965e9 / 1e12
@@ -469,6 +470,11 @@ def run_cuh2_batch(args, world, rank, local):
                               "and spends 10 FP64 instructions on an exp, so `frac` measures the path against a machine "
                               "doing the reference's arithmetic at DFMA peak; frac_executed is the FP64 work actually "
                               "issued (ncu) against the same peak",
+                # the same convention applied to what a half-list evaluation has to do: 108.5 owned candidates x 20
+                # + 27.4 owned pairs x (3 exp + 13 + 42 + 2 x 13) + 40 per atom
+                "flops_per_atom_eval_half_list": FLOPS_PER_ATOM_HALF_LIST,
+                "frac_half_list": (FLOPS_PER_ATOM_HALF_LIST * n_atoms_global / world / kernel_s / 1e12 / fp64_peak)
+                if fp64_peak else None,
                 "fp64_executed": executed,
                 "frac_executed": (executed["flops_per_atom_eval"] * n_atoms_global / world / kernel_s / 1e12 / fp64_peak)
                 if (executed and fp64_peak) else None,
