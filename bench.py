@@ -403,7 +403,7 @@ def run_cuh2_batch(args, world, rank, local):
         except OSError:
             pass
         ncpu_all = len(os.sched_getaffinity(0))
-        per_dev = max(1, min(12, ncpu_all // world))
+        per_dev = max(1, min(14, ncpu_all // world))
         multi = rgpot_b200.CuH2Pot(devices=list(range(world)), host_threads=per_dev) if world > 1 else \
             rgpot_b200.CuH2Pot(device=0, host_threads=per_dev)
         systems = [(pos[int(offsets[s]):int(offsets[s + 1])].copy(), Z[int(offsets[s]):int(offsets[s + 1])].copy(),

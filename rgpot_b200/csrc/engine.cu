@@ -448,7 +448,7 @@ struct DevGuard {
 // which those are, so the pinned staging they fill is local to the GPU's PCIe root)
 rb::Team* get_team(RgpotB200Pot* pot) {
   if (!pot->team) {
-    int want = pot->host_threads > 0 ? pot->host_threads : std::max(1, std::min(12, rb::usable_cpus()));
+    int want = pot->host_threads > 0 ? pot->host_threads : std::max(1, std::min(14, rb::usable_cpus()));
     cpu_set_t allowed, local;
     CPU_ZERO(&allowed);
     const bool place = sched_getaffinity(0, sizeof allowed, &allowed) == 0 &&
@@ -1666,7 +1666,7 @@ RgpotB200Pot* rgpot_b200_create(const RgpotB200Config* cfg, char* errbuf, size_t
     CPU_ZERO(&allowed);
     const bool have_mask = sched_getaffinity(0, sizeof allowed, &allowed) == 0;
     int per_dev = cfg->host_threads;
-    if (per_dev <= 0) per_dev = std::max(1, std::min(12, rb::usable_cpus() / (int)devs.size()));
+    if (per_dev <= 0) per_dev = std::max(1, std::min(14, rb::usable_cpus() / (int)devs.size()));
     pot->host_threads = per_dev;
     for (int d : devs) {
       RgpotB200Config c1 = *cfg;
