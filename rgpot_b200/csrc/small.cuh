@@ -404,7 +404,8 @@ k_eam_small(SmallArgs a) {
   // 2^-53 (terms < 0.25), forces 2^-40 eV/A (terms < 1024): the rounding, 1e-16 and 9e-13 absolute, is far inside
   // the 1e-10 / 1e-9 budget; a term outside those ranges (atoms almost on top of each other) sends the system to
   // the general path (kFlagListOverflow) like a full list does.
-  const bool half = !kFeHe && a.half != 0 && sb.fast != 0 && !sb.bad && a.emit.pairs == nullptr;
+  const bool half = !kFeHe && a.half != 0 && sb.fast != 0 && !sb.bad && a.emit.pairs == nullptr &&
+                    model_rc < 8.0;  // (the force range check below assumes |vec| < 8)
   long long* rho_acc = reinterpret_cast<long long*>(g3 + 2 * n);
   if (threadIdx.x < 27 && !sb.bad) {
     const int t = (int)threadIdx.x;
