@@ -30,31 +30,42 @@ struct SmallBox {
 };
 
 // vesin Matrix::determinant / inverse (:100-128) and face distances (:258-275)
+RB_HD double small_box_det(const double* m) {
+  return m[0] * (m[4] * m[8] - m[7] * m[5]) - m[1] * (m[3] * m[8] - m[5] * m[6]) + m[2] * (m[3] * m[7] - m[4] * m[6]);
+}
+// element k of the adjugate (the inverse is this over the determinant)
+RB_HD double small_box_cofactor(const double* m, int k) {
+  switch (k) {
+    case 0: return m[4] * m[8] - m[7] * m[5];
+    case 1: return m[2] * m[7] - m[1] * m[8];
+    case 2: return m[1] * m[5] - m[2] * m[4];
+    case 3: return m[5] * m[6] - m[3] * m[8];
+    case 4: return m[0] * m[8] - m[2] * m[6];
+    case 5: return m[3] * m[2] - m[0] * m[5];
+    case 6: return m[3] * m[7] - m[6] * m[4];
+    case 7: return m[6] * m[1] - m[0] * m[7];
+    default: return m[0] * m[4] - m[3] * m[1];
+  }
+}
+// rc / face distance k (+ margin); face distance k = 1 / |column k of Hinv| (equivalent to |n_k . H_k|, n_k the unit normal)
+RB_HD double small_box_q(const double* v, int k, double rc) {
+  const double cn = sqrt(v[k] * v[k] + v[3 + k] * v[3 + k] + v[6 + k] * v[6 + k]);
+  return rc * cn * (1.0 + 1e-9) + 1e-9;
+}
 RB_HD void small_box_init(const double* b, double rc, SmallBox& sb) {
   for (int k = 0; k < 9; ++k) sb.H[k] = b[k];
   const double* m = sb.H;
-  const double det = m[0] * (m[4] * m[8] - m[7] * m[5]) - m[1] * (m[3] * m[8] - m[5] * m[6]) +
-                     m[2] * (m[3] * m[7] - m[4] * m[6]);
+  const double det = small_box_det(m);
   sb.bad = !(fabs(det) >= 1e-30);
   if (sb.bad) {
     sb.fast = 0;
     return;
   }
   double* v = sb.Hinv;
-  v[0] = (m[4] * m[8] - m[7] * m[5]) / det;
-  v[1] = (m[2] * m[7] - m[1] * m[8]) / det;
-  v[2] = (m[1] * m[5] - m[2] * m[4]) / det;
-  v[3] = (m[5] * m[6] - m[3] * m[8]) / det;
-  v[4] = (m[0] * m[8] - m[2] * m[6]) / det;
-  v[5] = (m[3] * m[2] - m[0] * m[5]) / det;
-  v[6] = (m[3] * m[7] - m[6] * m[4]) / det;
-  v[7] = (m[6] * m[1] - m[0] * m[7]) / det;
-  v[8] = (m[0] * m[4] - m[3] * m[1]) / det;
-  // face distance k = 1 / |column k of Hinv|  (equivalent to |n_k . H_k| with n_k the unit normal)
+  for (int k = 0; k < 9; ++k) v[k] = small_box_cofactor(m, k) / det;
   sb.fast = 1;
   for (int k = 0; k < 3; ++k) {
-    const double cn = sqrt(v[k] * v[k] + v[3 + k] * v[3 + k] + v[6 + k] * v[6 + k]);
-    sb.q[k] = rc * cn * (1.0 + 1e-9) + 1e-9;
+    sb.q[k] = small_box_q(v, k, rc);
     if (!(sb.q[k] < 0.4999)) sb.fast = 0;
   }
 }
@@ -378,12 +389,37 @@ k_eam_small(SmallArgs a) {
     for (int t = threadIdx.x; t < 64; t += blockDim.x) tab[t] = g_exp2tab[t];
   }
   RB_STAMP(1);
-  if (threadIdx.x == 0) {
-    if (a.box_ready) {
-      sb = a.sb;  // one system: the host has inverted the cell (microseconds of FP64 divisions on one thread here)
-    } else {
-      small_box_init(a.boxes + 9 * (size_t)sys, model_rc, sb);
+  // this thread's first atom: the loads go out before the cell is inverted (the barriers below would otherwise
+  // sit between the two global-memory latencies)
+  const bool early = (int)threadIdx.x < n;
+  double ex = 0.0, ey = 0.0, ez = 0.0;
+  if (early) {
+    ex = a.pos[3 * (base + threadIdx.x)];
+    ey = a.pos[3 * (base + threadIdx.x) + 1];
+    ez = a.pos[3 * (base + threadIdx.x) + 2];
+  }
+  if (a.box_ready) {
+    if (threadIdx.x == 0) sb = a.sb;  // one system: the host has inverted the cell
+  } else {
+    // nine threads, one element of the inverse each (a thread alone spends ~3 us on the nine FP64 divisions and three
+    // square roots while the rest of the block waits), then three for the face distances
+    if (threadIdx.x < 9) {
+      const double* b = a.boxes + 9 * (size_t)sys;
+      double m[9];
+#pragma unroll
+      for (int k = 0; k < 9; ++k) m[k] = b[k];
+      const double det = small_box_det(m);
+      const bool bad = !(fabs(det) >= 1e-30);
+      sb.H[threadIdx.x] = m[threadIdx.x];
+      sb.Hinv[threadIdx.x] = bad ? 0.0 : small_box_cofactor(m, (int)threadIdx.x) / det;
+      if (threadIdx.x == 0) sb.bad = bad;
     }
+    __syncthreads();
+    if (threadIdx.x < 3) sb.q[threadIdx.x] = sb.bad ? 1.0 : small_box_q(sb.Hinv, (int)threadIdx.x, model_rc);
+    __syncthreads();
+    if (threadIdx.x == 0) sb.fast = !sb.bad && sb.q[0] < 0.4999 && sb.q[1] < 0.4999 && sb.q[2] < 0.4999;
+  }
+  if (threadIdx.x == 0) {
     blk_flags = sb.bad ? kFlagSingularBox : 0u;  // vesin: "the box matrix is not invertible"
     blk_bad[0] = INT_MAX;
     blk_bad[1] = 0;
@@ -418,7 +454,9 @@ k_eam_small(SmallArgs a) {
   RB_STAMP(2);
   // ---- phase A
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    const double x = a.pos[3 * (base + i)], y = a.pos[3 * (base + i) + 1], z = a.pos[3 * (base + i) + 2];
+    const bool first = i == (int)threadIdx.x;  // (loaded above)
+    const double x = first ? ex : a.pos[3 * (base + i)], y = first ? ey : a.pos[3 * (base + i) + 1],
+                 z = first ? ez : a.pos[3 * (base + i) + 2];
     pos3[3 * i] = x;
     pos3[3 * i + 1] = y;
     pos3[3 * i + 2] = z;
