@@ -334,6 +334,19 @@ RB_D void fixed_add(long long* acc, long long q) {
   atomicAdd(p + 1, hi + ((old + lo) < lo ? 1u : 0u));
 }
 
+// three accumulators at once (a force vector): the three returning adds go out back to back, so their latencies
+// overlap instead of each carry waiting for its own
+RB_D void fixed_add3(long long* acc, long long qx, long long qy, long long qz) {
+  unsigned* p = reinterpret_cast<unsigned*>(acc);
+  const unsigned lx = (unsigned)qx, ly = (unsigned)qy, lz = (unsigned)qz;
+  const unsigned ox = atomicAdd(p, lx);
+  const unsigned oy = atomicAdd(p + 2, ly);
+  const unsigned oz = atomicAdd(p + 4, lz);
+  atomicAdd(p + 1, (unsigned)((unsigned long long)qx >> 32) + ((ox + lx) < lx ? 1u : 0u));
+  atomicAdd(p + 3, (unsigned)((unsigned long long)qy >> 32) + ((oy + ly) < ly ? 1u : 0u));
+  atomicAdd(p + 5, (unsigned)((unsigned long long)qz >> 32) + ((oz + lz) < lz ? 1u : 0u));
+}
+
 template <int TPA, int M>
 __global__ void __launch_bounds__(448, 2)
 k_eam_small(SmallArgs a) {
@@ -932,10 +945,9 @@ k_eam_small(SmallArgs a) {
           fy += ty;
           fz += tz;
           range |= !(fabs(w) < 128.0);  // |v| <= rc < 8: every component term below 1024
-          long long* fj = facc + 3 * j;
-          fixed_add(fj, __double_as_longlong(fma(-tx, 0x1p40, kFixMagic)) - __double_as_longlong(kFixMagic));
-          fixed_add(fj + 1, __double_as_longlong(fma(-ty, 0x1p40, kFixMagic)) - __double_as_longlong(kFixMagic));
-          fixed_add(fj + 2, __double_as_longlong(fma(-tz, 0x1p40, kFixMagic)) - __double_as_longlong(kFixMagic));
+          fixed_add3(facc + 3 * j, __double_as_longlong(fma(-tx, 0x1p40, kFixMagic)) - __double_as_longlong(kFixMagic),
+                     __double_as_longlong(fma(-ty, 0x1p40, kFixMagic)) - __double_as_longlong(kFixMagic),
+                     __double_as_longlong(fma(-tz, 0x1p40, kFixMagic)) - __double_as_longlong(kFixMagic));
         }
       }
 #pragma unroll
@@ -947,10 +959,7 @@ k_eam_small(SmallArgs a) {
       }
       if (vi && sub == 0) {
         range |= !(fabs(fx) < 0x1p20 && fabs(fy) < 0x1p20 && fabs(fz) < 0x1p20);
-        long long* fi = facc + 3 * i;
-        fixed_add(fi, __double2ll_rn(fx * 0x1p40));
-        fixed_add(fi + 1, __double2ll_rn(fy * 0x1p40));
-        fixed_add(fi + 2, __double2ll_rn(fz * 0x1p40));
+        fixed_add3(facc + 3 * i, __double2ll_rn(fx * 0x1p40), __double2ll_rn(fy * 0x1p40), __double2ll_rn(fz * 0x1p40));
         eatom[i] += ep;
       }
       if (range) atomicOr(&blk_flags, kFlagListOverflow);
