@@ -1210,10 +1210,10 @@ int eam_small_maxnb(const RgpotB200Pot* pot, long nmax) {
   // two resident blocks per SM when possible, else the roomiest list that still fits one block
   const size_t per_sm = 227 * 1024;
   for (int maxnb : {160, 128, 96}) {
-    if (eam_small_smem(nmax, maxnb) + 6 * 1024 <= per_sm / 2 - 1024) return maxnb;
+    if (eam_small_smem(nmax, maxnb) + 10 * 1024 <= per_sm / 2 - 1024) return maxnb;  // (+ the kernel's static tables)
   }
   for (int maxnb : {160, 128, 96}) {
-    if (eam_small_smem(nmax, maxnb) + 6 * 1024 <= pot->smem_optin) return maxnb;
+    if (eam_small_smem(nmax, maxnb) + 10 * 1024 <= pot->smem_optin) return maxnb;
   }
   return 0;
 }

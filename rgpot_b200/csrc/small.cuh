@@ -368,6 +368,11 @@ k_eam_small(SmallArgs a) {
   __shared__ unsigned dq[kDeferCap];
   __shared__ int dq_n;
   __shared__ long long e_acc;
+  // half-list mode: every thread's list is split in two (even / odd entries); the 2 NTL half lists are sorted by
+  // length and a thread walks a long one and a short one, so that warps (and the lanes inside them) finish together
+  // -- the owned pairs per atom range from 8 to 38 in the 218-atom slab, and a barrier waits for the longest list
+  __shared__ unsigned short perm2[1024];  // half lists by decreasing length (half list v = 2 * column + parity)
+  __shared__ unsigned short vcnt[1024];   // entries of every half list that passed the exact test (density pass)
 
   const int sys = blockIdx.x;
   const long long base = a.single_n > 0 ? 0 : a.off[sys];
@@ -456,6 +461,7 @@ k_eam_small(SmallArgs a) {
   const bool half = !kFeHe && a.half != 0 && sb.fast != 0 && !sb.bad && a.emit.pairs == nullptr &&
                     model_rc < 8.0;  // (the force range check below assumes |vec| < 8)
   long long* rho_acc = reinterpret_cast<long long*>(g3 + 2 * n);
+  long long* e_fix = reinterpret_cast<long long*>(g3 + n);  // pair energies per atom, fixed point (g3[n, 2n): free outside Fe-He)
   if (threadIdx.x < 27 && !sb.bad) {
     const int t = (int)threadIdx.x;
     const double s0 = (double)(t % 3 - 1), s1 = (double)((t / 3) % 3 - 1), s2 = (double)(t / 9 - 1);
@@ -539,7 +545,10 @@ k_eam_small(SmallArgs a) {
     const bool ortho = sbf.ortho != 0;
     const unsigned lbase = (unsigned)__cvta_generic_to_shared(list), lstride = 2u * (unsigned)NTL;
     if (half) {  // (the FP64 fractional coordinates in g3 are not read again in this mode)
-      for (int t = threadIdx.x; t < n; t += blockDim.x) rho_acc[t] = 0;
+      for (int t = threadIdx.x; t < n; t += blockDim.x) {
+        rho_acc[t] = 0;
+        e_fix[t] = 0;
+      }
       for (int t = threadIdx.x; t < 3 * n; t += blockDim.x) facc[t] = 0;
     }
     for (int t = threadIdx.x; t < NTL; t += blockDim.x) {
@@ -713,7 +722,44 @@ k_eam_small(SmallArgs a) {
   // ---- phase C: order atoms by decreasing neighbor count (counting sort).  The order only decides
   // which lanes work on which atom; every per-atom result, and the energy sum below (taken in atom
   // order), is independent of it, so the integer atomics do not disturb reproducibility.
-  if (blockDim.x == 32) {
+  const int NL = 2 * NTL;  // half lists
+  if (half) {
+    // half lists by decreasing length (counting sort; ties in arrival order: every result below is an integer sum
+    // or a per-list sum in list order, so the order of equal lengths changes no bit)
+    for (int b = threadIdx.x; b < 256; b += blockDim.x) hist[b] = 0;
+    __syncthreads();
+    int my_rank[3] = {0, 0, 0};  // (NL <= 1024, >= 352 threads whenever NL > 704)
+    {
+      int k = 0;
+      for (int v = threadIdx.x; v < NL; v += blockDim.x, ++k) {
+        const int c = ((int)cnt16[v >> 1] + 1 - (v & 1)) >> 1;
+        vcnt[v] = (unsigned short)c;
+        my_rank[k] = atomicAdd(&hist[min(c, 255)], 1);
+      }
+    }
+    __syncthreads();
+    if (warp == 0) {  // exclusive scan over the bins, largest count first
+      int carry = 0;
+      for (int base = 255; base >= 0; base -= 32) {
+        const int b = base - lane;
+        const int v = hist[b];
+        int incl = v;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+          const int t = __shfl_up_sync(0xffffffffu, incl, off);
+          if (lane >= off) incl += t;
+        }
+        hist[b] = carry + incl - v;
+        carry += __shfl_sync(0xffffffffu, incl, 31);
+      }
+    }
+    __syncthreads();
+    {
+      int k = 0;
+      for (int v = threadIdx.x; v < NL; v += blockDim.x, ++k) perm2[hist[min((int)vcnt[v], 255)] + my_rank[k]] = (unsigned short)v;
+    }
+    __syncthreads();
+  } else if (blockDim.x == 32) {
     // one warp: the order cannot change which lanes wait for which (a handful of atoms, a single small system)
     for (int i = threadIdx.x; i < n; i += blockDim.x) perm[i] = i;
     __syncthreads();
@@ -762,22 +808,20 @@ k_eam_small(SmallArgs a) {
   constexpr int MM = kFeHe ? EAM_CUH2 : M;  // (the half-list branches are never taken for Fe-He)
   const double kFixMagic = 6755399441055744.0;  // 1.5 * 2^52: fma(v, scale, magic) holds rint(v * scale) in its low bits
   if (half) {
-    for (int ib = 0; ib < n; ib += ngrp) {
-      const int slot = ib + grp;
-      const bool vi = slot < n;
-      double rho = 0.0;
+    for (int u = threadIdx.x; u < NTL; u += blockDim.x) {
       bool coincident = false, range = false;
-      int i = 0;
-      if (vi) {
-        i = perm[slot];
-        const int c = cnt16[i * TPA + sub];
+#pragma unroll 1
+      for (int hl = 0; hl < 2; ++hl) {  // a long half list, then a short one
+        const int v = perm2[hl ? NL - 1 - u : u];
+        const int col = v >> 1, i = col / TPA, c = vcnt[v];
         const int zi = spc[i];
         const double xi = pos3[3 * i], yi = pos3[3 * i + 1], zi_ = pos3[3 * i + 2];
-        unsigned short* row = list + i * TPA + sub;
+        unsigned short* row = list + col + (v & 1) * NTL;  // entries v & 1, (v & 1) + 2, ... of the column
+        double rho = 0.0;
         int kept = 0;  // entries that pass the exact test are written back in place: the force pass walks only those
 #pragma unroll kSmallUnroll
         for (int s = 0; s < c; ++s) {
-          const unsigned en = row[s * NTL];
+          const unsigned en = row[2 * s * NTL];
           const int j = (int)(en & 511u);
           const double* pj = pos3 + 3 * j;
           const double* sv = svt + 3 * ((en >> 9) & 31u);
@@ -795,7 +839,7 @@ k_eam_small(SmallArgs a) {
               continue;
             }  // (queue full: the entry stays in the list and is evaluated in place)
           }
-          row[kept * NTL] = (unsigned short)en;  // (kept <= s: never ahead of the read cursor)
+          row[2 * kept * NTL] = (unsigned short)en;  // (kept <= s: never ahead of the read cursor)
           ++kept;
           double r, rinv;
           radial(d2, r, rinv);
@@ -806,15 +850,11 @@ k_eam_small(SmallArgs a) {
           const long long q = __double_as_longlong(fma(on_j, 0x1p53, kFixMagic)) - __double_as_longlong(kFixMagic);
           fixed_add(rho_acc + j, q);
         }
-        cnt16[i * TPA + sub] = (unsigned short)kept;  // (read again by this thread only)
-      }
-#pragma unroll
-      for (int off = TPA / 2; off > 0; off >>= 1) rho += __shfl_xor_sync(0xffffffffu, rho, off);
-      if (coincident) atomicOr(&blk_flags, kFlagCoincident);
-      if (vi && sub == 0) {
+        vcnt[v] = (unsigned short)kept;  // (the force pass gives this half list to the same thread)
         range |= !(fabs(rho) < 128.0);
         fixed_add(rho_acc + i, __double2ll_rn(rho * 0x1p53));
       }
+      if (coincident) atomicOr(&blk_flags, kFlagCoincident);
       if (range) atomicOr(&blk_flags, kFlagListOverflow);
     }
     if (MM != EAM_AL) {
@@ -914,22 +954,20 @@ k_eam_small(SmallArgs a) {
   RB_STAMP(6);
   // ---- phase E: pair energy and forces
   if (half) {
-    for (int ib = 0; ib < n; ib += ngrp) {
-      const int slot = ib + grp;
-      const bool vi = slot < n;
-      double fx = 0.0, fy = 0.0, fz = 0.0, ep = 0.0;
+    for (int u = threadIdx.x; u < NTL; u += blockDim.x) {
       bool range = false;
-      int i = 0;
-      if (vi) {
-        i = perm[slot];
-        const int c = cnt16[i * TPA + sub];
+#pragma unroll 1
+      for (int hl = 0; hl < 2; ++hl) {
+        const int v = perm2[hl ? NL - 1 - u : u];
+        const int col = v >> 1, i = col / TPA, c = vcnt[v];
         const int zi = spc[i];
         const double dfd_i = dfd[i];
         const double xi = pos3[3 * i], yi = pos3[3 * i + 1], zi_ = pos3[3 * i + 2];
-        const unsigned short* row = list + i * TPA + sub;
+        const unsigned short* row = list + col + (v & 1) * NTL;
+        double fx = 0.0, fy = 0.0, fz = 0.0, ep = 0.0;
 #pragma unroll kSmallUnroll
         for (int s = 0; s < c; ++s) {
-          const unsigned en = row[s * NTL];
+          const unsigned en = row[2 * s * NTL];
           const int j = (int)(en & 511u);
           const double* pj = pos3 + 3 * j;
           const double* sv = svt + 3 * ((en >> 9) & 31u);
@@ -949,18 +987,11 @@ k_eam_small(SmallArgs a) {
                      __double_as_longlong(fma(-ty, 0x1p40, kFixMagic)) - __double_as_longlong(kFixMagic),
                      __double_as_longlong(fma(-tz, 0x1p40, kFixMagic)) - __double_as_longlong(kFixMagic));
         }
-      }
-#pragma unroll
-      for (int off = TPA / 2; off > 0; off >>= 1) {
-        fx += __shfl_xor_sync(0xffffffffu, fx, off);
-        fy += __shfl_xor_sync(0xffffffffu, fy, off);
-        fz += __shfl_xor_sync(0xffffffffu, fz, off);
-        ep += __shfl_xor_sync(0xffffffffu, ep, off);
-      }
-      if (vi && sub == 0) {
-        range |= !(fabs(fx) < 0x1p20 && fabs(fy) < 0x1p20 && fabs(fz) < 0x1p20);
-        fixed_add3(facc + 3 * i, __double2ll_rn(fx * 0x1p40), __double2ll_rn(fy * 0x1p40), __double2ll_rn(fz * 0x1p40));
-        eatom[i] += ep;
+        if (c > 0) {
+          range |= !(fabs(fx) < 0x1p20 && fabs(fy) < 0x1p20 && fabs(fz) < 0x1p20 && fabs(ep) < 0x1p20);
+          fixed_add3(facc + 3 * i, __double2ll_rn(fx * 0x1p40), __double2ll_rn(fy * 0x1p40), __double2ll_rn(fz * 0x1p40));
+          fixed_add(e_fix + i, __double2ll_rn(ep * 0x1p40));
+        }
       }
       if (range) atomicOr(&blk_flags, kFlagListOverflow);
     }
@@ -1053,7 +1084,8 @@ k_eam_small(SmallArgs a) {
   RB_STAMP(7);
   __syncthreads();  // (also: every thread's force stores are ordered before thread 0's system fence below)
   RB_STAMP(8);
-  for (int i = threadIdx.x; i < n; i += blockDim.x) e += eatom[i];  // atom order: reproducible
+  for (int i = threadIdx.x; i < n; i += blockDim.x)  // atom order: reproducible
+    e += half ? eatom[i] + (double)e_fix[i] * 0x1p-40 : eatom[i];
   const double bs = block_sum(e, sh32);
   if (threadIdx.x == 0) {
     a.E[sys] = half ? bs + (double)e_acc * 0x1p-40 : bs;  // (+ the pair energies of the set-aside entries)
