@@ -621,10 +621,11 @@ k_eam_small(SmallArgs a) {
       const int c = (int)(((float)(la - la0) + 0.5f) / (float)lstride);
       // second sweep: image index S' = -rint(g_j - g_i) (the search's choice, recomputed the same
       // way) plus the atoms' own wrap counts, and the species of j
+      // (half-list mode: the density pass does this on the fly -- its lists are balanced, these are not)
       const int ai = ash[i];
       bool far_image = false;
       unsigned short* row = list + t;
-      for (int k = 0; k < c; ++k) {
+      for (int k = 0; k < (half ? 0 : c); ++k) {
         const int j = row[k * NTL];
         const float4 gj = g32[j];
         int S0 = -(int)rintf(gj.x - gi.x), S1 = -(int)rintf(gj.y - gi.y), S2 = -(int)rintf(gj.z - gi.z);
@@ -816,15 +817,29 @@ k_eam_small(SmallArgs a) {
         const int col = v >> 1, i = col / TPA, c = vcnt[v];
         const int zi = spc[i];
         const double xi = pos3[3 * i], yi = pos3[3 * i + 1], zi_ = pos3[3 * i + 2];
+        const float4 gi = g32[i];
+        const int ai = ash[i];
         unsigned short* row = list + col + (v & 1) * NTL;  // entries v & 1, (v & 1) + 2, ... of the column
         double rho = 0.0;
         int kept = 0;  // entries that pass the exact test are written back in place: the force pass walks only those
 #pragma unroll kSmallUnroll
         for (int s = 0; s < c; ++s) {
-          const unsigned en = row[2 * s * NTL];
-          const int j = (int)(en & 511u);
+          // the search left the partner's index; image index S' = -rint(g_j - g_i) (the search's choice, recomputed
+          // the same way) plus the atoms' own wrap counts, and the species of j, make the entry
+          const int j = row[2 * s * NTL];
+          const float4 gj = g32[j];
+          int S0 = -(int)rintf(gj.x - gi.x), S1 = -(int)rintf(gj.y - gi.y), S2 = -(int)rintf(gj.z - gi.z);
+          if (wrapped_atoms) {
+            const int aj = ash[j];
+            S0 += (ai & 1023) - (aj & 1023);
+            S1 += ((ai >> 10) & 1023) - ((aj >> 10) & 1023);
+            S2 += ((ai >> 20) & 1023) - ((aj >> 20) & 1023);
+            if (abs(S0) > 1 || abs(S1) > 1 || abs(S2) > 1) range = true;  // a far image: the general path's case
+          }
+          const unsigned tidx = (unsigned)((S0 + 1) + 3 * (S1 + 1) + 9 * (S2 + 1)) & 31u;
+          const unsigned en = (unsigned)j | (tidx << 9) | ((unsigned)spc[j] << 14);
           const double* pj = pos3 + 3 * j;
-          const double* sv = svt + 3 * ((en >> 9) & 31u);
+          const double* sv = svt + 3 * tidx;
           const double vx = xadd(xsub(pj[0], xi), sv[0]);
           const double vy = xadd(xsub(pj[1], yi), sv[1]);
           const double vz = xadd(xsub(pj[2], zi_), sv[2]);
