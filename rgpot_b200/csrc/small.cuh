@@ -727,7 +727,7 @@ k_eam_small(SmallArgs a) {
   if (half) {
     // half lists by decreasing length (counting sort; ties in arrival order: every result below is an integer sum
     // or a per-list sum in list order, so the order of equal lengths changes no bit)
-    for (int b = threadIdx.x; b < 256; b += blockDim.x) hist[b] = 0;
+    for (int b = threadIdx.x; b < 64; b += blockDim.x) hist[b] = 0;  // (64 bins: a half list holds a dozen entries; longer ones share the last bin)
     __syncthreads();
     int my_rank[3] = {0, 0, 0};  // (NL <= 1024, >= 352 threads whenever NL > 704)
     {
@@ -735,13 +735,13 @@ k_eam_small(SmallArgs a) {
       for (int v = threadIdx.x; v < NL; v += blockDim.x, ++k) {
         const int c = ((int)cnt16[v >> 1] + 1 - (v & 1)) >> 1;
         vcnt[v] = (unsigned short)c;
-        my_rank[k] = atomicAdd(&hist[min(c, 255)], 1);
+        my_rank[k] = atomicAdd(&hist[min(c, 63)], 1);
       }
     }
     __syncthreads();
     if (warp == 0) {  // exclusive scan over the bins, largest count first
       int carry = 0;
-      for (int base = 255; base >= 0; base -= 32) {
+      for (int base = 63; base >= 0; base -= 32) {
         const int b = base - lane;
         const int v = hist[b];
         int incl = v;
@@ -757,7 +757,7 @@ k_eam_small(SmallArgs a) {
     __syncthreads();
     {
       int k = 0;
-      for (int v = threadIdx.x; v < NL; v += blockDim.x, ++k) perm2[hist[min((int)vcnt[v], 255)] + my_rank[k]] = (unsigned short)v;
+      for (int v = threadIdx.x; v < NL; v += blockDim.x, ++k) perm2[hist[min((int)vcnt[v], 63)] + my_rank[k]] = (unsigned short)v;
     }
     __syncthreads();
   } else if (blockDim.x == 32) {
