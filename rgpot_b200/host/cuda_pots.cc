@@ -126,11 +126,19 @@ void Engine::force(const char *label, const ForceInput &in, ForceOut *out) const
 void Engine::forceBatch(const char *label, const ForceBatch &batch) const {
   const size_t n = batch.nSystems;
   if (n == 0) return;
-  std::vector<size_t> natoms(n);
-  std::vector<const double *> pos(n), box(n);
-  std::vector<const int *> z(n);
-  std::vector<double *> frc(n);
-  std::vector<double> energy(n);
+  // per-thread scratch, kept between calls: a 65 536-image batch would otherwise allocate (and fault in) 3 MB of
+  // pointer tables on every call
+  thread_local std::vector<size_t> natoms;
+  thread_local std::vector<const double *> pos, box;
+  thread_local std::vector<const int *> z;
+  thread_local std::vector<double *> frc;
+  thread_local std::vector<double> energy;
+  natoms.resize(n);
+  pos.resize(n);
+  box.resize(n);
+  z.resize(n);
+  frc.resize(n);
+  energy.resize(n);
   for (size_t i = 0; i < n; ++i) {
     natoms[i] = batch.in[i].nAtoms;
     pos[i] = batch.in[i].pos;
